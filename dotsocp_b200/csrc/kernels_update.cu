@@ -1,0 +1,887 @@
+// kernels_update.cu -- the per-iteration stencil / projection / multiplier kernels of the DOT-SOCP loop (sm_100a).
+//
+// Compiled with -fmad=false: every product and sum below is a separately rounded IEEE double operation in the
+// same order as the reference's scalar SSE2 MEX kernels and MATLAB expressions, so the cell-local arithmetic is
+// bit-identical to the CPU path (only the DCT-based Poisson solve differs in rounding).
+//
+// Data layout (MATLAB column-major == C order (t,x,y), y fastest):
+//   q/alpha/weight/q2 : [q0 (nt-1,nx,ny) | bx (nt,nx-1,ny) | by (nt,nx,ny-1)]
+//   beta/z            : 10 planes of L = (nt-1)*nx*ny doubles (structure of arrays)
+// All kernels are HBM-bound streaming kernels: warps run along y (coalesced), k_mult marches along t.
+#include "kernels.h"
+#include <cstring>
+
+namespace dsocp {
+
+__device__ __forceinline__ double inv_sqrt2_literal() { return __longlong_as_double((long long)DSOCP_INV_SQRT2_BITS); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Projection onto the second-order cone {(t,x): |x| <= t}, column 0 = t.          mexProjSoc.mexa64 @0x1170, @0x1440
+// Row-norm association order = Eigen's 2-row packet loop (4-way unrolled):
+//    acc = s1 + ((s5+s4)+(s3+s2)) ; acc += ((s9+s8)+(s7+s6))         (s_j = v_j^2)
+// ONE_D: the row has 6 columns (c0..c4 and c5 stored in slot 9; slots 5..8 are structural zeros):
+//    acc = s1 + ((s9+s4)+(s3+s2))
+// r = (v0/nrm + 1)*0.5 ; r>1 -> identity ; 0>r -> 0 ; else scale by r (t = r*nrm unless r == 1).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool ONE_D>
+__device__ __forceinline__ void proj_soc(double (&v)[10])
+{
+    const double s1 = dmul(v[1], v[1]), s2 = dmul(v[2], v[2]), s3 = dmul(v[3], v[3]), s4 = dmul(v[4], v[4]);
+    const double s9 = dmul(v[9], v[9]);
+    double acc;
+    if (ONE_D) {
+        acc = dadd(s1, dadd(dadd(s9, s4), dadd(s3, s2)));
+    } else {
+        const double s5 = dmul(v[5], v[5]), s6 = dmul(v[6], v[6]), s7 = dmul(v[7], v[7]), s8 = dmul(v[8], v[8]);
+        acc = dadd(s1, dadd(dadd(s5, s4), dadd(s3, s2)));
+        acc = dadd(acc, dadd(dadd(s9, s8), dadd(s7, s6)));
+    }
+    const double nrm = sqrt(acc);
+    const double r = dmul(dadd(v[0] / nrm, 1.0), 0.5);
+    double coef;
+    bool keep;
+    if (r > 1.0) {
+        coef = 1.0;
+        keep = true;
+    } else if (0.0 > r) {
+        coef = 0.0;
+        keep = false;
+    } else {
+        coef = r;
+        keep = (r == 1.0);
+    }
+#pragma unroll
+    for (int j = 1; j < 10; j++) v[j] = dmul(v[j], coef);
+    v[0] = keep ? v[0] : dmul(coef, nrm);
+}
+
+// z2 = d + s BF q of one cell from the 9 staggered values that touch it.        mexBFd.mexa64 @0x1120/@0x11a0/@0x1310
+// Out-of-domain neighbours give the structural zeros the reference never writes.
+struct CellQ {
+    double q0;
+    double bxm, bx, bxm1, bx1;   // bx[t,x-1], bx[t,x], bx[t+1,x-1], bx[t+1,x]
+    double bym, by, bym1, by1;   // by[t,y-1], by[t,y], by[t+1,y-1], by[t+1,y]
+};
+__device__ __forceinline__ void cell_z2(const CellQ& c, const IterScal& sc, bool hxm, bool hxp, bool hym, bool hyp,
+                                        double (&z2)[10])
+{
+    const double p = dmul(c.q0, sc.S);
+    z2[0] = dsub(sc.DF, p);
+    z2[9] = dadd(p, sc.DF);
+    z2[1] = hxm ? dmul(c.bxm, sc.SF) : 0.0;
+    z2[2] = hxp ? dmul(c.bx, sc.SF) : 0.0;
+    z2[3] = hxm ? dmul(c.bxm1, sc.SF) : 0.0;
+    z2[4] = hxp ? dmul(c.bx1, sc.SF) : 0.0;
+    z2[5] = hym ? dmul(c.bym, sc.SF) : 0.0;
+    z2[6] = hyp ? dmul(c.by, sc.SF) : 0.0;
+    z2[7] = hym ? dmul(c.bym1, sc.SF) : 0.0;
+    z2[8] = hyp ? dmul(c.by1, sc.SF) : 0.0;
+}
+
+// z of a cell: either materialised (zmat != NULL: PALM / acc-ADMM keep z as state) or recomputed from the inputs
+// of the z-step that produced it, z = Pi_Q(d + BF q_old - beta_old) (inPALM never stores z).
+template <bool ONE_D>
+__device__ __forceinline__ void load_z(const Geo& g, const IterScal& sc, const double* __restrict__ zmat,
+                                       const double* __restrict__ q_old, const double* __restrict__ beta_old, int t, int x,
+                                       int y, double (&z)[10])
+{
+    const i64 L = g.L, c = (i64)t * g.P + (i64)x * g.ny + y;
+    if (zmat != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 10; j++) z[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0 : zmat[(i64)j * L + c];
+        return;
+    }
+    const bool hxm = x > 0, hxp = x < g.nx - 1, hym = y > 0, hyp = y < g.ny - 1;
+    const double* bx = q_old + L;
+    const double* by = bx + g.NBX;
+    const i64 ox = (i64)t * g.PBX + (i64)x * g.ny + y, oy = (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
+    CellQ cq;
+    cq.q0 = q_old[c];
+    cq.bxm = hxm ? bx[ox - g.ny] : 0.0;
+    cq.bx = hxp ? bx[ox] : 0.0;
+    cq.bxm1 = hxm ? bx[ox + g.PBX - g.ny] : 0.0;
+    cq.bx1 = hxp ? bx[ox + g.PBX] : 0.0;
+    cq.bym = hym ? by[oy - 1] : 0.0;
+    cq.by = hyp ? by[oy] : 0.0;
+    cq.bym1 = hym ? by[oy + g.PBY - 1] : 0.0;
+    cq.by1 = hyp ? by[oy + g.PBY] : 0.0;
+    cell_z2(cq, sc, hxm, hxp, hym, hyp, z);
+#pragma unroll
+    for (int j = 0; j < 10; j++) z[j] = dsub(z[j], (ONE_D && j >= 5 && j <= 8) ? 0.0 : beta_old[(i64)j * L + c]);
+    proj_soc<ONE_D>(z);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Standalone mexBFd: one thread per cell, boundary entries NOT written (reference semantics).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bfd(Geo g, double S, double SF, double DF, const double* __restrict__ q,
+                                             double* __restrict__ z)
+{
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (p >= g.P) return;
+    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    const i64 c = (i64)t * g.P + p;
+    const double* bx = q + g.L;
+    const double* by = bx + g.NBX;
+    const double pr = dmul(q[c], S);
+    z[c] = dsub(DF, pr);
+    z[9 * g.L + c] = dadd(pr, DF);
+    if (x >= 1) {
+        z[1 * g.L + c] = dmul(bx[(i64)t * g.PBX + (i64)(x - 1) * g.ny + y], SF);
+        z[3 * g.L + c] = dmul(bx[(i64)(t + 1) * g.PBX + (i64)(x - 1) * g.ny + y], SF);
+    }
+    if (x <= g.nx - 2) {
+        z[2 * g.L + c] = dmul(bx[(i64)t * g.PBX + (i64)x * g.ny + y], SF);
+        z[4 * g.L + c] = dmul(bx[(i64)(t + 1) * g.PBX + (i64)x * g.ny + y], SF);
+    }
+    if (y >= 1) {
+        z[5 * g.L + c] = dmul(by[(i64)t * g.PBY + (i64)x * (g.ny - 1) + (y - 1)], SF);
+        z[7 * g.L + c] = dmul(by[(i64)(t + 1) * g.PBY + (i64)x * (g.ny - 1) + (y - 1)], SF);
+    }
+    if (y <= g.ny - 2) {
+        z[6 * g.L + c] = dmul(by[(i64)t * g.PBY + (i64)x * (g.ny - 1) + y], SF);
+        z[8 * g.L + c] = dmul(by[(i64)(t + 1) * g.PBY + (i64)x * (g.ny - 1) + y], SF);
+    }
+}
+
+static double host_sf(double S)
+{
+    uint64_t b = DSOCP_INV_SQRT2_BITS;
+    double d;
+    memcpy(&d, &b, 8);
+    return d * S;
+}
+
+void launch_bfd(const Geo& g, double S, double DF, const double* q, double* z, cudaStream_t st)
+{
+    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)(g.nt - 1));
+    k_bfd<<<grid, 256, 0, st>>>(g, S, host_sf(S), DF, q, z);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Standalone mexBFdConj: one thread per node; q0, bx, by entries owned by the node.   mexBFdConj.mexa64 @0x1120/1160/1310
+// add order ((z1[t,x+1] + z2[t,x]) + z3[t-1,x+1]) + z4[t-1,x]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bfdconj(Geo g, double S, double SF, const double* __restrict__ z,
+                                                 double* __restrict__ q2)
+{
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (p >= g.P) return;
+    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    const i64 L = g.L;
+    const i64 cu = (i64)t * g.P + p;         // cell (t,x,y)
+    const i64 cd = cu - g.P;                 // cell (t-1,x,y)
+    const bool up = t < g.nt - 1, dn = t > 0;
+    if (up) q2[cu] = dmul(dsub(z[9 * L + cu], z[cu]), S);
+    if (x < g.nx - 1) {
+        double s;
+        if (!dn)
+            s = dadd(z[1 * L + cu + g.ny], z[2 * L + cu]);
+        else if (!up)
+            s = dadd(z[3 * L + cd + g.ny], z[4 * L + cd]);
+        else {
+            s = dadd(z[1 * L + cu + g.ny], z[2 * L + cu]);
+            s = dadd(s, z[3 * L + cd + g.ny]);
+            s = dadd(s, z[4 * L + cd]);
+        }
+        q2[L + (i64)t * g.PBX + (i64)x * g.ny + y] = dmul(s, SF);
+    }
+    if (y < g.ny - 1) {
+        double s;
+        if (!dn)
+            s = dadd(z[5 * L + cu + 1], z[6 * L + cu]);
+        else if (!up)
+            s = dadd(z[7 * L + cd + 1], z[8 * L + cd]);
+        else {
+            s = dadd(z[5 * L + cu + 1], z[6 * L + cu]);
+            s = dadd(s, z[7 * L + cd + 1]);
+            s = dadd(s, z[8 * L + cd]);
+        }
+        q2[L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y] = dmul(s, SF);
+    }
+}
+
+void launch_bfdconj(const Geo& g, double S, const double* z, double* q2, cudaStream_t st)
+{
+    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)g.nt);
+    k_bfdconj<<<grid, 256, 0, st>>>(g, S, host_sf(S), z, q2);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Standalone mexProjSoc for an arbitrary M x N column-major matrix (generic column count; the fused kernels use the
+// unrolled proj_soc<> above).  Reproduces Eigen's packet order for paired rows and the sequential order of the
+// odd tail row (mexProjSoc.mexa64 @0x1530 / @0x1668).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_projsoc(i64 M, int N, const double* __restrict__ in, double* __restrict__ out)
+{
+    const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int n = N - 1;
+    double nrm = 0.0;
+    if (n > 0) {
+        const bool packet = i < (M & ~(i64)1);
+        double v = in[1 * M + i];
+        double acc = dmul(v, v);
+        int k = 1;
+        if (packet) {
+            const int kend = (n - 1) & ~3;
+            if (kend > 1) {
+                for (; k < kend; k += 4) {
+                    const double a0 = in[(i64)(k + 1) * M + i], a1 = in[(i64)(k + 2) * M + i];
+                    const double a2 = in[(i64)(k + 3) * M + i], a3 = in[(i64)(k + 4) * M + i];
+                    const double hi = dadd(dmul(a3, a3), dmul(a2, a2));
+                    const double lo = dadd(dmul(a1, a1), dmul(a0, a0));
+                    acc = dadd(acc, dadd(hi, lo));
+                }
+            }
+        }
+        for (; k < n; k++) {
+            const double a = in[(i64)(k + 1) * M + i];
+            acc = dadd(acc, dmul(a, a));
+        }
+        nrm = sqrt(acc);
+    }
+    const double v0 = in[i];
+    const double r = dmul(dadd(v0 / nrm, 1.0), 0.5);
+    double coef;
+    bool keep;
+    if (r > 1.0) {
+        coef = 1.0;
+        keep = true;
+    } else if (0.0 > r) {
+        coef = 0.0;
+        keep = false;
+    } else {
+        coef = r;
+        keep = (r == 1.0);
+    }
+    for (int j = 1; j < N; j++) out[(i64)j * M + i] = dmul(in[(i64)j * M + i], coef);
+    out[i] = keep ? v0 : dmul(coef, nrm);
+}
+
+void launch_projsoc(i64 M, int N, const double* in, double* out, cudaStream_t st)
+{
+    if (M <= 0) return;
+    k_projsoc<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(M, N, in, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// q-step + alpha-step, one thread per node (t,x,y); the node owns q0[t,x,y], bx[t,x,y], by[t,x,y].
+//   tmp_q = A*phi (CSR row: (-g)*phi_i + g*phi_{i+1})                                   solver_socp_inPALM.m:204
+//   q     = ((tmp_q + alpha) + q2) .* diagQInv          | weighted: (w.*(tmp_q+alpha) + q2) .* diagQInv   :206 / wsocp :212
+//   alpha = alpha + tau*(tmp_q - w.*q)                  | acc-ADMM: (alpha + tmp_q) - w.*q                :211,214 / accADMM :237
+// ---------------------------------------------------------------------------------------------------------------
+template <bool WEIGHTED, bool ACC>
+__device__ __forceinline__ void q_update(i64 e, double aphi, double dinv_plain, double s2term, const IterScal& sc,
+                                         const double* __restrict__ q2, const double* __restrict__ weight,
+                                         double* __restrict__ alpha, double* __restrict__ qout)
+{
+    const double a = alpha[e];
+    const double q2v = q2[e];
+    double qn, wq;
+    if (WEIGHTED) {
+        const double w = weight[e];
+        const double dinv = 1.0 / dadd(s2term, dmul(w, w));
+        qn = dmul(dadd(dmul(w, dadd(aphi, a)), q2v), dinv);
+        wq = dmul(w, qn);
+    } else {
+        qn = dmul(dadd(dadd(aphi, a), q2v), dinv_plain);
+        wq = qn;
+    }
+    qout[e] = qn;
+    if (ACC)
+        alpha[e] = dsub(dadd(a, aphi), wq);
+    else
+        alpha[e] = dadd(a, dmul(sc.tau, dsub(aphi, wq)));
+}
+
+template <bool WEIGHTED, bool ACC>
+__global__ void __launch_bounds__(256) k_qstep(Geo g, IterScal sc, const double* __restrict__ phi,
+                                               const double* __restrict__ q2, const double* __restrict__ weight,
+                                               double* __restrict__ alpha, double* __restrict__ qout)
+{
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (p >= g.P) return;
+    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    const i64 n = (i64)t * g.P + p;
+    const double ph = phi[n];
+    const bool edge_t = (t == 0) || (t == g.nt - 1);
+    if (t < g.nt - 1) {
+        const double aphi = dadd(dmul(-sc.gt, ph), dmul(sc.gt, phi[n + g.P]));
+        q_update<WEIGHTED, ACC>(n, aphi, sc.dinv1, sc.s2x2, sc, q2, weight, alpha, qout);
+    }
+    if (x < g.nx - 1) {
+        const double aphi = dadd(dmul(-sc.gx, ph), dmul(sc.gx, phi[n + g.ny]));
+        q_update<WEIGHTED, ACC>(g.L + (i64)t * g.PBX + (i64)x * g.ny + y, aphi, edge_t ? sc.dinv2 : sc.dinv1,
+                                edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout);
+    }
+    if (y < g.ny - 1) {
+        const double aphi = dadd(dmul(-sc.gy, ph), dmul(sc.gy, phi[n + 1]));
+        q_update<WEIGHTED, ACC>(g.L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y, aphi,
+                                edge_t ? sc.dinv2 : sc.dinv1, edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout);
+    }
+}
+
+void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st)
+{
+    dim3 grid((unsigned)((a.g.P + 255) / 256), (unsigned)a.g.nt);
+#define QS(W, A) k_qstep<W, A><<<grid, 256, 0, st>>>(a.g, a.sc, a.phi, a.q2, a.weight, a.alpha, a.q_new)
+    if (weighted) {
+        if (acc) QS(true, true); else QS(true, false);
+    } else {
+        if (acc) QS(false, true); else QS(false, false);
+    }
+#undef QS
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_mult: fused z-step + beta-step of iteration i, then the z-step inputs of iteration i+1.
+//
+// Each CTA owns a (TX-1) x (TY-1) tile of (x,y) columns (+1 halo row/column on the high side, recomputed) and
+// marches along t.  Per cell and step:
+//     z2o = d + BF q_old ; z = Pi_Q(z2o - beta)                   (mexBFd + mexProjSoc,   solver_socp_inPALM.m:199)
+//     z2n = d + BF q_new ; beta += tau (z - z2n)                  (mexBFd,                :212-215)
+//     w   = Pi_Q(z2n - beta) + beta                                (next iteration's z + beta, :199,:205)
+//     q2  = s (BF)^* w                                             (mexBFdConj,            :205)  -> consumed by k_qstep
+//     rhs = A'(w.*q_new - alpha) + c                               (next Poisson rhs,      :194)
+// so beta (the 10L array that dominates the traffic) is read once and written once per iteration and z, z2, q2's
+// 10-column temporaries never touch HBM.  The x+1 / y+1 neighbours' w (columns 1,3 / 5,7) come through shared
+// memory; the t-1 layer's columns 3,4,7,8 are carried in registers.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool WEIGHTED>
+__device__ __forceinline__ double uval(double q, double a, double w)
+{
+    return WEIGHTED ? dsub(dmul(w, q), a) : dsub(q, a);
+}
+
+template <int TX, int TY, bool WEIGHTED, bool ONE_D, bool UPDATE>
+__global__ void __launch_bounds__(TX* TY) k_mult(Geo g, IterScal sc, const double* __restrict__ qo,
+                                                 const double* __restrict__ qn, const double* __restrict__ alpha,
+                                                 const double* __restrict__ weight, const double* __restrict__ beta,
+                                                 double* __restrict__ beta_out, double* __restrict__ q2,
+                                                 double* __restrict__ rhs, const double* __restrict__ c0,
+                                                 const double* __restrict__ c1)
+{
+    __shared__ double sh[2][4][TX][TY];
+    const int ly = threadIdx.x, lx = threadIdx.y;
+    const int x = blockIdx.x * (TX - 1) + lx, y = blockIdx.y * (TY - 1) + ly;
+    const bool valid = (x < g.nx) && (y < g.ny);
+    const bool owner = valid && (lx < TX - 1) && (ly < TY - 1);
+    const bool hxm = valid && x > 0, hxp = valid && x < g.nx - 1, hym = valid && y > 0, hyp = valid && y < g.ny - 1;
+    const i64 L = g.L;
+    const i64 node = (i64)x * g.ny + y;
+    const i64 ibx = (i64)x * g.ny + y, ibxm = ibx - g.ny;
+    const i64 iby = (i64)x * (g.ny - 1) + y, ibym = iby - 1;
+    const double* __restrict__ qo_bx = qo + L;
+    const double* __restrict__ qo_by = qo_bx + g.NBX;
+    const double* __restrict__ qn_bx = qn + L;
+    const double* __restrict__ qn_by = qn_bx + g.NBX;
+    const double* __restrict__ al_bx = alpha + L;
+    const double* __restrict__ al_by = al_bx + g.NBX;
+    const double* __restrict__ w_bx = WEIGHTED ? weight + L : nullptr;
+    const double* __restrict__ w_by = WEIGHTED ? w_bx + g.NBX : nullptr;
+    double* __restrict__ q2_bx = q2 + L;
+    double* __restrict__ q2_by = q2_bx + g.NBX;
+
+    // staggered q at node level t (carried) -- old and new iterate
+    CellQ co, cn;
+    co.q0 = cn.q0 = 0.0;
+    co.bxm = co.bx = co.bym = co.by = co.bxm1 = co.bx1 = co.bym1 = co.by1 = 0.0;
+    cn = co;
+    if (UPDATE) {
+        if (hxm) co.bxm = qo_bx[ibxm];
+        if (hxp) co.bx = qo_bx[ibx];
+        if (hym) co.bym = qo_by[ibym];
+        if (hyp) co.by = qo_by[iby];
+    }
+    if (hxm) cn.bxm = qn_bx[ibxm];
+    if (hxp) cn.bx = qn_bx[ibx];
+    if (hym) cn.bym = qn_by[ibym];
+    if (hyp) cn.by = qn_by[iby];
+
+    double wp3n = 0.0, wp4 = 0.0, wp7n = 0.0, wp8 = 0.0, u0p = 0.0;
+
+    for (int t = 0; t < g.nt; t++) {
+        const int buf = t & 1;
+        const bool cell = t < g.nt - 1;
+        const i64 cidx = (i64)t * g.P + node;
+        double w[10];
+        double a0 = 0.0, wt0 = 1.0;
+#pragma unroll
+        for (int j = 0; j < 10; j++) w[j] = 0.0;
+        if (cell && valid) {
+            double b[10];
+#pragma unroll
+            for (int j = 0; j < 10; j++) b[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0 : beta[(i64)j * L + cidx];
+            cn.q0 = qn[cidx];
+            const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
+            cn.bxm1 = hxm ? qn_bx[o1x + ibxm] : 0.0;
+            cn.bx1 = hxp ? qn_bx[o1x + ibx] : 0.0;
+            cn.bym1 = hym ? qn_by[o1y + ibym] : 0.0;
+            cn.by1 = hyp ? qn_by[o1y + iby] : 0.0;
+            double z2n[10];
+            cell_z2(cn, sc, hxm, hxp, hym, hyp, z2n);
+            if (UPDATE) {
+                co.q0 = qo[cidx];
+                co.bxm1 = hxm ? qo_bx[o1x + ibxm] : 0.0;
+                co.bx1 = hxp ? qo_bx[o1x + ibx] : 0.0;
+                co.bym1 = hym ? qo_by[o1y + ibym] : 0.0;
+                co.by1 = hyp ? qo_by[o1y + iby] : 0.0;
+                double v[10];
+                cell_z2(co, sc, hxm, hxp, hym, hyp, v);
+#pragma unroll
+                for (int j = 0; j < 10; j++) v[j] = dsub(v[j], b[j]);
+                proj_soc<ONE_D>(v);  // v = z
+#pragma unroll
+                for (int j = 0; j < 10; j++) {
+                    b[j] = dadd(b[j], dmul(sc.tau, dsub(v[j], z2n[j])));
+                    if (owner && !(ONE_D && j >= 5 && j <= 8)) beta_out[(i64)j * L + cidx] = b[j];
+                }
+            }
+            // z-step input of the next iteration
+#pragma unroll
+            for (int j = 0; j < 10; j++) w[j] = dsub(z2n[j], b[j]);
+            proj_soc<ONE_D>(w);
+#pragma unroll
+            for (int j = 0; j < 10; j++) w[j] = dadd(w[j], b[j]);
+            sh[buf][0][lx][ly] = w[1];
+            sh[buf][1][lx][ly] = w[3];
+            sh[buf][2][lx][ly] = w[5];
+            sh[buf][3][lx][ly] = w[7];
+        }
+        __syncthreads();
+        if (owner) {
+            if (cell) {
+                q2[cidx] = dmul(dsub(w[9], w[0]), sc.S);
+                a0 = alpha[cidx];
+                if (WEIGHTED) wt0 = weight[cidx];
+            }
+            const double u0 = cell ? uval<WEIGHTED>(cn.q0, a0, wt0) : 0.0;
+            // rhs = A' u + c : CSR-transpose row order (t-1 edge, t edge, x-1, x, y-1, y)
+            double acc = 0.0;
+            bool first = true;
+#define ADDTERM(val)                         \
+    {                                        \
+        const double tv_ = (val);            \
+        acc = first ? tv_ : dadd(acc, tv_);  \
+        first = false;                       \
+    }
+            if (t > 0) ADDTERM(dmul(sc.gt, u0p));
+            if (cell) ADDTERM(dmul(-sc.gt, u0));
+            if (hxp || hxm) {
+                const i64 ox = (i64)t * g.PBX;
+                if (hxm) ADDTERM(dmul(sc.gx, uval<WEIGHTED>(cn.bxm, al_bx[ox + ibxm], WEIGHTED ? w_bx[ox + ibxm] : 1.0)));
+                if (hxp) {
+                    ADDTERM(dmul(-sc.gx, uval<WEIGHTED>(cn.bx, al_bx[ox + ibx], WEIGHTED ? w_bx[ox + ibx] : 1.0)));
+                    const double w1n = cell ? sh[buf][0][lx + 1][ly] : 0.0;
+                    const double w3n = cell ? sh[buf][1][lx + 1][ly] : 0.0;
+                    double s;
+                    if (t == 0)
+                        s = dadd(w1n, w[2]);
+                    else if (!cell)
+                        s = dadd(wp3n, wp4);
+                    else
+                        s = dadd(dadd(dadd(w1n, w[2]), wp3n), wp4);
+                    q2_bx[ox + ibx] = dmul(s, sc.SF);
+                    wp3n = w3n;
+                }
+            }
+            if (hyp || hym) {
+                const i64 oy = (i64)t * g.PBY;
+                if (hym) ADDTERM(dmul(sc.gy, uval<WEIGHTED>(cn.bym, al_by[oy + ibym], WEIGHTED ? w_by[oy + ibym] : 1.0)));
+                if (hyp) {
+                    ADDTERM(dmul(-sc.gy, uval<WEIGHTED>(cn.by, al_by[oy + iby], WEIGHTED ? w_by[oy + iby] : 1.0)));
+                    const double w5n = cell ? sh[buf][2][lx][ly + 1] : 0.0;
+                    const double w7n = cell ? sh[buf][3][lx][ly + 1] : 0.0;
+                    double s;
+                    if (t == 0)
+                        s = dadd(w5n, w[6]);
+                    else if (!cell)
+                        s = dadd(wp7n, wp8);
+                    else
+                        s = dadd(dadd(dadd(w5n, w[6]), wp7n), wp8);
+                    q2_by[oy + iby] = dmul(s, sc.SF);
+                    wp7n = w7n;
+                }
+            }
+#undef ADDTERM
+            double cv = 0.0;
+            if (t == 0) cv = c0[node];
+            else if (!cell) cv = c1[node];
+            rhs[cidx] = dadd(first ? 0.0 : acc, cv);
+            u0p = u0;
+            wp4 = w[4];
+            wp8 = w[8];
+        }
+        // advance the carried node-level values
+        cn.bxm = cn.bxm1; cn.bx = cn.bx1; cn.bym = cn.bym1; cn.by = cn.by1;
+        if (UPDATE) { co.bxm = co.bxm1; co.bx = co.bx1; co.bym = co.bym1; co.by = co.by1; }
+    }
+}
+
+void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st)
+{
+    constexpr int TX = 8, TY = 64;
+    dim3 block(TY, TX);
+    dim3 grid((unsigned)((a.g.nx + TX - 2) / (TX - 1)), (unsigned)((a.g.ny + TY - 2) / (TY - 1)));
+#define KM(W, O, U)                                                                                          \
+    k_mult<TX, TY, W, O, U><<<grid, block, 0, st>>>(a.g, a.sc, a.q_old, a.q_new, a.alpha, a.weight, a.beta_in, \
+                                                     a.beta_out, a.q2, a.rhs, a.c0, a.c1)
+    if (one_d) {
+        if (update) KM(false, true, true); else KM(false, true, false);
+    } else if (weighted) {
+        if (update) KM(true, false, true); else KM(true, false, false);
+    } else {
+        if (update) KM(false, false, true); else KM(false, false, false);
+    }
+#undef KM
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Deterministic reductions: every CTA writes its K partial sums, a single CTA adds them in a fixed tree order.
+// ---------------------------------------------------------------------------------------------------------------
+template <int K, int NT>
+__device__ __forceinline__ void block_reduce_store(double (&s)[K], double* __restrict__ partial)
+{
+    __shared__ double red[K][NT / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double v = s[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[k][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double v = 0.0;
+        for (int i = 0; i < NT / 32; i++) v += red[threadIdx.x][i];
+        partial[(i64)(blockIdx.y * gridDim.x + blockIdx.x) * K + threadIdx.x] = v;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) k_final_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ out)
+{
+    __shared__ double red[256];
+    for (int k = 0; k < K; k++) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < nblocks; i += 256) v += partial[(i64)i * K + k];
+        red[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[k] = red[0];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// KKT sums over cells (solver_socp_inPALM.m:228,231,236,240-241 and compute_kkt_dot_complement.m:2-8).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool WEIGHTED, bool ONE_D>
+__global__ void __launch_bounds__(256) k_kkt_cells(KktArgs a)
+{
+    const Geo& g = a.g;
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    double s[KC_COUNT];
+#pragma unroll
+    for (int k = 0; k < KC_COUNT; k++) s[k] = 0.0;
+    if (p < g.P) {
+        const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+        const bool hxm = x > 0, hxp = x < g.nx - 1, hym = y > 0, hyp = y < g.ny - 1;
+        const i64 L = g.L, c = (i64)t * g.P + p;
+        const double* bx = a.q + L;
+        const double* by = bx + g.NBX;
+        CellQ cq;
+        cq.q0 = a.q[c];
+        const i64 ox = (i64)t * g.PBX + (i64)x * g.ny + y, oy = (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
+        cq.bxm = hxm ? bx[ox - g.ny] : 0.0;
+        cq.bx = hxp ? bx[ox] : 0.0;
+        cq.bxm1 = hxm ? bx[ox + g.PBX - g.ny] : 0.0;
+        cq.bx1 = hxp ? bx[ox + g.PBX] : 0.0;
+        cq.bym = hym ? by[oy - 1] : 0.0;
+        cq.by = hyp ? by[oy] : 0.0;
+        cq.bym1 = hym ? by[oy + g.PBY - 1] : 0.0;
+        cq.by1 = hyp ? by[oy + g.PBY] : 0.0;
+        double z2[10], z[10], b[10], v[10];
+        cell_z2(cq, a.sc, hxm, hxp, hym, hyp, z2);
+        load_z<ONE_D>(a.g, a.sc, a.z, a.q_old, a.beta_old, t, x, y, z);
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+            const bool dead = ONE_D && j >= 5 && j <= 8;
+            b[j] = dead ? 0.0 : a.beta[(i64)j * L + c];
+            s[KC_Z2] += z[j] * z[j];
+            s[KC_BETA2] += b[j] * b[j];
+            const double r = dsub(z[j], z2[j]);
+            s[KC_PRIM2] += r * r;
+            v[j] = dsub(z[j], dmul(a.sigma, b[j]));
+        }
+        proj_soc<ONE_D>(v);
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+            const double r = dsub(z[j], v[j]);
+            s[KC_COMPL] += r * r;
+        }
+        // DOT-level complementarity
+        const double al = WEIGHTED ? dmul(a.weight[c], a.alpha[c]) : a.alpha[c];
+        const double rhoT = dmul(dmul(dmul(a.sigma, a.cScale), a.D), al);
+        const double sE = a.dScale / a.E;
+        double ss = 0.0;
+#pragma unroll
+        for (int j = 1; j <= 8; j++) {
+            const double e = dmul(sE, z2[j]);
+            ss = (j == 1) ? dmul(e, e) : dadd(ss, dmul(e, e));
+        }
+        double rhoFq = dadd(dadd(rhoT, dmul(a.dScale / a.D, cq.q0)), ss / 4.0);
+        if (rhoFq < 0.0) rhoFq = 0.0;
+        const double dr = dsub(rhoT, rhoFq);
+        s[KC_DOTC] = dr * dr;
+        s[KC_RHOT] = rhoT * rhoT;
+        s[KC_RHOFQ] = rhoFq * rhoFq;
+    }
+    block_reduce_store<KC_COUNT, 256>(s, a.partial);
+}
+
+int kkt_cells_blocks(const Geo& g) { return (int)((g.P + 255) / 256) * (g.nt - 1); }
+int kkt_nodes_blocks(const Geo& g) { return (int)((g.P + 255) / 256) * g.nt; }
+
+void launch_kkt_cells(const KktArgs& a, bool weighted, bool one_d, cudaStream_t st)
+{
+    dim3 grid((unsigned)((a.g.P + 255) / 256), (unsigned)(a.g.nt - 1));
+    if (one_d)
+        k_kkt_cells<false, true><<<grid, 256, 0, st>>>(a);
+    else if (weighted)
+        k_kkt_cells<true, false><<<grid, 256, 0, st>>>(a);
+    else
+        k_kkt_cells<false, false><<<grid, 256, 0, st>>>(a);
+    k_final_reduce<KC_COUNT><<<1, 256, 0, st>>>(a.partial, kkt_cells_blocks(a.g), a.out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// z = Pi_Q(d + BF q_old - beta_old) materialised (final output, :334) and/or its squared Frobenius norm (rescale
+// block, :141).  zout may alias beta_old (cell-local read-then-write).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool ONE_D>
+__global__ void __launch_bounds__(256) k_zstep(Geo g, IterScal sc, const double* q_old, const double* beta_old, double* zout,
+                                               double* __restrict__ partial)
+{
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    double s[1] = {0.0};
+    if (p < g.P) {
+        const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+        double z[10];
+        load_z<ONE_D>(g, sc, nullptr, q_old, beta_old, t, x, y, z);
+        const i64 c = (i64)t * g.P + p;
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+            s[0] += z[j] * z[j];
+            if (zout != nullptr && !(ONE_D && j >= 5 && j <= 8)) zout[(i64)j * g.L + c] = z[j];
+        }
+    }
+    block_reduce_store<1, 256>(s, partial);
+}
+
+void launch_zstep(const Geo& g, const IterScal& sc, bool one_d, const double* q_old, const double* beta_old, double* zout,
+                  double* partial, double* out, cudaStream_t st)
+{
+    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)(g.nt - 1));
+    if (one_d)
+        k_zstep<true><<<grid, 256, 0, st>>>(g, sc, q_old, beta_old, zout, partial);
+    else
+        k_zstep<false><<<grid, 256, 0, st>>>(g, sc, q_old, beta_old, zout, partial);
+    k_final_reduce<1><<<1, 256, 0, st>>>(partial, kkt_cells_blocks(g), out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// KKT sums over nodes / staggered edges (solver_socp_inPALM.m:227-238,265-266; compute_kkt_dot_complement.m:10-18).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_kkt_nodes(KktArgs a)
+{
+    const Geo& g = a.g;
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    double s[KN_COUNT];
+#pragma unroll
+    for (int k = 0; k < KN_COUNT; k++) s[k] = 0.0;
+    if (p < g.P) {
+        const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+        const i64 L = g.L, n = (i64)t * g.P + p;
+        const bool up = t < g.nt - 1, dn = t > 0;
+        const bool hxm = x > 0, hxp = x < g.nx - 1, hym = y > 0, hyp = y < g.ny - 1;
+        const IterScal& sc = a.sc;
+        const double ph = a.phi[n];
+        const double scD = dmul(dmul(a.sigma, a.cScale), a.D);   // sigma*cScale*D
+        const double dD = a.dScale / a.D;
+        // Dalpha on the t-edges around this node and its x+1 / y+1 neighbours (for rho = pair-average in t)
+        auto dal0 = [&](i64 c) -> double { return WEIGHTED ? dmul(a.weight[c], a.alpha[c]) : a.alpha[c]; };
+        auto rho_at = [&](i64 pp) -> double {   // rho(t, node pp) = (rhoT[t-1] + rhoT[t]) / 2 with zero padding
+            const double lo = dn ? dmul(scD, dal0((i64)(t - 1) * g.P + pp)) : 0.0;
+            const double hi = up ? dmul(scD, dal0((i64)t * g.P + pp)) : 0.0;
+            return dadd(lo, hi) / 2.0;
+        };
+        auto edge = [&](i64 e, double aphi, bool momentum, double rho_avg) {
+            const double qv = a.q[e], av = a.alpha[e], fb = a.q2b[e];
+            const double w = WEIGHTED ? a.weight[e] : 1.0;
+            const double wq = WEIGHTED ? dmul(w, qv) : qv;
+            const double wa = WEIGHTED ? dmul(w, av) : av;
+            s[KN_Q2] += qv * qv;
+            s[KN_APHI2] += aphi * aphi;
+            const double r1 = dsub(aphi, wq);
+            s[KN_PRIM1] += r1 * r1;
+            s[KN_ALPHA2] += av * av;
+            s[KN_FBB2] += fb * fb;
+            const double r2 = dadd(fb, wa);
+            s[KN_DUAL2] += r2 * r2;
+            s[KN_QDOTA] += wq * av;
+            if (momentum) {
+                const double m = dmul(scD, wa);
+                const double rb = dmul(dD, dmul(rho_avg, qv));
+                const double d = dsub(m, rb);
+                s[KN_MRHOB] += d * d;
+                s[KN_M2] += m * m;
+                s[KN_RHOB2] += rb * rb;
+            }
+        };
+        const double rho_c = rho_at(p);
+        if (up) edge(n, dadd(dmul(-sc.gt, ph), dmul(sc.gt, a.phi[n + g.P])), false, 0.0);
+        if (hxp)
+            edge(L + (i64)t * g.PBX + (i64)x * g.ny + y, dadd(dmul(-sc.gx, ph), dmul(sc.gx, a.phi[n + g.ny])), true,
+                 dadd(rho_c, rho_at(p + g.ny)) / 2.0);
+        if (hyp)
+            edge(L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y, dadd(dmul(-sc.gy, ph), dmul(sc.gy, a.phi[n + 1])),
+                 true, dadd(rho_c, rho_at(p + 1)) / 2.0);
+        // dual residual A' alpha - c at the node (CSR-transpose row order)
+        const double* al_bx = a.alpha + L;
+        const double* al_by = al_bx + g.NBX;
+        double acc = 0.0;
+        bool first = true;
+#define ADDTERM(val)                         \
+    {                                        \
+        const double tv_ = (val);            \
+        acc = first ? tv_ : dadd(acc, tv_);  \
+        first = false;                       \
+    }
+        if (dn) ADDTERM(dmul(sc.gt, a.alpha[n - g.P]));
+        if (up) ADDTERM(dmul(-sc.gt, a.alpha[n]));
+        const i64 ox = (i64)t * g.PBX + (i64)x * g.ny + y, oy = (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
+        if (hxm) ADDTERM(dmul(sc.gx, al_bx[ox - g.ny]));
+        if (hxp) ADDTERM(dmul(-sc.gx, al_bx[ox]));
+        if (hym) ADDTERM(dmul(sc.gy, al_by[oy - 1]));
+        if (hyp) ADDTERM(dmul(-sc.gy, al_by[oy]));
+#undef ADDTERM
+        double cv = 0.0;
+        if (t == 0) cv = a.c0[p];
+        else if (!up) cv = a.c1[p];
+        const double rd = dsub(first ? 0.0 : acc, cv);
+        s[KN_DUAL1] = rd * rd;
+        s[KN_CPHI] = cv * ph;
+        s[KN_PHI2] = ph * ph;
+    }
+    block_reduce_store<KN_COUNT, 256>(s, a.partial);
+}
+
+void launch_kkt_nodes(const KktArgs& a, bool weighted, cudaStream_t st)
+{
+    dim3 grid((unsigned)((a.g.P + 255) / 256), (unsigned)a.g.nt);
+    if (weighted)
+        k_kkt_nodes<true><<<grid, 256, 0, st>>>(a);
+    else
+        k_kkt_nodes<false><<<grid, 256, 0, st>>>(a);
+    k_final_reduce<KN_COUNT><<<1, 256, 0, st>>>(a.partial, kkt_nodes_blocks(a.g), a.out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small streaming helpers
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SUMSQ_MAX_BLOCKS = 148 * 8;
+__global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ x, i64 n, double* __restrict__ partial)
+{
+    double s[1] = {0.0};
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) s[0] += x[i] * x[i];
+    block_reduce_store<1, 256>(s, partial);
+}
+int sumsq_blocks(i64 n)
+{
+    i64 b = (n + 255) / 256;
+    if (b > SUMSQ_MAX_BLOCKS) b = SUMSQ_MAX_BLOCKS;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+void launch_sumsq(const double* x, i64 n, double* partial, double* out, cudaStream_t st)
+{
+    const int nb = sumsq_blocks(n);
+    k_sumsq<<<nb, 256, 0, st>>>(x, n, partial);
+    k_final_reduce<1><<<1, 256, 0, st>>>(partial, nb, out);
+}
+
+__global__ void __launch_bounds__(256) k_scale(double* __restrict__ x, i64 n, double mul, double div)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        x[i] = dmul(x[i], mul) / div;
+}
+void launch_scale(double* x, i64 n, double mul, double div, cudaStream_t st)
+{
+    if (n <= 0) return;
+    i64 b = (n + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    k_scale<<<(unsigned)b, 256, 0, st>>>(x, n, mul, div);
+}
+
+__global__ void __launch_bounds__(256) k_halpern(double* __restrict__ x, double* __restrict__ xold, double* __restrict__ x0,
+                                                 i64 n, double c1, double c2, double rho, int copy_anchor)
+{
+    const double omr = 1.0 - rho;
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double inner = dadd(dmul(omr, xold[i]), dmul(rho, x[i]));
+        const double v = dadd(dmul(c1, x0[i]), dmul(c2, inner));
+        x[i] = v;
+        xold[i] = v;
+        if (copy_anchor) x0[i] = v;
+    }
+}
+void launch_halpern(double* x, double* xold, double* x0, i64 n, double c1, double c2, double rho, bool copy_anchor,
+                    cudaStream_t st)
+{
+    if (n <= 0) return;
+    i64 b = (n + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    k_halpern<<<(unsigned)b, 256, 0, st>>>(x, xold, x0, n, c1, c2, rho, copy_anchor ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(256) k_cols6to10(const double* __restrict__ in6, double* __restrict__ out10, i64 L)
+{
+    const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (i >= L) return;
+#pragma unroll
+    for (int j = 0; j < 5; j++) out10[(i64)j * L + i] = in6[(i64)j * L + i];
+#pragma unroll
+    for (int j = 5; j < 9; j++) out10[(i64)j * L + i] = 0.0;
+    out10[9 * L + i] = in6[5 * L + i];
+}
+__global__ void __launch_bounds__(256) k_cols10to6(const double* __restrict__ in10, double* __restrict__ out6, i64 L)
+{
+    const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (i >= L) return;
+#pragma unroll
+    for (int j = 0; j < 5; j++) out6[(i64)j * L + i] = in10[(i64)j * L + i];
+    out6[5 * L + i] = in10[9 * L + i];
+}
+void launch_cols6to10(const double* in6, double* out10, i64 L, cudaStream_t st)
+{
+    k_cols6to10<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(in6, out10, L);
+}
+void launch_cols10to6(const double* in10, double* out6, i64 L, cudaStream_t st)
+{
+    k_cols10to6<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(in10, out6, L);
+}
+
+}  // namespace dsocp

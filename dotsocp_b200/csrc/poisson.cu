@@ -1,0 +1,611 @@
+// poisson.cu -- Neumann Poisson solve  phi = IDCT3( DCT3(rhs) ./ (D^2 kernel) )  as batched per-axis transforms (sm_100a).
+//
+// Reference: oper_poisson3dim.m:4, initialize_FFTkernel.m:6-15, mirt_dctn.m:64-96, mirt_idctn.m:59-95 (orthonormal
+// DCT-II per axis, implemented there as permute -> complex FFT -> twiddle).
+//
+// The grid lengths are n = 2^k + 1 (65, 129, 257, 513, 1025; 257 is prime), so no power-of-two FFT applies directly
+// and a dense n x n contraction costs 2n flop per 16 B moved (compute-bound beyond n ~ 64 even on the FP64 tensor
+// pipe).  Each 1-D DCT-II is therefore computed as
+//     Makhoul permutation -> length-n complex DFT of TWO real lines packed as re/im
+//                         -> Bluestein chirp-z: n-point DFT == circular convolution of length M,
+//                            M = 2(n-1) = 2^(k+1)   (valid because the chirp is even, see dct_plan_create)
+//                         -> two power-of-two FFTs of length M in shared memory (radix-8/4, digit-reversed middle)
+// which is O(log n) flop per element for every n.  The t axis is done as ONE kernel: forward DCT, division by the
+// eigenvalue table, inverse DCT, so the solve is 5 passes over N doubles (y, x, [t,/,t^-1], x^-1, y^-1).
+// Lengths <= 32 (coarse multilevel grids) use a dense matrix kernel.
+#include "kernels.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace dsocp {
+
+struct DctPlan {
+    int n;
+    int dense;         // 1: dense matrix path
+    int log2m, M;
+    double2* w;        // chirp  w[j] = exp(-i pi j^2 / n), j < n
+    double2* bhat;     // FFT_M(b_circ)/M in the digit-reversed order produced by the forward passes
+    double2* tw;       // exp(-2 pi i j / M), j < M
+    double2* pw;       // c_k exp(-i pi k / (2n)), k < n   (forward post-twiddle incl. orthonormal scale)
+    double2* ipw;      // exp(+i pi k / (2n)) / c_k / n     (inverse pre-twiddle incl. 1/n of the IDFT)
+    double* cmat;      // dense: C[k*n + j] = c_k cos(pi (2j+1) k / (2n))
+};
+
+// ------------------------------------------------------------------------------------------------ host tables
+static const long double PIl = 3.141592653589793238462643383279502884L;
+
+static void radices_for(int log2m, int* r, int* nr)
+{
+    int n8 = 0, n4 = 0;
+    switch (log2m % 3) {
+        case 0: n8 = log2m / 3; break;
+        case 1: n8 = (log2m - 4) / 3; n4 = 2; break;
+        default: n8 = (log2m - 2) / 3; n4 = 1; break;
+    }
+    int k = 0;
+    for (int i = 0; i < n8; i++) r[k++] = 8;
+    for (int i = 0; i < n4; i++) r[k++] = 4;
+    *nr = k;
+}
+
+static void host_fft(std::vector<long double>& re, std::vector<long double>& im)
+{
+    const size_t n = re.size();
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; k++) {
+                const long double ang = -2 * PIl * (long double)k / (long double)len;
+                const long double wr = cosl(ang), wi = sinl(ang);
+                const size_t a = i + k, b = i + k + len / 2;
+                const long double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+                re[b] = re[a] - xr; im[b] = im[a] - xi;
+                re[a] += xr; im[a] += xi;
+            }
+    }
+}
+
+template <typename T>
+static T* to_device(const std::vector<T>& v)
+{
+    T* d = nullptr;
+    if (cudaMalloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+}
+
+static DctPlan* dct_plan_create(int n)
+{
+    DctPlan* p = new DctPlan();
+    memset(p, 0, sizeof(*p));
+    p->n = n;
+    const long double c0 = sqrtl(1.0L / n), c1 = sqrtl(2.0L / n);
+    if (n <= 32) {
+        p->dense = 1;
+        std::vector<double> C((size_t)n * n);
+        for (int k = 0; k < n; k++)
+            for (int j = 0; j < n; j++) {
+                // reduce the angle pi (2j+1) k / (2n) exactly modulo 2 pi: (2j+1) k mod 4n
+                const long long a = ((long long)(2 * j + 1) * k) % (4LL * n);
+                C[(size_t)k * n + j] = (double)((k == 0 ? c0 : c1) * cosl(PIl * (long double)a / (2.0L * n)));
+            }
+        p->cmat = to_device(C);
+        return p;
+    }
+    // Bluestein length: the chirp b[m] = exp(+i pi m^2 / n) is even in m, so a circular convolution of length
+    // M >= 2n-2 already reproduces the linear one (lags +(n-1) and -(n-1) share a slot and need the same value).
+    int log2m = 1;
+    while ((1 << log2m) < 2 * n - 2) log2m++;
+    p->log2m = log2m;
+    p->M = 1 << log2m;
+    const int M = p->M;
+    std::vector<double2> w(n), pw(n), ipw(n), tw(M), bh(M);
+    std::vector<long double> wr(n), wi(n);
+    for (int j = 0; j < n; j++) {
+        const long long a = ((long long)j * j) % (2LL * n);   // j^2 mod 2n (exact)
+        wr[j] = cosl(PIl * (long double)a / n);
+        wi[j] = -sinl(PIl * (long double)a / n);
+        w[j] = make_double2((double)wr[j], (double)wi[j]);
+        const long double ck = (j == 0) ? c0 : c1;
+        const long double ang = PIl * (long double)j / (2.0L * n);
+        pw[j] = make_double2((double)(ck * cosl(ang)), (double)(-ck * sinl(ang)));
+        ipw[j] = make_double2((double)(cosl(ang) / ck / n), (double)(sinl(ang) / ck / n));
+    }
+    for (int j = 0; j < M; j++) {
+        const long double ang = -2 * PIl * (long double)j / M;
+        tw[j] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+    std::vector<long double> br(M, 0.0L), bi(M, 0.0L);
+    for (int s = 0; s < n; s++) {
+        br[s] = wr[s]; bi[s] = -wi[s];                       // b = conj(w)
+        if (s > 0) { br[M - s] = wr[s]; bi[M - s] = -wi[s]; }
+    }
+    host_fft(br, bi);
+    int rad[8], nr;
+    radices_for(log2m, rad, &nr);
+    for (int pos = 0; pos < M; pos++) {
+        // position -> frequency of the mixed-radix DIF passes (see fft_pass): pos = sum m_i * M/(r_1..r_i),
+        // freq = m_1 + r_1 (m_2 + r_2 (...))
+        int rem = pos, span = M, f = 0, mult = 1;
+        for (int i = 0; i < nr; i++) {
+            span /= rad[i];
+            const int m = rem / span;
+            rem -= m * span;
+            f += m * mult;
+            mult *= rad[i];
+        }
+        bh[pos] = make_double2((double)(br[f] / M), (double)(bi[f] / M));
+    }
+    p->w = to_device(w);
+    p->pw = to_device(pw);
+    p->ipw = to_device(ipw);
+    p->tw = to_device(tw);
+    p->bhat = to_device(bh);
+    return p;
+}
+
+static void dct_plan_destroy(DctPlan* p)
+{
+    if (!p) return;
+    cudaFree(p->w); cudaFree(p->bhat); cudaFree(p->tw); cudaFree(p->pw); cudaFree(p->ipw); cudaFree(p->cmat);
+    delete p;
+}
+
+// ------------------------------------------------------------------------------------------------ device FFT
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b)   // a * conj(b)
+{
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+// multiply by -i (SIGN<0) or +i (SIGN>0)
+template <int SIGN>
+__device__ __forceinline__ double2 cmuli(double2 a)
+{
+    return SIGN < 0 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x);
+}
+
+template <int SIGN>
+__device__ __forceinline__ void dft4(double2& a0, double2& a1, double2& a2, double2& a3)
+{
+    const double2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = cmuli<SIGN>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+template <int SIGN>
+__device__ __forceinline__ void dft8(double2 (&v)[8])
+{
+    double2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    double2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    dft4<SIGN>(e0, e1, e2, e3);
+    dft4<SIGN>(o0, o1, o2, o3);
+    const double h = 0.70710678118654752440;
+    // w8^1 = (1 -+ i)/sqrt2, w8^2 = -+i, w8^3 = (-1 -+ i)/sqrt2
+    const double2 t1 = SIGN < 0 ? make_double2((o1.x + o1.y) * h, (o1.y - o1.x) * h)
+                                : make_double2((o1.x - o1.y) * h, (o1.y + o1.x) * h);
+    const double2 t2 = cmuli<SIGN>(o2);
+    const double2 t3 = SIGN < 0 ? make_double2((o3.y - o3.x) * h, (-o3.x - o3.y) * h)
+                                : make_double2((-o3.x - o3.y) * h, (o3.x - o3.y) * h);
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, t1); v[5] = csub(e1, t1);
+    v[2] = cadd(e2, t2); v[6] = csub(e2, t2);
+    v[3] = cadd(e3, t3); v[7] = csub(e3, t3);
+}
+
+#define PADI(i) ((i) + ((i) >> 3))
+
+// One radix-R pass over an M-point array in shared memory, TP = M/8 cooperating threads.
+// forward (INV=false): decimation in frequency, butterfly then twiddle  -> digit-reversed spectrum after all passes
+// inverse (INV=true) : the transposed graph, conjugate twiddle then butterfly -> natural order from digit-reversed input
+template <int R, bool INV>
+__device__ __forceinline__ void fft_pass(double2* __restrict__ s, int ltid, int TP, int M, int len,
+                                         const double2* __restrict__ tw)
+{
+    const int q = len / R;
+    const int nb = M / R;
+    const int tstep = M / len;
+    for (int jb = ltid; jb < nb; jb += TP) {
+        const int b = jb / q, k = jb - b * q;
+        const int base = b * len + k;
+        if (R == 8) {
+            double2 v[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) v[m] = s[PADI(base + m * q)];
+            if (!INV) {
+                dft8<-1>(v);
+#pragma unroll
+                for (int f = 1; f < 8; f++) v[f] = cmul(v[f], __ldg(&tw[f * k * tstep]));
+            } else {
+#pragma unroll
+                for (int f = 1; f < 8; f++) v[f] = cmulc(v[f], __ldg(&tw[f * k * tstep]));
+                dft8<1>(v);
+            }
+#pragma unroll
+            for (int m = 0; m < 8; m++) s[PADI(base + m * q)] = v[m];
+        } else {
+            double2 a0 = s[PADI(base)], a1 = s[PADI(base + q)], a2 = s[PADI(base + 2 * q)], a3 = s[PADI(base + 3 * q)];
+            if (!INV) {
+                dft4<-1>(a0, a1, a2, a3);
+                a1 = cmul(a1, __ldg(&tw[k * tstep]));
+                a2 = cmul(a2, __ldg(&tw[2 * k * tstep]));
+                a3 = cmul(a3, __ldg(&tw[3 * k * tstep]));
+            } else {
+                a1 = cmulc(a1, __ldg(&tw[k * tstep]));
+                a2 = cmulc(a2, __ldg(&tw[2 * k * tstep]));
+                a3 = cmulc(a3, __ldg(&tw[3 * k * tstep]));
+                dft4<1>(a0, a1, a2, a3);
+            }
+            s[PADI(base)] = a0; s[PADI(base + q)] = a1; s[PADI(base + 2 * q)] = a2; s[PADI(base + 3 * q)] = a3;
+        }
+    }
+    __syncthreads();
+}
+
+template <int LOG2M>
+struct Radix {
+    static constexpr int N8 = (LOG2M % 3 == 0) ? LOG2M / 3 : (LOG2M % 3 == 1) ? (LOG2M - 4) / 3 : (LOG2M - 2) / 3;
+    static constexpr int N4 = (LOG2M % 3 == 0) ? 0 : (LOG2M % 3 == 1) ? 2 : 1;
+};
+
+// a <- circular convolution core: FFT_M (DIF), pointwise * bhat, IFFT_M (DIT).  Leaves the result in natural order.
+template <int LOG2M>
+__device__ __forceinline__ void conv_core(double2* __restrict__ s, int ltid, const double2* __restrict__ tw,
+                                          const double2* __restrict__ bhat)
+{
+    constexpr int M = 1 << LOG2M, TP = M / 8;
+    int len = M;
+#pragma unroll
+    for (int i = 0; i < Radix<LOG2M>::N8; i++) { fft_pass<8, false>(s, ltid, TP, M, len, tw); len >>= 3; }
+#pragma unroll
+    for (int i = 0; i < Radix<LOG2M>::N4; i++) { fft_pass<4, false>(s, ltid, TP, M, len, tw); len >>= 2; }
+    for (int i = ltid; i < M; i += TP) s[PADI(i)] = cmul(s[PADI(i)], __ldg(&bhat[i]));
+    __syncthreads();
+    len = 1;
+#pragma unroll
+    for (int i = 0; i < Radix<LOG2M>::N4; i++) { len <<= 2; fft_pass<4, true>(s, ltid, TP, M, len, tw); }
+#pragma unroll
+    for (int i = 0; i < Radix<LOG2M>::N8; i++) { len <<= 3; fft_pass<8, true>(s, ltid, TP, M, len, tw); }
+}
+
+// ------------------------------------------------------------------------------------------------ batched DCT kernel
+struct LineGeom {
+    int n;             // transform length
+    i64 estride;       // distance between consecutive elements of a line
+    i64 gstride;       // distance between the first elements of adjacent lines of a group
+    i64 inner;         // lines per outer index
+    i64 ostride;       // distance between outer indices
+    int contiguous;    // 1: lines are contiguous (estride == 1): flat staging index runs along the line
+};
+
+struct ScaleArgs {     // MODE 2 (t axis): divide the spectrum by D2*((lamY[y] + lamX[x]) + lamT[k]), zero -> 1
+    const double* lam_t;
+    const double* lam_x;
+    const double* lam_y;
+    int ny;
+    double D2;
+};
+
+// Makhoul index: real element i of the line -> position in v (x[2j] -> v[j], x[2j+1] -> v[n-1-j])
+__device__ __forceinline__ int makhoul(int i, int n) { return (i & 1) ? (n - 1 - (i >> 1)) : (i >> 1); }
+
+// MODE 0: forward DCT-II, 1: inverse, 2: forward -> ./kernel -> inverse
+template <int LOG2M, int PAIRS, int MODE>
+__global__ void __launch_bounds__((1 << LOG2M) / 8 * PAIRS)
+k_dct_bluestein(LineGeom lg, const double* ain, double* aout, const double2* __restrict__ w, const double2* __restrict__ bhat,
+                const double2* __restrict__ tw, const double2* __restrict__ pw, const double2* __restrict__ ipw,
+                ScaleArgs sa)
+{
+    constexpr int M = 1 << LOG2M, TP = M / 8, G = 2 * PAIRS, NTHR = TP * PAIRS, PADLEN = M + M / 8;
+    extern __shared__ double2 smem[];
+    const int n = lg.n;
+    const int tid = threadIdx.x;
+    const int pair = tid / TP, ltid = tid - pair * TP;
+    double2* __restrict__ s = smem + (size_t)pair * PADLEN;
+    const i64 line0 = (i64)blockIdx.x * G;
+    const i64 gbase = (i64)blockIdx.y * lg.ostride + line0 * lg.gstride;
+    const int nlines = (int)((lg.inner - line0) < (i64)G ? (lg.inner - line0) : (i64)G);
+
+    // ---- stage in: global -> shared -------------------------------------------------------------------------
+    for (int i = tid; i < PAIRS * PADLEN; i += NTHR) smem[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    {
+        const int total = G * n;
+        for (int f = tid; f < total; f += NTHR) {
+            int g, j;
+            if (lg.contiguous) { g = f / n; j = f - g * n; } else { j = f / G; g = f - j * G; }
+            if (g < nlines) {
+                const double val = ain[gbase + (i64)g * lg.gstride + (i64)j * lg.estride];
+                double* dst = reinterpret_cast<double*>(smem + (size_t)(g >> 1) * PADLEN +
+                                                        PADI(MODE == 1 ? j : makhoul(j, n)));
+                dst[g & 1] = val;
+            }
+        }
+    }
+    __syncthreads();
+
+    if (MODE != 1) {
+        // ---- forward: a[m] = (v1 + i v2)[m] * w[m]; V = w .* conv(a, b) ----------------------------------------
+        for (int m = ltid; m < n; m += TP) s[PADI(m)] = cmul(s[PADI(m)], __ldg(&w[m]));
+        __syncthreads();
+        conv_core<LOG2M>(s, ltid, tw, bhat);
+        for (int k = ltid; k < n; k += TP) s[PADI(k)] = cmul(s[PADI(k)], __ldg(&w[k]));
+        __syncthreads();
+        // separate the two real lines: V1 = (V[k] + conj V[n-k])/2, V2 = (V[k] - conj V[n-k])/(2i); X = Re(pw V)
+        constexpr int KPT = 5;   // n <= M/2 + 1 = 4 TP + 1  => at most 5 k per thread
+        double2 r[KPT];
+#pragma unroll
+        for (int cnt = 0; cnt < KPT; cnt++) {
+            const int k = ltid + cnt * TP;
+            if (k >= n) continue;
+            const double2 vk = s[PADI(k)];
+            const double2 vn = s[PADI(k == 0 ? 0 : n - k)];
+            const double2 v1 = make_double2(0.5 * (vk.x + vn.x), 0.5 * (vk.y - vn.y));
+            const double2 dd = make_double2(vk.x - vn.x, vk.y + vn.y);
+            const double2 v2 = make_double2(0.5 * dd.y, -0.5 * dd.x);
+            const double2 p = __ldg(&pw[k]);
+            double x1 = p.x * v1.x - p.y * v1.y;
+            double x2 = p.x * v2.x - p.y * v2.y;
+            if (MODE == 2) {
+                // spectral division, same operation order as D^2 * ((CY + CX) + CT) and rhs ./ kernel
+                const i64 l1 = line0 + 2 * pair, l2 = l1 + 1;
+                {
+                    const int xx = (int)(l1 / sa.ny), yy = (int)(l1 - (i64)xx * sa.ny);
+                    double kv = (l1 < lg.inner) ? __dadd_rn(__dadd_rn(sa.lam_y[yy], sa.lam_x[xx]), sa.lam_t[k]) : 1.0;
+                    if (kv == 0.0) kv = 1.0;
+                    x1 = x1 / __dmul_rn(sa.D2, kv);
+                }
+                {
+                    const int xx = (int)(l2 / sa.ny), yy = (int)(l2 - (i64)xx * sa.ny);
+                    double kv = (l2 < lg.inner) ? __dadd_rn(__dadd_rn(sa.lam_y[yy], sa.lam_x[xx]), sa.lam_t[k]) : 1.0;
+                    if (kv == 0.0) kv = 1.0;
+                    x2 = x2 / __dmul_rn(sa.D2, kv);
+                }
+            }
+            r[cnt] = make_double2(x1, x2);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int cnt = 0; cnt < KPT; cnt++) {
+            const int k = ltid + cnt * TP;
+            if (k < n) s[PADI(k)] = r[cnt];
+        }
+        if (MODE == 2)
+            for (int m = n + ltid; m < M; m += TP) s[PADI(m)] = make_double2(0.0, 0.0);
+        __syncthreads();
+    }
+    if (MODE != 0) {
+        // ---- inverse: s[k] = (X1[k], X2[k]) natural order.  V[k] = g_k [(X1[k]+X2[n-k]) + i (X2[k]-X1[n-k])], k>=1;
+        //      v = IDFT(V) = conj(DFT(conj V))/n through the same forward core. -------------------------------------
+        constexpr int KPT = 5;
+        double2 r[KPT];
+#pragma unroll
+        for (int cnt = 0; cnt < KPT; cnt++) {
+            const int k = ltid + cnt * TP;
+            if (k >= n) continue;
+            const double2 xk = s[PADI(k)];
+            double2 V;
+            const double2 gk = __ldg(&ipw[k]);
+            if (k == 0) {
+                V = make_double2(xk.x * gk.x, xk.y * gk.x);      // ipw[0] is real: 1/(c0 n)
+            } else {
+                const double2 xn = s[PADI(n - k)];
+                V = cmul(gk, make_double2(xk.x + xn.y, xk.y - xn.x));
+            }
+            // conj(V) * w[k]
+            r[cnt] = cmul(make_double2(V.x, -V.y), __ldg(&w[k]));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int cnt = 0; cnt < KPT; cnt++) {
+            const int k = ltid + cnt * TP;
+            if (k < n) s[PADI(k)] = r[cnt];
+        }
+        __syncthreads();
+        conv_core<LOG2M>(s, ltid, tw, bhat);
+        // v[j] = conj(w[j] c[j]) ; (1/n folded into ipw)
+        for (int j = ltid; j < n; j += TP) {
+            const double2 d = cmul(s[PADI(j)], __ldg(&w[j]));
+            s[PADI(j)] = make_double2(d.x, -d.y);
+        }
+        __syncthreads();
+    }
+
+    // ---- stage out: shared -> global ------------------------------------------------------------------------------
+    {
+        const int total = G * n;
+        for (int f = tid; f < total; f += NTHR) {
+            int g, j;
+            if (lg.contiguous) { g = f / n; j = f - g * n; } else { j = f / G; g = f - j * G; }
+            if (g < nlines) {
+                const double* src = reinterpret_cast<const double*>(smem + (size_t)(g >> 1) * PADLEN +
+                                                                    PADI(MODE == 0 ? j : makhoul(j, n)));
+                aout[gbase + (i64)g * lg.gstride + (i64)j * lg.estride] = src[g & 1];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ dense small-n kernel
+// One CTA = G lines staged in shared memory; thread (g,k) computes one output.  MODE as above.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_dct_dense(LineGeom lg, int G, const double* ain, double* aout,
+                                                   const double* __restrict__ cmat, ScaleArgs sa)
+{
+    extern __shared__ double sd[];   // [2][G][n]
+    const int n = lg.n;
+    double* buf0 = sd;
+    double* buf1 = sd + (size_t)G * n;
+    const i64 line0 = (i64)blockIdx.x * G;
+    const i64 gbase = (i64)blockIdx.y * lg.ostride + line0 * lg.gstride;
+    const int nlines = (int)((lg.inner - line0) < (i64)G ? (lg.inner - line0) : (i64)G);
+    const int total = G * n;
+    for (int f = threadIdx.x; f < total; f += blockDim.x) {
+        int g, j;
+        if (lg.contiguous) { g = f / n; j = f - g * n; } else { j = f / G; g = f - j * G; }
+        buf0[g * n + j] = (g < nlines) ? ain[gbase + (i64)g * lg.gstride + (i64)j * lg.estride] : 0.0;
+    }
+    __syncthreads();
+    if (MODE != 1) {
+        for (int f = threadIdx.x; f < total; f += blockDim.x) {
+            const int g = f / n, k = f - g * n;
+            double acc = 0.0;
+            for (int j = 0; j < n; j++) acc += __ldg(&cmat[k * n + j]) * buf0[g * n + j];
+            if (MODE == 2) {
+                const i64 l = line0 + g;
+                const int xx = (int)(l / sa.ny), yy = (int)(l - (i64)xx * sa.ny);
+                double kv = (l < lg.inner) ? __dadd_rn(__dadd_rn(sa.lam_y[yy], sa.lam_x[xx]), sa.lam_t[k]) : 1.0;
+                if (kv == 0.0) kv = 1.0;
+                acc = acc / __dmul_rn(sa.D2, kv);
+            }
+            buf1[g * n + k] = acc;
+        }
+        __syncthreads();
+    }
+    if (MODE != 0) {
+        double* src = (MODE == 1) ? buf0 : buf1;
+        double* dst = (MODE == 1) ? buf1 : buf0;
+        for (int f = threadIdx.x; f < total; f += blockDim.x) {
+            const int g = f / n, j = f - g * n;
+            double acc = 0.0;
+            for (int k = 0; k < n; k++) acc += __ldg(&cmat[k * n + j]) * src[g * n + k];
+            dst[g * n + j] = acc;
+        }
+        __syncthreads();
+    }
+    const double* res = (MODE == 2) ? buf0 : buf1;
+    for (int f = threadIdx.x; f < total; f += blockDim.x) {
+        int g, j;
+        if (lg.contiguous) { g = f / n; j = f - g * n; } else { j = f / G; g = f - j * G; }
+        if (g < nlines) aout[gbase + (i64)g * lg.gstride + (i64)j * lg.estride] = res[g * n + j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launch
+template <int LOG2M, int PAIRS>
+static void launch_blu(const DctPlan* p, const LineGeom& lg, i64 outer, const double* ain, double* a, int mode,
+                       const ScaleArgs& sa, cudaStream_t st)
+{
+    constexpr int M = 1 << LOG2M, TP = M / 8, G = 2 * PAIRS, NTHR = TP * PAIRS;
+    const size_t smem = (size_t)PAIRS * (M + M / 8) * sizeof(double2);
+    dim3 grid((unsigned)((lg.inner + G - 1) / G), (unsigned)outer);
+    static bool attr_set[3] = {false, false, false};
+#define BLU(MODE)                                                                                                     \
+    {                                                                                                                 \
+        if (!attr_set[MODE]) {                                                                                        \
+            cudaFuncSetAttribute(k_dct_bluestein<LOG2M, PAIRS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                 (int)smem);                                                                          \
+            attr_set[MODE] = true;                                                                                    \
+        }                                                                                                             \
+        k_dct_bluestein<LOG2M, PAIRS, MODE><<<grid, NTHR, smem, st>>>(lg, ain, a, p->w, p->bhat, p->tw, p->pw, p->ipw, sa); \
+    }
+    if (mode == 0) BLU(0) else if (mode == 1) BLU(1) else BLU(2)
+#undef BLU
+}
+
+static void launch_dct_axis(const DctPlan* p, LineGeom lg, i64 outer, const double* ain, double* a, int mode,
+                            const ScaleArgs& sa, cudaStream_t st)
+{
+    if (p->dense) {
+        const int n = p->n;
+        int G = 256 / n;
+        if (G < 1) G = 1;
+        if (!lg.contiguous && G < 4) G = 4;
+        if (G > 64) G = 64;
+        const size_t smem = (size_t)2 * G * n * sizeof(double);
+        dim3 grid((unsigned)((lg.inner + G - 1) / G), (unsigned)outer);
+        if (mode == 0) k_dct_dense<0><<<grid, 256, smem, st>>>(lg, G, ain, a, p->cmat, sa);
+        else if (mode == 1) k_dct_dense<1><<<grid, 256, smem, st>>>(lg, G, ain, a, p->cmat, sa);
+        else k_dct_dense<2><<<grid, 256, smem, st>>>(lg, G, ain, a, p->cmat, sa);
+        return;
+    }
+    switch (p->log2m) {
+        case 6: launch_blu<6, 32>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 7: launch_blu<7, 16>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 8: launch_blu<8, 8>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 9: launch_blu<9, 4>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 10: launch_blu<10, 2>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 11: launch_blu<11, 2>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 12: launch_blu<12, 2>(p, lg, outer, ain, a, mode, sa, st); break;
+        default: fprintf(stderr, "dotsocp: unsupported transform length %d\n", p->n); break;
+    }
+}
+
+static double* lam_table(int n)
+{
+    std::vector<double> v(n);
+    // (2*(n-1)^2) * (1 - cos(pi*k/n))   initialize_FFTkernel.m:6-8 (double arithmetic as in MATLAB)
+    for (int k = 0; k < n; k++) v[k] = (2.0 * (double)(n - 1) * (double)(n - 1)) * (1.0 - cos(M_PI * (double)k / (double)n));
+    return to_device(v);
+}
+
+PoissonPlan* poisson_plan_create(int nt, int nx, int ny)
+{
+    PoissonPlan* p = new PoissonPlan();
+    p->g = make_geo(nt, nx, ny);
+    p->py = dct_plan_create(ny);
+    p->px = dct_plan_create(nx);
+    p->pt = dct_plan_create(nt);
+    p->lam_t = lam_table(nt);
+    p->lam_x = lam_table(nx);
+    p->lam_y = lam_table(ny);
+    return p;
+}
+
+void poisson_plan_destroy(PoissonPlan* p)
+{
+    if (!p) return;
+    dct_plan_destroy(p->py); dct_plan_destroy(p->px); dct_plan_destroy(p->pt);
+    cudaFree(p->lam_t); cudaFree(p->lam_x); cudaFree(p->lam_y);
+    delete p;
+}
+
+static LineGeom geom_y(const Geo& g) { return LineGeom{g.ny, 1, (i64)g.ny, (i64)g.nt * g.nx, 0, 1}; }
+static LineGeom geom_x(const Geo& g)
+{
+    if (g.ny == 1) return LineGeom{g.nx, 1, (i64)g.nx, (i64)g.nt, 0, 1};   // 1-D variant: x lines are contiguous
+    return LineGeom{g.nx, (i64)g.ny, 1, (i64)g.ny, g.P, 0};
+}
+static LineGeom geom_t(const Geo& g) { return LineGeom{g.nt, g.P, 1, g.P, 0, 0}; }
+
+void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cudaStream_t st, double* launches)
+{
+    // first pass reads rhs and writes a (out of place), the rest works in place on a
+    const Geo& g = p->g;
+    ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, D2};
+    const i64 xo = (g.ny == 1) ? 1 : g.nt;
+    const double* src = rhs;
+    if (g.ny > 1) { launch_dct_axis(p->py, geom_y(g), 1, src, a, 0, sa, st); src = a; if (launches) *launches += 1; }
+    launch_dct_axis(p->px, geom_x(g), xo, src, a, 0, sa, st);
+    launch_dct_axis(p->pt, geom_t(g), 1, a, a, 2, sa, st);
+    launch_dct_axis(p->px, geom_x(g), xo, a, a, 1, sa, st);
+    if (launches) *launches += 3;
+    if (g.ny > 1) { launch_dct_axis(p->py, geom_y(g), 1, a, a, 1, sa, st); if (launches) *launches += 1; }
+}
+
+void poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches)
+{
+    const Geo& g = p->g;
+    ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, 1.0};
+    const int mode = inverse ? 1 : 0;
+    if (g.ny > 1) launch_dct_axis(p->py, geom_y(g), 1, a, a, mode, sa, st);
+    if (g.nx > 1) launch_dct_axis(p->px, geom_x(g), (g.ny == 1) ? 1 : g.nt, a, a, mode, sa, st);
+    if (g.nt > 1) launch_dct_axis(p->pt, geom_t(g), 1, a, a, mode, sa, st);
+    if (launches) *launches += 3;
+}
+
+}  // namespace dsocp

@@ -1,0 +1,211 @@
+"""Solver-level mirror of the reference's algorithms/*.m entry points, running on the GPU.
+
+    [runHist, sigma] = solver_socp_inPALM(var, opts, model)      socp/dot2d/algorithms/solver_socp_inPALM.m:1
+                       solver_socp_PALM / solver_socp_accADMM     socp/dot2d/algorithms/*.m
+                       solver_wsocp_inPALM / solver_wsocp_accADMM socp/wdot2d/algorithms/*.m
+                       (1-D) solver_socp_inPALM                   socp/dot1d/algorithms/solver_socp_inPALM.m:1
+
+Same argument meaning and side effects as the reference: ``var`` (phi, q, z, alpha, beta, cScale, dScale, D, E) is
+mutated in place, ``var.alpha``/``var.beta`` come back multiplied by sigma (:335-336), ``var.time`` carries the
+step-time table (:339-341), the returned sigma is un-rescaled (:357) and ``runHist`` has kkt/time/iter/pdGap/len
+(+ priVal/dualVal as extras).  ``var``/``model`` are any attribute containers (``types.SimpleNamespace`` works).
+
+``Session`` keeps the state resident in HBM (what the multilevel driver and the benchmark use).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+
+import numpy as np
+
+from ._lib import METHOD, VARIANT, HistBuffers, LevelOpts, LevelResult, check, lib, ptr
+
+TIME_NAMES = {
+    0: ["Step_1_1_FFT", "Step_1_2_ProjSOC", "Step_2_Q_Step", "Step_3_Multiplier", "KKT", "Total_Time"],
+    1: ["Step_1_Q_Step", "Step_2_1_FFT", "Step_2_2_ProjSOC", "Step_3_Q_Step", "Step_4_Multiplier", "KKT", "Total_Time"],
+    2: ["Step_1_Q_Step", "Step_2_Multiplier", "Step_3_1_FFT", "Step_3_2_ProjSOC", "KKT", "Interp", "Total_Time"],
+}
+METHOD_NAMES = {0: "Inexact Proximal ALM", 1: "Proximal ALM", 2: "Accelerated ADMM"}
+
+
+def _get(opts, name, default=None):
+    if isinstance(opts, dict):
+        return opts.get(name, default)
+    return getattr(opts, name, default)
+
+
+def grad_scalars(model):
+    """The three magnitudes of model.grad (already multiplied by D in InitialScaling): D*(1/ht), D*(1/hx), D*(1/hy).
+    The reference stores them in a sparse matrix (initialize.m:35-39,67-87); this path only needs the values."""
+    g = getattr(model, "grad", None)
+    if isinstance(g, (tuple, list)) and len(g) == 3:
+        return tuple(float(v) for v in g)
+    if g is not None and hasattr(g, "tocsr"):  # a scipy sparse matrix built like the reference's
+        nt, nx, ny = model.nt, model.nx, getattr(model, "ny", 1) or 1
+        L = (nt - 1) * nx * ny
+        nbx = nt * (nx - 1) * ny
+        g = g.tocsr()
+        gt = abs(g[0].data).max()
+        gx = abs(g[L].data).max()
+        gy = abs(g[L + nbx].data).max() if ny > 1 else 0.0
+        return float(gt), float(gx), float(gy)
+    raise ValueError("model.grad must be (grad_t, grad_x, grad_y) or the reference's sparse gradient")
+
+
+def make_level_opts(variant, method, var, opts, model):
+    nt, nx = int(model.nt), int(model.nx)
+    ny = 1 if variant == "dot1d" else int(model.ny)
+    gt, gx, gy = grad_scalars(model)
+    o = LevelOpts()
+    o.variant = VARIANT[variant]
+    o.method = METHOD[method]
+    o.nt, o.nx, o.ny = nt, nx, ny
+    o.maxit = int(_get(opts, "maxit"))
+    o.ifCheckStepByStep = 1 if _get(opts, "ifCheckStepByStep", False) else 0
+    o.scaling = 1 if _get(opts, "scaling", False) else 0
+    cpd = _get(opts, "checkPrimDualFeas", None)
+    o.checkPrimDualFeas = -1 if cpd is None else (1 if cpd else 0)
+    o.restart = int(_get(opts, "restart", 0) or 0)
+    o.tau = float(_get(opts, "tau", 1.0) or 1.0)
+    o.sigma = float(_get(opts, "sigma"))
+    o.tol = float(_get(opts, "tol"))
+    o.time_limit = float(_get(opts, "time_limit", 0) or 0)
+    o.rho = float(_get(opts, "rho", 0) or 0)
+    o.theta = float(_get(opts, "theta", 0) or 0)
+    o.cScale, o.dScale, o.D, o.E = float(var.cScale), float(var.dScale), float(var.D), float(var.E)
+    o.normc = float(model.normc)
+    o.normd = float(getattr(model, "normd", 0.0) or 0.0)
+    o.grad_t, o.grad_x, o.grad_y = gt, gx, gy
+    return o
+
+
+class Session:
+    """Device-resident state of one level (dotsocp_create / _upload / _run / _download / _destroy)."""
+
+    def __init__(self, variant, nt, nx, ny=1, rank=0, world=1, nccl_id=None):
+        self.variant = variant
+        self.nt, self.nx, self.ny = int(nt), int(nx), int(ny)
+        self.ncol = 6 if variant == "dot1d" else 10
+        self._h = C.c_void_p()
+        check(lib().dotsocp_create(C.byref(self._h), VARIANT[variant], self.nt, self.nx, self.ny, rank, world, nccl_id))
+        self.L = (self.nt - 1) * self.nx * self.ny
+        self.Q = self.L + self.nt * (self.nx - 1) * self.ny + self.nt * self.nx * (self.ny - 1)
+        self.N = self.nt * self.nx * self.ny
+
+    def close(self):
+        if self._h:
+            lib().dotsocp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, phi, q, z, alpha, beta, c, weight=None):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64) if a.ndim == 1 else np.asfortranarray(a, dtype=np.float64)
+        arrs = [f(np.asarray(a)) for a in (phi, q, z, alpha, beta, c)]
+        assert arrs[0].size == self.N and arrs[1].size == self.Q and arrs[3].size == self.Q and arrs[5].size == self.N
+        assert arrs[2].shape == (self.L, self.ncol) and arrs[4].shape == (self.L, self.ncol)
+        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        check(lib().dotsocp_upload(self._h, *[ptr(a) for a in arrs], ptr(w)))
+
+    def download(self):
+        phi = np.empty(self.N)
+        q = np.empty(self.Q)
+        alpha = np.empty(self.Q)
+        z = np.empty((self.L, self.ncol), order="F")
+        beta = np.empty((self.L, self.ncol), order="F")
+        check(lib().dotsocp_download(self._h, ptr(phi), ptr(q), ptr(z), ptr(alpha), ptr(beta)))
+        return phi, q, z, alpha, beta
+
+    def run(self, level_opts):
+        hb = HistBuffers(level_opts.maxit)
+        res = LevelResult()
+        check(lib().dotsocp_run(self._h, C.byref(level_opts), C.byref(hb.c), C.byref(res)))
+        return hb, res
+
+    # benchmark primitives -------------------------------------------------------------------------------------
+    def iter_begin(self, level_opts):
+        check(lib().dotsocp_iter_begin(self._h, C.byref(level_opts)))
+
+    def iterate(self, n, per_kernel=False):
+        ms = C.c_float()
+        k = (C.c_float * 4)()
+        check(lib().dotsocp_iterate(self._h, int(n), 0, C.byref(ms), k if per_kernel else None))
+        return (ms.value, list(k)) if per_kernel else ms.value
+
+    def iter_end(self):
+        check(lib().dotsocp_iter_end(self._h))
+
+    @property
+    def launches(self):
+        return lib().dotsocp_launch_count(self._h)
+
+
+def _finish(var, method_id, hb, res):
+    n = res.hist_len
+    runHist = SimpleNamespace(kkt=hb.kkt[:n].copy(), time=hb.time[:n].copy(), iter=hb.iter[:n].copy(),
+                              pdGap=hb.pdGap[:n].copy(), priVal=hb.priVal[:n].copy(), dualVal=hb.dualVal[:n].copy(), len=n)
+    names = TIME_NAMES[method_id]
+    var.time = {nm: res.times[i] for i, nm in enumerate(names)}
+    var.time["Iters"] = res.iters
+    var.name = METHOD_NAMES[method_id]
+    var.cScale, var.dScale, var.D, var.E = res.cScale, res.dScale, res.D, res.E
+    var.gpu_launches = res.gpu_launches
+    return runHist, res.sigma
+
+
+def _solve(variant, method, var, opts, model):
+    o = make_level_opts(variant, method, var, opts, model)
+    weight = getattr(model, "weight", None) if variant == "wdot2d" else None
+    if variant == "wdot2d" and weight is None:
+        raise ValueError("solver_wsocp_*: model.weight is required")
+    with Session(variant, o.nt, o.nx, o.ny) as s:
+        s.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c, weight)
+        hb, res = s.run(o)
+        var.phi, var.q, var.z, var.alpha, var.beta = s.download()
+    return _finish(var, o.method, hb, res)
+
+
+def _variant_of(model):
+    if getattr(model, "weight", None) is not None:
+        return "wdot2d"
+    return "dot1d" if (getattr(model, "ny", None) in (None, 1) or getattr(model, "dim", 2) == 1) else "dot2d"
+
+
+def solver_socp_inPALM(var, opts, model):
+    """socp/dot2d/algorithms/solver_socp_inPALM.m:1 and socp/dot1d/algorithms/solver_socp_inPALM.m:1
+    (ALG2 is this loop with opts.tau = 1, solver_dotsocp2d.m:133-137)."""
+    v = _variant_of(model)
+    if v == "wdot2d":
+        raise ValueError("use solver_wsocp_inPALM for weighted models")
+    return _solve(v, "inPALM", var, opts, model)
+
+
+def solver_wsocp_inPALM(var, opts, model):
+    """socp/wdot2d/algorithms/solver_wsocp_inPALM.m:1"""
+    return _solve("wdot2d", "inPALM", var, opts, model)
+
+
+def solver_socp_PALM(var, opts, model):
+    """socp/dot2d/algorithms/solver_socp_PALM.m:1"""
+    return _solve("dot2d", "PALM", var, opts, model)
+
+
+def solver_socp_accADMM(var, opts, model):
+    """socp/dot2d/algorithms/solver_socp_accADMM.m:1"""
+    return _solve("dot2d", "acc-ADMM", var, opts, model)
+
+
+def solver_wsocp_accADMM(var, opts, model):
+    """socp/wdot2d/algorithms/solver_wsocp_accADMM.m:1"""
+    return _solve("wdot2d", "acc-ADMM", var, opts, model)

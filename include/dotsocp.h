@@ -1,0 +1,152 @@
+/* dotsocp.h -- C ABI of libdotsocp.so, the B200 (sm_100a) implementation of DOTSOCP's iteration hot path.
+ *
+ * Everything here is plain C: pointers, sizes and POD structs; no torch / CUDA types cross the boundary.
+ * All arrays are FP64 in MATLAB column-major order (y fastest, then x, then t), exactly as the reference
+ * hands them to its own MEX kernels:
+ *     q, alpha, weight : [ q0 (nt-1,nx,ny) | bx (nt,nx-1,ny) | by (nt,nx,ny-1) ]      Q doubles
+ *     z, beta          : L x 10 column-major (L x 6 for the 1-D variant),  L = (nt-1)*nx*ny
+ *     phi, c           : N = nt*nx*ny doubles
+ * Unless stated otherwise pointers are HOST pointers; the library owns all device memory.
+ * Every function returns 0 on success, a negative DOTSOCP_E* code otherwise; dotsocp_last_error() gives text.
+ * There is NO CPU fallback: without a usable CUDA device every compute entry point fails with DOTSOCP_ENODEV.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   kernel level  (FFI the reference binds today: mexFunction of the pre-built MEX files)
+ *     dotsocp_mexBFd        <- mexBFd(z2,q,nt,nx,ny,scaleBF,scaleD)     socp/dot2d/algorithms/solver_socp_inPALM.m:133,187,212,242
+ *     dotsocp_mexBFdConj    <- mexBFdConj(q2,z,nt,nx,ny,scaleBF)        socp/dot2d/algorithms/solver_socp_inPALM.m:205,225 ; utils/jump_nextLevel.m:16
+ *     dotsocp_mexProjSoc    <- mexProjSoc(out,in)                        socp/dot2d/algorithms/solver_socp_inPALM.m:199,240
+ *     dotsocp_mexBFd1d      <- mexBFd1d(z,q,nt,nx,scale,dFactor)         socp/dot1d/algorithms/solver_socp_inPALM.m:132,186,211,241
+ *     dotsocp_mexBFdConj1d  <- mexBFdConj1d(q,z,nt,nx,scale)             socp/dot1d/algorithms/solver_socp_inPALM.m:204,224
+ *     dotsocp_poisson       <- oper_poisson3dim(D^2*initialize_FFTkernel(nt,nx,ny), rhs)   socp/dot2d/utils/oper_poisson3dim.m:4,
+ *                              initialize_FFTkernel.m:6-15 ; 1-D: socp/dot1d/utils/oper_poisson.m:4  (ny = 1)
+ *   solver level  (the boundary the north star names)
+ *     dotsocp_solve_level   <- [runHist,sigma] = solver_socp_inPALM(var,opts,model)   socp/dot2d/algorithms/solver_socp_inPALM.m:1
+ *                              solver_socp_PALM.m:1, solver_socp_accADMM.m:1,
+ *                              socp/wdot2d/algorithms/solver_wsocp_inPALM.m:1, solver_wsocp_accADMM.m:1,
+ *                              socp/dot1d/algorithms/solver_socp_inPALM.m:1
+ *   device-resident session (same loop, state stays in HBM; used by the multilevel driver and the benchmark)
+ *     dotsocp_create / _upload / _run / _iterate / _download / _destroy
+ */
+#ifndef DOTSOCP_H
+#define DOTSOCP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOTSOCP_OK        0
+#define DOTSOCP_EINVAL   -1   /* bad argument (sizes, NULL pointer, unknown variant/method) */
+#define DOTSOCP_ENODEV   -2   /* no CUDA device / driver: the library never falls back to the CPU */
+#define DOTSOCP_ECUDA    -3   /* a CUDA runtime call or kernel failed */
+#define DOTSOCP_ENOMEM   -4   /* device or host allocation failed */
+#define DOTSOCP_ENCCL    -5   /* NCCL failure (multi-GPU sessions) */
+#define DOTSOCP_ESTATE   -6   /* call sequence error (e.g. run before upload) */
+
+/* variants: which reference sub-tree the call mirrors */
+#define DOTSOCP_VARIANT_DOT2D   0   /* socp/dot2d  */
+#define DOTSOCP_VARIANT_WDOT2D  1   /* socp/wdot2d (needs weight) */
+#define DOTSOCP_VARIANT_DOT1D   2   /* socp/dot1d  (ny must be 1, z/beta have 6 columns at the boundary) */
+
+/* methods: which algorithms/*.m loop */
+#define DOTSOCP_METHOD_INPALM   0   /* solver_*socp_inPALM.m ; "ALG2" is the same loop with tau = 1 */
+#define DOTSOCP_METHOD_PALM     1   /* solver_socp_PALM.m (dot2d only) */
+#define DOTSOCP_METHOD_ACCADMM  2   /* solver_*socp_accADMM.m (dot2d, wdot2d) */
+
+#define DOTSOCP_NTIMES 8
+
+/* opts/var/model scalars of one level solve -- field meaning follows the reference names exactly */
+typedef struct dotsocp_level_opts {
+    int32_t variant;            /* DOTSOCP_VARIANT_*                                                   */
+    int32_t method;             /* DOTSOCP_METHOD_*                                                    */
+    int32_t nt, nx, ny;         /* model.nt, model.nx, model.ny (nodes); ny = 1 for the 1-D variant     */
+    int32_t maxit;              /* opts.maxit                                                          */
+    int32_t ifCheckStepByStep;  /* opts.ifCheckStepByStep                                              */
+    int32_t scaling;            /* opts.scaling (rescale = 1 when non-zero), solver_socp_inPALM.m:64-68 */
+    int32_t checkPrimDualFeas;  /* opts.checkPrimDualFeas; -1 = absent (default true, weighted: false)  */
+    int32_t restart;            /* accADMM opts.restart; <=0 = absent (100)                             */
+    double  tau;                /* opts.tau (inPALM/PALM); ignored by accADMM                           */
+    double  sigma;              /* opts.sigma                                                          */
+    double  tol;                /* opts.tol                                                            */
+    double  time_limit;         /* opts.time_limit; <=0 = absent (3600 s)                               */
+    double  rho;                /* accADMM opts.rho;   <=0 = absent (2)                                 */
+    double  theta;              /* accADMM opts.theta; <=0 = absent (2 => Halpern)                      */
+    double  cScale, dScale, D, E;   /* var.cScale, var.dScale, var.D, var.E  (InitialScaling)          */
+    double  normc, normd;       /* model.normc, model.normd                                            */
+    double  grad_t, grad_x, grad_y; /* the three distinct magnitudes of model.grad AFTER InitialScaling:
+                                       D*(1/ht), D*(1/hx), D*(1/hy)  (initialize.m:67-87, solver_dotsocp2d.m:338) */
+} dotsocp_level_opts;
+
+/* what the loop returns besides the mutated arrays */
+typedef struct dotsocp_level_result {
+    int32_t iters;              /* `it` at exit (var.time.Iters)                                        */
+    int32_t hist_len;           /* runHist.len                                                         */
+    double  sigma;              /* returned sigma (= sigma / sigmaScale, solver_socp_inPALM.m:357)      */
+    double  cScale, dScale, D, E;   /* var.* after rescaling (:344-347)                                 */
+    double  times[DOTSOCP_NTIMES];  /* seconds, device-measured; order per method:
+                                       inPALM : FFT, ProjSOC, Q_Step, Multiplier, KKT, Total, 0, 0      (:339-340)
+                                       PALM   : Q_Step(1), FFT, ProjSOC, Q_Step(3), Multiplier, KKT, Total, 0
+                                       accADMM: Q_Step, Multiplier, FFT, ProjSOC, KKT, Interp, Total, 0
+                                       The fused kernels do not separate ProjSOC from the multiplier step; the fused
+                                       time is booked under the step that dominates it.             */
+    double  gpu_launches;       /* number of kernels launched by this call                              */
+} dotsocp_level_result;
+
+/* runHist buffers, caller-allocated with room for `cap` checks (cap = maxit is always enough) */
+typedef struct dotsocp_hist {
+    int32_t cap;
+    double *kkt;                /* cap x 7, ROW-major here: kkt[i*7 + j] = runHist.kkt(i+1, j+1)       */
+    double *time;               /* cap                                                                 */
+    double *iter;               /* cap                                                                 */
+    double *pdGap;              /* cap                                                                 */
+    double *priVal;             /* cap -- extra: priVal of solver_socp_inPALM.m:265 (not in the reference struct) */
+    double *dualVal;            /* cap -- extra: dualVal of :266                                       */
+} dotsocp_hist;
+
+const char *dotsocp_last_error(void);
+int  dotsocp_version(void);
+int  dotsocp_device_count(void);          /* >= 0, or DOTSOCP_ENODEV */
+int  dotsocp_set_device(int device);
+
+/* ------------------------------------------------------------------ kernel level (host buffers, in place into arg 1) */
+int dotsocp_mexBFd(double *z2, const double *q, int nt, int nx, int ny, double scaleBF, double scaleD);
+int dotsocp_mexBFdConj(double *q2, const double *z, int nt, int nx, int ny, double scaleBF);
+int dotsocp_mexProjSoc(double *out, const double *in, int64_t M, int N);
+int dotsocp_mexBFd1d(double *z, const double *q, int nt, int nx, double scale, double dFactor);
+int dotsocp_mexBFdConj1d(double *q, const double *z, int nt, int nx, double scale);
+/* phi = idctn( dctn(rhs) ./ (D^2 * kernel) ), Neumann eigenvalues, zero mode := 1 */
+int dotsocp_poisson(double *phi, const double *rhs, int nt, int nx, int ny, double D);
+/* orthonormal DCT-II (inverse != 0: its inverse) along every axis of a (nt,nx,ny) array: mirt_dctn / mirt_idctn */
+int dotsocp_dctn(double *a, int nt, int nx, int ny, int inverse);
+
+/* ------------------------------------------------------------------ solver level (host buffers, mutated in place) */
+int dotsocp_solve_level(const dotsocp_level_opts *opts,
+                        double *phi, double *q, double *z, double *alpha, double *beta,
+                        const double *c, const double *weight /* NULL unless WDOT2D */,
+                        dotsocp_hist *hist, dotsocp_level_result *res);
+
+/* ------------------------------------------------------------------ device-resident session */
+typedef struct dotsocp_ctx dotsocp_ctx;
+/* world > 1 : time-slab partition over `world` ranks (one process per GPU); nccl_id is the 128-byte
+ * ncclUniqueId produced by dotsocp_nccl_unique_id() on rank 0 and broadcast by the caller.            */
+int  dotsocp_nccl_unique_id(char id128[128]);
+int  dotsocp_create(dotsocp_ctx **ctx, int variant, int nt, int nx, int ny, int rank, int world, const char *nccl_id);
+void dotsocp_destroy(dotsocp_ctx *ctx);
+/* full (global) host arrays in, each rank keeps its slab */
+int  dotsocp_upload(dotsocp_ctx *ctx, const double *phi, const double *q, const double *z,
+                    const double *alpha, const double *beta, const double *c, const double *weight);
+int  dotsocp_download(dotsocp_ctx *ctx, double *phi, double *q, double *z, double *alpha, double *beta);
+/* the reference loop on the resident state (sigma folding at entry, un-folding at exit, like :102-104, :335-336) */
+int  dotsocp_run(dotsocp_ctx *ctx, const dotsocp_level_opts *opts, dotsocp_hist *hist, dotsocp_level_result *res);
+/* benchmark primitive: begin (sigma folding + prologue), n plain iterations (no KKT), elapsed device ms */
+int  dotsocp_iter_begin(dotsocp_ctx *ctx, const dotsocp_level_opts *opts);
+int  dotsocp_iterate(dotsocp_ctx *ctx, int n_iters, int with_kkt_every, float *elapsed_ms, float *ms_by_kernel /* [4] or NULL */);
+int  dotsocp_iter_end(dotsocp_ctx *ctx);
+/* number of kernels launched by this context since creation */
+double dotsocp_launch_count(const dotsocp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOTSOCP_H */

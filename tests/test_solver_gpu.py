@@ -1,0 +1,125 @@
+"""GPU parity of the solver-level path (C ABI -> CUDA) against the CPU oracle on the same inputs.
+
+Tolerances are the north star's: objective within 1e-6 relative, KKT residual history within 1e-8 absolute, and the
+same iteration count (the +-2 % allowance is not used at these sizes: counts must match exactly)."""
+import numpy as np
+import pytest
+
+from oracle import dotsocp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o, dim=2):
+    assert out_g.level_iters == out_o.level_iters, (out_g.level_iters, out_o.level_iters)
+    assert ML_g.len == ML_o.len
+    assert np.array_equal(ML_g.iter, ML_o.iter)
+    assert np.abs(ML_g.kkt - ML_o.kkt).max() < 1e-8
+    assert np.abs(ML_g.pdGap - ML_o.pdGap).max() < 1e-8
+    assert abs(rh_g.priVal[-1] - rh_o.priVal[-1]) <= 1e-6 * abs(rh_o.priVal[-1])
+    assert abs(rh_g.dualVal[-1] - rh_o.dualVal[-1]) <= 1e-6 * abs(rh_o.dualVal[-1])
+    assert abs(out_g.sigma - out_o.sigma) <= 1e-9 * abs(out_o.sigma)
+    assert np.abs(out_g.rho - out_o.rho).max() < 1e-6
+    assert np.abs(out_g.Ex - out_o.Ex).max() < 1e-6
+    from dotsocp_b200 import driver
+    wg, wo = driver.w2_cost(out_g, dim), O.w2_cost(out_o, dim)
+    assert abs(wg - wo) <= 1e-6 * abs(wo)
+    assert out_g.massOK
+
+
+@pytest.mark.parametrize("problem,n,nt,levelN,method", [
+    ("example1", 17, 9, 1, "inPALM"),
+    ("example1", 33, 17, 2, "inPALM"),
+    ("example2", 33, 17, 2, "ALG2"),
+    ("circle", 33, 17, 1, "inPALM"),
+    ("example1", 65, 33, 3, "inPALM"),      # BASELINE config 2
+])
+def test_dot2d_multilevel_parity(gpu, problem, n, nt, levelN, method):
+    import dotsocp_b200 as dp
+    rho0, rho1 = O.get_example2d(problem, n, n)
+    opts = {"tol": 1e-4, "maxit": 3000}
+    out_g, _, ML_g, rh_g = dp.solver_dotsocp2d(rho0, rho1, nt, levelN, opts, method)
+    out_o, _, ML_o, rh_o = O.solver_dotsocp2d(rho0, rho1, nt, levelN, opts, method, workers=4)
+    _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o)
+    assert out_g.gpu_launches > 0
+
+
+def test_dot2d_rectangular_grid(gpu):
+    """nx != ny, single level (the reference's 2-D down-sampling assumes square grids)."""
+    import dotsocp_b200 as dp
+    rho0, rho1 = O.get_example2d("example2", 41, 29)      # MATLAB (ny, nx) = (29, 41)
+    opts = {"tol": 1e-4, "maxit": 600}
+    out_g, _, ML_g, rh_g = dp.solver_dotsocp2d(rho0, rho1, 13, 1, opts, "inPALM")
+    out_o, _, ML_o, rh_o = O.solver_dotsocp2d(rho0, rho1, 13, 1, opts, "inPALM")
+    _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o)
+
+
+def test_wdot2d_weighted_parity(gpu):
+    import dotsocp_b200 as dp
+    n, nt = 33, 17
+    rho0, rho1 = O.get_example2d("example1", n, n)
+    w = O.gene_weight_circle(nt, n, n)
+    opts = {"tol": 1e-3, "maxit": 10000, "weight": w}
+    out_g, _, ML_g, rh_g = dp.solver_wdotsocp2d(rho0, rho1, nt, 2, opts, "inPALM")
+    out_o, _, ML_o, rh_o = O.solver_wdotsocp2d(rho0, rho1, nt, 2, opts, "inPALM")
+    _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o)
+
+
+def test_wdot2d_barrier_parity(gpu):
+    import dotsocp_b200 as dp
+    n, nt = 33, 17
+    barrier = O.gene_barrier_of_love_heart()
+    rho0, rho1 = O.gene_exampleLoveHeart(n, n)
+    rho0, rho1 = O._normalize2d(rho0, rho1, n, n)
+    w = O.get_weight_by_barrier(n, n, nt, barrier)
+    rho0, rho1, _ = O.ensure_barrier_validity(rho0, rho1, barrier)
+    opts = {"tol": 1e-3, "maxit": 3000, "weight": w}
+    out_g, _, ML_g, rh_g = dp.solver_wdotsocp2d(rho0, rho1, nt, 2, opts, "inPALM", barrier)
+    out_o, _, ML_o, rh_o = O.solver_wdotsocp2d(rho0, rho1, nt, 2, opts, "inPALM", barrier)
+    _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o)
+
+
+@pytest.mark.parametrize("nx,nt,levelN,tol", [(129, 9, 1, 1e-4), (257, 17, 2, 1e-5)])
+def test_dot1d_parity(gpu, nx, nt, levelN, tol):
+    import dotsocp_b200 as dp
+    rho0, rho1 = O.get_example1d("gaussian", nx)
+    opts = {"tol": tol, "maxit": 3000}
+    out_g, _, ML_g, rh_g = dp.solver_dotsocp1d(rho0, rho1, nt, levelN, opts, "inPALM")
+    out_o, _, ML_o, rh_o = O.solver_dotsocp1d(rho0, rho1, nt, levelN, opts, "inPALM")
+    _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o, dim=1)
+
+
+def test_level_solver_mirrors_reference_side_effects(gpu):
+    """solver_socp_inPALM(var, opts, model): var mutated in place, alpha/beta returned times sigma, time table filled."""
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import driver
+    rho0, rho1 = O.get_example2d("example1", 17, 17)
+    var, model = driver.initialize(rho0, rho1, 9)
+    driver.InitialScaling(var, model, True, None, "dot2d")
+    vo, mo = O.initialize2d(rho0, rho1, 9)
+    O.InitialScaling(vo, mo, True, None, "dot2d")
+    opts = {"tol": 1e-4, "maxit": 25, "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": True, "scaling": True}
+    rh_g, sg = dp.solver_socp_inPALM(var, opts, model)
+    rh_o, so = O.solver_socp_inPALM(vo, opts, mo)
+    assert rh_g.len == rh_o.len == 25            # step-by-step checks: one history row per iteration
+    assert np.abs(rh_g.kkt - rh_o.kkt).max() < 1e-9
+    assert abs(sg - so) <= 1e-12 * abs(so)
+    for name in ("phi", "q", "alpha"):
+        assert np.abs(getattr(var, name) - getattr(vo, name)).max() < 1e-9, name
+    assert np.abs(var.z - vo.z).max() < 1e-9 and np.abs(var.beta - vo.beta).max() < 1e-9
+    assert set(["Step_1_1_FFT", "Step_1_2_ProjSOC", "Step_2_Q_Step", "Step_3_Multiplier", "KKT", "Total_Time", "Iters"]) <= set(var.time)
+    assert (var.cScale, var.dScale) == pytest.approx((vo.cScale, vo.dScale), rel=1e-12)
+
+
+def test_error_behaviour(gpu):
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import _lib
+    rho0, rho1 = O.get_example2d("example1", 9, 9)
+    with pytest.raises(ValueError):
+        dp.solver_dotsocp2d(rho0, rho1, 5, 1, {"tol": 1e-3}, "nonsense")
+    with pytest.raises(ValueError):
+        dp.solver_dotsocp2d(rho0, rho1, 5, 0, {"tol": 1e-3}, "inPALM")
+    with pytest.raises(_lib.DotsocpError):
+        dp.Session("dot1d", 5, 9, 3)             # 1-D variant with ny != 1
+    with pytest.raises(_lib.DotsocpError):
+        dp.Session("dot2d", 1, 9, 9)
