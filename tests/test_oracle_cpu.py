@@ -1,0 +1,199 @@
+"""CPU tests of the oracle itself: golden vectors from the reference's genuine MEX binaries, invariants of SURVEY.md §4,
+and the self-generated solver goldens.  No GPU needed."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.fft as sfft
+
+from oracle import dotsocp_oracle as O
+from oracle import kernels as K
+from oracle import refmex
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+BACKENDS = ["numpy"] + (["c"] if K.c_available() else []) + (["ref"] if refmex.available() else [])
+
+
+def same_bits(a, b):
+    return np.array_equal(np.asarray(a).ravel(order="K").view(np.uint64), np.asarray(b).ravel(order="K").view(np.uint64))
+
+
+@pytest.fixture(scope="module")
+def gk():
+    return np.load(os.path.join(GOLD, "kernels.npz"))
+
+
+def test_c_restatement_is_built(built):
+    assert K.c_available()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_kernels_match_reference_binaries_bit_for_bit(gk, backend):
+    for i in range(4):
+        nt, nx, ny = [int(v) for v in gk[f"g{i}_dims"]]
+        S, DF = float(gk[f"g{i}_S"]), float(gk[f"g{i}_DF"])
+        z2 = np.full(gk[f"g{i}_z2"].shape, 0.25, order="F")
+        K.mexBFd(z2, gk[f"g{i}_q"], nt, nx, ny, S, DF, backend=backend)
+        assert same_bits(z2, np.asfortranarray(gk[f"g{i}_z2"]))
+        q2 = np.zeros(gk[f"g{i}_q2"].shape)
+        K.mexBFdConj(q2, np.asfortranarray(gk[f"g{i}_z"]), nt, nx, ny, S, backend=backend)
+        assert same_bits(q2, gk[f"g{i}_q2"])
+    for i in range(6):
+        v = np.asfortranarray(gk[f"p{i}_in"])
+        p = np.zeros(v.shape, order="F")
+        K.mexProjSoc(p, v, backend=backend)
+        assert same_bits(p, np.asfortranarray(gk[f"p{i}_out"]))
+    for i in range(3):
+        nt, nx = [int(v) for v in gk[f"h{i}_dims"]]
+        S, DF = float(gk[f"h{i}_S"]), float(gk[f"h{i}_DF"])
+        z = np.full(gk[f"h{i}_z"].shape, -0.5, order="F")
+        K.mexBFd1d(z, gk[f"h{i}_q"], nt, nx, S, DF, backend=backend)
+        assert same_bits(z, np.asfortranarray(gk[f"h{i}_z"]))
+        q2 = np.zeros(gk[f"h{i}_q2"].shape)
+        K.mexBFdConj1d(q2, np.asfortranarray(gk[f"h{i}_zin"]), nt, nx, S, backend=backend)
+        assert same_bits(q2, gk[f"h{i}_q2"])
+
+
+def test_projection_known_answers():
+    """black-box probes of the binary recorded in SURVEY.md §8a3"""
+    for vin, vout in [((1, 0, 0), (1, 0, 0)), ((-1, 0, 0), (0, 0, 0)), ((0, 3, 4), (2.5, 1.5, 2.0))]:
+        v = np.asfortranarray(np.array([vin, vin], dtype=float))
+        p = np.zeros_like(v, order="F")
+        K.mexProjSoc(p, v, backend="numpy")
+        assert np.array_equal(p[0], np.array(vout, dtype=float))
+    v = np.zeros((2, 3), order="F")
+    p = np.zeros_like(v, order="F")
+    K.mexProjSoc(p, v, backend="numpy")
+    assert np.isnan(p).all()                         # (0,0,0) -> NaN row (0/0), like the binary
+
+
+def test_probe_dump_of_survey_A1():
+    """nt=3,nx=3,ny=4, q=1..75, S=sqrt2, DF=100: first row 98.6 0 25 0 33 0 49 0 58 101.4"""
+    nt, nx, ny = 3, 3, 4
+    L, nbx, nby = K.sizes2d(nt, nx, ny)
+    q = np.arange(1, L + nbx + nby + 1, dtype=float)
+    z = np.zeros((L, 10), order="F")
+    K.mexBFd(z, q, nt, nx, ny, np.sqrt(2), 100.0, backend="numpy")
+    assert np.allclose(z[0], [100 - np.sqrt(2), 0, 25, 0, 33, 0, 49, 0, 58, 100 + np.sqrt(2)], atol=1e-12)
+
+
+@pytest.mark.parametrize("nt,nx,ny", [(3, 3, 4), (5, 6, 4), (4, 7, 1)])
+def test_adjointness_and_oper_q_diagonal(nt, nx, ny):
+    rng = np.random.default_rng(0)
+    L, nbx, nby = K.sizes2d(nt, nx, ny)
+    Q = L + nbx + nby
+    S = 0.8
+    q = rng.standard_normal(Q)
+    z = np.asfortranarray(rng.standard_normal((L, 10)))
+    if ny == 1:
+        z[:, 5:9] = 0
+    bfq = np.zeros((L, 10), order="F")
+    K.mexBFd(bfq, q, nt, nx, ny, S, 0.0, backend="numpy")
+    adj = np.zeros(Q)
+    K.mexBFdConj(adj, z, nt, nx, ny, S, backend="numpy")
+    assert abs(np.vdot(bfq, z) - np.dot(q, adj)) < 1e-12 * (1 + abs(np.dot(q, adj)))
+    if ny > 1:
+        # diag(I + s^2 (BF)^* BF) == oper_q  (probe each coordinate direction through the quadratic form)
+        d = O.oper_q2d(ny, nx, nt, 1.0, S)           # D = 1, E = S  => (E/D)^2 = S^2
+        for _ in range(20):
+            k = rng.integers(Q)
+            e = np.zeros(Q); e[k] = 1.0
+            b = np.zeros((L, 10), order="F")
+            K.mexBFd(b, e, nt, nx, ny, S, 0.0, backend="numpy")
+            assert abs(1 + np.vdot(b, b) - d[k]) < 1e-12
+
+
+def test_dct_is_orthonormal_dct2_and_poisson_inverts_AtA():
+    rng = np.random.default_rng(1)
+    nt, nx, ny = 5, 9, 7
+    a = rng.standard_normal((nt, nx, ny))
+    assert np.allclose(sfft.idctn(sfft.dctn(a, type=2, norm="ortho"), type=2, norm="ortho"), a)
+    A = O.gene_grad2d(nt, nx, ny)
+    rhs = rng.standard_normal(nt * nx * ny)
+    rhs -= rhs.mean()
+    phi = O.oper_poisson(O.initialize_FFTkernel(nt, nx, ny), rhs)
+    assert np.abs(A.T @ (A @ phi) - rhs).max() < 1e-10
+    assert abs(phi.mean()) < 1e-12                     # DC convention: kernel(0)=1 => mean(phi) = mean(rhs)
+
+
+def test_sigma_rule_and_schedule():
+    s, f = O.adjust_lagrangianParam(1.0, 3.0, O.UPDATE_RULE)
+    assert (s, f) == (1.28, 1.28)
+    s, f = O.adjust_lagrangianParam(1.0, 1 / 60.0, O.UPDATE_RULE)
+    assert s == 0.5 and f == 0.5
+    s, f = O.adjust_lagrangianParam(900.0, 100.0, O.UPDATE_RULE)
+    assert s == 1e3 and abs(f - 1e3 / 900) < 1e-15     # clamp to [1e-3, 1e3]
+    s, f = O.adjust_lagrangianParam(2.0, 1.05, O.UPDATE_RULE)
+    assert (s, f) == (2.0, 1)
+    checks = []
+    last = -np.inf
+    for it in range(1, 700):
+        if O.IfAdjustSigma(it, last):
+            checks.append(it)
+            last = it
+    assert checks[:8] == [1, 4, 7, 10, 13, 16, 19, 25]
+    assert all(b - a == 40 for a, b in zip(checks[-3:], checks[-2:]))
+
+
+def test_level_transfer_shapes_and_consistency():
+    rho0, rho1 = O.get_example2d("example1", 9, 9)
+    var, model = O.initialize2d(rho0, rho1, 5)
+    rng = np.random.default_rng(2)
+    var.beta = np.asfortranarray(rng.standard_normal(var.beta.shape))
+    r0, r1 = O.get_example2d("example1", 17, 17)
+    phi_c = var.phi.copy()                            # interpolate() mutates the handle in place, like the reference
+    v2, m2 = O.jump_nextLevel(var, model, r0, r1, 9)
+    assert v2.phi.size == 9 * 17 * 17 and v2.beta.shape == (8 * 17 * 17, 10)
+    # phi was the exact quadratic (x^2+y^2)/2 on the coarse grid: linear interpolation keeps the nodal values
+    assert np.allclose(v2.phi.reshape(9, 17, 17)[::2, ::2, ::2], phi_c.reshape(5, 9, 9))
+    assert np.allclose(v2.q, m2.grad @ v2.phi)
+    d = O.downSample_phi2d(np.ones((17, 17)))
+    assert d.shape == (9, 9) and np.allclose(d, 1.0)
+    w = O.gene_weight_circle(9, 17, 17)
+    wc = O.downSample_q(9, 17, 17, w)
+    assert wc.size == K.sizes2d(5, 9, 9)[0] + sum(K.sizes2d(5, 9, 9)[1:]) and wc.min() > 0
+    assert np.allclose(O.downSample_barrier(9, 17, 17, np.full(w.size, 3.0)), 3.0)
+
+
+with open(os.path.join(GOLD, "solver.json")) as _f:
+    SOLVER_GOLD = json.load(_f)
+
+
+def _run_case(name):
+    if name.startswith("dot2d_example1_17x17x9_L2_inPALM"):
+        rho0, rho1 = O.get_example2d("example1", 17, 17)
+        return O.solver_dotsocp2d(rho0, rho1, 9, 2, {"tol": 1e-4, "maxit": 3000}, "inPALM"), 2
+    if name.startswith("dot2d_example1_17x17x9_L1_accADMM"):
+        rho0, rho1 = O.get_example2d("example1", 17, 17)
+        return O.solver_dotsocp2d(rho0, rho1, 9, 1, {"tol": 1e-4, "maxit": 3000}, "acc-ADMM"), 2
+    if name.startswith("dot2d_example1_17x17x9_L1_PALM"):
+        rho0, rho1 = O.get_example2d("example1", 17, 17)
+        return O.solver_dotsocp2d(rho0, rho1, 9, 1, {"tol": 1e-4, "maxit": 3000}, "PALM"), 2
+    if name.startswith("wdot2d"):
+        rho0, rho1 = O.get_example2d("example1", 17, 17)
+        w = O.gene_weight_circle(9, 17, 17)
+        return O.solver_wdotsocp2d(rho0, rho1, 9, 2, {"tol": 1e-3, "maxit": 10000, "weight": w}, "inPALM"), 2
+    if name.startswith("dot1d"):
+        rho0, rho1 = O.get_example1d("gaussian", 129)
+        return O.solver_dotsocp1d(rho0, rho1, 9, 2, {"tol": 1e-5, "maxit": 3000}, "inPALM"), 1
+    return None, None
+
+
+@pytest.mark.parametrize("case", [c for c in SOLVER_GOLD if "33x33" not in c["name"]], ids=lambda c: c["name"])
+def test_oracle_solver_reproduces_goldens(case):
+    res, dim = _run_case(case["name"])
+    out, _, ML, rh = res
+    assert [int(v) for v in out.level_iters] == case["level_iters"]
+    assert ML.iter.tolist() == case["hist_iter"]
+    assert np.abs(ML.kkt - np.array(case["kkt"])).max() < 1e-10
+    assert abs(rh.priVal[-1] - case["priVal"]) < 1e-10
+    assert abs(O.w2_cost(out, dim) - case["w2"]) < 1e-9
+    assert out.massOK and abs(out.sumRho - 1).max() < 1e-2
+
+
+def test_closed_form_sanity_1d_gaussian():
+    """W2^2/2 between N(0.3, 0.01) and N(0.7, 0.0025) is ((0.4)^2 + (0.1-0.05)^2)/2 = 0.08125 in the continuum; the
+    discrete objective on the demo grid is 0.0786 -- coarse grid here, loose band."""
+    c = [c for c in SOLVER_GOLD if c["name"].startswith("dot1d")][0]
+    assert 0.06 < c["priVal"] < 0.085
