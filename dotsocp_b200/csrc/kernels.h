@@ -7,6 +7,7 @@ namespace dsocp {
 // ---- standalone counterparts of the reference's MEX kernels (device pointers) -------------------------------
 void launch_bfd(const Geo& g, double S, double DF, const double* q, double* z, cudaStream_t st);
 void launch_bfdconj(const Geo& g, double S, const double* z, double* q2, cudaStream_t st);
+void launch_bfdconj_sum(const Geo& g, double S, const double* za, const double* zb, double* q2, cudaStream_t st);
 void launch_projsoc(i64 M, int N, const double* in, double* out, cudaStream_t st);
 
 // ---- fused iteration kernels --------------------------------------------------------------------------------
@@ -28,7 +29,14 @@ struct UpdateArgs {
 };
 // q_new = ((A phi + alpha) + q2) .* diagQInv ; alpha += tau (A phi - q_new)      (solver_socp_inPALM.m:204-214)
 // acc: alpha = (alpha + A phi) - q_new                                            (solver_socp_accADMM.m:237)
-void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st);
+// tmpq_in != NULL: take A*phi from that buffer instead of phi; tmpq_out != NULL: also store A*phi; upd_alpha=false: q only
+void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st, const double* tmpq_in = nullptr,
+                  double* tmpq_out = nullptr, bool upd_alpha = true);
+void launch_rhs(const Geo& g, const IterScal& sc, bool weighted, const double* q, const double* alpha, const double* weight,
+                const double* c0, const double* c1, double* rhs, cudaStream_t st);
+// mode 0: beta += tau (z - z2(q)) ; mode 1: beta = (beta + z) - z2(q), z = Pi_Q(z2(q) - beta) ; mode 2: z = d + BF q
+void launch_cells_update(const Geo& g, const IterScal& sc, bool one_d, int mode, const double* q, double* z, double* beta,
+                         cudaStream_t st);
 // z = Pi_Q(d + BF q_old - beta) ; beta += tau (z - (d + BF q_new)) ; then q2, rhs of the next iteration.
 // update=false ("prologue"): no multiplier step, only q2/rhs from the current (q_new, alpha, beta).
 void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st);

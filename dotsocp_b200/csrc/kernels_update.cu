@@ -163,9 +163,12 @@ void launch_bfd(const Geo& g, double S, double DF, const double* q, double* z, c
 // Standalone mexBFdConj: one thread per node; q0, bx, by entries owned by the node.   mexBFdConj.mexa64 @0x1120/1160/1310
 // add order ((z1[t,x+1] + z2[t,x]) + z3[t-1,x+1]) + z4[t-1,x]
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bfdconj(Geo g, double S, double SF, const double* __restrict__ z,
-                                                 double* __restrict__ q2)
+template <bool ADD2>
+__global__ void __launch_bounds__(256) k_bfdconj(Geo g, double S, double SF, const double* __restrict__ za,
+                                                 const double* __restrict__ zb, double* __restrict__ q2)
 {
+    // ADD2: the argument is the elementwise sum za + zb (mexBFdConj(q2, z + beta, ...), solver_socp_accADMM.m:229)
+    auto Z = [&](i64 idx) -> double { return ADD2 ? dadd(za[idx], zb[idx]) : za[idx]; };
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
     if (p >= g.P) return;
@@ -174,30 +177,30 @@ __global__ void __launch_bounds__(256) k_bfdconj(Geo g, double S, double SF, con
     const i64 cu = (i64)t * g.P + p;         // cell (t,x,y)
     const i64 cd = cu - g.P;                 // cell (t-1,x,y)
     const bool up = t < g.nt - 1, dn = t > 0;
-    if (up) q2[cu] = dmul(dsub(z[9 * L + cu], z[cu]), S);
+    if (up) q2[cu] = dmul(dsub(Z(9 * L + cu), Z(cu)), S);
     if (x < g.nx - 1) {
         double s;
         if (!dn)
-            s = dadd(z[1 * L + cu + g.ny], z[2 * L + cu]);
+            s = dadd(Z(1 * L + cu + g.ny), Z(2 * L + cu));
         else if (!up)
-            s = dadd(z[3 * L + cd + g.ny], z[4 * L + cd]);
+            s = dadd(Z(3 * L + cd + g.ny), Z(4 * L + cd));
         else {
-            s = dadd(z[1 * L + cu + g.ny], z[2 * L + cu]);
-            s = dadd(s, z[3 * L + cd + g.ny]);
-            s = dadd(s, z[4 * L + cd]);
+            s = dadd(Z(1 * L + cu + g.ny), Z(2 * L + cu));
+            s = dadd(s, Z(3 * L + cd + g.ny));
+            s = dadd(s, Z(4 * L + cd));
         }
         q2[L + (i64)t * g.PBX + (i64)x * g.ny + y] = dmul(s, SF);
     }
     if (y < g.ny - 1) {
         double s;
         if (!dn)
-            s = dadd(z[5 * L + cu + 1], z[6 * L + cu]);
+            s = dadd(Z(5 * L + cu + 1), Z(6 * L + cu));
         else if (!up)
-            s = dadd(z[7 * L + cd + 1], z[8 * L + cd]);
+            s = dadd(Z(7 * L + cd + 1), Z(8 * L + cd));
         else {
-            s = dadd(z[5 * L + cu + 1], z[6 * L + cu]);
-            s = dadd(s, z[7 * L + cd + 1]);
-            s = dadd(s, z[8 * L + cd]);
+            s = dadd(Z(5 * L + cu + 1), Z(6 * L + cu));
+            s = dadd(s, Z(7 * L + cd + 1));
+            s = dadd(s, Z(8 * L + cd));
         }
         q2[L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y] = dmul(s, SF);
     }
@@ -206,7 +209,12 @@ __global__ void __launch_bounds__(256) k_bfdconj(Geo g, double S, double SF, con
 void launch_bfdconj(const Geo& g, double S, const double* z, double* q2, cudaStream_t st)
 {
     dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)g.nt);
-    k_bfdconj<<<grid, 256, 0, st>>>(g, S, host_sf(S), z, q2);
+    k_bfdconj<false><<<grid, 256, 0, st>>>(g, S, host_sf(S), z, nullptr, q2);
+}
+void launch_bfdconj_sum(const Geo& g, double S, const double* za, const double* zb, double* q2, cudaStream_t st)
+{
+    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)g.nt);
+    k_bfdconj<true><<<grid, 256, 0, st>>>(g, S, host_sf(S), za, zb, q2);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -276,8 +284,11 @@ void launch_projsoc(i64 M, int N, const double* in, double* out, cudaStream_t st
 template <bool WEIGHTED, bool ACC>
 __device__ __forceinline__ void q_update(i64 e, double aphi, double dinv_plain, double s2term, const IterScal& sc,
                                          const double* __restrict__ q2, const double* __restrict__ weight,
-                                         double* __restrict__ alpha, double* __restrict__ qout)
+                                         double* __restrict__ alpha, double* __restrict__ qout,
+                                         const double* __restrict__ tmpq_in, double* __restrict__ tmpq_out, bool upd_alpha)
 {
+    if (tmpq_in != nullptr) aphi = tmpq_in[e];      // PALM's first q-step re-uses the stored A*phi (solver_socp_PALM.m:198-199)
+    if (tmpq_out != nullptr) tmpq_out[e] = aphi;
     const double a = alpha[e];
     const double q2v = q2[e];
     double qn, wq;
@@ -291,6 +302,7 @@ __device__ __forceinline__ void q_update(i64 e, double aphi, double dinv_plain, 
         wq = qn;
     }
     qout[e] = qn;
+    if (!upd_alpha) return;
     if (ACC)
         alpha[e] = dsub(dadd(a, aphi), wq);
     else
@@ -300,7 +312,9 @@ __device__ __forceinline__ void q_update(i64 e, double aphi, double dinv_plain, 
 template <bool WEIGHTED, bool ACC>
 __global__ void __launch_bounds__(256) k_qstep(Geo g, IterScal sc, const double* __restrict__ phi,
                                                const double* __restrict__ q2, const double* __restrict__ weight,
-                                               double* __restrict__ alpha, double* __restrict__ qout)
+                                               double* __restrict__ alpha, double* __restrict__ qout,
+                                               const double* __restrict__ tmpq_in, double* __restrict__ tmpq_out,
+                                               bool upd_alpha)
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
@@ -311,24 +325,27 @@ __global__ void __launch_bounds__(256) k_qstep(Geo g, IterScal sc, const double*
     const bool edge_t = (t == 0) || (t == g.nt - 1);
     if (t < g.nt - 1) {
         const double aphi = dadd(dmul(-sc.gt, ph), dmul(sc.gt, phi[n + g.P]));
-        q_update<WEIGHTED, ACC>(n, aphi, sc.dinv1, sc.s2x2, sc, q2, weight, alpha, qout);
+        q_update<WEIGHTED, ACC>(n, aphi, sc.dinv1, sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in, tmpq_out, upd_alpha);
     }
     if (x < g.nx - 1) {
         const double aphi = dadd(dmul(-sc.gx, ph), dmul(sc.gx, phi[n + g.ny]));
         q_update<WEIGHTED, ACC>(g.L + (i64)t * g.PBX + (i64)x * g.ny + y, aphi, edge_t ? sc.dinv2 : sc.dinv1,
-                                edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout);
+                                edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in, tmpq_out, upd_alpha);
     }
     if (y < g.ny - 1) {
         const double aphi = dadd(dmul(-sc.gy, ph), dmul(sc.gy, phi[n + 1]));
         q_update<WEIGHTED, ACC>(g.L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y, aphi,
-                                edge_t ? sc.dinv2 : sc.dinv1, edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout);
+                                edge_t ? sc.dinv2 : sc.dinv1, edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in,
+                                tmpq_out, upd_alpha);
     }
 }
 
-void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st)
+void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st, const double* tmpq_in, double* tmpq_out,
+                  bool upd_alpha)
 {
     dim3 grid((unsigned)((a.g.P + 255) / 256), (unsigned)a.g.nt);
-#define QS(W, A) k_qstep<W, A><<<grid, 256, 0, st>>>(a.g, a.sc, a.phi, a.q2, a.weight, a.alpha, a.q_new)
+#define QS(W, A) \
+    k_qstep<W, A><<<grid, 256, 0, st>>>(a.g, a.sc, a.phi, a.q2, a.weight, a.alpha, a.q_new, tmpq_in, tmpq_out, upd_alpha)
     if (weighted) {
         if (acc) QS(true, true); else QS(true, false);
     } else {
@@ -538,6 +555,115 @@ void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cu
         if (update) KM(false, false, true); else KM(false, false, false);
     }
 #undef KM
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Unfused building blocks for the loops that keep z as state (PALM, acc-ADMM).
+// rhs = A'(w.*q - alpha) + c                                                      solver_socp_accADMM.m:243
+// ---------------------------------------------------------------------------------------------------------------
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_rhs(Geo g, IterScal sc, const double* __restrict__ q, const double* __restrict__ alpha,
+                                             const double* __restrict__ weight, const double* __restrict__ c0,
+                                             const double* __restrict__ c1, double* __restrict__ rhs)
+{
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (p >= g.P) return;
+    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    const i64 L = g.L, n = (i64)t * g.P + p;
+    const bool up = t < g.nt - 1, dn = t > 0;
+    auto u = [&](i64 e) -> double { return uval<WEIGHTED>(q[e], alpha[e], WEIGHTED ? weight[e] : 1.0); };
+    double acc = 0.0;
+    bool first = true;
+#define ADDTERM(val)                         \
+    {                                        \
+        const double tv_ = (val);            \
+        acc = first ? tv_ : dadd(acc, tv_);  \
+        first = false;                       \
+    }
+    if (dn) ADDTERM(dmul(sc.gt, u(n - g.P)));
+    if (up) ADDTERM(dmul(-sc.gt, u(n)));
+    const i64 ox = L + (i64)t * g.PBX + (i64)x * g.ny + y, oy = L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
+    if (x > 0) ADDTERM(dmul(sc.gx, u(ox - g.ny)));
+    if (x < g.nx - 1) ADDTERM(dmul(-sc.gx, u(ox)));
+    if (y > 0) ADDTERM(dmul(sc.gy, u(oy - 1)));
+    if (y < g.ny - 1) ADDTERM(dmul(-sc.gy, u(oy)));
+#undef ADDTERM
+    double cv = 0.0;
+    if (t == 0) cv = c0[p];
+    else if (!up) cv = c1[p];
+    rhs[n] = dadd(first ? 0.0 : acc, cv);
+}
+void launch_rhs(const Geo& g, const IterScal& sc, bool weighted, const double* q, const double* alpha, const double* weight,
+                const double* c0, const double* c1, double* rhs, cudaStream_t st)
+{
+    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)g.nt);
+    if (weighted) k_rhs<true><<<grid, 256, 0, st>>>(g, sc, q, alpha, weight, c0, c1, rhs);
+    else k_rhs<false><<<grid, 256, 0, st>>>(g, sc, q, alpha, weight, c0, c1, rhs);
+}
+
+// cell-local multiplier updates with z materialised (in place; no neighbour cell is touched)
+//   MODE 0 (PALM :219-224)     : beta = beta + tau*(z - z2(q))
+//   MODE 1 (acc-ADMM :236-248) : beta = (beta + z) - z2(q) ; z = Pi_Q(z2(q) - beta)
+//   MODE 2 (PALM :137-138)     : z = d + BF q on the non-boundary entries only (mexBFd(z, tmp_q, ...))
+template <bool ONE_D, int MODE>
+__global__ void __launch_bounds__(256) k_cells_update(Geo g, IterScal sc, const double* __restrict__ q, double* z, double* beta)
+{
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (p >= g.P) return;
+    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    const bool hxm = x > 0, hxp = x < g.nx - 1, hym = y > 0, hyp = y < g.ny - 1;
+    const i64 L = g.L, c = (i64)t * g.P + p;
+    const double* bx = q + L;
+    const double* by = bx + g.NBX;
+    const i64 ox = (i64)t * g.PBX + (i64)x * g.ny + y, oy = (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
+    CellQ cq;
+    cq.q0 = q[c];
+    cq.bxm = hxm ? bx[ox - g.ny] : 0.0;
+    cq.bx = hxp ? bx[ox] : 0.0;
+    cq.bxm1 = hxm ? bx[ox + g.PBX - g.ny] : 0.0;
+    cq.bx1 = hxp ? bx[ox + g.PBX] : 0.0;
+    cq.bym = hym ? by[oy - 1] : 0.0;
+    cq.by = hyp ? by[oy] : 0.0;
+    cq.bym1 = hym ? by[oy + g.PBY - 1] : 0.0;
+    cq.by1 = hyp ? by[oy + g.PBY] : 0.0;
+    double z2[10];
+    cell_z2(cq, sc, hxm, hxp, hym, hyp, z2);
+    if (MODE == 2) {
+        const bool wr[10] = {true, hxm, hxp, hxm, hxp, hym, hyp, hym, hyp, true};
+#pragma unroll
+        for (int j = 0; j < 10; j++)
+            if (wr[j] && !(ONE_D && j >= 5 && j <= 8)) z[(i64)j * L + c] = z2[j];
+        return;
+    }
+    double zz[10], b[10];
+#pragma unroll
+    for (int j = 0; j < 10; j++) {
+        const bool dead = ONE_D && j >= 5 && j <= 8;
+        zz[j] = dead ? 0.0 : z[(i64)j * L + c];
+        b[j] = dead ? 0.0 : beta[(i64)j * L + c];
+        if (MODE == 0) b[j] = dadd(b[j], dmul(sc.tau, dsub(zz[j], z2[j])));
+        else b[j] = dsub(dadd(b[j], zz[j]), z2[j]);
+        if (!dead) beta[(i64)j * L + c] = b[j];
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 10; j++) zz[j] = dsub(z2[j], b[j]);
+        proj_soc<ONE_D>(zz);
+#pragma unroll
+        for (int j = 0; j < 10; j++)
+            if (!(ONE_D && j >= 5 && j <= 8)) z[(i64)j * L + c] = zz[j];
+    }
+}
+void launch_cells_update(const Geo& g, const IterScal& sc, bool one_d, int mode, const double* q, double* z, double* beta,
+                         cudaStream_t st)
+{
+    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)(g.nt - 1));
+#define CUK(O, M) k_cells_update<O, M><<<grid, 256, 0, st>>>(g, sc, q, z, beta)
+    if (one_d) { if (mode == 0) CUK(true, 0); else if (mode == 1) CUK(true, 1); else CUK(true, 2); }
+    else { if (mode == 0) CUK(false, 0); else if (mode == 1) CUK(false, 1); else CUK(false, 2); }
+#undef CUK
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -409,10 +409,24 @@ static double now_s()
     return duration<double>(steady_clock::now().time_since_epoch()).count();
 }
 
-// ------------------------------------------------------------------------------------------------ inPALM / ALG2
-static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* hist, dotsocp_level_result* res)
+// ------------------------------------------------------------------------------------------------ the level loops
+// One function for the three reference loops; the shared parts (rescaling, KKT, sigma rule, output) are literally the
+// same code in solver_socp_inPALM.m, solver_socp_PALM.m and solver_socp_accADMM.m, only the iteration body differs.
+//   inPALM / ALG2 : fused kernels, z never stored (recomputed from (q_old, beta_old) where the reference reads it)
+//   PALM, acc-ADMM: z is genuine state (it enters the first q-step / the extrapolation), kept in beta[1-bcur]
+static int ensure_alloc(double*& p, i64 n)
+{
+    if (p) return 0;
+    cudaError_t e = cudaMalloc(&p, (size_t)n * sizeof(double));
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(DOTSOCP_ENOMEM, "cudaMalloc(%lld doubles): %s", (long long)n, cudaGetErrorString(e)); }
+    return 0;
+}
+
+static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* hist, dotsocp_level_result* res)
 {
     const Geo& g = c->g;
+    const int method = o.method;
+    const bool inpalm = method == DOTSOCP_METHOD_INPALM, palm = method == DOTSOCP_METHOD_PALM, acc = method == DOTSOCP_METHOD_ACCADMM;
     const bool weighted = c->weighted;
     const bool checkPD = o.checkPrimDualFeas < 0 ? !weighted : (o.checkPrimDualFeas != 0);   // :20-24 / wsocp :25-29
     const double time_limit = o.time_limit > 0 ? o.time_limit : 3600;
@@ -427,26 +441,63 @@ static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist*
     int use_feasOrg = 0;
     const double tol_feasOrg = 5 * tol;
     int rescale = o.scaling ? 1 : 0;
-    const int firstScaleIter = 10, SecondScaleIter = 50, checkRescaleIters = 100;
+    const int firstScaleIter = 10, SecondScaleIter = 50, checkRescaleIters = acc ? 200 : 100;   // accADMM :96
     const double ratioThreshold = 1.2;
     double maxFeas = INFINITY, relGap = INFINITY;
     const double h = 1.0 / (double)g.N;
     double norm_c = o.normc, norm_d = o.normd;
     const double kktConst = 1;
     double sigmaScale = 1;
+    // acc-ADMM parameters (:11-34)
+    const int restart = o.restart > 0 ? o.restart : 100;
+    const double stepRho = o.rho > 0 ? o.rho : 2;
+    const double stepAlpha = o.theta > 0 ? o.theta : 2;
+    if (acc && stepAlpha != 2) return set_err(DOTSOCP_EINVAL, "acc-ADMM: only the Halpern iteration (opts.theta == 2, the default) is available");
+    if (palm && (weighted || c->one_d)) return set_err(DOTSOCP_EINVAL, "PALM exists only for socp/dot2d");
+    if (acc && c->one_d) return set_err(DOTSOCP_EINVAL, "acc-ADMM does not exist for socp/dot1d");
+    int kacc = 0;
 
     Loop L;
     L.c = c; L.o = &o;
     L.sc = make_scal(o, D, E, dScale, tau);
     L.sc_D2 = D * D;
+    const i64 nB = 10 * g.L;
+    double* zmat = nullptr;      // PALM / acc: z lives here
+    double* tmpq = nullptr;      // PALM: stored A*phi
+    i64 vn[5] = {g.N, nB, g.Q, g.Q, nB};
+    double* cur[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (!inpalm) {
+        if (!c->z_materialised) return set_err(DOTSOCP_ESTATE, "z is not materialised");
+        zmat = c->beta[1 - c->bcur];
+    }
+    if (palm) { int rc = ensure_alloc(c->zmat, g.Q); if (rc) return rc; tmpq = c->zmat; }
+    if (acc) {
+        for (int i = 0; i < 5; i++) {
+            int rc = ensure_alloc(c->old_[i], vn[i]); if (rc) return rc;
+            rc = ensure_alloc(c->anc_[i], vn[i]); if (rc) return rc;
+        }
+    }
+    auto refresh_cur = [&]() { cur[0] = c->phi; cur[1] = zmat; cur[2] = c->q[c->qcur]; cur[3] = c->alpha; cur[4] = c->beta[c->bcur]; };
+    auto copy_to = [&](double** dst) {
+        refresh_cur();
+        for (int i = 0; i < 5; i++) cudaMemcpyAsync(dst[i], cur[i], (size_t)vn[i] * sizeof(double), cudaMemcpyDeviceToDevice, c->st);
+    };
 
     // alpha, beta, c <- ./sigma  (:102-104)
     launch_scale(c->alpha, g.Q, 1.0, sigma, c->st);
-    launch_scale(c->beta[c->bcur], 10 * g.L, 1.0, sigma, c->st);
+    launch_scale(c->beta[c->bcur], nB, 1.0, sigma, c->st);
     launch_scale(c->c0, g.P, 1.0, sigma, c->st);
     launch_scale(c->c1, g.P, 1.0, sigma, c->st);
     c->launches += 4;
-    L.prologue();   // z2 := d + BF q (:133) folded into the first z-step
+    if (inpalm) L.prologue();   // z2 := d + BF q (:133) folded into the first z-step
+    if (palm) {                 // tmp_q = A*phi ; mexBFd(z, tmp_q, ...)   (PALM :137-138)
+        UpdateArgs a = L.ua();
+        a.q_new = c->q[1 - c->qcur];   // scratch: only tmpq_out matters here
+        launch_qstep(a, false, false, c->st, nullptr, tmpq, false);
+        launch_cells_update(g, L.sc, false, 2, tmpq, zmat, nullptr, c->st);
+        c->launches += 2;
+    }
+    if (acc) { copy_to(c->old_); copy_to(c->anc_); }   // :157-163
 
     cudaEvent_t ev_begin, ev_end;
     cudaEventCreate(&ev_begin);
@@ -454,12 +505,12 @@ static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist*
     cudaEventRecord(ev_begin, c->st);
     struct Seg { cudaEvent_t a, b; int kind; };
     std::vector<Seg> segs;
-    double T[5] = {0, 0, 0, 0, 0};   // lineq, proj, q, mult, kkt
+    double T[7] = {0, 0, 0, 0, 0, 0, 0};   // 0 lineq, 1 proj, 2 q, 3 mult, 4 kkt, 5 q0 (PALM) / interp (acc)
     auto flush_segs = [&]() {
-        for (auto& s : segs) {
+        for (auto& sg : segs) {
             float ms = 0;
-            cudaEventElapsedTime(&ms, s.a, s.b);
-            T[s.kind] += ms * 1e-3;
+            cudaEventElapsedTime(&ms, sg.a, sg.b);
+            T[sg.kind] += ms * 1e-3;
         }
         segs.clear();
         c->evs.reset();
@@ -479,7 +530,7 @@ static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist*
             if ((rc = sumsq_host(c, c->phi, g.N, &s_phi))) return rc;
             if ((rc = sumsq_host(c, c->q[c->qcur], g.Q, &s_q))) return rc;
             if (c->z_materialised) {
-                if ((rc = sumsq_host(c, c->beta[1 - c->bcur], 10 * g.L, &s_z))) return rc;
+                if ((rc = sumsq_host(c, c->beta[1 - c->bcur], nB, &s_z))) return rc;
             } else {
                 launch_zstep(g, L.sc, c->one_d, c->q[1 - c->qcur], c->beta[1 - c->bcur], nullptr, c->partial, c->dsums, c->st);
                 c->launches += 2;
@@ -487,7 +538,7 @@ static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist*
                 s_z = c->hsums[0];
             }
             if ((rc = sumsq_host(c, c->alpha, g.Q, &s_a))) return rc;
-            if ((rc = sumsq_host(c, c->beta[c->bcur], 10 * g.L, &s_b))) return rc;
+            if ((rc = sumsq_host(c, c->beta[c->bcur], nB, &s_b))) return rc;
             const double normPhi = sqrt(h) * sqrt(s_phi), normQ = sqrt(h) * sqrt(s_q), normZ = sqrt(h) * sqrt(s_z);
             const double normAlpha = sigma * (sqrt(h) * sqrt(s_a)), normBeta = sigma * (sqrt(h) * sqrt(s_b));
             normPhis = mmax({normPhi, normQ, normZ});
@@ -509,36 +560,89 @@ static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist*
             const double dScale2 = normPhis, cScale2 = normAlps;
             sigma = sigma * (cScale2 / dScale2);
             const double cs2 = cScale2 * cScale2;
-            // c, alpha, beta <- x * dScale2 / cScale2^2 ; q <- q / dScale2 (z is recomputed, never stored)
+            // c, alpha, beta <- x * dScale2 / cScale2^2 ; q, z <- ./dScale2 (inPALM: z is recomputed, never stored)
             launch_scale(c->c0, g.P, dScale2, cs2, c->st);
             launch_scale(c->c1, g.P, dScale2, cs2, c->st);
             norm_c = norm_c / cScale2;
             if (!weighted) norm_d = norm_d / dScale2;
             launch_scale(c->alpha, g.Q, dScale2, cs2, c->st);
-            launch_scale(c->beta[c->bcur], 10 * g.L, dScale2, cs2, c->st);
-            launch_scale(c->q[c->qcur], g.Q, 1.0, dScale2, c->st);
-            if (c->z_materialised) launch_scale(c->beta[1 - c->bcur], 10 * g.L, 1.0, dScale2, c->st);
-            c->launches += 6;
+            launch_scale(c->beta[c->bcur], nB, dScale2, cs2, c->st);
+            if (acc) launch_scale(c->phi, g.N, 1.0, dScale2, c->st);                 // accADMM :207
+            if (!palm) launch_scale(c->q[c->qcur], g.Q, 1.0, dScale2, c->st);        // :177 (absent in PALM)
+            if (c->z_materialised) launch_scale(c->beta[1 - c->bcur], nB, 1.0, dScale2, c->st);
+            if (palm) launch_scale(tmpq, g.Q, 1.0, dScale2, c->st);                  // PALM :191
+            c->launches += 7;
             dScale = dScale2 * dScale;
             cScale = cScale2 * cScale;
             L.sc.DF = E / dScale;                                   // scaleD
             sigmaScale = sigmaScale * (cScale2 / dScale2);
-            L.prologue();                                           // mexBFd(z2, q, ...) refresh (:187)
+            if (inpalm) L.prologue();                               // mexBFd(z2, q, ...) refresh (:187)
+            if (acc) { kacc = 0; copy_to(c->old_); copy_to(c->anc_); }   // accADMM :217-222
             rescale += 1;
         }
 
-        // ---------------------------------------------------------------- iteration :192-216 (fused order)
-        cudaEvent_t e0 = mark();
-        L.step_phi();
-        cudaEvent_t e1 = mark();
-        L.step_q(false);
-        cudaEvent_t e2 = mark();
-        L.step_mult();
-        cudaEvent_t e3 = mark();
-        segs.push_back({e0, e1, 0});
-        segs.push_back({e1, e2, 2});
-        segs.push_back({e2, e3, 3});
-        z_ever = true;
+        // ---------------------------------------------------------------- iteration
+        cudaEvent_t e_last;
+        if (inpalm) {   // :192-216, fused order
+            cudaEvent_t e0 = mark();
+            L.step_phi();
+            cudaEvent_t e1 = mark();
+            L.step_q(false);
+            cudaEvent_t e2 = mark();
+            L.step_mult();
+            cudaEvent_t e3 = mark();
+            segs.push_back({e0, e1, 0});
+            segs.push_back({e1, e2, 2});
+            segs.push_back({e2, e3, 3});
+            e_last = e3;
+            z_ever = true;
+        } else if (palm) {   // solver_socp_PALM.m:196-224
+            double* q = c->q[c->qcur];
+            double* beta = c->beta[c->bcur];
+            UpdateArgs a = L.ua();
+            a.q_new = q;
+            cudaEvent_t e0 = mark();
+            launch_bfdconj_sum(g, L.sc.S, zmat, beta, c->q2, c->st);
+            launch_qstep(a, false, false, c->st, tmpq, nullptr, false);              // q = (tmp_q + alpha + q2).*diagQInv
+            cudaEvent_t e1 = mark();
+            launch_rhs(g, L.sc, false, q, c->alpha, nullptr, c->c0, c->c1, c->rhs, c->st);
+            c->launches += 3;
+            L.step_phi();
+            cudaEvent_t e2 = mark();
+            launch_zstep(g, L.sc, false, q, beta, zmat, c->partial, c->dsums, c->st);   // mexBFd + mexProjSoc (:209-210)
+            cudaEvent_t e3 = mark();
+            launch_bfdconj_sum(g, L.sc.S, zmat, beta, c->q2, c->st);
+            launch_qstep(a, false, false, c->st, nullptr, tmpq, true);               // tmp_q = A*phi ; q ; alpha
+            cudaEvent_t e4 = mark();
+            launch_cells_update(g, L.sc, false, 0, q, zmat, beta, c->st);            // beta += tau (z - z2)
+            cudaEvent_t e5 = mark();
+            c->launches += 5;
+            segs.push_back({e0, e1, 5});
+            segs.push_back({e1, e2, 0});
+            segs.push_back({e2, e3, 1});
+            segs.push_back({e3, e4, 2});
+            segs.push_back({e4, e5, 3});
+            e_last = e5;
+        } else {   // solver_socp_accADMM.m:227-249
+            double* q = c->q[c->qcur];
+            double* beta = c->beta[c->bcur];
+            UpdateArgs a = L.ua();
+            a.q_new = q;
+            cudaEvent_t e0 = mark();
+            launch_bfdconj_sum(g, L.sc.S, zmat, beta, c->q2, c->st);
+            launch_qstep(a, weighted, true, c->st);                                  // q ; alpha = (alpha + A phi) - w.*q
+            cudaEvent_t e1 = mark();
+            launch_rhs(g, L.sc, weighted, q, c->alpha, c->weight, c->c0, c->c1, c->rhs, c->st);
+            L.step_phi();
+            cudaEvent_t e2 = mark();
+            launch_cells_update(g, L.sc, false, 1, q, zmat, beta, c->st);            // beta = (beta + z) - z2 ; z = Pi_Q(z2 - beta)
+            cudaEvent_t e3 = mark();
+            c->launches += 4;
+            segs.push_back({e0, e1, 2});
+            segs.push_back({e1, e2, 0});
+            segs.push_back({e2, e3, 3});
+            e_last = e3;
+        }
 
         // ---------------------------------------------------------------- kkt :218-324
         const bool adjustSigmaYes = IfAdjustSigma(it, lastSigmaIt);
@@ -548,12 +652,13 @@ static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist*
             over_time = (now_s() - clock_total) > time_limit;
         }
         const bool check = checkSByS || adjustSigmaYes || it == maxit || over_time;
+        bool stop = false;
         if (check) {
             launch_bfdconj(g, L.sc.S, c->beta[c->bcur], c->qtmp, c->st);   // q2 = s (BF)^* beta   (:225)
             KktArgs ka;
             ka.g = g; ka.sc = L.sc; ka.sigma = sigma; ka.cScale = cScale; ka.dScale = dScale; ka.D = D; ka.E = E;
             ka.phi = c->phi; ka.q = c->q[c->qcur]; ka.alpha = c->alpha; ka.weight = c->weight;
-            ka.beta = c->beta[c->bcur]; ka.z = nullptr; ka.q_old = c->q[1 - c->qcur]; ka.beta_old = c->beta[1 - c->bcur];
+            ka.beta = c->beta[c->bcur]; ka.z = zmat; ka.q_old = c->q[1 - c->qcur]; ka.beta_old = c->beta[1 - c->bcur];
             ka.q2b = c->qtmp; ka.c0 = c->c0; ka.c1 = c->c1; ka.partial = c->partial;
             ka.out = c->dsums;
             launch_kkt_cells(ka, weighted, c->one_d, c->st);
@@ -561,13 +666,13 @@ static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist*
             launch_kkt_nodes(ka, weighted, c->st);
             c->launches += 5;
             cudaEvent_t e4 = mark();
-            segs.push_back({e3, e4, 4});
+            segs.push_back({e_last, e4, 4});
             int rc = fetch_sums(c, KC_COUNT + KN_COUNT);
             if (rc) return rc;
             flush_segs();
             const double* sc_ = c->hsums;
             const double* sn = c->hsums + KC_COUNT;
-            auto nrm = [&](double s) { return sqrt(h) * sqrt(s); };
+            auto nrm = [&](double v) { return sqrt(h) * sqrt(v); };
             const double norm_q = nrm(sn[KN_Q2]);
             const double norm_z = nrm(sc_[KC_Z2]);
             const double norm_Aphi = nrm(sn[KN_APHI2]);
@@ -610,30 +715,53 @@ static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist*
             }
             hist_len++;
             const double stopv = checkPD ? mmax({KO[0], KO[2], KO[5], KO[6]}) : mmax({KO[0], KO[2], KO[5]});
-            if (stopv < tol || (now_s() - clock_total) > time_limit) break;
-            if (mmax({KR[0], KR[1], KR[2], KR[3], KR[4]}) < tol_feasOrg) use_feasOrg = 1;
-            if (adjustSigmaYes) {
-                lastSigmaIt = it;
-                double resiPri, resiDual;
-                if (use_feasOrg) { resiPri = mmax({KO[0], KO[1]}); resiDual = mmax({KO[2], KO[4]}); }
-                else { resiPri = mmax({KR[0], KR[1]}); resiDual = mmax({KR[2], KR[4]}); }
-                double factor = 1;
-                adjust_lagrangianParam(sigma, resiPri / resiDual, factor);
-                if (factor != 1) {
-                    launch_scale(c->alpha, g.Q, 1.0, factor, c->st);
-                    launch_scale(c->beta[c->bcur], 10 * g.L, 1.0, factor, c->st);
-                    launch_scale(c->c0, g.P, 1.0, factor, c->st);
-                    launch_scale(c->c1, g.P, 1.0, factor, c->st);
-                    c->launches += 4;
-                    // q2, rhs were computed with the old alpha/beta: refresh. beta_old/q_old stay untouched (they define z).
-                    // The prologue reads only the current buffers, so the z-defining pair survives.
-                    L.prologue();
+            if (stopv < tol || (now_s() - clock_total) > time_limit) {
+                stop = true;
+            } else {
+                if (mmax({KR[0], KR[1], KR[2], KR[3], KR[4]}) < tol_feasOrg) use_feasOrg = 1;
+                if (adjustSigmaYes) {
+                    lastSigmaIt = it;
+                    double resiPri, resiDual;
+                    if (use_feasOrg) { resiPri = mmax({KO[0], KO[1]}); resiDual = mmax({KO[2], KO[4]}); }
+                    else { resiPri = mmax({KR[0], KR[1]}); resiDual = mmax({KR[2], KR[4]}); }
+                    double factor = 1;
+                    adjust_lagrangianParam(sigma, resiPri / resiDual, factor);
+                    if (factor != 1) {
+                        launch_scale(c->alpha, g.Q, 1.0, factor, c->st);
+                        launch_scale(c->beta[c->bcur], nB, 1.0, factor, c->st);
+                        launch_scale(c->c0, g.P, 1.0, factor, c->st);
+                        launch_scale(c->c1, g.P, 1.0, factor, c->st);
+                        c->launches += 4;
+                        // inPALM: q2, rhs were computed with the old alpha/beta: refresh.  The prologue reads only the
+                        // current buffers, so the (q_old, beta_old) pair that defines z survives.
+                        if (inpalm) L.prologue();
+                        if (acc) {   // accADMM :346-358
+                            launch_scale(c->old_[3], g.Q, 1.0, factor, c->st);
+                            launch_scale(c->old_[4], nB, 1.0, factor, c->st);
+                            c->launches += 2;
+                            kacc = 0;
+                            copy_to(c->anc_);
+                        }
+                    }
+                }
+                if (rescale > 0) {
+                    maxFeas = mmax({KR[0], KR[1], KR[2], KR[3], KR[4]});
+                    relGap = pdGap;
                 }
             }
-            if (rescale > 0) {
-                maxFeas = mmax({KR[0], KR[1], KR[2], KR[3], KR[4]});
-                relGap = pdGap;
-            }
+        }
+        if (stop) break;
+        if (acc) {   // Halpern iteration, accADMM :371-388
+            cudaEvent_t e5 = mark();
+            const double c1 = 1.0 / (kacc + 2), c2 = (double)(kacc + 1) / (kacc + 2);
+            kacc += 1;
+            const bool anchor = kacc >= restart;
+            refresh_cur();
+            for (int i = 0; i < 5; i++) launch_halpern(cur[i], c->old_[i], c->anc_[i], vn[i], c1, c2, stepRho, anchor, c->st);
+            c->launches += 5;
+            if (anchor) kacc = 0;
+            cudaEvent_t e6 = mark();
+            segs.push_back({e5, e6, 5});
         }
     }
     if (it > maxit) it = maxit;
@@ -645,7 +773,7 @@ static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist*
         c->z_materialised = true;
     }
     launch_scale(c->alpha, g.Q, sigma, 1.0, c->st);               // var.alpha = sigma*alpha
-    launch_scale(c->beta[c->bcur], 10 * g.L, sigma, 1.0, c->st);  // var.beta  = sigma*beta
+    launch_scale(c->beta[c->bcur], nB, sigma, 1.0, c->st);        // var.beta  = sigma*beta
     launch_scale(c->c0, g.P, sigma, 1.0, c->st);                  // undo the folding of model.c (the reference never
     launch_scale(c->c1, g.P, sigma, 1.0, c->st);                  // writes its local copy back; keeps the session reusable)
     c->launches += 4;
@@ -656,14 +784,17 @@ static int run_inpalm(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist*
     cudaEventElapsedTime(&total_ms, ev_begin, ev_end);
     cudaEventDestroy(ev_begin);
     cudaEventDestroy(ev_end);
+    CU(cudaGetLastError());
     if (res) {
         memset(res, 0, sizeof(*res));
         res->iters = it;
         res->hist_len = hist_len;
         res->sigma = sigma / sigmaScale;
         res->cScale = cScale; res->dScale = dScale; res->D = D; res->E = E;
-        res->times[0] = T[0]; res->times[1] = T[1]; res->times[2] = T[2]; res->times[3] = T[3]; res->times[4] = T[4];
-        res->times[5] = total_ms * 1e-3;
+        const double tot = total_ms * 1e-3;
+        if (inpalm) { res->times[0] = T[0]; res->times[1] = T[1]; res->times[2] = T[2]; res->times[3] = T[3]; res->times[4] = T[4]; res->times[5] = tot; }
+        else if (palm) { res->times[0] = T[5]; res->times[1] = T[0]; res->times[2] = T[1]; res->times[3] = T[2]; res->times[4] = T[3]; res->times[5] = T[4]; res->times[6] = tot; }
+        else { res->times[0] = T[2]; res->times[1] = T[3]; res->times[2] = T[0]; res->times[3] = T[1]; res->times[4] = T[4]; res->times[5] = T[5]; res->times[6] = tot; }
         res->gpu_launches = c->launches;
     }
     return DOTSOCP_OK;
@@ -677,10 +808,8 @@ extern "C" int dotsocp_run(dotsocp_ctx* c, const dotsocp_level_opts* o, dotsocp_
     if (o->variant != c->variant || o->nt != c->g.nt || o->nx != c->g.nx || o->ny != c->g.ny)
         return set_err(DOTSOCP_EINVAL, "opts do not match the context (variant/grid)");
     if (o->maxit < 1) return set_err(DOTSOCP_EINVAL, "maxit must be >= 1");
-    switch (o->method) {
-        case DOTSOCP_METHOD_INPALM: return run_inpalm(c, *o, hist, res);
-        default: return set_err(DOTSOCP_EINVAL, "method %d is not available in this build", o->method);
-    }
+    if (o->method < 0 || o->method > 2) return set_err(DOTSOCP_EINVAL, "unknown method %d", o->method);
+    return run_level(c, *o, hist, res);
 }
 
 extern "C" int dotsocp_solve_level(const dotsocp_level_opts* o, double* phi, double* q, double* z, double* alpha, double* beta,

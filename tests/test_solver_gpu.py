@@ -123,3 +123,54 @@ def test_error_behaviour(gpu):
         dp.Session("dot1d", 5, 9, 3)             # 1-D variant with ny != 1
     with pytest.raises(_lib.DotsocpError):
         dp.Session("dot2d", 1, 9, 9)
+
+
+@pytest.mark.parametrize("method,n,nt,levelN", [("PALM", 17, 9, 1), ("acc-ADMM", 17, 9, 1), ("acc-ADMM", 33, 17, 2),
+                                                 ("PALM", 33, 17, 2)])
+def test_dot2d_palm_and_accadmm_parity(gpu, method, n, nt, levelN):
+    import dotsocp_b200 as dp
+    rho0, rho1 = O.get_example2d("example1", n, n)
+    opts = {"tol": 1e-4, "maxit": 3000}
+    out_g, _, ML_g, rh_g = dp.solver_dotsocp2d(rho0, rho1, nt, levelN, opts, method)
+    out_o, _, ML_o, rh_o = O.solver_dotsocp2d(rho0, rho1, nt, levelN, opts, method, workers=4)
+    _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o)
+
+
+def test_wdot2d_accadmm_parity(gpu):
+    import dotsocp_b200 as dp
+    n, nt = 17, 9
+    rho0, rho1 = O.get_example2d("example1", n, n)
+    w = O.gene_weight_circle(nt, n, n)
+    opts = {"tol": 1e-3, "maxit": 10000, "weight": w}
+    out_g, _, ML_g, rh_g = dp.solver_wdotsocp2d(rho0, rho1, nt, 2, opts, "acc-ADMM")
+    out_o, _, ML_o, rh_o = O.solver_wdotsocp2d(rho0, rho1, nt, 2, opts, "acc-ADMM")
+    _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o)
+
+
+def test_golden_solver_histories(gpu):
+    """committed goldens (tests/golden/solver.json): iteration counts exact, KKT history within 1e-8, objective 1e-6 rel"""
+    import json, os
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import driver
+    with open(os.path.join(os.path.dirname(__file__), "golden", "solver.json")) as f:
+        gold = {c["name"]: c for c in json.load(f)}
+    rho0, rho1 = O.get_example2d("example1", 17, 17)
+    runs = {
+        "dot2d_example1_17x17x9_L2_inPALM": lambda: dp.solver_dotsocp2d(rho0, rho1, 9, 2, {"tol": 1e-4, "maxit": 3000}, "inPALM"),
+        "dot2d_example1_17x17x9_L1_accADMM": lambda: dp.solver_dotsocp2d(rho0, rho1, 9, 1, {"tol": 1e-4, "maxit": 3000}, "acc-ADMM"),
+        "dot2d_example1_17x17x9_L1_PALM": lambda: dp.solver_dotsocp2d(rho0, rho1, 9, 1, {"tol": 1e-4, "maxit": 3000}, "PALM"),
+        "wdot2d_example1_circle_17x17x9_L2_inPALM": lambda: dp.solver_wdotsocp2d(
+            rho0, rho1, 9, 2, {"tol": 1e-3, "maxit": 10000, "weight": O.gene_weight_circle(9, 17, 17)}, "inPALM"),
+        "dot1d_gaussian_129x9_L2_inPALM": lambda: dp.solver_dotsocp1d(*O.get_example1d("gaussian", 129), 9, 2,
+                                                                       {"tol": 1e-5, "maxit": 3000}, "inPALM"),
+        "dot2d_example2_33x33x17_L2_ALG2": lambda: dp.solver_dotsocp2d(*O.get_example2d("example2", 33, 33), 17, 2,
+                                                                        {"tol": 1e-4, "maxit": 3000}, "ALG2"),
+    }
+    for name, fn in runs.items():
+        out, _, ML, rh = fn()
+        g = gold[name]
+        assert [int(v) for v in out.level_iters] == g["level_iters"], name
+        assert ML.iter.tolist() == g["hist_iter"], name
+        assert np.abs(ML.kkt - np.array(g["kkt"])).max() < 1e-8, name
+        assert abs(rh.priVal[-1] - g["priVal"]) <= 1e-6 * abs(g["priVal"]), name
+        assert abs(driver.w2_cost(out, 1 if name.startswith("dot1d") else 2) - g["w2"]) <= 1e-6 * abs(g["w2"]), name
