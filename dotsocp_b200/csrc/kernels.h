@@ -4,15 +4,20 @@
 
 namespace dsocp {
 
+// owned part of a time slab: cell layers [tc0, tc1), node levels [tn0, tn1) (the last slab also owns level nt-1)
+struct TRange { int tc0, tc1, tn0, tn1; };
+inline TRange full_range(const Geo& g) { return TRange{0, g.nt - 1, 0, g.nt}; }
+
 // ---- standalone counterparts of the reference's MEX kernels (device pointers) -------------------------------
 void launch_bfd(const Geo& g, double S, double DF, const double* q, double* z, cudaStream_t st);
-void launch_bfdconj(const Geo& g, double S, const double* z, double* q2, cudaStream_t st);
+void launch_bfdconj(const Geo& g, double S, const double* z, double* q2, cudaStream_t st, const TRange* tr = nullptr);
 void launch_bfdconj_sum(const Geo& g, double S, const double* za, const double* zb, double* q2, cudaStream_t st);
 void launch_projsoc(i64 M, int N, const double* in, double* out, cudaStream_t st);
 
 // ---- fused iteration kernels --------------------------------------------------------------------------------
 struct UpdateArgs {
     Geo g;
+    TRange tr;
     IterScal sc;
     const double* phi;
     const double* q_old;    // q of the previous iterate (input of the z-step), UPDATE only
@@ -42,7 +47,7 @@ void launch_cells_update(const Geo& g, const IterScal& sc, bool one_d, int mode,
 void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st);
 // z = Pi_Q(d + BF q_old - beta_old): optional store (zout may alias beta_old) and out[0] = sum z^2
 void launch_zstep(const Geo& g, const IterScal& sc, bool one_d, const double* q_old, const double* beta_old, double* zout,
-                  double* partial, double* out, cudaStream_t st);
+                  double* partial, double* out, cudaStream_t st, const TRange* tr = nullptr);
 
 // ---- KKT / norms --------------------------------------------------------------------------------------------
 enum { KC_Z2 = 0, KC_BETA2, KC_PRIM2, KC_COMPL, KC_DOTC, KC_RHOT, KC_RHOFQ, KC_COUNT };
@@ -50,6 +55,7 @@ enum { KN_Q2 = 0, KN_APHI2, KN_PRIM1, KN_ALPHA2, KN_FBB2, KN_DUAL2, KN_QDOTA, KN
        KN_DUAL1, KN_CPHI, KN_PHI2, KN_COUNT };
 struct KktArgs {
     Geo g;
+    TRange tr;
     IterScal sc;
     double sigma, cScale, dScale, D, E;
     const double* phi;
@@ -98,6 +104,10 @@ PoissonPlan* poisson_plan_create(int nt, int nx, int ny);
 void poisson_plan_destroy(PoissonPlan* p);
 // a <- idctn( dctn(rhs) ./ (D2 * kernel) ); rhs is only read (rhs == a is allowed)
 void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cudaStream_t st, double* launches);
+// time-slab pieces: forward (y then x) / inverse (x then y) transforms of node levels [tn0, tn0+nlev) of the global
+// array (src is only read; src == a allowed), and the t-pass on a transposed [nt][chunk] buffer of modes p0..p0+chunk-1
+void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev, bool inverse, cudaStream_t st, double* launches);
+void poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches);
 // in-place orthonormal DCT-II (or inverse) along all axes
 void poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches);
 

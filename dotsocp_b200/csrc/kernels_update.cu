@@ -164,13 +164,13 @@ void launch_bfd(const Geo& g, double S, double DF, const double* q, double* z, c
 // add order ((z1[t,x+1] + z2[t,x]) + z3[t-1,x+1]) + z4[t-1,x]
 // ---------------------------------------------------------------------------------------------------------------
 template <bool ADD2>
-__global__ void __launch_bounds__(256) k_bfdconj(Geo g, double S, double SF, const double* __restrict__ za,
+__global__ void __launch_bounds__(256) k_bfdconj(Geo g, int tn0, double S, double SF, const double* __restrict__ za,
                                                  const double* __restrict__ zb, double* __restrict__ q2)
 {
     // ADD2: the argument is the elementwise sum za + zb (mexBFdConj(q2, z + beta, ...), solver_socp_accADMM.m:229)
     auto Z = [&](i64 idx) -> double { return ADD2 ? dadd(za[idx], zb[idx]) : za[idx]; };
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int t = tn0 + blockIdx.y;
     if (p >= g.P) return;
     const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
     const i64 L = g.L;
@@ -206,15 +206,16 @@ __global__ void __launch_bounds__(256) k_bfdconj(Geo g, double S, double SF, con
     }
 }
 
-void launch_bfdconj(const Geo& g, double S, const double* z, double* q2, cudaStream_t st)
+void launch_bfdconj(const Geo& g, double S, const double* z, double* q2, cudaStream_t st, const TRange* tr)
 {
-    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)g.nt);
-    k_bfdconj<false><<<grid, 256, 0, st>>>(g, S, host_sf(S), z, nullptr, q2);
+    const int tn0 = tr ? tr->tn0 : 0, tn1 = tr ? tr->tn1 : g.nt;
+    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)(tn1 - tn0));
+    k_bfdconj<false><<<grid, 256, 0, st>>>(g, tn0, S, host_sf(S), z, nullptr, q2);
 }
 void launch_bfdconj_sum(const Geo& g, double S, const double* za, const double* zb, double* q2, cudaStream_t st)
 {
     dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)g.nt);
-    k_bfdconj<true><<<grid, 256, 0, st>>>(g, S, host_sf(S), za, zb, q2);
+    k_bfdconj<true><<<grid, 256, 0, st>>>(g, 0, S, host_sf(S), za, zb, q2);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -310,14 +311,14 @@ __device__ __forceinline__ void q_update(i64 e, double aphi, double dinv_plain, 
 }
 
 template <bool WEIGHTED, bool ACC>
-__global__ void __launch_bounds__(256) k_qstep(Geo g, IterScal sc, const double* __restrict__ phi,
+__global__ void __launch_bounds__(256) k_qstep(Geo g, int tn0, IterScal sc, const double* __restrict__ phi,
                                                const double* __restrict__ q2, const double* __restrict__ weight,
                                                double* __restrict__ alpha, double* __restrict__ qout,
                                                const double* __restrict__ tmpq_in, double* __restrict__ tmpq_out,
                                                bool upd_alpha)
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int t = tn0 + blockIdx.y;
     if (p >= g.P) return;
     const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
     const i64 n = (i64)t * g.P + p;
@@ -343,9 +344,9 @@ __global__ void __launch_bounds__(256) k_qstep(Geo g, IterScal sc, const double*
 void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st, const double* tmpq_in, double* tmpq_out,
                   bool upd_alpha)
 {
-    dim3 grid((unsigned)((a.g.P + 255) / 256), (unsigned)a.g.nt);
+    dim3 grid((unsigned)((a.g.P + 255) / 256), (unsigned)(a.tr.tn1 - a.tr.tn0));
 #define QS(W, A) \
-    k_qstep<W, A><<<grid, 256, 0, st>>>(a.g, a.sc, a.phi, a.q2, a.weight, a.alpha, a.q_new, tmpq_in, tmpq_out, upd_alpha)
+    k_qstep<W, A><<<grid, 256, 0, st>>>(a.g, a.tr.tn0, a.sc, a.phi, a.q2, a.weight, a.alpha, a.q_new, tmpq_in, tmpq_out, upd_alpha)
     if (weighted) {
         if (acc) QS(true, true); else QS(true, false);
     } else {
@@ -375,7 +376,7 @@ __device__ __forceinline__ double uval(double q, double a, double w)
 }
 
 template <int TX, int TY, bool WEIGHTED, bool ONE_D, bool UPDATE>
-__global__ void __launch_bounds__(TX* TY) k_mult(Geo g, IterScal sc, const double* __restrict__ qo,
+__global__ void __launch_bounds__(TX* TY) k_mult(Geo g, TRange tr, IterScal sc, const double* __restrict__ qo,
                                                  const double* __restrict__ qn, const double* __restrict__ alpha,
                                                  const double* __restrict__ weight, const double* __restrict__ beta,
                                                  double* __restrict__ beta_out, double* __restrict__ q2,
@@ -408,22 +409,29 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, IterScal sc, const doubl
     co.q0 = cn.q0 = 0.0;
     co.bxm = co.bx = co.bym = co.by = co.bxm1 = co.bx1 = co.bym1 = co.by1 = 0.0;
     cn = co;
-    if (UPDATE) {
-        if (hxm) co.bxm = qo_bx[ibxm];
-        if (hxp) co.bx = qo_bx[ibx];
-        if (hym) co.bym = qo_by[ibym];
-        if (hyp) co.by = qo_by[iby];
+    // time slab: march over the owned node levels [tn0, tn1); a slab that does not start at t = 0 first replays the
+    // cell layer below it (ghost layer, kept redundantly by both neighbours) to obtain the carried t-1 quantities
+    const int t_start = tr.tc0 > 0 ? tr.tc0 - 1 : 0;
+    {
+        const i64 s0x = (i64)t_start * g.PBX, s0y = (i64)t_start * g.PBY;
+        if (UPDATE) {
+            if (hxm) co.bxm = qo_bx[s0x + ibxm];
+            if (hxp) co.bx = qo_bx[s0x + ibx];
+            if (hym) co.bym = qo_by[s0y + ibym];
+            if (hyp) co.by = qo_by[s0y + iby];
+        }
+        if (hxm) cn.bxm = qn_bx[s0x + ibxm];
+        if (hxp) cn.bx = qn_bx[s0x + ibx];
+        if (hym) cn.bym = qn_by[s0y + ibym];
+        if (hyp) cn.by = qn_by[s0y + iby];
     }
-    if (hxm) cn.bxm = qn_bx[ibxm];
-    if (hxp) cn.bx = qn_bx[ibx];
-    if (hym) cn.bym = qn_by[ibym];
-    if (hyp) cn.by = qn_by[iby];
 
     double wp3n = 0.0, wp4 = 0.0, wp7n = 0.0, wp8 = 0.0, u0p = 0.0;
 
-    for (int t = 0; t < g.nt; t++) {
+    for (int t = t_start; t < tr.tn1; t++) {
         const int buf = t & 1;
         const bool cell = t < g.nt - 1;
+        const bool emit = t >= tr.tn0;      // false only on the replayed ghost layer
         const i64 cidx = (i64)t * g.P + node;
         double w[10];
         double a0 = 0.0, wt0 = 1.0;
@@ -472,7 +480,7 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, IterScal sc, const doubl
         __syncthreads();
         if (owner) {
             if (cell) {
-                q2[cidx] = dmul(dsub(w[9], w[0]), sc.S);
+                if (emit) q2[cidx] = dmul(dsub(w[9], w[0]), sc.S);
                 a0 = alpha[cidx];
                 if (WEIGHTED) wt0 = weight[cidx];
             }
@@ -502,7 +510,7 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, IterScal sc, const doubl
                         s = dadd(wp3n, wp4);
                     else
                         s = dadd(dadd(dadd(w1n, w[2]), wp3n), wp4);
-                    q2_bx[ox + ibx] = dmul(s, sc.SF);
+                    if (emit) q2_bx[ox + ibx] = dmul(s, sc.SF);
                     wp3n = w3n;
                 }
             }
@@ -520,7 +528,7 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, IterScal sc, const doubl
                         s = dadd(wp7n, wp8);
                     else
                         s = dadd(dadd(dadd(w5n, w[6]), wp7n), wp8);
-                    q2_by[oy + iby] = dmul(s, sc.SF);
+                    if (emit) q2_by[oy + iby] = dmul(s, sc.SF);
                     wp7n = w7n;
                 }
             }
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, IterScal sc, const doubl
             double cv = 0.0;
             if (t == 0) cv = c0[node];
             else if (!cell) cv = c1[node];
-            rhs[cidx] = dadd(first ? 0.0 : acc, cv);
+            if (emit) rhs[cidx] = dadd(first ? 0.0 : acc, cv);
             u0p = u0;
             wp4 = w[4];
             wp8 = w[8];
@@ -545,7 +553,7 @@ void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cu
     dim3 block(TY, TX);
     dim3 grid((unsigned)((a.g.nx + TX - 2) / (TX - 1)), (unsigned)((a.g.ny + TY - 2) / (TY - 1)));
 #define KM(W, O, U)                                                                                          \
-    k_mult<TX, TY, W, O, U><<<grid, block, 0, st>>>(a.g, a.sc, a.q_old, a.q_new, a.alpha, a.weight, a.beta_in, \
+    k_mult<TX, TY, W, O, U><<<grid, block, 0, st>>>(a.g, a.tr, a.sc, a.q_old, a.q_new, a.alpha, a.weight, a.beta_in, \
                                                      a.beta_out, a.q2, a.rhs, a.c0, a.c1)
     if (one_d) {
         if (update) KM(false, true, true); else KM(false, true, false);
@@ -715,7 +723,7 @@ __global__ void __launch_bounds__(256) k_kkt_cells(KktArgs a)
 {
     const Geo& g = a.g;
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int t = a.tr.tc0 + blockIdx.y;
     double s[KC_COUNT];
 #pragma unroll
     for (int k = 0; k < KC_COUNT; k++) s[k] = 0.0;
@@ -777,17 +785,19 @@ __global__ void __launch_bounds__(256) k_kkt_cells(KktArgs a)
 
 int kkt_cells_blocks(const Geo& g) { return (int)((g.P + 255) / 256) * (g.nt - 1); }
 int kkt_nodes_blocks(const Geo& g) { return (int)((g.P + 255) / 256) * g.nt; }
+static int blocks_x(const Geo& g) { return (int)((g.P + 255) / 256); }
 
 void launch_kkt_cells(const KktArgs& a, bool weighted, bool one_d, cudaStream_t st)
 {
-    dim3 grid((unsigned)((a.g.P + 255) / 256), (unsigned)(a.g.nt - 1));
+    const int nl = a.tr.tc1 - a.tr.tc0;
+    dim3 grid((unsigned)blocks_x(a.g), (unsigned)nl);
     if (one_d)
         k_kkt_cells<false, true><<<grid, 256, 0, st>>>(a);
     else if (weighted)
         k_kkt_cells<true, false><<<grid, 256, 0, st>>>(a);
     else
         k_kkt_cells<false, false><<<grid, 256, 0, st>>>(a);
-    k_final_reduce<KC_COUNT><<<1, 256, 0, st>>>(a.partial, kkt_cells_blocks(a.g), a.out);
+    k_final_reduce<KC_COUNT><<<1, 256, 0, st>>>(a.partial, blocks_x(a.g) * nl, a.out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -795,11 +805,11 @@ void launch_kkt_cells(const KktArgs& a, bool weighted, bool one_d, cudaStream_t 
 // block, :141).  zout may alias beta_old (cell-local read-then-write).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool ONE_D>
-__global__ void __launch_bounds__(256) k_zstep(Geo g, IterScal sc, const double* q_old, const double* beta_old, double* zout,
-                                               double* __restrict__ partial)
+__global__ void __launch_bounds__(256) k_zstep(Geo g, int tc0, IterScal sc, const double* q_old, const double* beta_old,
+                                               double* zout, double* __restrict__ partial)
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int t = tc0 + blockIdx.y;
     double s[1] = {0.0};
     if (p < g.P) {
         const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
@@ -816,14 +826,15 @@ __global__ void __launch_bounds__(256) k_zstep(Geo g, IterScal sc, const double*
 }
 
 void launch_zstep(const Geo& g, const IterScal& sc, bool one_d, const double* q_old, const double* beta_old, double* zout,
-                  double* partial, double* out, cudaStream_t st)
+                  double* partial, double* out, cudaStream_t st, const TRange* tr)
 {
-    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)(g.nt - 1));
+    const int tc0 = tr ? tr->tc0 : 0, tc1 = tr ? tr->tc1 : g.nt - 1;
+    dim3 grid((unsigned)blocks_x(g), (unsigned)(tc1 - tc0));
     if (one_d)
-        k_zstep<true><<<grid, 256, 0, st>>>(g, sc, q_old, beta_old, zout, partial);
+        k_zstep<true><<<grid, 256, 0, st>>>(g, tc0, sc, q_old, beta_old, zout, partial);
     else
-        k_zstep<false><<<grid, 256, 0, st>>>(g, sc, q_old, beta_old, zout, partial);
-    k_final_reduce<1><<<1, 256, 0, st>>>(partial, kkt_cells_blocks(g), out);
+        k_zstep<false><<<grid, 256, 0, st>>>(g, tc0, sc, q_old, beta_old, zout, partial);
+    k_final_reduce<1><<<1, 256, 0, st>>>(partial, blocks_x(g) * (tc1 - tc0), out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -834,7 +845,7 @@ __global__ void __launch_bounds__(256) k_kkt_nodes(KktArgs a)
 {
     const Geo& g = a.g;
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int t = a.tr.tn0 + blockIdx.y;
     double s[KN_COUNT];
 #pragma unroll
     for (int k = 0; k < KN_COUNT; k++) s[k] = 0.0;
@@ -917,12 +928,13 @@ __global__ void __launch_bounds__(256) k_kkt_nodes(KktArgs a)
 
 void launch_kkt_nodes(const KktArgs& a, bool weighted, cudaStream_t st)
 {
-    dim3 grid((unsigned)((a.g.P + 255) / 256), (unsigned)a.g.nt);
+    const int nl = a.tr.tn1 - a.tr.tn0;
+    dim3 grid((unsigned)blocks_x(a.g), (unsigned)nl);
     if (weighted)
         k_kkt_nodes<true><<<grid, 256, 0, st>>>(a);
     else
         k_kkt_nodes<false><<<grid, 256, 0, st>>>(a);
-    k_final_reduce<KN_COUNT><<<1, 256, 0, st>>>(a.partial, kkt_nodes_blocks(a.g), a.out);
+    k_final_reduce<KN_COUNT><<<1, 256, 0, st>>>(a.partial, blocks_x(a.g) * nl, a.out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

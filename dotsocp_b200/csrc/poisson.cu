@@ -298,6 +298,7 @@ struct ScaleArgs {     // MODE 2 (t axis): divide the spectrum by D2*((lamY[y] +
     const double* lam_y;
     int ny;
     double D2;
+    i64 line_offset;   // global index of the first line of the array (t-pass on a chunk of (x,y) modes)
 };
 
 // Makhoul index: real element i of the line -> position in v (x[2j] -> v[j], x[2j+1] -> v[n-1-j])
@@ -362,16 +363,16 @@ k_dct_bluestein(LineGeom lg, const double* ain, double* aout, const double2* __r
             double x2 = p.x * v2.x - p.y * v2.y;
             if (MODE == 2) {
                 // spectral division, same operation order as D^2 * ((CY + CX) + CT) and rhs ./ kernel
-                const i64 l1 = line0 + 2 * pair, l2 = l1 + 1;
+                const i64 l1 = sa.line_offset + line0 + 2 * pair, l2 = l1 + 1;
                 {
                     const int xx = (int)(l1 / sa.ny), yy = (int)(l1 - (i64)xx * sa.ny);
-                    double kv = (l1 < lg.inner) ? __dadd_rn(__dadd_rn(sa.lam_y[yy], sa.lam_x[xx]), sa.lam_t[k]) : 1.0;
+                    double kv = (l1 - sa.line_offset < lg.inner) ? __dadd_rn(__dadd_rn(sa.lam_y[yy], sa.lam_x[xx]), sa.lam_t[k]) : 1.0;
                     if (kv == 0.0) kv = 1.0;
                     x1 = x1 / __dmul_rn(sa.D2, kv);
                 }
                 {
                     const int xx = (int)(l2 / sa.ny), yy = (int)(l2 - (i64)xx * sa.ny);
-                    double kv = (l2 < lg.inner) ? __dadd_rn(__dadd_rn(sa.lam_y[yy], sa.lam_x[xx]), sa.lam_t[k]) : 1.0;
+                    double kv = (l2 - sa.line_offset < lg.inner) ? __dadd_rn(__dadd_rn(sa.lam_y[yy], sa.lam_x[xx]), sa.lam_t[k]) : 1.0;
                     if (kv == 0.0) kv = 1.0;
                     x2 = x2 / __dmul_rn(sa.D2, kv);
                 }
@@ -466,9 +467,9 @@ __global__ void __launch_bounds__(256) k_dct_dense(LineGeom lg, int G, const dou
             double acc = 0.0;
             for (int j = 0; j < n; j++) acc += __ldg(&cmat[k * n + j]) * buf0[g * n + j];
             if (MODE == 2) {
-                const i64 l = line0 + g;
+                const i64 l = sa.line_offset + line0 + g;
                 const int xx = (int)(l / sa.ny), yy = (int)(l - (i64)xx * sa.ny);
-                double kv = (l < lg.inner) ? __dadd_rn(__dadd_rn(sa.lam_y[yy], sa.lam_x[xx]), sa.lam_t[k]) : 1.0;
+                double kv = (l - sa.line_offset < lg.inner) ? __dadd_rn(__dadd_rn(sa.lam_y[yy], sa.lam_x[xx]), sa.lam_t[k]) : 1.0;
                 if (kv == 0.0) kv = 1.0;
                 acc = acc / __dmul_rn(sa.D2, kv);
             }
@@ -586,7 +587,7 @@ void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cuda
 {
     // first pass reads rhs and writes a (out of place), the rest works in place on a
     const Geo& g = p->g;
-    ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, D2};
+    ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, D2, 0};
     const i64 xo = (g.ny == 1) ? 1 : g.nt;
     const double* src = rhs;
     if (g.ny > 1) { launch_dct_axis(p->py, geom_y(g), 1, src, a, 0, sa, st); src = a; if (launches) *launches += 1; }
@@ -597,10 +598,40 @@ void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cuda
     if (g.ny > 1) { launch_dct_axis(p->py, geom_y(g), 1, a, a, 1, sa, st); if (launches) *launches += 1; }
 }
 
+// ---- pieces of the solve for a time slab (node levels [tn0, tn0+nlev) of the global array) --------------------------------
+void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev, bool inverse, cudaStream_t st, double* launches)
+{
+    const Geo& g = p->g;
+    ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, 1.0, 0};
+    const i64 off = (i64)tn0 * g.P;
+    LineGeom gy{g.ny, 1, (i64)g.ny, (i64)nlev * g.nx, 0, 1};
+    LineGeom gx = (g.ny == 1) ? LineGeom{g.nx, 1, (i64)g.nx, (i64)nlev, 0, 1} : LineGeom{g.nx, (i64)g.ny, 1, (i64)g.ny, g.P, 0};
+    const i64 xo = (g.ny == 1) ? 1 : nlev;
+    if (!inverse) {
+        const double* s0 = src + off;
+        if (g.ny > 1) { launch_dct_axis(p->py, gy, 1, s0, a + off, 0, sa, st); s0 = a + off; if (launches) *launches += 1; }
+        launch_dct_axis(p->px, gx, xo, s0, a + off, 0, sa, st);
+        if (launches) *launches += 1;
+    } else {
+        launch_dct_axis(p->px, gx, xo, a + off, a + off, 1, sa, st);
+        if (launches) *launches += 1;
+        if (g.ny > 1) { launch_dct_axis(p->py, gy, 1, a + off, a + off, 1, sa, st); if (launches) *launches += 1; }
+    }
+}
+// t-pass (DCT_t, ./kernel, IDCT_t) on a [nt][chunk] array holding the (x,y) modes p0 .. p0+chunk-1
+void poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches)
+{
+    const Geo& g = p->g;
+    ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, D2, p0};
+    LineGeom gt{g.nt, chunk, 1, chunk, 0, 0};
+    launch_dct_axis(p->pt, gt, 1, buf, buf, 2, sa, st);
+    if (launches) *launches += 1;
+}
+
 void poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches)
 {
     const Geo& g = p->g;
-    ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, 1.0};
+    ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, 1.0, 0};
     const int mode = inverse ? 1 : 0;
     if (g.ny > 1) launch_dct_axis(p->py, geom_y(g), 1, a, a, mode, sa, st);
     if (g.nx > 1) launch_dct_axis(p->px, geom_x(g), (g.ny == 1) ? 1 : g.nt, a, a, mode, sa, st);

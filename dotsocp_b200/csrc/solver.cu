@@ -1,12 +1,21 @@
-// solver.cu -- device-resident session, host control loop and the C ABI of libdotsocp.so.
+// solver.cu -- device-resident session (one or several time slabs), host control loop and the session part of the C ABI.
 //
 // The control flow mirrors socp/dot2d/algorithms/solver_socp_inPALM.m line by line (rescaling :138-190, iteration
 // :192-216, KKT :218-324, output :328-357); only the order of the cell-local steps inside one iteration is fused
 // differently (see kernels_update.cu / DESIGN.md): the z-step of iteration i+1 does not depend on phi_{i+1}, so it is
 // evaluated inside the multiplier kernel of iteration i.  All scalar decisions (sigma rule, rescale triggers, stop
 // test) stay on the host in double precision, exactly as in the reference.
+//
+// Multi-GPU: the grid is cut into `world` time slabs.  Every array keeps its global index space (vmm.h) and each slab
+// backs its own levels plus one ghost level per side; per iteration the slabs exchange one ghost plane of phi, the
+// ghost planes of the new q and of alpha_0 (neighbour send/recv) and transpose the spectrum twice (all-to-all) around
+// the t-pass of the Poisson solve; KKT sums are all-reduced.  A process owns either one slab (NCCL between processes,
+// one process per GPU) or -- world > 1 without an NCCL id -- all slabs on its own device ("emulation": the same code
+// path with device-to-device copies instead of NCCL, used to test the slab logic on a single GPU).
 #include "../../include/dotsocp.h"
+#include "errs.h"
 #include "kernels.h"
+#include "vmm.h"
 
 #include <chrono>
 #include <cmath>
@@ -21,7 +30,7 @@ using namespace dsocp;
 
 // ------------------------------------------------------------------------------------------------ error plumbing
 static thread_local char g_err[1024] = "";
-static int set_err(int code, const char* fmt, ...)
+int dsocp_set_err(int code, const char* fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -29,18 +38,10 @@ static int set_err(int code, const char* fmt, ...)
     va_end(ap);
     return code;
 }
-#define CU(call)                                                                                              \
-    do {                                                                                                      \
-        cudaError_t e_ = (call);                                                                              \
-        if (e_ != cudaSuccess)                                                                                \
-            return set_err(e_ == cudaErrorMemoryAllocation ? DOTSOCP_ENOMEM : DOTSOCP_ECUDA, "%s:%d %s: %s", __FILE__, \
-                           __LINE__, #call, cudaGetErrorString(e_));                                          \
-    } while (0)
-
 extern "C" const char* dotsocp_last_error(void) { return g_err; }
-extern "C" int dotsocp_version(void) { return 100; }
+extern "C" int dotsocp_version(void) { return 101; }
 
-static int require_device()
+int dsocp_require_device()
 {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -68,6 +69,11 @@ extern "C" int dotsocp_set_device(int device)
     CU(cudaSetDevice(device));
     return DOTSOCP_OK;
 }
+#define NC(call)                                                                                       \
+    do {                                                                                               \
+        int r_ = (call);                                                                               \
+        if (r_ != 0) return set_err(DOTSOCP_ENCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, nccl_api().GetErrorString(r_)); \
+    } while (0)
 
 // ------------------------------------------------------------------------------------------------ context
 struct EvPool {
@@ -86,35 +92,66 @@ struct EvPool {
     ~EvPool() { for (auto e : ev) cudaEventDestroy(e); }
 };
 
+struct Range { i64 b, e; };
+typedef std::vector<Range> Ranges;
+
+static void add_range(Ranges& r, i64 b, i64 e)
+{
+    if (e <= b) return;
+    if (!r.empty() && r.back().e == b) r.back().e = e;   // merge adjacent pieces (one slab => whole array)
+    else r.push_back({b, e});
+}
+
+struct Slab {
+    int id = 0;
+    TRange tr;
+    int lo_c = 0, hi_c = 0, lo_n = 0, hi_n = 0;   // backed cell layers / node levels (owned + ghosts)
+    i64 p0 = 0, p1 = 0;                           // (x,y) modes this slab solves along t
+    SparseArray a_phi, a_rhs, a_q[2], a_alpha, a_q2, a_qtmp, a_weight, a_beta[2];
+    double *phi = nullptr, *rhs = nullptr, *q[2] = {nullptr, nullptr}, *alpha = nullptr, *q2 = nullptr, *qtmp = nullptr,
+           *weight = nullptr, *beta[2] = {nullptr, nullptr};
+    double *c0 = nullptr, *c1 = nullptr, *partial = nullptr, *dsums = nullptr, *hsums = nullptr;
+    double *tsend = nullptr, *trecv = nullptr;
+    Ranges n_own, n_all, q_own, q_all, b_own, b_all;   // element ranges of node / staggered / 10-column arrays
+    // acc-ADMM / PALM state (single slab only)
+    double* tmpq = nullptr;
+    double* old_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double* anc_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Slab()
+    {
+        cudaFree(c0); cudaFree(c1); cudaFree(partial); cudaFree(dsums); cudaFree(tsend); cudaFree(trecv); cudaFree(tmpq);
+        for (int i = 0; i < 5; i++) { cudaFree(old_[i]); cudaFree(anc_[i]); }
+        if (hsums) cudaFreeHost(hsums);
+    }
+};
+
 struct dotsocp_ctx {
     int variant = 0;
     bool one_d = false, weighted = false;
-    int rank = 0, world = 1;
+    int world = 1;
+    bool emulate = false;       // all slabs in this process
+    int my = 0;                 // first (NCCL mode: only) local slab id
+    void* comm = nullptr;       // ncclComm_t
+    int device = 0;
     Geo g;
     cudaStream_t st = nullptr;
-    double *phi = nullptr, *rhs = nullptr;
-    double* q[2] = {nullptr, nullptr};
-    int qcur = 0;
-    double *alpha = nullptr, *q2 = nullptr, *qtmp = nullptr, *weight = nullptr;
-    double* beta[2] = {nullptr, nullptr};   // beta[bcur] = multiplier; beta[1-bcur] = previous multiplier / materialised z
-    int bcur = 0;
-    bool z_materialised = true;             // beta[1-bcur] holds z itself (after upload / at exit) instead of beta_old
-    double *c0 = nullptr, *c1 = nullptr;
-    double *partial = nullptr, *dsums = nullptr;
-    double* hsums = nullptr;                // pinned
+    std::vector<Slab*> slabs;   // local slabs
+    std::vector<TRange> part;   // partition of all `world` slabs
+    std::vector<i64> pcut;      // mode chunks [pcut[r], pcut[r+1])
+    int qcur = 0, bcur = 0;
+    bool z_materialised = true; // beta[1-bcur] holds z itself (after upload / at exit) instead of beta_old
     PoissonPlan* pp = nullptr;
     double launches = 0;
     bool uploaded = false;
-    // acc-ADMM / PALM state (allocated on demand)
-    double *zmat = nullptr;
-    double *old_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phi, z, q, alpha, beta
-    double *anc_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    // benchmark session (dotsocp_iter_begin .. _end)
     bool iter_open = false;
     IterScal sc;
-    double sigma_fold = 1.0;
-    double D2 = 1.0;
+    double sigma_fold = 1.0, D2 = 1.0;
     EvPool evs;
+    Slab* local(int id) const
+    {
+        for (Slab* s : slabs) if (s->id == id) return s;
+        return nullptr;
+    }
 };
 
 static size_t partial_doubles(const Geo& g)
@@ -128,68 +165,137 @@ static size_t partial_doubles(const Geo& g)
 
 extern "C" int dotsocp_nccl_unique_id(char id128[128])
 {
-    (void)id128;
-    return set_err(DOTSOCP_ENCCL, "multi-GPU sessions are not built into this library version");
+    if (!id128) return set_err(DOTSOCP_EINVAL, "NULL id buffer");
+    const NcclApi& n = nccl_api();
+    if (!n.ok) return set_err(DOTSOCP_ENCCL, "NCCL unavailable: %s", n.why);
+    NcclId id;
+    NC(n.GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return DOTSOCP_OK;
 }
 
 extern "C" void dotsocp_destroy(dotsocp_ctx* c)
 {
     if (!c) return;
-    cudaFree(c->phi); cudaFree(c->rhs); cudaFree(c->q[0]); cudaFree(c->q[1]); cudaFree(c->alpha); cudaFree(c->q2);
-    cudaFree(c->qtmp); cudaFree(c->weight); cudaFree(c->beta[0]); cudaFree(c->beta[1]); cudaFree(c->c0); cudaFree(c->c1);
-    cudaFree(c->partial); cudaFree(c->dsums); cudaFree(c->zmat);
-    for (int i = 0; i < 5; i++) { cudaFree(c->old_[i]); cudaFree(c->anc_[i]); }
-    if (c->hsums) cudaFreeHost(c->hsums);
+    if (c->st) cudaStreamSynchronize(c->st);
+    for (Slab* s : c->slabs) delete s;
+    if (c->comm && nccl_api().ok) nccl_api().CommDestroy(c->comm);
     poisson_plan_destroy(c->pp);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
 
+static int make_slab(dotsocp_ctx* c, int id)
+{
+    const Geo& g = c->g;
+    Slab* s = new Slab();
+    c->slabs.push_back(s);
+    s->id = id;
+    s->tr = c->part[id];
+    const TRange& tr = s->tr;
+    const bool dense = c->world == 1;
+    s->lo_c = tr.tc0 > 0 ? tr.tc0 - 1 : 0;
+    s->hi_c = tr.tc1 < g.nt - 1 ? tr.tc1 + 1 : g.nt - 1;
+    s->lo_n = tr.tn0 > 0 ? tr.tn0 - 1 : 0;
+    s->hi_n = tr.tn1 < g.nt ? tr.tn1 + 1 : g.nt;
+    s->p0 = c->pcut[id];
+    s->p1 = c->pcut[id + 1];
+    add_range(s->n_own, tr.tn0 * g.P, tr.tn1 * g.P);
+    add_range(s->n_all, s->lo_n * g.P, s->hi_n * g.P);
+    add_range(s->q_own, tr.tc0 * g.P, tr.tc1 * g.P);
+    add_range(s->q_own, g.L + tr.tn0 * g.PBX, g.L + tr.tn1 * g.PBX);
+    add_range(s->q_own, g.L + g.NBX + tr.tn0 * g.PBY, g.L + g.NBX + tr.tn1 * g.PBY);
+    add_range(s->q_all, s->lo_c * g.P, s->hi_c * g.P);
+    add_range(s->q_all, g.L + s->lo_n * g.PBX, g.L + s->hi_n * g.PBX);
+    add_range(s->q_all, g.L + g.NBX + s->lo_n * g.PBY, g.L + g.NBX + s->hi_n * g.PBY);
+    for (int j = 0; j < 10; j++) {
+        add_range(s->b_own, j * g.L + tr.tc0 * g.P, j * g.L + tr.tc1 * g.P);
+        add_range(s->b_all, j * g.L + s->lo_c * g.P, j * g.L + s->hi_c * g.P);
+    }
+    auto win = [](const Ranges& r) {
+        std::vector<std::pair<long long, long long>> w;
+        for (auto& x : r) w.emplace_back(x.b, x.e);
+        return w;
+    };
+    const char* why = "";
+#define MK(arr, count, ranges)                                                                        \
+    do {                                                                                              \
+        int e_ = arr.create((count), win(ranges), dense, c->device, &why);                            \
+        if (e_) return set_err(e_ == 2 ? DOTSOCP_ENOMEM : DOTSOCP_ECUDA, "device array of %lld doubles: %s", (long long)(count), why); \
+    } while (0)
+    MK(s->a_phi, g.N, s->n_all); MK(s->a_rhs, g.N, s->n_all);
+    MK(s->a_q[0], g.Q, s->q_all); MK(s->a_q[1], g.Q, s->q_all); MK(s->a_alpha, g.Q, s->q_all); MK(s->a_q2, g.Q, s->q_all);
+    MK(s->a_qtmp, g.Q, s->q_all);
+    if (c->weighted) MK(s->a_weight, g.Q, s->q_all);
+    MK(s->a_beta[0], 10 * g.L, s->b_all); MK(s->a_beta[1], 10 * g.L, s->b_all);
+#undef MK
+    s->phi = s->a_phi.ptr(); s->rhs = s->a_rhs.ptr(); s->q[0] = s->a_q[0].ptr(); s->q[1] = s->a_q[1].ptr();
+    s->alpha = s->a_alpha.ptr(); s->q2 = s->a_q2.ptr(); s->qtmp = s->a_qtmp.ptr();
+    s->weight = c->weighted ? s->a_weight.ptr() : nullptr;
+    s->beta[0] = s->a_beta[0].ptr(); s->beta[1] = s->a_beta[1].ptr();
+    CU(cudaMalloc(&s->c0, g.P * sizeof(double)));
+    CU(cudaMalloc(&s->c1, g.P * sizeof(double)));
+    CU(cudaMemsetAsync(s->c0, 0, g.P * sizeof(double), c->st));
+    CU(cudaMemsetAsync(s->c1, 0, g.P * sizeof(double), c->st));
+    CU(cudaMalloc(&s->partial, partial_doubles(g) * sizeof(double)));
+    CU(cudaMalloc(&s->dsums, 64 * sizeof(double)));
+    CU(cudaMallocHost(&s->hsums, 64 * sizeof(double)));
+    if (c->world > 1) {
+        CU(cudaMalloc(&s->tsend, (size_t)(tr.tn1 - tr.tn0) * g.P * sizeof(double)));
+        CU(cudaMalloc(&s->trecv, (size_t)g.nt * (s->p1 - s->p0) * sizeof(double)));
+    }
+    return 0;
+}
+
 extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id)
 {
-    (void)nccl_id;
     if (!out) return set_err(DOTSOCP_EINVAL, "ctx pointer is NULL");
     *out = nullptr;
     if (variant < 0 || variant > 2) return set_err(DOTSOCP_EINVAL, "unknown variant %d", variant);
     if (nt < 2 || nx < 2 || ny < 1) return set_err(DOTSOCP_EINVAL, "grid %d x %d x %d too small (need nt,nx >= 2)", nt, nx, ny);
     if (variant == DOTSOCP_VARIANT_DOT1D && ny != 1) return set_err(DOTSOCP_EINVAL, "1-D variant needs ny == 1");
     if (variant != DOTSOCP_VARIANT_DOT1D && ny < 2) return set_err(DOTSOCP_EINVAL, "2-D variants need ny >= 2");
-    if (world != 1 || rank != 0) return set_err(DOTSOCP_EINVAL, "world=%d: time-slab multi-GPU sessions are not available in this build", world);
+    if (world < 1 || rank < 0 || rank >= world) return set_err(DOTSOCP_EINVAL, "bad rank %d / world %d", rank, world);
+    if (world > nt - 1) return set_err(DOTSOCP_EINVAL, "world %d exceeds the %d cell layers", world, nt - 1);
     int rc = require_device();
     if (rc) return rc;
     dotsocp_ctx* c = new dotsocp_ctx();
     c->variant = variant;
     c->one_d = variant == DOTSOCP_VARIANT_DOT1D;
     c->weighted = variant == DOTSOCP_VARIANT_WDOT2D;
-    c->rank = rank;
     c->world = world;
+    c->emulate = world > 1 && nccl_id == nullptr;
+    c->my = c->emulate ? 0 : rank;
     c->g = make_geo(nt, nx, ny);
     const Geo& g = c->g;
-#define ALLOC(ptr, count)                                                                              \
-    do {                                                                                               \
-        cudaError_t e_ = cudaMalloc(&(ptr), (size_t)(count) * sizeof(double));                          \
-        if (e_ != cudaSuccess) {                                                                       \
-            cudaGetLastError();                                                                        \
-            int code_ = set_err(DOTSOCP_ENOMEM, "cudaMalloc of %zu bytes failed: %s",                   \
-                                (size_t)(count) * sizeof(double), cudaGetErrorString(e_));              \
-            dotsocp_destroy(c);                                                                        \
-            return code_;                                                                              \
-        }                                                                                              \
-    } while (0)
-    ALLOC(c->phi, g.N); ALLOC(c->rhs, g.N);
-    ALLOC(c->q[0], g.Q); ALLOC(c->q[1], g.Q); ALLOC(c->alpha, g.Q); ALLOC(c->q2, g.Q); ALLOC(c->qtmp, g.Q);
-    if (c->weighted) ALLOC(c->weight, g.Q);
-    ALLOC(c->beta[0], 10 * g.L); ALLOC(c->beta[1], 10 * g.L);
-    ALLOC(c->c0, g.P); ALLOC(c->c1, g.P);
-    ALLOC(c->partial, partial_doubles(g)); ALLOC(c->dsums, 64);
-#undef ALLOC
-    if (cudaMallocHost(&c->hsums, 64 * sizeof(double)) != cudaSuccess) {
-        dotsocp_destroy(c);
-        return set_err(DOTSOCP_ENOMEM, "cudaMallocHost failed");
+    cudaGetDevice(&c->device);
+    for (int r = 0; r < world; r++) {
+        TRange tr;
+        tr.tc0 = (int)((i64)r * (nt - 1) / world);
+        tr.tc1 = (int)((i64)(r + 1) * (nt - 1) / world);
+        tr.tn0 = tr.tc0;
+        tr.tn1 = (r == world - 1) ? nt : tr.tc1;
+        c->part.push_back(tr);
     }
+    for (int r = 0; r <= world; r++) c->pcut.push_back((i64)r * g.P / world);
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
         dotsocp_destroy(c);
         return set_err(DOTSOCP_ECUDA, "cudaStreamCreate failed");
+    }
+    if (world > 1 && !c->emulate) {
+        const NcclApi& n = nccl_api();
+        if (!n.ok) { dotsocp_destroy(c); return set_err(DOTSOCP_ENCCL, "NCCL unavailable: %s", n.why); }
+        NcclId id;
+        memcpy(id.internal, nccl_id, 128);
+        int r_ = n.CommInitRank(&c->comm, world, id, rank);
+        if (r_ != 0) { c->comm = nullptr; dotsocp_destroy(c); return set_err(DOTSOCP_ENCCL, "ncclCommInitRank: %s", n.GetErrorString(r_)); }
+    }
+    if (c->emulate) {
+        for (int r = 0; r < world; r++)
+            if ((rc = make_slab(c, r))) { dotsocp_destroy(c); return rc; }
+    } else if ((rc = make_slab(c, rank))) {
+        dotsocp_destroy(c);
+        return rc;
     }
     c->pp = poisson_plan_create(nt, nx, ny);
     cudaError_t e = cudaGetLastError();
@@ -203,38 +309,185 @@ extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, in
 
 extern "C" double dotsocp_launch_count(const dotsocp_ctx* c) { return c ? c->launches : 0.0; }
 
-static int upload_cols(dotsocp_ctx* c, double* dst10, const double* src)
+// ------------------------------------------------------------------------------------------------ slab communication
+// move `count` doubles at element offset `off` of the array selected by `sel` from slab `from` to slab `to`
+typedef double* (*ArrSel)(Slab*, int);
+static double* sel_phi(Slab* s, int) { return s->phi; }
+static double* sel_q(Slab* s, int k) { return s->q[k]; }
+static double* sel_alpha(Slab* s, int) { return s->alpha; }
+static double* sel_beta(Slab* s, int k) { return s->beta[k]; }
+static double* sel_weight(Slab* s, int) { return s->weight; }
+
+struct Xfer { ArrSel sel; int k; i64 off, count; int from, to; };
+
+static int do_xfers(dotsocp_ctx* c, const std::vector<Xfer>& xs)
 {
-    const Geo& g = c->g;
-    if (!c->one_d) {
-        CU(cudaMemcpyAsync(dst10, src, (size_t)10 * g.L * sizeof(double), cudaMemcpyHostToDevice, c->st));
-        return 0;
+    if (xs.empty()) return 0;
+    const NcclApi& n = nccl_api();
+    bool grouped = false;
+    for (const Xfer& x : xs) {
+        if (x.count <= 0) continue;
+        Slab* a = c->local(x.from);
+        Slab* b = c->local(x.to);
+        if (a && b) {
+            CU(cudaMemcpyAsync(x.sel(b, x.k) + x.off, x.sel(a, x.k) + x.off, (size_t)x.count * sizeof(double),
+                               cudaMemcpyDeviceToDevice, c->st));
+        } else if (a || b) {
+            if (!grouped) { NC(n.GroupStart()); grouped = true; }
+            if (a) NC(n.Send(x.sel(a, x.k) + x.off, (size_t)x.count, NCCL_FLOAT64, x.to, c->comm, c->st));
+            else NC(n.Recv(x.sel(b, x.k) + x.off, (size_t)x.count, NCCL_FLOAT64, x.from, c->comm, c->st));
+        }
     }
-    // 6 columns at the boundary: stage through qtmp/rhs-sized scratch is too small in general, use a temporary
-    double* tmp = nullptr;
-    CU(cudaMalloc(&tmp, (size_t)6 * g.L * sizeof(double)));
-    CU(cudaMemcpyAsync(tmp, src, (size_t)6 * g.L * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    launch_cols6to10(tmp, dst10, g.L, c->st);
-    c->launches += 1;
-    CU(cudaStreamSynchronize(c->st));
-    cudaFree(tmp);
+    if (grouped) NC(n.GroupEnd());
     return 0;
 }
 
-static int download_cols(dotsocp_ctx* c, double* dst, const double* src10)
+// ghost exchanges across every slab boundary (node level T between slab r and r+1)
+enum { GH_PHI_UP = 1, GH_Q_UP = 2, GH_Q_DOWN = 4, GH_ALPHA0_DOWN = 8, GH_BETA_DOWN = 16, GH_W = 32 };
+static int ghosts(dotsocp_ctx* c, int what, int qk, int bk)
+{
+    if (c->world == 1) return 0;
+    const Geo& g = c->g;
+    std::vector<Xfer> xs;
+    for (int r = 0; r + 1 < c->world; r++) {
+        const i64 T = c->part[r].tn1;   // == part[r+1].tn0
+        if (what & GH_PHI_UP) xs.push_back({sel_phi, 0, T * g.P, g.P, r + 1, r});
+        if (what & GH_Q_UP) {
+            xs.push_back({sel_q, qk, g.L + T * g.PBX, g.PBX, r + 1, r});
+            xs.push_back({sel_q, qk, g.L + g.NBX + T * g.PBY, g.PBY, r + 1, r});
+        }
+        if (what & GH_Q_DOWN) {
+            xs.push_back({sel_q, qk, (T - 1) * g.P, g.P, r, r + 1});
+            xs.push_back({sel_q, qk, g.L + (T - 1) * g.PBX, g.PBX, r, r + 1});
+            xs.push_back({sel_q, qk, g.L + g.NBX + (T - 1) * g.PBY, g.PBY, r, r + 1});
+        }
+        if (what & GH_ALPHA0_DOWN) xs.push_back({sel_alpha, 0, (T - 1) * g.P, g.P, r, r + 1});
+        if (what & GH_BETA_DOWN)
+            for (int j = 0; j < 10; j++) xs.push_back({sel_beta, bk, j * g.L + (T - 1) * g.P, g.P, r, r + 1});
+        if ((what & GH_W) && c->weighted) {
+            xs.push_back({sel_weight, 0, g.L + T * g.PBX, g.PBX, r + 1, r});
+            xs.push_back({sel_weight, 0, g.L + g.NBX + T * g.PBY, g.PBY, r + 1, r});
+            xs.push_back({sel_weight, 0, (T - 1) * g.P, g.P, r, r + 1});
+            xs.push_back({sel_weight, 0, g.L + (T - 1) * g.PBX, g.PBX, r, r + 1});
+            xs.push_back({sel_weight, 0, g.L + g.NBX + (T - 1) * g.PBY, g.PBY, r, r + 1});
+        }
+    }
+    return do_xfers(c, xs);
+}
+
+// Poisson solve: rhs -> phi.  One slab: 5 in-place passes.  Several slabs: (y,x) forward locally, transpose so that
+// every slab holds all t for its chunk of (x,y) modes, t-pass, transpose back, (x,y) inverse.
+static int solve_poisson(dotsocp_ctx* c, double D2)
 {
     const Geo& g = c->g;
-    if (!c->one_d) {
-        CU(cudaMemcpyAsync(dst, src10, (size_t)10 * g.L * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    if (c->world == 1) {
+        Slab* s = c->slabs[0];
+        poisson_solve(c->pp, s->rhs, s->phi, D2, c->st, &c->launches);
         return 0;
     }
-    double* tmp = nullptr;
-    CU(cudaMalloc(&tmp, (size_t)6 * g.L * sizeof(double)));
-    launch_cols10to6(src10, tmp, g.L, c->st);
-    c->launches += 1;
-    CU(cudaMemcpyAsync(dst, tmp, (size_t)6 * g.L * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));
-    cudaFree(tmp);
+    const NcclApi& n = nccl_api();
+    for (Slab* s : c->slabs) {
+        poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0, s->tr.tn1 - s->tr.tn0, false, c->st, &c->launches);
+        // pack: block r of the send buffer = rows of this slab x modes of slab r
+        const int nlev = s->tr.tn1 - s->tr.tn0;
+        for (int r = 0; r < c->world; r++) {
+            const i64 ch = c->pcut[r + 1] - c->pcut[r];
+            CU(cudaMemcpy2DAsync(s->tsend + (i64)nlev * c->pcut[r], ch * sizeof(double), s->phi + s->tr.tn0 * g.P + c->pcut[r],
+                                 g.P * sizeof(double), ch * sizeof(double), nlev, cudaMemcpyDeviceToDevice, c->st));
+        }
+    }
+    auto all_to_all = [&](bool forward) -> int {
+        bool grouped = false;
+        for (int a = 0; a < c->world; a++)          // a: owner of the time rows
+            for (int b = 0; b < c->world; b++) {    // b: owner of the mode chunk
+                Slab* sa = c->local(a);
+                Slab* sb = c->local(b);
+                if (!sa && !sb) continue;
+                const int nlev = c->part[a].tn1 - c->part[a].tn0;
+                const i64 ch = c->pcut[b + 1] - c->pcut[b];
+                const size_t cnt = (size_t)nlev * ch;
+                double* pa = sa ? sa->tsend + (i64)nlev * c->pcut[b] : nullptr;
+                double* pb = sb ? sb->trecv + (i64)c->part[a].tn0 * ch : nullptr;
+                if (sa && sb) {
+                    CU(cudaMemcpyAsync(forward ? pb : pa, forward ? pa : pb, cnt * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+                } else {
+                    if (!grouped) { NC(n.GroupStart()); grouped = true; }
+                    if (forward) {
+                        if (sa) NC(n.Send(pa, cnt, NCCL_FLOAT64, b, c->comm, c->st));
+                        else NC(n.Recv(pb, cnt, NCCL_FLOAT64, a, c->comm, c->st));
+                    } else {
+                        if (sb) NC(n.Send(pb, cnt, NCCL_FLOAT64, a, c->comm, c->st));
+                        else NC(n.Recv(pa, cnt, NCCL_FLOAT64, b, c->comm, c->st));
+                    }
+                }
+            }
+        if (grouped) NC(n.GroupEnd());
+        return 0;
+    };
+    int rc = all_to_all(true);
+    if (rc) return rc;
+    for (Slab* s : c->slabs) poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches);
+    if ((rc = all_to_all(false))) return rc;
+    for (Slab* s : c->slabs) {
+        const int nlev = s->tr.tn1 - s->tr.tn0;
+        for (int r = 0; r < c->world; r++) {
+            const i64 ch = c->pcut[r + 1] - c->pcut[r];
+            CU(cudaMemcpy2DAsync(s->phi + s->tr.tn0 * g.P + c->pcut[r], g.P * sizeof(double), s->tsend + (i64)nlev * c->pcut[r],
+                                 ch * sizeof(double), ch * sizeof(double), nlev, cudaMemcpyDeviceToDevice, c->st));
+        }
+        poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0, s->tr.tn1 - s->tr.tn0, true, c->st, &c->launches);
+    }
+    return ghosts(c, GH_PHI_UP, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ upload / download
+// Host layout: world == 1 or emulation -> GLOBAL arrays; NCCL mode -> the slab's owned part only:
+//   phi, c : owned node levels ; q, alpha, weight : [q0 owned cells | bx owned levels | by owned levels] ;
+//   z, beta: ncol columns of (owned cells) doubles, column-major.
+struct HostMap {
+    bool local;
+    const Geo* g;
+    TRange tr;
+    i64 nodes(i64 t) const { return (local ? t - tr.tn0 : t) * g->P; }
+    i64 q0(i64 t) const { return (local ? t - tr.tc0 : t) * g->P; }
+    i64 bx(i64 t) const { return local ? (i64)(tr.tc1 - tr.tc0) * g->P + (t - tr.tn0) * g->PBX : g->L + t * g->PBX; }
+    i64 by(i64 t) const
+    {
+        return local ? (i64)(tr.tc1 - tr.tc0) * g->P + (i64)(tr.tn1 - tr.tn0) * g->PBX + (t - tr.tn0) * g->PBY : g->L + g->NBX + t * g->PBY;
+    }
+    i64 col(int j, i64 t) const { return local ? (i64)j * (tr.tc1 - tr.tc0) * g->P + (t - tr.tc0) * g->P : (i64)j * g->L + t * g->P; }
+};
+
+static int copy_stag(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev, double* host, bool up)
+{
+    const Geo& g = c->g;
+    const TRange& tr = s->tr;
+    struct P { i64 d, h, n; } parts[3] = {{tr.tc0 * g.P, hm.q0(tr.tc0), (i64)(tr.tc1 - tr.tc0) * g.P},
+                                          {g.L + tr.tn0 * g.PBX, hm.bx(tr.tn0), (i64)(tr.tn1 - tr.tn0) * g.PBX},
+                                          {g.L + g.NBX + tr.tn0 * g.PBY, hm.by(tr.tn0), (i64)(tr.tn1 - tr.tn0) * g.PBY}};
+    for (auto& p : parts) {
+        if (p.n <= 0) continue;
+        if (up) CU(cudaMemcpyAsync(dev + p.d, host + p.h, p.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        else CU(cudaMemcpyAsync(host + p.h, dev + p.d, p.n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    }
+    return 0;
+}
+
+static int copy_cols(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev10, double* host, bool up)
+{
+    const Geo& g = c->g;
+    const TRange& tr = s->tr;
+    const i64 n = (i64)(tr.tc1 - tr.tc0) * g.P;
+    const int ncol = c->one_d ? 6 : 10;
+    // 1-D variant: 6 columns at the boundary (c0..c4 -> 0..4, c5 -> 9; columns 5..8 are structural zeros on the device)
+    for (int jh = 0; jh < ncol; jh++) {
+        const int j = (c->one_d && jh == 5) ? 9 : jh;
+        if (up) CU(cudaMemcpyAsync(dev10 + j * g.L + tr.tc0 * g.P, host + hm.col(jh, tr.tc0), n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        else CU(cudaMemcpyAsync(host + hm.col(jh, tr.tc0), dev10 + j * g.L + tr.tc0 * g.P, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    }
+    if (up && c->one_d)
+        for (int j = 5; j < 9; j++)
+            CU(cudaMemsetAsync(dev10 + j * g.L + s->lo_c * g.P, 0, (size_t)(s->hi_c - s->lo_c) * g.P * sizeof(double), c->st));
     return 0;
 }
 
@@ -244,23 +497,32 @@ extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q
     if (!c || !phi || !q || !z || !alpha || !beta || !cvec) return set_err(DOTSOCP_EINVAL, "NULL array");
     if (c->weighted && !weight) return set_err(DOTSOCP_EINVAL, "weighted variant needs weight");
     const Geo& g = c->g;
-    // c is -rho0/ht on the first time level, +rho1/ht on the last and zero in between (initialize.m:41-44); only the two
-    // planes are kept on the device.
-    for (i64 i = g.P; i < g.N - g.P; i++)
-        if (cvec[i] != 0.0) return set_err(DOTSOCP_EINVAL, "model.c has a non-zero interior entry at %lld: unsupported", (long long)i);
     c->qcur = 0;
     c->bcur = 0;
-    CU(cudaMemcpyAsync(c->phi, phi, g.N * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    CU(cudaMemcpyAsync(c->q[0], q, g.Q * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    CU(cudaMemcpyAsync(c->alpha, alpha, g.Q * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    if (c->weighted) CU(cudaMemcpyAsync(c->weight, weight, g.Q * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    CU(cudaMemcpyAsync(c->c0, cvec, g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    CU(cudaMemcpyAsync(c->c1, cvec + (g.N - g.P), g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    int rc = upload_cols(c, c->beta[0], beta);
-    if (rc) return rc;
-    rc = upload_cols(c, c->beta[1], z);
-    if (rc) return rc;
+    for (Slab* s : c->slabs) {
+        HostMap hm{c->world > 1 && !c->emulate, &g, s->tr};
+        const TRange& tr = s->tr;
+        // c is -rho0/ht on the first time level, +rho1/ht on the last and zero in between (initialize.m:41-44); only the
+        // two planes are kept on the device.
+        for (i64 t = tr.tn0; t < tr.tn1; t++) {
+            if (t == 0 || t == g.nt - 1) continue;
+            const double* row = cvec + hm.nodes(t);
+            for (i64 i = 0; i < g.P; i++)
+                if (row[i] != 0.0) return set_err(DOTSOCP_EINVAL, "model.c has a non-zero interior entry (t=%lld): unsupported", (long long)t);
+        }
+        CU(cudaMemcpyAsync(s->phi + tr.tn0 * g.P, phi + hm.nodes(tr.tn0), (size_t)(tr.tn1 - tr.tn0) * g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        int rc;
+        if ((rc = copy_stag(c, s, hm, s->q[0], const_cast<double*>(q), true))) return rc;
+        if ((rc = copy_stag(c, s, hm, s->alpha, const_cast<double*>(alpha), true))) return rc;
+        if (c->weighted && (rc = copy_stag(c, s, hm, s->weight, const_cast<double*>(weight), true))) return rc;
+        if (tr.tn0 == 0) CU(cudaMemcpyAsync(s->c0, cvec + hm.nodes(0), g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        if (tr.tn1 == g.nt) CU(cudaMemcpyAsync(s->c1, cvec + hm.nodes(g.nt - 1), g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        if ((rc = copy_cols(c, s, hm, s->beta[0], const_cast<double*>(beta), true))) return rc;
+        if ((rc = copy_cols(c, s, hm, s->beta[1], const_cast<double*>(z), true))) return rc;
+    }
     c->z_materialised = true;
+    int rc = ghosts(c, GH_PHI_UP | GH_Q_UP | GH_Q_DOWN | GH_ALPHA0_DOWN | GH_BETA_DOWN | GH_W, 0, 0);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(c->st));
     c->uploaded = true;
     return DOTSOCP_OK;
@@ -272,11 +534,16 @@ extern "C" int dotsocp_download(dotsocp_ctx* c, double* phi, double* q, double* 
     if (!c->uploaded) return set_err(DOTSOCP_ESTATE, "download before upload");
     if (!c->z_materialised && z) return set_err(DOTSOCP_ESTATE, "z is not materialised (session still open)");
     const Geo& g = c->g;
-    if (phi) CU(cudaMemcpyAsync(phi, c->phi, g.N * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    if (q) CU(cudaMemcpyAsync(q, c->q[c->qcur], g.Q * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    if (alpha) CU(cudaMemcpyAsync(alpha, c->alpha, g.Q * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    if (beta) { int rc = download_cols(c, beta, c->beta[c->bcur]); if (rc) return rc; }
-    if (z) { int rc = download_cols(c, z, c->beta[1 - c->bcur]); if (rc) return rc; }
+    for (Slab* s : c->slabs) {
+        HostMap hm{c->world > 1 && !c->emulate, &g, s->tr};
+        const TRange& tr = s->tr;
+        int rc;
+        if (phi) CU(cudaMemcpyAsync(phi + hm.nodes(tr.tn0), s->phi + tr.tn0 * g.P, (size_t)(tr.tn1 - tr.tn0) * g.P * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        if (q && (rc = copy_stag(c, s, hm, s->q[c->qcur], q, false))) return rc;
+        if (alpha && (rc = copy_stag(c, s, hm, s->alpha, alpha, false))) return rc;
+        if (beta && (rc = copy_cols(c, s, hm, s->beta[c->bcur], beta, false))) return rc;
+        if (z && (rc = copy_cols(c, s, hm, s->beta[1 - c->bcur], z, false))) return rc;
+    }
     CU(cudaStreamSynchronize(c->st));
     return DOTSOCP_OK;
 }
@@ -344,62 +611,108 @@ static IterScal make_scal(const dotsocp_level_opts& o, double D, double E, doubl
     return sc;
 }
 
+enum ArrKind { A_PHI, A_Q, A_ALPHA, A_BETA, A_ZMAT, A_C };
+
 struct Loop {
     dotsocp_ctx* c;
-    const dotsocp_level_opts* o;
     IterScal sc;
-    UpdateArgs ua() const
+    double sc_D2 = 1.0;
+    UpdateArgs ua(Slab* s) const
     {
         UpdateArgs a;
-        a.g = c->g; a.sc = sc; a.phi = c->phi; a.q_old = c->q[c->qcur]; a.q_new = c->q[1 - c->qcur];
-        a.alpha = c->alpha; a.weight = c->weight; a.beta_in = c->beta[c->bcur]; a.beta_out = c->beta[1 - c->bcur];
-        a.q2 = c->q2; a.rhs = c->rhs; a.c0 = c->c0; a.c1 = c->c1;
+        a.g = c->g; a.tr = s->tr; a.sc = sc; a.phi = s->phi; a.q_old = s->q[c->qcur]; a.q_new = s->q[1 - c->qcur];
+        a.alpha = s->alpha; a.weight = s->weight; a.beta_in = s->beta[c->bcur]; a.beta_out = s->beta[1 - c->bcur];
+        a.q2 = s->q2; a.rhs = s->rhs; a.c0 = s->c0; a.c1 = s->c1;
         return a;
     }
     // q2, rhs from the current (q, alpha, beta): the z-step part of the first iteration / after any rescaling
     void prologue()
     {
-        UpdateArgs a = ua();
-        a.q_old = nullptr;
-        a.q_new = c->q[c->qcur];
-        a.beta_out = nullptr;
-        launch_mult(a, c->weighted, c->one_d, false, c->st);
-        c->launches += 1;
+        for (Slab* s : c->slabs) {
+            UpdateArgs a = ua(s);
+            a.q_old = nullptr;
+            a.q_new = s->q[c->qcur];
+            a.beta_out = nullptr;
+            launch_mult(a, c->weighted, c->one_d, false, c->st);
+            c->launches += 1;
+        }
     }
-    void step_phi()
+    int step_phi() { return solve_poisson(c, sc_D2); }
+    int step_q(bool acc)
     {
-        poisson_solve(c->pp, c->rhs, c->phi, sc_D2, c->st, &c->launches);
-    }
-    void step_q(bool acc)
-    {
-        launch_qstep(ua(), c->weighted, acc, c->st);
-        c->launches += 1;
+        for (Slab* s : c->slabs) {
+            launch_qstep(ua(s), c->weighted, acc, c->st);
+            c->launches += 1;
+        }
+        return ghosts(c, GH_Q_UP | GH_Q_DOWN | GH_ALPHA0_DOWN, 1 - c->qcur, 0);
     }
     void step_mult()
     {
-        launch_mult(ua(), c->weighted, c->one_d, true, c->st);
-        c->launches += 1;
+        for (Slab* s : c->slabs) {
+            launch_mult(ua(s), c->weighted, c->one_d, true, c->st);
+            c->launches += 1;
+        }
         c->qcur ^= 1;
         c->bcur ^= 1;
         c->z_materialised = false;
     }
-    double sc_D2 = 1.0;
+    // x = (x*mul)/div on every backed window (owned + ghost copies, so the ghosts stay consistent without traffic)
+    void scale(ArrKind k, double mul, double div)
+    {
+        const Geo& g = c->g;
+        for (Slab* s : c->slabs) {
+            if (k == A_C) {
+                launch_scale(s->c0, g.P, mul, div, c->st);
+                launch_scale(s->c1, g.P, mul, div, c->st);
+                c->launches += 2;
+                continue;
+            }
+            double* base = k == A_PHI ? s->phi : k == A_Q ? s->q[c->qcur] : k == A_ALPHA ? s->alpha
+                         : k == A_BETA ? s->beta[c->bcur] : s->beta[1 - c->bcur];
+            const Ranges& r = k == A_PHI ? s->n_all : (k == A_Q || k == A_ALPHA) ? s->q_all : s->b_all;
+            for (auto& x : r) { launch_scale(base + x.b, x.e - x.b, mul, div, c->st); c->launches += 1; }
+        }
+    }
 };
 
-static int fetch_sums(dotsocp_ctx* c, int count)
+// sum over all slabs (and processes) of `count` per-slab device sums; result in out[]
+static int reduce_sums(dotsocp_ctx* c, int count, double* out)
 {
-    CU(cudaMemcpyAsync(c->hsums, c->dsums, count * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    for (Slab* s : c->slabs) CU(cudaMemcpyAsync(s->hsums, s->dsums, count * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < count; i++) out[i] = 0.0;
+    for (Slab* s : c->slabs)
+        for (int i = 0; i < count; i++) out[i] += s->hsums[i];
+    if (c->comm) {
+        Slab* s = c->slabs[0];
+        for (int i = 0; i < count; i++) s->hsums[i] = out[i];
+        CU(cudaMemcpyAsync(s->dsums, s->hsums, count * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        NC(nccl_api().AllReduce(s->dsums, s->dsums, (size_t)count, NCCL_FLOAT64, NCCL_SUM, c->comm, c->st));
+        CU(cudaMemcpyAsync(s->hsums, s->dsums, count * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        for (int i = 0; i < count; i++) out[i] = s->hsums[i];
+    }
     return 0;
 }
 
-static int sumsq_host(dotsocp_ctx* c, const double* x, i64 n, double* out)
+// sum of squares of the owned part of an array
+static int sumsq_owned(dotsocp_ctx* c, ArrKind k, double* out)
 {
-    launch_sumsq(x, n, c->partial, c->dsums, c->st);
-    c->launches += 2;
-    int rc = fetch_sums(c, 1);
+    const int maxr = 10;
+    for (Slab* s : c->slabs) {
+        double* base = k == A_PHI ? s->phi : k == A_Q ? s->q[c->qcur] : k == A_ALPHA ? s->alpha
+                     : k == A_BETA ? s->beta[c->bcur] : s->beta[1 - c->bcur];
+        const Ranges& r = k == A_PHI ? s->n_own : (k == A_Q || k == A_ALPHA) ? s->q_own : s->b_own;
+        int i = 0;
+        for (auto& x : r) { launch_sumsq(base + x.b, x.e - x.b, s->partial, s->dsums + i, c->st); c->launches += 2; i++; }
+        for (; i < maxr; i++) CU(cudaMemsetAsync(s->dsums + i, 0, sizeof(double), c->st));
+    }
+    double v[maxr];
+    int rc = reduce_sums(c, maxr, v);
     if (rc) return rc;
-    *out = c->hsums[0];
+    double t = 0;
+    for (int i = 0; i < maxr; i++) t += v[i];
+    *out = t;
     return 0;
 }
 
@@ -409,11 +722,6 @@ static double now_s()
     return duration<double>(steady_clock::now().time_since_epoch()).count();
 }
 
-// ------------------------------------------------------------------------------------------------ the level loops
-// One function for the three reference loops; the shared parts (rescaling, KKT, sigma rule, output) are literally the
-// same code in solver_socp_inPALM.m, solver_socp_PALM.m and solver_socp_accADMM.m, only the iteration body differs.
-//   inPALM / ALG2 : fused kernels, z never stored (recomputed from (q_old, beta_old) where the reference reads it)
-//   PALM, acc-ADMM: z is genuine state (it enters the first q-step / the extrapolation), kept in beta[1-bcur]
 static int ensure_alloc(double*& p, i64 n)
 {
     if (p) return 0;
@@ -422,6 +730,28 @@ static int ensure_alloc(double*& p, i64 n)
     return 0;
 }
 
+// z = Pi_Q(d + BF q_old - beta_old) of the owned cells: optional store over beta_old, sum of squares
+static int zstep_all(dotsocp_ctx* c, const IterScal& sc, bool store, double* sumsq)
+{
+    for (Slab* s : c->slabs) {
+        launch_zstep(c->g, sc, c->one_d, s->q[1 - c->qcur], s->beta[1 - c->bcur], store ? s->beta[1 - c->bcur] : nullptr, s->partial,
+                     s->dsums, c->st, &s->tr);
+        c->launches += 2;
+    }
+    if (sumsq) {
+        double v[1];
+        int rc = reduce_sums(c, 1, v);
+        if (rc) return rc;
+        *sumsq = v[0];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ the level loops
+// One function for the three reference loops; the shared parts (rescaling, KKT, sigma rule, output) are literally the
+// same code in solver_socp_inPALM.m, solver_socp_PALM.m and solver_socp_accADMM.m, only the iteration body differs.
+//   inPALM / ALG2 : fused kernels, z never stored (recomputed from (q_old, beta_old) where the reference reads it)
+//   PALM, acc-ADMM: z is genuine state (it enters the first q-step / the extrapolation), kept in beta[1-bcur]
 static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* hist, dotsocp_level_result* res)
 {
     const Geo& g = c->g;
@@ -455,49 +785,49 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     if (acc && stepAlpha != 2) return set_err(DOTSOCP_EINVAL, "acc-ADMM: only the Halpern iteration (opts.theta == 2, the default) is available");
     if (palm && (weighted || c->one_d)) return set_err(DOTSOCP_EINVAL, "PALM exists only for socp/dot2d");
     if (acc && c->one_d) return set_err(DOTSOCP_EINVAL, "acc-ADMM does not exist for socp/dot1d");
+    if (!inpalm && c->world > 1) return set_err(DOTSOCP_EINVAL, "PALM / acc-ADMM run on a single slab only (world == 1)");
     int kacc = 0;
 
     Loop L;
-    L.c = c; L.o = &o;
+    L.c = c;
     L.sc = make_scal(o, D, E, dScale, tau);
     L.sc_D2 = D * D;
     const i64 nB = 10 * g.L;
+    Slab* S0 = c->slabs[0];
     double* zmat = nullptr;      // PALM / acc: z lives here
     double* tmpq = nullptr;      // PALM: stored A*phi
     i64 vn[5] = {g.N, nB, g.Q, g.Q, nB};
     double* cur[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (!inpalm) {
         if (!c->z_materialised) return set_err(DOTSOCP_ESTATE, "z is not materialised");
-        zmat = c->beta[1 - c->bcur];
+        zmat = S0->beta[1 - c->bcur];
     }
-    if (palm) { int rc = ensure_alloc(c->zmat, g.Q); if (rc) return rc; tmpq = c->zmat; }
+    if (palm) { int rc = ensure_alloc(S0->tmpq, g.Q); if (rc) return rc; tmpq = S0->tmpq; }
     if (acc) {
         for (int i = 0; i < 5; i++) {
-            int rc = ensure_alloc(c->old_[i], vn[i]); if (rc) return rc;
-            rc = ensure_alloc(c->anc_[i], vn[i]); if (rc) return rc;
+            int rc = ensure_alloc(S0->old_[i], vn[i]); if (rc) return rc;
+            rc = ensure_alloc(S0->anc_[i], vn[i]); if (rc) return rc;
         }
     }
-    auto refresh_cur = [&]() { cur[0] = c->phi; cur[1] = zmat; cur[2] = c->q[c->qcur]; cur[3] = c->alpha; cur[4] = c->beta[c->bcur]; };
+    auto refresh_cur = [&]() { cur[0] = S0->phi; cur[1] = zmat; cur[2] = S0->q[c->qcur]; cur[3] = S0->alpha; cur[4] = S0->beta[c->bcur]; };
     auto copy_to = [&](double** dst) {
         refresh_cur();
         for (int i = 0; i < 5; i++) cudaMemcpyAsync(dst[i], cur[i], (size_t)vn[i] * sizeof(double), cudaMemcpyDeviceToDevice, c->st);
     };
 
     // alpha, beta, c <- ./sigma  (:102-104)
-    launch_scale(c->alpha, g.Q, 1.0, sigma, c->st);
-    launch_scale(c->beta[c->bcur], nB, 1.0, sigma, c->st);
-    launch_scale(c->c0, g.P, 1.0, sigma, c->st);
-    launch_scale(c->c1, g.P, 1.0, sigma, c->st);
-    c->launches += 4;
+    L.scale(A_ALPHA, 1.0, sigma);
+    L.scale(A_BETA, 1.0, sigma);
+    L.scale(A_C, 1.0, sigma);
     if (inpalm) L.prologue();   // z2 := d + BF q (:133) folded into the first z-step
     if (palm) {                 // tmp_q = A*phi ; mexBFd(z, tmp_q, ...)   (PALM :137-138)
-        UpdateArgs a = L.ua();
-        a.q_new = c->q[1 - c->qcur];   // scratch: only tmpq_out matters here
+        UpdateArgs a = L.ua(S0);
+        a.q_new = S0->q[1 - c->qcur];   // scratch: only tmpq_out matters here
         launch_qstep(a, false, false, c->st, nullptr, tmpq, false);
         launch_cells_update(g, L.sc, false, 2, tmpq, zmat, nullptr, c->st);
         c->launches += 2;
     }
-    if (acc) { copy_to(c->old_); copy_to(c->anc_); }   // :157-163
+    if (acc) { copy_to(S0->old_); copy_to(S0->anc_); }   // :157-163
 
     cudaEvent_t ev_begin, ev_end;
     cudaEventCreate(&ev_begin);
@@ -518,7 +848,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     auto mark = [&]() { cudaEvent_t e = c->evs.get(); cudaEventRecord(e, c->st); return e; };
 
     const double clock_total = now_s();
-    int it = 0, hist_len = 0;
+    int it = 0, hist_len = 0, rc = 0;
     bool z_ever = false;
     for (it = 1; it <= maxit; it++) {
         // ---------------------------------------------------------------- rescaling :138-190
@@ -526,19 +856,13 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         double normPhis = 0, normAlps = 0;
         auto rescale_norms = [&]() -> int {
             double s_phi, s_q, s_z, s_a, s_b;
-            int rc;
-            if ((rc = sumsq_host(c, c->phi, g.N, &s_phi))) return rc;
-            if ((rc = sumsq_host(c, c->q[c->qcur], g.Q, &s_q))) return rc;
-            if (c->z_materialised) {
-                if ((rc = sumsq_host(c, c->beta[1 - c->bcur], nB, &s_z))) return rc;
-            } else {
-                launch_zstep(g, L.sc, c->one_d, c->q[1 - c->qcur], c->beta[1 - c->bcur], nullptr, c->partial, c->dsums, c->st);
-                c->launches += 2;
-                if ((rc = fetch_sums(c, 1))) return rc;
-                s_z = c->hsums[0];
-            }
-            if ((rc = sumsq_host(c, c->alpha, g.Q, &s_a))) return rc;
-            if ((rc = sumsq_host(c, c->beta[c->bcur], nB, &s_b))) return rc;
+            int r;
+            if ((r = sumsq_owned(c, A_PHI, &s_phi))) return r;
+            if ((r = sumsq_owned(c, A_Q, &s_q))) return r;
+            if (c->z_materialised) { if ((r = sumsq_owned(c, A_ZMAT, &s_z))) return r; }
+            else if ((r = zstep_all(c, L.sc, false, &s_z))) return r;
+            if ((r = sumsq_owned(c, A_ALPHA, &s_a))) return r;
+            if ((r = sumsq_owned(c, A_BETA, &s_b))) return r;
             const double normPhi = sqrt(h) * sqrt(s_phi), normQ = sqrt(h) * sqrt(s_q), normZ = sqrt(h) * sqrt(s_z);
             const double normAlpha = sigma * (sqrt(h) * sqrt(s_a)), normBeta = sigma * (sqrt(h) * sqrt(s_b));
             normPhis = mmax({normPhi, normQ, normZ});
@@ -546,38 +870,32 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             return 0;
         };
         if (rescale >= 3 && it % checkRescaleIters == 0) {
-            int rc = rescale_norms();
-            if (rc) return rc;
+            if ((rc = rescale_norms())) return rc;
             const double ratio = fmax(normAlps, normPhis) / fmin(normAlps, normPhis);
             if (ratio > ratioThreshold) scaleYes = true;
         }
         if ((rescale == 1 && maxFeas < 2e-2 && it >= firstScaleIter && relGap < 5e-2) ||
             (rescale == 2 && maxFeas < 5e-3 && it >= SecondScaleIter && relGap < 1e-2) || scaleYes) {
-            if (!scaleYes) {
-                int rc = rescale_norms();
-                if (rc) return rc;
-            }
+            if (!scaleYes && (rc = rescale_norms())) return rc;
             const double dScale2 = normPhis, cScale2 = normAlps;
             sigma = sigma * (cScale2 / dScale2);
             const double cs2 = cScale2 * cScale2;
             // c, alpha, beta <- x * dScale2 / cScale2^2 ; q, z <- ./dScale2 (inPALM: z is recomputed, never stored)
-            launch_scale(c->c0, g.P, dScale2, cs2, c->st);
-            launch_scale(c->c1, g.P, dScale2, cs2, c->st);
+            L.scale(A_C, dScale2, cs2);
             norm_c = norm_c / cScale2;
             if (!weighted) norm_d = norm_d / dScale2;
-            launch_scale(c->alpha, g.Q, dScale2, cs2, c->st);
-            launch_scale(c->beta[c->bcur], nB, dScale2, cs2, c->st);
-            if (acc) launch_scale(c->phi, g.N, 1.0, dScale2, c->st);                 // accADMM :207
-            if (!palm) launch_scale(c->q[c->qcur], g.Q, 1.0, dScale2, c->st);        // :177 (absent in PALM)
-            if (c->z_materialised) launch_scale(c->beta[1 - c->bcur], nB, 1.0, dScale2, c->st);
-            if (palm) launch_scale(tmpq, g.Q, 1.0, dScale2, c->st);                  // PALM :191
-            c->launches += 7;
+            L.scale(A_ALPHA, dScale2, cs2);
+            L.scale(A_BETA, dScale2, cs2);
+            if (acc) L.scale(A_PHI, 1.0, dScale2);                 // accADMM :207
+            if (!palm) L.scale(A_Q, 1.0, dScale2);                 // :177 (absent in PALM)
+            if (c->z_materialised) L.scale(A_ZMAT, 1.0, dScale2);
+            if (palm) { launch_scale(tmpq, g.Q, 1.0, dScale2, c->st); c->launches += 1; }   // PALM :191
             dScale = dScale2 * dScale;
             cScale = cScale2 * cScale;
             L.sc.DF = E / dScale;                                   // scaleD
             sigmaScale = sigmaScale * (cScale2 / dScale2);
             if (inpalm) L.prologue();                               // mexBFd(z2, q, ...) refresh (:187)
-            if (acc) { kacc = 0; copy_to(c->old_); copy_to(c->anc_); }   // accADMM :217-222
+            if (acc) { kacc = 0; copy_to(S0->old_); copy_to(S0->anc_); }   // accADMM :217-222
             rescale += 1;
         }
 
@@ -585,9 +903,9 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         cudaEvent_t e_last;
         if (inpalm) {   // :192-216, fused order
             cudaEvent_t e0 = mark();
-            L.step_phi();
+            if ((rc = L.step_phi())) return rc;
             cudaEvent_t e1 = mark();
-            L.step_q(false);
+            if ((rc = L.step_q(false))) return rc;
             cudaEvent_t e2 = mark();
             L.step_mult();
             cudaEvent_t e3 = mark();
@@ -597,21 +915,21 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             e_last = e3;
             z_ever = true;
         } else if (palm) {   // solver_socp_PALM.m:196-224
-            double* q = c->q[c->qcur];
-            double* beta = c->beta[c->bcur];
-            UpdateArgs a = L.ua();
+            double* q = S0->q[c->qcur];
+            double* beta = S0->beta[c->bcur];
+            UpdateArgs a = L.ua(S0);
             a.q_new = q;
             cudaEvent_t e0 = mark();
-            launch_bfdconj_sum(g, L.sc.S, zmat, beta, c->q2, c->st);
+            launch_bfdconj_sum(g, L.sc.S, zmat, beta, S0->q2, c->st);
             launch_qstep(a, false, false, c->st, tmpq, nullptr, false);              // q = (tmp_q + alpha + q2).*diagQInv
             cudaEvent_t e1 = mark();
-            launch_rhs(g, L.sc, false, q, c->alpha, nullptr, c->c0, c->c1, c->rhs, c->st);
+            launch_rhs(g, L.sc, false, q, S0->alpha, nullptr, S0->c0, S0->c1, S0->rhs, c->st);
             c->launches += 3;
-            L.step_phi();
+            if ((rc = L.step_phi())) return rc;
             cudaEvent_t e2 = mark();
-            launch_zstep(g, L.sc, false, q, beta, zmat, c->partial, c->dsums, c->st);   // mexBFd + mexProjSoc (:209-210)
+            launch_zstep(g, L.sc, false, q, beta, zmat, S0->partial, S0->dsums, c->st);   // mexBFd + mexProjSoc (:209-210)
             cudaEvent_t e3 = mark();
-            launch_bfdconj_sum(g, L.sc.S, zmat, beta, c->q2, c->st);
+            launch_bfdconj_sum(g, L.sc.S, zmat, beta, S0->q2, c->st);
             launch_qstep(a, false, false, c->st, nullptr, tmpq, true);               // tmp_q = A*phi ; q ; alpha
             cudaEvent_t e4 = mark();
             launch_cells_update(g, L.sc, false, 0, q, zmat, beta, c->st);            // beta += tau (z - z2)
@@ -624,16 +942,16 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             segs.push_back({e4, e5, 3});
             e_last = e5;
         } else {   // solver_socp_accADMM.m:227-249
-            double* q = c->q[c->qcur];
-            double* beta = c->beta[c->bcur];
-            UpdateArgs a = L.ua();
+            double* q = S0->q[c->qcur];
+            double* beta = S0->beta[c->bcur];
+            UpdateArgs a = L.ua(S0);
             a.q_new = q;
             cudaEvent_t e0 = mark();
-            launch_bfdconj_sum(g, L.sc.S, zmat, beta, c->q2, c->st);
+            launch_bfdconj_sum(g, L.sc.S, zmat, beta, S0->q2, c->st);
             launch_qstep(a, weighted, true, c->st);                                  // q ; alpha = (alpha + A phi) - w.*q
             cudaEvent_t e1 = mark();
-            launch_rhs(g, L.sc, weighted, q, c->alpha, c->weight, c->c0, c->c1, c->rhs, c->st);
-            L.step_phi();
+            launch_rhs(g, L.sc, weighted, q, S0->alpha, S0->weight, S0->c0, S0->c1, S0->rhs, c->st);
+            if ((rc = L.step_phi())) return rc;
             cudaEvent_t e2 = mark();
             launch_cells_update(g, L.sc, false, 1, q, zmat, beta, c->st);            // beta = (beta + z) - z2 ; z = Pi_Q(z2 - beta)
             cudaEvent_t e3 = mark();
@@ -646,32 +964,41 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
 
         // ---------------------------------------------------------------- kkt :218-324
         const bool adjustSigmaYes = IfAdjustSigma(it, lastSigmaIt);
-        bool over_time = (now_s() - clock_total) > time_limit;
-        if (over_time) {   // the host runs ahead of the device: confirm against completed work
-            cudaStreamSynchronize(c->st);
+        bool over_time = false;
+        if (!c->comm) {   // (between processes the clock is only consulted at collective points, see below)
             over_time = (now_s() - clock_total) > time_limit;
+            if (over_time) {   // the host runs ahead of the device: confirm against completed work
+                cudaStreamSynchronize(c->st);
+                over_time = (now_s() - clock_total) > time_limit;
+            }
         }
         const bool check = checkSByS || adjustSigmaYes || it == maxit || over_time;
         bool stop = false;
         if (check) {
-            launch_bfdconj(g, L.sc.S, c->beta[c->bcur], c->qtmp, c->st);   // q2 = s (BF)^* beta   (:225)
-            KktArgs ka;
-            ka.g = g; ka.sc = L.sc; ka.sigma = sigma; ka.cScale = cScale; ka.dScale = dScale; ka.D = D; ka.E = E;
-            ka.phi = c->phi; ka.q = c->q[c->qcur]; ka.alpha = c->alpha; ka.weight = c->weight;
-            ka.beta = c->beta[c->bcur]; ka.z = zmat; ka.q_old = c->q[1 - c->qcur]; ka.beta_old = c->beta[1 - c->bcur];
-            ka.q2b = c->qtmp; ka.c0 = c->c0; ka.c1 = c->c1; ka.partial = c->partial;
-            ka.out = c->dsums;
-            launch_kkt_cells(ka, weighted, c->one_d, c->st);
-            ka.out = c->dsums + KC_COUNT;
-            launch_kkt_nodes(ka, weighted, c->st);
-            c->launches += 5;
+            for (Slab* s : c->slabs) {
+                launch_bfdconj(g, L.sc.S, s->beta[c->bcur], s->qtmp, c->st, &s->tr);   // q2 = s (BF)^* beta   (:225)
+                KktArgs ka;
+                ka.g = g; ka.tr = s->tr; ka.sc = L.sc; ka.sigma = sigma; ka.cScale = cScale; ka.dScale = dScale; ka.D = D; ka.E = E;
+                ka.phi = s->phi; ka.q = s->q[c->qcur]; ka.alpha = s->alpha; ka.weight = s->weight;
+                ka.beta = s->beta[c->bcur]; ka.z = zmat; ka.q_old = s->q[1 - c->qcur]; ka.beta_old = s->beta[1 - c->bcur];
+                ka.q2b = s->qtmp; ka.c0 = s->c0; ka.c1 = s->c1; ka.partial = s->partial;
+                ka.out = s->dsums;
+                launch_kkt_cells(ka, weighted, c->one_d, c->st);
+                ka.out = s->dsums + KC_COUNT;
+                launch_kkt_nodes(ka, weighted, c->st);
+                c->launches += 5;
+                // slot KC_COUNT+KN_COUNT carries the elapsed time seen by slab 0 so that all processes decide alike
+                s->hsums[63] = (s->id == 0) ? (now_s() - clock_total) : 0.0;
+                CU(cudaMemcpyAsync(s->dsums + KC_COUNT + KN_COUNT, s->hsums + 63, sizeof(double), cudaMemcpyHostToDevice, c->st));
+            }
             cudaEvent_t e4 = mark();
             segs.push_back({e_last, e4, 4});
-            int rc = fetch_sums(c, KC_COUNT + KN_COUNT);
-            if (rc) return rc;
+            double sums[KC_COUNT + KN_COUNT + 1];
+            if ((rc = reduce_sums(c, KC_COUNT + KN_COUNT + 1, sums))) return rc;
             flush_segs();
-            const double* sc_ = c->hsums;
-            const double* sn = c->hsums + KC_COUNT;
+            const double* sc_ = sums;
+            const double* sn = sums + KC_COUNT;
+            const double elapsed = c->comm ? sums[KC_COUNT + KN_COUNT] : (now_s() - clock_total);
             auto nrm = [&](double v) { return sqrt(h) * sqrt(v); };
             const double norm_q = nrm(sn[KN_Q2]);
             const double norm_z = nrm(sc_[KC_Z2]);
@@ -707,7 +1034,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             const double pdGap = fabs(priVal - dualVal) / (1 + fabs(priVal) + fabs(dualVal));
             if (hist && hist_len < hist->cap) {
                 if (hist->kkt) for (int j = 0; j < 7; j++) hist->kkt[(size_t)hist_len * 7 + j] = KO[j];
-                if (hist->time) hist->time[hist_len] = now_s() - clock_total;
+                if (hist->time) hist->time[hist_len] = elapsed;
                 if (hist->iter) hist->iter[hist_len] = it;
                 if (hist->pdGap) hist->pdGap[hist_len] = pdGap;
                 if (hist->priVal) hist->priVal[hist_len] = priVal;
@@ -715,7 +1042,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             }
             hist_len++;
             const double stopv = checkPD ? mmax({KO[0], KO[2], KO[5], KO[6]}) : mmax({KO[0], KO[2], KO[5]});
-            if (stopv < tol || (now_s() - clock_total) > time_limit) {
+            if (stopv < tol || elapsed > time_limit) {
                 stop = true;
             } else {
                 if (mmax({KR[0], KR[1], KR[2], KR[3], KR[4]}) < tol_feasOrg) use_feasOrg = 1;
@@ -727,20 +1054,18 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
                     double factor = 1;
                     adjust_lagrangianParam(sigma, resiPri / resiDual, factor);
                     if (factor != 1) {
-                        launch_scale(c->alpha, g.Q, 1.0, factor, c->st);
-                        launch_scale(c->beta[c->bcur], nB, 1.0, factor, c->st);
-                        launch_scale(c->c0, g.P, 1.0, factor, c->st);
-                        launch_scale(c->c1, g.P, 1.0, factor, c->st);
-                        c->launches += 4;
+                        L.scale(A_ALPHA, 1.0, factor);
+                        L.scale(A_BETA, 1.0, factor);
+                        L.scale(A_C, 1.0, factor);
                         // inPALM: q2, rhs were computed with the old alpha/beta: refresh.  The prologue reads only the
                         // current buffers, so the (q_old, beta_old) pair that defines z survives.
                         if (inpalm) L.prologue();
                         if (acc) {   // accADMM :346-358
-                            launch_scale(c->old_[3], g.Q, 1.0, factor, c->st);
-                            launch_scale(c->old_[4], nB, 1.0, factor, c->st);
+                            launch_scale(S0->old_[3], g.Q, 1.0, factor, c->st);
+                            launch_scale(S0->old_[4], nB, 1.0, factor, c->st);
                             c->launches += 2;
                             kacc = 0;
-                            copy_to(c->anc_);
+                            copy_to(S0->anc_);
                         }
                     }
                 }
@@ -757,7 +1082,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             kacc += 1;
             const bool anchor = kacc >= restart;
             refresh_cur();
-            for (int i = 0; i < 5; i++) launch_halpern(cur[i], c->old_[i], c->anc_[i], vn[i], c1, c2, stepRho, anchor, c->st);
+            for (int i = 0; i < 5; i++) launch_halpern(cur[i], S0->old_[i], S0->anc_[i], vn[i], c1, c2, stepRho, anchor, c->st);
             c->launches += 5;
             if (anchor) kacc = 0;
             cudaEvent_t e6 = mark();
@@ -768,15 +1093,12 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     // ---------------------------------------------------------------- output :328-357
     if (!c->z_materialised && z_ever) {
         // z = Pi_Q(d + BF q_old - beta_old), written over beta_old (cell-local, safe in place)
-        launch_zstep(g, L.sc, c->one_d, c->q[1 - c->qcur], c->beta[1 - c->bcur], c->beta[1 - c->bcur], c->partial, c->dsums, c->st);
-        c->launches += 2;
+        if ((rc = zstep_all(c, L.sc, true, nullptr))) return rc;
         c->z_materialised = true;
     }
-    launch_scale(c->alpha, g.Q, sigma, 1.0, c->st);               // var.alpha = sigma*alpha
-    launch_scale(c->beta[c->bcur], nB, sigma, 1.0, c->st);        // var.beta  = sigma*beta
-    launch_scale(c->c0, g.P, sigma, 1.0, c->st);                  // undo the folding of model.c (the reference never
-    launch_scale(c->c1, g.P, sigma, 1.0, c->st);                  // writes its local copy back; keeps the session reusable)
-    c->launches += 4;
+    L.scale(A_ALPHA, sigma, 1.0);      // var.alpha = sigma*alpha
+    L.scale(A_BETA, sigma, 1.0);       // var.beta  = sigma*beta
+    L.scale(A_C, sigma, 1.0);          // undo the folding of model.c (the reference never writes its local copy back)
     cudaEventRecord(ev_end, c->st);
     CU(cudaStreamSynchronize(c->st));
     flush_segs();
@@ -831,16 +1153,13 @@ extern "C" int dotsocp_iter_begin(dotsocp_ctx* c, const dotsocp_level_opts* o)
 {
     if (!c || !o) return set_err(DOTSOCP_EINVAL, "NULL ctx/opts");
     if (!c->uploaded) return set_err(DOTSOCP_ESTATE, "iter_begin before upload");
-    const Geo& g = c->g;
     c->sc = make_scal(*o, o->D, o->E, o->dScale, o->tau);
     c->sigma_fold = o->sigma;
     c->D2 = o->D * o->D;
-    launch_scale(c->alpha, g.Q, 1.0, o->sigma, c->st);
-    launch_scale(c->beta[c->bcur], 10 * g.L, 1.0, o->sigma, c->st);
-    launch_scale(c->c0, g.P, 1.0, o->sigma, c->st);
-    launch_scale(c->c1, g.P, 1.0, o->sigma, c->st);
-    c->launches += 4;
-    Loop L; L.c = c; L.o = o; L.sc = c->sc; L.sc_D2 = o->D * o->D;
+    Loop L; L.c = c; L.sc = c->sc; L.sc_D2 = c->D2;
+    L.scale(A_ALPHA, 1.0, o->sigma);
+    L.scale(A_BETA, 1.0, o->sigma);
+    L.scale(A_C, 1.0, o->sigma);
     L.prologue();
     CU(cudaStreamSynchronize(c->st));
     c->iter_open = true;
@@ -851,8 +1170,7 @@ extern "C" int dotsocp_iterate(dotsocp_ctx* c, int n_iters, int with_kkt_every, 
 {
     (void)with_kkt_every;
     if (!c || !c->iter_open) return set_err(DOTSOCP_ESTATE, "iterate without iter_begin");
-    Loop L; L.c = c; L.o = nullptr; L.sc = c->sc;
-    L.sc_D2 = c->D2;
+    Loop L; L.c = c; L.sc = c->sc; L.sc_D2 = c->D2;
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     std::vector<cudaEvent_t> ev;
@@ -860,17 +1178,19 @@ extern "C" int dotsocp_iterate(dotsocp_ctx* c, int n_iters, int with_kkt_every, 
         ev.resize((size_t)n_iters * 4);
         for (auto& e : ev) cudaEventCreate(&e);
     }
+    int rc = 0;
     cudaEventRecord(a, c->st);
-    for (int i = 0; i < n_iters; i++) {
+    for (int i = 0; i < n_iters && !rc; i++) {
         if (ms_by_kernel) cudaEventRecord(ev[4 * i + 0], c->st);
-        L.step_phi();
+        rc = L.step_phi();
         if (ms_by_kernel) cudaEventRecord(ev[4 * i + 1], c->st);
-        L.step_q(false);
+        if (!rc) rc = L.step_q(false);
         if (ms_by_kernel) cudaEventRecord(ev[4 * i + 2], c->st);
         L.step_mult();
         if (ms_by_kernel) cudaEventRecord(ev[4 * i + 3], c->st);
     }
     cudaEventRecord(b, c->st);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(c->st));
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);
@@ -893,140 +1213,16 @@ extern "C" int dotsocp_iterate(dotsocp_ctx* c, int n_iters, int with_kkt_every, 
 extern "C" int dotsocp_iter_end(dotsocp_ctx* c)
 {
     if (!c || !c->iter_open) return set_err(DOTSOCP_ESTATE, "iter_end without iter_begin");
-    const Geo& g = c->g;
+    Loop L; L.c = c; L.sc = c->sc; L.sc_D2 = c->D2;
     if (!c->z_materialised) {
-        launch_zstep(g, c->sc, c->one_d, c->q[1 - c->qcur], c->beta[1 - c->bcur], c->beta[1 - c->bcur], c->partial, c->dsums, c->st);
-        c->launches += 2;
+        int rc = zstep_all(c, c->sc, true, nullptr);
+        if (rc) return rc;
         c->z_materialised = true;
     }
-    launch_scale(c->alpha, g.Q, c->sigma_fold, 1.0, c->st);
-    launch_scale(c->beta[c->bcur], 10 * g.L, c->sigma_fold, 1.0, c->st);
-    launch_scale(c->c0, g.P, c->sigma_fold, 1.0, c->st);
-    launch_scale(c->c1, g.P, c->sigma_fold, 1.0, c->st);
-    c->launches += 4;
+    L.scale(A_ALPHA, c->sigma_fold, 1.0);
+    L.scale(A_BETA, c->sigma_fold, 1.0);
+    L.scale(A_C, c->sigma_fold, 1.0);
     CU(cudaStreamSynchronize(c->st));
     c->iter_open = false;
     return DOTSOCP_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ kernel-level entry points
-struct DevBuf {
-    double* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-    int alloc(size_t n)
-    {
-        cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(double));
-        if (e != cudaSuccess) { cudaGetLastError(); return set_err(DOTSOCP_ENOMEM, "cudaMalloc(%zu doubles): %s", n, cudaGetErrorString(e)); }
-        return 0;
-    }
-};
-
-extern "C" int dotsocp_mexBFd(double* z2, const double* q, int nt, int nx, int ny, double scaleBF, double scaleD)
-{
-    if (!z2 || !q || nt < 2 || nx < 1 || ny < 1) return set_err(DOTSOCP_EINVAL, "mexBFd: bad arguments");
-    int rc = require_device();
-    if (rc) return rc;
-    const Geo g = make_geo(nt, nx, ny);
-    DevBuf dz, dq;
-    if ((rc = dz.alloc(10 * g.L)) || (rc = dq.alloc(g.Q))) return rc;
-    // in-place semantics: entries the kernel does not write keep the caller's values
-    CU(cudaMemcpy(dz.p, z2, (size_t)10 * g.L * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dq.p, q, (size_t)g.Q * sizeof(double), cudaMemcpyHostToDevice));
-    launch_bfd(g, scaleBF, scaleD, dq.p, dz.p, 0);
-    CU(cudaGetLastError());
-    CU(cudaMemcpy(z2, dz.p, (size_t)10 * g.L * sizeof(double), cudaMemcpyDeviceToHost));
-    return DOTSOCP_OK;
-}
-
-extern "C" int dotsocp_mexBFdConj(double* q2, const double* z, int nt, int nx, int ny, double scaleBF)
-{
-    if (!q2 || !z || nt < 2 || nx < 1 || ny < 1) return set_err(DOTSOCP_EINVAL, "mexBFdConj: bad arguments");
-    int rc = require_device();
-    if (rc) return rc;
-    const Geo g = make_geo(nt, nx, ny);
-    DevBuf dz, dq;
-    if ((rc = dz.alloc(10 * g.L)) || (rc = dq.alloc(g.Q))) return rc;
-    CU(cudaMemcpy(dz.p, z, (size_t)10 * g.L * sizeof(double), cudaMemcpyHostToDevice));
-    launch_bfdconj(g, scaleBF, dz.p, dq.p, 0);
-    CU(cudaGetLastError());
-    CU(cudaMemcpy(q2, dq.p, (size_t)g.Q * sizeof(double), cudaMemcpyDeviceToHost));
-    return DOTSOCP_OK;
-}
-
-extern "C" int dotsocp_mexProjSoc(double* out, const double* in, int64_t M, int N)
-{
-    if (!out || !in || M < 0 || N < 1) return set_err(DOTSOCP_EINVAL, "mexProjSoc: bad arguments");
-    int rc = require_device();
-    if (rc) return rc;
-    if (M == 0) return DOTSOCP_OK;
-    DevBuf di, dout;
-    if ((rc = di.alloc((size_t)M * N)) || (rc = dout.alloc((size_t)M * N))) return rc;
-    CU(cudaMemcpy(di.p, in, (size_t)M * N * sizeof(double), cudaMemcpyHostToDevice));
-    launch_projsoc(M, N, di.p, dout.p, 0);
-    CU(cudaGetLastError());
-    CU(cudaMemcpy(out, dout.p, (size_t)M * N * sizeof(double), cudaMemcpyDeviceToHost));
-    return DOTSOCP_OK;
-}
-
-extern "C" int dotsocp_mexBFd1d(double* z, const double* q, int nt, int nx, double scale, double dFactor)
-{
-    if (!z || !q || nt < 2 || nx < 1) return set_err(DOTSOCP_EINVAL, "mexBFd:invalidInput");
-    int rc = require_device();
-    if (rc) return rc;
-    const Geo g = make_geo(nt, nx, 1);
-    DevBuf d6, d10, dq;
-    if ((rc = d6.alloc(6 * g.L)) || (rc = d10.alloc(10 * g.L)) || (rc = dq.alloc(g.Q))) return rc;
-    CU(cudaMemcpy(d6.p, z, (size_t)6 * g.L * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dq.p, q, (size_t)g.Q * sizeof(double), cudaMemcpyHostToDevice));
-    launch_cols6to10(d6.p, d10.p, g.L, 0);
-    launch_bfd(g, scale, dFactor, dq.p, d10.p, 0);
-    launch_cols10to6(d10.p, d6.p, g.L, 0);
-    CU(cudaGetLastError());
-    CU(cudaMemcpy(z, d6.p, (size_t)6 * g.L * sizeof(double), cudaMemcpyDeviceToHost));
-    return DOTSOCP_OK;
-}
-
-extern "C" int dotsocp_mexBFdConj1d(double* q, const double* z, int nt, int nx, double scale)
-{
-    if (!z || !q || nt < 2 || nx < 1) return set_err(DOTSOCP_EINVAL, "mexBFd:invalidInput");
-    int rc = require_device();
-    if (rc) return rc;
-    const Geo g = make_geo(nt, nx, 1);
-    DevBuf d6, d10, dq;
-    if ((rc = d6.alloc(6 * g.L)) || (rc = d10.alloc(10 * g.L)) || (rc = dq.alloc(g.Q))) return rc;
-    CU(cudaMemcpy(d6.p, z, (size_t)6 * g.L * sizeof(double), cudaMemcpyHostToDevice));
-    launch_cols6to10(d6.p, d10.p, g.L, 0);
-    launch_bfdconj(g, scale, d10.p, dq.p, 0);
-    CU(cudaGetLastError());
-    CU(cudaMemcpy(q, dq.p, (size_t)g.Q * sizeof(double), cudaMemcpyDeviceToHost));
-    return DOTSOCP_OK;
-}
-
-static int dct_common(double* out, const double* in, int nt, int nx, int ny, int what, double D)
-{
-    if (!out || !in || nt < 1 || nx < 1 || ny < 1) return set_err(DOTSOCP_EINVAL, "bad arguments");
-    int rc = require_device();
-    if (rc) return rc;
-    const i64 N = (i64)nt * nx * ny;
-    DevBuf a, b;
-    if ((rc = a.alloc(N)) || (rc = b.alloc(N))) return rc;
-    CU(cudaMemcpy(a.p, in, (size_t)N * sizeof(double), cudaMemcpyHostToDevice));
-    PoissonPlan* pp = poisson_plan_create(nt, nx, ny);
-    if (what == 2) poisson_solve(pp, a.p, b.p, D * D, 0, nullptr);
-    else { CU(cudaMemcpy(b.p, a.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice)); poisson_dctn(pp, b.p, what == 1, 0, nullptr); }
-    cudaError_t e = cudaDeviceSynchronize();
-    poisson_plan_destroy(pp);
-    if (e != cudaSuccess) return set_err(DOTSOCP_ECUDA, "transform kernels: %s", cudaGetErrorString(e));
-    CU(cudaGetLastError());
-    CU(cudaMemcpy(out, b.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
-    return DOTSOCP_OK;
-}
-
-extern "C" int dotsocp_poisson(double* phi, const double* rhs, int nt, int nx, int ny, double D)
-{
-    return dct_common(phi, rhs, nt, nx, ny, 2, D);
-}
-extern "C" int dotsocp_dctn(double* a, int nt, int nx, int ny, int inverse)
-{
-    return dct_common(a, a, nt, nx, ny, inverse ? 1 : 0, 1.0);
 }

@@ -84,7 +84,11 @@ class Session:
     """Device-resident state of one level (dotsocp_create / _upload / _run / _download / _destroy)."""
 
     def __init__(self, variant, nt, nx, ny=1, rank=0, world=1, nccl_id=None):
+        """world > 1 with nccl_id=None: all `world` time slabs live in this process on the current device (emulation of
+        the multi-GPU path, global host arrays); with a 128-byte nccl_id: this process owns slab `rank` (one process per
+        GPU, NCCL between them) and upload/download take the slab-local parts (see slab.py)."""
         self.variant = variant
+        self.rank, self.world, self.distributed = int(rank), int(world), nccl_id is not None
         self.nt, self.nx, self.ny = int(nt), int(nx), int(ny)
         self.ncol = 6 if variant == "dot1d" else 10
         self._h = C.c_void_p()

@@ -174,3 +174,35 @@ def test_golden_solver_histories(gpu):
         assert np.abs(ML.kkt - np.array(g["kkt"])).max() < 1e-8, name
         assert abs(rh.priVal[-1] - g["priVal"]) <= 1e-6 * abs(g["priVal"]), name
         assert abs(driver.w2_cost(out, 1 if name.startswith("dot1d") else 2) - g["w2"]) <= 1e-6 * abs(g["w2"]), name
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("variant", ["dot2d", "wdot2d"])
+def test_time_slab_partition_emulated_on_one_gpu(gpu, world, variant):
+    """The multi-GPU code path (time slabs, ghost planes, transposed t-pass, reduced KKT sums) with all slabs on ONE
+    device (device-to-device copies instead of NCCL): must reproduce the single-slab solve."""
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import driver, solver
+    n, nt = 33, 17
+    rho0, rho1 = O.get_example2d("example2", n, n)
+    weight = O.gene_weight_circle(nt, n, n) if variant == "wdot2d" else None
+    results = []
+    for w in (1, world):
+        var, model = driver.initialize(rho0, rho1, nt)
+        if weight is not None:
+            model.weight = weight
+        driver.InitialScaling(var, model, True, None, variant)
+        opts = {"tol": 1e-4 if variant == "dot2d" else 1e-3, "maxit": 400, "tau": 1.9, "sigma": 1.0,
+                "ifCheckStepByStep": False, "scaling": True}
+        o = solver.make_level_opts(variant, "inPALM", var, opts, model)
+        with dp.Session(variant, nt, n, n, world=w) as s:
+            s.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c, weight)
+            hb, res = s.run(o)
+            state = s.download()
+        results.append((hb, res, state))
+    (hb1, r1, s1), (hbw, rw, sw) = results
+    assert r1.iters == rw.iters and r1.hist_len == rw.hist_len
+    assert np.abs(hb1.kkt[:r1.hist_len] - hbw.kkt[:rw.hist_len]).max() < 1e-12
+    assert abs(r1.sigma - rw.sigma) <= 1e-13 * abs(r1.sigma)
+    for a, b, name in zip(s1, sw, ("phi", "q", "z", "alpha", "beta")):
+        assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), name
