@@ -98,10 +98,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_problem(nt, nx, ny, problem="example1"):
-    """Synthetic Gaussian densities (examples/dot2d/gene_example1.m) on the named grid, reference initial state
-    (initialize.m) after InitialScaling -- built with the product's own host mirror (no oracle on this path)."""
-    from dotsocp_b200 import driver
+def make_problem(nt, nx, ny, rank=0, world=1, problem="example1"):
+    """Synthetic Gaussian densities (examples/dot2d/gene_example1.m) on the named grid and the reference's initial state
+    (initialize.m) after InitialScaling (solver_dotsocp2d.m:304-365) -- built slab-locally with the product's own host
+    code (no oracle on this path): every rank only materialises its time slab; q, z, alpha, beta start as zeros."""
+    from dotsocp_b200 import slab
     x = np.linspace(0, 1, nx).reshape(nx, 1)
     y = np.linspace(0, 1, ny).reshape(1, ny)
     s = 0.05
@@ -114,27 +115,45 @@ def make_problem(nt, nx, ny, problem="example1"):
         rho1 = g(.25, .25, .05) + g(.25, .75, .05) + g(.75, .25, .05) + g(.75, .75, .05)
     rho0 = rho0 * (nx * ny / rho0.sum())
     rho1 = rho1 * (nx * ny / rho1.sum())
-    var, model = driver.initialize(rho0, rho1, nt)
-    # q, z, alpha, beta start as zeros (initialize.m:53-58): keep the lazily allocated zero pages instead of letting
-    # InitialScaling multiply 120 GB of zeros by a scalar
-    big = {k: getattr(var, k) for k in ("q", "z", "alpha", "beta")}
-    for k in big:
-        setattr(var, k, np.zeros(1))
-    driver.InitialScaling(var, model, True, None, "dot2d")
-    for k, v in big.items():
-        setattr(var, k, v)
+    N = nt * nx * ny
+    ht, hx, hy = 1 / (nt - 1), 1 / (nx - 1), 1 / (ny - 1)
+    c_first, c_last = (-rho0 / ht).ravel(), (rho1 / ht).ravel()           # initialize.m:41-44, C order (x, y)
+    h = 1.0 / N
+    hMean = h ** (1 / 3)
+    norm_c = np.sqrt(h) * np.sqrt(np.dot(c_first, c_first) + np.dot(c_last, c_last)) * np.sqrt(nt)
+    D = np.sqrt(2) * np.sqrt(hMean)
+    E = D / np.sqrt(2)
+    cScale = max(1.0, norm_c * np.sqrt(hMean))
+    dScale = E * np.sqrt(2)
+    tc0, tc1, tn0, tn1 = slab.partition(nt, world)[rank]
+    P = nx * ny
+    phi_plane = (0.5 * ((np.arange(nx) * hx)[:, None] ** 2 + (np.arange(ny) * hy)[None, :] ** 2)).ravel() * (1 / dScale)
+    phi = np.tile(phi_plane, tn1 - tn0)
+    c = np.zeros((tn1 - tn0) * P)
+    if tn0 == 0:
+        c[:P] = (1.0 / cScale) * c_first
+    if tn1 == nt:
+        c[-P:] = (1.0 / cScale) * c_last
+    sz = slab.local_sizes(rank, world, nt, nx, ny)
+    from types import SimpleNamespace
+    var = SimpleNamespace(phi=phi, q=np.zeros(sz["Q"]), alpha=np.zeros(sz["Q"]), z=np.zeros((sz["L"], 10), order="F"),
+                          beta=np.zeros((sz["L"], 10), order="F"), cScale=cScale, dScale=dScale, D=D, E=E)
+    model = SimpleNamespace(nt=nt, nx=nx, ny=ny, dim=2, c=c, normc=norm_c / cScale, normd=np.sqrt(2) * E / dScale,
+                            grad=(D / ht, D / hx, D / hy))
     return var, model
 
 
-def level_opts(var, model, maxit):
+def level_opts(var, model, maxit, tol=1e-4):
     from dotsocp_b200 import solver
-    opts = {"tol": 1e-4, "maxit": maxit, "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": False, "scaling": True}
+    opts = {"tol": tol, "maxit": maxit, "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": False, "scaling": True}
     return solver.make_level_opts("dot2d", "inPALM", var, opts, model)
 
 
-def pick_workload(requested):
+def pick_workload(requested, world=1):
     if requested != "auto":
         return requested
+    if world > 1:
+        return "c5"    # 147 GB of state / world GPUs and 121 GB of host buffers / world ranks
     # the metric's grid needs ~147 GB of HBM (34 N doubles) and 121 GB of host buffers for the e2e leg
     try:
         out = subprocess.check_output(["nvidia-smi", "--query-gpu=memory.total,memory.used", "--format=csv,noheader,nounits", "-i", "0"], text=True)
@@ -193,11 +212,17 @@ def main():
     K_, W_ = args.steps, max(args.warmup, 3)
     hbm_peak, peak_src = measured_peaks()
 
-    wl = pick_workload(args.workload) if rank == 0 or world == 1 else args.workload
+    wl = pick_workload(args.workload, world) if rank == 0 or world == 1 else args.workload
+    dist = None
+    if world > 1 and args.impl == "reference":
+        if rank != 0:
+            return                                            # the CPU arm runs on rank 0 alone
+        world = 1
     if world > 1:
         import torch
         import torch.distributed as dist
-        dist.init_process_group("gloo" if args.impl == "reference" else "nccl")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
         obj = [wl]
         dist.broadcast_object_list(obj, src=0)
         wl = obj[0]
@@ -233,58 +258,88 @@ def main():
     # ---------------------------------------------------------------------------------------------- this repo's arm
     import dotsocp_b200 as dp
     from dotsocp_b200 import _lib
-    if world > 1:
-        raise SystemExit("multi-GPU time-slab sessions are not available in this build (run with --gpus 1)")
     _lib.check(_lib.lib().dotsocp_set_device(local_rank))
-    var, model = make_problem(nt, nx, ny)
+    ident = None
+    if world > 1:
+        import torch
+        torch.cuda.set_device(local_rank)
+        from dotsocp_b200 import slab
+        ident = slab.broadcast_unique_id(dist, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    var, model = make_problem(nt, nx, ny, rank, world)
     o = level_opts(var, model, K_)
 
-    sess = dp.Session("dot2d", nt, nx, ny)
+    sess = dp.Session("dot2d", nt, nx, ny, rank=rank, world=world, nccl_id=ident)
     sess.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c)
     sess.iter_begin(o)
     sess.iterate(W_)                                         # warm-up (untimed)
     sampler = ClockSampler(local_rank)
+    barrier()
     sampler.start()
     launches0 = sess.launches
     t_wall0 = time.perf_counter()
     ms, per_kernel = sess.iterate(K_, per_kernel=True)       # CUDA events on the launching stream
+    barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = sess.launches - launches0
     clocks = sampler.stop()
     sess.iter_end()
     sess.close()
+    ms = max_over_ranks(ms)
+    per_kernel = [max_over_ranks(v) for v in per_kernel]
     ms_per_step = ms / K_
     value = 1e3 / ms_per_step
 
     # roofline of the dominant kernel (k_mult: projection + multiplier step + next rhs/q2), measured live with events
     mult_ms = per_kernel[2] / K_
-    mult_bytes = (N + 4 * Q + 20 * L) * 8.0                  # reads q_old,q_new,alpha,beta ; writes beta,q2,rhs
+    mult_bytes = (N + 4 * Q + 20 * L) * 8.0 / world          # per GPU: reads q_old,q_new,alpha,beta ; writes beta,q2,rhs
     ach = mult_bytes / (mult_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_mult", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": None, "peak_source": peak_src,
-                "per_kernel_ms": {"poisson(5 passes)": per_kernel[0] / K_, "k_qstep": per_kernel[1] / K_, "k_mult": mult_ms}}
+                "per_kernel_ms": {"poisson": per_kernel[0] / K_, "k_qstep": per_kernel[1] / K_, "k_mult": mult_ms}}
     it_ach = W_iter / (ms_per_step * 1e-3) / 1e9
     roofline_iter = {"bound": "hbm", "achieved": it_ach, "peak": hbm_peak * world, "unit": "GB/s", "frac": it_ach / (hbm_peak * world),
                      "bytes_per_iteration": W_iter, "note": "W_iter = (14N+6Q+30L)*8 B, SURVEY.md §8(d)"}
 
-    # e2e: the reference-facing call with HOST buffers (upload + K iterations + download inside the timed region)
+    # e2e: the reference-facing call with HOST buffers (upload + K iterations incl. the KKT checks the loop schedules +
+    # download inside the timed region); every rank moves its own slab
     e2e = None
     if not args.no_e2e:
-        from dotsocp_b200 import solver as S
-        var2, model2 = var, model
-        o2 = level_opts(var2, model2, K_)
-        o2.tol = 1e-30                                        # run exactly K iterations
+        o2 = level_opts(var, model, K_, tol=1e-30)            # run exactly K iterations
+        ident2 = slab.broadcast_unique_id(dist, rank) if world > 1 else None   # one id per communicator
+        barrier()
         t0 = time.perf_counter()
-        S.solver_socp_inPALM(var2, {"tol": 1e-30, "maxit": K_, "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": False,
-                                    "scaling": True}, model2)
-        dt = time.perf_counter() - t0
+        with dp.Session("dot2d", nt, nx, ny, rank=rank, world=world, nccl_id=ident2) as s2:
+            s2.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c)
+            s2.run(o2)
+            out_state = s2.download()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        del out_state
         h2d = (2 * N + 2 * Q + 20 * L) * 8.0
         d2h = (N + 2 * Q + 20 * L) * 8.0
         e2e = {"value": K_ / dt, "unit": "iterations/s", "h2d_bytes_per_step": h2d / K_, "d2h_bytes_per_step": d2h / K_,
-               "seconds": dt, "call": "dotsocp_solve_level (solver_socp_inPALM mirror), pageable host buffers"}
+               "seconds": dt, "call": "dotsocp_create+upload+run+download (= dotsocp_solve_level / solver_socp_inPALM), "
+                                     "pageable host buffers, all ranks"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         its, cores, backend, sg, dt, tbl = cpu_reference_leg(6, 1)
         Ns = sg[0] * sg[1] * sg[2]
         cpu = {"value": its * Ns / N, "unit": "iterations/s", "cores": cores, "kind": "reference" if backend == "ref" else "port",
@@ -297,6 +352,8 @@ def main():
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": 1e3 * t_wall / K_,
             "roofline": roofline, "roofline_iteration": roofline_iter, "e2e": e2e, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -7,7 +7,7 @@ Layout
   solver.py    solver-level mirror: solver_socp_inPALM(var, opts, model), ... and the device-resident Session
   driver.py    host-side mirror of the multilevel drivers solver_dotsocp2d / solver_wdotsocp2d / solver_dotsocp1d
 """
-from . import _lib, driver, ops, solver  # noqa: F401
+from . import _lib, driver, ops, slab, solver  # noqa: F401
 from .driver import solver_dotsocp1d, solver_dotsocp2d, solver_wdotsocp2d  # noqa: F401
 from .solver import (Session, solver_socp_accADMM, solver_socp_inPALM, solver_socp_PALM,  # noqa: F401
                      solver_wsocp_accADMM, solver_wsocp_inPALM)

@@ -96,6 +96,10 @@ class Session:
         self.L = (self.nt - 1) * self.nx * self.ny
         self.Q = self.L + self.nt * (self.nx - 1) * self.ny + self.nt * self.nx * (self.ny - 1)
         self.N = self.nt * self.nx * self.ny
+        if self.distributed:   # host arrays hold this slab's owned part only (slab.py)
+            from .slab import local_sizes
+            sz = local_sizes(self.rank, self.world, self.nt, self.nx, self.ny)
+            self.L, self.Q, self.N = sz["L"], sz["Q"], sz["N"]
 
     def close(self):
         if self._h:

@@ -1,0 +1,72 @@
+"""Run under torchrun on >= 2 GPUs (one process per GPU): the NCCL time-slab solve must reproduce the committed golden
+history (tests/golden/solver.json, produced by the CPU oracle) and the single-GPU state.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_parity.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import dotsocp_b200 as dp  # noqa: E402
+from dotsocp_b200 import _lib, driver, slab, solver  # noqa: E402
+from oracle import dotsocp_oracle as O  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    _lib.check(_lib.lib().dotsocp_set_device(local))
+    dist.init_process_group("nccl")
+    n, nt = 33, 17
+    for variant in ("dot2d", "wdot2d"):
+        ident = slab.broadcast_unique_id(dist, rank)     # an ncclUniqueId serves exactly one communicator
+        rho0, rho1 = O.get_example2d("example2", n, n)
+        weight = O.gene_weight_circle(nt, n, n) if variant == "wdot2d" else None
+        var, model = driver.initialize(rho0, rho1, nt)
+        if weight is not None:
+            model.weight = weight
+        driver.InitialScaling(var, model, True, None, variant)
+        opts = {"tol": 1e-4 if variant == "dot2d" else 1e-3, "maxit": 400, "tau": 1.9, "sigma": 1.0,
+                "ifCheckStepByStep": False, "scaling": True}
+        o = solver.make_level_opts(variant, "inPALM", var, opts, model)
+        mine = slab.split_state(rank, world, nt, n, n, var.phi, var.q, var.z, var.alpha, var.beta, model.c, weight)
+        with dp.Session(variant, nt, n, n, rank=rank, world=world, nccl_id=ident) as s:
+            s.upload(*mine[:6], mine[6])
+            hb, res = s.run(o)
+            part = s.download()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, part)
+        if rank == 0:
+            state = slab.merge_state(world, nt, n, n, gathered)
+            # single-GPU reference on this rank's device
+            with dp.Session(variant, nt, n, n) as s1:
+                s1.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c, weight)
+                hb1, res1 = s1.run(o)
+                state1 = s1.download()
+            assert res.iters == res1.iters and res.hist_len == res1.hist_len, (res.iters, res1.iters)
+            assert np.abs(hb.kkt[:res.hist_len] - hb1.kkt[:res1.hist_len]).max() < 1e-12
+            for a, b, name in zip(state, state1, ("phi", "q", "z", "alpha", "beta")):
+                assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), name
+            # and against the CPU oracle
+            vo, mo = O.initialize2d(rho0, rho1, nt)
+            if weight is not None:
+                mo.weight = weight
+            O.InitialScaling(vo, mo, True, None, variant)
+            rh_o, _ = O.solver_socp_inPALM(vo, opts, mo)
+            assert rh_o.len == res.hist_len and int(vo.time["Iters"]) == res.iters
+            assert np.abs(rh_o.kkt - hb.kkt[:res.hist_len]).max() < 1e-8
+            print(f"dist parity ok: {variant} world={world} iters={res.iters}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

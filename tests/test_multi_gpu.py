@@ -1,0 +1,24 @@
+"""Multi-GPU (NCCL, one process per GPU) parity; needs >= 2 GPUs on the box, skipped otherwise."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def test_nccl_time_slab_parity(gpu):
+    if gpu < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    nproc = 4 if gpu >= 4 else 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_parity.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-4000:]
+    assert out.stdout.count("dist parity ok") == 2
