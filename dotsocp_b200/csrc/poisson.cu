@@ -14,6 +14,7 @@
 // eigenvalue table, inverse DCT, so the solve is 5 passes over N doubles (y, x, [t,/,t^-1], x^-1, y^-1).
 // Lengths <= 32 (coarse multilevel grids) use a dense matrix kernel.
 #include "kernels.h"
+#include "fft16.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -28,6 +29,7 @@ struct DctPlan {
     int log2m, M;
     double2* w;        // chirp  w[j] = exp(-i pi j^2 / n), j < n
     double2* bhat;     // FFT_M(b_circ)/M in the digit-reversed order produced by the forward passes
+    double2* bhat16;   // same spectrum in the order of the register radix-16 passes (fft16.cuh), M >= 256 only
     double2* tw;       // exp(-2 pi i j / M), j < M
     double2* pw;       // c_k exp(-i pi k / (2n)), k < n   (forward post-twiddle incl. orthonormal scale)
     double2* ipw;      // exp(+i pi k / (2n)) / c_k / n     (inverse pre-twiddle incl. 1/n of the IDFT)
@@ -149,13 +151,23 @@ static DctPlan* dct_plan_create(int n)
     p->ipw = to_device(ipw);
     p->tw = to_device(tw);
     p->bhat = to_device(bh);
+    if (log2m >= 8 && log2m <= 12) {
+        std::vector<double2> b16(M);
+        const int TP = M / 16, Q2 = M / 256;
+        for (int pos = 0; pos < M; pos++) {
+            const int m1 = pos / TP, r = pos % TP, m2 = r / Q2, m3 = r % Q2;
+            const int f = m1 + 16 * m2 + 256 * m3;
+            b16[pos] = make_double2((double)(br[f] / M), (double)(bi[f] / M));
+        }
+        p->bhat16 = to_device(b16);
+    }
     return p;
 }
 
 static void dct_plan_destroy(DctPlan* p)
 {
     if (!p) return;
-    cudaFree(p->w); cudaFree(p->bhat); cudaFree(p->tw); cudaFree(p->pw); cudaFree(p->ipw); cudaFree(p->cmat);
+    cudaFree(p->w); cudaFree(p->bhat); cudaFree(p->bhat16); cudaFree(p->tw); cudaFree(p->pw); cudaFree(p->ipw); cudaFree(p->cmat);
     delete p;
 }
 
@@ -441,6 +453,229 @@ k_dct_bluestein(LineGeom lg, const double* ain, double* aout, const double2* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------------ v2: register radix-16
+// Same mathematics as k_dct_bluestein, but the two M-point FFTs of the chirp-z convolution run on TP = M/16 threads with
+// 16 complex values per thread in registers (fft16.cuh): 4 shared-memory exchanges per convolution instead of ~14 passes,
+// twiddles by a multiplication ladder instead of table loads, the chirp and the chirp spectrum applied in registers.
+// barrier among the TP threads that share one line pair (named barrier 1 + pair; whole warps only)
+template <int TP>
+__device__ __forceinline__ void pair_sync(int pair)
+{
+    if (TP <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(pair + 1), "r"(TP) : "memory");
+}
+
+template <int LOG2M>
+__device__ __forceinline__ void conv16(double2 (&v)[16], int j, int pair, double2* __restrict__ s,
+                                       const double2* __restrict__ tw, const double2* __restrict__ bhat16)
+{
+    typedef F16<LOG2M> F;
+#define __syncthreads() pair_sync<F::TP>(pair)
+    F::fwd1(v, j, tw);
+    F::store1(s, j, v);
+    __syncthreads();
+    F::load2(s, j, v);
+    F::fwd2(v, j, tw);
+    F::store2(s, j, v);
+    __syncthreads();
+    F::load3(s, j, v);
+    F::fwd3(v);
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = c_mul(v[e], __ldg(&bhat16[16 * j + e]));
+    F::inv3(v);
+    F::store3(s, j, v);
+    __syncthreads();
+    F::load2(s, j, v);
+    F::inv2(v, j, tw);
+    F::store2(s, j, v);
+    __syncthreads();
+    F::load1(s, j, v);
+    F::inv1(v, j, tw);
+#undef __syncthreads
+}
+
+template <int LOG2M, int PAIRS, int MODE>
+__global__ void __launch_bounds__((1 << LOG2M) / 16 * PAIRS, (LOG2M >= 12 ? 1 : 2))
+k_dct_blu16(LineGeom lg, const double* ain, double* aout, const double2* __restrict__ w, const double2* __restrict__ bhat16,
+            const double2* __restrict__ tw, const double2* __restrict__ pw, const double2* __restrict__ ipw, ScaleArgs sa)
+{
+    typedef F16<LOG2M> F;
+    constexpr int M = F::M, TP = F::TP, G = 2 * PAIRS, NTHR = TP * PAIRS, PADLEN = M + M / 16 + 1;
+    constexpr int NM = 9;    // n <= M/2 + 1  =>  positions j + m*TP < n only for m <= 8
+    extern __shared__ double2 smem[];
+    const int n = lg.n;
+    const int tid = threadIdx.x;
+    const int pair = tid / TP, j = tid - pair * TP;
+    double2* __restrict__ s = smem + (size_t)pair * PADLEN;
+    const i64 line0 = (i64)blockIdx.x * G;
+    const i64 gbase = (i64)blockIdx.y * lg.ostride + line0 * lg.gstride;
+    const int nlines = (int)((lg.inner - line0) < (i64)G ? (lg.inner - line0) : (i64)G);
+
+    // ---- stage in ---------------------------------------------------------------------------------------------------
+    {
+        // all global loads of a thread are issued before the first shared store (G*n/NTHR <= 2*(M/2+1)*PAIRS/NTHR = 16.x)
+        constexpr int NLD = (G * (M / 2 + 1) + NTHR - 1) / NTHR;
+        const int total = G * n;
+        double vals[NLD];
+#pragma unroll
+        for (int u = 0; u < NLD; u++) {
+            const int f = tid + u * NTHR;
+            int g, jj;
+            if (lg.contiguous) { g = f / n; jj = f - g * n; } else { jj = f / G; g = f - jj * G; }
+            vals[u] = (f < total && g < nlines) ? ain[gbase + (i64)g * lg.gstride + (i64)jj * lg.estride] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < NLD; u++) {
+            const int f = tid + u * NTHR;
+            if (f < total) {
+                int g, jj;
+                if (lg.contiguous) { g = f / n; jj = f - g * n; } else { jj = f / G; g = f - jj * G; }
+                double* dst = reinterpret_cast<double*>(smem + (size_t)(g >> 1) * PADLEN + PAD16(MODE == 1 ? jj : makhoul(jj, n)));
+                dst[g & 1] = vals[u];
+            }
+        }
+    }
+    __syncthreads();
+    double2 v[16];
+    if (MODE != 1) {
+        // a[m] = (v1 + i v2)[m] * w[m], zero beyond n
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const int pos = j + m * TP;
+            v[m] = (m < NM && pos < n) ? c_mul(s[PAD16(pos)], __ldg(&w[pos])) : make_double2(0.0, 0.0);
+        }
+        conv16<LOG2M>(v, j, pair, s, tw, bhat16);
+        pair_sync<TP>(pair);
+        // V[k] = w[k] c[k], natural positions
+#pragma unroll
+        for (int m = 0; m < NM; m++) {
+            const int pos = j + m * TP;
+            if (pos < n) { v[m] = c_mul(v[m], __ldg(&w[pos])); s[PAD16(pos)] = v[m]; }
+        }
+        pair_sync<TP>(pair);
+        double2 pr[NM];
+#pragma unroll
+        for (int m = 0; m < NM; m++) {
+            const int pos = j + m * TP;
+            if (pos < n) pr[m] = s[PAD16(pos == 0 ? 0 : n - pos)];
+        }
+        pair_sync<TP>(pair);
+#pragma unroll
+        for (int m = 0; m < NM; m++) {
+            const int k = j + m * TP;
+            if (k < n) {
+            const double2 vk = v[m], vn = pr[m];
+            const double2 v1 = make_double2(0.5 * (vk.x + vn.x), 0.5 * (vk.y - vn.y));
+            const double2 dd = make_double2(vk.x - vn.x, vk.y + vn.y);
+            const double2 v2 = make_double2(0.5 * dd.y, -0.5 * dd.x);
+            const double2 p = __ldg(&pw[k]);
+            double x1 = p.x * v1.x - p.y * v1.y;
+            double x2 = p.x * v2.x - p.y * v2.y;
+            s[PAD16(k)] = make_double2(x1, x2);
+            }
+        }
+        if (MODE == 2) {
+            // spectral division rhs ./ (D^2 * ((CY + CX) + CT)) on the thread's own entries; kept out of the unrolled
+            // register-resident section (FP64 division needs many temporaries)
+            const i64 l1 = sa.line_offset + line0 + 2 * pair, l2 = l1 + 1;
+            const int xx1 = (int)(l1 / sa.ny), yy1 = (int)(l1 - (i64)xx1 * sa.ny);
+            const int xx2 = (int)(l2 / sa.ny), yy2 = (int)(l2 - (i64)xx2 * sa.ny);
+            const bool ok1 = l1 - sa.line_offset < lg.inner, ok2 = l2 - sa.line_offset < lg.inner;
+            const double lxy1 = ok1 ? __dadd_rn(sa.lam_y[yy1], sa.lam_x[xx1]) : 1.0;
+            const double lxy2 = ok2 ? __dadd_rn(sa.lam_y[yy2], sa.lam_x[xx2]) : 1.0;
+#pragma unroll 1
+            for (int m = 0; m < NM; m++) {
+                const int k = j + m * TP;
+                if (k < n) {
+                    double2 x = s[PAD16(k)];
+                    const double lt = sa.lam_t[k];
+                    double k1 = ok1 ? __dadd_rn(lxy1, lt) : 1.0, k2 = ok2 ? __dadd_rn(lxy2, lt) : 1.0;
+                    if (k1 == 0.0) k1 = 1.0;
+                    if (k2 == 0.0) k2 = 1.0;
+                    x.x = x.x / __dmul_rn(sa.D2, k1);
+                    x.y = x.y / __dmul_rn(sa.D2, k2);
+                    s[PAD16(k)] = x;
+                }
+            }
+        }
+        pair_sync<TP>(pair);
+    }
+    if (MODE != 0) {
+        // s[k] = (X1[k], X2[k]);  V[k] = g_k [(X1[k]+X2[n-k]) + i (X2[k]-X1[n-k])];  input of the core = conj(V) w
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const int k = j + m * TP;
+            if (m < NM && k < n) {
+                const double2 xk = s[PAD16(k)];
+                const double2 gk = __ldg(&ipw[k]);
+                double2 V;
+                if (k == 0) {
+                    V = make_double2(xk.x * gk.x, xk.y * gk.x);
+                } else {
+                    const double2 xn = s[PAD16(n - k)];
+                    V = c_mul(gk, make_double2(xk.x + xn.y, xk.y - xn.x));
+                }
+                v[m] = c_mul(c_conj(V), __ldg(&w[k]));
+            } else {
+                v[m] = make_double2(0.0, 0.0);
+            }
+        }
+        pair_sync<TP>(pair);
+        {
+            // MODE 2 runs the convolution core twice: hide the table pointers from CSE, otherwise the compiler keeps the
+            // 46 twiddle / spectrum values of the first call alive in local memory (1 KB of spills per thread)
+            const double2* tw_b = tw;
+            const double2* bh_b = bhat16;
+            if (MODE == 2) { asm volatile("" : "+l"(tw_b)); asm volatile("" : "+l"(bh_b)); }
+            conv16<LOG2M>(v, j, pair, s, tw_b, bh_b);
+        }
+        pair_sync<TP>(pair);
+#pragma unroll
+        for (int m = 0; m < NM; m++) {
+            const int pos = j + m * TP;
+            if (pos < n) {
+                const double2 d = c_mul(v[m], __ldg(&w[pos]));
+                s[PAD16(pos)] = make_double2(d.x, -d.y);
+            }
+        }
+        pair_sync<TP>(pair);
+    }
+    __syncthreads();
+    // ---- stage out --------------------------------------------------------------------------------------------------
+    {
+        const int total = G * n;
+        for (int f = tid; f < total; f += NTHR) {
+            int g, jj;
+            if (lg.contiguous) { g = f / n; jj = f - g * n; } else { jj = f / G; g = f - jj * G; }
+            if (g < nlines) {
+                const double* src = reinterpret_cast<const double*>(smem + (size_t)(g >> 1) * PADLEN + PAD16(MODE == 0 ? jj : makhoul(jj, n)));
+                aout[gbase + (i64)g * lg.gstride + (i64)jj * lg.estride] = src[g & 1];
+            }
+        }
+    }
+}
+
+template <int LOG2M, int PAIRS>
+static void launch_blu16(const DctPlan* p, const LineGeom& lg, i64 outer, const double* ain, double* a, int mode,
+                         const ScaleArgs& sa, cudaStream_t st)
+{
+    constexpr int M = 1 << LOG2M, TP = M / 16, G = 2 * PAIRS, NTHR = TP * PAIRS;
+    const size_t smem = (size_t)PAIRS * (M + M / 16 + 1) * sizeof(double2);
+    dim3 grid((unsigned)((lg.inner + G - 1) / G), (unsigned)outer);
+    static bool attr_set[3] = {false, false, false};
+#define BLU(MODE)                                                                                                  \
+    {                                                                                                              \
+        if (!attr_set[MODE]) {                                                                                     \
+            cudaFuncSetAttribute(k_dct_blu16<LOG2M, PAIRS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                 (int)smem);                                                                       \
+            attr_set[MODE] = true;                                                                                 \
+        }                                                                                                          \
+        k_dct_blu16<LOG2M, PAIRS, MODE><<<grid, NTHR, smem, st>>>(lg, ain, a, p->w, p->bhat16, p->tw, p->pw, p->ipw, sa); \
+    }
+    if (mode == 0) BLU(0) else if (mode == 1) BLU(1) else BLU(2)
+#undef BLU
+}
+
 // ------------------------------------------------------------------------------------------------ dense small-n kernel
 // One CTA = G lines staged in shared memory; thread (g,k) computes one output.  MODE as above.
 template <int MODE>
@@ -537,11 +772,11 @@ static void launch_dct_axis(const DctPlan* p, LineGeom lg, i64 outer, const doub
     switch (p->log2m) {
         case 6: launch_blu<6, 32>(p, lg, outer, ain, a, mode, sa, st); break;
         case 7: launch_blu<7, 16>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 8: launch_blu<8, 8>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 9: launch_blu<9, 4>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 10: launch_blu<10, 2>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 11: launch_blu<11, 2>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 12: launch_blu<12, 2>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 8: launch_blu16<8, 16>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 9: launch_blu16<9, 8>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 10: launch_blu16<10, 4>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 11: launch_blu16<11, 2>(p, lg, outer, ain, a, mode, sa, st); break;
+        case 12: launch_blu16<12, 2>(p, lg, outer, ain, a, mode, sa, st); break;
         default: fprintf(stderr, "dotsocp: unsupported transform length %d\n", p->n); break;
     }
 }
