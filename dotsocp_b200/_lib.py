@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdotsocp.so")
+LIB_PATH = os.environ.get("DOTSOCP_LIB") or os.path.join(_HERE, "libdotsocp.so")   # override only for A/B experiments
 
 VARIANT = {"dot2d": 0, "wdot2d": 1, "dot1d": 2}
 METHOD = {"inPALM": 0, "ALG2": 0, "PALM": 1, "acc-ADMM": 2}

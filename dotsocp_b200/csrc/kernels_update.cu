@@ -369,26 +369,49 @@ void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st,
 // 10-column temporaries never touch HBM.  The x+1 / y+1 neighbours' w (columns 1,3 / 5,7) come through shared
 // memory; the t-1 layer's columns 3,4,7,8 are carried in registers.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 template <bool WEIGHTED>
 __device__ __forceinline__ double uval(double q, double a, double w)
 {
     return WEIGHTED ? dsub(dmul(w, q), a) : dsub(q, a);
 }
 
-template <int TX, int TY, bool WEIGHTED, bool ONE_D, bool UPDATE>
-__global__ void __launch_bounds__(TX* TY) k_mult(Geo g, TRange tr, IterScal sc, const double* __restrict__ qo,
-                                                 const double* __restrict__ qn, const double* __restrict__ alpha,
-                                                 const double* __restrict__ weight, const double* __restrict__ beta,
-                                                 double* __restrict__ beta_out, double* __restrict__ q2,
-                                                 double* __restrict__ rhs, const double* __restrict__ c0,
-                                                 const double* __restrict__ c1)
+#ifndef KM_MIN_BLOCKS
+#define KM_MIN_BLOCKS 2
+#endif
+#ifndef KM_PREFETCH
+#define KM_PREFETCH 0     // 1: cp.async ring for the next step's loads (measured: no gain, the kernel is issue/latency bound)
+#endif
+template <int TX, int TY, bool WEIGHTED, bool ONE_D, bool UPDATE, bool EDGE>
+__device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, const IterScal& sc, const double* __restrict__ qo,
+                                            const double* __restrict__ qn, const double* __restrict__ alpha,
+                                            const double* __restrict__ weight, const double* __restrict__ beta,
+                                            double* __restrict__ beta_out, double* __restrict__ q2,
+                                            double* __restrict__ rhs, const double* __restrict__ c0,
+                                            const double* __restrict__ c1)
 {
-    __shared__ double sh[2][4][TX][TY];
+    // dynamic shared memory: [2][4][NT] exchange of the w columns 1,3,5,7 + a two-stage ring [2][NV][NT] into which every
+    // thread prefetches (cp.async, 8 B) the 21 values of its NEXT time step while it works on the current one, so the
+    // HBM latency of the beta / q streams is overlapped with the two projections instead of being exposed once per step
+    constexpr int NT = TX * TY, NV = 21;
+    extern __shared__ double dyn_smem[];
+    double (*sh)[4][TX][TY] = reinterpret_cast<double (*)[4][TX][TY]>(dyn_smem);
+    double* ring = dyn_smem + 2 * 4 * NT;
     const int ly = threadIdx.x, lx = threadIdx.y;
-    const int x = blockIdx.x * (TX - 1) + lx, y = blockIdx.y * (TY - 1) + ly;
-    const bool valid = (x < g.nx) && (y < g.ny);
+    const int tid = lx * TY + ly;
+    // y tiles vary fastest over the grid so that CTAs running side by side stream adjacent pieces of the same rows
+    const int x = blockIdx.y * (TX - 1) + lx, y = blockIdx.x * (TY - 1) + ly;
+    // EDGE = false: the whole tile (halo included) lies strictly inside the domain, every neighbour exists and all the
+    // boundary predicates fold away at compile time (most CTAs of a large grid)
+    const bool valid = EDGE ? ((x < g.nx) && (y < g.ny)) : true;
     const bool owner = valid && (lx < TX - 1) && (ly < TY - 1);
-    const bool hxm = valid && x > 0, hxp = valid && x < g.nx - 1, hym = valid && y > 0, hyp = valid && y < g.ny - 1;
+    const bool hxm = EDGE ? (valid && x > 0) : true, hxp = EDGE ? (valid && x < g.nx - 1) : true;
+    const bool hym = EDGE ? (valid && y > 0) : true, hyp = EDGE ? (valid && y < g.ny - 1) : true;
     const i64 L = g.L;
     const i64 node = (i64)x * g.ny + y;
     const i64 ibx = (i64)x * g.ny + y, ibxm = ibx - g.ny;
@@ -428,6 +451,34 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, TRange tr, IterScal sc, 
 
     double wp3n = 0.0, wp4 = 0.0, wp7n = 0.0, wp8 = 0.0, u0p = 0.0;
 
+    // ring slots: 0..9 beta, 10 q0 new, 11 q0 old, 12 alpha0, 13..16 new bx/by at level t+1, 17..20 old bx/by at t+1
+    auto prefetch = [&](int tt) {
+        if (!KM_PREFETCH) return;
+        if (tt < g.nt - 1 && valid) {
+            double* dst = ring + (size_t)(tt & 1) * NV * NT + tid;
+            const i64 cc = (i64)tt * g.P + node;
+#pragma unroll
+            for (int j = 0; j < 10; j++)
+                if (!(ONE_D && j >= 5 && j <= 8)) cp_async8(dst + j * NT, beta + (i64)j * L + cc);
+            cp_async8(dst + 10 * NT, qn + cc);
+            if (UPDATE) cp_async8(dst + 11 * NT, qo + cc);
+            cp_async8(dst + 12 * NT, alpha + cc);
+            const i64 o1x = (i64)(tt + 1) * g.PBX, o1y = (i64)(tt + 1) * g.PBY;
+            if (hxm) cp_async8(dst + 13 * NT, qn_bx + o1x + ibxm);
+            if (hxp) cp_async8(dst + 14 * NT, qn_bx + o1x + ibx);
+            if (hym) cp_async8(dst + 15 * NT, qn_by + o1y + ibym);
+            if (hyp) cp_async8(dst + 16 * NT, qn_by + o1y + iby);
+            if (UPDATE) {
+                if (hxm) cp_async8(dst + 17 * NT, qo_bx + o1x + ibxm);
+                if (hxp) cp_async8(dst + 18 * NT, qo_bx + o1x + ibx);
+                if (hym) cp_async8(dst + 19 * NT, qo_by + o1y + ibym);
+                if (hyp) cp_async8(dst + 20 * NT, qo_by + o1y + iby);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(t_start);
+
     for (int t = t_start; t < tr.tn1; t++) {
         const int buf = t & 1;
         const bool cell = t < g.nt - 1;
@@ -437,24 +488,50 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, TRange tr, IterScal sc, 
         double a0 = 0.0, wt0 = 1.0;
 #pragma unroll
         for (int j = 0; j < 10; j++) w[j] = 0.0;
+        if (t + 1 < tr.tn1) prefetch(t + 1);
+        // the level-t alpha (and weight) values of the rhs stencil are only needed after the barrier: issue them now so
+        // that their latency hides behind the two projections
+        double al_xm = 0.0, al_x = 0.0, al_ym = 0.0, al_y = 0.0, wt_xm = 1.0, wt_x = 1.0, wt_ym = 1.0, wt_y = 1.0;
+        if (owner) {
+            const i64 ox = (i64)t * g.PBX, oy = (i64)t * g.PBY;
+            if (hxm) al_xm = al_bx[ox + ibxm];
+            if (hxp) al_x = al_bx[ox + ibx];
+            if (hym) al_ym = al_by[oy + ibym];
+            if (hyp) al_y = al_by[oy + iby];
+            if (WEIGHTED) {
+                if (hxm) wt_xm = w_bx[ox + ibxm];
+                if (hxp) wt_x = w_bx[ox + ibx];
+                if (hym) wt_ym = w_by[oy + ibym];
+                if (hyp) wt_y = w_by[oy + iby];
+                if (cell) wt0 = weight[cidx];
+            }
+        }
+        if (KM_PREFETCH) {
+            if (t + 1 < tr.tn1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         if (cell && valid) {
+            const double* src = ring + (size_t)buf * NV * NT + tid;
+            const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
+#define LDV(slot, gexpr) (KM_PREFETCH ? src[(slot) * NT] : (gexpr))
             double b[10];
 #pragma unroll
-            for (int j = 0; j < 10; j++) b[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0 : beta[(i64)j * L + cidx];
-            cn.q0 = qn[cidx];
-            const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
-            cn.bxm1 = hxm ? qn_bx[o1x + ibxm] : 0.0;
-            cn.bx1 = hxp ? qn_bx[o1x + ibx] : 0.0;
-            cn.bym1 = hym ? qn_by[o1y + ibym] : 0.0;
-            cn.by1 = hyp ? qn_by[o1y + iby] : 0.0;
+            for (int j = 0; j < 10; j++) b[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0 : LDV(j, beta[(i64)j * L + cidx]);
+            cn.q0 = LDV(10, qn[cidx]);
+            a0 = LDV(12, alpha[cidx]);
+            cn.bxm1 = hxm ? LDV(13, qn_bx[o1x + ibxm]) : 0.0;
+            cn.bx1 = hxp ? LDV(14, qn_bx[o1x + ibx]) : 0.0;
+            cn.bym1 = hym ? LDV(15, qn_by[o1y + ibym]) : 0.0;
+            cn.by1 = hyp ? LDV(16, qn_by[o1y + iby]) : 0.0;
             double z2n[10];
             cell_z2(cn, sc, hxm, hxp, hym, hyp, z2n);
             if (UPDATE) {
-                co.q0 = qo[cidx];
-                co.bxm1 = hxm ? qo_bx[o1x + ibxm] : 0.0;
-                co.bx1 = hxp ? qo_bx[o1x + ibx] : 0.0;
-                co.bym1 = hym ? qo_by[o1y + ibym] : 0.0;
-                co.by1 = hyp ? qo_by[o1y + iby] : 0.0;
+                co.q0 = LDV(11, qo[cidx]);
+                co.bxm1 = hxm ? LDV(17, qo_bx[o1x + ibxm]) : 0.0;
+                co.bx1 = hxp ? LDV(18, qo_bx[o1x + ibx]) : 0.0;
+                co.bym1 = hym ? LDV(19, qo_by[o1y + ibym]) : 0.0;
+                co.by1 = hyp ? LDV(20, qo_by[o1y + iby]) : 0.0;
+#undef LDV
                 double v[10];
                 cell_z2(co, sc, hxm, hxp, hym, hyp, v);
 #pragma unroll
@@ -481,8 +558,6 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, TRange tr, IterScal sc, 
         if (owner) {
             if (cell) {
                 if (emit) q2[cidx] = dmul(dsub(w[9], w[0]), sc.S);
-                a0 = alpha[cidx];
-                if (WEIGHTED) wt0 = weight[cidx];
             }
             const double u0 = cell ? uval<WEIGHTED>(cn.q0, a0, wt0) : 0.0;
             // rhs = A' u + c : CSR-transpose row order (t-1 edge, t edge, x-1, x, y-1, y)
@@ -498,9 +573,9 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, TRange tr, IterScal sc, 
             if (cell) ADDTERM(dmul(-sc.gt, u0));
             if (hxp || hxm) {
                 const i64 ox = (i64)t * g.PBX;
-                if (hxm) ADDTERM(dmul(sc.gx, uval<WEIGHTED>(cn.bxm, al_bx[ox + ibxm], WEIGHTED ? w_bx[ox + ibxm] : 1.0)));
+                if (hxm) ADDTERM(dmul(sc.gx, uval<WEIGHTED>(cn.bxm, al_xm, wt_xm)));
                 if (hxp) {
-                    ADDTERM(dmul(-sc.gx, uval<WEIGHTED>(cn.bx, al_bx[ox + ibx], WEIGHTED ? w_bx[ox + ibx] : 1.0)));
+                    ADDTERM(dmul(-sc.gx, uval<WEIGHTED>(cn.bx, al_x, wt_x)));
                     const double w1n = cell ? sh[buf][0][lx + 1][ly] : 0.0;
                     const double w3n = cell ? sh[buf][1][lx + 1][ly] : 0.0;
                     double s;
@@ -516,9 +591,9 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, TRange tr, IterScal sc, 
             }
             if (hyp || hym) {
                 const i64 oy = (i64)t * g.PBY;
-                if (hym) ADDTERM(dmul(sc.gy, uval<WEIGHTED>(cn.bym, al_by[oy + ibym], WEIGHTED ? w_by[oy + ibym] : 1.0)));
+                if (hym) ADDTERM(dmul(sc.gy, uval<WEIGHTED>(cn.bym, al_ym, wt_ym)));
                 if (hyp) {
-                    ADDTERM(dmul(-sc.gy, uval<WEIGHTED>(cn.by, al_by[oy + iby], WEIGHTED ? w_by[oy + iby] : 1.0)));
+                    ADDTERM(dmul(-sc.gy, uval<WEIGHTED>(cn.by, al_y, wt_y)));
                     const double w5n = cell ? sh[buf][2][lx][ly + 1] : 0.0;
                     const double w7n = cell ? sh[buf][3][lx][ly + 1] : 0.0;
                     double s;
@@ -547,20 +622,44 @@ __global__ void __launch_bounds__(TX* TY) k_mult(Geo g, TRange tr, IterScal sc, 
     }
 }
 
+template <int TX, int TY, bool WEIGHTED, bool ONE_D, bool UPDATE>
+__global__ void __launch_bounds__(TX* TY, KM_MIN_BLOCKS) k_mult(Geo g, TRange tr, IterScal sc, const double* __restrict__ qo,
+                                                 const double* __restrict__ qn, const double* __restrict__ alpha,
+                                                 const double* __restrict__ weight, const double* __restrict__ beta,
+                                                 double* __restrict__ beta_out, double* __restrict__ q2,
+                                                 double* __restrict__ rhs, const double* __restrict__ c0,
+                                                 const double* __restrict__ c1)
+{
+    const int x0 = blockIdx.y * (TX - 1), y0 = blockIdx.x * (TY - 1);
+    const bool interior = !ONE_D && x0 >= 1 && x0 + TX - 1 <= g.nx - 2 && y0 >= 1 && y0 + TY - 1 <= g.ny - 2;
+    if (interior)
+        k_mult_body<TX, TY, WEIGHTED, ONE_D, UPDATE, false>(g, tr, sc, qo, qn, alpha, weight, beta, beta_out, q2, rhs, c0, c1);
+    else
+        k_mult_body<TX, TY, WEIGHTED, ONE_D, UPDATE, true>(g, tr, sc, qo, qn, alpha, weight, beta, beta_out, q2, rhs, c0, c1);
+}
+
 void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st)
 {
-    constexpr int TX = 8, TY = 64;
+    constexpr int TX = 8, TY = 32;
     dim3 block(TY, TX);
-    dim3 grid((unsigned)((a.g.nx + TX - 2) / (TX - 1)), (unsigned)((a.g.ny + TY - 2) / (TY - 1)));
-#define KM(W, O, U)                                                                                          \
-    k_mult<TX, TY, W, O, U><<<grid, block, 0, st>>>(a.g, a.tr, a.sc, a.q_old, a.q_new, a.alpha, a.weight, a.beta_in, \
-                                                     a.beta_out, a.q2, a.rhs, a.c0, a.c1)
+    dim3 grid((unsigned)((a.g.ny + TY - 2) / (TY - 1)), (unsigned)((a.g.nx + TX - 2) / (TX - 1)));
+    const size_t smem = (size_t)(2 * 4 + (KM_PREFETCH ? 2 * 21 : 0)) * TX * TY * sizeof(double);
+#define KM(W, O, U)                                                                                                   \
+    {                                                                                                                 \
+        static bool attr_done = false;                                                                                \
+        if (!attr_done) {                                                                                             \
+            cudaFuncSetAttribute(k_mult<TX, TY, W, O, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+            attr_done = true;                                                                                         \
+        }                                                                                                             \
+        k_mult<TX, TY, W, O, U><<<grid, block, smem, st>>>(a.g, a.tr, a.sc, a.q_old, a.q_new, a.alpha, a.weight,      \
+                                                            a.beta_in, a.beta_out, a.q2, a.rhs, a.c0, a.c1);          \
+    }
     if (one_d) {
-        if (update) KM(false, true, true); else KM(false, true, false);
+        if (update) KM(false, true, true) else KM(false, true, false)
     } else if (weighted) {
-        if (update) KM(true, false, true); else KM(true, false, false);
+        if (update) KM(true, false, true) else KM(true, false, false)
     } else {
-        if (update) KM(false, false, true); else KM(false, false, false);
+        if (update) KM(false, false, true) else KM(false, false, false)
     }
 #undef KM
 }
