@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <vector>
+
 namespace dsocp {
 
 // owned part of a time slab: cell layers [tc0, tc1), node levels [tn0, tn1) (the last slab also owns level nt-1)
@@ -99,6 +101,11 @@ struct PoissonPlan {
     double* lam_t;  // (2 (n-1)^2)(1 - cos(pi k / n))   initialize_FFTkernel.m:6-8
     double* lam_x;
     double* lam_y;
+    // tridiagonal t-solve (default; DOTSOCP_TSOLVE=dct selects the fused DCT_t / divide / IDCT_t kernel instead)
+    bool use_thomas;
+    struct GTab { i64 p0, lines; double* tab; };   // pivot reciprocals g_t(mode), [nt][lines] for modes [p0, p0+lines)
+    std::vector<GTab> gtabs;
+    double* cmat_t;     // dense nt x nt orthonormal DCT-II matrix for the singular mode kx = ky = 0
 };
 PoissonPlan* poisson_plan_create(int nt, int nx, int ny);
 void poisson_plan_destroy(PoissonPlan* p);

@@ -18,6 +18,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -781,6 +782,96 @@ static void launch_dct_axis(const DctPlan* p, LineGeom lg, i64 outer, const doub
     }
 }
 
+// ------------------------------------------------------------------------------------------------ t-solve without transforms
+// After the (y,x) transforms every (kx,ky) mode is an independent tridiagonal system along t:
+//     D^2 ( (nt-1)^2 T + (CY[ky]+CX[kx]) I ) phi = rhs ,   T = tridiag(-1, 2, -1) with 1 in the two corners,
+// exactly the operator whose eigenvalues the reference divides by (initialize_FFTkernel.m:6-15).  It is solved by the
+// Thomas algorithm with the pivot reciprocals g_t(mode) tabulated once per plan (they depend only on the grid), which
+// replaces two of the six O(n log n) transforms of the solve by 6N doubles of streaming traffic.  The singular mode
+// kx = ky = 0 keeps the reference's convention (zero eigenvalue := 1) through a dense DCT of that single line.
+__global__ void __launch_bounds__(256) k_thomas_table(int nt, int ny, i64 lines, i64 stride, i64 p0, const double* __restrict__ lam_x,
+                                                      const double* __restrict__ lam_y, double* __restrict__ gtab)
+{
+    const i64 l = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (l >= lines) return;
+    const i64 p = p0 + l;
+    const int kx = (int)(p / ny), ky = (int)(p - (i64)kx * ny);
+    const double ct = (double)(nt - 1) * (double)(nt - 1);
+    const double nu = (lam_y[ky] + lam_x[kx]) / ct;
+    double g = 1.0 / (1.0 + nu);
+    gtab[l] = g;
+    for (int t = 1; t < nt; t++) {
+        const double diag = (t == nt - 1 ? 1.0 : 2.0) + nu;
+        g = 1.0 / (diag - g);
+        gtab[(i64)t * stride + l] = g;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_thomas(int nt, i64 lines, i64 stride, i64 p0, double inv_scale, const double* __restrict__ gtab,
+                                                double* __restrict__ a)
+{
+    const i64 l = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (l >= lines || p0 + l == 0) return;      // mode (0,0) is handled by k_tline0
+    double d = 0.0;
+    int t = 0;
+    // forward elimination, 4 time levels per trip so that the loads of a trip are in flight together
+    for (; t + 4 <= nt; t += 4) {
+        double r[4], g[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { r[u] = a[(i64)(t + u) * stride + l]; g[u] = gtab[(i64)(t + u) * stride + l]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { d = (r[u] * inv_scale + d) * g[u]; a[(i64)(t + u) * stride + l] = d; }
+    }
+    for (; t < nt; t++) { d = (a[(i64)t * stride + l] * inv_scale + d) * gtab[(i64)t * stride + l]; a[(i64)t * stride + l] = d; }
+    // back substitution
+    double x = d;
+    t = nt - 2;
+    for (; t - 3 >= 0; t -= 4) {
+        double dd[4], g[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { dd[u] = a[(i64)(t - u) * stride + l]; g[u] = gtab[(i64)(t - u) * stride + l]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { x = dd[u] + g[u] * x; a[(i64)(t - u) * stride + l] = x; }
+    }
+    for (; t >= 0; t--) { x = a[(i64)t * stride + l] + gtab[(i64)t * stride + l] * x; a[(i64)t * stride + l] = x; }
+}
+
+// mode (0,0): phi = IDCT_t( DCT_t(r) ./ (D2 * lam_t) ), lam_t[0] := 1, dense nt x nt transform by one CTA
+__global__ void __launch_bounds__(256) k_tline0(int nt, i64 stride, double D2, const double* __restrict__ lam_t,
+                                                const double* __restrict__ cmat, double* __restrict__ a)
+{
+    extern __shared__ double sl[];   // [2][nt]
+    double* r = sl;
+    double* X = sl + nt;
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) r[t] = a[(i64)t * stride];
+    __syncthreads();
+    for (int k = threadIdx.x; k < nt; k += blockDim.x) {
+        double acc = 0.0;
+        for (int t = 0; t < nt; t++) acc += cmat[(i64)k * nt + t] * r[t];
+        double kv = lam_t[k];
+        if (kv == 0.0) kv = 1.0;
+        X[k] = acc / (D2 * kv);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+        double acc = 0.0;
+        for (int k = 0; k < nt; k++) acc += cmat[(i64)k * nt + t] * X[k];
+        a[(i64)t * stride] = acc;
+    }
+}
+
+static double* dense_dct_matrix(int n)
+{
+    std::vector<double> C((size_t)n * n);
+    const long double c0 = sqrtl(1.0L / n), c1 = sqrtl(2.0L / n);
+    for (int k = 0; k < n; k++)
+        for (int j = 0; j < n; j++) {
+            const long long a = ((long long)(2 * j + 1) * k) % (4LL * n);
+            C[(size_t)k * n + j] = (double)((k == 0 ? c0 : c1) * cosl(PIl * (long double)a / (2.0L * n)));
+        }
+    return to_device(C);
+}
+
 static double* lam_table(int n)
 {
     std::vector<double> v(n);
@@ -799,15 +890,51 @@ PoissonPlan* poisson_plan_create(int nt, int nx, int ny)
     p->lam_t = lam_table(nt);
     p->lam_x = lam_table(nx);
     p->lam_y = lam_table(ny);
+    p->cmat_t = nullptr;
+    const char* e = getenv("DOTSOCP_TSOLVE");
+    p->use_thomas = !(e && strcmp(e, "dct") == 0);
     return p;
 }
 
 void poisson_plan_destroy(PoissonPlan* p)
 {
     if (!p) return;
+    for (auto& e : p->gtabs) cudaFree(e.tab);
+    cudaFree(p->cmat_t);
     dct_plan_destroy(p->py); dct_plan_destroy(p->px); dct_plan_destroy(p->pt);
     cudaFree(p->lam_t); cudaFree(p->lam_x); cudaFree(p->lam_y);
     delete p;
+}
+
+// t-solve on a [nt][lines] array (line stride = lines) holding the modes p0 .. p0+lines-1
+static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, cudaStream_t st, double* launches)
+{
+    const Geo& g = p->g;
+    if (!p->use_thomas || g.nt < 3) {
+        ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, D2, p0};
+        LineGeom gt{g.nt, lines, 1, lines, 0, 0};
+        launch_dct_axis(p->pt, gt, 1, buf, buf, 2, sa, st);
+        if (launches) *launches += 1;
+        return;
+    }
+    // one table per mode range (a process that emulates several slabs keeps one per slab)
+    double* gtab = nullptr;
+    for (auto& e : p->gtabs)
+        if (e.p0 == p0 && e.lines == lines) gtab = e.tab;
+    if (!gtab) {
+        cudaMalloc(&gtab, (size_t)g.nt * lines * sizeof(double));
+        k_thomas_table<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, g.ny, lines, lines, p0, p->lam_x, p->lam_y, gtab);
+        p->gtabs.push_back({p0, lines, gtab});
+        if (!p->cmat_t) p->cmat_t = dense_dct_matrix(g.nt);
+        if (launches) *launches += 1;
+    }
+    const double ct = (double)(g.nt - 1) * (double)(g.nt - 1);
+    if (p0 == 0) {
+        k_tline0<<<1, 256, (size_t)2 * g.nt * sizeof(double), st>>>(g.nt, lines, D2, p->lam_t, p->cmat_t, buf);
+        if (launches) *launches += 1;
+    }
+    k_thomas<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, lines, lines, p0, 1.0 / (D2 * ct), gtab, buf);
+    if (launches) *launches += 1;
 }
 
 static LineGeom geom_y(const Geo& g) { return LineGeom{g.ny, 1, (i64)g.ny, (i64)g.nt * g.nx, 0, 1}; }
@@ -827,9 +954,9 @@ void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cuda
     const double* src = rhs;
     if (g.ny > 1) { launch_dct_axis(p->py, geom_y(g), 1, src, a, 0, sa, st); src = a; if (launches) *launches += 1; }
     launch_dct_axis(p->px, geom_x(g), xo, src, a, 0, sa, st);
-    launch_dct_axis(p->pt, geom_t(g), 1, a, a, 2, sa, st);
+    t_solve(p, a, g.P, 0, D2, st, launches);
     launch_dct_axis(p->px, geom_x(g), xo, a, a, 1, sa, st);
-    if (launches) *launches += 3;
+    if (launches) *launches += 2;
     if (g.ny > 1) { launch_dct_axis(p->py, geom_y(g), 1, a, a, 1, sa, st); if (launches) *launches += 1; }
 }
 
@@ -856,11 +983,7 @@ void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev,
 // t-pass (DCT_t, ./kernel, IDCT_t) on a [nt][chunk] array holding the (x,y) modes p0 .. p0+chunk-1
 void poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches)
 {
-    const Geo& g = p->g;
-    ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, D2, p0};
-    LineGeom gt{g.nt, chunk, 1, chunk, 0, 0};
-    launch_dct_axis(p->pt, gt, 1, buf, buf, 2, sa, st);
-    if (launches) *launches += 1;
+    t_solve(p, buf, chunk, p0, D2, st, launches);
 }
 
 void poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches)
