@@ -386,10 +386,15 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
         return 0;
     }
     const NcclApi& n = nccl_api();
+    const bool fused_pack = poisson_can_pack(c->pp);
     for (Slab* s : c->slabs) {
-        poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0, s->tr.tn1 - s->tr.tn0, false, c->st, &c->launches);
-        // pack: block r of the send buffer = rows of this slab x modes of slab r
         const int nlev = s->tr.tn1 - s->tr.tn0;
+        if (fused_pack) {   // the x-forward kernel scatters straight into the send buffer
+            poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0, nlev, false, c->st, &c->launches, s->tsend, c->world);
+            continue;
+        }
+        poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0, nlev, false, c->st, &c->launches);
+        // pack: block r of the send buffer = rows of this slab x modes of slab r
         for (int r = 0; r < c->world; r++) {
             const i64 ch = c->pcut[r + 1] - c->pcut[r];
             CU(cudaMemcpy2DAsync(s->tsend + (i64)nlev * c->pcut[r], ch * sizeof(double), s->phi + s->tr.tn0 * g.P + c->pcut[r],
@@ -430,12 +435,16 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
     if ((rc = all_to_all(false))) return rc;
     for (Slab* s : c->slabs) {
         const int nlev = s->tr.tn1 - s->tr.tn0;
+        if (fused_pack) {   // the x-inverse kernel gathers straight from the receive side of the second transpose
+            poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0, nlev, true, c->st, &c->launches, s->tsend, c->world);
+            continue;
+        }
         for (int r = 0; r < c->world; r++) {
             const i64 ch = c->pcut[r + 1] - c->pcut[r];
             CU(cudaMemcpy2DAsync(s->phi + s->tr.tn0 * g.P + c->pcut[r], g.P * sizeof(double), s->tsend + (i64)nlev * c->pcut[r],
                                  ch * sizeof(double), ch * sizeof(double), nlev, cudaMemcpyDeviceToDevice, c->st));
         }
-        poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0, s->tr.tn1 - s->tr.tn0, true, c->st, &c->launches);
+        poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0, nlev, true, c->st, &c->launches);
     }
     return ghosts(c, GH_PHI_UP, 0, 0);
 }

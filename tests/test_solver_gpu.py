@@ -206,3 +206,31 @@ def test_time_slab_partition_emulated_on_one_gpu(gpu, world, variant):
     assert abs(r1.sigma - rw.sigma) <= 1e-13 * abs(r1.sigma)
     for a, b, name in zip(s1, sw, ("phi", "q", "z", "alpha", "beta")):
         assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), name
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_time_slabs_with_fused_transpose_pack(gpu, world):
+    """nx = 129 uses the register-FFT DCT kernel, whose x passes write/read the packed all-to-all buffer directly."""
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import driver, solver
+    nt, nx, ny = 9, 129, 12
+    rng = np.random.default_rng(5)
+    rho0 = np.abs(rng.standard_normal((ny, nx))) + 0.1
+    rho1 = np.abs(rng.standard_normal((ny, nx))) + 0.1
+    rho0 *= rho0.size / rho0.sum()
+    rho1 *= rho1.size / rho1.sum()
+    out = []
+    for w in (1, world):
+        var, model = driver.initialize(rho0, rho1, nt)
+        driver.InitialScaling(var, model, True, None, "dot2d")
+        opts = {"tol": 1e-12, "maxit": 60, "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": False, "scaling": True}
+        o = solver.make_level_opts("dot2d", "inPALM", var, opts, model)
+        with dp.Session("dot2d", nt, nx, ny, world=w) as s:
+            s.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c)
+            hb, res = s.run(o)
+            out.append((hb, res, s.download()))
+    (hb1, r1, s1), (hbw, rw, sw) = out
+    assert r1.iters == rw.iters == 60 and r1.hist_len == rw.hist_len
+    assert np.abs(hb1.kkt[:r1.hist_len] - hbw.kkt[:rw.hist_len]).max() < 1e-12
+    for a, b, name in zip(s1, sw, ("phi", "q", "z", "alpha", "beta")):
+        assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), name
