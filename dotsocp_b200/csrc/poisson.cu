@@ -304,19 +304,22 @@ struct LineGeom {
     i64 ostride;       // distance between outer indices
     int contiguous;    // 1: lines are contiguous (estride == 1): flat staging index runs along the line
     // time-slab transposes fused into the x passes: element (t_loc = blockIdx.y, p = x*ny + y) lives in the packed
-    // all-to-all buffer at  nlev*pcut[r] + t_loc*(pcut[r+1]-pcut[r]) + (p - pcut[r]),  pcut[r] = r*P/world,  r = owner of p
+    // all-to-all buffer at  nlev*pcut[r] + t_loc*(pcut[r+1]-pcut[r]) + (p - pcut[r]),  pcut[r] = min(P, r*ceil(P/world))
     int rm_world;      // 0: no remap
     int rm_nlev;
+    int rm_t0;         // first local level of this launch (the slab is processed in groups of levels)
     i64 rm_P;
     int rm_ny;
 };
 
 __device__ __forceinline__ i64 remap_index(const LineGeom& lg, int t_loc, i64 p)
 {
-    i64 r = (p * lg.rm_world) / lg.rm_P;
-    if (((r + 1) * lg.rm_P) / lg.rm_world <= p) r++;
-    const i64 c0 = (r * lg.rm_P) / lg.rm_world, c1 = ((r + 1) * lg.rm_P) / lg.rm_world;
-    return (i64)lg.rm_nlev * c0 + (i64)t_loc * (c1 - c0) + (p - c0);
+    // chunks of C = ceil(P/world) modes (the last one shorter): one 32-bit division per element
+    const unsigned C = (unsigned)((lg.rm_P + lg.rm_world - 1) / lg.rm_world);
+    const unsigned r = (unsigned)p / C;
+    const i64 c0 = (i64)r * C;
+    const i64 ch = (lg.rm_P - c0) < (i64)C ? (lg.rm_P - c0) : (i64)C;
+    return (i64)lg.rm_nlev * c0 + (i64)t_loc * ch + (p - c0);
 }
 
 struct ScaleArgs {     // MODE 2 (t axis): divide the spectrum by D2*((lamY[y] + lamX[x]) + lamT[k]), zero -> 1
@@ -539,7 +542,7 @@ k_dct_blu16(LineGeom lg, const double* ain, double* aout, const double2* __restr
             if (lg.contiguous) { g = f / n; jj = f - g * n; } else { jj = f / G; g = f - jj * G; }
             if (f < total && g < nlines) {
                 if (MODE == 1 && lg.rm_world)   // x-inverse of a slab: read straight from the packed all-to-all buffer
-                    vals[u] = ain[remap_index(lg, blockIdx.y, (i64)jj * lg.rm_ny + (line0 + g))];
+                    vals[u] = ain[remap_index(lg, lg.rm_t0 + blockIdx.y, (i64)jj * lg.rm_ny + (line0 + g))];
                 else
                     vals[u] = ain[gbase + (i64)g * lg.gstride + (i64)jj * lg.estride];
             } else {
@@ -672,7 +675,7 @@ k_dct_blu16(LineGeom lg, const double* ain, double* aout, const double2* __restr
             if (g < nlines) {
                 const double* src = reinterpret_cast<const double*>(smem + (size_t)(g >> 1) * PADLEN + PAD16(MODE == 0 ? jj : makhoul(jj, n)));
                 if (MODE == 0 && lg.rm_world)   // x-forward of a slab: write straight into the packed all-to-all buffer
-                    aout[remap_index(lg, blockIdx.y, (i64)jj * lg.rm_ny + (line0 + g))] = src[g & 1];
+                    aout[remap_index(lg, lg.rm_t0 + blockIdx.y, (i64)jj * lg.rm_ny + (line0 + g))] = src[g & 1];
                 else
                     aout[gbase + (i64)g * lg.gstride + (i64)jj * lg.estride] = src[g & 1];
             }
@@ -936,7 +939,7 @@ static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, c
     const Geo& g = p->g;
     if (!p->use_thomas || g.nt < 3) {
         ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, D2, p0};
-        LineGeom gt{g.nt, lines, 1, lines, 0, 0, 0, 0, 0, 0};
+        LineGeom gt{g.nt, lines, 1, lines, 0, 0, 0, 0, 0, 0, 0};
         launch_dct_axis(p->pt, gt, 1, buf, buf, 2, sa, st);
         if (launches) *launches += 1;
         return;
@@ -961,13 +964,13 @@ static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, c
     if (launches) *launches += 1;
 }
 
-static LineGeom geom_y(const Geo& g) { return LineGeom{g.ny, 1, (i64)g.ny, (i64)g.nt * g.nx, 0, 1, 0, 0, 0, 0}; }
+static LineGeom geom_y(const Geo& g) { return LineGeom{g.ny, 1, (i64)g.ny, (i64)g.nt * g.nx, 0, 1, 0, 0, 0, 0, 0}; }
 static LineGeom geom_x(const Geo& g)
 {
-    if (g.ny == 1) return LineGeom{g.nx, 1, (i64)g.nx, (i64)g.nt, 0, 1, 0, 0, 0, 0};   // 1-D variant: x lines are contiguous
-    return LineGeom{g.nx, (i64)g.ny, 1, (i64)g.ny, g.P, 0, 0, 0, 0, 0};
+    if (g.ny == 1) return LineGeom{g.nx, 1, (i64)g.nx, (i64)g.nt, 0, 1, 0, 0, 0, 0, 0};   // 1-D variant: x lines are contiguous
+    return LineGeom{g.nx, (i64)g.ny, 1, (i64)g.ny, g.P, 0, 0, 0, 0, 0, 0};
 }
-static LineGeom geom_t(const Geo& g) { return LineGeom{g.nt, g.P, 1, g.P, 0, 0, 0, 0, 0, 0}; }
+static LineGeom geom_t(const Geo& g) { return LineGeom{g.nt, g.P, 1, g.P, 0, 0, 0, 0, 0, 0, 0}; }
 
 void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cudaStream_t st, double* launches)
 {
@@ -986,16 +989,17 @@ void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cuda
 
 // ---- pieces of the solve for a time slab (node levels [tn0, tn0+nlev) of the global array) --------------------------------
 void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev, bool inverse, cudaStream_t st, double* launches,
-                double* packed, int world)
+                double* packed, int world, int slab_nlev, int slab_t0)
 {
+    // (tn0, nlev) may be a group of levels of a slab that owns slab_nlev levels starting slab_t0 levels before tn0
     // packed != NULL (and the x length uses the register-FFT kernel): the forward x pass writes, and the inverse x pass
     // reads, the packed all-to-all buffer directly instead of the slab rows of `a`
     const Geo& g = p->g;
     ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, 1.0, 0};
     const i64 off = (i64)tn0 * g.P;
-    LineGeom gy{g.ny, 1, (i64)g.ny, (i64)nlev * g.nx, 0, 1, 0, 0, 0, 0};
-    LineGeom gx = (g.ny == 1) ? LineGeom{g.nx, 1, (i64)g.nx, (i64)nlev, 0, 1, 0, 0, 0, 0} : LineGeom{g.nx, (i64)g.ny, 1, (i64)g.ny, g.P, 0, 0, 0, 0, 0};
-    if (packed) { gx.rm_world = world; gx.rm_nlev = nlev; gx.rm_P = g.P; gx.rm_ny = g.ny; }
+    LineGeom gy{g.ny, 1, (i64)g.ny, (i64)nlev * g.nx, 0, 1, 0, 0, 0, 0, 0};
+    LineGeom gx = (g.ny == 1) ? LineGeom{g.nx, 1, (i64)g.nx, (i64)nlev, 0, 1, 0, 0, 0, 0, 0} : LineGeom{g.nx, (i64)g.ny, 1, (i64)g.ny, g.P, 0, 0, 0, 0, 0, 0};
+    if (packed) { gx.rm_world = world; gx.rm_nlev = slab_nlev > 0 ? slab_nlev : nlev; gx.rm_t0 = slab_t0; gx.rm_P = g.P; gx.rm_ny = g.ny; }
     const i64 xo = (g.ny == 1) ? 1 : nlev;
     if (!inverse) {
         const double* s0 = src + off;

@@ -17,6 +17,7 @@
 #include "kernels.h"
 #include "vmm.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -135,6 +136,14 @@ struct dotsocp_ctx {
     int device = 0;
     Geo g;
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;  // communication stream (time slabs): transposes and ghost planes overlap with compute
+    std::vector<cudaEvent_t> cev;   // reusable events for the st <-> st2 hand-offs
+    size_t cev_used = 0;
+    cudaEvent_t comm_event()
+    {
+        if (cev_used == cev.size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); cev.push_back(e); }
+        return cev[cev_used++];
+    }
     std::vector<Slab*> slabs;   // local slabs
     std::vector<TRange> part;   // partition of all `world` slabs
     std::vector<i64> pcut;      // mode chunks [pcut[r], pcut[r+1])
@@ -178,6 +187,9 @@ extern "C" void dotsocp_destroy(dotsocp_ctx* c)
 {
     if (!c) return;
     if (c->st) cudaStreamSynchronize(c->st);
+    if (c->st2) cudaStreamSynchronize(c->st2);
+    for (auto e : c->cev) cudaEventDestroy(e);
+    if (c->st2) cudaStreamDestroy(c->st2);
     for (Slab* s : c->slabs) delete s;
     if (c->comm && nccl_api().ok) nccl_api().CommDestroy(c->comm);
     poisson_plan_destroy(c->pp);
@@ -277,8 +289,12 @@ extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, in
         tr.tn1 = (r == world - 1) ? nt : tr.tc1;
         c->part.push_back(tr);
     }
-    for (int r = 0; r <= world; r++) c->pcut.push_back((i64)r * g.P / world);
-    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
+    {   // mode chunks of ceil(P/world) (the last one shorter): cheap owner arithmetic inside the fused-pack DCT kernels
+        const i64 C = (g.P + world - 1) / world;
+        for (int r = 0; r <= world; r++) c->pcut.push_back(std::min(g.P, (i64)r * C));
+    }
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
+        (world > 1 && cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) != cudaSuccess)) {
         dotsocp_destroy(c);
         return set_err(DOTSOCP_ECUDA, "cudaStreamCreate failed");
     }
@@ -320,7 +336,7 @@ static double* sel_weight(Slab* s, int) { return s->weight; }
 
 struct Xfer { ArrSel sel; int k; i64 off, count; int from, to; };
 
-static int do_xfers(dotsocp_ctx* c, const std::vector<Xfer>& xs)
+static int do_xfers(dotsocp_ctx* c, const std::vector<Xfer>& xs, cudaStream_t st)
 {
     if (xs.empty()) return 0;
     const NcclApi& n = nccl_api();
@@ -331,11 +347,11 @@ static int do_xfers(dotsocp_ctx* c, const std::vector<Xfer>& xs)
         Slab* b = c->local(x.to);
         if (a && b) {
             CU(cudaMemcpyAsync(x.sel(b, x.k) + x.off, x.sel(a, x.k) + x.off, (size_t)x.count * sizeof(double),
-                               cudaMemcpyDeviceToDevice, c->st));
+                               cudaMemcpyDeviceToDevice, st));
         } else if (a || b) {
             if (!grouped) { NC(n.GroupStart()); grouped = true; }
-            if (a) NC(n.Send(x.sel(a, x.k) + x.off, (size_t)x.count, NCCL_FLOAT64, x.to, c->comm, c->st));
-            else NC(n.Recv(x.sel(b, x.k) + x.off, (size_t)x.count, NCCL_FLOAT64, x.from, c->comm, c->st));
+            if (a) NC(n.Send(x.sel(a, x.k) + x.off, (size_t)x.count, NCCL_FLOAT64, x.to, c->comm, st));
+            else NC(n.Recv(x.sel(b, x.k) + x.off, (size_t)x.count, NCCL_FLOAT64, x.from, c->comm, st));
         }
     }
     if (grouped) NC(n.GroupEnd());
@@ -344,9 +360,10 @@ static int do_xfers(dotsocp_ctx* c, const std::vector<Xfer>& xs)
 
 // ghost exchanges across every slab boundary (node level T between slab r and r+1)
 enum { GH_PHI_UP = 1, GH_Q_UP = 2, GH_Q_DOWN = 4, GH_ALPHA0_DOWN = 8, GH_BETA_DOWN = 16, GH_W = 32 };
-static int ghosts(dotsocp_ctx* c, int what, int qk, int bk)
+static int ghosts(dotsocp_ctx* c, int what, int qk, int bk, cudaStream_t st = nullptr)
 {
     if (c->world == 1) return 0;
+    if (!st) st = c->st;
     const Geo& g = c->g;
     std::vector<Xfer> xs;
     for (int r = 0; r + 1 < c->world; r++) {
@@ -372,7 +389,7 @@ static int ghosts(dotsocp_ctx* c, int what, int qk, int bk)
             xs.push_back({sel_weight, 0, g.L + g.NBX + (T - 1) * g.PBY, g.PBY, r, r + 1});
         }
     }
-    return do_xfers(c, xs);
+    return do_xfers(c, xs, st);
 }
 
 // Poisson solve: rhs -> phi.  One slab: 5 in-place passes.  Several slabs: (y,x) forward locally, transpose so that
@@ -387,12 +404,81 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
     }
     const NcclApi& n = nccl_api();
     const bool fused_pack = poisson_can_pack(c->pp);
+    // rows [r0, r1) (local level indices of the slab that owns the rows) of the transposed exchange, both directions
+    auto exchange_rows = [&](bool forward, int grp, int ngrp, cudaStream_t st) -> int {
+        bool grouped = false;
+        for (int a = 0; a < c->world; a++)          // a: owner of the time rows
+            for (int b = 0; b < c->world; b++) {    // b: owner of the mode chunk
+                Slab* sa = c->local(a);
+                Slab* sb = c->local(b);
+                if (!sa && !sb) continue;
+                const int nlev = c->part[a].tn1 - c->part[a].tn0;
+                const int r0 = (int)((i64)grp * nlev / ngrp), r1 = (int)((i64)(grp + 1) * nlev / ngrp);
+                if (r1 <= r0) continue;
+                const i64 ch = c->pcut[b + 1] - c->pcut[b];
+                const size_t cnt = (size_t)(r1 - r0) * ch;
+                double* pa = sa ? sa->tsend + (i64)nlev * c->pcut[b] + (i64)r0 * ch : nullptr;
+                double* pb = sb ? sb->trecv + (i64)(c->part[a].tn0 + r0) * ch : nullptr;
+                if (sa && sb) {
+                    CU(cudaMemcpyAsync(forward ? pb : pa, forward ? pa : pb, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                } else {
+                    if (!grouped) { NC(n.GroupStart()); grouped = true; }
+                    if (forward) {
+                        if (sa) NC(n.Send(pa, cnt, NCCL_FLOAT64, b, c->comm, st));
+                        else NC(n.Recv(pb, cnt, NCCL_FLOAT64, a, c->comm, st));
+                    } else {
+                        if (sb) NC(n.Send(pb, cnt, NCCL_FLOAT64, a, c->comm, st));
+                        else NC(n.Recv(pa, cnt, NCCL_FLOAT64, b, c->comm, st));
+                    }
+                }
+            }
+        if (grouped) NC(n.GroupEnd());
+        return 0;
+    };
+    int rc = 0;
+    if (fused_pack) {
+        // pipelined in groups of time levels: the transforms of group i overlap the all-to-all of group i-1 (forward), the
+        // all-to-all of group i+1 overlaps the inverse transforms of group i (backward); rows of a level group are contiguous
+        // in the packed buffers, so no data layout changes.  st = compute stream, st2 = communication stream.
+        int minlev = g.nt;
+        for (auto& tr : c->part) minlev = std::min(minlev, tr.tn1 - tr.tn0);
+        const int ngrp = std::max(1, std::min(4, minlev));
+        c->cev_used = 0;
+        for (int i = 0; i < ngrp; i++) {
+            for (Slab* s : c->slabs) {
+                const int nlev = s->tr.tn1 - s->tr.tn0;
+                const int r0 = (int)((i64)i * nlev / ngrp), r1 = (int)((i64)(i + 1) * nlev / ngrp);
+                if (r1 > r0)
+                    poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0 + r0, r1 - r0, false, c->st, &c->launches, s->tsend, c->world, nlev, r0);
+            }
+            cudaEvent_t e = c->comm_event();
+            CU(cudaEventRecord(e, c->st));
+            CU(cudaStreamWaitEvent(c->st2, e, 0));
+            if ((rc = exchange_rows(true, i, ngrp, c->st2))) return rc;
+        }
+        cudaEvent_t e1 = c->comm_event();
+        CU(cudaEventRecord(e1, c->st2));
+        CU(cudaStreamWaitEvent(c->st, e1, 0));
+        for (Slab* s : c->slabs) poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches);
+        cudaEvent_t e2 = c->comm_event();
+        CU(cudaEventRecord(e2, c->st));
+        CU(cudaStreamWaitEvent(c->st2, e2, 0));
+        for (int i = 0; i < ngrp; i++) {
+            if ((rc = exchange_rows(false, i, ngrp, c->st2))) return rc;
+            cudaEvent_t e = c->comm_event();
+            CU(cudaEventRecord(e, c->st2));
+            CU(cudaStreamWaitEvent(c->st, e, 0));
+            for (Slab* s : c->slabs) {
+                const int nlev = s->tr.tn1 - s->tr.tn0;
+                const int r0 = (int)((i64)i * nlev / ngrp), r1 = (int)((i64)(i + 1) * nlev / ngrp);
+                if (r1 > r0)
+                    poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0 + r0, r1 - r0, true, c->st, &c->launches, s->tsend, c->world, nlev, r0);
+            }
+        }
+        return ghosts(c, GH_PHI_UP, 0, 0);
+    }
     for (Slab* s : c->slabs) {
         const int nlev = s->tr.tn1 - s->tr.tn0;
-        if (fused_pack) {   // the x-forward kernel scatters straight into the send buffer
-            poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0, nlev, false, c->st, &c->launches, s->tsend, c->world);
-            continue;
-        }
         poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0, nlev, false, c->st, &c->launches);
         // pack: block r of the send buffer = rows of this slab x modes of slab r
         for (int r = 0; r < c->world; r++) {
@@ -401,44 +487,11 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
                                  g.P * sizeof(double), ch * sizeof(double), nlev, cudaMemcpyDeviceToDevice, c->st));
         }
     }
-    auto all_to_all = [&](bool forward) -> int {
-        bool grouped = false;
-        for (int a = 0; a < c->world; a++)          // a: owner of the time rows
-            for (int b = 0; b < c->world; b++) {    // b: owner of the mode chunk
-                Slab* sa = c->local(a);
-                Slab* sb = c->local(b);
-                if (!sa && !sb) continue;
-                const int nlev = c->part[a].tn1 - c->part[a].tn0;
-                const i64 ch = c->pcut[b + 1] - c->pcut[b];
-                const size_t cnt = (size_t)nlev * ch;
-                double* pa = sa ? sa->tsend + (i64)nlev * c->pcut[b] : nullptr;
-                double* pb = sb ? sb->trecv + (i64)c->part[a].tn0 * ch : nullptr;
-                if (sa && sb) {
-                    CU(cudaMemcpyAsync(forward ? pb : pa, forward ? pa : pb, cnt * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-                } else {
-                    if (!grouped) { NC(n.GroupStart()); grouped = true; }
-                    if (forward) {
-                        if (sa) NC(n.Send(pa, cnt, NCCL_FLOAT64, b, c->comm, c->st));
-                        else NC(n.Recv(pb, cnt, NCCL_FLOAT64, a, c->comm, c->st));
-                    } else {
-                        if (sb) NC(n.Send(pb, cnt, NCCL_FLOAT64, a, c->comm, c->st));
-                        else NC(n.Recv(pa, cnt, NCCL_FLOAT64, b, c->comm, c->st));
-                    }
-                }
-            }
-        if (grouped) NC(n.GroupEnd());
-        return 0;
-    };
-    int rc = all_to_all(true);
-    if (rc) return rc;
+    if ((rc = exchange_rows(true, 0, 1, c->st))) return rc;
     for (Slab* s : c->slabs) poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches);
-    if ((rc = all_to_all(false))) return rc;
+    if ((rc = exchange_rows(false, 0, 1, c->st))) return rc;
     for (Slab* s : c->slabs) {
         const int nlev = s->tr.tn1 - s->tr.tn0;
-        if (fused_pack) {   // the x-inverse kernel gathers straight from the receive side of the second transpose
-            poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0, nlev, true, c->st, &c->launches, s->tsend, c->world);
-            continue;
-        }
         for (int r = 0; r < c->world; r++) {
             const i64 ch = c->pcut[r + 1] - c->pcut[r];
             CU(cudaMemcpy2DAsync(s->phi + s->tr.tn0 * g.P + c->pcut[r], g.P * sizeof(double), s->tsend + (i64)nlev * c->pcut[r],
@@ -649,11 +702,36 @@ struct Loop {
     int step_phi() { return solve_poisson(c, sc_D2); }
     int step_q(bool acc)
     {
-        for (Slab* s : c->slabs) {
-            launch_qstep(ua(s), c->weighted, acc, c->st);
+        if (c->world == 1) {
+            launch_qstep(ua(c->slabs[0]), c->weighted, acc, c->st);
             c->launches += 1;
+            return 0;
         }
-        return ghosts(c, GH_Q_UP | GH_Q_DOWN | GH_ALPHA0_DOWN, 1 - c->qcur, 0);
+        // time slabs: first the two node levels whose q / alpha_0 the neighbours need, then their exchange on the
+        // communication stream while the interior levels are processed
+        auto part = [&](Slab* s, int t0, int t1) {
+            if (t1 <= t0) return;
+            UpdateArgs a = ua(s);
+            a.tr.tn0 = t0; a.tr.tn1 = t1;
+            launch_qstep(a, c->weighted, acc, c->st);
+            c->launches += 1;
+        };
+        for (Slab* s : c->slabs) {
+            const int t0 = s->tr.tn0, t1 = s->tr.tn1;
+            part(s, t0, t0 + 1);
+            if (t1 - 1 > t0) part(s, t1 - 1, t1);
+        }
+        c->cev_used = 0;
+        cudaEvent_t e = c->comm_event();
+        CU(cudaEventRecord(e, c->st));
+        CU(cudaStreamWaitEvent(c->st2, e, 0));
+        int rc = ghosts(c, GH_Q_UP | GH_Q_DOWN | GH_ALPHA0_DOWN, 1 - c->qcur, 0, c->st2);
+        if (rc) return rc;
+        for (Slab* s : c->slabs) part(s, s->tr.tn0 + 1, s->tr.tn1 - 1);
+        cudaEvent_t e2 = c->comm_event();
+        CU(cudaEventRecord(e2, c->st2));
+        CU(cudaStreamWaitEvent(c->st, e2, 0));
+        return 0;
     }
     void step_mult()
     {
