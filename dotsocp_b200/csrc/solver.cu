@@ -172,6 +172,9 @@ static size_t partial_doubles(const Geo& g)
     return (m > c ? m : c) + 64;
 }
 
+static void* g_comm = nullptr;   // process-wide NCCL communicator (one process per GPU)
+static int g_comm_world = 0, g_comm_rank = -1;
+
 extern "C" int dotsocp_nccl_unique_id(char id128[128])
 {
     if (!id128) return set_err(DOTSOCP_EINVAL, "NULL id buffer");
@@ -191,7 +194,7 @@ extern "C" void dotsocp_destroy(dotsocp_ctx* c)
     for (auto e : c->cev) cudaEventDestroy(e);
     if (c->st2) cudaStreamDestroy(c->st2);
     for (Slab* s : c->slabs) delete s;
-    if (c->comm && nccl_api().ok) nccl_api().CommDestroy(c->comm);
+    // the communicator is process-wide (g_comm) and survives the session so that later sessions can reuse it
     poisson_plan_destroy(c->pp);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
@@ -293,18 +296,35 @@ extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, in
         const i64 C = (g.P + world - 1) / world;
         for (int r = 0; r <= world; r++) c->pcut.push_back(std::min(g.P, (i64)r * C));
     }
+    // the communication stream gets the highest priority so that the NCCL copy kernels are scheduled as soon as SM slots
+    // free up instead of queueing behind the (much larger) compute grids they are meant to overlap with
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
-        (world > 1 && cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) != cudaSuccess)) {
+        (world > 1 && cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_hi) != cudaSuccess)) {
         dotsocp_destroy(c);
         return set_err(DOTSOCP_ECUDA, "cudaStreamCreate failed");
     }
     if (world > 1 && !c->emulate) {
         const NcclApi& n = nccl_api();
         if (!n.ok) { dotsocp_destroy(c); return set_err(DOTSOCP_ENCCL, "NCCL unavailable: %s", n.why); }
-        NcclId id;
-        memcpy(id.internal, nccl_id, 128);
-        int r_ = n.CommInitRank(&c->comm, world, id, rank);
-        if (r_ != 0) { c->comm = nullptr; dotsocp_destroy(c); return set_err(DOTSOCP_ENCCL, "ncclCommInitRank: %s", n.GetErrorString(r_)); }
+        bool zero_id = true;
+        for (int i = 0; i < 128; i++) zero_id = zero_id && nccl_id[i] == 0;
+        if (zero_id) {   // reuse the process-wide communicator of an earlier session (its peer connections are warm)
+            if (!g_comm || g_comm_world != world || g_comm_rank != rank) {
+                dotsocp_destroy(c);
+                return set_err(DOTSOCP_ESTATE, "no reusable communicator for rank %d / world %d", rank, world);
+            }
+        } else {
+            if (g_comm) { n.CommDestroy(g_comm); g_comm = nullptr; }
+            NcclId id;
+            memcpy(id.internal, nccl_id, 128);
+            int r_ = n.CommInitRank(&g_comm, world, id, rank);
+            if (r_ != 0) { g_comm = nullptr; dotsocp_destroy(c); return set_err(DOTSOCP_ENCCL, "ncclCommInitRank: %s", n.GetErrorString(r_)); }
+            g_comm_world = world;
+            g_comm_rank = rank;
+        }
+        c->comm = g_comm;
     }
     if (c->emulate) {
         for (int r = 0; r < world; r++)

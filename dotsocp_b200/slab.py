@@ -72,6 +72,9 @@ def local_sizes(rank, world, nt, nx, ny):
     return {"N": (tn1 - tn0) * P, "L": (tc1 - tc0) * P, "Q": (tc1 - tc0) * P + (tn1 - tn0) * (PBX + PBY)}
 
 
+REUSE_COMM = b"\0" * 128   # pass as nccl_id to re-use the process-wide communicator of an earlier session
+
+
 def nccl_unique_id():
     """128-byte ncclUniqueId (call on rank 0, broadcast to the others, pass to Session(..., nccl_id=...))."""
     buf = C.create_string_buffer(128)

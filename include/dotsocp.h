@@ -129,7 +129,10 @@ int dotsocp_solve_level(const dotsocp_level_opts *opts,
 /* ------------------------------------------------------------------ device-resident session */
 typedef struct dotsocp_ctx dotsocp_ctx;
 /* world > 1 : time-slab partition over `world` ranks (one process per GPU); nccl_id is the 128-byte
- * ncclUniqueId produced by dotsocp_nccl_unique_id() on rank 0 and broadcast by the caller.            */
+ * ncclUniqueId produced by dotsocp_nccl_unique_id() on rank 0 and broadcast by the caller.  The communicator is
+ * process-wide: passing 128 zero bytes re-uses the communicator of an earlier session of this process (same rank/world),
+ * whose peer connections are already established.  world > 1 with nccl_id == NULL runs all slabs in this process on
+ * the current device (single-GPU emulation of the slab code path, used by the tests).                               */
 int  dotsocp_nccl_unique_id(char id128[128]);
 int  dotsocp_create(dotsocp_ctx **ctx, int variant, int nt, int nx, int ny, int rank, int world, const char *nccl_id);
 void dotsocp_destroy(dotsocp_ctx *ctx);
