@@ -864,7 +864,7 @@ __global__ void __launch_bounds__(256) k_thomas(int nt, i64 lines, i64 stride, i
 }
 
 // mode (0,0): phi = IDCT_t( DCT_t(r) ./ (D2 * lam_t) ), lam_t[0] := 1, dense nt x nt transform by one CTA
-__global__ void __launch_bounds__(256) k_tline0(int nt, i64 stride, double D2, const double* __restrict__ lam_t,
+__global__ void __launch_bounds__(1024) k_tline0(int nt, i64 stride, double D2, const double* __restrict__ lam_t,
                                                 const double* __restrict__ cmat, double* __restrict__ a)
 {
     extern __shared__ double sl[];   // [2][nt]
@@ -872,12 +872,18 @@ __global__ void __launch_bounds__(256) k_tline0(int nt, i64 stride, double D2, c
     double* X = sl + nt;
     for (int t = threadIdx.x; t < nt; t += blockDim.x) r[t] = a[(i64)t * stride];
     __syncthreads();
-    for (int k = threadIdx.x; k < nt; k += blockDim.x) {
+    // forward: one warp per coefficient row (coalesced reads of the row, shuffle reduction)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = wid; k < nt; k += nw) {
         double acc = 0.0;
-        for (int t = 0; t < nt; t++) acc += cmat[(i64)k * nt + t] * r[t];
-        double kv = lam_t[k];
-        if (kv == 0.0) kv = 1.0;
-        X[k] = acc / (D2 * kv);
+        for (int t = lane; t < nt; t += 32) acc += cmat[(i64)k * nt + t] * r[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            double kv = lam_t[k];
+            if (kv == 0.0) kv = 1.0;
+            X[k] = acc / (D2 * kv);
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nt; t += blockDim.x) {
@@ -957,7 +963,7 @@ static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, c
     }
     const double ct = (double)(g.nt - 1) * (double)(g.nt - 1);
     if (p0 == 0) {
-        k_tline0<<<1, 256, (size_t)2 * g.nt * sizeof(double), st>>>(g.nt, lines, D2, p->lam_t, p->cmat_t, buf);
+        k_tline0<<<1, 1024, (size_t)2 * g.nt * sizeof(double), st>>>(g.nt, lines, D2, p->lam_t, p->cmat_t, buf);
         if (launches) *launches += 1;
     }
     k_thomas<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, lines, lines, p0, 1.0 / (D2 * ct), gtab, buf);

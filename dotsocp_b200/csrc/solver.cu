@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -113,6 +114,7 @@ struct Slab {
            *weight = nullptr, *beta[2] = {nullptr, nullptr};
     double *c0 = nullptr, *c1 = nullptr, *partial = nullptr, *dsums = nullptr, *hsums = nullptr;
     double *tsend = nullptr, *trecv = nullptr;
+    std::vector<double*> peer_tsend, peer_trecv;   // CUDA-IPC mappings of the other ranks' transpose buffers (NCCL mode)
     Ranges n_own, n_all, q_own, q_all, b_own, b_all;   // element ranges of node / staggered / 10-column arrays
     // acc-ADMM / PALM state (single slab only)
     double* tmpq = nullptr;
@@ -120,6 +122,8 @@ struct Slab {
     double* anc_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     ~Slab()
     {
+        for (double* p : peer_tsend) if (p) cudaIpcCloseMemHandle(p);
+        for (double* p : peer_trecv) if (p) cudaIpcCloseMemHandle(p);
         cudaFree(c0); cudaFree(c1); cudaFree(partial); cudaFree(dsums); cudaFree(tsend); cudaFree(trecv); cudaFree(tmpq);
         for (int i = 0; i < 5; i++) { cudaFree(old_[i]); cudaFree(anc_[i]); }
         if (hsums) cudaFreeHost(hsums);
@@ -144,6 +148,14 @@ struct dotsocp_ctx {
         if (cev_used == cev.size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); cev.push_back(e); }
         return cev[cev_used++];
     }
+    // DOTSOCP_TRACE=1: device time of the phases of the distributed Poisson solve (printed by rank/slab 0 at destroy)
+    bool trace = false;
+    bool ipc = false;           // transposes by peer-to-peer copies (copy engines over NVLink) instead of NCCL send/recv
+    double* barrier_buf = nullptr;
+    std::vector<cudaStream_t> cps;   // one copy stream per peer so that the pushes use several copy engines at once
+    std::vector<cudaEvent_t> tev;
+    double tacc[6] = {0, 0, 0, 0, 0, 0};
+    long tcount = 0, tseen = 0;
     std::vector<Slab*> slabs;   // local slabs
     std::vector<TRange> part;   // partition of all `world` slabs
     std::vector<i64> pcut;      // mode chunks [pcut[r], pcut[r+1])
@@ -191,7 +203,18 @@ extern "C" void dotsocp_destroy(dotsocp_ctx* c)
     if (!c) return;
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->st2) cudaStreamSynchronize(c->st2);
+    if (c->trace && c->tcount > 0 && c->my == 0)
+        fprintf(stderr, "[dotsocp trace] distributed Poisson, mean ms over %ld solves: (y,x) forward %.3f | wait for all-to-all %.3f | "
+                "t-solve %.3f | all-to-all back + (x,y) inverse %.3f | phi ghost %.3f\n", c->tcount, c->tacc[0] / c->tcount,
+                c->tacc[1] / c->tcount, c->tacc[2] / c->tcount, c->tacc[3] / c->tcount, c->tacc[4] / c->tcount);
+    for (auto e : c->tev) cudaEventDestroy(e);
+    if (c->ipc && c->comm && c->barrier_buf) {   // nobody may unmap / free while a peer can still touch the buffers
+        nccl_api().AllReduce(c->barrier_buf, c->barrier_buf, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->st);
+        cudaStreamSynchronize(c->st);
+    }
+    cudaFree(c->barrier_buf);
     for (auto e : c->cev) cudaEventDestroy(e);
+    for (auto cs : c->cps) cudaStreamDestroy(cs);
     if (c->st2) cudaStreamDestroy(c->st2);
     for (Slab* s : c->slabs) delete s;
     // the communicator is process-wide (g_comm) and survives the session so that later sessions can reuse it
@@ -280,6 +303,7 @@ extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, in
     c->weighted = variant == DOTSOCP_VARIANT_WDOT2D;
     c->world = world;
     c->emulate = world > 1 && nccl_id == nullptr;
+    { const char* tr_ = getenv("DOTSOCP_TRACE"); c->trace = tr_ && tr_[0] == '1'; }
     c->my = c->emulate ? 0 : rank;
     c->g = make_geo(nt, nx, ny);
     const Geo& g = c->g;
@@ -332,6 +356,66 @@ extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, in
     } else if ((rc = make_slab(c, rank))) {
         dotsocp_destroy(c);
         return rc;
+    }
+    if (c->comm) {
+        // exchange CUDA-IPC handles of the transpose buffers; any failure just keeps the NCCL send/recv path
+        const char* noipc = getenv("DOTSOCP_NO_IPC");
+        Slab* s = c->slabs[0];
+        cudaIpcMemHandle_t mine[2];
+        bool ok = !(noipc && noipc[0] == '1') && cudaMalloc(&c->barrier_buf, 64) == cudaSuccess &&
+                  cudaIpcGetMemHandle(&mine[0], s->tsend) == cudaSuccess && cudaIpcGetMemHandle(&mine[1], s->trecv) == cudaSuccess;
+        cudaGetLastError();
+        if (c->barrier_buf) cudaMemset(c->barrier_buf, 0, 64);
+        const size_t hb = sizeof(cudaIpcMemHandle_t) * 2;
+        char* dall = nullptr;
+        std::vector<char> hall(hb * world);
+        // every rank takes part in the collective even if its own export failed (flag byte), to stay in lock-step
+        std::vector<char> sendb(hb + 8, 0);
+        if (ok) memcpy(sendb.data(), mine, hb);
+        sendb[hb] = ok ? 1 : 0;
+        std::vector<char> recvb((hb + 8) * world);
+        if (cudaMalloc(&dall, (hb + 8) * (world + 1)) == cudaSuccess) {
+            cudaMemcpyAsync(dall + (hb + 8) * world, sendb.data(), hb + 8, cudaMemcpyHostToDevice, c->st);
+            int r_ = nccl_api().AllGather(dall + (hb + 8) * world, dall, hb + 8, NCCL_INT8, c->comm, c->st);
+            cudaMemcpyAsync(recvb.data(), dall, (hb + 8) * world, cudaMemcpyDeviceToHost, c->st);
+            cudaStreamSynchronize(c->st);
+            cudaFree(dall);
+            bool all_ok = r_ == 0;
+            for (int r = 0; r < world; r++) all_ok = all_ok && recvb[(hb + 8) * r + hb] == 1;
+            if (all_ok) {
+                s->peer_tsend.assign(world, nullptr);
+                s->peer_trecv.assign(world, nullptr);
+                for (int r = 0; r < world && all_ok; r++) {
+                    if (r == rank) continue;
+                    cudaIpcMemHandle_t hh[2];
+                    memcpy(hh, recvb.data() + (hb + 8) * r, hb);
+                    void *p0 = nullptr, *p1 = nullptr;
+                    if (cudaIpcOpenMemHandle(&p0, hh[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                        cudaIpcOpenMemHandle(&p1, hh[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                        all_ok = false;
+                        cudaGetLastError();
+                    }
+                    s->peer_tsend[r] = (double*)p0;
+                    s->peer_trecv[r] = (double*)p1;
+                }
+            }
+            // agree collectively (a rank that failed to open a handle disables the path for everybody)
+            double flag = all_ok ? 0.0 : 1.0, *dflag = c->barrier_buf;
+            if (dflag) {
+                cudaMemcpyAsync(dflag, &flag, sizeof(double), cudaMemcpyHostToDevice, c->st);
+                nccl_api().AllReduce(dflag, dflag, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->st);
+                cudaMemcpyAsync(&flag, dflag, sizeof(double), cudaMemcpyDeviceToHost, c->st);
+                cudaStreamSynchronize(c->st);
+                c->ipc = flag == 0.0;
+            }
+            if (c->ipc) {
+                int plo = 0, phi_ = 0;
+                cudaDeviceGetStreamPriorityRange(&plo, &phi_);
+                c->cps.assign(world, nullptr);
+                for (int r = 0; r < world; r++) cudaStreamCreateWithPriority(&c->cps[r], cudaStreamNonBlocking, phi_);
+            }
+        }
+        cudaGetLastError();
     }
     c->pp = poisson_plan_create(nt, nx, ny);
     cudaError_t e = cudaGetLastError();
@@ -426,7 +510,8 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
     const bool fused_pack = poisson_can_pack(c->pp);
     // rows [r0, r1) (local level indices of the slab that owns the rows) of the transposed exchange, both directions
     auto exchange_rows = [&](bool forward, int grp, int ngrp, cudaStream_t st) -> int {
-        bool grouped = false;
+        bool grouped = false, forked = false;
+        cudaEvent_t e_fork = nullptr;
         for (int a = 0; a < c->world; a++)          // a: owner of the time rows
             for (int b = 0; b < c->world; b++) {    // b: owner of the mode chunk
                 Slab* sa = c->local(a);
@@ -441,6 +526,25 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
                 double* pb = sb ? sb->trecv + (i64)(c->part[a].tn0 + r0) * ch : nullptr;
                 if (sa && sb) {
                     CU(cudaMemcpyAsync(forward ? pb : pa, forward ? pa : pb, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                } else if (c->ipc) {
+                    // push model over CUDA IPC: the owner of the source writes straight into the peer's buffer (copy engines);
+                    // each peer has its own stream, forked from / joined to `st` by events
+                    const int peer = forward ? b : a;
+                    if ((forward && sa) || (!forward && sb)) {
+                        cudaStream_t cs = c->cps[peer];
+                        if (!forked) { e_fork = c->comm_event(); CU(cudaEventRecord(e_fork, st)); forked = true; }
+                        CU(cudaStreamWaitEvent(cs, e_fork, 0));
+                        if (forward) {
+                            double* dst = sa->peer_trecv[b] + (i64)(c->part[a].tn0 + r0) * ch;
+                            CU(cudaMemcpyAsync(dst, pa, cnt * sizeof(double), cudaMemcpyDeviceToDevice, cs));
+                        } else {
+                            double* dst = sb->peer_tsend[a] + (i64)nlev * c->pcut[b] + (i64)r0 * ch;
+                            CU(cudaMemcpyAsync(dst, pb, cnt * sizeof(double), cudaMemcpyDeviceToDevice, cs));
+                        }
+                        cudaEvent_t ej = c->comm_event();
+                        CU(cudaEventRecord(ej, cs));
+                        CU(cudaStreamWaitEvent(st, ej, 0));
+                    }
                 } else {
                     if (!grouped) { NC(n.GroupStart()); grouped = true; }
                     if (forward) {
@@ -453,6 +557,8 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
                 }
             }
         if (grouped) NC(n.GroupEnd());
+        // pushes are complete everywhere once every rank has passed this point of its stream
+        if (c->ipc) NC(n.AllReduce(c->barrier_buf, c->barrier_buf, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, st));
         return 0;
     };
     int rc = 0;
@@ -464,6 +570,19 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
         for (auto& tr : c->part) minlev = std::min(minlev, tr.tn1 - tr.tn0);
         const int ngrp = std::max(1, std::min(4, minlev));
         c->cev_used = 0;
+        auto tmark = [&](int i) {
+            if (!c->trace) return;
+            if (c->tev.size() < 6) { c->tev.resize(6); for (auto& e : c->tev) cudaEventCreate(&e); }
+            cudaEventRecord(c->tev[i], c->st);
+        };
+        if (c->trace && c->tev.size() == 6) {   // fold the previous solve's timings (its events have completed by now or will block briefly)
+            cudaEventSynchronize(c->tev[5]);
+            if (++c->tseen > 3) {   // skip the first solves (NCCL connection set-up, table creation)
+                for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, c->tev[i], c->tev[i + 1]); c->tacc[i] += ms; }
+                c->tcount++;
+            }
+        }
+        tmark(0);
         for (int i = 0; i < ngrp; i++) {
             for (Slab* s : c->slabs) {
                 const int nlev = s->tr.tn1 - s->tr.tn0;
@@ -476,10 +595,13 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
             CU(cudaStreamWaitEvent(c->st2, e, 0));
             if ((rc = exchange_rows(true, i, ngrp, c->st2))) return rc;
         }
+        tmark(1);
         cudaEvent_t e1 = c->comm_event();
         CU(cudaEventRecord(e1, c->st2));
         CU(cudaStreamWaitEvent(c->st, e1, 0));
+        tmark(2);
         for (Slab* s : c->slabs) poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches);
+        tmark(3);
         cudaEvent_t e2 = c->comm_event();
         CU(cudaEventRecord(e2, c->st));
         CU(cudaStreamWaitEvent(c->st2, e2, 0));
@@ -495,7 +617,10 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
                     poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0 + r0, r1 - r0, true, c->st, &c->launches, s->tsend, c->world, nlev, r0);
             }
         }
-        return ghosts(c, GH_PHI_UP, 0, 0);
+        tmark(4);
+        rc = ghosts(c, GH_PHI_UP, 0, 0);
+        tmark(5);
+        return rc;
     }
     for (Slab* s : c->slabs) {
         const int nlev = s->tr.tn1 - s->tr.tn0;

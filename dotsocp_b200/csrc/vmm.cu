@@ -176,6 +176,7 @@ const NcclApi& nccl_api()
         SYM(Send, "ncclSend")
         SYM(Recv, "ncclRecv")
         SYM(AllReduce, "ncclAllReduce")
+        SYM(AllGather, "ncclAllGather")
         SYM(GroupStart, "ncclGroupStart")
         SYM(GroupEnd, "ncclGroupEnd")
         SYM(GetErrorString, "ncclGetErrorString")

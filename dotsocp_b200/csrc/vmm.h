@@ -50,11 +50,12 @@ struct NcclApi {
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 const NcclApi& nccl_api();
-enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_INT8 = 0, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
 
 }  // namespace dsocp
