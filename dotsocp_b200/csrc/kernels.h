@@ -114,9 +114,11 @@ void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cuda
 // time-slab pieces: forward (y then x) / inverse (x then y) transforms of node levels [tn0, tn0+nlev) of the global
 // array (src is only read; src == a allowed), and the t-pass on a transposed [nt][chunk] buffer of modes p0..p0+chunk-1
 void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev, bool inverse, cudaStream_t st, double* launches,
-                double* packed = nullptr, int world = 1, int slab_nlev = 0, int slab_t0 = 0);
+                double* packed = nullptr, int world = 1, int slab_nlev = 0, int slab_t0 = 0, double* const* push_tab = nullptr);
 bool poisson_can_pack(const PoissonPlan* p);   // the x passes can read/write the packed all-to-all buffer themselves
-void poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches);
+// push_tab / tcut (device tables, see Slab::d_bwd): store the solution in the buffers of the owners of the time levels
+void poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches,
+                     double* const* push_tab = nullptr, const int* tcut = nullptr, int world = 1);
 // in-place orthonormal DCT-II (or inverse) along all axes
 void poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches);
 

@@ -310,6 +310,9 @@ struct LineGeom {
     int rm_t0;         // first local level of this launch (the slab is processed in groups of levels)
     i64 rm_P;
     int rm_ny;
+    // direct push (forward x pass only): rm_tab[r] = address of row 0 of this slab's rows inside the t-solve buffer of the
+    // owner of chunk r (peer memory mapped through CUDA IPC, or a local buffer) -- the transform stores its result there
+    double* const* rm_tab;
 };
 
 __device__ __forceinline__ i64 remap_index(const LineGeom& lg, int t_loc, i64 p)
@@ -674,9 +677,17 @@ k_dct_blu16(LineGeom lg, const double* ain, double* aout, const double2* __restr
             if (lg.contiguous) { g = f / n; jj = f - g * n; } else { jj = f / G; g = f - jj * G; }
             if (g < nlines) {
                 const double* src = reinterpret_cast<const double*>(smem + (size_t)(g >> 1) * PADLEN + PAD16(MODE == 0 ? jj : makhoul(jj, n)));
-                if (MODE == 0 && lg.rm_world)   // x-forward of a slab: write straight into the packed all-to-all buffer
-                    aout[remap_index(lg, lg.rm_t0 + blockIdx.y, (i64)jj * lg.rm_ny + (line0 + g))] = src[g & 1];
-                else
+                if (MODE == 0 && lg.rm_world) {   // x-forward of a slab: write straight into the packed all-to-all buffer
+                    const i64 pp = (i64)jj * lg.rm_ny + (line0 + g);
+                    if (lg.rm_tab) {              // ... or straight into the t-solve buffer of the chunk's owner
+                        const unsigned C = (unsigned)((lg.rm_P + lg.rm_world - 1) / lg.rm_world);
+                        const unsigned r = (unsigned)pp / C;
+                        const i64 c0 = (i64)r * C;
+                        const i64 ch = (lg.rm_P - c0) < (i64)C ? (lg.rm_P - c0) : (i64)C;
+                        lg.rm_tab[r][(i64)(lg.rm_t0 + blockIdx.y) * ch + (pp - c0)] = src[g & 1];
+                    } else
+                        aout[remap_index(lg, lg.rm_t0 + blockIdx.y, pp)] = src[g & 1];
+                } else
                     aout[gbase + (i64)g * lg.gstride + (i64)jj * lg.estride] = src[g & 1];
             }
         }
@@ -834,11 +845,30 @@ __global__ void __launch_bounds__(256) k_thomas_table(int nt, int ny, i64 lines,
     }
 }
 
+// PUSH: the solution of time level t is stored in the buffer of the slab that owns the level (obase[owner] = first owned
+// row of this mode chunk there, tcut = first level of every slab) -- peer memory over NVLink -- instead of in place
+template <bool PUSH>
 __global__ void __launch_bounds__(256) k_thomas(int nt, i64 lines, i64 stride, i64 p0, double inv_scale, const double* __restrict__ gtab,
-                                                double* __restrict__ a)
+                                                double* __restrict__ a, double* const* __restrict__ obase, const int* __restrict__ tcut,
+                                                int world)
 {
     const i64 l = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    if (l >= lines || p0 + l == 0) return;      // mode (0,0) is handled by k_tline0
+    if (l >= lines) return;
+    int ow = world - 1, tlo = 0;
+    double* ob = nullptr;
+    if (PUSH) { tlo = tcut[ow]; ob = obase[ow] + l; }
+    auto put = [&](int t, double v) {
+        if (PUSH) {
+            while (t < tlo) { ow--; tlo = tcut[ow]; ob = obase[ow] + l; }
+            ob[(i64)(t - tlo) * lines] = v;
+        } else
+            a[(i64)t * stride + l] = v;
+    };
+    if (p0 + l == 0) {      // mode (0,0) is handled by k_tline0 (in place); only forward its result
+        if (PUSH)
+            for (int t = nt - 1; t >= 0; t--) put(t, a[(i64)t * stride]);
+        return;
+    }
     double d = 0.0;
     int t = 0;
     // forward elimination, 4 time levels per trip so that the loads of a trip are in flight together
@@ -852,15 +882,16 @@ __global__ void __launch_bounds__(256) k_thomas(int nt, i64 lines, i64 stride, i
     for (; t < nt; t++) { d = (a[(i64)t * stride + l] * inv_scale + d) * gtab[(i64)t * stride + l]; a[(i64)t * stride + l] = d; }
     // back substitution
     double x = d;
+    if (PUSH) put(nt - 1, x);
     t = nt - 2;
     for (; t - 3 >= 0; t -= 4) {
         double dd[4], g[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) { dd[u] = a[(i64)(t - u) * stride + l]; g[u] = gtab[(i64)(t - u) * stride + l]; }
 #pragma unroll
-        for (int u = 0; u < 4; u++) { x = dd[u] + g[u] * x; a[(i64)(t - u) * stride + l] = x; }
+        for (int u = 0; u < 4; u++) { x = dd[u] + g[u] * x; put(t - u, x); }
     }
-    for (; t >= 0; t--) { x = a[(i64)t * stride + l] + gtab[(i64)t * stride + l] * x; a[(i64)t * stride + l] = x; }
+    for (; t >= 0; t--) { x = a[(i64)t * stride + l] + gtab[(i64)t * stride + l] * x; put(t, x); }
 }
 
 // mode (0,0): phi = IDCT_t( DCT_t(r) ./ (D2 * lam_t) ), lam_t[0] := 1, dense nt x nt transform by one CTA
@@ -940,7 +971,8 @@ void poisson_plan_destroy(PoissonPlan* p)
 }
 
 // t-solve on a [nt][lines] array (line stride = lines) holding the modes p0 .. p0+lines-1
-static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, cudaStream_t st, double* launches)
+static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, cudaStream_t st, double* launches,
+                    double* const* push_tab = nullptr, const int* tcut = nullptr, int world = 1)
 {
     const Geo& g = p->g;
     if (!p->use_thomas || g.nt < 3) {
@@ -966,7 +998,10 @@ static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, c
         k_tline0<<<1, 1024, (size_t)2 * g.nt * sizeof(double), st>>>(g.nt, lines, D2, p->lam_t, p->cmat_t, buf);
         if (launches) *launches += 1;
     }
-    k_thomas<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, lines, lines, p0, 1.0 / (D2 * ct), gtab, buf);
+    if (push_tab)
+        k_thomas<true><<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, lines, lines, p0, 1.0 / (D2 * ct), gtab, buf, push_tab, tcut, world);
+    else
+        k_thomas<false><<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, lines, lines, p0, 1.0 / (D2 * ct), gtab, buf, nullptr, nullptr, 1);
     if (launches) *launches += 1;
 }
 
@@ -995,7 +1030,7 @@ void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cuda
 
 // ---- pieces of the solve for a time slab (node levels [tn0, tn0+nlev) of the global array) --------------------------------
 void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev, bool inverse, cudaStream_t st, double* launches,
-                double* packed, int world, int slab_nlev, int slab_t0)
+                double* packed, int world, int slab_nlev, int slab_t0, double* const* push_tab)
 {
     // (tn0, nlev) may be a group of levels of a slab that owns slab_nlev levels starting slab_t0 levels before tn0
     // packed != NULL (and the x length uses the register-FFT kernel): the forward x pass writes, and the inverse x pass
@@ -1005,7 +1040,7 @@ void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev,
     const i64 off = (i64)tn0 * g.P;
     LineGeom gy{g.ny, 1, (i64)g.ny, (i64)nlev * g.nx, 0, 1, 0, 0, 0, 0, 0};
     LineGeom gx = (g.ny == 1) ? LineGeom{g.nx, 1, (i64)g.nx, (i64)nlev, 0, 1, 0, 0, 0, 0, 0} : LineGeom{g.nx, (i64)g.ny, 1, (i64)g.ny, g.P, 0, 0, 0, 0, 0, 0};
-    if (packed) { gx.rm_world = world; gx.rm_nlev = slab_nlev > 0 ? slab_nlev : nlev; gx.rm_t0 = slab_t0; gx.rm_P = g.P; gx.rm_ny = g.ny; }
+    if (packed) { gx.rm_world = world; gx.rm_nlev = slab_nlev > 0 ? slab_nlev : nlev; gx.rm_t0 = slab_t0; gx.rm_P = g.P; gx.rm_ny = g.ny; gx.rm_tab = inverse ? nullptr : push_tab; }
     const i64 xo = (g.ny == 1) ? 1 : nlev;
     if (!inverse) {
         const double* s0 = src + off;
@@ -1020,9 +1055,11 @@ void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev,
 }
 bool poisson_can_pack(const PoissonPlan* p) { return p->g.ny > 1 && !p->px->dense && p->px->log2m >= 8 && p->px->log2m <= 12; }
 // t-pass (DCT_t, ./kernel, IDCT_t) on a [nt][chunk] array holding the (x,y) modes p0 .. p0+chunk-1
-void poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches)
+void poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches,
+                     double* const* push_tab, const int* tcut, int world)
 {
-    t_solve(p, buf, chunk, p0, D2, st, launches);
+    // push_tab != NULL needs the Thomas solve (the transform-based t pass works in place only)
+    t_solve(p, buf, chunk, p0, D2, st, launches, p->use_thomas && p->g.nt >= 3 ? push_tab : nullptr, tcut, world);
 }
 
 void poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches)

@@ -115,6 +115,10 @@ struct Slab {
     double *c0 = nullptr, *c1 = nullptr, *partial = nullptr, *dsums = nullptr, *hsums = nullptr;
     double *tsend = nullptr, *trecv = nullptr;
     std::vector<double*> peer_tsend, peer_trecv;   // CUDA-IPC mappings of the other ranks' transpose buffers (NCCL mode)
+    // direct exchange (kernels store into the destination slab's buffer): device tables of `world` pointers
+    //   d_fwd[b] = row tn0 of the t-solve buffer (trecv) of slab b   -- written by this slab's forward x pass
+    //   d_bwd[a] = block of this slab's mode chunk in the packed buffer (tsend) of slab a   -- written by this slab's t-solve
+    double **d_fwd = nullptr, **d_bwd = nullptr;
     Ranges n_own, n_all, q_own, q_all, b_own, b_all;   // element ranges of node / staggered / 10-column arrays
     // acc-ADMM / PALM state (single slab only)
     double* tmpq = nullptr;
@@ -124,7 +128,7 @@ struct Slab {
     {
         for (double* p : peer_tsend) if (p) cudaIpcCloseMemHandle(p);
         for (double* p : peer_trecv) if (p) cudaIpcCloseMemHandle(p);
-        cudaFree(c0); cudaFree(c1); cudaFree(partial); cudaFree(dsums); cudaFree(tsend); cudaFree(trecv); cudaFree(tmpq);
+        cudaFree(c0); cudaFree(c1); cudaFree(partial); cudaFree(dsums); cudaFree(tsend); cudaFree(trecv); cudaFree(tmpq); cudaFree(d_fwd); cudaFree(d_bwd);
         for (int i = 0; i < 5; i++) { cudaFree(old_[i]); cudaFree(anc_[i]); }
         if (hsums) cudaFreeHost(hsums);
     }
@@ -151,6 +155,8 @@ struct dotsocp_ctx {
     // DOTSOCP_TRACE=1: device time of the phases of the distributed Poisson solve (printed by rank/slab 0 at destroy)
     bool trace = false;
     bool ipc = false;           // transposes by peer-to-peer copies (copy engines over NVLink) instead of NCCL send/recv
+    bool direct = false;        // ... or by the transform / t-solve kernels storing straight into the destination slab's buffer
+    int* d_tcut = nullptr;      // first node level of every slab (world + 1 entries), device copy
     double* barrier_buf = nullptr;
     std::vector<cudaStream_t> cps;   // one copy stream per peer so that the pushes use several copy engines at once
     std::vector<cudaEvent_t> tev;
@@ -213,6 +219,7 @@ extern "C" void dotsocp_destroy(dotsocp_ctx* c)
         cudaStreamSynchronize(c->st);
     }
     cudaFree(c->barrier_buf);
+    cudaFree(c->d_tcut);
     for (auto e : c->cev) cudaEventDestroy(e);
     for (auto cs : c->cps) cudaStreamDestroy(cs);
     if (c->st2) cudaStreamDestroy(c->st2);
@@ -417,6 +424,35 @@ extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, in
         }
         cudaGetLastError();
     }
+    if (world > 1 && (c->ipc || !c->comm)) {
+        // DOTSOCP_XCHG=direct: the kernels store straight into the destination slab's buffers instead of the copy-engine
+        // pushes.  Off by default: on 8 B200s the t-solve of every GPU then writes to the SAME peer at the same time (the owner
+        // of the current time level), and the 32-byte runs of the x pass cost more than the copies they replace
+        // (Poisson solve 8.99 ms against 6.59 ms at 1024x1024x512, profiles/README.md).
+        const char* xm = getenv("DOTSOCP_XCHG");
+        c->direct = xm && strcmp(xm, "direct") == 0;
+        if (c->direct) {
+            std::vector<int> tc(world + 1);
+            for (int r = 0; r < world; r++) tc[r] = c->part[r].tn0;
+            tc[world] = c->part[world - 1].tn1;
+            CU(cudaMalloc(&c->d_tcut, (world + 1) * sizeof(int)));
+            CU(cudaMemcpy(c->d_tcut, tc.data(), (world + 1) * sizeof(int), cudaMemcpyHostToDevice));
+            for (Slab* s : c->slabs) {
+                std::vector<double*> fwd(world), bwd(world);
+                for (int r = 0; r < world; r++) {
+                    Slab* o = c->local(r);
+                    double* o_trecv = o ? o->trecv : s->peer_trecv[r];
+                    double* o_tsend = o ? o->tsend : s->peer_tsend[r];
+                    fwd[r] = o_trecv + (i64)s->tr.tn0 * (c->pcut[r + 1] - c->pcut[r]);
+                    bwd[r] = o_tsend + (i64)(c->part[r].tn1 - c->part[r].tn0) * c->pcut[s->id];
+                }
+                CU(cudaMalloc(&s->d_fwd, world * sizeof(double*)));
+                CU(cudaMalloc(&s->d_bwd, world * sizeof(double*)));
+                CU(cudaMemcpy(s->d_fwd, fwd.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(s->d_bwd, bwd.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
+            }
+        }
+    }
     c->pp = poisson_plan_create(nt, nx, ny);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -581,6 +617,42 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
                 for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, c->tev[i], c->tev[i + 1]); c->tacc[i] += ms; }
                 c->tcount++;
             }
+        }
+        if (c->direct) {
+            // the kernels do the exchange: the forward x pass stores every result in the t-solve buffer of the owner of its
+            // mode chunk, the t-solve stores every level in the packed buffer of the owner of the level (peer memory over
+            // NVLink, plain local memory when one process emulates the slabs); the only communication calls left are the
+            // two barriers that order "everybody has written" before "anybody reads".
+            auto barrier = [&]() -> int {
+                if (c->comm) NC(n.AllReduce(c->barrier_buf, c->barrier_buf, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->st));
+                return 0;
+            };
+            tmark(0);
+            for (int i = 0; i < ngrp; i++)
+                for (Slab* s : c->slabs) {
+                    const int nlev = s->tr.tn1 - s->tr.tn0;
+                    const int r0 = (int)((i64)i * nlev / ngrp), r1 = (int)((i64)(i + 1) * nlev / ngrp);
+                    if (r1 > r0)
+                        poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0 + r0, r1 - r0, false, c->st, &c->launches, s->tsend, c->world, nlev, r0, s->d_fwd);
+                }
+            tmark(1);
+            if ((rc = barrier())) return rc;
+            tmark(2);
+            for (Slab* s : c->slabs)
+                poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches, s->d_bwd, c->d_tcut, c->world);
+            tmark(3);
+            if ((rc = barrier())) return rc;
+            for (int i = 0; i < ngrp; i++)
+                for (Slab* s : c->slabs) {
+                    const int nlev = s->tr.tn1 - s->tr.tn0;
+                    const int r0 = (int)((i64)i * nlev / ngrp), r1 = (int)((i64)(i + 1) * nlev / ngrp);
+                    if (r1 > r0)
+                        poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0 + r0, r1 - r0, true, c->st, &c->launches, s->tsend, c->world, nlev, r0);
+                }
+            tmark(4);
+            rc = ghosts(c, GH_PHI_UP, 0, 0);
+            tmark(5);
+            return rc;
         }
         tmark(0);
         for (int i = 0; i < ngrp; i++) {

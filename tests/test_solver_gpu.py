@@ -208,10 +208,14 @@ def test_time_slab_partition_emulated_on_one_gpu(gpu, world, variant):
         assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), name
 
 
+@pytest.mark.parametrize("xchg", ["copy", "direct"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_time_slabs_with_fused_transpose_pack(gpu, world):
-    """nx = 129 uses the register-FFT DCT kernel, whose x passes write/read the packed all-to-all buffer directly."""
+def test_time_slabs_with_fused_transpose_pack(gpu, world, xchg, monkeypatch):
+    """nx = 129 uses the register-FFT DCT kernel, whose x passes write/read the packed all-to-all buffer directly.
+    xchg = direct: the x pass and the t-solve store straight into the destination slab's buffers (DOTSOCP_XCHG, read when
+    the session is created)."""
     import dotsocp_b200 as dp
+    monkeypatch.setenv("DOTSOCP_XCHG", xchg)
     from dotsocp_b200 import driver, solver
     nt, nx, ny = 9, 129, 12
     rng = np.random.default_rng(5)
