@@ -1,0 +1,180 @@
+// hostcopy.cu -- see hostcopy.h
+#include "hostcopy.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+
+namespace dsocp {
+
+// ------------------------------------------------------------------------------------------------ worker pool
+WorkerPool::WorkerPool(int nthreads)
+{
+    for (int i = 1; i < nthreads; i++) threads_.emplace_back([this] { worker(); });
+}
+
+WorkerPool::~WorkerPool()
+{
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+}
+
+void WorkerPool::worker()
+{
+    unsigned long seen = 0;
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+        cv_.wait(lk, [&] { return stop_ || (gen_ != seen && fn_ != nullptr); });
+        if (stop_) return;
+        seen = gen_;
+        while (fn_ && next_ < n_) {
+            const int i = next_++;
+            const std::function<void(int)>* fn = fn_;
+            lk.unlock();
+            (*fn)(i);
+            lk.lock();
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+}
+
+void WorkerPool::parallel_for(int n, const std::function<void(int)>& fn)
+{
+    if (n <= 0) return;
+    if (n == 1 || threads_.empty()) {
+        for (int i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::unique_lock<std::mutex> lk(mu_);
+    fn_ = &fn;
+    n_ = n;
+    next_ = 0;
+    pending_ = n;
+    gen_++;
+    cv_.notify_all();
+    while (next_ < n_) {
+        const int i = next_++;
+        lk.unlock();
+        fn(i);
+        lk.lock();
+        --pending_;
+    }
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ staged copies
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const int v = atoi(e);
+    return v > 0 ? v : dflt;
+}
+
+HostCopier::HostCopier()
+{
+    // threads: the host cores divided among the ranks that share the node (torchrun exports LOCAL_WORLD_SIZE)
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int lws = env_int("LOCAL_WORLD_SIZE", 1);
+    const int nthr = env_int("DOTSOCP_COPY_THREADS", std::min(8, std::max(2, hw / lws)));
+    chunk_ = (size_t)env_int("DOTSOCP_COPY_CHUNK_MB", 32) << 20;
+    pool_ = new WorkerPool(nthr);
+    ok_ = true;
+    for (int b = 0; b < NBUF; b++) {
+        if (cudaHostAlloc((void**)&pinned_[b], chunk_, cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_[b], cudaEventDisableTiming) != cudaSuccess) {
+            ok_ = false;
+            cudaGetLastError();
+            break;
+        }
+    }
+}
+
+HostCopier::~HostCopier()
+{
+    for (int b = 0; b < NBUF; b++) {
+        if (pinned_[b]) cudaFreeHost(pinned_[b]);
+        if (ev_[b]) cudaEventDestroy(ev_[b]);
+    }
+    delete pool_;
+}
+
+HostCopier* HostCopier::get()
+{
+    // deliberately never destroyed: at process exit the CUDA context may already be gone
+    static HostCopier* inst = new HostCopier();
+    return inst;
+}
+
+void HostCopier::par_memcpy(char* dst, const char* src, size_t bytes)
+{
+    const int T = pool_->size();
+    const size_t piece = ((bytes + T - 1) / T + 4095) & ~(size_t)4095;
+    const int n = (int)((bytes + piece - 1) / piece);
+    pool_->parallel_for(n, [&](int i) {
+        const size_t o = (size_t)i * piece;
+        memcpy(dst + o, src + o, std::min(piece, bytes - o));
+    });
+}
+
+int HostCopier::h2d(void* dev, const void* host, size_t bytes, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(mu_);
+    char* d = (char*)dev;
+    const char* h = (const char*)host;
+    for (size_t off = 0; off < bytes; off += chunk_) {
+        const size_t len = std::min(chunk_, bytes - off);
+        const int b = cursor_;
+        cursor_ = (cursor_ + 1) % NBUF;
+        cudaError_t e;
+        if (busy_[b] && (e = cudaEventSynchronize(ev_[b])) != cudaSuccess) return (int)e;
+        par_memcpy(pinned_[b], h + off, len);
+        if ((e = cudaMemcpyAsync(d + off, pinned_[b], len, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaEventRecord(ev_[b], st)) != cudaSuccess) return (int)e;
+        busy_[b] = true;
+    }
+    return 0;
+}
+
+int HostCopier::d2h(void* host, const void* dev, size_t bytes, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(mu_);
+    char* h = (char*)host;
+    const char* d = (const char*)dev;
+    struct Item { int b; size_t off, len; };
+    std::deque<Item> fifo;
+    auto drain_one = [&]() -> int {
+        const Item it = fifo.front();
+        fifo.pop_front();
+        cudaError_t e = cudaEventSynchronize(ev_[it.b]);
+        if (e != cudaSuccess) return (int)e;
+        par_memcpy(h + it.off, pinned_[it.b], it.len);
+        busy_[it.b] = false;
+        return 0;
+    };
+    for (size_t off = 0; off < bytes; off += chunk_) {
+        const size_t len = std::min(chunk_, bytes - off);
+        const int b = cursor_;
+        cursor_ = (cursor_ + 1) % NBUF;
+        cudaError_t e;
+        if (busy_[b]) {   // still owned by an earlier h2d (its event), or by this call's pipeline (then it is the oldest item)
+            if (!fifo.empty() && fifo.front().b == b) { int rc = drain_one(); if (rc) return rc; }
+            else if ((e = cudaEventSynchronize(ev_[b])) != cudaSuccess) return (int)e;
+        }
+        if ((e = cudaMemcpyAsync(pinned_[b], d + off, len, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaEventRecord(ev_[b], st)) != cudaSuccess) return (int)e;
+        busy_[b] = true;
+        fifo.push_back({b, off, len});
+        if ((int)fifo.size() >= NBUF - 1) { int rc = drain_one(); if (rc) return rc; }
+    }
+    while (!fifo.empty()) { int rc = drain_one(); if (rc) return rc; }
+    return 0;
+}
+
+}  // namespace dsocp

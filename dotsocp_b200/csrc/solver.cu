@@ -16,8 +16,10 @@
 #include "errs.h"
 #include "kernels.h"
 #include "vmm.h"
+#include "hostcopy.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -737,6 +739,25 @@ struct HostMap {
     i64 col(int j, i64 t) const { return local ? (i64)j * (tr.tc1 - tr.tc0) * g->P + (t - tr.tc0) * g->P : (i64)j * g->L + t * g->P; }
 };
 
+// host <-> device transfer of one contiguous piece: staged through the pinned ring (hostcopy.h) unless the piece is small or
+// DOTSOCP_HOSTCOPY=plain asks for the driver's own pageable path (A/B measurements)
+static int xfer(dotsocp_ctx* c, double* dev, double* host, size_t n, bool up)
+{
+    static const bool plain = [] { const char* e = getenv("DOTSOCP_HOSTCOPY"); return e && strcmp(e, "plain") == 0; }();
+    const size_t bytes = n * sizeof(double);
+    if (!plain && bytes >= ((size_t)4 << 20)) {
+        HostCopier* hc = HostCopier::get();
+        if (hc->ok()) {
+            const int e = up ? hc->h2d(dev, host, bytes, c->st) : hc->d2h(host, dev, bytes, c->st);
+            if (e) return set_err(DOTSOCP_ECUDA, "staged %s copy failed: %s", up ? "host-to-device" : "device-to-host", cudaGetErrorString((cudaError_t)e));
+            return 0;
+        }
+    }
+    if (up) CU(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->st));
+    else CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->st));
+    return 0;
+}
+
 static int copy_stag(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev, double* host, bool up)
 {
     const Geo& g = c->g;
@@ -746,8 +767,8 @@ static int copy_stag(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev, do
                                           {g.L + g.NBX + tr.tn0 * g.PBY, hm.by(tr.tn0), (i64)(tr.tn1 - tr.tn0) * g.PBY}};
     for (auto& p : parts) {
         if (p.n <= 0) continue;
-        if (up) CU(cudaMemcpyAsync(dev + p.d, host + p.h, p.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-        else CU(cudaMemcpyAsync(host + p.h, dev + p.d, p.n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        int rc = xfer(c, dev + p.d, host + p.h, (size_t)p.n, up);
+        if (rc) return rc;
     }
     return 0;
 }
@@ -761,8 +782,8 @@ static int copy_cols(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev10, 
     // 1-D variant: 6 columns at the boundary (c0..c4 -> 0..4, c5 -> 9; columns 5..8 are structural zeros on the device)
     for (int jh = 0; jh < ncol; jh++) {
         const int j = (c->one_d && jh == 5) ? 9 : jh;
-        if (up) CU(cudaMemcpyAsync(dev10 + j * g.L + tr.tc0 * g.P, host + hm.col(jh, tr.tc0), n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-        else CU(cudaMemcpyAsync(host + hm.col(jh, tr.tc0), dev10 + j * g.L + tr.tc0 * g.P, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        int rc = xfer(c, dev10 + j * g.L + tr.tc0 * g.P, host + hm.col(jh, tr.tc0), (size_t)n, up);
+        if (rc) return rc;
     }
     if (up && c->one_d)
         for (int j = 5; j < 9; j++)
@@ -783,14 +804,20 @@ extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q
         const TRange& tr = s->tr;
         // c is -rho0/ht on the first time level, +rho1/ht on the last and zero in between (initialize.m:41-44); only the
         // two planes are kept on the device.
-        for (i64 t = tr.tn0; t < tr.tn1; t++) {
-            if (t == 0 || t == g.nt - 1) continue;
-            const double* row = cvec + hm.nodes(t);
-            for (i64 i = 0; i < g.P; i++)
-                if (row[i] != 0.0) return set_err(DOTSOCP_EINVAL, "model.c has a non-zero interior entry (t=%lld): unsupported", (long long)t);
+        {
+            std::atomic<long long> bad(-1);
+            const int nrows = (int)(tr.tn1 - tr.tn0);
+            HostCopier::get()->pool().parallel_for(nrows, [&](int k) {
+                const i64 t = tr.tn0 + k;
+                if (t == 0 || t == g.nt - 1 || bad.load(std::memory_order_relaxed) >= 0) return;
+                const double* row = cvec + hm.nodes(t);
+                for (i64 i = 0; i < g.P; i++)
+                    if (row[i] != 0.0) { bad.store((long long)t); return; }
+            });
+            if (bad.load() >= 0) return set_err(DOTSOCP_EINVAL, "model.c has a non-zero interior entry (t=%lld): unsupported", bad.load());
         }
-        CU(cudaMemcpyAsync(s->phi + tr.tn0 * g.P, phi + hm.nodes(tr.tn0), (size_t)(tr.tn1 - tr.tn0) * g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
         int rc;
+        if ((rc = xfer(c, s->phi + tr.tn0 * g.P, const_cast<double*>(phi) + hm.nodes(tr.tn0), (size_t)(tr.tn1 - tr.tn0) * g.P, true))) return rc;
         if ((rc = copy_stag(c, s, hm, s->q[0], const_cast<double*>(q), true))) return rc;
         if ((rc = copy_stag(c, s, hm, s->alpha, const_cast<double*>(alpha), true))) return rc;
         if (c->weighted && (rc = copy_stag(c, s, hm, s->weight, const_cast<double*>(weight), true))) return rc;
@@ -817,7 +844,7 @@ extern "C" int dotsocp_download(dotsocp_ctx* c, double* phi, double* q, double* 
         HostMap hm{c->world > 1 && !c->emulate, &g, s->tr};
         const TRange& tr = s->tr;
         int rc;
-        if (phi) CU(cudaMemcpyAsync(phi + hm.nodes(tr.tn0), s->phi + tr.tn0 * g.P, (size_t)(tr.tn1 - tr.tn0) * g.P * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        if (phi && (rc = xfer(c, s->phi + tr.tn0 * g.P, phi + hm.nodes(tr.tn0), (size_t)(tr.tn1 - tr.tn0) * g.P, false))) return rc;
         if (q && (rc = copy_stag(c, s, hm, s->q[c->qcur], q, false))) return rc;
         if (alpha && (rc = copy_stag(c, s, hm, s->alpha, alpha, false))) return rc;
         if (beta && (rc = copy_cols(c, s, hm, s->beta[c->bcur], beta, false))) return rc;

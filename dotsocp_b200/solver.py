@@ -126,12 +126,21 @@ class Session:
         w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
         check(lib().dotsocp_upload(self._h, *[ptr(a) for a in arrs], ptr(w)))
 
-    def download(self):
-        phi = np.empty(self.N)
-        q = np.empty(self.Q)
-        alpha = np.empty(self.Q)
-        z = np.empty((self.L, self.ncol), order="F")
-        beta = np.empty((self.L, self.ncol), order="F")
+    def download(self, out=None):
+        """out = (phi, q, z, alpha, beta): fill these float64 arrays IN PLACE (the convention of the reference's MEX
+        kernels and of dotsocp_solve_level); default: fresh arrays."""
+        if out is not None:
+            phi, q, z, alpha, beta = out
+            for a, n in ((phi, self.N), (q, self.Q), (alpha, self.Q)):
+                assert a.dtype == np.float64 and a.size == n and a.flags.c_contiguous and a.flags.writeable
+            for a in (z, beta):
+                assert a.dtype == np.float64 and a.shape == (self.L, self.ncol) and a.flags.f_contiguous and a.flags.writeable
+        else:
+            phi = np.empty(self.N)
+            q = np.empty(self.Q)
+            alpha = np.empty(self.Q)
+            z = np.empty((self.L, self.ncol), order="F")
+            beta = np.empty((self.L, self.ncol), order="F")
         check(lib().dotsocp_download(self._h, ptr(phi), ptr(q), ptr(z), ptr(alpha), ptr(beta)))
         return phi, q, z, alpha, beta
 
