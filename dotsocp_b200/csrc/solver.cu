@@ -745,7 +745,7 @@ static int xfer(dotsocp_ctx* c, double* dev, double* host, size_t n, bool up)
 {
     static const bool plain = [] { const char* e = getenv("DOTSOCP_HOSTCOPY"); return e && strcmp(e, "plain") == 0; }();
     const size_t bytes = n * sizeof(double);
-    if (!plain && bytes >= ((size_t)4 << 20)) {
+    if (!plain && bytes >= ((size_t)1 << 20)) {
         HostCopier* hc = HostCopier::get();
         if (hc->ok()) {
             const int e = up ? hc->h2d(dev, host, bytes, c->st) : hc->d2h(host, dev, bytes, c->st);
