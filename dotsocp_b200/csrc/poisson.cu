@@ -158,7 +158,9 @@ static DctPlan* dct_plan_create(int n)
         for (int pos = 0; pos < M; pos++) {
             const int m1 = pos / TP, r = pos % TP, m2 = r / Q2, m3 = r % Q2;
             const int f = m1 + 16 * m2 + 256 * m3;
-            b16[pos] = make_double2((double)(br[f] / M), (double)(bi[f] / M));
+            // thread j multiplies its registers e = 0..15 (positions 16j + e): stored as [e][j] so that a warp reads one
+            // contiguous 512-byte run per e instead of 32 different cache lines
+            b16[(size_t)(pos % 16) * TP + pos / 16] = make_double2((double)(br[f] / M), (double)(bi[f] / M));
         }
         p->bhat16 = to_device(b16);
     }
@@ -313,6 +315,7 @@ struct LineGeom {
     // direct push (forward x pass only): rm_tab[r] = address of row 0 of this slab's rows inside the t-solve buffer of the
     // owner of chunk r (peer memory mapped through CUDA IPC, or a local buffer) -- the transform stores its result there
     double* const* rm_tab;
+    unsigned n_inv;    // floor(2^32 / n) + 1: f / n == __umulhi(f, n_inv) for f < 2^32 / n (set by the launcher)
 };
 
 __device__ __forceinline__ i64 remap_index(const LineGeom& lg, int t_loc, i64 p)
@@ -502,7 +505,7 @@ __device__ __forceinline__ void conv16(double2 (&v)[16], int j, int pair, double
     F::load3(s, j, v);
     F::fwd3(v);
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = c_mul(v[e], __ldg(&bhat16[16 * j + e]));
+    for (int e = 0; e < 16; e++) v[e] = c_mul(v[e], __ldg(&bhat16[e * F::TP + j]));
     F::inv3(v);
     F::store3(s, j, v);
     __syncthreads();
@@ -515,7 +518,7 @@ __device__ __forceinline__ void conv16(double2 (&v)[16], int j, int pair, double
 #undef __syncthreads
 }
 
-template <int LOG2M, int PAIRS, int MODE>
+template <int LOG2M, int PAIRS, int MODE, bool CONTIG>
 __global__ void __launch_bounds__((1 << LOG2M) / 16 * PAIRS, (LOG2M >= 12 ? 1 : 2))
 k_dct_blu16(LineGeom lg, const double* ain, double* aout, const double2* __restrict__ w, const double2* __restrict__ bhat16,
             const double2* __restrict__ tw, const double2* __restrict__ pw, const double2* __restrict__ ipw, ScaleArgs sa)
@@ -533,32 +536,38 @@ k_dct_blu16(LineGeom lg, const double* ain, double* aout, const double2* __restr
     const int nlines = (int)((lg.inner - line0) < (i64)G ? (lg.inner - line0) : (i64)G);
 
     // ---- stage in ---------------------------------------------------------------------------------------------------
+    // element f of the CTA's G x n block: CONTIG (lines contiguous, gstride == n): f = g*n + jj is also the global offset;
+    // otherwise (lines strided, G adjacent lines contiguous, gstride == 1): f = jj*G + g.  All offsets relative to the
+    // CTA's first element fit 32 bits (N < 2^31 is checked by the launcher).
+    const double* __restrict__ in_b = ain + gbase;
+    double* __restrict__ out_b = aout + gbase;
+    const unsigned es = (unsigned)lg.estride;
+    const unsigned total = (unsigned)(G * n);
     {
         // all global loads of a thread are issued before the first shared store (G*n/NTHR <= 2*(M/2+1)*PAIRS/NTHR = 16.x)
         constexpr int NLD = (G * (M / 2 + 1) + NTHR - 1) / NTHR;
-        const int total = G * n;
         double vals[NLD];
 #pragma unroll
         for (int u = 0; u < NLD; u++) {
-            const int f = tid + u * NTHR;
-            int g, jj;
-            if (lg.contiguous) { g = f / n; jj = f - g * n; } else { jj = f / G; g = f - jj * G; }
-            if (f < total && g < nlines) {
+            const unsigned f = tid + u * NTHR;
+            unsigned g, jj;
+            if (CONTIG) { g = __umulhi(f, lg.n_inv); jj = f - g * n; } else { jj = f / G; g = f % G; }
+            if (f < total && (int)g < nlines) {
                 if (MODE == 1 && lg.rm_world)   // x-inverse of a slab: read straight from the packed all-to-all buffer
                     vals[u] = ain[remap_index(lg, lg.rm_t0 + blockIdx.y, (i64)jj * lg.rm_ny + (line0 + g))];
                 else
-                    vals[u] = ain[gbase + (i64)g * lg.gstride + (i64)jj * lg.estride];
+                    vals[u] = in_b[CONTIG ? f : jj * es + g];
             } else {
                 vals[u] = 0.0;
             }
         }
 #pragma unroll
         for (int u = 0; u < NLD; u++) {
-            const int f = tid + u * NTHR;
+            const unsigned f = tid + u * NTHR;
             if (f < total) {
-                int g, jj;
-                if (lg.contiguous) { g = f / n; jj = f - g * n; } else { jj = f / G; g = f - jj * G; }
-                double* dst = reinterpret_cast<double*>(smem + (size_t)(g >> 1) * PADLEN + PAD16(MODE == 1 ? jj : makhoul(jj, n)));
+                unsigned g, jj;
+                if (CONTIG) { g = __umulhi(f, lg.n_inv); jj = f - g * n; } else { jj = f / G; g = f % G; }
+                double* dst = reinterpret_cast<double*>(smem + (g >> 1) * PADLEN + PAD16(MODE == 1 ? (int)jj : makhoul((int)jj, n)));
                 dst[g & 1] = vals[u];
             }
         }
@@ -671,12 +680,11 @@ k_dct_blu16(LineGeom lg, const double* ain, double* aout, const double2* __restr
     __syncthreads();
     // ---- stage out --------------------------------------------------------------------------------------------------
     {
-        const int total = G * n;
-        for (int f = tid; f < total; f += NTHR) {
-            int g, jj;
-            if (lg.contiguous) { g = f / n; jj = f - g * n; } else { jj = f / G; g = f - jj * G; }
-            if (g < nlines) {
-                const double* src = reinterpret_cast<const double*>(smem + (size_t)(g >> 1) * PADLEN + PAD16(MODE == 0 ? jj : makhoul(jj, n)));
+        for (unsigned f = tid; f < total; f += NTHR) {
+            unsigned g, jj;
+            if (CONTIG) { g = __umulhi(f, lg.n_inv); jj = f - g * n; } else { jj = f / G; g = f % G; }
+            if ((int)g < nlines) {
+                const double* src = reinterpret_cast<const double*>(smem + (g >> 1) * PADLEN + PAD16(MODE == 0 ? (int)jj : makhoul((int)jj, n)));
                 if (MODE == 0 && lg.rm_world) {   // x-forward of a slab: write straight into the packed all-to-all buffer
                     const i64 pp = (i64)jj * lg.rm_ny + (line0 + g);
                     if (lg.rm_tab) {              // ... or straight into the t-solve buffer of the chunk's owner
@@ -688,7 +696,7 @@ k_dct_blu16(LineGeom lg, const double* ain, double* aout, const double2* __restr
                     } else
                         aout[remap_index(lg, lg.rm_t0 + blockIdx.y, pp)] = src[g & 1];
                 } else
-                    aout[gbase + (i64)g * lg.gstride + (i64)jj * lg.estride] = src[g & 1];
+                    out_b[CONTIG ? f : jj * es + g] = src[g & 1];
             }
         }
     }
@@ -701,17 +709,27 @@ static void launch_blu16(const DctPlan* p, const LineGeom& lg, i64 outer, const 
     constexpr int M = 1 << LOG2M, TP = M / 16, G = 2 * PAIRS, NTHR = TP * PAIRS;
     const size_t smem = (size_t)PAIRS * (M + M / 16 + 1) * sizeof(double2);
     dim3 grid((unsigned)((lg.inner + G - 1) / G), (unsigned)outer);
-    static bool attr_set[3] = {false, false, false};
-#define BLU(MODE)                                                                                                  \
-    {                                                                                                              \
-        if (!attr_set[MODE]) {                                                                                     \
-            cudaFuncSetAttribute(k_dct_blu16<LOG2M, PAIRS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                 (int)smem);                                                                       \
-            attr_set[MODE] = true;                                                                                 \
-        }                                                                                                          \
-        k_dct_blu16<LOG2M, PAIRS, MODE><<<grid, NTHR, smem, st>>>(lg, ain, a, p->w, p->bhat16, p->tw, p->pw, p->ipw, sa); \
+    static bool attr_set[3][2] = {{false, false}, {false, false}, {false, false}};
+    // the kernel's two line layouts (see its stage-in comment)
+    const bool contig = lg.contiguous != 0;
+    if ((contig ? (lg.estride != 1 || lg.gstride != lg.n) : (lg.gstride != 1)) ||
+        (i64)lg.n * lg.estride + (i64)G * lg.gstride >= ((i64)1 << 31)) {
+        fprintf(stderr, "dotsocp: unsupported line geometry for the register-FFT DCT kernel\n");
+        return;
     }
-    if (mode == 0) BLU(0) else if (mode == 1) BLU(1) else BLU(2)
+    LineGeom lgn = lg;
+    lgn.n_inv = (unsigned)((((unsigned long long)1 << 32) / (unsigned)lg.n) + 1);
+#define BLU(MODE, CT)                                                                                              \
+    {                                                                                                              \
+        if (!attr_set[MODE][CT]) {                                                                                 \
+            cudaFuncSetAttribute(k_dct_blu16<LOG2M, PAIRS, MODE, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem);                                                                       \
+            attr_set[MODE][CT] = true;                                                                             \
+        }                                                                                                          \
+        k_dct_blu16<LOG2M, PAIRS, MODE, CT><<<grid, NTHR, smem, st>>>(lgn, ain, a, p->w, p->bhat16, p->tw, p->pw, p->ipw, sa); \
+    }
+    if (contig) { if (mode == 0) BLU(0, true) else if (mode == 1) BLU(1, true) else BLU(2, true) }
+    else { if (mode == 0) BLU(0, false) else if (mode == 1) BLU(1, false) else BLU(2, false) }
 #undef BLU
 }
 
