@@ -384,6 +384,47 @@ __device__ __forceinline__ double uval(double q, double a, double w)
 #ifndef KM_MIN_BLOCKS
 #define KM_MIN_BLOCKS 2
 #endif
+#ifndef KM_BULK
+#define KM_BULK 0         // 1: interior CTAs stage every step's input rows with cp.async.bulk (TMA engine) two steps ahead.
+                          // Bit-exact and fewer instructions per step, but measured SLOWER than the plain loads on B200
+                          // (512x512x256: 5.67 vs 5.01 ms, 1024x1024x512: 48.0 vs 37.9 ms); so is KM_L2PF (5.52 / 49.2 ms).
+                          // Deeper look-ahead loses more than the hidden latency wins; kept for experiments.
+#endif
+constexpr int KM_ROWD = 36;   // doubles per staged row: 32 (+1 for the y-1 neighbour) needed, + alignment slack, 288 B = 18 x 16 B
+__host__ __device__ constexpr int km_nrows(int TX) { return 16 * TX + 3 * (TX + 1); }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "KM_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra KM_WAIT_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// 16-byte aligned global -> shared bulk copy, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ unsigned ptr_par(const void* p) { return (unsigned)((unsigned long long)p >> 3) & 1u; }
+
+#ifndef KM_L2PF
+#define KM_L2PF 0         // 1: prefetch.global.L2 of the next step's lines
+#endif
 #ifndef KM_PREFETCH
 #define KM_PREFETCH 0     // 1: cp.async ring for the next step's loads (measured: no gain, the kernel is issue/latency bound)
 #endif
@@ -399,7 +440,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
     // thread prefetches (cp.async, 8 B) the 21 values of its NEXT time step while it works on the current one, so the
     // HBM latency of the beta / q streams is overlapped with the two projections instead of being exposed once per step
     constexpr int NT = TX * TY, NV = 21;
-    extern __shared__ double dyn_smem[];
+    extern __shared__ __align__(16) double dyn_smem[];
     double (*sh)[4][TX][TY] = reinterpret_cast<double (*)[4][TX][TY]>(dyn_smem);
     double* ring = dyn_smem + 2 * 4 * NT;
     const int ly = threadIdx.x, lx = threadIdx.y;
@@ -451,6 +492,100 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
 
     double wp3n = 0.0, wp4 = 0.0, wp7n = 0.0, wp8 = 0.0, u0p = 0.0;
 
+    // ---- bulk-copy ring (interior CTAs) ---------------------------------------------------------------------------------
+    // Every input of a time step is a set of rows of 32 (33) consecutive doubles.  Thread r < NROWS owns row r of the
+    // stage: slots 0..9 beta planes, 10 q0 new, 11 q0 old, 12 alpha0 (TX rows each, cell level t), then bx new / bx old at
+    // level t+1 (TX+1 rows from x0-1), by new / by old at level t+1 (TX rows, from y0-1), alpha_bx (TX+1 rows) and alpha_by
+    // (TX rows) at level t.  A row is fetched as 288 bytes from the 16-byte aligned address at or below its first element
+    // (the grids have odd lengths, so rows start on odd multiples of 8 bytes half of the time); readers add the parity of
+    // the row's first address to their index.  Step t+2 is issued right after the barrier of step t: two stages.
+    constexpr bool BULK = KM_BULK && !EDGE && !KM_PREFETCH;
+    constexpr int NROWS = km_nrows(TX), STAGE_D = NROWS * KM_ROWD;
+    constexpr int R_QN0 = 10 * TX, R_QO0 = 11 * TX, R_A0 = 12 * TX, R_QNBX = 13 * TX, R_QOBX = R_QNBX + TX + 1,
+                  R_QNBY = R_QOBX + TX + 1, R_QOBY = R_QNBY + TX, R_ALBX = R_QOBY + TX, R_ALBY = R_ALBX + TX + 1;
+    double* bring = dyn_smem + 2 * 4 * NT;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(bring + 2 * STAGE_D);
+    const char* p_src = nullptr;      // producer: first byte of my row at the first step
+    i64 p_stride = 0;                 //           bytes per time step
+    bool p_cell = true, p_on = false; //           row exists only while t is a cell level / row is used at all
+    if (BULK) {
+        const int x0 = blockIdx.y * (TX - 1), y0 = blockIdx.x * (TY - 1);
+        if (tid < NROWS) {
+            const int r = tid;
+            const double* base;
+            i64 idx, str;
+            p_on = true;
+            if (r < R_QNBX) {          // cell-indexed planes
+                const int slot = r / TX, row = r - slot * TX;
+                base = slot < 10 ? beta + (i64)slot * L : slot == 10 ? qn : slot == 11 ? qo : alpha;
+                if (slot == 11 && !UPDATE) p_on = false;
+                idx = (i64)t_start * g.P + (i64)(x0 + row) * g.ny + y0;
+                str = g.P;
+            } else if (r < R_QNBY) {   // bx at level t+1, rows x0-1 ..
+                const bool old = r >= R_QOBX;
+                const int row = r - (old ? R_QOBX : R_QNBX);
+                base = old ? qo_bx : qn_bx;
+                if (old && !UPDATE) p_on = false;
+                idx = (i64)(t_start + 1) * g.PBX + (i64)(x0 - 1 + row) * g.ny + y0;
+                str = g.PBX;
+            } else if (r < R_ALBX) {   // by at level t+1, from y0-1
+                const bool old = r >= R_QOBY;
+                const int row = r - (old ? R_QOBY : R_QNBY);
+                base = old ? qo_by : qn_by;
+                if (old && !UPDATE) p_on = false;
+                idx = (i64)(t_start + 1) * g.PBY + (i64)(x0 + row) * (g.ny - 1) + y0 - 1;
+                str = g.PBY;
+            } else if (r < R_ALBY) {   // alpha_bx at level t
+                base = al_bx;
+                idx = (i64)t_start * g.PBX + (i64)(x0 - 1 + (r - R_ALBX)) * g.ny + y0;
+                str = g.PBX;
+                p_cell = false;
+            } else {                   // alpha_by at level t
+                base = al_by;
+                idx = (i64)t_start * g.PBY + (i64)(x0 + (r - R_ALBY)) * (g.ny - 1) + y0 - 1;
+                str = g.PBY;
+                p_cell = false;
+            }
+            p_src = reinterpret_cast<const char*>(base + idx);
+            p_stride = str * (i64)sizeof(double);
+        }
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    auto fill = [&](int tt) {   // issue the rows of step tt into stage (tt - t_start) & 1
+        if (!BULK) return;
+        const int k = tt - t_start;
+        const bool cellt = tt < g.nt - 1;
+        unsigned long long* bar = &mbar[k & 1];
+        if (tid == 0) {
+            const int rows = cellt ? (NROWS - (UPDATE ? 0 : 3 * TX + 1)) : (2 * TX + 1);
+            mbar_expect_tx(bar, (unsigned)(rows * KM_ROWD * sizeof(double)));
+        }
+        if (p_on && (cellt || !p_cell)) {
+            const unsigned long long a = (unsigned long long)(p_src + (i64)k * p_stride) & ~15ull;
+            bulk_g2s(bring + (size_t)(k & 1) * STAGE_D + (size_t)tid * KM_ROWD, reinterpret_cast<const void*>(a),
+                     (unsigned)(KM_ROWD * sizeof(double)), bar);
+        }
+    };
+    // parity of the first address of my rows (low word arithmetic is enough), advanced every step
+    unsigned cw = 0, bw = 0, yw = 0;
+    unsigned par_c = 0, par_bxn = 0, par_bxo = 0, par_byn = 0, par_byo = 0, par_albx = 0, par_alby = 0;
+    if (BULK) {
+        const int y0 = blockIdx.x * (TY - 1);
+        cw = (unsigned)((i64)t_start * g.P + (i64)x * g.ny + y0);                       // cell planes, row x
+        bw = (unsigned)((i64)(t_start + 1) * g.PBX + (i64)(x - 1) * g.ny + y0);         // bx planes at t+1, row x-1
+        yw = (unsigned)((i64)(t_start + 1) * g.PBY + (i64)x * (g.ny - 1) + y0 - 1);     // by planes at t+1, row x (from y0-1)
+        par_c = ptr_par(beta) | (ptr_par(qn) << 1) | (ptr_par(qo) << 2) | (ptr_par(alpha) << 3) | ((unsigned)(L & 1) << 4);
+        par_bxn = ptr_par(qn_bx); par_bxo = ptr_par(qo_bx); par_byn = ptr_par(qn_by); par_byo = ptr_par(qo_by);
+        par_albx = ptr_par(al_bx) ^ (unsigned)(g.PBX & 1); par_alby = ptr_par(al_by) ^ (unsigned)(g.PBY & 1);
+        fill(t_start);
+        if (t_start + 1 < tr.tn1) fill(t_start + 1);
+    }
+
     // ring slots: 0..9 beta, 10 q0 new, 11 q0 old, 12 alpha0, 13..16 new bx/by at level t+1, 17..20 old bx/by at t+1
     auto prefetch = [&](int tt) {
         if (!KM_PREFETCH) return;
@@ -478,6 +613,13 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     prefetch(t_start);
+    // KM_L2PF: no ring, but ask the L2 for the next step's lines one step ahead (prefetch.global.L2 needs no registers and
+    // no shared memory), so that the loads of the next step find their data on chip
+    auto l2pf = [&](const double* p) {
+#if KM_L2PF
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+    };
 
     for (int t = t_start; t < tr.tn1; t++) {
         const int buf = t & 1;
@@ -489,15 +631,41 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
 #pragma unroll
         for (int j = 0; j < 10; j++) w[j] = 0.0;
         if (t + 1 < tr.tn1) prefetch(t + 1);
+        // bulk ring: wait for this step's stage, then all reads below are shared-memory loads at fixed offsets
+        const int kst = t - t_start;
+        const double* S = bring + (size_t)(kst & 1) * STAGE_D + ly;
+        const unsigned nyp = (unsigned)(g.ny & 1);
+        const unsigned pc = cw & 1u, pbx = bw & 1u, pby = yw & 1u;
+        if (BULK) mbar_wait(&mbar[kst & 1], (unsigned)(kst >> 1) & 1u);
+#define RB(rowbase, row, off) S[((rowbase) + (row)) * KM_ROWD + (int)(off)]
+        if (KM_L2PF && valid && t + 1 < g.nt - 1 && t + 1 < tr.tn1) {
+            const i64 cn1 = cidx + g.P;
+#pragma unroll
+            for (int j = 0; j < 10; j++)
+                if (!(ONE_D && j >= 5 && j <= 8)) l2pf(beta + (i64)j * L + cn1);
+            l2pf(qn + cn1);
+            l2pf(alpha + cn1);
+            if (UPDATE) l2pf(qo + cn1);
+            const i64 o2x = (i64)(t + 2) * g.PBX + ibx, o2y = (i64)(t + 2) * g.PBY + iby;
+            if (hxp) { l2pf(qn_bx + o2x); l2pf(al_bx + o2x - g.PBX); if (UPDATE) l2pf(qo_bx + o2x); }
+            if (hyp) { l2pf(qn_by + o2y); l2pf(al_by + o2y - g.PBY); if (UPDATE) l2pf(qo_by + o2y); }
+        }
         // the level-t alpha (and weight) values of the rhs stencil are only needed after the barrier: issue them now so
         // that their latency hides behind the two projections
         double al_xm = 0.0, al_x = 0.0, al_ym = 0.0, al_y = 0.0, wt_xm = 1.0, wt_x = 1.0, wt_ym = 1.0, wt_y = 1.0;
         if (owner) {
             const i64 ox = (i64)t * g.PBX, oy = (i64)t * g.PBY;
-            if (hxm) al_xm = al_bx[ox + ibxm];
-            if (hxp) al_x = al_bx[ox + ibx];
-            if (hym) al_ym = al_by[oy + ibym];
-            if (hyp) al_y = al_by[oy + iby];
+            if (BULK) {
+                al_xm = RB(R_ALBX, lx, pbx ^ par_albx);
+                al_x = RB(R_ALBX, lx + 1, pbx ^ nyp ^ par_albx);
+                al_ym = RB(R_ALBY, lx, pby ^ par_alby);
+                al_y = RB(R_ALBY, lx, 1 + (pby ^ par_alby));
+            } else {
+                if (hxm) al_xm = al_bx[ox + ibxm];
+                if (hxp) al_x = al_bx[ox + ibx];
+                if (hym) al_ym = al_by[oy + ibym];
+                if (hyp) al_y = al_by[oy + iby];
+            }
             if (WEIGHTED) {
                 if (hxm) wt_xm = w_bx[ox + ibxm];
                 if (hxp) wt_x = w_bx[ox + ibx];
@@ -513,24 +681,26 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
         if (cell && valid) {
             const double* src = ring + (size_t)buf * NV * NT + tid;
             const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
-#define LDV(slot, gexpr) (KM_PREFETCH ? src[(slot) * NT] : (gexpr))
+#define LDV(slot, gexpr, bexpr) (BULK ? (bexpr) : KM_PREFETCH ? src[(slot) * NT] : (gexpr))
             double b[10];
 #pragma unroll
-            for (int j = 0; j < 10; j++) b[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0 : LDV(j, beta[(i64)j * L + cidx]);
-            cn.q0 = LDV(10, qn[cidx]);
-            a0 = LDV(12, alpha[cidx]);
-            cn.bxm1 = hxm ? LDV(13, qn_bx[o1x + ibxm]) : 0.0;
-            cn.bx1 = hxp ? LDV(14, qn_bx[o1x + ibx]) : 0.0;
-            cn.bym1 = hym ? LDV(15, qn_by[o1y + ibym]) : 0.0;
-            cn.by1 = hyp ? LDV(16, qn_by[o1y + iby]) : 0.0;
+            for (int j = 0; j < 10; j++)
+                b[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0
+                                                   : LDV(j, beta[(i64)j * L + cidx], RB(j * TX, lx, (pc ^ par_c ^ ((j & 1) & (par_c >> 4))) & 1u));
+            cn.q0 = LDV(10, qn[cidx], RB(R_QN0, lx, (pc ^ (par_c >> 1)) & 1u));
+            a0 = LDV(12, alpha[cidx], RB(R_A0, lx, (pc ^ (par_c >> 3)) & 1u));
+            cn.bxm1 = hxm ? LDV(13, qn_bx[o1x + ibxm], RB(R_QNBX, lx, pbx ^ par_bxn)) : 0.0;
+            cn.bx1 = hxp ? LDV(14, qn_bx[o1x + ibx], RB(R_QNBX, lx + 1, pbx ^ nyp ^ par_bxn)) : 0.0;
+            cn.bym1 = hym ? LDV(15, qn_by[o1y + ibym], RB(R_QNBY, lx, pby ^ par_byn)) : 0.0;
+            cn.by1 = hyp ? LDV(16, qn_by[o1y + iby], RB(R_QNBY, lx, 1 + (pby ^ par_byn))) : 0.0;
             double z2n[10];
             cell_z2(cn, sc, hxm, hxp, hym, hyp, z2n);
             if (UPDATE) {
-                co.q0 = LDV(11, qo[cidx]);
-                co.bxm1 = hxm ? LDV(17, qo_bx[o1x + ibxm]) : 0.0;
-                co.bx1 = hxp ? LDV(18, qo_bx[o1x + ibx]) : 0.0;
-                co.bym1 = hym ? LDV(19, qo_by[o1y + ibym]) : 0.0;
-                co.by1 = hyp ? LDV(20, qo_by[o1y + iby]) : 0.0;
+                co.q0 = LDV(11, qo[cidx], RB(R_QO0, lx, (pc ^ (par_c >> 2)) & 1u));
+                co.bxm1 = hxm ? LDV(17, qo_bx[o1x + ibxm], RB(R_QOBX, lx, pbx ^ par_bxo)) : 0.0;
+                co.bx1 = hxp ? LDV(18, qo_bx[o1x + ibx], RB(R_QOBX, lx + 1, pbx ^ nyp ^ par_bxo)) : 0.0;
+                co.bym1 = hym ? LDV(19, qo_by[o1y + ibym], RB(R_QOBY, lx, pby ^ par_byo)) : 0.0;
+                co.by1 = hyp ? LDV(20, qo_by[o1y + iby], RB(R_QOBY, lx, 1 + (pby ^ par_byo))) : 0.0;
 #undef LDV
                 double v[10];
                 cell_z2(co, sc, hxm, hxp, hym, hyp, v);
@@ -555,6 +725,11 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
             sh[buf][3][lx][ly] = w[7];
         }
         __syncthreads();
+        // every thread has read stage kst: refill it with the rows of step t+2
+        if (BULK && t + 2 < tr.tn1) fill(t + 2);
+        cw += (unsigned)g.P;
+        bw += (unsigned)g.PBX;
+        yw += (unsigned)g.PBY;
         if (owner) {
             if (cell) {
                 if (emit) q2[cidx] = dmul(dsub(w[9], w[0]), sc.S);
@@ -616,6 +791,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
             wp4 = w[4];
             wp8 = w[8];
         }
+#undef RB
         // advance the carried node-level values
         cn.bxm = cn.bxm1; cn.bx = cn.bx1; cn.bym = cn.bym1; cn.by = cn.by1;
         if (UPDATE) { co.bxm = co.bxm1; co.bx = co.bx1; co.bym = co.bym1; co.by = co.by1; }
@@ -643,7 +819,10 @@ void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cu
     constexpr int TX = 8, TY = 32;
     dim3 block(TY, TX);
     dim3 grid((unsigned)((a.g.ny + TY - 2) / (TY - 1)), (unsigned)((a.g.nx + TX - 2) / (TX - 1)));
-    const size_t smem = (size_t)(2 * 4 + (KM_PREFETCH ? 2 * 21 : 0)) * TX * TY * sizeof(double);
+    const size_t ring = KM_PREFETCH ? (size_t)2 * 21 * TX * TY * sizeof(double)
+                        : KM_BULK   ? (size_t)2 * km_nrows(TX) * KM_ROWD * sizeof(double) + 16
+                                    : 0;
+    const size_t smem = (size_t)2 * 4 * TX * TY * sizeof(double) + ring;
 #define KM(W, O, U)                                                                                                   \
     {                                                                                                                 \
         static bool attr_done = false;                                                                                \
