@@ -9,6 +9,8 @@
 //   beta/z            : 10 planes of L = (nt-1)*nx*ny doubles (structure of arrays)
 // All kernels are HBM-bound streaming kernels: warps run along y (coalesced), k_mult marches along t.
 #include "kernels.h"
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace dsocp {
@@ -381,8 +383,17 @@ __device__ __forceinline__ double uval(double q, double a, double w)
     return WEIGHTED ? dsub(dmul(w, q), a) : dsub(q, a);
 }
 
+#ifndef KM_PAIRSYNC
+#define KM_PAIRSYNC 0     // 1: no CTA-wide barrier in the time loop: a warp (= one x row of the tile) only waits for the row
+                          //    above it (full/empty mbarrier pair per row), y neighbours are exchanged by warp shuffles.
+                          //    Bit-exact; measured 5.14 ms against 5.01 ms with __syncthreads (512x512x256): the barrier is
+                          //    not what limits the kernel.
+#endif
+#ifndef KM_TX
+#define KM_TX 8          // tile rows (x) per CTA; 16 (one 512-thread CTA per SM) measured in profiles/README.md
+#endif
 #ifndef KM_MIN_BLOCKS
-#define KM_MIN_BLOCKS 2
+#define KM_MIN_BLOCKS (KM_TX > 8 ? 1 : 2)
 #endif
 #ifndef KM_BULK
 #define KM_BULK 0         // 1: interior CTAs stage every step's input rows with cp.async.bulk (TMA engine) two steps ahead.
@@ -401,6 +412,10 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
 {
@@ -556,6 +571,14 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
         }
         __syncthreads();
     }
+    constexpr bool PAIR = KM_PAIRSYNC && !BULK && !KM_PREFETCH;
+    static_assert(!PAIR || TY == 32, "one warp per tile row");
+    __shared__ unsigned long long xbar[2][2][TX];   // [full | empty][buffer][row]
+    if (PAIR) {
+        if (tid < 4 * TX) mbar_init(&xbar[0][0][0] + tid, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
     auto fill = [&](int tt) {   // issue the rows of step tt into stage (tt - t_start) & 1
         if (!BULK) return;
         const int k = tt - t_start;
@@ -678,6 +701,9 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
             if (t + 1 < tr.tn1) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        const int sb = PAIR ? (kst & 1) : buf;
+        // the row below me has consumed what I wrote two steps ago into this buffer (passes at once on the first two steps)
+        if (PAIR && lx >= 1) mbar_wait(&xbar[1][sb][lx], ((unsigned)(kst >> 1) & 1u) ^ 1u);
         if (cell && valid) {
             const double* src = ring + (size_t)buf * NV * NT + tid;
             const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
@@ -719,12 +745,31 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
             proj_soc<ONE_D>(w);
 #pragma unroll
             for (int j = 0; j < 10; j++) w[j] = dadd(w[j], b[j]);
-            sh[buf][0][lx][ly] = w[1];
-            sh[buf][1][lx][ly] = w[3];
-            sh[buf][2][lx][ly] = w[5];
-            sh[buf][3][lx][ly] = w[7];
+            sh[sb][0][lx][ly] = w[1];
+            sh[sb][1][lx][ly] = w[3];
+            if (!PAIR) {
+                sh[sb][2][lx][ly] = w[5];
+                sh[sb][3][lx][ly] = w[7];
+            }
         }
-        __syncthreads();
+        double w1n_ = 0.0, w3n_ = 0.0, w5n_ = 0.0, w7n_ = 0.0;   // w columns 1,3 of (x+1,y) and 5,7 of (x,y+1)
+        if (PAIR) {
+            __syncwarp();
+            if (lx >= 1 && ly == 0) mbar_arrive(&xbar[0][sb][lx]);          // my row is published
+            w5n_ = __shfl_down_sync(0xffffffffu, w[5], 1);
+            w7n_ = __shfl_down_sync(0xffffffffu, w[7], 1);
+            if (lx < TX - 1) {
+                mbar_wait(&xbar[0][sb][lx + 1], (unsigned)(kst >> 1) & 1u);     // the row above is published
+                w1n_ = sh[sb][0][lx + 1][ly];
+                w3n_ = sh[sb][1][lx + 1][ly];
+                __syncwarp();
+                if (ly == 0) mbar_arrive(&xbar[1][sb][lx + 1]);              // ... and consumed
+            }
+        } else {
+            __syncthreads();
+            if (lx < TX - 1) { w1n_ = sh[sb][0][lx + 1][ly]; w3n_ = sh[sb][1][lx + 1][ly]; }
+            if (ly < TY - 1) { w5n_ = sh[sb][2][lx][ly + 1]; w7n_ = sh[sb][3][lx][ly + 1]; }
+        }
         // every thread has read stage kst: refill it with the rows of step t+2
         if (BULK && t + 2 < tr.tn1) fill(t + 2);
         cw += (unsigned)g.P;
@@ -751,8 +796,8 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
                 if (hxm) ADDTERM(dmul(sc.gx, uval<WEIGHTED>(cn.bxm, al_xm, wt_xm)));
                 if (hxp) {
                     ADDTERM(dmul(-sc.gx, uval<WEIGHTED>(cn.bx, al_x, wt_x)));
-                    const double w1n = cell ? sh[buf][0][lx + 1][ly] : 0.0;
-                    const double w3n = cell ? sh[buf][1][lx + 1][ly] : 0.0;
+                    const double w1n = cell ? w1n_ : 0.0;
+                    const double w3n = cell ? w3n_ : 0.0;
                     double s;
                     if (t == 0)
                         s = dadd(w1n, w[2]);
@@ -769,8 +814,8 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
                 if (hym) ADDTERM(dmul(sc.gy, uval<WEIGHTED>(cn.bym, al_ym, wt_ym)));
                 if (hyp) {
                     ADDTERM(dmul(-sc.gy, uval<WEIGHTED>(cn.by, al_y, wt_y)));
-                    const double w5n = cell ? sh[buf][2][lx][ly + 1] : 0.0;
-                    const double w7n = cell ? sh[buf][3][lx][ly + 1] : 0.0;
+                    const double w5n = cell ? w5n_ : 0.0;
+                    const double w7n = cell ? w7n_ : 0.0;
                     double s;
                     if (t == 0)
                         s = dadd(w5n, w[6]);
@@ -799,13 +844,20 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
 }
 
 template <int TX, int TY, bool WEIGHTED, bool ONE_D, bool UPDATE>
-__global__ void __launch_bounds__(TX* TY, KM_MIN_BLOCKS) k_mult(Geo g, TRange tr, IterScal sc, const double* __restrict__ qo,
+__global__ void __launch_bounds__(TX* TY, KM_MIN_BLOCKS) k_mult(Geo g, TRange tr, int nchunk, IterScal sc, const double* __restrict__ qo,
                                                  const double* __restrict__ qn, const double* __restrict__ alpha,
                                                  const double* __restrict__ weight, const double* __restrict__ beta,
                                                  double* __restrict__ beta_out, double* __restrict__ q2,
                                                  double* __restrict__ rhs, const double* __restrict__ c0,
                                                  const double* __restrict__ c1)
 {
+    if (nchunk > 1) {
+        // the time range is cut into nchunk pieces (blockIdx.z), each marched by its own CTA exactly like the slab of a
+        // multi-GPU run: a piece that does not start at the range's first cell layer replays the layer below it
+        const int i = blockIdx.z, nc = tr.tc1 - tr.tc0;
+        const int a = tr.tc0 + (int)((i64)i * nc / nchunk), b = tr.tc0 + (int)((i64)(i + 1) * nc / nchunk);
+        tr = TRange{a, b, i == 0 ? tr.tn0 : a, i == nchunk - 1 ? tr.tn1 : b};
+    }
     const int x0 = blockIdx.y * (TX - 1), y0 = blockIdx.x * (TY - 1);
     const bool interior = !ONE_D && x0 >= 1 && x0 + TX - 1 <= g.nx - 2 && y0 >= 1 && y0 + TY - 1 <= g.ny - 2;
     if (interior)
@@ -814,24 +866,50 @@ __global__ void __launch_bounds__(TX* TY, KM_MIN_BLOCKS) k_mult(Geo g, TRange tr
         k_mult_body<TX, TY, WEIGHTED, ONE_D, UPDATE, true>(g, tr, sc, qo, qn, alpha, weight, beta, beta_out, q2, rhs, c0, c1);
 }
 
+// number of time pieces that maximises (fraction of the last round that is filled) x (useful layers / marched layers)
+static int km_pick_chunks(long long base_ctas, int ncells, int slots)
+{
+    int best = 1;
+    double best_eff = 0.0;
+    const int nmax = std::max(1, std::min(32, ncells / 4));
+    for (int n = 1; n <= nmax; n++) {
+        const long long total = base_ctas * n;
+        const long long rounds = (total + slots - 1) / slots;
+        const double eff = (double)total / (double)(rounds * slots) * (double)ncells / (double)(ncells + n - 1);
+        if (eff > best_eff * 1.01) { best_eff = eff; best = n; }
+    }
+    return best;
+}
+
 void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st)
 {
-    constexpr int TX = 8, TY = 32;
+    constexpr int TX = KM_TX, TY = 32;
     dim3 block(TY, TX);
     dim3 grid((unsigned)((a.g.ny + TY - 2) / (TY - 1)), (unsigned)((a.g.nx + TX - 2) / (TX - 1)));
     const size_t ring = KM_PREFETCH ? (size_t)2 * 21 * TX * TY * sizeof(double)
                         : KM_BULK   ? (size_t)2 * km_nrows(TX) * KM_ROWD * sizeof(double) + 16
                                     : 0;
     const size_t smem = (size_t)2 * 4 * TX * TY * sizeof(double) + ring;
+    // Every CTA marches the same number of time steps, so a grid that fills the machine 4.25 times runs for 5 full rounds
+    // (512x512x256: 1258 CTAs on 296 slots).  Cutting the time range into pieces (grid.z) lets the CTA count land just below
+    // a whole number of rounds; each extra piece costs one replayed cell layer.  DOTSOCP_KM_CHUNKS=n forces n pieces.
+    static const int forced = [] { const char* e = getenv("DOTSOCP_KM_CHUNKS"); return e ? atoi(e) : 0; }();
 #define KM(W, O, U)                                                                                                   \
     {                                                                                                                 \
-        static bool attr_done = false;                                                                                \
-        if (!attr_done) {                                                                                             \
+        static int slots = 0;                                                                                         \
+        if (!slots) {                                                                                                 \
             cudaFuncSetAttribute(k_mult<TX, TY, W, O, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-            attr_done = true;                                                                                         \
+            int per_sm = 0, dev = 0, sms = 0;                                                                         \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mult<TX, TY, W, O, U>, TX * TY, smem);           \
+            cudaGetDevice(&dev);                                                                                      \
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);                                        \
+            slots = per_sm > 0 && sms > 0 ? per_sm * sms : 1;                                                         \
         }                                                                                                             \
-        k_mult<TX, TY, W, O, U><<<grid, block, smem, st>>>(a.g, a.tr, a.sc, a.q_old, a.q_new, a.alpha, a.weight,      \
-                                                            a.beta_in, a.beta_out, a.q2, a.rhs, a.c0, a.c1);          \
+        const int nchunk = forced > 0 ? std::min(forced, std::max(1, a.tr.tc1 - a.tr.tc0))                            \
+                                      : km_pick_chunks((long long)grid.x * grid.y, a.tr.tc1 - a.tr.tc0, slots);       \
+        grid.z = (unsigned)nchunk;                                                                                    \
+        k_mult<TX, TY, W, O, U><<<grid, block, smem, st>>>(a.g, a.tr, nchunk, a.sc, a.q_old, a.q_new, a.alpha,        \
+                                                            a.weight, a.beta_in, a.beta_out, a.q2, a.rhs, a.c0, a.c1); \
     }
     if (one_d) {
         if (update) KM(false, true, true) else KM(false, true, false)

@@ -238,3 +238,46 @@ def test_time_slabs_with_fused_transpose_pack(gpu, world, xchg, monkeypatch):
     assert np.abs(hb1.kkt[:r1.hist_len] - hbw.kkt[:rw.hist_len]).max() < 1e-12
     for a, b, name in zip(s1, sw, ("phi", "q", "z", "alpha", "beta")):
         assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), name
+
+
+CHUNK_SCRIPT = """
+import sys, hashlib
+import numpy as np
+sys.path.insert(0, %r)
+from oracle import dotsocp_oracle as O
+import dotsocp_b200 as dp
+from dotsocp_b200 import driver, solver
+n, nt = 65, 33
+rho0, rho1 = O.get_example2d("example2", n, n)
+var, model = driver.initialize(rho0, rho1, nt)
+driver.InitialScaling(var, model, True, None, "dot2d")
+opts = {"tol": 1e-12, "maxit": 40, "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": False, "scaling": True}
+o = solver.make_level_opts("dot2d", "inPALM", var, opts, model)
+h = hashlib.sha256()
+for world in (1, 2):
+    with dp.Session("dot2d", nt, n, n, world=world) as s:
+        s.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c)
+        hb, res = s.run(o)
+        for a in s.download():
+            h.update(np.ascontiguousarray(a).tobytes())
+        h.update(hb.kkt[:res.hist_len].tobytes())
+print("HASH", h.hexdigest())
+"""
+
+
+def test_time_chunked_mult_kernel_is_bit_identical(gpu, tmp_path):
+    """k_mult cuts the time range into pieces (grid.z) to fill the last round of CTAs; every piece replays the cell layer
+    below it like a slab does, so any number of pieces must give bit-identical iterates (single slab and emulated slabs)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "chunks.py"
+    script.write_text(CHUNK_SCRIPT % root)
+    hashes = {}
+    for n in ("1", "3", "8"):
+        e = dict(os.environ, DOTSOCP_KM_CHUNKS=n)
+        r = subprocess.run([sys.executable, str(script)], env=e, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        hashes[n] = [l for l in r.stdout.splitlines() if l.startswith("HASH")][0]
+    assert hashes["1"] == hashes["3"] == hashes["8"], hashes
