@@ -64,6 +64,37 @@ def main():
             assert rh_o.len == res.hist_len and int(vo.time["Iters"]) == res.iters
             assert np.abs(rh_o.kkt - hb.kkt[:res.hist_len]).max() < 1e-8
             print(f"dist parity ok: {variant} world={world} iters={res.iters}", flush=True)
+    # nx = 129 uses the register-FFT DCT kernel: its x passes write / read the packed transpose buffers directly and the
+    # exchange is pipelined in groups of time levels (CUDA-IPC pushes, NCCL send/recv or direct stores, by environment);
+    # the communicator of the first session is re-used (slab.REUSE_COMM)
+    nt, nx, ny = 17, 129, 24
+    rng = np.random.default_rng(5)
+    rho0 = np.abs(rng.standard_normal((ny, nx))) + 0.1
+    rho1 = np.abs(rng.standard_normal((ny, nx))) + 0.1
+    rho0 *= rho0.size / rho0.sum()
+    rho1 *= rho1.size / rho1.sum()
+    var, model = driver.initialize(rho0, rho1, nt)
+    driver.InitialScaling(var, model, True, None, "dot2d")
+    opts = {"tol": 1e-12, "maxit": 60, "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": False, "scaling": True}
+    o = solver.make_level_opts("dot2d", "inPALM", var, opts, model)
+    mine = slab.split_state(rank, world, nt, nx, ny, var.phi, var.q, var.z, var.alpha, var.beta, model.c, None)
+    with dp.Session("dot2d", nt, nx, ny, rank=rank, world=world, nccl_id=slab.REUSE_COMM) as s:
+        s.upload(*mine[:6], mine[6])
+        hb, res = s.run(o)
+        part = s.download()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, part)
+    if rank == 0:
+        state = slab.merge_state(world, nt, nx, ny, gathered)
+        with dp.Session("dot2d", nt, nx, ny) as s1:
+            s1.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c)
+            hb1, res1 = s1.run(o)
+            state1 = s1.download()
+        assert res.iters == res1.iters == 60 and res.hist_len == res1.hist_len
+        assert np.abs(hb.kkt[:res.hist_len] - hb1.kkt[:res1.hist_len]).max() < 1e-12
+        for a, b, name in zip(state, state1, ("phi", "q", "z", "alpha", "beta")):
+            assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), name
+        print(f"dist parity ok: fused transposes world={world}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

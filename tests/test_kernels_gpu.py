@@ -146,3 +146,21 @@ def test_poisson_1d_variant(gpu):
     phi = ops.oper_poisson(rhs, nt, nx, 0.5)
     ref = O.oper_poisson(0.25 * O.initialize_FFTkernel(nt, nx), rhs)
     assert np.abs(phi - ref).max() <= 1e-11 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("nt,nx,ny", [(17, 33, 20), (33, 129, 65)])
+def test_poisson_t_direction_thomas_equals_transform(gpu, nt, nx, ny, monkeypatch):
+    """The t direction is a tridiagonal solve by default; DOTSOCP_TSOLVE=dct (read when the plan is created) selects the
+    fused DCT_t -> ./kernel -> IDCT_t pass.  Both must match the reference formula."""
+    from dotsocp_b200 import ops
+    rng = np.random.default_rng(21)
+    rhs = rng.standard_normal(nt * nx * ny)
+    D = 0.61
+    ref = O.oper_poisson(D ** 2 * O.initialize_FFTkernel(nt, nx, ny), rhs)
+    monkeypatch.delenv("DOTSOCP_TSOLVE", raising=False)
+    thomas = ops.oper_poisson3dim(rhs, nt, nx, ny, D)
+    monkeypatch.setenv("DOTSOCP_TSOLVE", "dct")
+    viadct = ops.oper_poisson3dim(rhs, nt, nx, ny, D)
+    for got in (thomas, viadct):
+        assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max()
+    assert np.abs(thomas - viadct).max() > 0.0 or nt < 3   # they really are two different code paths

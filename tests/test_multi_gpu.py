@@ -10,7 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def test_nccl_time_slab_parity(gpu):
+@pytest.mark.parametrize("env", [{}, {"DOTSOCP_NO_IPC": "1"}, {"DOTSOCP_XCHG": "direct"}],
+                         ids=["ipc-push", "nccl-sendrecv", "direct-stores"])
+def test_nccl_time_slab_parity(gpu, env):
     if gpu < 2:
         pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
     nproc = 4 if gpu >= 4 else 2
@@ -19,6 +21,6 @@ def test_nccl_time_slab_parity(gpu):
         port = s.getsockname()[1]
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_parity.py")],
-                         capture_output=True, text=True, timeout=900)
+                         capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
     assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-4000:]
-    assert out.stdout.count("dist parity ok") == 2
+    assert out.stdout.count("dist parity ok") == 3
