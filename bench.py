@@ -49,6 +49,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, wl, world):
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json);
+    only the single-GPU captures exist, so multi-GPU lines report null."""
+    if world != 1:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)[kernel][wl]["bytes"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -321,7 +333,7 @@ def main():
     mult_bytes = (N + 4 * Q + 20 * L) * 8.0 / world          # per GPU: reads q_old,q_new,alpha,beta ; writes beta,q2,rhs
     ach = mult_bytes / (mult_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_mult", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": measured_traffic("k_mult", wl, world), "peak_source": peak_src,
                 "per_kernel_ms": {"poisson": per_kernel[0] / K_, "k_qstep": per_kernel[1] / K_, "k_mult": mult_ms}}
     it_ach = W_iter / (ms_per_step * 1e-3) / 1e9
     roofline_iter = {"bound": "hbm", "achieved": it_ach, "peak": hbm_peak * world, "unit": "GB/s", "frac": it_ach / (hbm_peak * world),
