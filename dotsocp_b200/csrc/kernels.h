@@ -87,6 +87,9 @@ void launch_scale(double* x, i64 n, double mul, double div, cudaStream_t st);
 //   x = c1*x0 + c2*((1-rho)*xold + rho*x) ; xold = x ; if (copy_anchor) x0 = x
 void launch_halpern(double* x, double* xold, double* x0, i64 n, double c1, double c2, double rho, bool copy_anchor,
                     cudaStream_t st);
+// general acc-ADMM extrapolation (opts.theta != 2): x, old, hatOld updated in place (k_accel3)
+void launch_accel3(double* x, double* xold, double* xhatold, i64 n, double rho, double a, double b, double c2, bool first,
+                   bool keep_hat, cudaStream_t st);
 // 6 <-> 10 column conversion of the 1-D variant's z/beta (cols 0..4 -> 0..4, col 5 -> 9; 5..8 zero)
 void launch_cols6to10(const double* in6, double* out10, i64 L, cudaStream_t st);
 void launch_cols10to6(const double* in10, double* out6, i64 L, cudaStream_t st);

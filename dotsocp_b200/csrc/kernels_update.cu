@@ -392,8 +392,11 @@ __device__ __forceinline__ double uval(double q, double a, double w)
 #ifndef KM_TX
 #define KM_TX 8          // tile rows (x) per CTA; 16 (one 512-thread CTA per SM) measured in profiles/README.md
 #endif
+#ifndef KM_TY
+#define KM_TY 32         // tile columns (y, contiguous) per CTA
+#endif
 #ifndef KM_MIN_BLOCKS
-#define KM_MIN_BLOCKS (KM_TX > 8 ? 1 : 2)
+#define KM_MIN_BLOCKS (KM_TX * KM_TY > 256 ? 1 : 2)
 #endif
 #ifndef KM_BULK
 #define KM_BULK 0         // 1: interior CTAs stage every step's input rows with cp.async.bulk (TMA engine) two steps ahead.
@@ -886,7 +889,7 @@ static int km_pick_chunks(long long base_ctas, int ncells, int slots)
 
 void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st)
 {
-    constexpr int TX = KM_TX, TY = 32;
+    constexpr int TX = KM_TX, TY = KM_TY;
     dim3 block(TY, TX);
     dim3 grid((unsigned)((a.g.ny + TY - 2) / (TY - 1)), (unsigned)((a.g.nx + TX - 2) / (TX - 1)));
     const size_t ring = KM_PREFETCH ? (size_t)2 * 21 * TX * TY * sizeof(double)
@@ -1352,6 +1355,32 @@ void launch_halpern(double* x, double* xold, double* x0, i64 n, double c1, doubl
     i64 b = (n + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
     k_halpern<<<(unsigned)b, 256, 0, st>>>(x, xold, x0, n, c1, c2, rho, copy_anchor ? 1 : 0);
+}
+
+// acc-ADMM, general extrapolation (opts.theta != 2), solver_socp_accADMM.m:389-417:
+//   hat = (1-rho)*old + rho*x ;  x = (1-c1)*old + c1*hat                      (k == 0)
+//                                x = (1-c1)*old + (c1+c2)*hat - c2*hatOld      (k  > 0) ;  old = x ; hatOld = hat (unless restart)
+__global__ void __launch_bounds__(256) k_accel3(double* __restrict__ x, double* __restrict__ xold, double* __restrict__ xhatold,
+                                                i64 n, double rho, double a, double b, double c2, int first, int keep_hat)
+{
+    const double omr = 1.0 - rho;
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double o = xold[i];
+        const double hat = dadd(dmul(omr, o), dmul(rho, x[i]));
+        double v = dadd(dmul(a, o), dmul(b, hat));
+        if (!first) v = dsub(v, dmul(c2, xhatold[i]));
+        x[i] = v;
+        xold[i] = v;
+        if (keep_hat) xhatold[i] = hat;
+    }
+}
+void launch_accel3(double* x, double* xold, double* xhatold, i64 n, double rho, double a, double b, double c2, bool first,
+                   bool keep_hat, cudaStream_t st)
+{
+    if (n <= 0) return;
+    i64 blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_accel3<<<(unsigned)blocks, 256, 0, st>>>(x, xold, xhatold, n, rho, a, b, c2, first ? 1 : 0, keep_hat ? 1 : 0);
 }
 
 __global__ void __launch_bounds__(256) k_cols6to10(const double* __restrict__ in6, double* __restrict__ out10, i64 L)

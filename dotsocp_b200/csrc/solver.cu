@@ -1113,7 +1113,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     const int restart = o.restart > 0 ? o.restart : 100;
     const double stepRho = o.rho > 0 ? o.rho : 2;
     const double stepAlpha = o.theta > 0 ? o.theta : 2;
-    if (acc && stepAlpha != 2) return set_err(DOTSOCP_EINVAL, "acc-ADMM: only the Halpern iteration (opts.theta == 2, the default) is available");
+    const bool halpern = stepAlpha == 2;   // :30
     if (palm && (weighted || c->one_d)) return set_err(DOTSOCP_EINVAL, "PALM exists only for socp/dot2d");
     if (acc && c->one_d) return set_err(DOTSOCP_EINVAL, "acc-ADMM does not exist for socp/dot1d");
     if (!inpalm && c->world > 1) return set_err(DOTSOCP_EINVAL, "PALM / acc-ADMM run on a single slab only (world == 1)");
@@ -1407,7 +1407,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             }
         }
         if (stop) break;
-        if (acc) {   // Halpern iteration, accADMM :371-388
+        if (acc && halpern) {   // Halpern iteration, accADMM :371-388
             cudaEvent_t e5 = mark();
             const double c1 = 1.0 / (kacc + 2), c2 = (double)(kacc + 1) / (kacc + 2);
             kacc += 1;
@@ -1416,6 +1416,20 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             for (int i = 0; i < 5; i++) launch_halpern(cur[i], S0->old_[i], S0->anc_[i], vn[i], c1, c2, stepRho, anchor, c->st);
             c->launches += 5;
             if (anchor) kacc = 0;
+            cudaEvent_t e6 = mark();
+            segs.push_back({e5, e6, 5});
+        } else if (acc) {       // general extrapolation, accADMM :389-417 (anc_ holds the previous "hat" iterate)
+            cudaEvent_t e5 = mark();
+            const double c1 = stepAlpha / (2 * (kacc + stepAlpha));
+            const double c2 = kacc / (kacc + stepAlpha);
+            const bool first = kacc == 0;
+            kacc += 1;
+            const bool restarted = kacc >= restart;
+            refresh_cur();
+            for (int i = 0; i < 5; i++)
+                launch_accel3(cur[i], S0->old_[i], S0->anc_[i], vn[i], stepRho, 1 - c1, first ? c1 : c1 + c2, c2, first, !restarted, c->st);
+            c->launches += 5;
+            if (restarted) kacc = 0;
             cudaEvent_t e6 = mark();
             segs.push_back({e5, e6, 5});
         }

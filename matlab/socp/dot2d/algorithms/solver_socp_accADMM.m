@@ -1,5 +1,5 @@
 function [runHist, sigma] = solver_socp_accADMM(var, opts, model)
-%% GPU drop-in for socp/dot2d/algorithms/solver_socp_accADMM.m (Halpern, opts.theta == 2)
+%% GPU drop-in for socp/dot2d/algorithms/solver_socp_accADMM.m (Halpern iteration and the general opts.theta extrapolation)
 % Place this file (with dotsocp_gpu_level.m and the built mexDotSocpGPU) in a copy of the reference's socp/ tree: the
 % drivers add their own algorithms/ directory to the front of the path (solver_dotsocp2d.m:37-54), so the replacement
 % must keep this file name.  Demos and drivers stay byte-identical.

@@ -281,3 +281,32 @@ def test_time_chunked_mult_kernel_is_bit_identical(gpu, tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
         hashes[n] = [l for l in r.stdout.splitlines() if l.startswith("HASH")][0]
     assert hashes["1"] == hashes["3"] == hashes["8"], hashes
+
+
+@pytest.mark.parametrize("variant,theta,rho,restart", [("dot2d", 3.0, 1.6, 25), ("dot2d", 5.0, 2.0, 7), ("wdot2d", 3.0, 1.8, 40)])
+def test_accadmm_general_extrapolation_parity(gpu, variant, theta, rho, restart):
+    """opts.theta != 2 leaves the Halpern iteration for the three-term extrapolation of solver_socp_accADMM.m:389-417
+    (reachable only through the level solver: the drivers never set theta)."""
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import driver
+    n, nt = 17, 9
+    rho0, rho1 = O.get_example2d("example1", n, n)
+    weight = O.gene_weight_circle(nt, n, n) if variant == "wdot2d" else None
+    var, model = driver.initialize(rho0, rho1, nt)
+    vo, mo = O.initialize2d(rho0, rho1, nt)
+    if weight is not None:
+        model.weight = weight
+        mo.weight = weight
+    driver.InitialScaling(var, model, True, None, variant)
+    O.InitialScaling(vo, mo, True, None, variant)
+    opts = {"tol": 1e-4 if weight is None else 1e-3, "maxit": 400, "sigma": 1.0, "ifCheckStepByStep": False, "scaling": True,
+            "theta": theta, "rho": rho, "restart": restart}
+    fn_g = dp.solver_socp_accADMM if weight is None else dp.solver_wsocp_accADMM
+    rh_g, sg = fn_g(var, opts, model)
+    rh_o, so = O.solver_socp_accADMM(vo, opts, mo)
+    assert rh_g.len == rh_o.len and int(var.time["Iters"]) == int(vo.time["Iters"])
+    assert np.abs(rh_g.kkt - rh_o.kkt).max() < 1e-8
+    assert abs(sg - so) <= 1e-12 * abs(so)
+    for name in ("phi", "q", "alpha", "z", "beta"):
+        a, b = np.asarray(getattr(var, name)), np.asarray(getattr(vo, name))
+        assert np.abs(a - b).max() <= 1e-8 * max(1.0, np.abs(b).max()), name
