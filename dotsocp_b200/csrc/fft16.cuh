@@ -7,7 +7,7 @@
 // with one shared-memory exchange between consecutive passes.  The spectrum comes out digit-reversed
 // (position m1*TP + m2*Q2 + m3  <->  frequency m1 + 16*m2 + 256*m3); the point-wise product with the chirp spectrum is
 // done in that order in registers and the inverse transform runs the transposed graph (pass 3', 2', 1').
-// Everything is __host__ __device__ so that the index algebra is unit-tested on the CPU (tests/fft16_host_test.cu).
+// Everything is __host__ __device__ so that the index algebra is unit-tested on the CPU (tests/host/fft16_host_test.cu).
 #pragma once
 #include <cuda_runtime.h>
 
