@@ -169,6 +169,7 @@ struct dotsocp_ctx {
     std::vector<i64> pcut;      // mode chunks [pcut[r], pcut[r+1])
     int qcur = 0, bcur = 0;
     bool z_materialised = true; // beta[1-bcur] holds z itself (after upload / at exit) instead of beta_old
+    bool z_absent = false;      // upload was given no z: legal only for inPALM with maxit >= 1, which overwrites z before any read
     PoissonPlan* pp = nullptr;
     double launches = 0;
     bool uploaded = false;
@@ -794,7 +795,7 @@ static int copy_cols(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev10, 
 extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q, const double* z, const double* alpha,
                               const double* beta, const double* cvec, const double* weight)
 {
-    if (!c || !phi || !q || !z || !alpha || !beta || !cvec) return set_err(DOTSOCP_EINVAL, "NULL array");
+    if (!c || !phi || !q || !alpha || !beta || !cvec) return set_err(DOTSOCP_EINVAL, "NULL array");
     if (c->weighted && !weight) return set_err(DOTSOCP_EINVAL, "weighted variant needs weight");
     const Geo& g = c->g;
     c->qcur = 0;
@@ -824,9 +825,10 @@ extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q
         if (tr.tn0 == 0) CU(cudaMemcpyAsync(s->c0, cvec + hm.nodes(0), g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
         if (tr.tn1 == g.nt) CU(cudaMemcpyAsync(s->c1, cvec + hm.nodes(g.nt - 1), g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
         if ((rc = copy_cols(c, s, hm, s->beta[0], const_cast<double*>(beta), true))) return rc;
-        if ((rc = copy_cols(c, s, hm, s->beta[1], const_cast<double*>(z), true))) return rc;
+        if (z && (rc = copy_cols(c, s, hm, s->beta[1], const_cast<double*>(z), true))) return rc;
     }
     c->z_materialised = true;
+    c->z_absent = (z == nullptr);
     int rc = ghosts(c, GH_PHI_UP | GH_Q_UP | GH_Q_DOWN | GH_ALPHA0_DOWN | GH_BETA_DOWN | GH_W, 0, 0);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->st));
@@ -839,6 +841,7 @@ extern "C" int dotsocp_download(dotsocp_ctx* c, double* phi, double* q, double* 
     if (!c) return set_err(DOTSOCP_EINVAL, "NULL ctx");
     if (!c->uploaded) return set_err(DOTSOCP_ESTATE, "download before upload");
     if (!c->z_materialised && z) return set_err(DOTSOCP_ESTATE, "z is not materialised (session still open)");
+    if (c->z_absent && z) return set_err(DOTSOCP_ESTATE, "z was neither uploaded nor computed yet");
     const Geo& g = c->g;
     for (Slab* s : c->slabs) {
         HostMap hm{c->world > 1 && !c->emulate, &g, s->tr};
@@ -1114,6 +1117,8 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     const double stepRho = o.rho > 0 ? o.rho : 2;
     const double stepAlpha = o.theta > 0 ? o.theta : 2;
     const bool halpern = stepAlpha == 2;   // :30
+    if (c->z_absent && (!inpalm || maxit < 1))
+        return set_err(DOTSOCP_ESTATE, "z was not uploaded: only inPALM with maxit >= 1 never reads the incoming z");
     if (palm && (weighted || c->one_d)) return set_err(DOTSOCP_EINVAL, "PALM exists only for socp/dot2d");
     if (acc && c->one_d) return set_err(DOTSOCP_EINVAL, "acc-ADMM does not exist for socp/dot1d");
     if (!inpalm && c->world > 1) return set_err(DOTSOCP_EINVAL, "PALM / acc-ADMM run on a single slab only (world == 1)");
@@ -1440,6 +1445,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         // z = Pi_Q(d + BF q_old - beta_old), written over beta_old (cell-local, safe in place)
         if ((rc = zstep_all(c, L.sc, true, nullptr))) return rc;
         c->z_materialised = true;
+        c->z_absent = false;
     }
     L.scale(A_ALPHA, sigma, 1.0);      // var.alpha = sigma*alpha
     L.scale(A_BETA, sigma, 1.0);       // var.beta  = sigma*beta
@@ -1486,7 +1492,9 @@ extern "C" int dotsocp_solve_level(const dotsocp_level_opts* o, double* phi, dou
     dotsocp_ctx* c = nullptr;
     int rc = dotsocp_create(&c, o->variant, o->nt, o->nx, o->ny, 0, 1, nullptr);
     if (rc) return rc;
-    rc = dotsocp_upload(c, phi, q, z, alpha, beta, cvec, weight);
+    // inPALM overwrites z (solver_socp_inPALM.m:199) before it is ever read, so its incoming value need not cross PCIe
+    const bool z_dead = o->method == DOTSOCP_METHOD_INPALM && o->maxit >= 1;
+    rc = dotsocp_upload(c, phi, q, z_dead ? nullptr : z, alpha, beta, cvec, weight);
     if (!rc) rc = dotsocp_run(c, o, hist, res);
     if (!rc) rc = dotsocp_download(c, phi, q, z, alpha, beta);
     dotsocp_destroy(c);
@@ -1563,6 +1571,7 @@ extern "C" int dotsocp_iter_end(dotsocp_ctx* c)
         int rc = zstep_all(c, c->sc, true, nullptr);
         if (rc) return rc;
         c->z_materialised = true;
+        c->z_absent = false;
     }
     L.scale(A_ALPHA, c->sigma_fold, 1.0);
     L.scale(A_BETA, c->sigma_fold, 1.0);

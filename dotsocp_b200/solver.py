@@ -120,9 +120,10 @@ class Session:
 
     def upload(self, phi, q, z, alpha, beta, c, weight=None):
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64) if a.ndim == 1 else np.asfortranarray(a, dtype=np.float64)
-        arrs = [f(np.asarray(a)) for a in (phi, q, z, alpha, beta, c)]
+        arrs = [None if a is None else f(np.asarray(a)) for a in (phi, q, z, alpha, beta, c)]
         assert arrs[0].size == self.N and arrs[1].size == self.Q and arrs[3].size == self.Q and arrs[5].size == self.N
-        assert arrs[2].shape == (self.L, self.ncol) and arrs[4].shape == (self.L, self.ncol)
+        assert arrs[4].shape == (self.L, self.ncol)
+        assert arrs[2] is None or arrs[2].shape == (self.L, self.ncol)   # z=None: inPALM never reads the incoming z
         w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
         check(lib().dotsocp_upload(self._h, *[ptr(a) for a in arrs], ptr(w)))
 
@@ -187,7 +188,9 @@ def _solve(variant, method, var, opts, model):
     if variant == "wdot2d" and weight is None:
         raise ValueError("solver_wsocp_*: model.weight is required")
     with Session(variant, o.nt, o.nx, o.ny) as s:
-        s.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c, weight)
+        # inPALM overwrites z (solver_socp_inPALM.m:199) before reading it: the incoming z stays on the host
+        z_dead = o.method == METHOD["inPALM"] and o.maxit >= 1
+        s.upload(var.phi, var.q, None if z_dead else var.z, var.alpha, var.beta, model.c, weight)
         hb, res = s.run(o)
         var.phi, var.q, var.z, var.alpha, var.beta = s.download()
     return _finish(var, o.method, hb, res)

@@ -136,7 +136,9 @@ typedef struct dotsocp_ctx dotsocp_ctx;
 int  dotsocp_nccl_unique_id(char id128[128]);
 int  dotsocp_create(dotsocp_ctx **ctx, int variant, int nt, int nx, int ny, int rank, int world, const char *nccl_id);
 void dotsocp_destroy(dotsocp_ctx *ctx);
-/* full (global) host arrays in, each rank keeps its slab */
+/* full (global) host arrays in, each rank keeps its slab.  z may be NULL when the next run is inPALM with maxit >= 1:
+ * that loop overwrites z (solver_socp_inPALM.m:199) before reading it, so its incoming value need not cross PCIe
+ * (dotsocp_solve_level does this itself); any other run, or a download of z before a run, then fails with DOTSOCP_ESTATE. */
 int  dotsocp_upload(dotsocp_ctx *ctx, const double *phi, const double *q, const double *z,
                     const double *alpha, const double *beta, const double *c, const double *weight);
 int  dotsocp_download(dotsocp_ctx *ctx, double *phi, double *q, double *z, double *alpha, double *beta);

@@ -310,3 +310,36 @@ def test_accadmm_general_extrapolation_parity(gpu, variant, theta, rho, restart)
     for name in ("phi", "q", "alpha", "z", "beta"):
         a, b = np.asarray(getattr(var, name)), np.asarray(getattr(vo, name))
         assert np.abs(a - b).max() <= 1e-8 * max(1.0, np.abs(b).max()), name
+
+
+def test_inpalm_never_reads_the_incoming_z(gpu):
+    """solver_socp_inPALM.m:199 overwrites z before any read, so the upload may omit it (dotsocp_solve_level does): same
+    iterates bit for bit with a garbage z, and the calls that do need z refuse to run without it."""
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import _lib, driver, solver
+    n, nt = 33, 17
+    rho0, rho1 = O.get_example2d("example2", n, n)
+    var, model = driver.initialize(rho0, rho1, nt)
+    driver.InitialScaling(var, model, True, None, "dot2d")
+    opts = {"tol": 1e-4, "maxit": 60, "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": False, "scaling": True}
+    o = solver.make_level_opts("dot2d", "inPALM", var, opts, model)
+    states = []
+    for z in (var.z, None, np.full_like(var.z, 1e300)):
+        with dp.Session("dot2d", nt, n, n) as s:
+            s.upload(var.phi, var.q, z, var.alpha, var.beta, model.c)
+            hb, res = s.run(o)
+            states.append((hb.kkt[:res.hist_len].copy(), s.download()))
+    for kkt, st in states[1:]:
+        assert np.array_equal(kkt, states[0][0])
+        for a, b in zip(st, states[0][1]):
+            assert np.array_equal(a, b)
+    with dp.Session("dot2d", nt, n, n) as s:
+        s.upload(var.phi, var.q, None, var.alpha, var.beta, model.c)
+        with pytest.raises(_lib.DotsocpError):
+            s.download()                                  # z neither uploaded nor computed
+        with pytest.raises(_lib.DotsocpError):
+            s.run(solver.make_level_opts("dot2d", "PALM", var, opts, model))
+        with pytest.raises(_lib.DotsocpError):
+            s.run(solver.make_level_opts("dot2d", "acc-ADMM", var, opts, model))
+        hb, res = s.run(o)                                # inPALM is fine
+        assert np.array_equal(hb.kkt[:res.hist_len], states[0][0])
