@@ -106,7 +106,9 @@ struct PoissonPlan {
     double* lam_y;
     // tridiagonal t-solve (default; DOTSOCP_TSOLVE=dct selects the fused DCT_t / divide / IDCT_t kernel instead)
     bool use_thomas;
-    struct GTab { i64 p0, lines; double* tab; };   // pivot reciprocals g_t(mode), [nt][lines] for modes [p0, p0+lines)
+    // pivot reciprocals g_t(mode), [nt][lines] for modes [p0, p0+lines); t_fix[mode] = first level from which g_t no longer
+    // changes (the recurrence has reached its fixed point bit for bit), so levels t_fix .. nt-2 need no table read
+    struct GTab { i64 p0, lines; double* tab; int* t_fix; };
     std::vector<GTab> gtabs;
     double* cmat_t;     // dense nt x nt orthonormal DCT-II matrix for the singular mode kx = ky = 0
 };

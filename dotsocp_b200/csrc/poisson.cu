@@ -846,7 +846,8 @@ static void launch_dct_axis(const DctPlan* p, LineGeom lg, i64 outer, const doub
 // replaces two of the six O(n log n) transforms of the solve by 6N doubles of streaming traffic.  The singular mode
 // kx = ky = 0 keeps the reference's convention (zero eigenvalue := 1) through a dense DCT of that single line.
 __global__ void __launch_bounds__(256) k_thomas_table(int nt, int ny, i64 lines, i64 stride, i64 p0, const double* __restrict__ lam_x,
-                                                      const double* __restrict__ lam_y, double* __restrict__ gtab)
+                                                      const double* __restrict__ lam_y, double* __restrict__ gtab,
+                                                      int* __restrict__ t_fix)
 {
     const i64 l = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     if (l >= lines) return;
@@ -856,22 +857,30 @@ __global__ void __launch_bounds__(256) k_thomas_table(int nt, int ny, i64 lines,
     const double nu = (lam_y[ky] + lam_x[kx]) / ct;
     double g = 1.0 / (1.0 + nu);
     gtab[l] = g;
+    int fix = nt;   // g_t == g_{t-1} => every later interior level repeats it (same expression, same inputs)
     for (int t = 1; t < nt; t++) {
         const double diag = (t == nt - 1 ? 1.0 : 2.0) + nu;
-        g = 1.0 / (diag - g);
+        const double gn = 1.0 / (diag - g);
+        if (fix == nt && t < nt - 1 && gn == g) fix = t;
+        g = gn;
         gtab[(i64)t * stride + l] = g;
     }
+    t_fix[l] = fix;
 }
 
 // PUSH: the solution of time level t is stored in the buffer of the slab that owns the level (obase[owner] = first owned
 // row of this mode chunk there, tcut = first level of every slab) -- peer memory over NVLink -- instead of in place
 template <bool PUSH>
 __global__ void __launch_bounds__(256) k_thomas(int nt, i64 lines, i64 stride, i64 p0, double inv_scale, const double* __restrict__ gtab,
-                                                double* __restrict__ a, double* const* __restrict__ obase, const int* __restrict__ tcut,
-                                                int world)
+                                                const int* __restrict__ t_fix, double* __restrict__ a,
+                                                double* const* __restrict__ obase, const int* __restrict__ tcut, int world)
 {
     const i64 l = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     if (l >= lines) return;
+    // table reads only for t < tf and for the last level; in between g_t is the fixed point gs (bit-identical to the table)
+    const int tf = t_fix[l];
+    const double gs = tf < nt ? gtab[(i64)tf * stride + l] : 0.0;
+    auto gt = [&](int t) { return (t < tf || t == nt - 1) ? gtab[(i64)t * stride + l] : gs; };
     int ow = world - 1, tlo = 0;
     double* ob = nullptr;
     if (PUSH) { tlo = tcut[ow]; ob = obase[ow] + l; }
@@ -893,11 +902,11 @@ __global__ void __launch_bounds__(256) k_thomas(int nt, i64 lines, i64 stride, i
     for (; t + 4 <= nt; t += 4) {
         double r[4], g[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { r[u] = a[(i64)(t + u) * stride + l]; g[u] = gtab[(i64)(t + u) * stride + l]; }
+        for (int u = 0; u < 4; u++) { r[u] = a[(i64)(t + u) * stride + l]; g[u] = gt(t + u); }
 #pragma unroll
         for (int u = 0; u < 4; u++) { d = (r[u] * inv_scale + d) * g[u]; a[(i64)(t + u) * stride + l] = d; }
     }
-    for (; t < nt; t++) { d = (a[(i64)t * stride + l] * inv_scale + d) * gtab[(i64)t * stride + l]; a[(i64)t * stride + l] = d; }
+    for (; t < nt; t++) { d = (a[(i64)t * stride + l] * inv_scale + d) * gt(t); a[(i64)t * stride + l] = d; }
     // back substitution
     double x = d;
     if (PUSH) put(nt - 1, x);
@@ -905,11 +914,11 @@ __global__ void __launch_bounds__(256) k_thomas(int nt, i64 lines, i64 stride, i
     for (; t - 3 >= 0; t -= 4) {
         double dd[4], g[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { dd[u] = a[(i64)(t - u) * stride + l]; g[u] = gtab[(i64)(t - u) * stride + l]; }
+        for (int u = 0; u < 4; u++) { dd[u] = a[(i64)(t - u) * stride + l]; g[u] = gt(t - u); }
 #pragma unroll
         for (int u = 0; u < 4; u++) { x = dd[u] + g[u] * x; put(t - u, x); }
     }
-    for (; t >= 0; t--) { x = a[(i64)t * stride + l] + gtab[(i64)t * stride + l] * x; put(t, x); }
+    for (; t >= 0; t--) { x = a[(i64)t * stride + l] + gt(t) * x; put(t, x); }
 }
 
 // mode (0,0): phi = IDCT_t( DCT_t(r) ./ (D2 * lam_t) ), lam_t[0] := 1, dense nt x nt transform by one CTA
@@ -981,7 +990,7 @@ PoissonPlan* poisson_plan_create(int nt, int nx, int ny)
 void poisson_plan_destroy(PoissonPlan* p)
 {
     if (!p) return;
-    for (auto& e : p->gtabs) cudaFree(e.tab);
+    for (auto& e : p->gtabs) { cudaFree(e.tab); cudaFree(e.t_fix); }
     cudaFree(p->cmat_t);
     dct_plan_destroy(p->py); dct_plan_destroy(p->px); dct_plan_destroy(p->pt);
     cudaFree(p->lam_t); cudaFree(p->lam_x); cudaFree(p->lam_y);
@@ -1002,12 +1011,14 @@ static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, c
     }
     // one table per mode range (a process that emulates several slabs keeps one per slab)
     double* gtab = nullptr;
+    int* t_fix = nullptr;
     for (auto& e : p->gtabs)
-        if (e.p0 == p0 && e.lines == lines) gtab = e.tab;
+        if (e.p0 == p0 && e.lines == lines) { gtab = e.tab; t_fix = e.t_fix; }
     if (!gtab) {
         cudaMalloc(&gtab, (size_t)g.nt * lines * sizeof(double));
-        k_thomas_table<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, g.ny, lines, lines, p0, p->lam_x, p->lam_y, gtab);
-        p->gtabs.push_back({p0, lines, gtab});
+        cudaMalloc(&t_fix, (size_t)lines * sizeof(int));
+        k_thomas_table<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, g.ny, lines, lines, p0, p->lam_x, p->lam_y, gtab, t_fix);
+        p->gtabs.push_back({p0, lines, gtab, t_fix});
         if (!p->cmat_t) p->cmat_t = dense_dct_matrix(g.nt);
         if (launches) *launches += 1;
     }
@@ -1017,9 +1028,9 @@ static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, c
         if (launches) *launches += 1;
     }
     if (push_tab)
-        k_thomas<true><<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, lines, lines, p0, 1.0 / (D2 * ct), gtab, buf, push_tab, tcut, world);
+        k_thomas<true><<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, lines, lines, p0, 1.0 / (D2 * ct), gtab, t_fix, buf, push_tab, tcut, world);
     else
-        k_thomas<false><<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, lines, lines, p0, 1.0 / (D2 * ct), gtab, buf, nullptr, nullptr, 1);
+        k_thomas<false><<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, lines, lines, p0, 1.0 / (D2 * ct), gtab, t_fix, buf, nullptr, nullptr, 1);
     if (launches) *launches += 1;
 }
 

@@ -1165,9 +1165,12 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     }
     if (acc) { copy_to(S0->old_); copy_to(S0->anc_); }   // :157-163
 
-    cudaEvent_t ev_begin, ev_end;
-    cudaEventCreate(&ev_begin);
-    cudaEventCreate(&ev_end);
+    struct EvPair {   // destroyed on every exit path
+        cudaEvent_t a = nullptr, b = nullptr;
+        EvPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+        ~EvPair() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    } ev_total;
+    const cudaEvent_t ev_begin = ev_total.a, ev_end = ev_total.b;
     cudaEventRecord(ev_begin, c->st);
     struct Seg { cudaEvent_t a, b; int kind; };
     std::vector<Seg> segs;
@@ -1455,8 +1458,6 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     flush_segs();
     float total_ms = 0;
     cudaEventElapsedTime(&total_ms, ev_begin, ev_end);
-    cudaEventDestroy(ev_begin);
-    cudaEventDestroy(ev_end);
     CU(cudaGetLastError());
     if (res) {
         memset(res, 0, sizeof(*res));
