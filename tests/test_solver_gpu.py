@@ -217,7 +217,7 @@ def test_time_slabs_with_fused_transpose_pack(gpu, world, xchg, monkeypatch):
     import dotsocp_b200 as dp
     monkeypatch.setenv("DOTSOCP_XCHG", xchg)
     from dotsocp_b200 import driver, solver
-    nt, nx, ny = 9, 129, 12
+    nt, nx, ny = (33 if world == 2 else 9), 129, 12    # 16 levels per slab: all 8 pipeline groups of the transposes are used
     rng = np.random.default_rng(5)
     rho0 = np.abs(rng.standard_normal((ny, nx))) + 0.1
     rho1 = np.abs(rng.standard_normal((ny, nx))) + 0.1
