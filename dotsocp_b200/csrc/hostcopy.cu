@@ -107,9 +107,15 @@ HostCopier::~HostCopier()
 
 HostCopier* HostCopier::get()
 {
-    // deliberately never destroyed: at process exit the CUDA context may already be gone
-    static HostCopier* inst = new HostCopier();
-    return inst;
+    // one instance per device (its events belong to that device's context); deliberately never destroyed: at process
+    // exit the CUDA context may already be gone
+    static std::mutex mu;
+    static HostCopier* inst[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); dev = 0; }
+    std::lock_guard<std::mutex> lk(mu);
+    if (!inst[dev]) inst[dev] = new HostCopier();
+    return inst[dev];
 }
 
 void HostCopier::par_memcpy(char* dst, const char* src, size_t bytes)

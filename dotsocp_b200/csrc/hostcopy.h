@@ -38,7 +38,8 @@ private:
 
 class HostCopier {
 public:
-    // process-wide instance (created on first use; pinned ring + thread pool are reused by every session)
+    // per-device instance of the calling thread's current device (created on first use; pinned ring + thread pool are
+    // reused by every session on that device)
     static HostCopier* get();
     // both return a cudaError_t-compatible code (0 = ok); `st` orders the transfer against the caller's other work and is
     // synchronised before d2h returns (h2d returns once the last chunk has been queued and its staging buffer may be reused
