@@ -46,6 +46,12 @@ class LevelResult(C.Structure):
     ]
 
 
+class ProlongScal(C.Structure):
+    _fields_ = [("phi_recover", C.c_double), ("beta_recover", C.c_double),
+                ("grad_t", C.c_double), ("grad_x", C.c_double), ("grad_y", C.c_double),
+                ("phi_scale", C.c_double), ("q_scale", C.c_double), ("alpha_scale", C.c_double), ("beta_scale", C.c_double)]
+
+
 class Hist(C.Structure):
     _fields_ = [
         ("cap", C.c_int32), ("kkt", C.c_void_p), ("time", C.c_void_p), ("iter", C.c_void_p),
@@ -58,7 +64,7 @@ EXPORTS = [
     "dotsocp_mexBFd", "dotsocp_mexBFdConj", "dotsocp_mexProjSoc", "dotsocp_mexBFd1d", "dotsocp_mexBFdConj1d",
     "dotsocp_poisson", "dotsocp_dctn", "dotsocp_solve_level",
     "dotsocp_nccl_unique_id", "dotsocp_create", "dotsocp_destroy", "dotsocp_upload", "dotsocp_download",
-    "dotsocp_run", "dotsocp_iter_begin", "dotsocp_iterate", "dotsocp_iter_end", "dotsocp_launch_count",
+    "dotsocp_prolong", "dotsocp_run", "dotsocp_iter_begin", "dotsocp_iterate", "dotsocp_iter_end", "dotsocp_launch_count",
 ]
 
 _lib = None
@@ -92,6 +98,7 @@ def lib():
     L.dotsocp_destroy.restype = None
     L.dotsocp_upload.argtypes = [P, P, P, P, P, P, P, P]
     L.dotsocp_download.argtypes = [P, P, P, P, P, P]
+    L.dotsocp_prolong.argtypes = [P, P, C.POINTER(ProlongScal), P, P, P]
     L.dotsocp_run.argtypes = [P, C.POINTER(LevelOpts), C.POINTER(Hist), C.POINTER(LevelResult)]
     L.dotsocp_iter_begin.argtypes = [P, C.POINTER(LevelOpts)]
     L.dotsocp_iterate.argtypes = [P, I, I, C.POINTER(C.c_float), C.POINTER(C.c_float)]

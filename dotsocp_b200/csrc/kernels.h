@@ -82,6 +82,15 @@ void launch_kkt_nodes(const KktArgs& a, bool weighted, cudaStream_t st);
 int  sumsq_blocks(i64 n);
 void launch_sumsq(const double* x, i64 n, double* partial, double* out, cudaStream_t st);
 // x = (x * mul) / div, elementwise (mul == 1 and div == 1 are exact no-ops)
+// level transfer on the device (prolong.cu): coarse (phi, beta) of a finished level -> fine (phi, q, alpha, beta) of the next,
+// with the recoverOrgVar / InitialScaling factors folded in exactly where the host path rounds them
+struct ProlongScal {
+    double phi_recover, beta_recover;   // dScale, cScale*E of the coarse level (recoverOrgVar)
+    double grad_t, grad_x, grad_y;      // unscaled forward-difference weights of the fine grid: 1/ht, 1/hx, 1/hy
+    double phi_scale, q_scale, alpha_scale, beta_scale;   // 1/dScale, D/dScale, 1/cScale/D, 1/cScale/E of the fine level
+};
+int launch_prolong(const Geo& gc, const Geo& gf, const ProlongScal& s, const double* phi_c, const double* beta_c, double* phi_f,
+                   double* q_f, double* alpha_f, double* beta_f, const double* weight_f, cudaStream_t st);
 void launch_scale(double* x, i64 n, double mul, double div, cudaStream_t st);
 // Halpern / affine extrapolation of solver_socp_accADMM.m:371-388:
 //   x = c1*x0 + c2*((1-rho)*xold + rho*x) ; xold = x ; if (copy_anchor) x0 = x

@@ -838,6 +838,48 @@ extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q
     return DOTSOCP_OK;
 }
 
+// Level transfer on the device: recoverOrgVar + interpolate + jump_nextLevel + InitialScaling of
+// solver_dotsocp2d.m:230-250 without the state ever leaving HBM.  `coarse` holds the output state of a finished level
+// (after dotsocp_run), `fine` is a fresh session of the refined grid (2n-1 nodes per refined axis); afterwards `fine` is
+// in the state dotsocp_upload would have left it in (z = 0).  Single-slab sessions only.
+extern "C" int dotsocp_prolong(dotsocp_ctx* coarse, dotsocp_ctx* fine, const dotsocp_prolong_scal* ps, const double* c_first,
+                               const double* c_last, const double* weight)
+{
+    if (!coarse || !fine || !ps || !c_first || !c_last) return set_err(DOTSOCP_EINVAL, "NULL argument");
+    if (coarse->world != 1 || fine->world != 1) return set_err(DOTSOCP_EINVAL, "prolong: single-slab sessions only");
+    if (coarse->variant != fine->variant) return set_err(DOTSOCP_EINVAL, "prolong: variants differ");
+    if (!coarse->uploaded || !coarse->z_materialised || coarse->iter_open)
+        return set_err(DOTSOCP_ESTATE, "prolong: the coarse session must hold the output state of a finished run");
+    const Geo &gc = coarse->g, &gf = fine->g;
+    if (gf.nt != 2 * gc.nt - 1 || gf.nx != 2 * gc.nx - 1 || gf.ny != (gc.ny > 1 ? 2 * gc.ny - 1 : 1))
+        return set_err(DOTSOCP_EINVAL, "prolong: the fine grid must have 2n-1 nodes per axis (%d,%d,%d) -> (%d,%d,%d)", gc.nt, gc.nx,
+                       gc.ny, gf.nt, gf.nx, gf.ny);
+    if (fine->weighted && !weight) return set_err(DOTSOCP_EINVAL, "weighted variant needs weight");
+    Slab* sc = coarse->slabs[0];
+    Slab* sf = fine->slabs[0];
+    fine->qcur = 0;
+    fine->bcur = 0;
+    int rc;
+    if (fine->weighted) {
+        HostMap hm{false, &gf, sf->tr};
+        if ((rc = copy_stag(fine, sf, hm, sf->weight, const_cast<double*>(weight), true))) return rc;
+    }
+    CU(cudaMemcpyAsync(sf->c0, c_first, gf.P * sizeof(double), cudaMemcpyHostToDevice, fine->st));
+    CU(cudaMemcpyAsync(sf->c1, c_last, gf.P * sizeof(double), cudaMemcpyHostToDevice, fine->st));
+    CU(cudaStreamSynchronize(coarse->st));   // the coarse state is final
+    ProlongScal k{ps->phi_recover, ps->beta_recover, ps->grad_t, ps->grad_x, ps->grad_y,
+                  ps->phi_scale, ps->q_scale, ps->alpha_scale, ps->beta_scale};
+    fine->launches += launch_prolong(gc, gf, k, sc->phi, sc->beta[coarse->bcur], sf->phi, sf->q[0], sf->alpha, sf->beta[0],
+                                     fine->weighted ? sf->weight : nullptr, fine->st);
+    CU(cudaMemsetAsync(sf->beta[1], 0, (size_t)10 * gf.L * sizeof(double), fine->st));   // z = 0 (jump_nextLevel.m:9)
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(fine->st));
+    fine->z_materialised = true;
+    fine->z_absent = false;
+    fine->uploaded = true;
+    return DOTSOCP_OK;
+}
+
 extern "C" int dotsocp_download(dotsocp_ctx* c, double* phi, double* q, double* z, double* alpha, double* beta)
 {
     if (!c) return set_err(DOTSOCP_EINVAL, "NULL ctx");

@@ -67,20 +67,22 @@ def normL2(x, h):
     return math.sqrt(h) * float(np.linalg.norm(np.ravel(x, order="K")))
 
 
-def InitialScaling(var, model, scalingYes, lastLevelKKT, variant):
-    """solver_dotsocp2d.m:304-365 ; solver_wdotsocp2d.m:297-342 ; solver_dotsocp1d.m:263-313"""
-    h = 1 / var.phi.size
+def scaling_scalars(N, model, scalingYes, lastLevelKKT, E2_prev, variant):
+    """The scalar half of InitialScaling (solver_dotsocp2d.m:304-336 ; solver_wdotsocp2d.m:297-320 ; solver_dotsocp1d.m
+    :263-290): returns (cScale, dScale, D, E, Escale2) and rescales model.c / model.grad / model.normc / model.normd.
+    Needs only host scalars, model.c and the weight, so the resident multilevel path can run it before the state exists."""
+    h = 1 / N
     hMean = h ** (1 / 2) if variant == "dot1d" else h ** (1 / 3)
-    if lastLevelKKT is None or not hasattr(var, "E2"):
+    if lastLevelKKT is None or E2_prev is None:
         Escale2 = math.sqrt(2)
     elif variant == "wdot2d":
-        Escale2 = var.E2 * min(4, max(1 / 4, math.sqrt(lastLevelKKT[0] / lastLevelKKT[1])))
+        Escale2 = E2_prev * min(4, max(1 / 4, math.sqrt(lastLevelKKT[0] / lastLevelKKT[1])))
     else:
         ratio = math.sqrt(lastLevelKKT[0] / lastLevelKKT[1])
         if ratio < 0.8333:
-            Escale2 = var.E2 * max(1 / math.sqrt(2), ratio / 0.8333)
+            Escale2 = E2_prev * max(1 / math.sqrt(2), ratio / 0.8333)
         else:
-            Escale2 = var.E2 * min(math.sqrt(2), max(1, ratio))
+            Escale2 = E2_prev * min(math.sqrt(2), max(1, ratio))
     if scalingYes:
         norm_c = normL2(model.c, h) * math.sqrt(model.nt)
         norm_d = math.sqrt(2)
@@ -99,15 +101,23 @@ def InitialScaling(var, model, scalingYes, lastLevelKKT, variant):
         model.normd = norm_d * E / dScale
         model.c = (1.0 / cScale) * model.c if variant == "dot2d" else model.c / cScale
         model.grad = tuple(D * g for g in model.grad)
+    else:
+        cScale = dScale = D = E = 1
+        model.normc = normL2(model.c, h)
+        model.normd = math.sqrt(2)
+    return cScale, dScale, D, E, Escale2
+
+
+def InitialScaling(var, model, scalingYes, lastLevelKKT, variant):
+    """solver_dotsocp2d.m:304-365 ; solver_wdotsocp2d.m:297-342 ; solver_dotsocp1d.m:263-313"""
+    cScale, dScale, D, E, Escale2 = scaling_scalars(var.phi.size, model, scalingYes, lastLevelKKT, getattr(var, "E2", None),
+                                                    variant)
+    if scalingYes:
         var.phi = (1 / dScale) * var.phi
         var.q = (D / dScale) * var.q
         var.z = (E / dScale) * var.z
         var.alpha = (1 / cScale / D) * var.alpha
         var.beta = (1 / cScale / E) * var.beta
-    else:
-        cScale = dScale = D = E = 1
-        model.normc = normL2(model.c, h)
-        model.normd = math.sqrt(2)
     var.cScale, var.dScale, var.D, var.E, var.E2 = cScale, dScale, D, E, Escale2
 
 
@@ -428,6 +438,11 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
     runHist = None
     level_iters, launches = [], 0.0
     sigma = optsML["sigma"]
+    resident = bool(optsML.pop("resident", False))
+    opts.pop("resident", None)
+    if resident:
+        return _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model, rho0s, rho1s, nts, tols, weights,
+                                    timeML, ML, clk)
     for level in range(levelN):
         InitialScaling(var, model, scalingYes, lastLevelKKT, variant)
         o2 = dict(optsML)
@@ -459,6 +474,72 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
     output.massOK, output.sumRho, output.sumNegRho = check_massConservation(output.rho, 1e-2)
     output.var, output.model, output.level_iters, output.sigma, output.gpu_launches = var, model, level_iters, sigma, launches
     timeML[levelN] = {"ML_Time": time.perf_counter() - clk}
+    return output, timeML, ML, runHist
+
+
+def _finish_output(variant, var, model, level_iters, sigma, launches, timeML, levelN, clk):
+    output = SimpleNamespace()
+    if variant == "dot1d":
+        output.rho, output.Ex = recover_RhoE(var, model)
+        output.q0, output.bx = recover_q(var, model)
+    else:
+        output.rho, output.Ex, output.Ey = recover_RhoE(var, model)
+        output.q0, output.bx, output.by = recover_q(var, model)
+    output.massOK, output.sumRho, output.sumNegRho = check_massConservation(output.rho, 1e-2)
+    output.var, output.model, output.level_iters, output.sigma, output.gpu_launches = var, model, level_iters, sigma, launches
+    timeML[levelN] = {"ML_Time": time.perf_counter() - clk}
+    return output
+
+
+def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model, rho0s, rho1s, nts, tols, weights, timeML, ML,
+                         clk):
+    """The same multilevel loop with the state resident in HBM between levels (opts["resident"] = True): the transitions
+    of solver_dotsocp2d.m:230-250 run on the device (dotsocp_prolong) instead of download -> host -> upload, and only the
+    last level is downloaded.  Bit-identical to the host-transition path (tests/test_solver_gpu.py)."""
+    weighted = variant == "wdot2d"
+    InitialScaling(var, model, scalingYes, None, variant)          # coarsest level: host arrays, as the reference
+    sess = S.Session(variant, model.nt, model.nx, model.ny)
+    mname = "inPALM" if method in ("inPALM", "ALG2") else method
+    z_dead = mname == "inPALM" and int(optsML["maxit"]) >= 1
+    sess.upload(var.phi, var.q, None if z_dead else var.z, var.alpha, var.beta, model.c, model.weight if weighted else None)
+    level_iters, launches, runHist, sigma = [], 0.0, None, optsML["sigma"]
+    try:
+        for level in range(levelN):
+            o2 = dict(optsML)
+            o2["tol"] = tols[level]
+            lo = S.make_level_opts(variant, mname, var, o2, model)
+            hb, res = sess.run(lo)
+            runHist, sigma = S._finish(var, lo.method, hb, res)      # var.cScale/dScale/D/E after in-loop rescaling, var.time
+            timeML[level] = var.time
+            level_iters.append(var.time["Iters"])
+            launches += var.gpu_launches
+            _cat_hist(ML, runHist)
+            if level == levelN - 1:
+                break
+            optsML["time_limit"] = optsML["time_limit"] - var.time["Total_Time"]
+            optsML["sigma"] = 10 ** (math.log10(optsML["sigma"] * sigma) / 2)
+            var_f, model_f = initialize(rho0s[level + 1], rho1s[level + 1], nts[level + 1])
+            if weighted:
+                model_f.weight = weights[level + 1]
+            gt, gx, gy = model_f.grad                               # unscaled 1/ht, 1/hx, 1/hy
+            cS, dS, D, E, E2 = scaling_scalars(var_f.phi.size, model_f, scalingYes, runHist.kkt[-1, :], var.E2, variant)
+            scal = dict(phi_recover=var.dScale, beta_recover=var.cScale * var.E, grad_t=gt, grad_x=gx, grad_y=gy,
+                        phi_scale=1 / dS, q_scale=D / dS, alpha_scale=1 / cS / D, beta_scale=1 / cS / E)
+            fine = S.Session(variant, model_f.nt, model_f.nx, model_f.ny)
+            try:
+                fine.prolong_from(sess, scal, model_f.c, model_f.weight if weighted else None)
+            except Exception:
+                fine.close()
+                raise
+            sess.close()
+            sess = fine
+            var = SimpleNamespace(qInd=var_f.qInd, cScale=cS, dScale=dS, D=D, E=E, E2=E2)
+            model = model_f
+        var.phi, var.q, var.z, var.alpha, var.beta = sess.download()
+    finally:
+        sess.close()
+    recoverOrgVar(var)
+    output = _finish_output(variant, var, model, level_iters, sigma, launches, timeML, levelN, clk)
     return output, timeML, ML, runHist
 
 

@@ -19,7 +19,7 @@ from types import SimpleNamespace
 
 import numpy as np
 
-from ._lib import METHOD, VARIANT, HistBuffers, LevelOpts, LevelResult, check, lib, ptr
+from ._lib import METHOD, VARIANT, HistBuffers, LevelOpts, LevelResult, ProlongScal, check, lib, ptr
 
 TIME_NAMES = {
     0: ["Step_1_1_FFT", "Step_1_2_ProjSOC", "Step_2_Q_Step", "Step_3_Multiplier", "KKT", "Total_Time"],
@@ -144,6 +144,18 @@ class Session:
             beta = np.empty((self.L, self.ncol), order="F")
         check(lib().dotsocp_download(self._h, ptr(phi), ptr(q), ptr(z), ptr(alpha), ptr(beta)))
         return phi, q, z, alpha, beta
+
+    def prolong_from(self, coarse, scal, c, weight=None):
+        """Level transfer on the device (dotsocp_prolong): fill this fresh session of the refined grid from the finished
+        `coarse` session.  scal: dict of the ProlongScal fields; c: the fine model.c (already divided by cScale)."""
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        assert c.size == self.N
+        P = self.nx * self.ny
+        first, last = np.ascontiguousarray(c[:P]), np.ascontiguousarray(c[-P:])
+        assert not c[P:-P].any(), "model.c has a non-zero interior entry: unsupported"
+        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        ps = ProlongScal(**{k: float(v) for k, v in scal.items()})
+        check(lib().dotsocp_prolong(coarse._h, self._h, C.byref(ps), ptr(first), ptr(last), ptr(w)))
 
     def run(self, level_opts):
         hb = HistBuffers(level_opts.maxit)

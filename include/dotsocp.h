@@ -142,6 +142,24 @@ void dotsocp_destroy(dotsocp_ctx *ctx);
 int  dotsocp_upload(dotsocp_ctx *ctx, const double *phi, const double *q, const double *z,
                     const double *alpha, const double *beta, const double *c, const double *weight);
 int  dotsocp_download(dotsocp_ctx *ctx, double *phi, double *q, double *z, double *alpha, double *beta);
+/* Level transfer of the multilevel drivers with the state resident in HBM: what solver_dotsocp2d.m:230-250 does between two
+ * levels -- recoverOrgVar (:368-386), interpolate (utils/interpolate.m:46-84), jump_nextLevel (utils/jump_nextLevel.m:5-16:
+ * z = 0, q = A phi, alpha = (BF)^*(-beta)), InitialScaling (:304-365) -- from the finished coarse session into a fresh
+ * session of the refined grid (2n-1 nodes per refined axis).  The scalars are the ones the driver computes on the host;
+ * every value is rounded exactly where the host path rounds it.  c_first / c_last: the two non-zero planes of the fine
+ * model.c (nx*ny doubles each, already divided by cScale); weight: fine weight (Q doubles) for WDOT2D, else NULL.
+ * Single-GPU sessions only.                                                                                            */
+typedef struct dotsocp_prolong_scal {
+    double phi_recover;             /* coarse var.dScale                 (var.phi  = dScale * var.phi)             */
+    double beta_recover;            /* coarse var.cScale * var.E         (var.beta = (cScale*E) * var.beta)        */
+    double grad_t, grad_x, grad_y;  /* fine, UNSCALED: 1/ht, 1/hx, 1/hy  (initialize.m:67-87)                      */
+    double phi_scale;               /* fine 1/dScale                                                               */
+    double q_scale;                 /* fine D/dScale                                                               */
+    double alpha_scale;             /* fine 1/cScale/D                                                             */
+    double beta_scale;              /* fine 1/cScale/E                                                             */
+} dotsocp_prolong_scal;
+int  dotsocp_prolong(dotsocp_ctx *coarse, dotsocp_ctx *fine, const dotsocp_prolong_scal *s,
+                     const double *c_first, const double *c_last, const double *weight);
 /* the reference loop on the resident state (sigma folding at entry, un-folding at exit, like :102-104, :335-336) */
 int  dotsocp_run(dotsocp_ctx *ctx, const dotsocp_level_opts *opts, dotsocp_hist *hist, dotsocp_level_result *res);
 /* benchmark primitive: begin (sigma folding + prologue), n plain iterations (no KKT), elapsed device ms */

@@ -343,3 +343,39 @@ def test_inpalm_never_reads_the_incoming_z(gpu):
             s.run(solver.make_level_opts("dot2d", "acc-ADMM", var, opts, model))
         hb, res = s.run(o)                                # inPALM is fine
         assert np.array_equal(hb.kkt[:res.hist_len], states[0][0])
+
+
+@pytest.mark.parametrize("case", ["dot2d-inPALM", "dot2d-accADMM", "wdot2d-inPALM", "dot1d-inPALM", "dot2d-noscaling"])
+def test_resident_multilevel_transitions_match_host_transitions(gpu, case):
+    """opts["resident"]: recoverOrgVar + interpolate + jump_nextLevel + InitialScaling run on the device (dotsocp_prolong)
+    and only the last level is downloaded.  Every value is rounded where the host path rounds it, so the two solves agree
+    bit for bit: same iteration counts, same KKT history, same iterates."""
+    import dotsocp_b200 as dp
+    if case.startswith("dot1d"):
+        rho0, rho1 = O.get_example1d("gaussian", 257)
+        run = lambda o: dp.solver_dotsocp1d(rho0, rho1, 17, 3, o, "inPALM")
+        opts = {"tol": 1e-5, "maxit": 3000}
+    elif case.startswith("wdot2d"):
+        n, nt = 33, 17
+        rho0, rho1 = O.get_example2d("example1", n, n)
+        opts = {"tol": 1e-3, "maxit": 10000, "weight": O.gene_weight_circle(nt, n, n)}
+        run = lambda o: dp.solver_wdotsocp2d(rho0, rho1, nt, 2, o, "inPALM")
+    else:
+        n, nt = 65, 33
+        rho0, rho1 = O.get_example2d("example2", n, n)
+        opts = {"tol": 1e-4, "maxit": 3000}
+        if case.endswith("noscaling"):
+            opts["scaling"] = False
+        method = "acc-ADMM" if case.endswith("accADMM") else "inPALM"
+        levels = 2 if case.endswith("accADMM") else 3
+        run = lambda o: dp.solver_dotsocp2d(rho0, rho1, nt, levels, o, method)
+    out_h, _, ML_h, rh_h = run(dict(opts))
+    out_r, _, ML_r, rh_r = run(dict(opts, resident=True))
+    assert [int(v) for v in out_r.level_iters] == [int(v) for v in out_h.level_iters]
+    assert ML_r.len == ML_h.len and np.array_equal(ML_r.iter, ML_h.iter)
+    assert np.abs(ML_r.kkt - ML_h.kkt).max() <= 1e-13, np.abs(ML_r.kkt - ML_h.kkt).max()
+    for name in ("phi", "q", "z", "alpha", "beta"):
+        a, b = np.asarray(getattr(out_r.var, name)), np.asarray(getattr(out_h.var, name))
+        assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max()), (name, np.abs(a - b).max())
+    assert np.abs(out_r.rho - out_h.rho).max() <= 1e-12 * np.abs(out_h.rho).max()
+    assert out_r.sigma == pytest.approx(out_h.sigma, rel=1e-13)
