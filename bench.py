@@ -395,6 +395,23 @@ def main():
                "final_kkt_max": float(np.max(hb3.kkt[r3.hist_len - 1][[0, 2, 5, 6]])),
                "objective": float(hb3.priVal[r3.hist_len - 1]),
                "device_seconds_by_step": {"FFT": r3.times[0], "Q_Step": r3.times[2], "ProjSOC+Multiplier": r3.times[3], "KKT": r3.times[4]}}
+        # whole multilevel solve (solver_dotsocp2d, 3 levels up to the same grid, reference defaults) through the driver mirror:
+        # transitions on the device (state resident in HBM, only the last level downloaded) against download/host/upload
+        if world == 1:
+            xs = np.linspace(0, 1, tnx).reshape(1, tnx)
+            ys = np.linspace(0, 1, tny).reshape(tny, 1)
+            r0 = np.exp(-0.5 * ((xs - 0.25) ** 2 + (ys - 0.75) ** 2) / 0.05)    # (ny, nx), gene_example1.m
+            r1 = np.exp(-0.5 * ((xs - 0.75) ** 2 + (ys - 0.25) ** 2) / 0.05)
+            r0 *= r0.size / r0.sum()
+            r1 *= r1.size / r1.sum()
+            ml = {}
+            for mode in ("resident", "host"):
+                t0 = time.perf_counter()
+                out_ml, _, ML_ml, _ = dp.solver_dotsocp2d(r0, r1, tnt, 3, {"tol": 1e-4, "maxit": 3000, "resident": mode == "resident"},
+                                                          "inPALM")
+                ml[mode] = {"seconds": time.perf_counter() - t0, "level_iters": [int(v) for v in out_ml.level_iters],
+                            "final_kkt_max": float(np.max(ML_ml.kkt[-1][[0, 2, 5, 6]]))}
+            ttt["multilevel_3_levels"] = ml
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
