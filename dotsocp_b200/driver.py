@@ -438,7 +438,9 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
     runHist = None
     level_iters, launches = [], 0.0
     sigma = optsML["sigma"]
-    resident = bool(optsML.pop("resident", False))
+    # state resident in HBM between levels (device-side transitions) unless opts["resident"] = False asks for the
+    # reference-shaped download -> host transfer -> upload loop; both give the same bits
+    resident = bool(optsML.pop("resident", True))
     opts.pop("resident", None)
     if resident:
         return _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model, rho0s, rho1s, nts, tols, weights,
@@ -493,7 +495,8 @@ def _finish_output(variant, var, model, level_iters, sigma, launches, timeML, le
 
 def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model, rho0s, rho1s, nts, tols, weights, timeML, ML,
                          clk):
-    """The same multilevel loop with the state resident in HBM between levels (opts["resident"] = True): the transitions
+    """The same multilevel loop with the state resident in HBM between levels (the default; opts["resident"] = False selects
+    the host-transition loop): the transitions
     of solver_dotsocp2d.m:230-250 run on the device (dotsocp_prolong) instead of download -> host -> upload, and only the
     last level is downloaded.  Bit-identical to the host-transition path (tests/test_solver_gpu.py)."""
     weighted = variant == "wdot2d"

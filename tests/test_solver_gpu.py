@@ -347,8 +347,8 @@ def test_inpalm_never_reads_the_incoming_z(gpu):
 
 @pytest.mark.parametrize("case", ["dot2d-inPALM", "dot2d-accADMM", "wdot2d-inPALM", "dot1d-inPALM", "dot2d-noscaling"])
 def test_resident_multilevel_transitions_match_host_transitions(gpu, case):
-    """opts["resident"]: recoverOrgVar + interpolate + jump_nextLevel + InitialScaling run on the device (dotsocp_prolong)
-    and only the last level is downloaded.  Every value is rounded where the host path rounds it, so the two solves agree
+    """opts["resident"] (the default): recoverOrgVar + interpolate + jump_nextLevel + InitialScaling run on the device
+    (dotsocp_prolong) and only the last level is downloaded; resident=False is the download -> host -> upload loop.  Every value is rounded where the host path rounds it, so the two solves agree
     bit for bit: same iteration counts, same KKT history, same iterates."""
     import dotsocp_b200 as dp
     if case.startswith("dot1d"):
@@ -369,7 +369,7 @@ def test_resident_multilevel_transitions_match_host_transitions(gpu, case):
         method = "acc-ADMM" if case.endswith("accADMM") else "inPALM"
         levels = 2 if case.endswith("accADMM") else 3
         run = lambda o: dp.solver_dotsocp2d(rho0, rho1, nt, levels, o, method)
-    out_h, _, ML_h, rh_h = run(dict(opts))
+    out_h, _, ML_h, rh_h = run(dict(opts, resident=False))
     out_r, _, ML_r, rh_r = run(dict(opts, resident=True))
     assert [int(v) for v in out_r.level_iters] == [int(v) for v in out_h.level_iters]
     assert ML_r.len == ML_h.len and np.array_equal(ML_r.iter, ML_h.iter)
