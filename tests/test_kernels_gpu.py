@@ -107,7 +107,10 @@ def test_1d_kernels_bit_exact(gpu, nt, nx):
 
 
 DCT_GRIDS = [(5, 9, 9), (9, 17, 17), (17, 33, 33), (33, 65, 65), (7, 12, 20), (40, 50, 70), (3, 129, 5), (65, 7, 257),
-             (2, 300, 3), (33, 1, 1)]
+             (2, 300, 3), (33, 1, 1),
+             # the line lengths of the BASELINE grids (257, 513, 1025 and the next one), along x and along y: every
+             # instantiation of the register-FFT kernel (M = 512 ... 4096) in both of its line layouts
+             (4, 257, 6), (3, 513, 4), (2, 1025, 3), (3, 5, 513), (2, 3, 1025), (2, 2049, 2)]
 
 
 @pytest.mark.parametrize("nt,nx,ny", DCT_GRIDS)
