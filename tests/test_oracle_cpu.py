@@ -197,3 +197,20 @@ def test_closed_form_sanity_1d_gaussian():
     discrete objective on the demo grid is 0.0786 -- coarse grid here, loose band."""
     c = [c for c in SOLVER_GOLD if c["name"].startswith("dot1d")][0]
     assert 0.06 < c["priVal"] < 0.085
+
+
+def test_oracle_reproduces_the_survey_probe_of_the_1d_demo():
+    """demo_dot1d.m defaults (nt = 33, nx = 1025, 3 levels, tol 1e-5): the structural survey of the reference recorded
+    2809 / 1489 / 849 iterations per level for this instance; the committed
+    golden of BASELINE configs[0] must be that run."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "solver_baseline_configs.json")) as f:
+        gold = json.load(f)["dot1d_demo_default"]
+    assert gold["level_iters"] == [2809, 1489, 849]
+    rho0, rho1 = O.get_example1d("gaussian", 1025)
+    out, _, ML, rh = O.solver_dotsocp1d(rho0, rho1, 33, 3, {"tol": 1e-5, "maxit": 3000}, "inPALM")
+    assert [int(v) for v in out.level_iters] == gold["level_iters"]
+    assert np.abs(ML.kkt - np.array(gold["kkt"])).max() < 1e-12
+    assert abs(rh.priVal[-1] - gold["priVal"]) <= 1e-12 * abs(gold["priVal"])
