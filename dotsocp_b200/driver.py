@@ -121,14 +121,27 @@ def InitialScaling(var, model, scalingYes, lastLevelKKT, variant):
     var.cScale, var.dScale, var.D, var.E, var.E2 = cScale, dScale, D, E, Escale2
 
 
-def recoverOrgVar(var):
-    """solver_dotsocp2d.m:368-386"""
+def _scaled(a, s, inplace):
+    """s * a ; inplace: overwrite a (chunks on a few threads -- numpy releases the GIL inside the multiply), same bits"""
+    if not inplace or a.size < (1 << 20) or not a.flags.writeable:
+        return s * a
+    from concurrent.futures import ThreadPoolExecutor
+    v = a.reshape(-1, order="A")
+    step = -(-v.size // 16)
+    with ThreadPoolExecutor(8) as ex:
+        list(ex.map(lambda i: np.multiply(v[i:i + step], s, out=v[i:i + step]), range(0, v.size, step)))
+    return a
+
+
+def recoverOrgVar(var, inplace=False):
+    """solver_dotsocp2d.m:368-386.  inplace=True (used by the multilevel drivers on the arrays they have just downloaded and
+    own) overwrites the arrays instead of allocating new ones."""
     cScale, dScale, D, E = var.cScale, var.dScale, var.D, var.E
-    var.phi = dScale * var.phi
-    var.z = (dScale / E) * var.z
-    var.q = (dScale / D) * var.q
-    var.alpha = (cScale * D) * var.alpha
-    var.beta = (cScale * E) * var.beta
+    var.phi = _scaled(var.phi, dScale, inplace)
+    var.z = _scaled(var.z, dScale / E, inplace)
+    var.q = _scaled(var.q, dScale / D, inplace)
+    var.alpha = _scaled(var.alpha, cScale * D, inplace)
+    var.beta = _scaled(var.beta, cScale * E, inplace)
 
 
 # ------------------------------------------------------------------------------------------------ level transfer
@@ -288,6 +301,21 @@ def ensure_barrier_validity(rho0, rho1, barrier):
 
 
 # ------------------------------------------------------------------------------------------------ output recovery
+def _pair_mean_padded(e, ax):
+    """zeros at both ends of `ax`, the means of adjacent pairs in between: (n) -> (n+1), written into one fresh array"""
+    shape = list(e.shape)
+    shape[ax] += 1
+    out = np.zeros(shape)
+    lo = [slice(None)] * e.ndim
+    hi = [slice(None)] * e.ndim
+    mid = [slice(None)] * e.ndim
+    lo[ax], hi[ax], mid[ax] = slice(0, -1), slice(1, None), slice(1, -1)
+    dst = out[tuple(mid)]
+    np.add(e[tuple(lo)], e[tuple(hi)], out=dst)
+    dst /= 2
+    return out
+
+
 def recover_RhoE(var, model):
     """socp/dot2d/utils/recover_RhoE.m:13-25 (wdot2d :11 multiplies alpha by the weight) ; dot1d :12-20.
     Returns C-order arrays (nt, nx, ny) [1-D: (nt, nx)]."""
@@ -300,19 +328,17 @@ def recover_RhoE(var, model):
     shp = (nx, ny) if model.dim == 2 else (nx,)
     r0 = model.rho0.T if model.dim == 2 else model.rho0
     r1 = model.rho1.T if model.dim == 2 else model.rho1
-    rho = alpha[:L].reshape((nt - 1,) + shp)
-    rho = np.concatenate([r0[None], (rho[:-1] + rho[1:]) / 2, r1[None]], axis=0)
+    a0 = alpha[:L].reshape((nt - 1,) + shp)
+    rho = np.empty((nt,) + shp)
+    rho[0], rho[-1] = r0, r1
+    np.add(a0[:-1], a0[1:], out=rho[1:-1])
+    rho[1:-1] /= 2
 
     def centre(e, ax):
-        e = e.copy()
-        e[[0, -1]] = 2 * e[[0, -1]]
-        zshape = list(e.shape)
-        zshape[ax] = 1
-        zz = np.zeros(zshape)
-        lo = [slice(None)] * e.ndim
-        hi = [slice(None)] * e.ndim
-        lo[ax], hi[ax] = slice(0, -1), slice(1, None)
-        return np.concatenate([zz, (e[tuple(lo)] + e[tuple(hi)]) / 2, zz], axis=ax)
+        e = e.copy()                      # first and last time level count twice (recover_RhoE.m:17-18)
+        e[0] *= 2
+        e[-1] *= 2
+        return _pair_mean_padded(e, ax)
     if model.dim == 2:
         Ex = centre(alpha[L:nb].reshape(nt, nx - 1, ny), 1)
         Ey = centre(alpha[nb:].reshape(nt, nx, ny - 1), 2)
@@ -328,14 +354,10 @@ def recover_q(var, model):
     nb = L + nt * (nx - 1) * ny
 
     def centre(e, ax):
-        zshape = list(e.shape)
-        zshape[ax] = 1
-        zz = np.zeros(zshape)
-        lo = [slice(None)] * e.ndim
-        hi = [slice(None)] * e.ndim
-        lo[ax], hi[ax] = slice(0, -1), slice(1, None)
-        e = np.concatenate([zz, (e[tuple(lo)] + e[tuple(hi)]) / 2, zz], axis=ax)
-        return (e[:-1] + e[1:]) / 2
+        e = _pair_mean_padded(e, ax)
+        out = e[:-1] + e[1:]
+        out /= 2
+        return out
     if model.dim == 2:
         return (q[:L].reshape(nt - 1, nx, ny), centre(q[L:nb].reshape(nt, nx - 1, ny), 1),
                 centre(q[nb:].reshape(nt, nx, ny - 1), 2))
@@ -455,7 +477,7 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
             runHist, sigma = (S.solver_wsocp_inPALM if variant == "wdot2d" else S.solver_socp_inPALM)(var, o2, model)
         else:
             runHist, sigma = (S.solver_wsocp_accADMM if variant == "wdot2d" else S.solver_socp_accADMM)(var, o2, model)
-        recoverOrgVar(var)
+        recoverOrgVar(var, inplace=True)          # the level solver returned freshly downloaded arrays
         timeML[level] = var.time
         level_iters.append(var.time["Iters"])
         launches += getattr(var, "gpu_launches", 0.0)
@@ -541,7 +563,7 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
         var.phi, var.q, var.z, var.alpha, var.beta = sess.download()
     finally:
         sess.close()
-    recoverOrgVar(var)
+    recoverOrgVar(var, inplace=True)
     output = _finish_output(variant, var, model, level_iters, sigma, launches, timeML, levelN, clk)
     return output, timeML, ML, runHist
 
