@@ -36,6 +36,9 @@ private:
     bool stop_ = false;
 };
 
+// memcpy with non-temporal stores (x86-64; plain memcpy elsewhere)
+void host_copy_streaming(char* dst, const char* src, size_t n);
+
 class HostCopier {
 public:
     // per-device instance of the calling thread's current device (created on first use; pinned ring + thread pool are

@@ -1,7 +1,9 @@
 // Host check of the worker pool behind the staged host<->device copies (dotsocp_b200/csrc/hostcopy.cu): every index is
 // visited exactly once, for many back-to-back jobs of varying size (generation / wake-up races), including n < threads.
 #include <atomic>
+#include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "hostcopy.h"
@@ -26,6 +28,21 @@ int main()
             }
             if (asum.load() != sum) { printf("threads %d job %d: sum mismatch\n", threads, job); return 1; }
         }
+    }
+    // streaming copy: every size / alignment combination around the vector and head/tail boundaries, and a large block
+    {
+        std::vector<char> src(1 << 22), dst(1 << 22), ref(1 << 22);
+        for (size_t i = 0; i < src.size(); i++) src[i] = (char)(i * 131 + 7);
+        const size_t sizes[] = {0, 1, 15, 16, 17, 63, 64, 65, 4095, 4096, 4097, 4111, 8191, 100003, (1 << 21) + 5};
+        for (size_t n : sizes)
+            for (int da = 0; da < 17; da += 4)
+                for (int sa = 0; sa < 17; sa += 5) {
+                    std::fill(dst.begin(), dst.end(), (char)0x55);
+                    ref = dst;
+                    memcpy(ref.data() + 64 + da, src.data() + 32 + sa, n);
+                    host_copy_streaming(dst.data() + 64 + da, src.data() + 32 + sa, n);
+                    if (dst != ref) { printf("streaming copy differs: n=%zu da=%d sa=%d\n", n, da, sa); return 1; }
+                }
     }
     printf("POOL_HOST_OK\n");
     return 0;
