@@ -29,12 +29,6 @@ def test_three_level_solve_at_256x256x128_matches_the_oracle_golden(gpu):
     assert abs(rh.priVal[-1] - gold["priVal"]) <= 1e-6 * abs(gold["priVal"])
 
 
-FIRST_HARDWARE_RUN = pytest.mark.xfail(
-    strict=False,
-    reason="golden generated on the CPU after this round's GPU budget was spent: the round-end suite is the first hardware run "
-           "of this case (an XPASS is the expected outcome)")
-
-
 def _load_cfg():
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_golden_baseline_configs",
@@ -58,7 +52,6 @@ def _check_against_golden(out, ML, rh, gold, dim):
 
 
 @pytest.mark.gpu
-@FIRST_HARDWARE_RUN
 def test_baseline_config0_dot1d_demo_defaults(gpu):
     """BASELINE.json configs[0]: demo_dot1d.m defaults (nt = 33, nx = 1025, 3 levels, tol 1e-5, Gaussian instance)."""
     import dotsocp_b200 as dp
@@ -69,7 +62,6 @@ def test_baseline_config0_dot1d_demo_defaults(gpu):
 
 
 @pytest.mark.gpu
-@FIRST_HARDWARE_RUN
 def test_baseline_config2_weighted_256x256x128(gpu):
     """BASELINE.json configs[2]: weighted 2-D DOT, circle weight, 256x256x128 cells, 3 levels, tol 1e-3."""
     import dotsocp_b200 as dp
