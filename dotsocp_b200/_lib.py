@@ -62,7 +62,7 @@ class Hist(C.Structure):
 EXPORTS = [
     "dotsocp_last_error", "dotsocp_version", "dotsocp_device_count", "dotsocp_set_device",
     "dotsocp_mexBFd", "dotsocp_mexBFdConj", "dotsocp_mexProjSoc", "dotsocp_mexBFd1d", "dotsocp_mexBFdConj1d",
-    "dotsocp_poisson", "dotsocp_dctn", "dotsocp_solve_level",
+    "dotsocp_poisson", "dotsocp_dctn", "dotsocp_solve_level", "dotsocp_release_cached",
     "dotsocp_nccl_unique_id", "dotsocp_create", "dotsocp_destroy", "dotsocp_upload", "dotsocp_download",
     "dotsocp_prolong", "dotsocp_run", "dotsocp_iter_begin", "dotsocp_iterate", "dotsocp_iter_end", "dotsocp_launch_count",
 ]
@@ -92,6 +92,8 @@ def lib():
     L.dotsocp_poisson.argtypes = [P, P, I, I, I, D]
     L.dotsocp_dctn.argtypes = [P, I, I, I, I]
     L.dotsocp_solve_level.argtypes = [C.POINTER(LevelOpts), P, P, P, P, P, P, P, C.POINTER(Hist), C.POINTER(LevelResult)]
+    L.dotsocp_release_cached.argtypes = []
+    L.dotsocp_release_cached.restype = None
     L.dotsocp_nccl_unique_id.argtypes = [P]
     L.dotsocp_create.argtypes = [C.POINTER(P), I, I, I, I, I, I, P]
     L.dotsocp_destroy.argtypes = [P]
@@ -117,7 +119,10 @@ def ptr(a):
     if a is None:
         return None
     assert isinstance(a, np.ndarray) and a.dtype == np.float64, "float64 ndarray expected"
-    assert a.flags.c_contiguous or a.flags.f_contiguous, "array must be contiguous"
+    if a.ndim >= 2 and min(a.shape) > 1:
+        assert a.flags.f_contiguous, "matrices cross the C ABI in column-major (MATLAB) order"
+    else:
+        assert a.flags.c_contiguous or a.flags.f_contiguous, "array must be contiguous"
     return a.ctypes.data
 
 

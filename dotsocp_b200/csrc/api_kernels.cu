@@ -109,10 +109,12 @@ static int dct_common(double* out, const double* in, int nt, int nx, int ny, int
     if ((rc = a.alloc(N)) || (rc = b.alloc(N))) return rc;
     CU(cudaMemcpy(a.p, in, (size_t)N * sizeof(double), cudaMemcpyHostToDevice));
     PoissonPlan* pp = poisson_plan_create(nt, nx, ny);
-    if (what == 2) poisson_solve(pp, a.p, b.p, D * D, 0, nullptr);
-    else { CU(cudaMemcpy(b.p, a.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice)); poisson_dctn(pp, b.p, what == 1, 0, nullptr); }
+    int prc = 0;
+    if (what == 2) prc = poisson_solve(pp, a.p, b.p, D * D, 0, nullptr);
+    else { CU(cudaMemcpy(b.p, a.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice)); prc = poisson_dctn(pp, b.p, what == 1, 0, nullptr); }
     cudaError_t e = cudaDeviceSynchronize();
     poisson_plan_destroy(pp);
+    if (prc) return prc;   // unsupported geometry: dotsocp_last_error() says which
     if (e != cudaSuccess) return set_err(DOTSOCP_ECUDA, "transform kernels: %s", cudaGetErrorString(e));
     CU(cudaGetLastError());
     CU(cudaMemcpy(out, b.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));

@@ -53,6 +53,9 @@ void WorkerPool::parallel_for(int n, const std::function<void(int)>& fn)
         for (int i = 0; i < n; i++) fn(i);
         return;
     }
+    // one job at a time: a second caller (another host thread driving its own session on this device) waits here
+    // instead of overwriting the shared job state
+    std::lock_guard<std::mutex> job(submit_mu_);
     std::unique_lock<std::mutex> lk(mu_);
     fn_ = &fn;
     n_ = n;

@@ -28,7 +28,7 @@ public:
 private:
     void worker();
     std::vector<std::thread> threads_;
-    std::mutex mu_;
+    std::mutex mu_, submit_mu_;   // submit_mu_ is held for the whole of a parallel_for (serialises concurrent callers)
     std::condition_variable cv_, done_cv_;
     const std::function<void(int)>* fn_ = nullptr;
     int n_ = 0, next_ = 0, pending_ = 0;

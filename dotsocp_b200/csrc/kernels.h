@@ -17,6 +17,7 @@ void launch_bfdconj_sum(const Geo& g, double S, const double* za, const double* 
 void launch_projsoc(i64 M, int N, const double* in, double* out, cudaStream_t st);
 
 // ---- fused iteration kernels --------------------------------------------------------------------------------
+struct KktFused;
 struct UpdateArgs {
     Geo g;
     TRange tr;
@@ -33,12 +34,13 @@ struct UpdateArgs {
     double* rhs;            // out: A'(w.*q - alpha) + c for the next Poisson solve
     const double* c0;       // c on the first time level (nx*ny)
     const double* c1;       // c on the last time level
+    int kkt_t0;             // first node level of the slab (row 0 of the fused KKT partials)
 };
 // q_new = ((A phi + alpha) + q2) .* diagQInv ; alpha += tau (A phi - q_new)      (solver_socp_inPALM.m:204-214)
 // acc: alpha = (alpha + A phi) - q_new                                            (solver_socp_accADMM.m:237)
 // tmpq_in != NULL: take A*phi from that buffer instead of phi; tmpq_out != NULL: also store A*phi; upd_alpha=false: q only
 void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st, const double* tmpq_in = nullptr,
-                  double* tmpq_out = nullptr, bool upd_alpha = true);
+                  double* tmpq_out = nullptr, bool upd_alpha = true, const KktFused* kkt = nullptr);
 void launch_rhs(const Geo& g, const IterScal& sc, bool weighted, const double* q, const double* alpha, const double* weight,
                 const double* c0, const double* c1, double* rhs, cudaStream_t st);
 // mode 0: beta += tau (z - z2(q)) ; mode 1: beta = (beta + z) - z2(q), z = Pi_Q(z2(q) - beta) ; mode 2: z = d + BF q
@@ -46,15 +48,26 @@ void launch_cells_update(const Geo& g, const IterScal& sc, bool one_d, int mode,
                          cudaStream_t st);
 // z = Pi_Q(d + BF q_old - beta) ; beta += tau (z - (d + BF q_new)) ; then q2, rhs of the next iteration.
 // update=false ("prologue"): no multiplier step, only q2/rhs from the current (q_new, alpha, beta).
-void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st);
-// z = Pi_Q(d + BF q_old - beta_old): optional store (zout may alias beta_old) and out[0] = sum z^2
+// kkt != NULL (update only): the launch also leaves the per-(time level, tile) partial sums of the KKT terms that live on
+// the data it streams anyway (see KktFused) -- a check then costs no extra pass over the 10-column arrays.
+void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st, const KktFused* kkt = nullptr);
+int  mult_tiles(const Geo& g);   // CTAs per time level of launch_mult (rows of its KKT partials)
+// z = Pi_Q(d + BF q_old - beta_old): optional store (zout may alias beta_old)
 void launch_zstep(const Geo& g, const IterScal& sc, bool one_d, const double* q_old, const double* beta_old, double* zout,
-                  double* partial, double* out, cudaStream_t st, const TRange* tr = nullptr);
+                  cudaStream_t st, const TRange* tr = nullptr);
 
 // ---- KKT / norms --------------------------------------------------------------------------------------------
+// All sums are reduced in three fixed-order stages so that the result does not depend on how the time axis is cut into
+// slabs (1, 2, 4 or 8 GPUs give the same bits): CTA partial -> one sum per TIME LEVEL (k_level_reduce: row t of the
+// level table, KSL slots per row) -> sum over the nt levels (k_levels_total).  Between the last two stages the rows owned
+// by other ranks arrive by an all-reduce of the table (every row has exactly one non-zero contributor, so it is exact).
 enum { KC_Z2 = 0, KC_BETA2, KC_PRIM2, KC_COMPL, KC_DOTC, KC_RHOT, KC_RHOFQ, KC_COUNT };
 enum { KN_Q2 = 0, KN_APHI2, KN_PRIM1, KN_ALPHA2, KN_FBB2, KN_DUAL2, KN_QDOTA, KN_MRHOB, KN_M2, KN_RHOB2,
        KN_DUAL1, KN_CPHI, KN_PHI2, KN_COUNT };
+constexpr int KSL = 24;                       // slots per level row: KC_* at 0.., KN_* at KC_COUNT.., then KS_*
+constexpr int KS_ELAPSED = KC_COUNT + KN_COUNT;   // host clock of slab 0 (row 0 only), so that all ranks decide alike
+// rescale norms (solver_socp_inPALM.m:140-143): one fused pass, slots 0..4 of a level row
+enum { NR_PHI2 = 0, NR_Q2, NR_Z2, NR_ALPHA2, NR_BETA2, NR_COUNT };
 struct KktArgs {
     Geo g;
     TRange tr;
@@ -71,16 +84,27 @@ struct KktArgs {
     const double* q2b;      // s (BF)^* beta (from launch_bfdconj)
     const double* c0;
     const double* c1;
-    double* partial;        // scratch: [nblocks][K]
-    double* out;            // [K] results (device)
+    double* partial;        // scratch: [level][block][K]
+    double* lvl;            // level table [nt][KSL] (device)
+};
+// fused KKT (inPALM check iterations): k_qstep leaves KQ_COUNT sums per (level, block), k_mult KM_COUNT per (level, tile)
+enum { KQ_Q2 = 0, KQ_APHI2, KQ_PRIM1, KQ_ALPHA2, KQ_QDOTA, KQ_CPHI, KQ_PHI2, KQ_COUNT };
+enum { KM_Z2 = 0, KM_BETA2, KM_PRIM2, KM_COMPL, KM_DOTC, KM_RHOT, KM_RHOFQ, KM_FBB2, KM_DUAL2, KM_DUAL1, KM_MRHOB, KM_M2,
+       KM_RHOB2, KM_COUNT };
+struct KktFused {
+    double sigma, cScale, dScale, D, E;
+    double* partial_q;      // [owned node levels][blocks_x][KQ_COUNT]
+    double* partial_m;      // [owned node levels][mult_tiles][KM_COUNT]
+    double* lvl;            // level table [nt][KSL]
 };
 int  kkt_cells_blocks(const Geo& g);
 int  kkt_nodes_blocks(const Geo& g);
-void launch_kkt_cells(const KktArgs& a, bool weighted, bool one_d, cudaStream_t st);
-void launch_kkt_nodes(const KktArgs& a, bool weighted, cudaStream_t st);
-// out[0] = sum x[i]^2 (deterministic two-stage reduction); partial needs sumsq_blocks(n) doubles
-int  sumsq_blocks(i64 n);
-void launch_sumsq(const double* x, i64 n, double* partial, double* out, cudaStream_t st);
+int  kkt_blocks_x(const Geo& g);
+void launch_kkt_cells(const KktArgs& a, bool weighted, bool one_d, cudaStream_t st);   // -> rows tc0..tc1-1, slots KC_*
+void launch_kkt_nodes(const KktArgs& a, bool weighted, cudaStream_t st);               // -> rows tn0..tn1-1, slots KC_COUNT + KN_*
+void launch_kkt_fused_reduce(const Geo& g, const TRange& tr, const KktFused& k, cudaStream_t st);   // partial_q / partial_m -> rows
+void launch_norms(const KktArgs& a, bool one_d, cudaStream_t st);                      // -> rows tn0..tn1-1, slots NR_*
+void launch_levels_total(const double* lvl, int nt, double* out, cudaStream_t st);     // out[KSL] = fixed-order sum over the rows
 // x = (x * mul) / div, elementwise (mul == 1 and div == 1 are exact no-ops)
 // level transfer on the device (prolong.cu): coarse (phi, beta) of a finished level -> fine (phi, q, alpha, beta) of the next,
 // with the recoverOrgVar / InitialScaling factors folded in exactly where the host path rounds them
@@ -123,17 +147,18 @@ struct PoissonPlan {
 };
 PoissonPlan* poisson_plan_create(int nt, int nx, int ny);
 void poisson_plan_destroy(PoissonPlan* p);
+// All poisson_* launchers return 0, or a negative DOTSOCP_E* code with dotsocp_last_error() set (unsupported geometry).
 // a <- idctn( dctn(rhs) ./ (D2 * kernel) ); rhs is only read (rhs == a is allowed)
-void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cudaStream_t st, double* launches);
+int  poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cudaStream_t st, double* launches);
 // time-slab pieces: forward (y then x) / inverse (x then y) transforms of node levels [tn0, tn0+nlev) of the global
 // array (src is only read; src == a allowed), and the t-pass on a transposed [nt][chunk] buffer of modes p0..p0+chunk-1
-void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev, bool inverse, cudaStream_t st, double* launches,
+int  poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev, bool inverse, cudaStream_t st, double* launches,
                 double* packed = nullptr, int world = 1, int slab_nlev = 0, int slab_t0 = 0, double* const* push_tab = nullptr);
 bool poisson_can_pack(const PoissonPlan* p);   // the x passes can read/write the packed all-to-all buffer themselves
 // push_tab / tcut (device tables, see Slab::d_bwd): store the solution in the buffers of the owners of the time levels
-void poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches,
+int  poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches,
                      double* const* push_tab = nullptr, const int* tcut = nullptr, int world = 1);
 // in-place orthonormal DCT-II (or inverse) along all axes
-void poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches);
+int  poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches);
 
 }  // namespace dsocp

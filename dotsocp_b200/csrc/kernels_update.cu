@@ -284,11 +284,12 @@ void launch_projsoc(i64 M, int N, const double* in, double* out, cudaStream_t st
 //   q     = ((tmp_q + alpha) + q2) .* diagQInv          | weighted: (w.*(tmp_q+alpha) + q2) .* diagQInv   :206 / wsocp :212
 //   alpha = alpha + tau*(tmp_q - w.*q)                  | acc-ADMM: (alpha + tmp_q) - w.*q                :211,214 / accADMM :237
 // ---------------------------------------------------------------------------------------------------------------
-template <bool WEIGHTED, bool ACC>
+template <bool WEIGHTED, bool ACC, bool KKT>
 __device__ __forceinline__ void q_update(i64 e, double aphi, double dinv_plain, double s2term, const IterScal& sc,
                                          const double* __restrict__ q2, const double* __restrict__ weight,
                                          double* __restrict__ alpha, double* __restrict__ qout,
-                                         const double* __restrict__ tmpq_in, double* __restrict__ tmpq_out, bool upd_alpha)
+                                         const double* __restrict__ tmpq_in, double* __restrict__ tmpq_out, bool upd_alpha,
+                                         double (&ks)[KQ_COUNT])
 {
     if (tmpq_in != nullptr) aphi = tmpq_in[e];      // PALM's first q-step re-uses the stored A*phi (solver_socp_PALM.m:198-199)
     if (tmpq_out != nullptr) tmpq_out[e] = aphi;
@@ -306,53 +307,83 @@ __device__ __forceinline__ void q_update(i64 e, double aphi, double dinv_plain, 
     }
     qout[e] = qn;
     if (!upd_alpha) return;
+    double an;
     if (ACC)
-        alpha[e] = dsub(dadd(a, aphi), wq);
+        an = dsub(dadd(a, aphi), wq);
     else
-        alpha[e] = dadd(a, dmul(sc.tau, dsub(aphi, wq)));
+        an = dadd(a, dmul(sc.tau, dsub(aphi, wq)));
+    alpha[e] = an;
+    if (KKT) {   // the terms of the check that live on this edge (solver_socp_inPALM.m:227-230,234,265)
+        ks[KQ_Q2] += qn * qn;
+        ks[KQ_APHI2] += aphi * aphi;
+        const double r1 = dsub(aphi, wq);
+        ks[KQ_PRIM1] += r1 * r1;
+        ks[KQ_ALPHA2] += an * an;
+        ks[KQ_QDOTA] += wq * an;
+    }
 }
 
-template <bool WEIGHTED, bool ACC>
+template <int K, int NT>
+__device__ __forceinline__ void block_reduce_store(double (&s)[K], double* __restrict__ partial, i64 block);
+
+template <bool WEIGHTED, bool ACC, bool KKT>
 __global__ void __launch_bounds__(256) k_qstep(Geo g, int tn0, IterScal sc, const double* __restrict__ phi,
                                                const double* __restrict__ q2, const double* __restrict__ weight,
                                                double* __restrict__ alpha, double* __restrict__ qout,
                                                const double* __restrict__ tmpq_in, double* __restrict__ tmpq_out,
-                                               bool upd_alpha)
+                                               bool upd_alpha, const double* __restrict__ c0, const double* __restrict__ c1,
+                                               double* __restrict__ kpart, int kkt_t0)
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int t = tn0 + blockIdx.y;
-    if (p >= g.P) return;
-    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
-    const i64 n = (i64)t * g.P + p;
-    const double ph = phi[n];
-    const bool edge_t = (t == 0) || (t == g.nt - 1);
-    if (t < g.nt - 1) {
-        const double aphi = dadd(dmul(-sc.gt, ph), dmul(sc.gt, phi[n + g.P]));
-        q_update<WEIGHTED, ACC>(n, aphi, sc.dinv1, sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in, tmpq_out, upd_alpha);
+    double ks[KQ_COUNT];
+#pragma unroll
+    for (int k = 0; k < KQ_COUNT; k++) ks[k] = 0.0;
+    if (p < g.P) {
+        const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+        const i64 n = (i64)t * g.P + p;
+        const double ph = phi[n];
+        const bool edge_t = (t == 0) || (t == g.nt - 1);
+        if (t < g.nt - 1) {
+            const double aphi = dadd(dmul(-sc.gt, ph), dmul(sc.gt, phi[n + g.P]));
+            q_update<WEIGHTED, ACC, KKT>(n, aphi, sc.dinv1, sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in, tmpq_out, upd_alpha, ks);
+        }
+        if (x < g.nx - 1) {
+            const double aphi = dadd(dmul(-sc.gx, ph), dmul(sc.gx, phi[n + g.ny]));
+            q_update<WEIGHTED, ACC, KKT>(g.L + (i64)t * g.PBX + (i64)x * g.ny + y, aphi, edge_t ? sc.dinv2 : sc.dinv1,
+                                         edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in, tmpq_out, upd_alpha, ks);
+        }
+        if (y < g.ny - 1) {
+            const double aphi = dadd(dmul(-sc.gy, ph), dmul(sc.gy, phi[n + 1]));
+            q_update<WEIGHTED, ACC, KKT>(g.L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y, aphi,
+                                         edge_t ? sc.dinv2 : sc.dinv1, edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout,
+                                         tmpq_in, tmpq_out, upd_alpha, ks);
+        }
+        if (KKT) {
+            double cv = 0.0;
+            if (t == 0) cv = c0[p];
+            else if (t == g.nt - 1) cv = c1[p];
+            ks[KQ_CPHI] = cv * ph;
+            ks[KQ_PHI2] = ph * ph;
+        }
     }
-    if (x < g.nx - 1) {
-        const double aphi = dadd(dmul(-sc.gx, ph), dmul(sc.gx, phi[n + g.ny]));
-        q_update<WEIGHTED, ACC>(g.L + (i64)t * g.PBX + (i64)x * g.ny + y, aphi, edge_t ? sc.dinv2 : sc.dinv1,
-                                edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in, tmpq_out, upd_alpha);
-    }
-    if (y < g.ny - 1) {
-        const double aphi = dadd(dmul(-sc.gy, ph), dmul(sc.gy, phi[n + 1]));
-        q_update<WEIGHTED, ACC>(g.L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y, aphi,
-                                edge_t ? sc.dinv2 : sc.dinv1, edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in,
-                                tmpq_out, upd_alpha);
-    }
+    if (KKT) block_reduce_store<KQ_COUNT, 256>(ks, kpart, (i64)(t - kkt_t0) * gridDim.x + blockIdx.x);
 }
 
 void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st, const double* tmpq_in, double* tmpq_out,
-                  bool upd_alpha)
+                  bool upd_alpha, const KktFused* kkt)
 {
     dim3 grid((unsigned)((a.g.P + 255) / 256), (unsigned)(a.tr.tn1 - a.tr.tn0));
-#define QS(W, A) \
-    k_qstep<W, A><<<grid, 256, 0, st>>>(a.g, a.tr.tn0, a.sc, a.phi, a.q2, a.weight, a.alpha, a.q_new, tmpq_in, tmpq_out, upd_alpha)
-    if (weighted) {
-        if (acc) QS(true, true); else QS(true, false);
+    if (grid.y == 0) return;
+#define QS(W, A, K)                                                                                                          \
+    k_qstep<W, A, K><<<grid, 256, 0, st>>>(a.g, a.tr.tn0, a.sc, a.phi, a.q2, a.weight, a.alpha, a.q_new, tmpq_in, tmpq_out, \
+                                           upd_alpha, a.c0, a.c1, kkt ? kkt->partial_q : nullptr, a.kkt_t0)
+    if (kkt) {   // inPALM check iteration
+        if (weighted) QS(true, false, true); else QS(false, false, true);
+    } else if (weighted) {
+        if (acc) QS(true, true, false); else QS(true, false, false);
     } else {
-        if (acc) QS(false, true); else QS(false, false);
+        if (acc) QS(false, true, false); else QS(false, false, false);
     }
 #undef QS
 }
@@ -370,99 +401,65 @@ void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st,
 // so beta (the 10L array that dominates the traffic) is read once and written once per iteration and z, z2, q2's
 // 10-column temporaries never touch HBM.  The x+1 / y+1 neighbours' w (columns 1,3 / 5,7) come through shared
 // memory; the t-1 layer's columns 3,4,7,8 are carried in registers.
+//
+// A step has two phases: phase 1 is cell-local (loads, two projections, the multiplier update, publish w to shared memory),
+// phase 2 gathers the neighbours' w after the CTA barrier and emits q2 / rhs.  TU consecutive time steps share one barrier:
+// their phase-1 chains are independent (the z-step of a cell needs nothing from the cell below it), so the compiler
+// interleaves the TU sqrt/division chains in one instruction stream and all loads of the TU steps are in flight together.
+//
+// KKT (check iterations, TU = 1): the same march also accumulates every KKT term that lives on the data in registers
+// (solver_socp_inPALM.m:225-244, compute_kkt_dot_complement.m) -- z, beta, z2, alpha and q are all there -- and leaves one
+// partial sum per (time level, tile); s(BF)^* beta uses a second set of exchange planes.  The remaining terms (A*phi, q,
+// alpha norms, <c,phi>) come from k_qstep<KKT>.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-
 template <bool WEIGHTED>
 __device__ __forceinline__ double uval(double q, double a, double w)
 {
     return WEIGHTED ? dsub(dmul(w, q), a) : dsub(q, a);
 }
 
-#ifndef KM_PAIRSYNC
-#define KM_PAIRSYNC 0     // 1: no CTA-wide barrier in the time loop: a warp (= one x row of the tile) only waits for the row
-                          //    above it (full/empty mbarrier pair per row), y neighbours are exchanged by warp shuffles.
-                          //    Bit-exact; measured 5.14 ms against 5.01 ms with __syncthreads (512x512x256): the barrier is
-                          //    not what limits the kernel.
-#endif
 #ifndef KM_TX
-#define KM_TX 8          // tile rows (x) per CTA; 16 (one 512-thread CTA per SM) measured in profiles/README.md
+#define KM_TX 8          // tile rows (x) per CTA
 #endif
 #ifndef KM_TY
-#define KM_TY 32         // tile columns (y, contiguous) per CTA
+#define KM_TY 32         // tile columns (y, contiguous) per CTA: one warp per tile row
 #endif
-#ifndef KM_MIN_BLOCKS
-#define KM_MIN_BLOCKS (KM_TX * KM_TY > 256 ? 1 : 2)
+#ifndef KM_TU
+#define KM_TU 2          // time steps per barrier in the update kernel (DOTSOCP_KM_TU=1 selects the one-step kernel at run time)
 #endif
-#ifndef KM_BULK
-#define KM_BULK 0         // 1: interior CTAs stage every step's input rows with cp.async.bulk (TMA engine) two steps ahead.
-                          // Bit-exact and fewer instructions per step, but measured SLOWER than the plain loads on B200
-                          // (512x512x256: 5.67 vs 5.01 ms, 1024x1024x512: 48.0 vs 37.9 ms); so is KM_L2PF (5.52 / 49.2 ms).
-                          // Deeper look-ahead loses more than the hidden latency wins; kept for experiments.
-#endif
-constexpr int KM_ROWD = 36;   // doubles per staged row: 32 (+1 for the y-1 neighbour) needed, + alignment slack, 288 B = 18 x 16 B
-__host__ __device__ constexpr int km_nrows(int TX) { return 16 * TX + 3 * (TX + 1); }
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "KM_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@!p bra KM_WAIT_%=;\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-// 16-byte aligned global -> shared bulk copy, completion counted in bytes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ unsigned ptr_par(const void* p) { return (unsigned)((unsigned long long)p >> 3) & 1u; }
+struct KktDev {          // scalars of the fused KKT terms
+    double sigma, scD, dD, sE, dSD;   // sigma ; sigma*cScale*D ; dScale/D (momentum) ; dScale/E ; dScale/D (rhoFq)
+};
 
-#ifndef KM_L2PF
-#define KM_L2PF 0         // 1: prefetch.global.L2 of the next step's lines
-#endif
-#ifndef KM_PREFETCH
-#define KM_PREFETCH 0     // 1: cp.async ring for the next step's loads (measured: no gain, the kernel is issue/latency bound)
-#endif
-template <int TX, int TY, bool WEIGHTED, bool ONE_D, bool UPDATE, bool EDGE>
-__device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, const IterScal& sc, const double* __restrict__ qo,
-                                            const double* __restrict__ qn, const double* __restrict__ alpha,
-                                            const double* __restrict__ weight, const double* __restrict__ beta,
-                                            double* __restrict__ beta_out, double* __restrict__ q2,
-                                            double* __restrict__ rhs, const double* __restrict__ c0,
-                                            const double* __restrict__ c1)
+// what phase 2 of a step needs from its phase 1
+struct MultKeep {
+    double w2, w4, w6, w8;            // own w columns of the (BF)^* sums
+    double u0, uxm, ux, uym, uy;      // (w.*q - alpha) on the 5 edges of the rhs stencil that phase 1 can already form
+    double cv;                        // c on the first / last time level
+};
+struct MultKeepK {                    // KKT extras
+    double b2, b4, b6, b8, fb0;       // beta columns of s(BF)^* beta ; fb0 = S (b9 - b0)
+    double a0, axm, ax, aym, ay;      // alpha on the node's edges (a0: t-edge above)
+    double wa0;                       // w .* alpha0 (rho, dual residual 2)
+    double qx, qy, wx, wy;            // q and weight on the node's own bx / by edge (momentum terms)
+    double rhoc;                      // rho at the node: pair average in t of sigma*cScale*D*w.*alpha0
+    double cell[KM_RHOFQ + 1];        // the 7 cell sums of this thread
+};
+
+template <int TX, int TY, int TU, bool WEIGHTED, bool ONE_D, bool UPDATE, bool EDGE, bool KKT>
+__device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int kkt_t0, const IterScal& sc, const KktDev& kd,
+                                            const double* __restrict__ qo, const double* __restrict__ qn,
+                                            const double* __restrict__ alpha, const double* __restrict__ weight,
+                                            const double* __restrict__ beta, double* __restrict__ beta_out,
+                                            double* __restrict__ q2, double* __restrict__ rhs, const double* __restrict__ c0,
+                                            const double* __restrict__ c1, double* __restrict__ kpart)
 {
-    // dynamic shared memory: [2][4][NT] exchange of the w columns 1,3,5,7 + a two-stage ring [2][NV][NT] into which every
-    // thread prefetches (cp.async, 8 B) the 21 values of its NEXT time step while it works on the current one, so the
-    // HBM latency of the beta / q streams is overlapped with the two projections instead of being exposed once per step
-    constexpr int NT = TX * TY, NV = 21;
+    static_assert(!KKT || (UPDATE && TU == 1), "the KKT variant is the single-step update kernel");
+    constexpr int NPL = KKT ? 9 : 4;   // exchange planes: w1,w3,w5,w7 (+ b1,b3,b5,b7, rho)
     extern __shared__ __align__(16) double dyn_smem[];
-    double (*sh)[4][TX][TY] = reinterpret_cast<double (*)[4][TX][TY]>(dyn_smem);
-    double* ring = dyn_smem + 2 * 4 * NT;
+    double (*sh)[TU][NPL][TX][TY] = reinterpret_cast<double (*)[TU][NPL][TX][TY]>(dyn_smem);
     const int ly = threadIdx.x, lx = threadIdx.y;
-    const int tid = lx * TY + ly;
     // y tiles vary fastest over the grid so that CTAs running side by side stream adjacent pieces of the same rows
     const int x = blockIdx.y * (TX - 1) + lx, y = blockIdx.x * (TY - 1) + ly;
     // EDGE = false: the whole tile (halo included) lies strictly inside the domain, every neighbour exists and all the
@@ -488,7 +485,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
 
     // staggered q at node level t (carried) -- old and new iterate
     CellQ co, cn;
-    co.q0 = cn.q0 = 0.0;
+    co.q0 = 0.0;
     co.bxm = co.bx = co.bym = co.by = co.bxm1 = co.bx1 = co.bym1 = co.by1 = 0.0;
     cn = co;
     // time slab: march over the owned node levels [tn0, tn1); a slab that does not start at t = 0 first replays the
@@ -507,230 +504,60 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
         if (hym) cn.bym = qn_by[s0y + ibym];
         if (hyp) cn.by = qn_by[s0y + iby];
     }
+    double wp3n = 0.0, wp4 = 0.0, wp7n = 0.0, wp8 = 0.0, u0p = 0.0;     // carried from the cell layer below
+    double bp3n = 0.0, bp4 = 0.0, bp7n = 0.0, bp8 = 0.0, a0p = 0.0, wa0p = 0.0;   // KKT: same for beta / alpha0
 
-    double wp3n = 0.0, wp4 = 0.0, wp7n = 0.0, wp8 = 0.0, u0p = 0.0;
-
-    // ---- bulk-copy ring (interior CTAs) ---------------------------------------------------------------------------------
-    // Every input of a time step is a set of rows of 32 (33) consecutive doubles.  Thread r < NROWS owns row r of the
-    // stage: slots 0..9 beta planes, 10 q0 new, 11 q0 old, 12 alpha0 (TX rows each, cell level t), then bx new / bx old at
-    // level t+1 (TX+1 rows from x0-1), by new / by old at level t+1 (TX rows, from y0-1), alpha_bx (TX+1 rows) and alpha_by
-    // (TX rows) at level t.  A row is fetched as 288 bytes from the 16-byte aligned address at or below its first element
-    // (the grids have odd lengths, so rows start on odd multiples of 8 bytes half of the time); readers add the parity of
-    // the row's first address to their index.  Step t+2 is issued right after the barrier of step t: two stages.
-    constexpr bool BULK = KM_BULK && !EDGE && !KM_PREFETCH;
-    constexpr int NROWS = km_nrows(TX), STAGE_D = NROWS * KM_ROWD;
-    constexpr int R_QN0 = 10 * TX, R_QO0 = 11 * TX, R_A0 = 12 * TX, R_QNBX = 13 * TX, R_QOBX = R_QNBX + TX + 1,
-                  R_QNBY = R_QOBX + TX + 1, R_QOBY = R_QNBY + TX, R_ALBX = R_QOBY + TX, R_ALBY = R_ALBX + TX + 1;
-    double* bring = dyn_smem + 2 * 4 * NT;
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(bring + 2 * STAGE_D);
-    const char* p_src = nullptr;      // producer: first byte of my row at the first step
-    i64 p_stride = 0;                 //           bytes per time step
-    bool p_cell = true, p_on = false; //           row exists only while t is a cell level / row is used at all
-    if (BULK) {
-        const int x0 = blockIdx.y * (TX - 1), y0 = blockIdx.x * (TY - 1);
-        if (tid < NROWS) {
-            const int r = tid;
-            const double* base;
-            i64 idx, str;
-            p_on = true;
-            if (r < R_QNBX) {          // cell-indexed planes
-                const int slot = r / TX, row = r - slot * TX;
-                base = slot < 10 ? beta + (i64)slot * L : slot == 10 ? qn : slot == 11 ? qo : alpha;
-                if (slot == 11 && !UPDATE) p_on = false;
-                idx = (i64)t_start * g.P + (i64)(x0 + row) * g.ny + y0;
-                str = g.P;
-            } else if (r < R_QNBY) {   // bx at level t+1, rows x0-1 ..
-                const bool old = r >= R_QOBX;
-                const int row = r - (old ? R_QOBX : R_QNBX);
-                base = old ? qo_bx : qn_bx;
-                if (old && !UPDATE) p_on = false;
-                idx = (i64)(t_start + 1) * g.PBX + (i64)(x0 - 1 + row) * g.ny + y0;
-                str = g.PBX;
-            } else if (r < R_ALBX) {   // by at level t+1, from y0-1
-                const bool old = r >= R_QOBY;
-                const int row = r - (old ? R_QOBY : R_QNBY);
-                base = old ? qo_by : qn_by;
-                if (old && !UPDATE) p_on = false;
-                idx = (i64)(t_start + 1) * g.PBY + (i64)(x0 + row) * (g.ny - 1) + y0 - 1;
-                str = g.PBY;
-            } else if (r < R_ALBY) {   // alpha_bx at level t
-                base = al_bx;
-                idx = (i64)t_start * g.PBX + (i64)(x0 - 1 + (r - R_ALBX)) * g.ny + y0;
-                str = g.PBX;
-                p_cell = false;
-            } else {                   // alpha_by at level t
-                base = al_by;
-                idx = (i64)t_start * g.PBY + (i64)(x0 + (r - R_ALBY)) * (g.ny - 1) + y0 - 1;
-                str = g.PBY;
-                p_cell = false;
-            }
-            p_src = reinterpret_cast<const char*>(base + idx);
-            p_stride = str * (i64)sizeof(double);
-        }
-        if (tid == 0) {
-            mbar_init(&mbar[0], 1);
-            mbar_init(&mbar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-    }
-    constexpr bool PAIR = KM_PAIRSYNC && !BULK && !KM_PREFETCH;
-    static_assert(!PAIR || TY == 32, "one warp per tile row");
-    __shared__ unsigned long long xbar[2][2][TX];   // [full | empty][buffer][row]
-    if (PAIR) {
-        if (tid < 4 * TX) mbar_init(&xbar[0][0][0] + tid, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncthreads();
-    }
-    auto fill = [&](int tt) {   // issue the rows of step tt into stage (tt - t_start) & 1
-        if (!BULK) return;
-        const int k = tt - t_start;
-        const bool cellt = tt < g.nt - 1;
-        unsigned long long* bar = &mbar[k & 1];
-        if (tid == 0) {
-            const int rows = cellt ? (NROWS - (UPDATE ? 0 : 3 * TX + 1)) : (2 * TX + 1);
-            mbar_expect_tx(bar, (unsigned)(rows * KM_ROWD * sizeof(double)));
-        }
-        if (p_on && (cellt || !p_cell)) {
-            const unsigned long long a = (unsigned long long)(p_src + (i64)k * p_stride) & ~15ull;
-            bulk_g2s(bring + (size_t)(k & 1) * STAGE_D + (size_t)tid * KM_ROWD, reinterpret_cast<const void*>(a),
-                     (unsigned)(KM_ROWD * sizeof(double)), bar);
-        }
-    };
-    // parity of the first address of my rows (low word arithmetic is enough), advanced every step
-    unsigned cw = 0, bw = 0, yw = 0;
-    unsigned par_c = 0, par_bxn = 0, par_bxo = 0, par_byn = 0, par_byo = 0, par_albx = 0, par_alby = 0;
-    if (BULK) {
-        const int y0 = blockIdx.x * (TY - 1);
-        cw = (unsigned)((i64)t_start * g.P + (i64)x * g.ny + y0);                       // cell planes, row x
-        bw = (unsigned)((i64)(t_start + 1) * g.PBX + (i64)(x - 1) * g.ny + y0);         // bx planes at t+1, row x-1
-        yw = (unsigned)((i64)(t_start + 1) * g.PBY + (i64)x * (g.ny - 1) + y0 - 1);     // by planes at t+1, row x (from y0-1)
-        par_c = ptr_par(beta) | (ptr_par(qn) << 1) | (ptr_par(qo) << 2) | (ptr_par(alpha) << 3) | ((unsigned)(L & 1) << 4);
-        par_bxn = ptr_par(qn_bx); par_bxo = ptr_par(qo_bx); par_byn = ptr_par(qn_by); par_byo = ptr_par(qo_by);
-        par_albx = ptr_par(al_bx) ^ (unsigned)(g.PBX & 1); par_alby = ptr_par(al_by) ^ (unsigned)(g.PBY & 1);
-        fill(t_start);
-        if (t_start + 1 < tr.tn1) fill(t_start + 1);
-    }
-
-    // ring slots: 0..9 beta, 10 q0 new, 11 q0 old, 12 alpha0, 13..16 new bx/by at level t+1, 17..20 old bx/by at t+1
-    auto prefetch = [&](int tt) {
-        if (!KM_PREFETCH) return;
-        if (tt < g.nt - 1 && valid) {
-            double* dst = ring + (size_t)(tt & 1) * NV * NT + tid;
-            const i64 cc = (i64)tt * g.P + node;
-#pragma unroll
-            for (int j = 0; j < 10; j++)
-                if (!(ONE_D && j >= 5 && j <= 8)) cp_async8(dst + j * NT, beta + (i64)j * L + cc);
-            cp_async8(dst + 10 * NT, qn + cc);
-            if (UPDATE) cp_async8(dst + 11 * NT, qo + cc);
-            cp_async8(dst + 12 * NT, alpha + cc);
-            const i64 o1x = (i64)(tt + 1) * g.PBX, o1y = (i64)(tt + 1) * g.PBY;
-            if (hxm) cp_async8(dst + 13 * NT, qn_bx + o1x + ibxm);
-            if (hxp) cp_async8(dst + 14 * NT, qn_bx + o1x + ibx);
-            if (hym) cp_async8(dst + 15 * NT, qn_by + o1y + ibym);
-            if (hyp) cp_async8(dst + 16 * NT, qn_by + o1y + iby);
-            if (UPDATE) {
-                if (hxm) cp_async8(dst + 17 * NT, qo_bx + o1x + ibxm);
-                if (hxp) cp_async8(dst + 18 * NT, qo_bx + o1x + ibx);
-                if (hym) cp_async8(dst + 19 * NT, qo_by + o1y + ibym);
-                if (hyp) cp_async8(dst + 20 * NT, qo_by + o1y + iby);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    prefetch(t_start);
-    // KM_L2PF: no ring, but ask the L2 for the next step's lines one step ahead (prefetch.global.L2 needs no registers and
-    // no shared memory), so that the loads of the next step find their data on chip
-    auto l2pf = [&](const double* p) {
-#if KM_L2PF
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-    };
-
-    for (int t = t_start; t < tr.tn1; t++) {
-        const int buf = t & 1;
+    // ---- phase 1 of step t into exchange slot (buf, u) ---------------------------------------------------------------
+    auto phase1 = [&](int t, int buf, int u, MultKeep& k, MultKeepK& kk) {
         const bool cell = t < g.nt - 1;
-        const bool emit = t >= tr.tn0;      // false only on the replayed ghost layer
         const i64 cidx = (i64)t * g.P + node;
         double w[10];
-        double a0 = 0.0, wt0 = 1.0;
 #pragma unroll
         for (int j = 0; j < 10; j++) w[j] = 0.0;
-        if (t + 1 < tr.tn1) prefetch(t + 1);
-        // bulk ring: wait for this step's stage, then all reads below are shared-memory loads at fixed offsets
-        const int kst = t - t_start;
-        const double* S = bring + (size_t)(kst & 1) * STAGE_D + ly;
-        const unsigned nyp = (unsigned)(g.ny & 1);
-        const unsigned pc = cw & 1u, pbx = bw & 1u, pby = yw & 1u;
-        if (BULK) mbar_wait(&mbar[kst & 1], (unsigned)(kst >> 1) & 1u);
-#define RB(rowbase, row, off) S[((rowbase) + (row)) * KM_ROWD + (int)(off)]
-        if (KM_L2PF && valid && t + 1 < g.nt - 1 && t + 1 < tr.tn1) {
-            const i64 cn1 = cidx + g.P;
-#pragma unroll
-            for (int j = 0; j < 10; j++)
-                if (!(ONE_D && j >= 5 && j <= 8)) l2pf(beta + (i64)j * L + cn1);
-            l2pf(qn + cn1);
-            l2pf(alpha + cn1);
-            if (UPDATE) l2pf(qo + cn1);
-            const i64 o2x = (i64)(t + 2) * g.PBX + ibx, o2y = (i64)(t + 2) * g.PBY + iby;
-            if (hxp) { l2pf(qn_bx + o2x); l2pf(al_bx + o2x - g.PBX); if (UPDATE) l2pf(qo_bx + o2x); }
-            if (hyp) { l2pf(qn_by + o2y); l2pf(al_by + o2y - g.PBY); if (UPDATE) l2pf(qo_by + o2y); }
-        }
-        // the level-t alpha (and weight) values of the rhs stencil are only needed after the barrier: issue them now so
-        // that their latency hides behind the two projections
+        double a0 = 0.0, wt0 = 1.0;
+        // level-t alpha (and weight) of the rhs stencil: independent of the projections, issued first
         double al_xm = 0.0, al_x = 0.0, al_ym = 0.0, al_y = 0.0, wt_xm = 1.0, wt_x = 1.0, wt_ym = 1.0, wt_y = 1.0;
+        k.cv = 0.0;
         if (owner) {
             const i64 ox = (i64)t * g.PBX, oy = (i64)t * g.PBY;
-            if (BULK) {
-                al_xm = RB(R_ALBX, lx, pbx ^ par_albx);
-                al_x = RB(R_ALBX, lx + 1, pbx ^ nyp ^ par_albx);
-                al_ym = RB(R_ALBY, lx, pby ^ par_alby);
-                al_y = RB(R_ALBY, lx, 1 + (pby ^ par_alby));
-            } else {
-                if (hxm) al_xm = al_bx[ox + ibxm];
-                if (hxp) al_x = al_bx[ox + ibx];
-                if (hym) al_ym = al_by[oy + ibym];
-                if (hyp) al_y = al_by[oy + iby];
-            }
+            if (hxm) al_xm = al_bx[ox + ibxm];
+            if (hxp) al_x = al_bx[ox + ibx];
+            if (hym) al_ym = al_by[oy + ibym];
+            if (hyp) al_y = al_by[oy + iby];
             if (WEIGHTED) {
                 if (hxm) wt_xm = w_bx[ox + ibxm];
                 if (hxp) wt_x = w_bx[ox + ibx];
                 if (hym) wt_ym = w_by[oy + ibym];
                 if (hyp) wt_y = w_by[oy + iby];
-                if (cell) wt0 = weight[cidx];
             }
+            if (t == 0) k.cv = c0[node];
+            else if (!cell) k.cv = c1[node];
         }
-        if (KM_PREFETCH) {
-            if (t + 1 < tr.tn1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (WEIGHTED && cell && valid) wt0 = weight[cidx];
+        if (KKT) {
+#pragma unroll
+            for (int j = 0; j <= KM_RHOFQ; j++) kk.cell[j] = 0.0;
+            kk.b2 = kk.b4 = kk.b6 = kk.b8 = kk.fb0 = 0.0;
         }
-        const int sb = PAIR ? (kst & 1) : buf;
-        // the row below me has consumed what I wrote two steps ago into this buffer (passes at once on the first two steps)
-        if (PAIR && lx >= 1) mbar_wait(&xbar[1][sb][lx], ((unsigned)(kst >> 1) & 1u) ^ 1u);
         if (cell && valid) {
-            const double* src = ring + (size_t)buf * NV * NT + tid;
             const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
-#define LDV(slot, gexpr, bexpr) (BULK ? (bexpr) : KM_PREFETCH ? src[(slot) * NT] : (gexpr))
             double b[10];
 #pragma unroll
-            for (int j = 0; j < 10; j++)
-                b[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0
-                                                   : LDV(j, beta[(i64)j * L + cidx], RB(j * TX, lx, (pc ^ par_c ^ ((j & 1) & (par_c >> 4))) & 1u));
-            cn.q0 = LDV(10, qn[cidx], RB(R_QN0, lx, (pc ^ (par_c >> 1)) & 1u));
-            a0 = LDV(12, alpha[cidx], RB(R_A0, lx, (pc ^ (par_c >> 3)) & 1u));
-            cn.bxm1 = hxm ? LDV(13, qn_bx[o1x + ibxm], RB(R_QNBX, lx, pbx ^ par_bxn)) : 0.0;
-            cn.bx1 = hxp ? LDV(14, qn_bx[o1x + ibx], RB(R_QNBX, lx + 1, pbx ^ nyp ^ par_bxn)) : 0.0;
-            cn.bym1 = hym ? LDV(15, qn_by[o1y + ibym], RB(R_QNBY, lx, pby ^ par_byn)) : 0.0;
-            cn.by1 = hyp ? LDV(16, qn_by[o1y + iby], RB(R_QNBY, lx, 1 + (pby ^ par_byn))) : 0.0;
+            for (int j = 0; j < 10; j++) b[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0 : beta[(i64)j * L + cidx];
+            cn.q0 = qn[cidx];
+            a0 = alpha[cidx];
+            cn.bxm1 = hxm ? qn_bx[o1x + ibxm] : 0.0;
+            cn.bx1 = hxp ? qn_bx[o1x + ibx] : 0.0;
+            cn.bym1 = hym ? qn_by[o1y + ibym] : 0.0;
+            cn.by1 = hyp ? qn_by[o1y + iby] : 0.0;
             double z2n[10];
             cell_z2(cn, sc, hxm, hxp, hym, hyp, z2n);
             if (UPDATE) {
-                co.q0 = LDV(11, qo[cidx], RB(R_QO0, lx, (pc ^ (par_c >> 2)) & 1u));
-                co.bxm1 = hxm ? LDV(17, qo_bx[o1x + ibxm], RB(R_QOBX, lx, pbx ^ par_bxo)) : 0.0;
-                co.bx1 = hxp ? LDV(18, qo_bx[o1x + ibx], RB(R_QOBX, lx + 1, pbx ^ nyp ^ par_bxo)) : 0.0;
-                co.bym1 = hym ? LDV(19, qo_by[o1y + ibym], RB(R_QOBY, lx, pby ^ par_byo)) : 0.0;
-                co.by1 = hyp ? LDV(20, qo_by[o1y + iby], RB(R_QOBY, lx, 1 + (pby ^ par_byo))) : 0.0;
-#undef LDV
+                co.q0 = qo[cidx];
+                co.bxm1 = hxm ? qo_bx[o1x + ibxm] : 0.0;
+                co.bx1 = hxp ? qo_bx[o1x + ibx] : 0.0;
+                co.bym1 = hym ? qo_by[o1y + ibym] : 0.0;
+                co.by1 = hyp ? qo_by[o1y + iby] : 0.0;
                 double v[10];
                 cell_z2(co, sc, hxm, hxp, hym, hyp, v);
 #pragma unroll
@@ -741,6 +568,43 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
                     b[j] = dadd(b[j], dmul(sc.tau, dsub(v[j], z2n[j])));
                     if (owner && !(ONE_D && j >= 5 && j <= 8)) beta_out[(i64)j * L + cidx] = b[j];
                 }
+                if (KKT) {
+                    // cell terms of the check (:228,231,236,240-241 ; compute_kkt_dot_complement.m:2-8) on z, the new beta and z2n
+                    double sz = 0.0, sb = 0.0, sp = 0.0, scp = 0.0, vv[10];
+#pragma unroll
+                    for (int j = 0; j < 10; j++) {
+                        sz += v[j] * v[j];
+                        sb += b[j] * b[j];
+                        const double r = dsub(v[j], z2n[j]);
+                        sp += r * r;
+                        vv[j] = dsub(v[j], dmul(kd.sigma, b[j]));
+                    }
+                    proj_soc<ONE_D>(vv);
+#pragma unroll
+                    for (int j = 0; j < 10; j++) {
+                        const double r = dsub(v[j], vv[j]);
+                        scp += r * r;
+                    }
+                    const double al = WEIGHTED ? dmul(wt0, a0) : a0;
+                    const double rhoT = dmul(kd.scD, al);
+                    double ss = 0.0;
+#pragma unroll
+                    for (int j = 1; j <= 8; j++) {
+                        const double e = dmul(kd.sE, z2n[j]);
+                        ss = (j == 1) ? dmul(e, e) : dadd(ss, dmul(e, e));
+                    }
+                    double rhoFq = dadd(dadd(rhoT, dmul(kd.dSD, cn.q0)), ss / 4.0);
+                    if (rhoFq < 0.0) rhoFq = 0.0;
+                    const double dr = dsub(rhoT, rhoFq);
+                    kk.cell[KM_Z2] = sz; kk.cell[KM_BETA2] = sb; kk.cell[KM_PRIM2] = sp; kk.cell[KM_COMPL] = scp;
+                    kk.cell[KM_DOTC] = dr * dr; kk.cell[KM_RHOT] = rhoT * rhoT; kk.cell[KM_RHOFQ] = rhoFq * rhoFq;
+                    sh[buf][u][4][lx][ly] = b[1];
+                    sh[buf][u][5][lx][ly] = b[3];
+                    sh[buf][u][6][lx][ly] = b[5];
+                    sh[buf][u][7][lx][ly] = b[7];
+                    kk.b2 = b[2]; kk.b4 = b[4]; kk.b6 = b[6]; kk.b8 = b[8];
+                    kk.fb0 = dmul(dsub(b[9], b[0]), sc.S);
+                }
             }
             // z-step input of the next iteration
 #pragma unroll
@@ -748,112 +612,212 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, cons
             proj_soc<ONE_D>(w);
 #pragma unroll
             for (int j = 0; j < 10; j++) w[j] = dadd(w[j], b[j]);
-            sh[sb][0][lx][ly] = w[1];
-            sh[sb][1][lx][ly] = w[3];
-            if (!PAIR) {
-                sh[sb][2][lx][ly] = w[5];
-                sh[sb][3][lx][ly] = w[7];
-            }
+            sh[buf][u][0][lx][ly] = w[1];
+            sh[buf][u][1][lx][ly] = w[3];
+            sh[buf][u][2][lx][ly] = w[5];
+            sh[buf][u][3][lx][ly] = w[7];
+            if (owner && t >= tr.tn0) q2[cidx] = dmul(dsub(w[9], w[0]), sc.S);
         }
-        double w1n_ = 0.0, w3n_ = 0.0, w5n_ = 0.0, w7n_ = 0.0;   // w columns 1,3 of (x+1,y) and 5,7 of (x,y+1)
-        if (PAIR) {
-            __syncwarp();
-            if (lx >= 1 && ly == 0) mbar_arrive(&xbar[0][sb][lx]);          // my row is published
-            w5n_ = __shfl_down_sync(0xffffffffu, w[5], 1);
-            w7n_ = __shfl_down_sync(0xffffffffu, w[7], 1);
-            if (lx < TX - 1) {
-                mbar_wait(&xbar[0][sb][lx + 1], (unsigned)(kst >> 1) & 1u);     // the row above is published
-                w1n_ = sh[sb][0][lx + 1][ly];
-                w3n_ = sh[sb][1][lx + 1][ly];
-                __syncwarp();
-                if (ly == 0) mbar_arrive(&xbar[1][sb][lx + 1]);              // ... and consumed
-            }
-        } else {
-            __syncthreads();
-            if (lx < TX - 1) { w1n_ = sh[sb][0][lx + 1][ly]; w3n_ = sh[sb][1][lx + 1][ly]; }
-            if (ly < TY - 1) { w5n_ = sh[sb][2][lx][ly + 1]; w7n_ = sh[sb][3][lx][ly + 1]; }
+        k.w2 = w[2]; k.w4 = w[4]; k.w6 = w[6]; k.w8 = w[8];
+        k.u0 = cell ? uval<WEIGHTED>(cn.q0, a0, wt0) : 0.0;
+        k.uxm = uval<WEIGHTED>(cn.bxm, al_xm, wt_xm);
+        k.ux = uval<WEIGHTED>(cn.bx, al_x, wt_x);
+        k.uym = uval<WEIGHTED>(cn.bym, al_ym, wt_ym);
+        k.uy = uval<WEIGHTED>(cn.by, al_y, wt_y);
+        if (KKT) {
+            kk.a0 = cell ? a0 : 0.0;
+            kk.axm = al_xm; kk.ax = al_x; kk.aym = al_ym; kk.ay = al_y;
+            kk.qx = cn.bx; kk.qy = cn.by; kk.wx = wt_x; kk.wy = wt_y;
+            // rho at this node (compute_kkt_dot_complement.m:10): pair average in t of rhoT, zero beyond the two ends
+            kk.wa0 = cell ? (WEIGHTED ? dmul(wt0, a0) : a0) : 0.0;
+            const double lo = t > 0 ? dmul(kd.scD, wa0p) : 0.0;
+            const double hi = cell ? dmul(kd.scD, kk.wa0) : 0.0;
+            kk.rhoc = dadd(lo, hi) / 2.0;
+            if (valid) sh[buf][u][8][lx][ly] = kk.rhoc;
+            wa0p = kk.wa0;
         }
-        // every thread has read stage kst: refill it with the rows of step t+2
-        if (BULK && t + 2 < tr.tn1) fill(t + 2);
-        cw += (unsigned)g.P;
-        bw += (unsigned)g.PBX;
-        yw += (unsigned)g.PBY;
-        if (owner) {
-            if (cell) {
-                if (emit) q2[cidx] = dmul(dsub(w[9], w[0]), sc.S);
-            }
-            const double u0 = cell ? uval<WEIGHTED>(cn.q0, a0, wt0) : 0.0;
-            // rhs = A' u + c : CSR-transpose row order (t-1 edge, t edge, x-1, x, y-1, y)
-            double acc = 0.0;
-            bool first = true;
+        // advance the carried node-level values
+        cn.bxm = cn.bxm1; cn.bx = cn.bx1; cn.bym = cn.bym1; cn.by = cn.by1;
+        if (UPDATE) { co.bxm = co.bxm1; co.bx = co.bx1; co.bym = co.bym1; co.by = co.by1; }
+    };
+
+    // ---- phase 2: gather the neighbours' columns, emit q2 (bx, by) and rhs of node level t -----------------------------
+    auto phase2 = [&](int t, int buf, int u, const MultKeep& k, const MultKeepK& kk, double (&ks)[KM_COUNT]) {
+        if (!owner) return;
+        const bool cell = t < g.nt - 1;
+        const bool emit = t >= tr.tn0;      // false only on the replayed ghost layer
+        const i64 cidx = (i64)t * g.P + node;
+        const double w1n = cell ? sh[buf][u][0][lx + 1][ly] : 0.0, w3n = cell ? sh[buf][u][1][lx + 1][ly] : 0.0;
+        const double w5n = cell ? sh[buf][u][2][lx][ly + 1] : 0.0, w7n = cell ? sh[buf][u][3][lx][ly + 1] : 0.0;
+        // rhs = A' u + c : CSR-transpose row order (t-1 edge, t edge, x-1, x, y-1, y)
+        double acc = 0.0;
+        bool first = true;
 #define ADDTERM(val)                         \
     {                                        \
         const double tv_ = (val);            \
         acc = first ? tv_ : dadd(acc, tv_);  \
         first = false;                       \
     }
-            if (t > 0) ADDTERM(dmul(sc.gt, u0p));
-            if (cell) ADDTERM(dmul(-sc.gt, u0));
-            if (hxp || hxm) {
-                const i64 ox = (i64)t * g.PBX;
-                if (hxm) ADDTERM(dmul(sc.gx, uval<WEIGHTED>(cn.bxm, al_xm, wt_xm)));
-                if (hxp) {
-                    ADDTERM(dmul(-sc.gx, uval<WEIGHTED>(cn.bx, al_x, wt_x)));
-                    const double w1n = cell ? w1n_ : 0.0;
-                    const double w3n = cell ? w3n_ : 0.0;
-                    double s;
-                    if (t == 0)
-                        s = dadd(w1n, w[2]);
-                    else if (!cell)
-                        s = dadd(wp3n, wp4);
-                    else
-                        s = dadd(dadd(dadd(w1n, w[2]), wp3n), wp4);
-                    if (emit) q2_bx[ox + ibx] = dmul(s, sc.SF);
-                    wp3n = w3n;
-                }
-            }
-            if (hyp || hym) {
-                const i64 oy = (i64)t * g.PBY;
-                if (hym) ADDTERM(dmul(sc.gy, uval<WEIGHTED>(cn.bym, al_ym, wt_ym)));
-                if (hyp) {
-                    ADDTERM(dmul(-sc.gy, uval<WEIGHTED>(cn.by, al_y, wt_y)));
-                    const double w5n = cell ? w5n_ : 0.0;
-                    const double w7n = cell ? w7n_ : 0.0;
-                    double s;
-                    if (t == 0)
-                        s = dadd(w5n, w[6]);
-                    else if (!cell)
-                        s = dadd(wp7n, wp8);
-                    else
-                        s = dadd(dadd(dadd(w5n, w[6]), wp7n), wp8);
-                    if (emit) q2_by[oy + iby] = dmul(s, sc.SF);
-                    wp7n = w7n;
-                }
-            }
-#undef ADDTERM
-            double cv = 0.0;
-            if (t == 0) cv = c0[node];
-            else if (!cell) cv = c1[node];
-            if (emit) rhs[cidx] = dadd(first ? 0.0 : acc, cv);
-            u0p = u0;
-            wp4 = w[4];
-            wp8 = w[8];
+        if (t > 0) ADDTERM(dmul(sc.gt, u0p));
+        if (cell) ADDTERM(dmul(-sc.gt, k.u0));
+        if (hxm) ADDTERM(dmul(sc.gx, k.uxm));
+        if (hxp) {
+            ADDTERM(dmul(-sc.gx, k.ux));
+            double s;
+            if (t == 0)
+                s = dadd(w1n, k.w2);
+            else if (!cell)
+                s = dadd(wp3n, wp4);
+            else
+                s = dadd(dadd(dadd(w1n, k.w2), wp3n), wp4);
+            if (emit) q2_bx[(i64)t * g.PBX + ibx] = dmul(s, sc.SF);
+            wp3n = w3n;
         }
-#undef RB
-        // advance the carried node-level values
-        cn.bxm = cn.bxm1; cn.bx = cn.bx1; cn.bym = cn.bym1; cn.by = cn.by1;
-        if (UPDATE) { co.bxm = co.bxm1; co.bx = co.bx1; co.bym = co.bym1; co.by = co.by1; }
+        if (hym) ADDTERM(dmul(sc.gy, k.uym));
+        if (hyp) {
+            ADDTERM(dmul(-sc.gy, k.uy));
+            double s;
+            if (t == 0)
+                s = dadd(w5n, k.w6);
+            else if (!cell)
+                s = dadd(wp7n, wp8);
+            else
+                s = dadd(dadd(dadd(w5n, k.w6), wp7n), wp8);
+            if (emit) q2_by[(i64)t * g.PBY + iby] = dmul(s, sc.SF);
+            wp7n = w7n;
+        }
+        if (emit) rhs[cidx] = dadd(first ? 0.0 : acc, k.cv);
+        u0p = k.u0;
+        wp4 = k.w4;
+        wp8 = k.w8;
+        if (KKT) {
+            // node / edge terms (:225-238 ; compute_kkt_dot_complement.m:10-18) of node level t
+            const double b1n = cell ? sh[buf][u][4][lx + 1][ly] : 0.0, b3n = cell ? sh[buf][u][5][lx + 1][ly] : 0.0;
+            const double b5n = cell ? sh[buf][u][6][lx][ly + 1] : 0.0, b7n = cell ? sh[buf][u][7][lx][ly + 1] : 0.0;
+            double fbb = 0.0, du2 = 0.0, mrb = 0.0, m2 = 0.0, rb2 = 0.0;
+            auto edge = [&](double fb, double wa, bool momentum, double qv, double rho_avg) {   // wa = w .* alpha on the edge
+                fbb += fb * fb;
+                const double r2 = dadd(fb, wa);
+                du2 += r2 * r2;
+                if (momentum) {
+                    const double m = dmul(kd.scD, wa);
+                    const double rb = dmul(kd.dD, dmul(rho_avg, qv));
+                    const double d = dsub(m, rb);
+                    mrb += d * d;
+                    m2 += m * m;
+                    rb2 += rb * rb;
+                }
+            };
+            // dual residual A' alpha - c (CSR-transpose row order)
+            double ad = 0.0;
+            bool f2 = true;
+#define ADDA(val)                          \
+    {                                      \
+        const double tv_ = (val);          \
+        ad = f2 ? tv_ : dadd(ad, tv_);     \
+        f2 = false;                        \
+    }
+            if (t > 0) ADDA(dmul(sc.gt, a0p));
+            if (cell) {
+                ADDA(dmul(-sc.gt, kk.a0));
+                edge(kk.fb0, kk.wa0, false, 0.0, 0.0);
+            }
+            if (hxm) ADDA(dmul(sc.gx, kk.axm));
+            if (hxp) {
+                ADDA(dmul(-sc.gx, kk.ax));
+                double s;
+                if (t == 0)
+                    s = dadd(b1n, kk.b2);
+                else if (!cell)
+                    s = dadd(bp3n, bp4);
+                else
+                    s = dadd(dadd(dadd(b1n, kk.b2), bp3n), bp4);
+                edge(dmul(s, sc.SF), WEIGHTED ? dmul(kk.wx, kk.ax) : kk.ax, true, kk.qx, dadd(kk.rhoc, sh[buf][u][8][lx + 1][ly]) / 2.0);
+                bp3n = b3n;
+            }
+            if (hym) ADDA(dmul(sc.gy, kk.aym));
+            if (hyp) {
+                ADDA(dmul(-sc.gy, kk.ay));
+                double s;
+                if (t == 0)
+                    s = dadd(b5n, kk.b6);
+                else if (!cell)
+                    s = dadd(bp7n, bp8);
+                else
+                    s = dadd(dadd(dadd(b5n, kk.b6), bp7n), bp8);
+                edge(dmul(s, sc.SF), WEIGHTED ? dmul(kk.wy, kk.ay) : kk.ay, true, kk.qy, dadd(kk.rhoc, sh[buf][u][8][lx][ly + 1]) / 2.0);
+                bp7n = b7n;
+            }
+#undef ADDA
+            const double rd = dsub(f2 ? 0.0 : ad, k.cv);
+            a0p = kk.a0;
+            bp4 = kk.b4;
+            bp8 = kk.b8;
+            if (emit) {
+#pragma unroll
+                for (int j = 0; j <= KM_RHOFQ; j++) ks[j] = kk.cell[j];
+                ks[KM_FBB2] = fbb; ks[KM_DUAL2] = du2; ks[KM_DUAL1] = rd * rd;
+                ks[KM_MRHOB] = mrb; ks[KM_M2] = m2; ks[KM_RHOB2] = rb2;
+            }
+        }
+#undef ADDTERM
+    };
+
+    MultKeep keep[TU];
+    MultKeepK keepk[KKT ? TU : 1];
+    int t = t_start, it = 0;
+    if (TU > 1) {
+        for (; t + TU <= tr.tn1; t += TU, it++) {
+            const int buf = it & 1;
+#pragma unroll
+            for (int u = 0; u < TU; u++) phase1(t + u, buf, u, keep[u], keepk[0]);
+            __syncthreads();
+            double ks[KM_COUNT];
+#pragma unroll
+            for (int u = 0; u < TU; u++) phase2(t + u, buf, u, keep[u], keepk[0], ks);
+        }
+    }
+    for (; t < tr.tn1; t++, it++) {
+        const int buf = it & 1;
+        phase1(t, buf, 0, keep[0], keepk[0]);
+        __syncthreads();
+        double ks[KM_COUNT];
+        if (KKT) {
+#pragma unroll
+            for (int j = 0; j < KM_COUNT; j++) ks[j] = 0.0;
+        }
+        phase2(t, buf, 0, keep[0], keepk[0], ks);
+        if (KKT && t >= tr.tn0) {
+            // one partial per (time level, tile): warp shuffles, then the TX warp sums in fixed order
+            __shared__ double red[KM_COUNT][TX];
+#pragma unroll
+            for (int j = 0; j < KM_COUNT; j++) {
+                double v = ks[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if (ly == 0) red[j][lx] = v;
+            }
+            __syncthreads();
+            const int tid = lx * TY + ly;
+            if (tid < KM_COUNT) {
+                double v = 0.0;
+#pragma unroll
+                for (int i = 0; i < TX; i++) v += red[tid][i];
+                const i64 tile = (i64)blockIdx.y * gridDim.x + blockIdx.x;
+                kpart[((i64)(t - kkt_t0) * ((i64)gridDim.x * gridDim.y) + tile) * KM_COUNT + tid] = v;
+            }
+        }
     }
 }
 
-template <int TX, int TY, bool WEIGHTED, bool ONE_D, bool UPDATE>
-__global__ void __launch_bounds__(TX* TY, KM_MIN_BLOCKS) k_mult(Geo g, TRange tr, int nchunk, IterScal sc, const double* __restrict__ qo,
-                                                 const double* __restrict__ qn, const double* __restrict__ alpha,
-                                                 const double* __restrict__ weight, const double* __restrict__ beta,
-                                                 double* __restrict__ beta_out, double* __restrict__ q2,
-                                                 double* __restrict__ rhs, const double* __restrict__ c0,
-                                                 const double* __restrict__ c1)
+template <int TX, int TY, int TU, bool WEIGHTED, bool ONE_D, bool UPDATE, bool KKT>
+__global__ void __launch_bounds__(TX* TY, (TU == 1 && !KKT) ? 2 : 1)
+k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, const double* __restrict__ qo, const double* __restrict__ qn,
+       const double* __restrict__ alpha, const double* __restrict__ weight, const double* __restrict__ beta,
+       double* __restrict__ beta_out, double* __restrict__ q2, double* __restrict__ rhs, const double* __restrict__ c0,
+       const double* __restrict__ c1, double* __restrict__ kpart)
 {
+    const int kkt_t0 = tr.tn0;
     if (nchunk > 1) {
         // the time range is cut into nchunk pieces (blockIdx.z), each marched by its own CTA exactly like the slab of a
         // multi-GPU run: a piece that does not start at the range's first cell layer replays the layer below it
@@ -864,9 +828,11 @@ __global__ void __launch_bounds__(TX* TY, KM_MIN_BLOCKS) k_mult(Geo g, TRange tr
     const int x0 = blockIdx.y * (TX - 1), y0 = blockIdx.x * (TY - 1);
     const bool interior = !ONE_D && x0 >= 1 && x0 + TX - 1 <= g.nx - 2 && y0 >= 1 && y0 + TY - 1 <= g.ny - 2;
     if (interior)
-        k_mult_body<TX, TY, WEIGHTED, ONE_D, UPDATE, false>(g, tr, sc, qo, qn, alpha, weight, beta, beta_out, q2, rhs, c0, c1);
+        k_mult_body<TX, TY, TU, WEIGHTED, ONE_D, UPDATE, false, KKT>(g, tr, kkt_t0, sc, kd, qo, qn, alpha, weight, beta, beta_out, q2,
+                                                                     rhs, c0, c1, kpart);
     else
-        k_mult_body<TX, TY, WEIGHTED, ONE_D, UPDATE, true>(g, tr, sc, qo, qn, alpha, weight, beta, beta_out, q2, rhs, c0, c1);
+        k_mult_body<TX, TY, TU, WEIGHTED, ONE_D, UPDATE, true, KKT>(g, tr, kkt_t0, sc, kd, qo, qn, alpha, weight, beta, beta_out, q2,
+                                                                    rhs, c0, c1, kpart);
 }
 
 // number of time pieces that maximises (fraction of the last round that is filled) x (useful layers / marched layers)
@@ -887,26 +853,37 @@ static int km_pick_chunks(long long base_ctas, int ncells, int slots)
     return best;
 }
 
-void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st)
+int mult_tiles(const Geo& g) { return ((g.ny + KM_TY - 2) / (KM_TY - 1)) * ((g.nx + KM_TX - 2) / (KM_TX - 1)); }
+
+void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st, const KktFused* kkt)
 {
     constexpr int TX = KM_TX, TY = KM_TY;
     dim3 block(TY, TX);
     dim3 grid((unsigned)((a.g.ny + TY - 2) / (TY - 1)), (unsigned)((a.g.nx + TX - 2) / (TX - 1)));
-    const size_t ring = KM_PREFETCH ? (size_t)2 * 21 * TX * TY * sizeof(double)
-                        : KM_BULK   ? (size_t)2 * km_nrows(TX) * KM_ROWD * sizeof(double) + 16
-                                    : 0;
-    const size_t smem = (size_t)2 * 4 * TX * TY * sizeof(double) + ring;
-    // Every CTA marches the same number of time steps, so a grid that fills the machine 4.25 times runs for 5 full rounds
-    // (512x512x256: 1258 CTAs on 296 slots).  Cutting the time range into pieces (grid.z) lets the CTA count land just below
-    // a whole number of rounds; each extra piece costs one replayed cell layer.  DOTSOCP_KM_CHUNKS=n forces n pieces.
+    KktDev kd{0, 0, 0, 0, 0};
+    double* kpart = nullptr;
+    if (kkt) {
+        kd.sigma = kkt->sigma;
+        kd.scD = (kkt->sigma * kkt->cScale) * kkt->D;
+        kd.dD = kkt->dScale / kkt->D;
+        kd.sE = kkt->dScale / kkt->E;
+        kd.dSD = kkt->dScale / kkt->D;
+        kpart = kkt->partial_m;
+    }
+    // Every CTA marches the same number of time steps, so a grid that fills the machine 4.25 times runs for 5 full rounds.
+    // Cutting the time range into pieces (grid.z) lets the CTA count land just below a whole number of rounds; each extra
+    // piece costs one replayed cell layer.  DOTSOCP_KM_CHUNKS=n forces n pieces.
     static const int forced = [] { const char* e = getenv("DOTSOCP_KM_CHUNKS"); return e ? atoi(e) : 0; }();
-#define KM(W, O, U)                                                                                                   \
+    const char* tu_env = getenv("DOTSOCP_KM_TU");   // read per launch: tests and A/B runs switch it inside one process
+    const int tu = (tu_env && atoi(tu_env) == 1) ? 1 : KM_TU;
+#define KM(TU, W, O, U, K)                                                                                            \
     {                                                                                                                 \
+        constexpr size_t smem = (size_t)2 * TU * (K ? 9 : 4) * TX * TY * sizeof(double);                              \
         static int slots = 0;                                                                                         \
         if (!slots) {                                                                                                 \
-            cudaFuncSetAttribute(k_mult<TX, TY, W, O, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+            cudaFuncSetAttribute(k_mult<TX, TY, TU, W, O, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             int per_sm = 0, dev = 0, sms = 0;                                                                         \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mult<TX, TY, W, O, U>, TX * TY, smem);           \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mult<TX, TY, TU, W, O, U, K>, TX * TY, smem);    \
             cudaGetDevice(&dev);                                                                                      \
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);                                        \
             slots = per_sm > 0 && sms > 0 ? per_sm * sms : 1;                                                         \
@@ -914,15 +891,17 @@ void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cu
         const int nchunk = forced > 0 ? std::min(forced, std::max(1, a.tr.tc1 - a.tr.tc0))                            \
                                       : km_pick_chunks((long long)grid.x * grid.y, a.tr.tc1 - a.tr.tc0, slots);       \
         grid.z = (unsigned)nchunk;                                                                                    \
-        k_mult<TX, TY, W, O, U><<<grid, block, smem, st>>>(a.g, a.tr, nchunk, a.sc, a.q_old, a.q_new, a.alpha,        \
-                                                            a.weight, a.beta_in, a.beta_out, a.q2, a.rhs, a.c0, a.c1); \
+        k_mult<TX, TY, TU, W, O, U, K><<<grid, block, smem, st>>>(a.g, a.tr, nchunk, a.sc, kd, a.q_old, a.q_new, a.alpha, \
+                                                                  a.weight, a.beta_in, a.beta_out, a.q2, a.rhs, a.c0, a.c1, kpart); \
     }
-    if (one_d) {
-        if (update) KM(false, true, true) else KM(false, true, false)
+    if (kkt && update) {
+        if (one_d) KM(1, false, true, true, true) else if (weighted) KM(1, true, false, true, true) else KM(1, false, false, true, true)
+    } else if (one_d) {
+        if (update) KM(1, false, true, true, false) else KM(1, false, true, false, false)
     } else if (weighted) {
-        if (update) KM(true, false, true) else KM(true, false, false)
+        if (!update) KM(1, true, false, false, false) else if (tu == 1) KM(1, true, false, true, false) else KM(KM_TU, true, false, true, false)
     } else {
-        if (update) KM(false, false, true) else KM(false, false, false)
+        if (!update) KM(1, false, false, false, false) else if (tu == 1) KM(1, false, false, true, false) else KM(KM_TU, false, false, true, false)
     }
 #undef KM
 }
@@ -1040,7 +1019,7 @@ void launch_cells_update(const Geo& g, const IterScal& sc, bool one_d, int mode,
 // Deterministic reductions: every CTA writes its K partial sums, a single CTA adds them in a fixed tree order.
 // ---------------------------------------------------------------------------------------------------------------
 template <int K, int NT>
-__device__ __forceinline__ void block_reduce_store(double (&s)[K], double* __restrict__ partial)
+__device__ __forceinline__ void block_reduce_store(double (&s)[K], double* __restrict__ partial, i64 block)
 {
     __shared__ double red[K][NT / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1055,17 +1034,43 @@ __device__ __forceinline__ void block_reduce_store(double (&s)[K], double* __res
     if (threadIdx.x < K) {
         double v = 0.0;
         for (int i = 0; i < NT / 32; i++) v += red[threadIdx.x][i];
-        partial[(i64)(blockIdx.y * gridDim.x + blockIdx.x) * K + threadIdx.x] = v;
+        partial[block * K + threadIdx.x] = v;
     }
 }
+template <int K, int NT>
+__device__ __forceinline__ void block_reduce_store(double (&s)[K], double* __restrict__ partial)
+{
+    block_reduce_store<K, NT>(s, partial, (i64)blockIdx.y * gridDim.x + blockIdx.x);
+}
 
-template <int K>
-__global__ void __launch_bounds__(256) k_final_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ out)
+// stage 2: one CTA per time level adds the level's `nb` CTA partials (K sums each) in a fixed order and stores them in
+// slots slot[0..K) of row t0 + blockIdx.x of the level table
+struct SlotMap { int n; int slot[16]; };
+__global__ void __launch_bounds__(256) k_level_reduce(const double* __restrict__ partial, int nb, int K, SlotMap sm, int t0,
+                                                      double* __restrict__ lvl)
 {
     __shared__ double red[256];
+    const double* row = partial + (i64)blockIdx.x * nb * K;
     for (int k = 0; k < K; k++) {
         double v = 0.0;
-        for (int i = threadIdx.x; i < nblocks; i += 256) v += partial[(i64)i * K + k];
+        for (int i = threadIdx.x; i < nb; i += 256) v += row[(i64)i * K + k];
+        red[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) lvl[(i64)(t0 + blockIdx.x) * KSL + sm.slot[k]] = red[0];
+        __syncthreads();
+    }
+}
+// stage 3: out[k] = sum over the nt rows of the level table, fixed order (depends on nt only)
+__global__ void __launch_bounds__(256) k_levels_total(const double* __restrict__ lvl, int nt, double* __restrict__ out)
+{
+    __shared__ double red[256];
+    for (int k = 0; k < KSL; k++) {
+        double v = 0.0;
+        for (int t = threadIdx.x; t < nt; t += 256) v += lvl[(i64)t * KSL + k];
         red[threadIdx.x] = v;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) {
@@ -1075,6 +1080,15 @@ __global__ void __launch_bounds__(256) k_final_reduce(const double* __restrict__
         if (threadIdx.x == 0) out[k] = red[0];
         __syncthreads();
     }
+}
+void launch_levels_total(const double* lvl, int nt, double* out, cudaStream_t st) { k_levels_total<<<1, 256, 0, st>>>(lvl, nt, out); }
+static void level_reduce(const double* partial, int nb, int K, const int* slots, int t0, int nlev, double* lvl, cudaStream_t st)
+{
+    if (nlev <= 0) return;
+    SlotMap sm;
+    sm.n = K;
+    for (int k = 0; k < K; k++) sm.slot[k] = slots[k];
+    k_level_reduce<<<nlev, 256, 0, st>>>(partial, nb, K, sm, t0, lvl);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1148,10 +1162,12 @@ __global__ void __launch_bounds__(256) k_kkt_cells(KktArgs a)
 int kkt_cells_blocks(const Geo& g) { return (int)((g.P + 255) / 256) * (g.nt - 1); }
 int kkt_nodes_blocks(const Geo& g) { return (int)((g.P + 255) / 256) * g.nt; }
 static int blocks_x(const Geo& g) { return (int)((g.P + 255) / 256); }
+int kkt_blocks_x(const Geo& g) { return blocks_x(g); }
 
 void launch_kkt_cells(const KktArgs& a, bool weighted, bool one_d, cudaStream_t st)
 {
     const int nl = a.tr.tc1 - a.tr.tc0;
+    if (nl <= 0) return;
     dim3 grid((unsigned)blocks_x(a.g), (unsigned)nl);
     if (one_d)
         k_kkt_cells<false, true><<<grid, 256, 0, st>>>(a);
@@ -1159,7 +1175,9 @@ void launch_kkt_cells(const KktArgs& a, bool weighted, bool one_d, cudaStream_t 
         k_kkt_cells<true, false><<<grid, 256, 0, st>>>(a);
     else
         k_kkt_cells<false, false><<<grid, 256, 0, st>>>(a);
-    k_final_reduce<KC_COUNT><<<1, 256, 0, st>>>(a.partial, blocks_x(a.g) * nl, a.out);
+    int slots[KC_COUNT];
+    for (int k = 0; k < KC_COUNT; k++) slots[k] = k;
+    level_reduce(a.partial, blocks_x(a.g), KC_COUNT, slots, a.tr.tc0, nl, a.lvl, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1167,36 +1185,81 @@ void launch_kkt_cells(const KktArgs& a, bool weighted, bool one_d, cudaStream_t 
 // block, :141).  zout may alias beta_old (cell-local read-then-write).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool ONE_D>
-__global__ void __launch_bounds__(256) k_zstep(Geo g, int tc0, IterScal sc, const double* q_old, const double* beta_old,
-                                               double* zout, double* __restrict__ partial)
+__global__ void __launch_bounds__(256) k_zstep(Geo g, int tc0, IterScal sc, const double* q_old, const double* beta_old, double* zout)
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int t = tc0 + blockIdx.y;
-    double s[1] = {0.0};
-    if (p < g.P) {
-        const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
-        double z[10];
-        load_z<ONE_D>(g, sc, nullptr, q_old, beta_old, t, x, y, z);
-        const i64 c = (i64)t * g.P + p;
+    if (p >= g.P) return;
+    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    double z[10];
+    load_z<ONE_D>(g, sc, nullptr, q_old, beta_old, t, x, y, z);
+    const i64 c = (i64)t * g.P + p;
 #pragma unroll
-        for (int j = 0; j < 10; j++) {
-            s[0] += z[j] * z[j];
-            if (zout != nullptr && !(ONE_D && j >= 5 && j <= 8)) zout[(i64)j * g.L + c] = z[j];
-        }
-    }
-    block_reduce_store<1, 256>(s, partial);
+    for (int j = 0; j < 10; j++)
+        if (!(ONE_D && j >= 5 && j <= 8)) zout[(i64)j * g.L + c] = z[j];
 }
 
 void launch_zstep(const Geo& g, const IterScal& sc, bool one_d, const double* q_old, const double* beta_old, double* zout,
-                  double* partial, double* out, cudaStream_t st, const TRange* tr)
+                  cudaStream_t st, const TRange* tr)
 {
     const int tc0 = tr ? tr->tc0 : 0, tc1 = tr ? tr->tc1 : g.nt - 1;
+    if (tc1 <= tc0) return;
     dim3 grid((unsigned)blocks_x(g), (unsigned)(tc1 - tc0));
     if (one_d)
-        k_zstep<true><<<grid, 256, 0, st>>>(g, tc0, sc, q_old, beta_old, zout, partial);
+        k_zstep<true><<<grid, 256, 0, st>>>(g, tc0, sc, q_old, beta_old, zout);
     else
-        k_zstep<false><<<grid, 256, 0, st>>>(g, tc0, sc, q_old, beta_old, zout, partial);
-    k_final_reduce<1><<<1, 256, 0, st>>>(partial, blocks_x(g) * (tc1 - tc0), out);
+        k_zstep<false><<<grid, 256, 0, st>>>(g, tc0, sc, q_old, beta_old, zout);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rescale norms (solver_socp_inPALM.m:140-143): sum of squares of phi, q, z, alpha, beta in ONE pass, one thread per
+// node (t,x,y) that owns phi[t,x,y], the edges q0/bx/by[t,x,y] and the cell (t,x,y); z is read or recomputed (load_z).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool ONE_D>
+__global__ void __launch_bounds__(256) k_norms(KktArgs a)
+{
+    const Geo& g = a.g;
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    const int t = a.tr.tn0 + blockIdx.y;
+    double s[NR_COUNT];
+#pragma unroll
+    for (int k = 0; k < NR_COUNT; k++) s[k] = 0.0;
+    if (p < g.P) {
+        const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+        const i64 L = g.L, n = (i64)t * g.P + p;
+        const double ph = a.phi[n];
+        s[NR_PHI2] = ph * ph;
+        auto edge = [&](i64 e) {
+            const double qv = a.q[e], av = a.alpha[e];
+            s[NR_Q2] += qv * qv;
+            s[NR_ALPHA2] += av * av;
+        };
+        if (t < g.nt - 1) {
+            edge(n);
+            double z[10];
+            load_z<ONE_D>(g, a.sc, a.z, a.q_old, a.beta_old, t, x, y, z);
+#pragma unroll
+            for (int j = 0; j < 10; j++) {
+                const double b = (ONE_D && j >= 5 && j <= 8) ? 0.0 : a.beta[(i64)j * L + n];
+                s[NR_Z2] += z[j] * z[j];
+                s[NR_BETA2] += b * b;
+            }
+        }
+        if (x < g.nx - 1) edge(L + (i64)t * g.PBX + (i64)x * g.ny + y);
+        if (y < g.ny - 1) edge(L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y);
+    }
+    block_reduce_store<NR_COUNT, 256>(s, a.partial);
+}
+void launch_norms(const KktArgs& a, bool one_d, cudaStream_t st)
+{
+    const int nl = a.tr.tn1 - a.tr.tn0;
+    if (nl <= 0) return;
+    dim3 grid((unsigned)blocks_x(a.g), (unsigned)nl);
+    if (one_d) k_norms<true><<<grid, 256, 0, st>>>(a);
+    else k_norms<false><<<grid, 256, 0, st>>>(a);
+    int slots[NR_COUNT];
+    for (int k = 0; k < NR_COUNT; k++) slots[k] = k;
+    level_reduce(a.partial, blocks_x(a.g), NR_COUNT, slots, a.tr.tn0, nl, a.lvl, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1291,38 +1354,33 @@ __global__ void __launch_bounds__(256) k_kkt_nodes(KktArgs a)
 void launch_kkt_nodes(const KktArgs& a, bool weighted, cudaStream_t st)
 {
     const int nl = a.tr.tn1 - a.tr.tn0;
+    if (nl <= 0) return;
     dim3 grid((unsigned)blocks_x(a.g), (unsigned)nl);
     if (weighted)
         k_kkt_nodes<true><<<grid, 256, 0, st>>>(a);
     else
         k_kkt_nodes<false><<<grid, 256, 0, st>>>(a);
-    k_final_reduce<KN_COUNT><<<1, 256, 0, st>>>(a.partial, blocks_x(a.g) * nl, a.out);
+    int slots[KN_COUNT];
+    for (int k = 0; k < KN_COUNT; k++) slots[k] = KC_COUNT + k;
+    level_reduce(a.partial, blocks_x(a.g), KN_COUNT, slots, a.tr.tn0, nl, a.lvl, st);
+}
+
+// fused check: the partials left by k_qstep<KKT> and k_mult<KKT> -> the same slots of the level table
+void launch_kkt_fused_reduce(const Geo& g, const TRange& tr, const KktFused& k, cudaStream_t st)
+{
+    const int nl = tr.tn1 - tr.tn0;
+    static const int qs[KQ_COUNT] = {KC_COUNT + KN_Q2, KC_COUNT + KN_APHI2, KC_COUNT + KN_PRIM1, KC_COUNT + KN_ALPHA2,
+                                     KC_COUNT + KN_QDOTA, KC_COUNT + KN_CPHI, KC_COUNT + KN_PHI2};
+    static const int ms[KM_COUNT] = {KC_Z2, KC_BETA2, KC_PRIM2, KC_COMPL, KC_DOTC, KC_RHOT, KC_RHOFQ, KC_COUNT + KN_FBB2,
+                                     KC_COUNT + KN_DUAL2, KC_COUNT + KN_DUAL1, KC_COUNT + KN_MRHOB, KC_COUNT + KN_M2,
+                                     KC_COUNT + KN_RHOB2};
+    level_reduce(k.partial_q, blocks_x(g), KQ_COUNT, qs, tr.tn0, nl, k.lvl, st);
+    level_reduce(k.partial_m, mult_tiles(g), KM_COUNT, ms, tr.tn0, nl, k.lvl, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // small streaming helpers
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SUMSQ_MAX_BLOCKS = 148 * 8;
-__global__ void __launch_bounds__(256) k_sumsq(const double* __restrict__ x, i64 n, double* __restrict__ partial)
-{
-    double s[1] = {0.0};
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) s[0] += x[i] * x[i];
-    block_reduce_store<1, 256>(s, partial);
-}
-int sumsq_blocks(i64 n)
-{
-    i64 b = (n + 255) / 256;
-    if (b > SUMSQ_MAX_BLOCKS) b = SUMSQ_MAX_BLOCKS;
-    if (b < 1) b = 1;
-    return (int)b;
-}
-void launch_sumsq(const double* x, i64 n, double* partial, double* out, cudaStream_t st)
-{
-    const int nb = sumsq_blocks(n);
-    k_sumsq<<<nb, 256, 0, st>>>(x, n, partial);
-    k_final_reduce<1><<<1, 256, 0, st>>>(partial, nb, out);
-}
-
 __global__ void __launch_bounds__(256) k_scale(double* __restrict__ x, i64 n, double mul, double div)
 {
     for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)

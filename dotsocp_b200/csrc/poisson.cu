@@ -14,6 +14,7 @@
 // eigenvalue table, inverse DCT, so the solve is 5 passes over N doubles (y, x, [t,/,t^-1], x^-1, y^-1).
 // Lengths <= 32 (coarse multilevel grids) use a dense matrix kernel.
 #include "kernels.h"
+#include "errs.h"
 #include "fft16.cuh"
 
 #include <cmath>
@@ -703,8 +704,8 @@ k_dct_blu16(LineGeom lg, const double* ain, double* aout, const double2* __restr
 }
 
 template <int LOG2M, int PAIRS>
-static void launch_blu16(const DctPlan* p, const LineGeom& lg, i64 outer, const double* ain, double* a, int mode,
-                         const ScaleArgs& sa, cudaStream_t st)
+static int launch_blu16(const DctPlan* p, const LineGeom& lg, i64 outer, const double* ain, double* a, int mode,
+                        const ScaleArgs& sa, cudaStream_t st)
 {
     constexpr int M = 1 << LOG2M, TP = M / 16, G = 2 * PAIRS, NTHR = TP * PAIRS;
     const size_t smem = (size_t)PAIRS * (M + M / 16 + 1) * sizeof(double2);
@@ -714,8 +715,8 @@ static void launch_blu16(const DctPlan* p, const LineGeom& lg, i64 outer, const 
     const bool contig = lg.contiguous != 0;
     if ((contig ? (lg.estride != 1 || lg.gstride != lg.n) : (lg.gstride != 1)) ||
         (i64)lg.n * lg.estride + (i64)G * lg.gstride >= ((i64)1 << 31)) {
-        fprintf(stderr, "dotsocp: unsupported line geometry for the register-FFT DCT kernel\n");
-        return;
+        return dsocp_set_err(-1, "unsupported line geometry for the register-FFT DCT kernel (n = %d, element stride %lld, line stride "
+                             "%lld): offsets inside one CTA must stay below 2^31", lg.n, (long long)lg.estride, (long long)lg.gstride);
     }
     LineGeom lgn = lg;
     lgn.n_inv = (unsigned)((((unsigned long long)1 << 32) / (unsigned)lg.n) + 1);
@@ -731,6 +732,7 @@ static void launch_blu16(const DctPlan* p, const LineGeom& lg, i64 outer, const 
     if (contig) { if (mode == 0) BLU(0, true) else if (mode == 1) BLU(1, true) else BLU(2, true) }
     else { if (mode == 0) BLU(0, false) else if (mode == 1) BLU(1, false) else BLU(2, false) }
 #undef BLU
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ dense small-n kernel
@@ -810,8 +812,8 @@ static void launch_blu(const DctPlan* p, const LineGeom& lg, i64 outer, const do
 #undef BLU
 }
 
-static void launch_dct_axis(const DctPlan* p, LineGeom lg, i64 outer, const double* ain, double* a, int mode,
-                            const ScaleArgs& sa, cudaStream_t st)
+static int launch_dct_axis(const DctPlan* p, LineGeom lg, i64 outer, const double* ain, double* a, int mode,
+                           const ScaleArgs& sa, cudaStream_t st)
 {
     if (p->dense) {
         const int n = p->n;
@@ -824,17 +826,17 @@ static void launch_dct_axis(const DctPlan* p, LineGeom lg, i64 outer, const doub
         if (mode == 0) k_dct_dense<0><<<grid, 256, smem, st>>>(lg, G, ain, a, p->cmat, sa);
         else if (mode == 1) k_dct_dense<1><<<grid, 256, smem, st>>>(lg, G, ain, a, p->cmat, sa);
         else k_dct_dense<2><<<grid, 256, smem, st>>>(lg, G, ain, a, p->cmat, sa);
-        return;
+        return 0;
     }
     switch (p->log2m) {
-        case 6: launch_blu<6, 32>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 7: launch_blu<7, 16>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 8: launch_blu16<8, 16>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 9: launch_blu16<9, 8>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 10: launch_blu16<10, 4>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 11: launch_blu16<11, 2>(p, lg, outer, ain, a, mode, sa, st); break;
-        case 12: launch_blu16<12, 2>(p, lg, outer, ain, a, mode, sa, st); break;
-        default: fprintf(stderr, "dotsocp: unsupported transform length %d\n", p->n); break;
+        case 6: launch_blu<6, 32>(p, lg, outer, ain, a, mode, sa, st); return 0;
+        case 7: launch_blu<7, 16>(p, lg, outer, ain, a, mode, sa, st); return 0;
+        case 8: return launch_blu16<8, 16>(p, lg, outer, ain, a, mode, sa, st);
+        case 9: return launch_blu16<9, 8>(p, lg, outer, ain, a, mode, sa, st);
+        case 10: return launch_blu16<10, 4>(p, lg, outer, ain, a, mode, sa, st);
+        case 11: return launch_blu16<11, 2>(p, lg, outer, ain, a, mode, sa, st);
+        case 12: return launch_blu16<12, 2>(p, lg, outer, ain, a, mode, sa, st);
+        default: return dsocp_set_err(-1, "unsupported transform length %d (Bluestein length 2^%d): supported up to 2^12", p->n, p->log2m);
     }
 }
 
@@ -998,16 +1000,15 @@ void poisson_plan_destroy(PoissonPlan* p)
 }
 
 // t-solve on a [nt][lines] array (line stride = lines) holding the modes p0 .. p0+lines-1
-static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, cudaStream_t st, double* launches,
-                    double* const* push_tab = nullptr, const int* tcut = nullptr, int world = 1)
+static int t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, cudaStream_t st, double* launches,
+                   double* const* push_tab = nullptr, const int* tcut = nullptr, int world = 1)
 {
     const Geo& g = p->g;
     if (!p->use_thomas || g.nt < 3) {
         ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, D2, p0};
         LineGeom gt{g.nt, lines, 1, lines, 0, 0, 0, 0, 0, 0, 0};
-        launch_dct_axis(p->pt, gt, 1, buf, buf, 2, sa, st);
         if (launches) *launches += 1;
-        return;
+        return launch_dct_axis(p->pt, gt, 1, buf, buf, 2, sa, st);
     }
     // one table per mode range (a process that emulates several slabs keeps one per slab)
     double* gtab = nullptr;
@@ -1032,6 +1033,7 @@ static void t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, c
     else
         k_thomas<false><<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, lines, lines, p0, 1.0 / (D2 * ct), gtab, t_fix, buf, nullptr, nullptr, 1);
     if (launches) *launches += 1;
+    return 0;
 }
 
 static LineGeom geom_y(const Geo& g) { return LineGeom{g.ny, 1, (i64)g.ny, (i64)g.nt * g.nx, 0, 1, 0, 0, 0, 0, 0}; }
@@ -1042,24 +1044,26 @@ static LineGeom geom_x(const Geo& g)
 }
 static LineGeom geom_t(const Geo& g) { return LineGeom{g.nt, g.P, 1, g.P, 0, 0, 0, 0, 0, 0, 0}; }
 
-void poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cudaStream_t st, double* launches)
+int poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cudaStream_t st, double* launches)
 {
     // first pass reads rhs and writes a (out of place), the rest works in place on a
     const Geo& g = p->g;
     ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, D2, 0};
     const i64 xo = (g.ny == 1) ? 1 : g.nt;
     const double* src = rhs;
-    if (g.ny > 1) { launch_dct_axis(p->py, geom_y(g), 1, src, a, 0, sa, st); src = a; if (launches) *launches += 1; }
-    launch_dct_axis(p->px, geom_x(g), xo, src, a, 0, sa, st);
-    t_solve(p, a, g.P, 0, D2, st, launches);
-    launch_dct_axis(p->px, geom_x(g), xo, a, a, 1, sa, st);
+    int rc = 0;
+    if (g.ny > 1) { rc = launch_dct_axis(p->py, geom_y(g), 1, src, a, 0, sa, st); src = a; if (launches) *launches += 1; }
+    if (!rc) rc = launch_dct_axis(p->px, geom_x(g), xo, src, a, 0, sa, st);
+    if (!rc) rc = t_solve(p, a, g.P, 0, D2, st, launches);
+    if (!rc) rc = launch_dct_axis(p->px, geom_x(g), xo, a, a, 1, sa, st);
     if (launches) *launches += 2;
-    if (g.ny > 1) { launch_dct_axis(p->py, geom_y(g), 1, a, a, 1, sa, st); if (launches) *launches += 1; }
+    if (!rc && g.ny > 1) { rc = launch_dct_axis(p->py, geom_y(g), 1, a, a, 1, sa, st); if (launches) *launches += 1; }
+    return rc;
 }
 
 // ---- pieces of the solve for a time slab (node levels [tn0, tn0+nlev) of the global array) --------------------------------
-void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev, bool inverse, cudaStream_t st, double* launches,
-                double* packed, int world, int slab_nlev, int slab_t0, double* const* push_tab)
+int poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev, bool inverse, cudaStream_t st, double* launches,
+               double* packed, int world, int slab_nlev, int slab_t0, double* const* push_tab)
 {
     // (tn0, nlev) may be a group of levels of a slab that owns slab_nlev levels starting slab_t0 levels before tn0
     // packed != NULL (and the x length uses the register-FFT kernel): the forward x pass writes, and the inverse x pass
@@ -1071,35 +1075,39 @@ void poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev,
     LineGeom gx = (g.ny == 1) ? LineGeom{g.nx, 1, (i64)g.nx, (i64)nlev, 0, 1, 0, 0, 0, 0, 0} : LineGeom{g.nx, (i64)g.ny, 1, (i64)g.ny, g.P, 0, 0, 0, 0, 0, 0};
     if (packed) { gx.rm_world = world; gx.rm_nlev = slab_nlev > 0 ? slab_nlev : nlev; gx.rm_t0 = slab_t0; gx.rm_P = g.P; gx.rm_ny = g.ny; gx.rm_tab = inverse ? nullptr : push_tab; }
     const i64 xo = (g.ny == 1) ? 1 : nlev;
+    int rc = 0;
     if (!inverse) {
         const double* s0 = src + off;
-        if (g.ny > 1) { launch_dct_axis(p->py, gy, 1, s0, a + off, 0, sa, st); s0 = a + off; if (launches) *launches += 1; }
-        launch_dct_axis(p->px, gx, xo, s0, packed ? packed : a + off, 0, sa, st);
+        if (g.ny > 1) { rc = launch_dct_axis(p->py, gy, 1, s0, a + off, 0, sa, st); s0 = a + off; if (launches) *launches += 1; }
+        if (!rc) rc = launch_dct_axis(p->px, gx, xo, s0, packed ? packed : a + off, 0, sa, st);
         if (launches) *launches += 1;
     } else {
-        launch_dct_axis(p->px, gx, xo, packed ? packed : a + off, a + off, 1, sa, st);
+        rc = launch_dct_axis(p->px, gx, xo, packed ? packed : a + off, a + off, 1, sa, st);
         if (launches) *launches += 1;
-        if (g.ny > 1) { launch_dct_axis(p->py, gy, 1, a + off, a + off, 1, sa, st); if (launches) *launches += 1; }
+        if (!rc && g.ny > 1) { rc = launch_dct_axis(p->py, gy, 1, a + off, a + off, 1, sa, st); if (launches) *launches += 1; }
     }
+    return rc;
 }
 bool poisson_can_pack(const PoissonPlan* p) { return p->g.ny > 1 && !p->px->dense && p->px->log2m >= 8 && p->px->log2m <= 12; }
 // t-pass (DCT_t, ./kernel, IDCT_t) on a [nt][chunk] array holding the (x,y) modes p0 .. p0+chunk-1
-void poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches,
-                     double* const* push_tab, const int* tcut, int world)
+int poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches,
+                    double* const* push_tab, const int* tcut, int world)
 {
     // push_tab != NULL needs the Thomas solve (the transform-based t pass works in place only)
-    t_solve(p, buf, chunk, p0, D2, st, launches, p->use_thomas && p->g.nt >= 3 ? push_tab : nullptr, tcut, world);
+    return t_solve(p, buf, chunk, p0, D2, st, launches, p->use_thomas && p->g.nt >= 3 ? push_tab : nullptr, tcut, world);
 }
 
-void poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches)
+int poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches)
 {
     const Geo& g = p->g;
     ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, 1.0, 0};
     const int mode = inverse ? 1 : 0;
-    if (g.ny > 1) launch_dct_axis(p->py, geom_y(g), 1, a, a, mode, sa, st);
-    if (g.nx > 1) launch_dct_axis(p->px, geom_x(g), (g.ny == 1) ? 1 : g.nt, a, a, mode, sa, st);
-    if (g.nt > 1) launch_dct_axis(p->pt, geom_t(g), 1, a, a, mode, sa, st);
+    int rc = 0;
+    if (g.ny > 1) rc = launch_dct_axis(p->py, geom_y(g), 1, a, a, mode, sa, st);
+    if (!rc && g.nx > 1) rc = launch_dct_axis(p->px, geom_x(g), (g.ny == 1) ? 1 : g.nt, a, a, mode, sa, st);
+    if (!rc && g.nt > 1) rc = launch_dct_axis(p->pt, geom_t(g), 1, a, a, mode, sa, st);
     if (launches) *launches += 3;
+    return rc;
 }
 
 }  // namespace dsocp

@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -114,7 +115,8 @@ struct Slab {
     SparseArray a_phi, a_rhs, a_q[2], a_alpha, a_q2, a_qtmp, a_weight, a_beta[2];
     double *phi = nullptr, *rhs = nullptr, *q[2] = {nullptr, nullptr}, *alpha = nullptr, *q2 = nullptr, *qtmp = nullptr,
            *weight = nullptr, *beta[2] = {nullptr, nullptr};
-    double *c0 = nullptr, *c1 = nullptr, *partial = nullptr, *dsums = nullptr, *hsums = nullptr;
+    double *c0 = nullptr, *c1 = nullptr, *partial = nullptr;
+    double *partial_q = nullptr, *partial_m = nullptr;   // fused KKT partials (allocated at the first fused check)
     double *tsend = nullptr, *trecv = nullptr;
     std::vector<double*> peer_tsend, peer_trecv;   // CUDA-IPC mappings of the other ranks' transpose buffers (NCCL mode)
     // direct exchange (kernels store into the destination slab's buffer): device tables of `world` pointers
@@ -130,9 +132,9 @@ struct Slab {
     {
         for (double* p : peer_tsend) if (p) cudaIpcCloseMemHandle(p);
         for (double* p : peer_trecv) if (p) cudaIpcCloseMemHandle(p);
-        cudaFree(c0); cudaFree(c1); cudaFree(partial); cudaFree(dsums); cudaFree(tsend); cudaFree(trecv); cudaFree(tmpq); cudaFree(d_fwd); cudaFree(d_bwd);
+        cudaFree(c0); cudaFree(c1); cudaFree(partial); cudaFree(partial_q); cudaFree(partial_m); cudaFree(tsend); cudaFree(trecv);
+        cudaFree(tmpq); cudaFree(d_fwd); cudaFree(d_bwd);
         for (int i = 0; i < 5; i++) { cudaFree(old_[i]); cudaFree(anc_[i]); }
-        if (hsums) cudaFreeHost(hsums);
     }
 };
 
@@ -171,11 +173,15 @@ struct dotsocp_ctx {
     bool z_materialised = true; // beta[1-bcur] holds z itself (after upload / at exit) instead of beta_old
     bool z_absent = false;      // upload was given no z: legal only for inPALM with maxit >= 1, which overwrites z before any read
     PoissonPlan* pp = nullptr;
+    // KKT / norm sums: level table [nt][KSL] (every slab fills its own rows), totals, pinned host copies
+    double *d_lvl = nullptr, *d_tot = nullptr, *h_tot = nullptr, *h_elapsed = nullptr;
+    bool fuse_kkt = true;        // DOTSOCP_KKT=separate: always use the stand-alone KKT kernels (A/B and tests)
     double launches = 0;
     bool uploaded = false;
     bool iter_open = false;
     IterScal sc;
     double sigma_fold = 1.0, D2 = 1.0;
+    double it_cScale = 1.0, it_dScale = 1.0, it_D = 1.0, it_E = 1.0;   // scalars of the open benchmark session
     EvPool evs;
     Slab* local(int id) const
     {
@@ -184,13 +190,11 @@ struct dotsocp_ctx {
     }
 };
 
-static size_t partial_doubles(const Geo& g)
+// CTA partials of the stand-alone KKT / norm kernels for `nlev` time levels
+static size_t partial_doubles(const Geo& g, int nlev)
 {
-    size_t a = (size_t)kkt_nodes_blocks(g) * KN_COUNT;
-    size_t b = (size_t)kkt_cells_blocks(g) * KC_COUNT;
-    size_t c = (size_t)sumsq_blocks(10 * g.L + g.Q);
-    size_t m = a > b ? a : b;
-    return (m > c ? m : c) + 64;
+    const int k = std::max(std::max((int)KN_COUNT, (int)KC_COUNT), (int)NR_COUNT);
+    return (size_t)kkt_blocks_x(g) * (size_t)nlev * k + 64;
 }
 
 static void* g_comm = nullptr;   // process-wide NCCL communicator (one process per GPU)
@@ -223,6 +227,10 @@ extern "C" void dotsocp_destroy(dotsocp_ctx* c)
     }
     cudaFree(c->barrier_buf);
     cudaFree(c->d_tcut);
+    cudaFree(c->d_lvl);
+    cudaFree(c->d_tot);
+    if (c->h_tot) cudaFreeHost(c->h_tot);
+    if (c->h_elapsed) cudaFreeHost(c->h_elapsed);
     for (auto e : c->cev) cudaEventDestroy(e);
     for (auto cs : c->cps) cudaStreamDestroy(cs);
     if (c->st2) cudaStreamDestroy(c->st2);
@@ -285,9 +293,7 @@ static int make_slab(dotsocp_ctx* c, int id)
     CU(cudaMalloc(&s->c1, g.P * sizeof(double)));
     CU(cudaMemsetAsync(s->c0, 0, g.P * sizeof(double), c->st));
     CU(cudaMemsetAsync(s->c1, 0, g.P * sizeof(double), c->st));
-    CU(cudaMalloc(&s->partial, partial_doubles(g) * sizeof(double)));
-    CU(cudaMalloc(&s->dsums, 64 * sizeof(double)));
-    CU(cudaMallocHost(&s->hsums, 64 * sizeof(double)));
+    CU(cudaMalloc(&s->partial, partial_doubles(g, tr.tn1 - tr.tn0) * sizeof(double)));
     if (c->world > 1) {
         CU(cudaMalloc(&s->tsend, (size_t)(tr.tn1 - tr.tn0) * g.P * sizeof(double)));
         CU(cudaMalloc(&s->trecv, (size_t)g.nt * (s->p1 - s->p0) * sizeof(double)));
@@ -295,7 +301,18 @@ static int make_slab(dotsocp_ctx* c, int id)
     return 0;
 }
 
+static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id);
+static void release_cached_unlocked_if_free();
 extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id)
+{
+    int rc = create_impl(out, variant, nt, nx, ny, rank, world, nccl_id);
+    if (rc == DOTSOCP_ENOMEM && !(world > 1 && nccl_id)) {   // the session cached by dotsocp_solve_level may hold the memory
+        release_cached_unlocked_if_free();
+        rc = create_impl(out, variant, nt, nx, ny, rank, world, nccl_id);
+    }
+    return rc;
+}
+static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id)
 {
     if (!out) return set_err(DOTSOCP_EINVAL, "ctx pointer is NULL");
     *out = nullptr;
@@ -438,8 +455,8 @@ extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, in
             std::vector<int> tc(world + 1);
             for (int r = 0; r < world; r++) tc[r] = c->part[r].tn0;
             tc[world] = c->part[world - 1].tn1;
-            CU(cudaMalloc(&c->d_tcut, (world + 1) * sizeof(int)));
-            CU(cudaMemcpy(c->d_tcut, tc.data(), (world + 1) * sizeof(int), cudaMemcpyHostToDevice));
+            cudaError_t de = cudaMalloc(&c->d_tcut, (world + 1) * sizeof(int));
+            if (de == cudaSuccess) de = cudaMemcpy(c->d_tcut, tc.data(), (world + 1) * sizeof(int), cudaMemcpyHostToDevice);
             for (Slab* s : c->slabs) {
                 std::vector<double*> fwd(world), bwd(world);
                 for (int r = 0; r < world; r++) {
@@ -449,18 +466,29 @@ extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, in
                     fwd[r] = o_trecv + (i64)s->tr.tn0 * (c->pcut[r + 1] - c->pcut[r]);
                     bwd[r] = o_tsend + (i64)(c->part[r].tn1 - c->part[r].tn0) * c->pcut[s->id];
                 }
-                CU(cudaMalloc(&s->d_fwd, world * sizeof(double*)));
-                CU(cudaMalloc(&s->d_bwd, world * sizeof(double*)));
-                CU(cudaMemcpy(s->d_fwd, fwd.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
-                CU(cudaMemcpy(s->d_bwd, bwd.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
+                if (de == cudaSuccess) de = cudaMalloc(&s->d_fwd, world * sizeof(double*));
+                if (de == cudaSuccess) de = cudaMalloc(&s->d_bwd, world * sizeof(double*));
+                if (de == cudaSuccess) de = cudaMemcpy(s->d_fwd, fwd.data(), world * sizeof(double*), cudaMemcpyHostToDevice);
+                if (de == cudaSuccess) de = cudaMemcpy(s->d_bwd, bwd.data(), world * sizeof(double*), cudaMemcpyHostToDevice);
+            }
+            if (de != cudaSuccess) {
+                cudaGetLastError();
+                dotsocp_destroy(c);
+                return set_err(DOTSOCP_ECUDA, "direct-exchange tables: %s", cudaGetErrorString(de));
             }
         }
     }
     c->pp = poisson_plan_create(nt, nx, ny);
+    { const char* kk = getenv("DOTSOCP_KKT"); c->fuse_kkt = !(kk && strcmp(kk, "separate") == 0); }
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_lvl, (size_t)nt * KSL * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_tot, KSL * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_tot, KSL * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_elapsed, sizeof(double));
     if (e != cudaSuccess) {
+        cudaGetLastError();
         dotsocp_destroy(c);
-        return set_err(DOTSOCP_ECUDA, "plan creation: %s", cudaGetErrorString(e));
+        return set_err(DOTSOCP_ECUDA, "plan / reduction buffers: %s", cudaGetErrorString(e));
     }
     *out = c;
     return DOTSOCP_OK;
@@ -542,8 +570,7 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
     const Geo& g = c->g;
     if (c->world == 1) {
         Slab* s = c->slabs[0];
-        poisson_solve(c->pp, s->rhs, s->phi, D2, c->st, &c->launches);
-        return 0;
+        return poisson_solve(c->pp, s->rhs, s->phi, D2, c->st, &c->launches);
     }
     const NcclApi& n = nccl_api();
     const bool fused_pack = poisson_can_pack(c->pp);
@@ -638,13 +665,13 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
                     const int nlev = s->tr.tn1 - s->tr.tn0;
                     const int r0 = (int)((i64)i * nlev / ngrp), r1 = (int)((i64)(i + 1) * nlev / ngrp);
                     if (r1 > r0)
-                        poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0 + r0, r1 - r0, false, c->st, &c->launches, s->tsend, c->world, nlev, r0, s->d_fwd);
+                        if ((rc = poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0 + r0, r1 - r0, false, c->st, &c->launches, s->tsend, c->world, nlev, r0, s->d_fwd))) return rc;
                 }
             tmark(1);
             if ((rc = barrier())) return rc;
             tmark(2);
             for (Slab* s : c->slabs)
-                poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches, s->d_bwd, c->d_tcut, c->world);
+                if ((rc = poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches, s->d_bwd, c->d_tcut, c->world))) return rc;
             tmark(3);
             if ((rc = barrier())) return rc;
             for (int i = 0; i < ngrp; i++)
@@ -652,7 +679,7 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
                     const int nlev = s->tr.tn1 - s->tr.tn0;
                     const int r0 = (int)((i64)i * nlev / ngrp), r1 = (int)((i64)(i + 1) * nlev / ngrp);
                     if (r1 > r0)
-                        poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0 + r0, r1 - r0, true, c->st, &c->launches, s->tsend, c->world, nlev, r0);
+                        if ((rc = poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0 + r0, r1 - r0, true, c->st, &c->launches, s->tsend, c->world, nlev, r0))) return rc;
                 }
             tmark(4);
             rc = ghosts(c, GH_PHI_UP, 0, 0);
@@ -665,7 +692,7 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
                 const int nlev = s->tr.tn1 - s->tr.tn0;
                 const int r0 = (int)((i64)i * nlev / ngrp), r1 = (int)((i64)(i + 1) * nlev / ngrp);
                 if (r1 > r0)
-                    poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0 + r0, r1 - r0, false, c->st, &c->launches, s->tsend, c->world, nlev, r0);
+                    if ((rc = poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0 + r0, r1 - r0, false, c->st, &c->launches, s->tsend, c->world, nlev, r0))) return rc;
             }
             cudaEvent_t e = c->comm_event();
             CU(cudaEventRecord(e, c->st));
@@ -677,7 +704,7 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
         CU(cudaEventRecord(e1, c->st2));
         CU(cudaStreamWaitEvent(c->st, e1, 0));
         tmark(2);
-        for (Slab* s : c->slabs) poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches);
+        for (Slab* s : c->slabs) if ((rc = poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches))) return rc;
         tmark(3);
         cudaEvent_t e2 = c->comm_event();
         CU(cudaEventRecord(e2, c->st));
@@ -691,7 +718,7 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
                 const int nlev = s->tr.tn1 - s->tr.tn0;
                 const int r0 = (int)((i64)i * nlev / ngrp), r1 = (int)((i64)(i + 1) * nlev / ngrp);
                 if (r1 > r0)
-                    poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0 + r0, r1 - r0, true, c->st, &c->launches, s->tsend, c->world, nlev, r0);
+                    if ((rc = poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0 + r0, r1 - r0, true, c->st, &c->launches, s->tsend, c->world, nlev, r0))) return rc;
             }
         }
         tmark(4);
@@ -701,7 +728,7 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
     }
     for (Slab* s : c->slabs) {
         const int nlev = s->tr.tn1 - s->tr.tn0;
-        poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0, nlev, false, c->st, &c->launches);
+        if ((rc = poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0, nlev, false, c->st, &c->launches))) return rc;
         // pack: block r of the send buffer = rows of this slab x modes of slab r
         for (int r = 0; r < c->world; r++) {
             const i64 ch = c->pcut[r + 1] - c->pcut[r];
@@ -710,7 +737,7 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
         }
     }
     if ((rc = exchange_rows(true, 0, 1, c->st))) return rc;
-    for (Slab* s : c->slabs) poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches);
+    for (Slab* s : c->slabs) if ((rc = poisson_t_chunk(c->pp, s->trecv, s->p1 - s->p0, s->p0, D2, c->st, &c->launches))) return rc;
     if ((rc = exchange_rows(false, 0, 1, c->st))) return rc;
     for (Slab* s : c->slabs) {
         const int nlev = s->tr.tn1 - s->tr.tn0;
@@ -719,7 +746,7 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
             CU(cudaMemcpy2DAsync(s->phi + s->tr.tn0 * g.P + c->pcut[r], g.P * sizeof(double), s->tsend + (i64)nlev * c->pcut[r],
                                  ch * sizeof(double), ch * sizeof(double), nlev, cudaMemcpyDeviceToDevice, c->st));
         }
-        poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0, nlev, true, c->st, &c->launches);
+        if ((rc = poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0, nlev, true, c->st, &c->launches))) return rc;
     }
     return ghosts(c, GH_PHI_UP, 0, 0);
 }
@@ -964,6 +991,14 @@ static IterScal make_scal(const dotsocp_level_opts& o, double D, double E, doubl
     return sc;
 }
 
+static int ensure_alloc(double*& p, i64 n)
+{
+    if (p) return 0;
+    cudaError_t e = cudaMalloc(&p, (size_t)n * sizeof(double));
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(DOTSOCP_ENOMEM, "cudaMalloc(%lld doubles): %s", (long long)n, cudaGetErrorString(e)); }
+    return 0;
+}
+
 enum ArrKind { A_PHI, A_Q, A_ALPHA, A_BETA, A_ZMAT, A_C };
 
 struct Loop {
@@ -975,7 +1010,7 @@ struct Loop {
         UpdateArgs a;
         a.g = c->g; a.tr = s->tr; a.sc = sc; a.phi = s->phi; a.q_old = s->q[c->qcur]; a.q_new = s->q[1 - c->qcur];
         a.alpha = s->alpha; a.weight = s->weight; a.beta_in = s->beta[c->bcur]; a.beta_out = s->beta[1 - c->bcur];
-        a.q2 = s->q2; a.rhs = s->rhs; a.c0 = s->c0; a.c1 = s->c1;
+        a.q2 = s->q2; a.rhs = s->rhs; a.c0 = s->c0; a.c1 = s->c1; a.kkt_t0 = s->tr.tn0;
         return a;
     }
     // q2, rhs from the current (q, alpha, beta): the z-step part of the first iteration / after any rescaling
@@ -991,10 +1026,27 @@ struct Loop {
         }
     }
     int step_phi() { return solve_poisson(c, sc_D2); }
-    int step_q(bool acc)
+    // fused KKT: per-slab partial buffers (allocated at the first fused check) + the scalars of the terms
+    int kkt_fused(Slab* s, double sigma, double cScale, double dScale, double D, double E, KktFused* kf)
     {
+        const int nlev = s->tr.tn1 - s->tr.tn0;
+        int rc = ensure_alloc(s->partial_q, (i64)nlev * kkt_blocks_x(c->g) * KQ_COUNT);
+        if (!rc) rc = ensure_alloc(s->partial_m, (i64)nlev * mult_tiles(c->g) * KM_COUNT);
+        if (rc) return rc;
+        *kf = KktFused{sigma, cScale, dScale, D, E, s->partial_q, s->partial_m, c->d_lvl};
+        return 0;
+    }
+    int step_q(bool acc, const KktFused* kf_tmpl = nullptr)
+    {
+        auto fused = [&](Slab* s, KktFused* kf) -> const KktFused* {
+            if (!kf_tmpl) return nullptr;
+            *kf = *kf_tmpl;
+            kf->partial_q = s->partial_q; kf->partial_m = s->partial_m;
+            return kf;
+        };
         if (c->world == 1) {
-            launch_qstep(ua(c->slabs[0]), c->weighted, acc, c->st);
+            KktFused kf;
+            launch_qstep(ua(c->slabs[0]), c->weighted, acc, c->st, nullptr, nullptr, true, fused(c->slabs[0], &kf));
             c->launches += 1;
             return 0;
         }
@@ -1004,7 +1056,8 @@ struct Loop {
             if (t1 <= t0) return;
             UpdateArgs a = ua(s);
             a.tr.tn0 = t0; a.tr.tn1 = t1;
-            launch_qstep(a, c->weighted, acc, c->st);
+            KktFused kf;
+            launch_qstep(a, c->weighted, acc, c->st, nullptr, nullptr, true, fused(s, &kf));
             c->launches += 1;
         };
         for (Slab* s : c->slabs) {
@@ -1024,10 +1077,12 @@ struct Loop {
         CU(cudaStreamWaitEvent(c->st, e2, 0));
         return 0;
     }
-    void step_mult()
+    void step_mult(const KktFused* kf_tmpl = nullptr)
     {
         for (Slab* s : c->slabs) {
-            launch_mult(ua(s), c->weighted, c->one_d, true, c->st);
+            KktFused kf;
+            if (kf_tmpl) { kf = *kf_tmpl; kf.partial_q = s->partial_q; kf.partial_m = s->partial_m; }
+            launch_mult(ua(s), c->weighted, c->one_d, true, c->st, kf_tmpl ? &kf : nullptr);
             c->launches += 1;
         }
         c->qcur ^= 1;
@@ -1053,44 +1108,23 @@ struct Loop {
     }
 };
 
-// sum over all slabs (and processes) of `count` per-slab device sums; result in out[]
-static int reduce_sums(dotsocp_ctx* c, int count, double* out)
+// Level-table reductions (kernels.h): the producers of a check fill their own rows of c->d_lvl; finish_sums() brings in the
+// rows of the other ranks (all-reduce of rows with exactly one non-zero contributor: exact), adds the nt rows in a fixed order
+// and returns the KSL totals on the host.  The result is bit-identical for any number of slabs / GPUs.
+static int begin_sums(dotsocp_ctx* c)
 {
-    for (Slab* s : c->slabs) CU(cudaMemcpyAsync(s->hsums, s->dsums, count * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));
-    for (int i = 0; i < count; i++) out[i] = 0.0;
-    for (Slab* s : c->slabs)
-        for (int i = 0; i < count; i++) out[i] += s->hsums[i];
-    if (c->comm) {
-        Slab* s = c->slabs[0];
-        for (int i = 0; i < count; i++) s->hsums[i] = out[i];
-        CU(cudaMemcpyAsync(s->dsums, s->hsums, count * sizeof(double), cudaMemcpyHostToDevice, c->st));
-        NC(nccl_api().AllReduce(s->dsums, s->dsums, (size_t)count, NCCL_FLOAT64, NCCL_SUM, c->comm, c->st));
-        CU(cudaMemcpyAsync(s->hsums, s->dsums, count * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-        CU(cudaStreamSynchronize(c->st));
-        for (int i = 0; i < count; i++) out[i] = s->hsums[i];
-    }
+    CU(cudaMemsetAsync(c->d_lvl, 0, (size_t)c->g.nt * KSL * sizeof(double), c->st));
     return 0;
 }
-
-// sum of squares of the owned part of an array
-static int sumsq_owned(dotsocp_ctx* c, ArrKind k, double* out)
+static int finish_sums(dotsocp_ctx* c, const double** out)
 {
-    const int maxr = 10;
-    for (Slab* s : c->slabs) {
-        double* base = k == A_PHI ? s->phi : k == A_Q ? s->q[c->qcur] : k == A_ALPHA ? s->alpha
-                     : k == A_BETA ? s->beta[c->bcur] : s->beta[1 - c->bcur];
-        const Ranges& r = k == A_PHI ? s->n_own : (k == A_Q || k == A_ALPHA) ? s->q_own : s->b_own;
-        int i = 0;
-        for (auto& x : r) { launch_sumsq(base + x.b, x.e - x.b, s->partial, s->dsums + i, c->st); c->launches += 2; i++; }
-        for (; i < maxr; i++) CU(cudaMemsetAsync(s->dsums + i, 0, sizeof(double), c->st));
-    }
-    double v[maxr];
-    int rc = reduce_sums(c, maxr, v);
-    if (rc) return rc;
-    double t = 0;
-    for (int i = 0; i < maxr; i++) t += v[i];
-    *out = t;
+    if (c->comm)
+        NC(nccl_api().AllReduce(c->d_lvl, c->d_lvl, (size_t)c->g.nt * KSL, NCCL_FLOAT64, NCCL_SUM, c->comm, c->st));
+    launch_levels_total(c->d_lvl, c->g.nt, c->d_tot, c->st);
+    c->launches += 1;
+    CU(cudaMemcpyAsync(c->h_tot, c->d_tot, KSL * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    *out = c->h_tot;
     return 0;
 }
 
@@ -1100,27 +1134,12 @@ static double now_s()
     return duration<double>(steady_clock::now().time_since_epoch()).count();
 }
 
-static int ensure_alloc(double*& p, i64 n)
-{
-    if (p) return 0;
-    cudaError_t e = cudaMalloc(&p, (size_t)n * sizeof(double));
-    if (e != cudaSuccess) { cudaGetLastError(); return set_err(DOTSOCP_ENOMEM, "cudaMalloc(%lld doubles): %s", (long long)n, cudaGetErrorString(e)); }
-    return 0;
-}
-
-// z = Pi_Q(d + BF q_old - beta_old) of the owned cells: optional store over beta_old, sum of squares
-static int zstep_all(dotsocp_ctx* c, const IterScal& sc, bool store, double* sumsq)
+// z = Pi_Q(d + BF q_old - beta_old) of the owned cells, written over beta_old
+static int zstep_all(dotsocp_ctx* c, const IterScal& sc)
 {
     for (Slab* s : c->slabs) {
-        launch_zstep(c->g, sc, c->one_d, s->q[1 - c->qcur], s->beta[1 - c->bcur], store ? s->beta[1 - c->bcur] : nullptr, s->partial,
-                     s->dsums, c->st, &s->tr);
-        c->launches += 2;
-    }
-    if (sumsq) {
-        double v[1];
-        int rc = reduce_sums(c, 1, v);
-        if (rc) return rc;
-        *sumsq = v[0];
+        launch_zstep(c->g, sc, c->one_d, s->q[1 - c->qcur], s->beta[1 - c->bcur], s->beta[1 - c->bcur], c->st, &s->tr);
+        c->launches += 1;
     }
     return 0;
 }
@@ -1137,7 +1156,9 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     const bool inpalm = method == DOTSOCP_METHOD_INPALM, palm = method == DOTSOCP_METHOD_PALM, acc = method == DOTSOCP_METHOD_ACCADMM;
     const bool weighted = c->weighted;
     const bool checkPD = o.checkPrimDualFeas < 0 ? !weighted : (o.checkPrimDualFeas != 0);   // :20-24 / wsocp :25-29
-    const double time_limit = o.time_limit > 0 ? o.time_limit : 3600;
+    // NaN = opts.time_limit absent (default 3600 s, :26-30); a non-positive value is a budget that is already spent (the
+    // multilevel drivers pass time_limit - Total_Time on, solver_dotsocp2d.m:244): one iteration, one check, stop (:287-289)
+    const double time_limit = std::isnan(o.time_limit) ? 3600 : o.time_limit;
     const double tau = o.tau;
     double sigma = o.sigma;
     const int maxit = o.maxit;
@@ -1238,16 +1259,22 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         bool scaleYes = false;
         double normPhis = 0, normAlps = 0;
         auto rescale_norms = [&]() -> int {
-            double s_phi, s_q, s_z, s_a, s_b;
             int r;
-            if ((r = sumsq_owned(c, A_PHI, &s_phi))) return r;
-            if ((r = sumsq_owned(c, A_Q, &s_q))) return r;
-            if (c->z_materialised) { if ((r = sumsq_owned(c, A_ZMAT, &s_z))) return r; }
-            else if ((r = zstep_all(c, L.sc, false, &s_z))) return r;
-            if ((r = sumsq_owned(c, A_ALPHA, &s_a))) return r;
-            if ((r = sumsq_owned(c, A_BETA, &s_b))) return r;
-            const double normPhi = sqrt(h) * sqrt(s_phi), normQ = sqrt(h) * sqrt(s_q), normZ = sqrt(h) * sqrt(s_z);
-            const double normAlpha = sigma * (sqrt(h) * sqrt(s_a)), normBeta = sigma * (sqrt(h) * sqrt(s_b));
+            if ((r = begin_sums(c))) return r;
+            for (Slab* s : c->slabs) {
+                KktArgs ka;
+                ka.g = g; ka.tr = s->tr; ka.sc = L.sc; ka.sigma = sigma; ka.cScale = cScale; ka.dScale = dScale; ka.D = D; ka.E = E;
+                ka.phi = s->phi; ka.q = s->q[c->qcur]; ka.alpha = s->alpha; ka.weight = s->weight; ka.beta = s->beta[c->bcur];
+                ka.z = c->z_materialised ? s->beta[1 - c->bcur] : nullptr;
+                ka.q_old = s->q[1 - c->qcur]; ka.beta_old = s->beta[1 - c->bcur];
+                ka.q2b = nullptr; ka.c0 = s->c0; ka.c1 = s->c1; ka.partial = s->partial; ka.lvl = c->d_lvl;
+                launch_norms(ka, c->one_d, c->st);
+                c->launches += 2;
+            }
+            const double* v;
+            if ((r = finish_sums(c, &v))) return r;
+            const double normPhi = sqrt(h) * sqrt(v[NR_PHI2]), normQ = sqrt(h) * sqrt(v[NR_Q2]), normZ = sqrt(h) * sqrt(v[NR_Z2]);
+            const double normAlpha = sigma * (sqrt(h) * sqrt(v[NR_ALPHA2])), normBeta = sigma * (sqrt(h) * sqrt(v[NR_BETA2]));
             normPhis = mmax({normPhi, normQ, normZ});
             normAlps = mmax({normAlpha, normBeta});
             return 0;
@@ -1284,13 +1311,22 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
 
         // ---------------------------------------------------------------- iteration
         cudaEvent_t e_last;
+        // the check schedule depends only on (it, lastSigmaIt), so an inPALM iteration knows beforehand whether a check
+        // follows it and lets k_qstep / k_mult accumulate the KKT sums on the data they stream anyway (:218-267)
+        bool fused_check = false;
         if (inpalm) {   // :192-216, fused order
+            fused_check = c->fuse_kkt && (checkSByS || IfAdjustSigma(it, lastSigmaIt) || it == maxit);
+            KktFused kf{sigma, cScale, dScale, D, E, nullptr, nullptr, c->d_lvl};
+            if (fused_check) {
+                for (Slab* s : c->slabs) { KktFused tmp; if ((rc = L.kkt_fused(s, sigma, cScale, dScale, D, E, &tmp))) return rc; }
+                if ((rc = begin_sums(c))) return rc;
+            }
             cudaEvent_t e0 = mark();
             if ((rc = L.step_phi())) return rc;
             cudaEvent_t e1 = mark();
-            if ((rc = L.step_q(false))) return rc;
+            if ((rc = L.step_q(false, fused_check ? &kf : nullptr))) return rc;
             cudaEvent_t e2 = mark();
-            L.step_mult();
+            L.step_mult(fused_check ? &kf : nullptr);
             cudaEvent_t e3 = mark();
             segs.push_back({e0, e1, 0});
             segs.push_back({e1, e2, 2});
@@ -1310,7 +1346,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             c->launches += 3;
             if ((rc = L.step_phi())) return rc;
             cudaEvent_t e2 = mark();
-            launch_zstep(g, L.sc, false, q, beta, zmat, S0->partial, S0->dsums, c->st);   // mexBFd + mexProjSoc (:209-210)
+            launch_zstep(g, L.sc, false, q, beta, zmat, c->st);   // mexBFd + mexProjSoc (:209-210)
             cudaEvent_t e3 = mark();
             launch_bfdconj_sum(g, L.sc.S, zmat, beta, S0->q2, c->st);
             launch_qstep(a, false, false, c->st, nullptr, tmpq, true);               // tmp_q = A*phi ; q ; alpha
@@ -1358,30 +1394,37 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         const bool check = checkSByS || adjustSigmaYes || it == maxit || over_time;
         bool stop = false;
         if (check) {
+            if (!fused_check && (rc = begin_sums(c))) return rc;
             for (Slab* s : c->slabs) {
-                launch_bfdconj(g, L.sc.S, s->beta[c->bcur], s->qtmp, c->st, &s->tr);   // q2 = s (BF)^* beta   (:225)
-                KktArgs ka;
-                ka.g = g; ka.tr = s->tr; ka.sc = L.sc; ka.sigma = sigma; ka.cScale = cScale; ka.dScale = dScale; ka.D = D; ka.E = E;
-                ka.phi = s->phi; ka.q = s->q[c->qcur]; ka.alpha = s->alpha; ka.weight = s->weight;
-                ka.beta = s->beta[c->bcur]; ka.z = zmat; ka.q_old = s->q[1 - c->qcur]; ka.beta_old = s->beta[1 - c->bcur];
-                ka.q2b = s->qtmp; ka.c0 = s->c0; ka.c1 = s->c1; ka.partial = s->partial;
-                ka.out = s->dsums;
-                launch_kkt_cells(ka, weighted, c->one_d, c->st);
-                ka.out = s->dsums + KC_COUNT;
-                launch_kkt_nodes(ka, weighted, c->st);
-                c->launches += 5;
-                // slot KC_COUNT+KN_COUNT carries the elapsed time seen by slab 0 so that all processes decide alike
-                s->hsums[63] = (s->id == 0) ? (now_s() - clock_total) : 0.0;
-                CU(cudaMemcpyAsync(s->dsums + KC_COUNT + KN_COUNT, s->hsums + 63, sizeof(double), cudaMemcpyHostToDevice, c->st));
+                if (fused_check) {
+                    KktFused kf{sigma, cScale, dScale, D, E, s->partial_q, s->partial_m, c->d_lvl};
+                    launch_kkt_fused_reduce(g, s->tr, kf, c->st);
+                    c->launches += 2;
+                } else {
+                    launch_bfdconj(g, L.sc.S, s->beta[c->bcur], s->qtmp, c->st, &s->tr);   // q2 = s (BF)^* beta   (:225)
+                    KktArgs ka;
+                    ka.g = g; ka.tr = s->tr; ka.sc = L.sc; ka.sigma = sigma; ka.cScale = cScale; ka.dScale = dScale; ka.D = D; ka.E = E;
+                    ka.phi = s->phi; ka.q = s->q[c->qcur]; ka.alpha = s->alpha; ka.weight = s->weight;
+                    ka.beta = s->beta[c->bcur]; ka.z = zmat; ka.q_old = s->q[1 - c->qcur]; ka.beta_old = s->beta[1 - c->bcur];
+                    ka.q2b = s->qtmp; ka.c0 = s->c0; ka.c1 = s->c1; ka.partial = s->partial; ka.lvl = c->d_lvl;
+                    launch_kkt_cells(ka, weighted, c->one_d, c->st);
+                    launch_kkt_nodes(ka, weighted, c->st);
+                    c->launches += 5;
+                }
+                // row 0 carries the elapsed time seen by slab 0 so that all processes decide alike
+                if (s->id == 0) {
+                    *c->h_elapsed = now_s() - clock_total;
+                    CU(cudaMemcpyAsync(c->d_lvl + KS_ELAPSED, c->h_elapsed, sizeof(double), cudaMemcpyHostToDevice, c->st));
+                }
             }
             cudaEvent_t e4 = mark();
             segs.push_back({e_last, e4, 4});
-            double sums[KC_COUNT + KN_COUNT + 1];
-            if ((rc = reduce_sums(c, KC_COUNT + KN_COUNT + 1, sums))) return rc;
+            const double* sums;
+            if ((rc = finish_sums(c, &sums))) return rc;
             flush_segs();
             const double* sc_ = sums;
             const double* sn = sums + KC_COUNT;
-            const double elapsed = c->comm ? sums[KC_COUNT + KN_COUNT] : (now_s() - clock_total);
+            const double elapsed = c->comm ? sums[KS_ELAPSED] : (now_s() - clock_total);
             auto nrm = [&](double v) { return sqrt(h) * sqrt(v); };
             const double norm_q = nrm(sn[KN_Q2]);
             const double norm_z = nrm(sc_[KC_Z2]);
@@ -1490,7 +1533,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     // ---------------------------------------------------------------- output :328-357
     if (!c->z_materialised && z_ever) {
         // z = Pi_Q(d + BF q_old - beta_old), written over beta_old (cell-local, safe in place)
-        if ((rc = zstep_all(c, L.sc, true, nullptr))) return rc;
+        if ((rc = zstep_all(c, L.sc))) return rc;
         c->z_materialised = true;
         c->z_absent = false;
     }
@@ -1530,19 +1573,53 @@ extern "C" int dotsocp_run(dotsocp_ctx* c, const dotsocp_level_opts* o, dotsocp_
     return run_level(c, *o, hist, res);
 }
 
+// dotsocp_solve_level keeps its session alive between calls (process lifetime, keyed by variant and grid): the MEX gateway is
+// called once per level and per solve, and at 1024x1024x512 creating and destroying the 147 GB of device arrays costs about a
+// second per call.  dotsocp_release_cached() frees it (the gateway registers it with mexAtExit); a later dotsocp_create that
+// runs out of device memory releases it too and retries.  DOTSOCP_CACHE_CTX=0 restores create/destroy per call.
+static dotsocp_ctx* g_cached = nullptr;
+static std::mutex g_cached_mu;
+static void release_cached_locked()
+{
+    if (g_cached) { dotsocp_destroy(g_cached); g_cached = nullptr; }
+}
+static void release_cached_unlocked_if_free()
+{
+    // called from dotsocp_create: inside dotsocp_solve_level the lock is held and g_cached is already detached (nothing to do)
+    if (g_cached_mu.try_lock()) { release_cached_locked(); g_cached_mu.unlock(); }
+}
+extern "C" void dotsocp_release_cached(void)
+{
+    std::lock_guard<std::mutex> lk(g_cached_mu);
+    release_cached_locked();
+}
+
 extern "C" int dotsocp_solve_level(const dotsocp_level_opts* o, double* phi, double* q, double* z, double* alpha, double* beta,
                                    const double* cvec, const double* weight, dotsocp_hist* hist, dotsocp_level_result* res)
 {
     if (!o) return set_err(DOTSOCP_EINVAL, "NULL opts");
-    dotsocp_ctx* c = nullptr;
-    int rc = dotsocp_create(&c, o->variant, o->nt, o->nx, o->ny, 0, 1, nullptr);
+    static const bool keep = [] { const char* e = getenv("DOTSOCP_CACHE_CTX"); return !(e && e[0] == '0'); }();
+    std::lock_guard<std::mutex> lk(g_cached_mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dotsocp_ctx* c = g_cached;
+    g_cached = nullptr;
+    if (c && !(c->variant == o->variant && c->g.nt == o->nt && c->g.nx == o->nx && c->g.ny == o->ny && c->device == dev && c->world == 1)) {
+        dotsocp_destroy(c);
+        c = nullptr;
+    }
+    int rc = 0;
+    if (!c) rc = dotsocp_create(&c, o->variant, o->nt, o->nx, o->ny, 0, 1, nullptr);
     if (rc) return rc;
+    const double launches0 = c->launches;
     // inPALM overwrites z (solver_socp_inPALM.m:199) before it is ever read, so its incoming value need not cross PCIe
     const bool z_dead = o->method == DOTSOCP_METHOD_INPALM && o->maxit >= 1;
     rc = dotsocp_upload(c, phi, q, z_dead ? nullptr : z, alpha, beta, cvec, weight);
     if (!rc) rc = dotsocp_run(c, o, hist, res);
     if (!rc) rc = dotsocp_download(c, phi, q, z, alpha, beta);
-    dotsocp_destroy(c);
+    if (!rc && res) res->gpu_launches -= launches0;
+    if (rc || !keep) dotsocp_destroy(c);   // a failed call leaves no state behind
+    else g_cached = c;
     return rc;
 }
 
@@ -1554,6 +1631,7 @@ extern "C" int dotsocp_iter_begin(dotsocp_ctx* c, const dotsocp_level_opts* o)
     c->sc = make_scal(*o, o->D, o->E, o->dScale, o->tau);
     c->sigma_fold = o->sigma;
     c->D2 = o->D * o->D;
+    c->it_cScale = o->cScale; c->it_dScale = o->dScale; c->it_D = o->D; c->it_E = o->E;
     Loop L; L.c = c; L.sc = c->sc; L.sc_D2 = c->D2;
     L.scale(A_ALPHA, 1.0, o->sigma);
     L.scale(A_BETA, 1.0, o->sigma);
@@ -1566,7 +1644,6 @@ extern "C" int dotsocp_iter_begin(dotsocp_ctx* c, const dotsocp_level_opts* o)
 
 extern "C" int dotsocp_iterate(dotsocp_ctx* c, int n_iters, int with_kkt_every, float* elapsed_ms, float* ms_by_kernel)
 {
-    (void)with_kkt_every;
     if (!c || !c->iter_open) return set_err(DOTSOCP_ESTATE, "iterate without iter_begin");
     Loop L; L.c = c; L.sc = c->sc; L.sc_D2 = c->D2;
     cudaEvent_t a, b;
@@ -1579,13 +1656,32 @@ extern "C" int dotsocp_iterate(dotsocp_ctx* c, int n_iters, int with_kkt_every, 
     int rc = 0;
     cudaEventRecord(a, c->st);
     for (int i = 0; i < n_iters && !rc; i++) {
+        // with_kkt_every = k > 0: every k-th iteration is a check iteration (KKT sums fused into the update kernels, the
+        // level-table reduction, the all-reduce between ranks and the read-back of the totals, like run_level's checks)
+        const bool chk = with_kkt_every > 0 && (i + 1) % with_kkt_every == 0;
+        KktFused kf{c->sigma_fold, c->it_cScale, c->it_dScale, c->it_D, c->it_E, nullptr, nullptr, c->d_lvl};
+        if (chk) {
+            for (Slab* s : c->slabs) { KktFused tmp; if ((rc = L.kkt_fused(s, kf.sigma, kf.cScale, kf.dScale, kf.D, kf.E, &tmp))) break; }
+            if (!rc) rc = begin_sums(c);
+            if (rc) break;
+        }
         if (ms_by_kernel) cudaEventRecord(ev[4 * i + 0], c->st);
         rc = L.step_phi();
         if (ms_by_kernel) cudaEventRecord(ev[4 * i + 1], c->st);
-        if (!rc) rc = L.step_q(false);
+        if (!rc) rc = L.step_q(false, chk ? &kf : nullptr);
         if (ms_by_kernel) cudaEventRecord(ev[4 * i + 2], c->st);
-        L.step_mult();
+        L.step_mult(chk ? &kf : nullptr);
         if (ms_by_kernel) cudaEventRecord(ev[4 * i + 3], c->st);
+        if (chk && !rc) {
+            for (Slab* s : c->slabs) {
+                KktFused k2 = kf;
+                k2.partial_q = s->partial_q; k2.partial_m = s->partial_m;
+                launch_kkt_fused_reduce(c->g, s->tr, k2, c->st);
+                c->launches += 2;
+            }
+            const double* sums;
+            rc = finish_sums(c, &sums);
+        }
     }
     cudaEventRecord(b, c->st);
     if (rc) return rc;
@@ -1613,7 +1709,7 @@ extern "C" int dotsocp_iter_end(dotsocp_ctx* c)
     if (!c || !c->iter_open) return set_err(DOTSOCP_ESTATE, "iter_end without iter_begin");
     Loop L; L.c = c; L.sc = c->sc; L.sc_D2 = c->D2;
     if (!c->z_materialised) {
-        int rc = zstep_all(c, c->sc, true, nullptr);
+        int rc = zstep_all(c, c->sc);
         if (rc) return rc;
         c->z_materialised = true;
         c->z_absent = false;

@@ -70,7 +70,8 @@ def make_level_opts(variant, method, var, opts, model):
     o.tau = float(_get(opts, "tau", 1.0) or 1.0)
     o.sigma = float(_get(opts, "sigma"))
     o.tol = float(_get(opts, "tol"))
-    o.time_limit = float(_get(opts, "time_limit", 0) or 0)
+    tl = _get(opts, "time_limit", None)          # NaN = absent (3600 s); <= 0 = budget already spent (one iteration + check)
+    o.time_limit = float("nan") if tl is None else float(tl)
     o.rho = float(_get(opts, "rho", 0) or 0)
     o.theta = float(_get(opts, "theta", 0) or 0)
     o.cScale, o.dScale, o.D, o.E = float(var.cScale), float(var.dScale), float(var.D), float(var.E)
@@ -124,7 +125,9 @@ class Session:
         assert arrs[0].size == self.N and arrs[1].size == self.Q and arrs[3].size == self.Q and arrs[5].size == self.N
         assert arrs[4].shape == (self.L, self.ncol)
         assert arrs[2] is None or arrs[2].shape == (self.L, self.ncol)   # z=None: inPALM never reads the incoming z
-        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64).reshape(-1)
+        assert (w is None) == (self.variant != "wdot2d"), "weight is required for (and only for) the weighted variant"
+        assert w is None or w.size == self.Q, f"weight has {0 if w is None else w.size} entries, expected {self.Q}"
         check(lib().dotsocp_upload(self._h, *[ptr(a) for a in arrs], ptr(w)))
 
     def download(self, out=None):
@@ -153,7 +156,8 @@ class Session:
         P = self.nx * self.ny
         first, last = np.ascontiguousarray(c[:P]), np.ascontiguousarray(c[-P:])
         assert not c[P:-P].any(), "model.c has a non-zero interior entry: unsupported"
-        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64).reshape(-1)
+        assert w is None or w.size == self.Q, f"weight has {0 if w is None else w.size} entries, expected {self.Q}"
         ps = ProlongScal(**{k: float(v) for k, v in scal.items()})
         check(lib().dotsocp_prolong(coarse._h, self._h, C.byref(ps), ptr(first), ptr(last), ptr(w)))
 
@@ -167,10 +171,11 @@ class Session:
     def iter_begin(self, level_opts):
         check(lib().dotsocp_iter_begin(self._h, C.byref(level_opts)))
 
-    def iterate(self, n, per_kernel=False):
+    def iterate(self, n, per_kernel=False, kkt_every=0):
+        """n iterations; kkt_every = k > 0: every k-th one is a check iteration (fused KKT sums + reduction + read-back)"""
         ms = C.c_float()
         k = (C.c_float * 4)()
-        check(lib().dotsocp_iterate(self._h, int(n), 0, C.byref(ms), k if per_kernel else None))
+        check(lib().dotsocp_iterate(self._h, int(n), int(kkt_every), C.byref(ms), k if per_kernel else None))
         return (ms.value, list(k)) if per_kernel else ms.value
 
     def iter_end(self):

@@ -69,7 +69,9 @@ typedef struct dotsocp_level_opts {
     double  tau;                /* opts.tau (inPALM/PALM); ignored by accADMM                           */
     double  sigma;              /* opts.sigma                                                          */
     double  tol;                /* opts.tol                                                            */
-    double  time_limit;         /* opts.time_limit; <=0 = absent (3600 s)                               */
+    double  time_limit;         /* opts.time_limit; NaN = absent (3600 s).  <= 0 = budget already spent: the loop runs one
+                                   iteration and one check and stops, as the reference does when the driver hands down
+                                   time_limit - Total_Time (solver_dotsocp2d.m:244, solver_socp_inPALM.m:287-289)  */
     double  rho;                /* accADMM opts.rho;   <=0 = absent (2)                                 */
     double  theta;              /* accADMM opts.theta; <=0 = absent (2 => Halpern)                      */
     double  cScale, dScale, D, E;   /* var.cScale, var.dScale, var.D, var.E  (InitialScaling)          */
@@ -125,6 +127,9 @@ int dotsocp_solve_level(const dotsocp_level_opts *opts,
                         double *phi, double *q, double *z, double *alpha, double *beta,
                         const double *c, const double *weight /* NULL unless WDOT2D */,
                         dotsocp_hist *hist, dotsocp_level_result *res);
+/* dotsocp_solve_level keeps its device session alive between calls (process lifetime, keyed by variant and grid; the MEX
+ * gateway registers this with mexAtExit).  Frees it; a no-op when nothing is cached.  DOTSOCP_CACHE_CTX=0 disables caching. */
+void dotsocp_release_cached(void);
 
 /* ------------------------------------------------------------------ device-resident session */
 typedef struct dotsocp_ctx dotsocp_ctx;
@@ -162,7 +167,8 @@ int  dotsocp_prolong(dotsocp_ctx *coarse, dotsocp_ctx *fine, const dotsocp_prolo
                      const double *c_first, const double *c_last, const double *weight);
 /* the reference loop on the resident state (sigma folding at entry, un-folding at exit, like :102-104, :335-336) */
 int  dotsocp_run(dotsocp_ctx *ctx, const dotsocp_level_opts *opts, dotsocp_hist *hist, dotsocp_level_result *res);
-/* benchmark primitive: begin (sigma folding + prologue), n plain iterations (no KKT), elapsed device ms */
+/* benchmark primitive: begin (sigma folding + prologue), n iterations, elapsed device ms.  with_kkt_every = k > 0 makes every
+ * k-th iteration a check iteration (KKT sums fused into the update kernels + reductions + read-back); 0 = no checks.      */
 int  dotsocp_iter_begin(dotsocp_ctx *ctx, const dotsocp_level_opts *opts);
 int  dotsocp_iterate(dotsocp_ctx *ctx, int n_iters, int with_kkt_every, float *elapsed_ms, float *ms_by_kernel /* [4] or NULL */);
 int  dotsocp_iter_end(dotsocp_ctx *ctx);

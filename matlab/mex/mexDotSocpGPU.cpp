@@ -54,8 +54,14 @@ static double* dbl(const mxArray* a, size_t expect, const char* what)
     return mxGetPr(a);
 }
 
+// libdotsocp keeps the device session of the last (variant, grid) alive between calls; keep this MEX file (and with it the
+// library's state) loaded for the life of the MATLAB process and free the device memory when MATLAB unloads it
+static void at_exit() { dotsocp_release_cached(); }
+
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
 {
+    static bool locked = false;
+    if (!locked) { mexLock(); mexAtExit(at_exit); locked = true; }
     if (nrhs != 8) mexErrMsgIdAndTxt("dotsocp:invalidNumInputs", "8 inputs required: phi,q,z,alpha,beta,c,weight,P");
     if (nlhs > 1) mexErrMsgIdAndTxt("dotsocp:invalidNumOutputs", "at most one output");
     const mxArray* P = prhs[7];
@@ -83,7 +89,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
     o.tau = field(P, "tau", 1.0, false);
     o.sigma = field(P, "sigma", 0, true);
     o.tol = field(P, "tol", 0, true);
-    o.time_limit = field(P, "time_limit", 0, false);
+    o.time_limit = field(P, "time_limit", mxGetNaN(), false);   // NaN = absent (3600 s); <= 0 = budget already spent
     o.rho = field(P, "rho", 0, false);
     o.theta = field(P, "theta", 0, false);
     o.cScale = field(P, "cScale", 0, true); o.dScale = field(P, "dScale", 0, true);

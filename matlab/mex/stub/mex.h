@@ -31,6 +31,7 @@ mxArray *mxCreateStructMatrix(mwSize m, mwSize n, int nfields, const char **fiel
 void mxSetField(mxArray *pa, mwIndex index, const char *fieldname, mxArray *value);
 char *mxArrayToString(const mxArray *pa);
 void mxFree(void *ptr);
+double mxGetNaN(void);
 void mexErrMsgIdAndTxt(const char *identifier, const char *fmt, ...);
 void mexWarnMsgIdAndTxt(const char *identifier, const char *fmt, ...);
 int mexPrintf(const char *fmt, ...);

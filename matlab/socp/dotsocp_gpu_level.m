@@ -15,7 +15,7 @@ if isfield(opts, 'tau'), P.tau = opts.tau; else, P.tau = 1; end
 P.ifCheckStepByStep = double(opts.ifCheckStepByStep);
 P.scaling = double(isfield(opts, 'scaling') && opts.scaling);
 if isfield(opts, 'checkPrimDualFeas'), P.checkPrimDualFeas = double(opts.checkPrimDualFeas); else, P.checkPrimDualFeas = -1; end
-if isfield(opts, 'time_limit'), P.time_limit = opts.time_limit; else, P.time_limit = 0; end
+if isfield(opts, 'time_limit'), P.time_limit = opts.time_limit; else, P.time_limit = NaN; end   % NaN = absent (3600 s)
 if isfield(opts, 'restart'), P.restart = opts.restart; else, P.restart = 0; end
 if isfield(opts, 'rho'),     P.rho = opts.rho;         else, P.rho = 0; end
 if isfield(opts, 'theta'),   P.theta = opts.theta;     else, P.theta = 0; end
@@ -31,15 +31,15 @@ P.grad_t = full(max(abs(model.grad(1, :))));
 P.grad_x = full(max(abs(model.grad(lenT + 1, :))));
 if P.ny > 1, P.grad_y = full(max(abs(model.grad(lenT + lenX + 1, :)))); else, P.grad_y = 0; end
 
-% detach the iterates from the handle so that the in-place MEX write cannot alias another variable (:89-93)
+% detach the iterates from the handle (:89-93): after this the local variables hold the ONLY reference to each array, so the
+% in-place MEX write below cannot alias another MATLAB variable and no private copy is needed (the reference loop relies on
+% exactly this; a forced copy would double the host footprint, 120 GB at 1024x1024x512).  The multilevel drivers create
+% these arrays themselves (initialize.m / jump_nextLevel.m) and keep no second handle to them.
 phi = var.phi;    var.phi   = [];
 q = var.q;        var.q     = [];
 z = var.z;        var.z     = [];
 alpha = var.alpha; var.alpha = [];
 beta = var.beta;  var.beta  = [];
-% force private copies (MATLAB is copy-on-write; same trick as CopyVar, solver_socp_accADMM.m:480-484)
-phi = phi(1:end); q = q(1:end); alpha = alpha(1:end);
-z = reshape(z(1:end), size(z));  beta = reshape(beta(1:end), size(beta));
 
 if strcmp(variant, 'wdot2d'), weight = model.weight; else, weight = []; end
 

@@ -201,11 +201,14 @@ def test_time_slab_partition_emulated_on_one_gpu(gpu, world, variant):
             state = s.download()
         results.append((hb, res, state))
     (hb1, r1, s1), (hbw, rw, sw) = results
+    # every sum is reduced per time level and then over the levels in a fixed order, and every kernel's per-element
+    # arithmetic is independent of the partition: the slab count must not change a single bit
     assert r1.iters == rw.iters and r1.hist_len == rw.hist_len
-    assert np.abs(hb1.kkt[:r1.hist_len] - hbw.kkt[:rw.hist_len]).max() < 1e-12
-    assert abs(r1.sigma - rw.sigma) <= 1e-13 * abs(r1.sigma)
+    assert np.array_equal(hb1.kkt[:r1.hist_len], hbw.kkt[:rw.hist_len])
+    assert np.array_equal(hb1.priVal[:r1.hist_len], hbw.priVal[:rw.hist_len])
+    assert r1.sigma == rw.sigma
     for a, b, name in zip(s1, sw, ("phi", "q", "z", "alpha", "beta")):
-        assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), name
+        assert np.array_equal(a, b), name
 
 
 @pytest.mark.parametrize("xchg", ["copy", "direct"])
@@ -235,9 +238,73 @@ def test_time_slabs_with_fused_transpose_pack(gpu, world, xchg, monkeypatch):
             out.append((hb, res, s.download()))
     (hb1, r1, s1), (hbw, rw, sw) = out
     assert r1.iters == rw.iters == 60 and r1.hist_len == rw.hist_len
-    assert np.abs(hb1.kkt[:r1.hist_len] - hbw.kkt[:rw.hist_len]).max() < 1e-12
+    assert np.array_equal(hb1.kkt[:r1.hist_len], hbw.kkt[:rw.hist_len])
     for a, b, name in zip(s1, sw, ("phi", "q", "z", "alpha", "beta")):
-        assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), name
+        assert np.array_equal(a, b), name
+
+
+def _level_run(variant, nt, nx, ny, rho0, rho1, weight, opts, world=1):
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import driver, solver
+    var, model = driver.initialize(rho0, rho1, nt)
+    if weight is not None:
+        model.weight = weight
+    driver.InitialScaling(var, model, True, None, variant)
+    o = solver.make_level_opts(variant, "inPALM", var, opts, model)
+    with dp.Session(variant, nt, nx, ny, world=world) as s:
+        s.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c, weight)
+        hb, res = s.run(o)
+        return hb, res, s.download()
+
+
+@pytest.mark.parametrize("variant", ["dot2d", "wdot2d", "dot1d"])
+def test_fused_kkt_check_matches_the_standalone_kkt_kernels(gpu, variant, monkeypatch):
+    """inPALM check iterations accumulate the KKT sums inside k_qstep / k_mult (no extra pass over the 10-column arrays);
+    DOTSOCP_KKT=separate (read when the session is created) selects the stand-alone KKT kernels that PALM / acc-ADMM use.
+    Same check schedule and sigma decisions, residuals equal up to the rounding of a different summation order, and the
+    iterates -- which the sums only steer -- identical bit for bit.  Also on emulated slabs."""
+    if variant == "dot1d":
+        nt, nx, ny = 17, 257, 1
+        rho0, rho1 = O.get_example1d("gaussian", nx)
+        weight, opts = None, {"tol": 1e-5, "maxit": 300}
+    else:
+        nt, nx, ny = 17, 37, 33
+        rho0, rho1 = O.get_example2d("example2", nx, ny)
+        weight = O.gene_weight_circle(nt, nx, ny) if variant == "wdot2d" else None
+        opts = {"tol": 1e-4 if weight is None else 1e-3, "maxit": 300}
+    opts.update(tau=1.9, sigma=1.0, ifCheckStepByStep=False, scaling=True)
+    for world in (1, 3):
+        monkeypatch.setenv("DOTSOCP_KKT", "separate")
+        hb_s, r_s, st_s = _level_run(variant, nt, nx, ny, rho0, rho1, weight, opts, world)
+        monkeypatch.delenv("DOTSOCP_KKT")
+        hb_f, r_f, st_f = _level_run(variant, nt, nx, ny, rho0, rho1, weight, opts, world)
+        assert r_f.iters == r_s.iters and r_f.hist_len == r_s.hist_len > 5
+        assert np.array_equal(hb_f.iter[:r_f.hist_len], hb_s.iter[:r_s.hist_len])
+        assert np.abs(hb_f.kkt[:r_f.hist_len] - hb_s.kkt[:r_s.hist_len]).max() < 1e-13
+        assert np.abs(hb_f.priVal[:r_f.hist_len] - hb_s.priVal[:r_s.hist_len]).max() < 1e-13
+        assert np.abs(hb_f.pdGap[:r_f.hist_len] - hb_s.pdGap[:r_s.hist_len]).max() < 1e-13
+        assert r_f.sigma == r_s.sigma
+        for a, b, name in zip(st_f, st_s, ("phi", "q", "z", "alpha", "beta")):
+            assert np.array_equal(a, b), (name, world)
+
+
+@pytest.mark.parametrize("variant", ["dot2d", "wdot2d"])
+def test_two_time_steps_per_barrier_is_bit_identical_to_one(gpu, variant, monkeypatch):
+    """k_mult marches two time steps per CTA barrier (their projection chains are independent and interleave in one
+    instruction stream); DOTSOCP_KM_TU=1 selects the one-step march.  Odd and even numbers of levels, slabs and pieces."""
+    for nt, world in ((18, 1), (17, 1), (23, 3)):
+        nx, ny = 41, 35
+        rho0, rho1 = O.get_example2d("example2", nx, ny)
+        weight = O.gene_weight_circle(nt, nx, ny) if variant == "wdot2d" else None
+        opts = {"tol": 1e-12, "maxit": 30, "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": False, "scaling": True}
+        monkeypatch.setenv("DOTSOCP_KM_TU", "1")
+        hb1, r1, st1 = _level_run(variant, nt, nx, ny, rho0, rho1, weight, opts, world)
+        monkeypatch.delenv("DOTSOCP_KM_TU")
+        hb2, r2, st2 = _level_run(variant, nt, nx, ny, rho0, rho1, weight, opts, world)
+        assert r1.iters == r2.iters == 30
+        assert np.array_equal(hb1.kkt[:r1.hist_len], hb2.kkt[:r2.hist_len])
+        for a, b, name in zip(st1, st2, ("phi", "q", "z", "alpha", "beta")):
+            assert np.array_equal(a, b), (name, nt, world)
 
 
 CHUNK_SCRIPT = """

@@ -69,3 +69,57 @@ def test_baseline_config2_weighted_256x256x128(gpu):
     rho0, rho1, nt, levelN, opts = m.config_wdot2d()
     out, _, ML, rh = dp.solver_wdotsocp2d(rho0, rho1, nt, levelN, opts, "inPALM")
     _check_against_golden(out, ML, rh, gold["wdot2d_circle_256x256x128"], 2)
+
+
+def _c4_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_c4", os.path.join(ROOT, "tests", "golden", "make_golden_c4.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def check_c4_golden(hb, res, state, gold, tol_kkt=1e-8):
+    """shared by this test and tests/dist_parity_big.py (the same run on 2/4/8 GPUs)"""
+    m = _c4_module()
+    n = res.hist_len
+    assert res.iters == gold["iters"] and [int(v) for v in hb.iter[:n]] == gold["hist_iter"]
+    assert np.abs(hb.kkt[:n] - np.array(gold["kkt"])).max() < tol_kkt, np.abs(hb.kkt[:n] - np.array(gold["kkt"])).max()
+    assert np.abs(hb.pdGap[:n] - np.array(gold["pdGap"])).max() < 1e-8
+    for name in ("priVal", "dualVal"):
+        a, b = getattr(hb, name)[:n], np.array(gold[name])
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), name
+    assert abs(res.sigma - gold["sigma"]) <= 1e-12 * gold["sigma"]
+    for a, name in zip(state, ("phi", "q", "z", "alpha", "beta")):
+        fp = gold["final"][name]
+        v = a.reshape(-1, order="F" if a.ndim == 2 else "C")
+        nrm = float(np.sqrt(np.dot(v, v)))
+        assert abs(nrm - fp["norm2"]) <= 1e-9 * fp["norm2"], (name, nrm, fp["norm2"])
+        got = np.array([v[i] for i in m.sample_index(v.size)])
+        scale = max(1.0, float(np.abs(np.array(fp["samples"])).max()))
+        assert np.abs(got - np.array(fp["samples"])).max() <= 1e-9 * scale, name
+
+
+@pytest.mark.gpu
+def test_baseline_config3_mixture_512x512x256_checked_iterations(gpu):
+    """BASELINE.json configs[3]: example2 (Gaussian -> mixture) at 512x512x256 cells, one level from the reference's initial
+    state, 12 inPALM iterations with ifCheckStepByStep: every KKT row, the objective values and fingerprints of the final
+    iterates against the CPU oracle's golden (tests/golden/solver_c4.json, 14 minutes and 50 GB on the CPU)."""
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import driver, solver
+    with open(os.path.join(ROOT, "tests", "golden", "solver_c4.json")) as f:
+        gold = json.load(f)
+    nt, nx, ny = gold["grid_nodes"]
+    m = _c4_module()
+    rho0, rho1 = m.problem(nx, ny)
+    var, model = driver.initialize(rho0, rho1, nt)
+    driver.InitialScaling(var, model, True, None, "dot2d")
+    assert [var.cScale, var.dScale, var.D, var.E] == pytest.approx(gold["scal"], rel=1e-13)
+    opts = {"tol": 1e-4, "maxit": gold["iters"], "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": True, "scaling": True}
+    o = solver.make_level_opts("dot2d", "inPALM", var, opts, model)
+    with dp.Session("dot2d", nt, nx, ny) as s:
+        s.upload(var.phi, var.q, None, var.alpha, var.beta, model.c)
+        del var
+        hb, res = s.run(o)
+        state = s.download()
+    check_c4_golden(hb, res, state, gold)
