@@ -52,6 +52,10 @@ class ProlongScal(C.Structure):
                 ("phi_scale", C.c_double), ("q_scale", C.c_double), ("alpha_scale", C.c_double), ("beta_scale", C.c_double)]
 
 
+class RecoverScal(C.Structure):
+    _fields_ = [("alpha_recover", C.c_double), ("q_recover", C.c_double)]
+
+
 class Hist(C.Structure):
     _fields_ = [
         ("cap", C.c_int32), ("kkt", C.c_void_p), ("time", C.c_void_p), ("iter", C.c_void_p),
@@ -64,7 +68,7 @@ EXPORTS = [
     "dotsocp_mexBFd", "dotsocp_mexBFdConj", "dotsocp_mexProjSoc", "dotsocp_mexBFd1d", "dotsocp_mexBFdConj1d",
     "dotsocp_poisson", "dotsocp_dctn", "dotsocp_solve_level", "dotsocp_release_cached",
     "dotsocp_nccl_unique_id", "dotsocp_create", "dotsocp_destroy", "dotsocp_upload", "dotsocp_download",
-    "dotsocp_prolong", "dotsocp_run", "dotsocp_iter_begin", "dotsocp_iterate", "dotsocp_iter_end", "dotsocp_launch_count",
+    "dotsocp_create_refined", "dotsocp_prolong", "dotsocp_recover", "dotsocp_run", "dotsocp_iter_begin", "dotsocp_iterate", "dotsocp_iter_end", "dotsocp_launch_count",
 ]
 
 _lib = None
@@ -101,6 +105,8 @@ def lib():
     L.dotsocp_upload.argtypes = [P, P, P, P, P, P, P, P]
     L.dotsocp_download.argtypes = [P, P, P, P, P, P]
     L.dotsocp_prolong.argtypes = [P, P, C.POINTER(ProlongScal), P, P, P]
+    L.dotsocp_create_refined.argtypes = [C.POINTER(P), P]
+    L.dotsocp_recover.argtypes = [P, C.POINTER(RecoverScal), P, P, P, P, P, P, P, P, P, P, P]
     L.dotsocp_run.argtypes = [P, C.POINTER(LevelOpts), C.POINTER(Hist), C.POINTER(LevelResult)]
     L.dotsocp_iter_begin.argtypes = [P, C.POINTER(LevelOpts)]
     L.dotsocp_iterate.argtypes = [P, I, I, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -137,5 +143,6 @@ class HistBuffers:
         self.pdGap = np.full(cap, np.inf)
         self.priVal = np.full(cap, np.inf)
         self.dualVal = np.full(cap, np.inf)
-        self.c = Hist(cap, ptr(self.kkt), ptr(self.time), ptr(self.iter), ptr(self.pdGap), ptr(self.priVal),
+        # kkt is ROW-major on purpose (dotsocp_hist: kkt[i*7 + j]): hand over the raw address, not ptr()
+        self.c = Hist(cap, self.kkt.ctypes.data, ptr(self.time), ptr(self.iter), ptr(self.pdGap), ptr(self.priVal),
                       ptr(self.dualVal))

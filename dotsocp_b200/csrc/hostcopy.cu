@@ -88,7 +88,7 @@ HostCopier::HostCopier()
     // threads: the host cores divided among the ranks that share the node (torchrun exports LOCAL_WORLD_SIZE)
     const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     const int lws = env_int("LOCAL_WORLD_SIZE", 1);
-    const int nthr = env_int("DOTSOCP_COPY_THREADS", std::min(8, std::max(2, hw / lws)));
+    const int nthr = env_int("DOTSOCP_COPY_THREADS", std::min(16, std::max(2, hw / lws)));
     chunk_ = (size_t)env_int("DOTSOCP_COPY_CHUNK_MB", 32) << 20;
     pool_ = new WorkerPool(nthr);
     ok_ = true;

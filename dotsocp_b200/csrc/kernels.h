@@ -105,6 +105,26 @@ void launch_kkt_nodes(const KktArgs& a, bool weighted, cudaStream_t st);        
 void launch_kkt_fused_reduce(const Geo& g, const TRange& tr, const KktFused& k, cudaStream_t st);   // partial_q / partial_m -> rows
 void launch_norms(const KktArgs& a, bool one_d, cudaStream_t st);                      // -> rows tn0..tn1-1, slots NR_*
 void launch_levels_total(const double* lvl, int nt, double* out, cudaStream_t st);     // out[KSL] = fixed-order sum over the rows
+// stage 2 for any producer: partial[level][block][K] -> slots[k] of rows t0 .. t0+nlev-1
+void level_reduce(const double* partial, int nb, int K, const int* slots, int t0, int nlev, double* lvl, cudaStream_t st);
+// ---- output recovery on the device (recover.cu): recover_RhoE.m:13-25, recover_q.m:12-22, check_massConservation.m:16-34
+enum { RC_RHO = 0, RC_EX, RC_EY, RC_Q0, RC_BX, RC_BY };
+enum { RS_SUMRHO = 0, RS_SUMNEG, RS_W2, RS_COUNT };
+struct RecoverArgs {
+    Geo g;
+    TRange tr;
+    double arec, qrec;        // cScale*D (var.alpha = (cScale*D)*alpha), dScale/D (var.q = (dScale/D)*q): recoverOrgVar
+    const double* alpha;
+    const double* q;
+    const double* weight;     // NULL unless weighted
+    const double* rho0;       // nx*ny planes (device): model.rho0(:), model.rho1(:)
+    const double* rho1;
+    double* out;              // node-indexed scratch (global index space), levels of the slab
+    double* partial;
+    double* lvl;
+};
+void launch_recover(const RecoverArgs& a, int which, bool weighted, cudaStream_t st);      // one field into a.out
+void launch_recover_stats(const RecoverArgs& a, bool weighted, bool one_d, cudaStream_t st);   // rows tn0..tn1-1, slots RS_*
 // x = (x * mul) / div, elementwise (mul == 1 and div == 1 are exact no-ops)
 // level transfer on the device (prolong.cu): coarse (phi, beta) of a finished level -> fine (phi, q, alpha, beta) of the next,
 // with the recoverOrgVar / InitialScaling factors folded in exactly where the host path rounds them
@@ -113,8 +133,13 @@ struct ProlongScal {
     double grad_t, grad_x, grad_y;      // unscaled forward-difference weights of the fine grid: 1/ht, 1/hx, 1/hy
     double phi_scale, q_scale, alpha_scale, beta_scale;   // 1/dScale, D/dScale, 1/cScale/D, 1/cScale/E of the fine level
 };
-int launch_prolong(const Geo& gc, const Geo& gf, const ProlongScal& s, const double* phi_c, const double* beta_c, double* phi_f,
-                   double* q_f, double* alpha_f, double* beta_f, const double* weight_f, cudaStream_t st);
+// stages of the transfer, each on a range of fine time levels (prolong.cu); dotsocp_prolong strings them together per slab
+void launch_prolong_phi(const Geo& gc, const Geo& gf, double rec, const double* phi_c, double* phi_f, int t0, int t1, cudaStream_t st);
+void launch_prolong_q(const Geo& gf, const ProlongScal& s, const double* phi_f, const double* weight_f, double* q_f, int t0, int t1,
+                      cudaStream_t st);
+void launch_prolong_beta(const Geo& gc, const Geo& gf, double rec, const double* beta_c, double* beta_f, int c0, int c1, cudaStream_t st);
+void launch_mul_inplace(double* x, i64 n, double s, cudaStream_t st);
+void launch_prolong_alpha(double* alpha, const double* weight, i64 n, double scale, cudaStream_t st);
 void launch_scale(double* x, i64 n, double mul, double div, cudaStream_t st);
 // Halpern / affine extrapolation of solver_socp_accADMM.m:371-388:
 //   x = c1*x0 + c2*((1-rho)*xold + rho*x) ; xold = x ; if (copy_anchor) x0 = x

@@ -9,6 +9,7 @@
 //   beta/z            : 10 planes of L = (nt-1)*nx*ny doubles (structure of arrays)
 // All kernels are HBM-bound streaming kernels: warps run along y (coalesced), k_mult marches along t.
 #include "kernels.h"
+#include "reduce.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -323,9 +324,6 @@ __device__ __forceinline__ void q_update(i64 e, double aphi, double dinv_plain, 
     }
 }
 
-template <int K, int NT>
-__device__ __forceinline__ void block_reduce_store(double (&s)[K], double* __restrict__ partial, i64 block);
-
 template <bool WEIGHTED, bool ACC, bool KKT>
 __global__ void __launch_bounds__(256) k_qstep(Geo g, int tn0, IterScal sc, const double* __restrict__ phi,
                                                const double* __restrict__ q2, const double* __restrict__ weight,
@@ -402,12 +400,14 @@ void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st,
 // 10-column temporaries never touch HBM.  The x+1 / y+1 neighbours' w (columns 1,3 / 5,7) come through shared
 // memory; the t-1 layer's columns 3,4,7,8 are carried in registers.
 //
-// A step has two phases: phase 1 is cell-local (loads, two projections, the multiplier update, publish w to shared memory),
-// phase 2 gathers the neighbours' w after the CTA barrier and emits q2 / rhs.  TU consecutive time steps share one barrier:
-// their phase-1 chains are independent (the z-step of a cell needs nothing from the cell below it), so the compiler
-// interleaves the TU sqrt/division chains in one instruction stream and all loads of the TU steps are in flight together.
+// A step has three stages: LOAD (the 25 values of the step, nothing else), phase 1 (cell-local: two projections, the
+// multiplier update, publish w to shared memory) and phase 2 (gather the neighbours' w after the CTA barrier, emit q2 / rhs).
+// ncu on the round-1 kernel: 55 % of the warp samples waited on the first use of a step's loads (long scoreboard), i.e. the
+// HBM latency was exposed once per step.  PF = true keeps the loaded values of step t+1 in a second register set that is
+// filled BEFORE step t is computed (software pipeline, one 255-register CTA per SM), so a step's loads have a whole step of
+// arithmetic to arrive.  PF = false is the round-1 schedule (two 128-register CTAs per SM); DOTSOCP_KM_PF selects.
 //
-// KKT (check iterations, TU = 1): the same march also accumulates every KKT term that lives on the data in registers
+// KKT (check iterations): the same march also accumulates every KKT term that lives on the data in registers
 // (solver_socp_inPALM.m:225-244, compute_kkt_dot_complement.m) -- z, beta, z2, alpha and q are all there -- and leaves one
 // partial sum per (time level, tile); s(BF)^* beta uses a second set of exchange planes.  The remaining terms (A*phi, q,
 // alpha norms, <c,phi>) come from k_qstep<KKT>.
@@ -424,8 +424,8 @@ __device__ __forceinline__ double uval(double q, double a, double w)
 #ifndef KM_TY
 #define KM_TY 32         // tile columns (y, contiguous) per CTA: one warp per tile row
 #endif
-#ifndef KM_TU
-#define KM_TU 2          // time steps per barrier in the update kernel (DOTSOCP_KM_TU=1 selects the one-step kernel at run time)
+#ifndef KM_PF
+#define KM_PF 1          // default of DOTSOCP_KM_PF: register prefetch of the next time step in the update kernel
 #endif
 
 struct KktDev {          // scalars of the fused KKT terms
@@ -447,7 +447,18 @@ struct MultKeepK {                    // KKT extras
     double cell[KM_RHOFQ + 1];        // the 7 cell sums of this thread
 };
 
-template <int TX, int TY, int TU, bool WEIGHTED, bool ONE_D, bool UPDATE, bool EDGE, bool KKT>
+// the values one time step reads from HBM
+struct MultLoad {
+    double b[10];                                 // beta of the cell
+    double q0n, bxm1n, bx1n, bym1n, by1n;         // new q: q0 of the cell, bx / by at node level t+1
+    double q0o, bxm1o, bx1o, bym1o, by1o;         // old q (UPDATE)
+    double a0;                                    // alpha0 of the cell
+    double al_xm, al_x, al_ym, al_y;              // alpha on the x / y edges of node level t (owner threads)
+    double wt0, wt_xm, wt_x, wt_ym, wt_y;         // weights on the same edges (WEIGHTED)
+    double cv;                                    // c on the first / last time level
+};
+
+template <int TX, int TY, bool PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool EDGE, bool KKT>
 __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int kkt_t0, const IterScal& sc, const KktDev& kd,
                                             const double* __restrict__ qo, const double* __restrict__ qn,
                                             const double* __restrict__ alpha, const double* __restrict__ weight,
@@ -455,7 +466,8 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
                                             double* __restrict__ q2, double* __restrict__ rhs, const double* __restrict__ c0,
                                             const double* __restrict__ c1, double* __restrict__ kpart)
 {
-    static_assert(!KKT || (UPDATE && TU == 1), "the KKT variant is the single-step update kernel");
+    static_assert(!KKT || UPDATE, "the KKT variant is an update kernel");
+    constexpr int TU = 1;
     constexpr int NPL = KKT ? 9 : 4;   // exchange planes: w1,w3,w5,w7 (+ b1,b3,b5,b7, rho)
     extern __shared__ __align__(16) double dyn_smem[];
     double (*sh)[TU][NPL][TX][TY] = reinterpret_cast<double (*)[TU][NPL][TX][TY]>(dyn_smem);
@@ -507,57 +519,78 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
     double wp3n = 0.0, wp4 = 0.0, wp7n = 0.0, wp8 = 0.0, u0p = 0.0;     // carried from the cell layer below
     double bp3n = 0.0, bp4 = 0.0, bp7n = 0.0, bp8 = 0.0, a0p = 0.0, wa0p = 0.0;   // KKT: same for beta / alpha0
 
+    // ---- LOAD: everything step t reads from HBM, and nothing else ------------------------------------------------------
+    auto load = [&](int t, MultLoad& ld) {
+        const bool cell = t < g.nt - 1;
+        const i64 cidx = (i64)t * g.P + node;
+        ld.al_xm = ld.al_x = ld.al_ym = ld.al_y = 0.0;
+        ld.wt0 = ld.wt_xm = ld.wt_x = ld.wt_ym = ld.wt_y = 1.0;
+        ld.cv = 0.0;
+        if (owner) {
+            const i64 ox = (i64)t * g.PBX, oy = (i64)t * g.PBY;
+            if (hxm) ld.al_xm = al_bx[ox + ibxm];
+            if (hxp) ld.al_x = al_bx[ox + ibx];
+            if (hym) ld.al_ym = al_by[oy + ibym];
+            if (hyp) ld.al_y = al_by[oy + iby];
+            if (WEIGHTED) {
+                if (hxm) ld.wt_xm = w_bx[ox + ibxm];
+                if (hxp) ld.wt_x = w_bx[ox + ibx];
+                if (hym) ld.wt_ym = w_by[oy + ibym];
+                if (hyp) ld.wt_y = w_by[oy + iby];
+            }
+            if (t == 0) ld.cv = c0[node];
+            else if (!cell) ld.cv = c1[node];
+        }
+        if (cell && valid) {
+            const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
+            if (WEIGHTED) ld.wt0 = weight[cidx];
+#pragma unroll
+            for (int j = 0; j < 10; j++) ld.b[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0 : beta[(i64)j * L + cidx];
+            ld.q0n = qn[cidx];
+            ld.a0 = alpha[cidx];
+            ld.bxm1n = hxm ? qn_bx[o1x + ibxm] : 0.0;
+            ld.bx1n = hxp ? qn_bx[o1x + ibx] : 0.0;
+            ld.bym1n = hym ? qn_by[o1y + ibym] : 0.0;
+            ld.by1n = hyp ? qn_by[o1y + iby] : 0.0;
+            if (UPDATE) {
+                ld.q0o = qo[cidx];
+                ld.bxm1o = hxm ? qo_bx[o1x + ibxm] : 0.0;
+                ld.bx1o = hxp ? qo_bx[o1x + ibx] : 0.0;
+                ld.bym1o = hym ? qo_by[o1y + ibym] : 0.0;
+                ld.by1o = hyp ? qo_by[o1y + iby] : 0.0;
+            }
+        }
+    };
+
     // ---- phase 1 of step t into exchange slot (buf, u) ---------------------------------------------------------------
-    auto phase1 = [&](int t, int buf, int u, MultKeep& k, MultKeepK& kk) {
+    auto phase1 = [&](int t, int buf, int u, const MultLoad& ld, MultKeep& k, MultKeepK& kk) {
         const bool cell = t < g.nt - 1;
         const i64 cidx = (i64)t * g.P + node;
         double w[10];
 #pragma unroll
         for (int j = 0; j < 10; j++) w[j] = 0.0;
-        double a0 = 0.0, wt0 = 1.0;
-        // level-t alpha (and weight) of the rhs stencil: independent of the projections, issued first
-        double al_xm = 0.0, al_x = 0.0, al_ym = 0.0, al_y = 0.0, wt_xm = 1.0, wt_x = 1.0, wt_ym = 1.0, wt_y = 1.0;
-        k.cv = 0.0;
-        if (owner) {
-            const i64 ox = (i64)t * g.PBX, oy = (i64)t * g.PBY;
-            if (hxm) al_xm = al_bx[ox + ibxm];
-            if (hxp) al_x = al_bx[ox + ibx];
-            if (hym) al_ym = al_by[oy + ibym];
-            if (hyp) al_y = al_by[oy + iby];
-            if (WEIGHTED) {
-                if (hxm) wt_xm = w_bx[ox + ibxm];
-                if (hxp) wt_x = w_bx[ox + ibx];
-                if (hym) wt_ym = w_by[oy + ibym];
-                if (hyp) wt_y = w_by[oy + iby];
-            }
-            if (t == 0) k.cv = c0[node];
-            else if (!cell) k.cv = c1[node];
-        }
-        if (WEIGHTED && cell && valid) wt0 = weight[cidx];
+        double a0 = 0.0;
+        const double wt0 = ld.wt0;
+        const double al_xm = ld.al_xm, al_x = ld.al_x, al_ym = ld.al_ym, al_y = ld.al_y;
+        const double wt_xm = ld.wt_xm, wt_x = ld.wt_x, wt_ym = ld.wt_ym, wt_y = ld.wt_y;
+        k.cv = ld.cv;
         if (KKT) {
 #pragma unroll
             for (int j = 0; j <= KM_RHOFQ; j++) kk.cell[j] = 0.0;
             kk.b2 = kk.b4 = kk.b6 = kk.b8 = kk.fb0 = 0.0;
         }
         if (cell && valid) {
-            const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
             double b[10];
 #pragma unroll
-            for (int j = 0; j < 10; j++) b[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0 : beta[(i64)j * L + cidx];
-            cn.q0 = qn[cidx];
-            a0 = alpha[cidx];
-            cn.bxm1 = hxm ? qn_bx[o1x + ibxm] : 0.0;
-            cn.bx1 = hxp ? qn_bx[o1x + ibx] : 0.0;
-            cn.bym1 = hym ? qn_by[o1y + ibym] : 0.0;
-            cn.by1 = hyp ? qn_by[o1y + iby] : 0.0;
+            for (int j = 0; j < 10; j++) b[j] = ld.b[j];
+            cn.q0 = ld.q0n;
+            a0 = ld.a0;
+            cn.bxm1 = ld.bxm1n; cn.bx1 = ld.bx1n; cn.bym1 = ld.bym1n; cn.by1 = ld.by1n;
             double z2n[10];
             cell_z2(cn, sc, hxm, hxp, hym, hyp, z2n);
             if (UPDATE) {
-                co.q0 = qo[cidx];
-                co.bxm1 = hxm ? qo_bx[o1x + ibxm] : 0.0;
-                co.bx1 = hxp ? qo_bx[o1x + ibx] : 0.0;
-                co.bym1 = hym ? qo_by[o1y + ibym] : 0.0;
-                co.by1 = hyp ? qo_by[o1y + iby] : 0.0;
+                co.q0 = ld.q0o;
+                co.bxm1 = ld.bxm1o; co.bx1 = ld.bx1o; co.bym1 = ld.bym1o; co.by1 = ld.by1o;
                 double v[10];
                 cell_z2(co, sc, hxm, hxp, hym, hyp, v);
 #pragma unroll
@@ -763,30 +796,19 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
 #undef ADDTERM
     };
 
-    MultKeep keep[TU];
-    MultKeepK keepk[KKT ? TU : 1];
-    int t = t_start, it = 0;
-    if (TU > 1) {
-        for (; t + TU <= tr.tn1; t += TU, it++) {
-            const int buf = it & 1;
-#pragma unroll
-            for (int u = 0; u < TU; u++) phase1(t + u, buf, u, keep[u], keepk[0]);
-            __syncthreads();
-            double ks[KM_COUNT];
-#pragma unroll
-            for (int u = 0; u < TU; u++) phase2(t + u, buf, u, keep[u], keepk[0], ks);
-        }
-    }
-    for (; t < tr.tn1; t++, it++) {
+    MultKeep keep;
+    MultKeepK keepk;
+    // one step: phase 1 on the loaded values, barrier, phase 2 (+ the per-level KKT partial of the tile)
+    auto step = [&](int t, int it, const MultLoad& ld) {
         const int buf = it & 1;
-        phase1(t, buf, 0, keep[0], keepk[0]);
+        phase1(t, buf, 0, ld, keep, keepk);
         __syncthreads();
         double ks[KM_COUNT];
         if (KKT) {
 #pragma unroll
             for (int j = 0; j < KM_COUNT; j++) ks[j] = 0.0;
         }
-        phase2(t, buf, 0, keep[0], keepk[0], ks);
+        phase2(t, buf, 0, keep, keepk, ks);
         if (KKT && t >= tr.tn0) {
             // one partial per (time level, tile): warp shuffles, then the TX warp sums in fixed order
             __shared__ double red[KM_COUNT][TX];
@@ -807,11 +829,30 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
                 kpart[((i64)(t - kkt_t0) * ((i64)gridDim.x * gridDim.y) + tile) * KM_COUNT + tid] = v;
             }
         }
+    };
+    int t = t_start, it = 0;
+    if (PF) {
+        // software pipeline, unrolled by two so that the two register sets swap roles without moves
+        MultLoad la, lb;
+        load(t, la);
+        for (; t + 2 <= tr.tn1; t += 2, it += 2) {
+            load(t + 1, lb);
+            step(t, it, la);
+            if (t + 2 < tr.tn1) load(t + 2, la);
+            step(t + 1, it + 1, lb);
+        }
+        if (t < tr.tn1) step(t, it, la);
+    } else {
+        for (; t < tr.tn1; t++, it++) {
+            MultLoad ld;
+            load(t, ld);
+            step(t, it, ld);
+        }
     }
 }
 
-template <int TX, int TY, int TU, bool WEIGHTED, bool ONE_D, bool UPDATE, bool KKT>
-__global__ void __launch_bounds__(TX* TY, (TU == 1 && !KKT) ? 2 : 1)
+template <int TX, int TY, bool PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool KKT>
+__global__ void __launch_bounds__(TX* TY, (PF || KKT) ? 1 : 2)
 k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, const double* __restrict__ qo, const double* __restrict__ qn,
        const double* __restrict__ alpha, const double* __restrict__ weight, const double* __restrict__ beta,
        double* __restrict__ beta_out, double* __restrict__ q2, double* __restrict__ rhs, const double* __restrict__ c0,
@@ -828,10 +869,10 @@ k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, const double* __res
     const int x0 = blockIdx.y * (TX - 1), y0 = blockIdx.x * (TY - 1);
     const bool interior = !ONE_D && x0 >= 1 && x0 + TX - 1 <= g.nx - 2 && y0 >= 1 && y0 + TY - 1 <= g.ny - 2;
     if (interior)
-        k_mult_body<TX, TY, TU, WEIGHTED, ONE_D, UPDATE, false, KKT>(g, tr, kkt_t0, sc, kd, qo, qn, alpha, weight, beta, beta_out, q2,
+        k_mult_body<TX, TY, PF, WEIGHTED, ONE_D, UPDATE, false, KKT>(g, tr, kkt_t0, sc, kd, qo, qn, alpha, weight, beta, beta_out, q2,
                                                                      rhs, c0, c1, kpart);
     else
-        k_mult_body<TX, TY, TU, WEIGHTED, ONE_D, UPDATE, true, KKT>(g, tr, kkt_t0, sc, kd, qo, qn, alpha, weight, beta, beta_out, q2,
+        k_mult_body<TX, TY, PF, WEIGHTED, ONE_D, UPDATE, true, KKT>(g, tr, kkt_t0, sc, kd, qo, qn, alpha, weight, beta, beta_out, q2,
                                                                     rhs, c0, c1, kpart);
 }
 
@@ -874,16 +915,16 @@ void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cu
     // Cutting the time range into pieces (grid.z) lets the CTA count land just below a whole number of rounds; each extra
     // piece costs one replayed cell layer.  DOTSOCP_KM_CHUNKS=n forces n pieces.
     static const int forced = [] { const char* e = getenv("DOTSOCP_KM_CHUNKS"); return e ? atoi(e) : 0; }();
-    const char* tu_env = getenv("DOTSOCP_KM_TU");   // read per launch: tests and A/B runs switch it inside one process
-    const int tu = (tu_env && atoi(tu_env) == 1) ? 1 : KM_TU;
-#define KM(TU, W, O, U, K)                                                                                            \
+    const char* pf_env = getenv("DOTSOCP_KM_PF");   // read per launch: tests and A/B runs switch it inside one process
+    const bool pf = pf_env ? atoi(pf_env) != 0 : (KM_PF != 0);
+#define KM(PF, W, O, U, K)                                                                                            \
     {                                                                                                                 \
-        constexpr size_t smem = (size_t)2 * TU * (K ? 9 : 4) * TX * TY * sizeof(double);                              \
+        constexpr size_t smem = (size_t)2 * (K ? 9 : 4) * TX * TY * sizeof(double);                                   \
         static int slots = 0;                                                                                         \
         if (!slots) {                                                                                                 \
-            cudaFuncSetAttribute(k_mult<TX, TY, TU, W, O, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            cudaFuncSetAttribute(k_mult<TX, TY, PF, W, O, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             int per_sm = 0, dev = 0, sms = 0;                                                                         \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mult<TX, TY, TU, W, O, U, K>, TX * TY, smem);    \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mult<TX, TY, PF, W, O, U, K>, TX * TY, smem);    \
             cudaGetDevice(&dev);                                                                                      \
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);                                        \
             slots = per_sm > 0 && sms > 0 ? per_sm * sms : 1;                                                         \
@@ -891,17 +932,17 @@ void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cu
         const int nchunk = forced > 0 ? std::min(forced, std::max(1, a.tr.tc1 - a.tr.tc0))                            \
                                       : km_pick_chunks((long long)grid.x * grid.y, a.tr.tc1 - a.tr.tc0, slots);       \
         grid.z = (unsigned)nchunk;                                                                                    \
-        k_mult<TX, TY, TU, W, O, U, K><<<grid, block, smem, st>>>(a.g, a.tr, nchunk, a.sc, kd, a.q_old, a.q_new, a.alpha, \
+        k_mult<TX, TY, PF, W, O, U, K><<<grid, block, smem, st>>>(a.g, a.tr, nchunk, a.sc, kd, a.q_old, a.q_new, a.alpha, \
                                                                   a.weight, a.beta_in, a.beta_out, a.q2, a.rhs, a.c0, a.c1, kpart); \
     }
     if (kkt && update) {
-        if (one_d) KM(1, false, true, true, true) else if (weighted) KM(1, true, false, true, true) else KM(1, false, false, true, true)
+        if (one_d) KM(false, false, true, true, true) else if (weighted) KM(false, true, false, true, true) else KM(false, false, false, true, true)
     } else if (one_d) {
-        if (update) KM(1, false, true, true, false) else KM(1, false, true, false, false)
+        if (update) KM(false, false, true, true, false) else KM(false, false, true, false, false)
     } else if (weighted) {
-        if (!update) KM(1, true, false, false, false) else if (tu == 1) KM(1, true, false, true, false) else KM(KM_TU, true, false, true, false)
+        if (!update) KM(false, true, false, false, false) else if (pf) KM(true, true, false, true, false) else KM(false, true, false, true, false)
     } else {
-        if (!update) KM(1, false, false, false, false) else if (tu == 1) KM(1, false, false, true, false) else KM(KM_TU, false, false, true, false)
+        if (!update) KM(false, false, false, false, false) else if (pf) KM(true, false, false, true, false) else KM(false, false, false, true, false)
     }
 #undef KM
 }
@@ -1018,31 +1059,6 @@ void launch_cells_update(const Geo& g, const IterScal& sc, bool one_d, int mode,
 // ---------------------------------------------------------------------------------------------------------------
 // Deterministic reductions: every CTA writes its K partial sums, a single CTA adds them in a fixed tree order.
 // ---------------------------------------------------------------------------------------------------------------
-template <int K, int NT>
-__device__ __forceinline__ void block_reduce_store(double (&s)[K], double* __restrict__ partial, i64 block)
-{
-    __shared__ double red[K][NT / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        double v = s[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) red[k][wid] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < K) {
-        double v = 0.0;
-        for (int i = 0; i < NT / 32; i++) v += red[threadIdx.x][i];
-        partial[block * K + threadIdx.x] = v;
-    }
-}
-template <int K, int NT>
-__device__ __forceinline__ void block_reduce_store(double (&s)[K], double* __restrict__ partial)
-{
-    block_reduce_store<K, NT>(s, partial, (i64)blockIdx.y * gridDim.x + blockIdx.x);
-}
-
 // stage 2: one CTA per time level adds the level's `nb` CTA partials (K sums each) in a fixed order and stores them in
 // slots slot[0..K) of row t0 + blockIdx.x of the level table
 struct SlotMap { int n; int slot[16]; };
@@ -1082,7 +1098,7 @@ __global__ void __launch_bounds__(256) k_levels_total(const double* __restrict__
     }
 }
 void launch_levels_total(const double* lvl, int nt, double* out, cudaStream_t st) { k_levels_total<<<1, 256, 0, st>>>(lvl, nt, out); }
-static void level_reduce(const double* partial, int nb, int K, const int* slots, int t0, int nlev, double* lvl, cudaStream_t st)
+void level_reduce(const double* partial, int nb, int K, const int* slots, int t0, int nlev, double* lvl, cudaStream_t st)
 {
     if (nlev <= 0) return;
     SlotMap sm;

@@ -5,6 +5,11 @@
 // solver_dotsocp2d.m:368-386 (recoverOrgVar) and :304-365 (InitialScaling).  Every value goes through the same sequence
 // of individually rounded operations as the host path (dotsocp_b200/driver.py), so a solve with resident transitions is
 // bit-identical to one that downloads, transfers on the host and uploads again.  Compiled with -fmad=false.
+//
+// Every stage works on a range of fine time levels, so that a time slab fills exactly its own part (plus the ghost layer
+// of beta below it, which the slab keeps redundantly) from the coarse slab with the same index: fine level tf reads the
+// coarse levels tf/2 and tf/2 + 1, which the coarse slab backs (its own levels plus one ghost level per side) when the
+// fine partition is the coarse one with every cut doubled (dotsocp_create_refined).
 #include "kernels.h"
 
 namespace dsocp {
@@ -12,10 +17,11 @@ namespace dsocp {
 __device__ __forceinline__ double avg2(double a, double b) { return dmul(dadd(a, b), 0.5); }
 
 // fine node (tf,xf,yf) <- coarse array (values pre-multiplied by `rec`, the recoverOrgVar factor)
-__global__ void __launch_bounds__(256) k_prolong_phi(Geo gf, Geo gc, double rec, const double* __restrict__ pc, double* __restrict__ pf)
+__global__ void __launch_bounds__(256) k_prolong_phi(Geo gf, Geo gc, int t0, double rec, const double* __restrict__ pc,
+                                                     double* __restrict__ pf)
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    const int tf = blockIdx.y;
+    const int tf = t0 + blockIdx.y;
     if (p >= gf.P) return;
     const int xf = (int)(p / gf.ny), yf = (int)(p - (i64)xf * gf.ny);
     const bool ry = gc.ny > 1;                     // the 1-D variant has no y direction to refine
@@ -28,10 +34,11 @@ __global__ void __launch_bounds__(256) k_prolong_phi(Geo gf, Geo gc, double rec,
 }
 
 // fine cell (tf,xf,yf), all 10 planes <- coarse cell layer tf/2
-__global__ void __launch_bounds__(256) k_prolong_beta(Geo gf, Geo gc, double rec, const double* __restrict__ bc, double* __restrict__ bf)
+__global__ void __launch_bounds__(256) k_prolong_beta(Geo gf, Geo gc, int t0, double rec, const double* __restrict__ bc,
+                                                      double* __restrict__ bf)
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    const int tf = blockIdx.y;
+    const int tf = t0 + blockIdx.y;
     if (p >= gf.P) return;
     const int xf = (int)(p / gf.ny), yf = (int)(p - (i64)xf * gf.ny);
     const bool ry = gc.ny > 1;
@@ -47,11 +54,12 @@ __global__ void __launch_bounds__(256) k_prolong_beta(Geo gf, Geo gc, double rec
 }
 
 // q = scale * ((A phi) [./ weight])  with the UNSCALED forward differences of the fine grid (initialize.m:67-87)
-__global__ void __launch_bounds__(256) k_prolong_q(Geo g, double gt, double gx, double gy, double scale, const double* __restrict__ phi,
-                                                   const double* __restrict__ weight, double* __restrict__ q)
+__global__ void __launch_bounds__(256) k_prolong_q(Geo g, int t0, double gt, double gx, double gy, double scale,
+                                                   const double* __restrict__ phi, const double* __restrict__ weight,
+                                                   double* __restrict__ q)
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int t = t0 + blockIdx.y;
     if (p >= g.P) return;
     const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
     const i64 n = (i64)t * g.P + p;
@@ -86,19 +94,32 @@ static unsigned stream_blocks(i64 n)
     i64 b = (n + 255) / 256;
     return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
 }
+static dim3 level_grid(const Geo& g, int nlev) { return dim3((unsigned)((g.P + 255) / 256), (unsigned)nlev); }
 
-int launch_prolong(const Geo& gc, const Geo& gf, const ProlongScal& s, const double* phi_c, const double* beta_c, double* phi_f,
-                   double* q_f, double* alpha_f, double* beta_f, const double* weight_f, cudaStream_t st)
+// unscaled fine phi on node levels [t0, t1)
+void launch_prolong_phi(const Geo& gc, const Geo& gf, double rec, const double* phi_c, double* phi_f, int t0, int t1, cudaStream_t st)
 {
-    const dim3 gn((unsigned)((gf.P + 255) / 256), (unsigned)gf.nt), gcell((unsigned)((gf.P + 255) / 256), (unsigned)(gf.nt - 1));
-    k_prolong_phi<<<gn, 256, 0, st>>>(gf, gc, s.phi_recover, phi_c, phi_f);                       // unscaled fine phi
-    k_prolong_q<<<gn, 256, 0, st>>>(gf, s.grad_t, s.grad_x, s.grad_y, s.q_scale, phi_f, weight_f, q_f);
-    k_mul_inplace<<<stream_blocks(gf.N), 256, 0, st>>>(gf.N, s.phi_scale, phi_f);
-    k_prolong_beta<<<gcell, 256, 0, st>>>(gf, gc, s.beta_recover, beta_c, beta_f);                // unscaled fine beta
-    launch_bfdconj(gf, 1.0, beta_f, alpha_f, st);                                                // mexBFdConj(alpha, ., 1)
-    k_prolong_alpha<<<stream_blocks(gf.Q), 256, 0, st>>>(gf.Q, s.alpha_scale, weight_f, alpha_f);
-    k_mul_inplace<<<stream_blocks(10 * gf.L), 256, 0, st>>>(10 * gf.L, s.beta_scale, beta_f);
-    return 7;   // launches (launch_bfdconj counts as one)
+    if (t1 > t0) k_prolong_phi<<<level_grid(gf, t1 - t0), 256, 0, st>>>(gf, gc, t0, rec, phi_c, phi_f);
+}
+// q on the edges owned by node levels [t0, t1) from the unscaled fine phi (needs phi on level t1 as well)
+void launch_prolong_q(const Geo& gf, const ProlongScal& s, const double* phi_f, const double* weight_f, double* q_f, int t0, int t1,
+                      cudaStream_t st)
+{
+    if (t1 > t0) k_prolong_q<<<level_grid(gf, t1 - t0), 256, 0, st>>>(gf, t0, s.grad_t, s.grad_x, s.grad_y, s.q_scale, phi_f, weight_f, q_f);
+}
+// unscaled fine beta on cell layers [c0, c1)
+void launch_prolong_beta(const Geo& gc, const Geo& gf, double rec, const double* beta_c, double* beta_f, int c0, int c1, cudaStream_t st)
+{
+    if (c1 > c0) k_prolong_beta<<<level_grid(gf, c1 - c0), 256, 0, st>>>(gf, gc, c0, rec, beta_c, beta_f);
+}
+// x[0..n) *= s  /  alpha[0..n) = scale * ((-alpha) [./ weight])
+void launch_mul_inplace(double* x, i64 n, double s, cudaStream_t st)
+{
+    if (n > 0) k_mul_inplace<<<stream_blocks(n), 256, 0, st>>>(n, s, x);
+}
+void launch_prolong_alpha(double* alpha, const double* weight, i64 n, double scale, cudaStream_t st)
+{
+    if (n > 0) k_prolong_alpha<<<stream_blocks(n), 256, 0, st>>>(n, scale, weight, alpha);
 }
 
 }  // namespace dsocp

@@ -301,18 +301,41 @@ static int make_slab(dotsocp_ctx* c, int id)
     return 0;
 }
 
-static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id);
+// cuts: first cell layer of every slab (world + 1 entries, 0 .. nt-1, strictly increasing), or NULL for the even partition
+static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id,
+                       const int* cuts);
 static void release_cached_unlocked_if_free();
-extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id)
+static int create_retry(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id,
+                        const int* cuts)
 {
-    int rc = create_impl(out, variant, nt, nx, ny, rank, world, nccl_id);
+    int rc = create_impl(out, variant, nt, nx, ny, rank, world, nccl_id, cuts);
     if (rc == DOTSOCP_ENOMEM && !(world > 1 && nccl_id)) {   // the session cached by dotsocp_solve_level may hold the memory
         release_cached_unlocked_if_free();
-        rc = create_impl(out, variant, nt, nx, ny, rank, world, nccl_id);
+        rc = create_impl(out, variant, nt, nx, ny, rank, world, nccl_id, cuts);
     }
     return rc;
 }
-static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id)
+extern "C" int dotsocp_create(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id)
+{
+    return create_retry(out, variant, nt, nx, ny, rank, world, nccl_id, nullptr);
+}
+// Session of the next finer level (2n-1 nodes per refined axis) with the same variant, rank, world and communicator as
+// `coarse` and the SAME partition in physical time: every cut of the coarse partition doubled, so that slab r of the fine
+// grid covers exactly the cells of slab r of the coarse grid and dotsocp_prolong needs no data from another rank.
+extern "C" int dotsocp_create_refined(dotsocp_ctx** out, const dotsocp_ctx* coarse)
+{
+    if (!out || !coarse) return set_err(DOTSOCP_EINVAL, "NULL argument");
+    const Geo& gc = coarse->g;
+    std::vector<int> cuts(coarse->world + 1);
+    for (int r = 0; r < coarse->world; r++) cuts[r] = 2 * coarse->part[r].tc0;
+    cuts[coarse->world] = 2 * (gc.nt - 1);
+    static const char zero_id[128] = {0};
+    const char* id = coarse->comm ? zero_id : nullptr;   // re-use the process-wide communicator / stay in emulation
+    return create_retry(out, coarse->variant, 2 * gc.nt - 1, 2 * gc.nx - 1, gc.ny > 1 ? 2 * gc.ny - 1 : 1, coarse->my, coarse->world, id,
+                        cuts.data());
+}
+static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, int rank, int world, const char* nccl_id,
+                       const int* cuts)
 {
     if (!out) return set_err(DOTSOCP_EINVAL, "ctx pointer is NULL");
     *out = nullptr;
@@ -337,10 +360,14 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
     cudaGetDevice(&c->device);
     for (int r = 0; r < world; r++) {
         TRange tr;
-        tr.tc0 = (int)((i64)r * (nt - 1) / world);
-        tr.tc1 = (int)((i64)(r + 1) * (nt - 1) / world);
+        tr.tc0 = cuts ? cuts[r] : (int)((i64)r * (nt - 1) / world);
+        tr.tc1 = cuts ? cuts[r + 1] : (int)((i64)(r + 1) * (nt - 1) / world);
         tr.tn0 = tr.tc0;
         tr.tn1 = (r == world - 1) ? nt : tr.tc1;
+        if (tr.tc1 <= tr.tc0 || tr.tc0 < 0 || tr.tc1 > nt - 1 || (r == 0 && tr.tc0 != 0) || (r == world - 1 && tr.tc1 != nt - 1)) {
+            delete c;
+            return set_err(DOTSOCP_EINVAL, "bad time partition: slab %d = cell layers [%d, %d) of %d", r, tr.tc0, tr.tc1, nt - 1);
+        }
         c->part.push_back(tr);
     }
     {   // mode chunks of ceil(P/world) (the last one shorter): cheap owner arithmetic inside the fused-pack DCT kernels
@@ -868,12 +895,13 @@ extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q
 // Level transfer on the device: recoverOrgVar + interpolate + jump_nextLevel + InitialScaling of
 // solver_dotsocp2d.m:230-250 without the state ever leaving HBM.  `coarse` holds the output state of a finished level
 // (after dotsocp_run), `fine` is a fresh session of the refined grid (2n-1 nodes per refined axis); afterwards `fine` is
-// in the state dotsocp_upload would have left it in (z = 0).  Single-slab sessions only.
+// in the state dotsocp_upload would have left it in (z = 0).  Time slabs: `fine` must come from dotsocp_create_refined
+// (aligned partition), every slab fills its own part from the coarse slab with the same index and the ghost planes are
+// exchanged exactly as after an upload; host arrays follow the upload convention (global, or the slab's part in NCCL mode).
 extern "C" int dotsocp_prolong(dotsocp_ctx* coarse, dotsocp_ctx* fine, const dotsocp_prolong_scal* ps, const double* c_first,
                                const double* c_last, const double* weight)
 {
-    if (!coarse || !fine || !ps || !c_first || !c_last) return set_err(DOTSOCP_EINVAL, "NULL argument");
-    if (coarse->world != 1 || fine->world != 1) return set_err(DOTSOCP_EINVAL, "prolong: single-slab sessions only");
+    if (!coarse || !fine || !ps) return set_err(DOTSOCP_EINVAL, "NULL argument");
     if (coarse->variant != fine->variant) return set_err(DOTSOCP_EINVAL, "prolong: variants differ");
     if (!coarse->uploaded || !coarse->z_materialised || coarse->iter_open)
         return set_err(DOTSOCP_ESTATE, "prolong: the coarse session must hold the output state of a finished run");
@@ -882,25 +910,60 @@ extern "C" int dotsocp_prolong(dotsocp_ctx* coarse, dotsocp_ctx* fine, const dot
         return set_err(DOTSOCP_EINVAL, "prolong: the fine grid must have 2n-1 nodes per axis (%d,%d,%d) -> (%d,%d,%d)", gc.nt, gc.nx,
                        gc.ny, gf.nt, gf.nx, gf.ny);
     if (fine->weighted && !weight) return set_err(DOTSOCP_EINVAL, "weighted variant needs weight");
-    Slab* sc = coarse->slabs[0];
-    Slab* sf = fine->slabs[0];
+    if (coarse->world != fine->world || coarse->emulate != fine->emulate || coarse->comm != fine->comm || coarse->my != fine->my)
+        return set_err(DOTSOCP_EINVAL, "prolong: the two sessions must share rank, world and communicator (dotsocp_create_refined)");
+    for (int r = 0; r < fine->world; r++)
+        if (fine->part[r].tc0 != 2 * coarse->part[r].tc0 || fine->part[r].tc1 != 2 * coarse->part[r].tc1)
+            return set_err(DOTSOCP_EINVAL, "prolong: slab %d of the fine session is not the refined coarse slab (dotsocp_create_refined)", r);
     fine->qcur = 0;
     fine->bcur = 0;
     int rc;
-    if (fine->weighted) {
-        HostMap hm{false, &gf, sf->tr};
-        if ((rc = copy_stag(fine, sf, hm, sf->weight, const_cast<double*>(weight), true))) return rc;
-    }
-    CU(cudaMemcpyAsync(sf->c0, c_first, gf.P * sizeof(double), cudaMemcpyHostToDevice, fine->st));
-    CU(cudaMemcpyAsync(sf->c1, c_last, gf.P * sizeof(double), cudaMemcpyHostToDevice, fine->st));
     CU(cudaStreamSynchronize(coarse->st));   // the coarse state is final
-    ProlongScal k{ps->phi_recover, ps->beta_recover, ps->grad_t, ps->grad_x, ps->grad_y,
-                  ps->phi_scale, ps->q_scale, ps->alpha_scale, ps->beta_scale};
-    fine->launches += launch_prolong(gc, gf, k, sc->phi, sc->beta[coarse->bcur], sf->phi, sf->q[0], sf->alpha, sf->beta[0],
-                                     fine->weighted ? sf->weight : nullptr, fine->st);
-    CU(cudaMemsetAsync(sf->beta[1], 0, (size_t)10 * gf.L * sizeof(double), fine->st));   // z = 0 (jump_nextLevel.m:9)
+    const ProlongScal k{ps->phi_recover, ps->beta_recover, ps->grad_t, ps->grad_x, ps->grad_y,
+                        ps->phi_scale, ps->q_scale, ps->alpha_scale, ps->beta_scale};
+    cudaStream_t st = fine->st;
+    const bool local_host = fine->world > 1 && !fine->emulate;
+    // stage A (per slab): weight and c from the host, unscaled fine phi on the owned node levels
+    for (Slab* sf : fine->slabs) {
+        Slab* sc = coarse->local(sf->id);
+        const TRange& tr = sf->tr;
+        if (fine->weighted) {
+            HostMap hm{local_host, &gf, tr};
+            if ((rc = copy_stag(fine, sf, hm, sf->weight, const_cast<double*>(weight), true))) return rc;
+        }
+        if (tr.tn0 == 0) {
+            if (!c_first) return set_err(DOTSOCP_EINVAL, "prolong: c_first is required on the slab that owns the first time level");
+            CU(cudaMemcpyAsync(sf->c0, c_first, gf.P * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        if (tr.tn1 == gf.nt) {
+            if (!c_last) return set_err(DOTSOCP_EINVAL, "prolong: c_last is required on the slab that owns the last time level");
+            CU(cudaMemcpyAsync(sf->c1, c_last, gf.P * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        launch_prolong_phi(gc, gf, k.phi_recover, sc->phi, sf->phi, tr.tn0, tr.tn1, st);
+        fine->launches += 1;
+    }
+    // q0 = Dt phi needs the level above the slab
+    if ((rc = ghosts(fine, GH_PHI_UP, 0, 0))) return rc;
+    // stage B: q = A phi (unscaled phi), then phi and its ghost level scaled; beta on the owned cells AND the ghost layer below
+    // (both neighbours keep that layer), alpha = (BF)^*(-beta), scalings, z = 0
+    for (Slab* sf : fine->slabs) {
+        Slab* sc = coarse->local(sf->id);
+        const TRange& tr = sf->tr;
+        const double* w = fine->weighted ? sf->weight : nullptr;
+        launch_prolong_q(gf, k, sf->phi, w, sf->q[0], tr.tn0, tr.tn1, st);
+        const int n_hi = std::min(tr.tn1 + 1, gf.nt);
+        launch_mul_inplace(sf->phi + (i64)tr.tn0 * gf.P, (i64)(n_hi - tr.tn0) * gf.P, k.phi_scale, st);
+        launch_prolong_beta(gc, gf, k.beta_recover, sc->beta[coarse->bcur], sf->beta[0], sf->lo_c, tr.tc1, st);
+        launch_bfdconj(gf, 1.0, sf->beta[0], sf->alpha, st, &tr);                                   // mexBFdConj(alpha, ., 1)
+        for (auto& x : sf->q_own) launch_prolong_alpha(sf->alpha + x.b, w ? w + x.b : nullptr, x.e - x.b, k.alpha_scale, st);
+        for (int j = 0; j < 10; j++)
+            launch_mul_inplace(sf->beta[0] + (i64)j * gf.L + (i64)sf->lo_c * gf.P, (i64)(tr.tc1 - sf->lo_c) * gf.P, k.beta_scale, st);
+        for (auto& x : sf->b_all) CU(cudaMemsetAsync(sf->beta[1] + x.b, 0, (size_t)(x.e - x.b) * sizeof(double), st));   // z = 0 (jump_nextLevel.m:9)
+        fine->launches += 5 + (double)sf->q_own.size() + 10;
+    }
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(fine->st));
+    if ((rc = ghosts(fine, GH_Q_UP | GH_Q_DOWN | GH_ALPHA0_DOWN | GH_W, 0, 0))) return rc;
+    CU(cudaStreamSynchronize(st));
     fine->z_materialised = true;
     fine->z_absent = false;
     fine->uploaded = true;
@@ -1142,6 +1205,72 @@ static int zstep_all(dotsocp_ctx* c, const IterScal& sc)
         c->launches += 1;
     }
     return 0;
+}
+
+// Output recovery on the device: what solver_dotsocp2d.m:268-287 does after the last level --
+// recoverOrgVar, recover_RhoE, recover_q, check_massConservation -- from the resident state of a finished run.  Every field
+// is produced into the (now free) Poisson rhs buffer and copied to the host array, NULL fields are skipped; host arrays
+// follow the download convention (global, or the slab's own levels in a one-process-per-GPU session).
+extern "C" int dotsocp_recover(dotsocp_ctx* c, const dotsocp_recover_scal* rs, const double* rho0, const double* rho1, double* rho,
+                               double* Ex, double* Ey, double* q0, double* bx, double* by, double* sumRho, double* sumNegRho,
+                               double* w2cost)
+{
+    if (!c || !rs) return set_err(DOTSOCP_EINVAL, "NULL argument");
+    if (!c->uploaded || c->iter_open) return set_err(DOTSOCP_ESTATE, "recover: needs the state of a finished run");
+    if (c->one_d && (Ey || by)) return set_err(DOTSOCP_EINVAL, "recover: the 1-D variant has no y fields");
+    const Geo& g = c->g;
+    const bool local_host = c->world > 1 && !c->emulate;
+    const bool need_rho = rho || sumRho || sumNegRho || w2cost;
+    double *d0 = nullptr, *d1 = nullptr;
+    struct Free { double*& a; double*& b; ~Free() { cudaFree(a); cudaFree(b); } } fr{d0, d1};
+    if (need_rho) {
+        if (!rho0 || !rho1) return set_err(DOTSOCP_EINVAL, "recover: rho0 / rho1 are required for rho, the mass check and the cost");
+        CU(cudaMalloc(&d0, g.P * sizeof(double)));
+        CU(cudaMalloc(&d1, g.P * sizeof(double)));
+        CU(cudaMemcpyAsync(d0, rho0, g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(d1, rho1, g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    }
+    auto args = [&](Slab* s) {
+        RecoverArgs a;
+        a.g = g; a.tr = s->tr; a.arec = rs->alpha_recover; a.qrec = rs->q_recover;
+        a.alpha = s->alpha; a.q = s->q[c->qcur]; a.weight = c->weighted ? s->weight : nullptr;
+        a.rho0 = d0; a.rho1 = d1; a.out = s->rhs; a.partial = s->partial; a.lvl = c->d_lvl;
+        return a;
+    };
+    int rc;
+    double* outs[6] = {rho, Ex, Ey, q0, bx, by};
+    for (int which = 0; which < 6; which++) {
+        if (!outs[which]) continue;
+        const bool cells = which >= RC_Q0;
+        for (Slab* s : c->slabs) {
+            const TRange& tr = s->tr;
+            launch_recover(args(s), which, c->weighted, c->st);
+            c->launches += 1;
+            const int t0 = tr.tn0, t1 = cells ? tr.tc1 : tr.tn1;
+            if (t1 <= t0) continue;
+            double* host = outs[which] + (local_host ? 0 : (i64)t0 * g.P);
+            if ((rc = xfer(c, s->rhs + (i64)t0 * g.P, host, (size_t)(t1 - t0) * g.P, false))) return rc;
+        }
+        CU(cudaStreamSynchronize(c->st));   // the scratch buffer is reused by the next field
+    }
+    if (sumRho || sumNegRho || w2cost) {
+        if ((rc = begin_sums(c))) return rc;
+        for (Slab* s : c->slabs) { launch_recover_stats(args(s), c->weighted, c->one_d, c->st); c->launches += 2; }
+        if (c->comm) NC(nccl_api().AllReduce(c->d_lvl, c->d_lvl, (size_t)g.nt * KSL, NCCL_FLOAT64, NCCL_SUM, c->comm, c->st));
+        std::vector<double> lv((size_t)g.nt * KSL);
+        CU(cudaMemcpyAsync(lv.data(), c->d_lvl, lv.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        double w2 = 0.0;
+        for (int t = 0; t < g.nt; t++) {
+            if (sumRho) sumRho[t] = lv[(size_t)t * KSL + RS_SUMRHO] / (double)g.P;        // check_massConservation.m:20-24
+            if (sumNegRho) sumNegRho[t] = lv[(size_t)t * KSL + RS_SUMNEG] / (double)g.P;
+            w2 += lv[(size_t)t * KSL + RS_W2];
+        }
+        if (w2cost) *w2cost = w2 / (double)g.N;
+    }
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaGetLastError());
+    return DOTSOCP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ the level loops

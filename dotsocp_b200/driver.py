@@ -46,6 +46,7 @@ def initialize(rho0, rho1, nt):
     c[: nx * ny] = -r0 / ht
     c[n - nx * ny:] = r1 / ht
     model.c = c
+    model.c_first, model.c_last = c[: nx * ny], c[n - nx * ny:]     # views: model.c is zero in between (initialize.m:41-44)
     xs = np.arange(nx) * hx
     if dim == 2:
         ys = np.arange(ny) * hy
@@ -67,6 +68,43 @@ def normL2(x, h):
     return math.sqrt(h) * float(np.linalg.norm(np.ravel(x, order="K")))
 
 
+def level_model(rho0, rho1, nt):
+    """The part of initialize.m:1-44 that a level with device-side transitions needs: the grid, model.grad as the triple of
+    forward-difference weights and the two non-zero planes of model.c -- no N-sized host array is built."""
+    rho0 = np.asarray(rho0, dtype=np.float64)
+    rho1 = np.asarray(rho1, dtype=np.float64)
+    if rho0.ndim == 1:
+        nx, ny, dim = rho0.size, 1, 1
+        r0, r1 = rho0, rho1
+    else:
+        ny, nx = rho0.shape
+        dim = 2
+        r0, r1 = rho0.ravel(order="F"), rho1.ravel(order="F")
+    ht, hx = 1 / (nt - 1), 1 / (nx - 1)
+    hy = 1 / (ny - 1) if ny > 1 else 1.0
+    model = SimpleNamespace(rho0=rho0, rho1=rho1, nt=nt, nx=nx, ny=ny, dim=dim, c=None, c_first=-r0 / ht, c_last=r1 / ht,
+                            grad=(1 / ht, 1 / hx, (1 / hy) if ny > 1 else 0.0))
+    L = (nt - 1) * nx * ny
+    qInd = SimpleNamespace(bx=L + 1, by=L + nt * (nx - 1) * ny + 1)
+    return SimpleNamespace(qInd=qInd), model
+
+
+def norm_c_planes(model):
+    """||model.c||_2 from its two non-zero planes (the same value for a full model.c and for level_model's planes)"""
+    a, b = np.ravel(model.c_first), np.ravel(model.c_last)
+    return math.sqrt(float(np.dot(a, a)) + float(np.dot(b, b)))
+
+
+def _scale_c(model, fn):
+    """apply fn to model.c -- the full vector (whose planes are views of it) or, without one, the two planes"""
+    if model.c is not None:
+        n = model.c_first.size
+        model.c = fn(model.c)
+        model.c_first, model.c_last = model.c[:n], model.c[model.c.size - n:]
+    else:
+        model.c_first, model.c_last = fn(model.c_first), fn(model.c_last)
+
+
 def scaling_scalars(N, model, scalingYes, lastLevelKKT, E2_prev, variant):
     """The scalar half of InitialScaling (solver_dotsocp2d.m:304-336 ; solver_wdotsocp2d.m:297-320 ; solver_dotsocp1d.m
     :263-290): returns (cScale, dScale, D, E, Escale2) and rescales model.c / model.grad / model.normc / model.normd.
@@ -84,7 +122,7 @@ def scaling_scalars(N, model, scalingYes, lastLevelKKT, E2_prev, variant):
         else:
             Escale2 = E2_prev * min(math.sqrt(2), max(1, ratio))
     if scalingYes:
-        norm_c = normL2(model.c, h) * math.sqrt(model.nt)
+        norm_c = (math.sqrt(h) * norm_c_planes(model)) * math.sqrt(model.nt)
         norm_d = math.sqrt(2)
         if variant == "wdot2d":
             adjust = 10 ** float(np.mean(np.log10(model.weight + 1e-10)))
@@ -99,11 +137,11 @@ def scaling_scalars(N, model, scalingYes, lastLevelKKT, E2_prev, variant):
             dScale = E * norm_d
         model.normc = norm_c / cScale
         model.normd = norm_d * E / dScale
-        model.c = (1.0 / cScale) * model.c if variant == "dot2d" else model.c / cScale
+        _scale_c(model, (lambda c: (1.0 / cScale) * c) if variant == "dot2d" else (lambda c: c / cScale))
         model.grad = tuple(D * g for g in model.grad)
     else:
         cScale = dScale = D = E = 1
-        model.normc = normL2(model.c, h)
+        model.normc = math.sqrt(h) * norm_c_planes(model)
         model.normd = math.sqrt(2)
     return cScale, dScale, D, E, Escale2
 
@@ -501,32 +539,35 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
     return output, timeML, ML, runHist
 
 
-def _finish_output(variant, var, model, level_iters, sigma, launches, timeML, levelN, clk):
-    output = SimpleNamespace()
-    if variant == "dot1d":
-        output.rho, output.Ex = recover_RhoE(var, model)
-        output.q0, output.bx = recover_q(var, model)
-    else:
-        output.rho, output.Ex, output.Ey = recover_RhoE(var, model)
-        output.q0, output.bx, output.by = recover_q(var, model)
-    output.massOK, output.sumRho, output.sumNegRho = check_massConservation(output.rho, 1e-2)
-    output.var, output.model, output.level_iters, output.sigma, output.gpu_launches = var, model, level_iters, sigma, launches
-    timeML[levelN] = {"ML_Time": time.perf_counter() - clk}
-    return output
-
-
 def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model, rho0s, rho1s, nts, tols, weights, timeML, ML,
                          clk):
     """The same multilevel loop with the state resident in HBM between levels (the default; opts["resident"] = False selects
-    the host-transition loop): the transitions
-    of solver_dotsocp2d.m:230-250 run on the device (dotsocp_prolong) instead of download -> host -> upload, and only the
-    last level is downloaded.  Bit-identical to the host-transition path (tests/test_solver_gpu.py)."""
+    the host-transition loop): the transitions of solver_dotsocp2d.m:230-250 run on the device (dotsocp_prolong) instead of
+    download -> host -> upload, and after the last level the outputs (rho, Ex, Ey, q0, bx, by, mass check) are recovered on
+    the device as well (dotsocp_recover), so only 6N doubles ever cross PCIe.  Bit-identical to the host path.
+
+    opts["slabs"]: None = one GPU; an int k = k time slabs emulated on this GPU; {"rank", "world", "nccl_id"} = this process
+    owns slab `rank` of a one-process-per-GPU run (every rank calls the driver with the same arguments; the output fields
+    then hold the rank's own time levels, output.slab = (first level, one past the last), the scalars are global).
+    opts["return_state"] = True also downloads the final iterates into output.var (recoverOrgVar applied)."""
+    from . import slab as SL
     weighted = variant == "wdot2d"
+    slabs = optsML.pop("slabs", None)
+    return_state = bool(optsML.pop("return_state", False))
+    if isinstance(slabs, dict):
+        rank, world, ident, distributed = int(slabs["rank"]), int(slabs["world"]), slabs["nccl_id"], True
+    else:
+        rank, world, ident, distributed = 0, int(slabs or 1), None, False
     InitialScaling(var, model, scalingYes, None, variant)          # coarsest level: host arrays, as the reference
-    sess = S.Session(variant, model.nt, model.nx, model.ny)
+    sess = S.Session(variant, model.nt, model.nx, model.ny, rank=rank, world=world, nccl_id=ident)
     mname = "inPALM" if method in ("inPALM", "ALG2") else method
     z_dead = mname == "inPALM" and int(optsML["maxit"]) >= 1
-    sess.upload(var.phi, var.q, None if z_dead else var.z, var.alpha, var.beta, model.c, model.weight if weighted else None)
+    state0 = (var.phi, var.q, None if z_dead else var.z, var.alpha, var.beta, model.c, model.weight if weighted else None)
+    if distributed:
+        state0 = SL.split_state(rank, world, model.nt, model.nx, model.ny, *state0, cuts=sess.cuts)
+    sess.upload(*state0)
+    del state0
+    var.phi = var.q = var.z = var.alpha = var.beta = None
     level_iters, launches, runHist, sigma = [], 0.0, None, optsML["sigma"]
     try:
         for level in range(levelN):
@@ -543,16 +584,21 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
                 break
             optsML["time_limit"] = optsML["time_limit"] - var.time["Total_Time"]
             optsML["sigma"] = 10 ** (math.log10(optsML["sigma"] * sigma) / 2)
-            var_f, model_f = initialize(rho0s[level + 1], rho1s[level + 1], nts[level + 1])
+            var_f, model_f = level_model(rho0s[level + 1], rho1s[level + 1], nts[level + 1])
             if weighted:
                 model_f.weight = weights[level + 1]
             gt, gx, gy = model_f.grad                               # unscaled 1/ht, 1/hx, 1/hy
-            cS, dS, D, E, E2 = scaling_scalars(var_f.phi.size, model_f, scalingYes, runHist.kkt[-1, :], var.E2, variant)
+            Nf = model_f.nt * model_f.nx * model_f.ny
+            cS, dS, D, E, E2 = scaling_scalars(Nf, model_f, scalingYes, runHist.kkt[-1, :], var.E2, variant)
             scal = dict(phi_recover=var.dScale, beta_recover=var.cScale * var.E, grad_t=gt, grad_x=gx, grad_y=gy,
                         phi_scale=1 / dS, q_scale=D / dS, alpha_scale=1 / cS / D, beta_scale=1 / cS / E)
-            fine = S.Session(variant, model_f.nt, model_f.nx, model_f.ny)
+            fine = S.Session.refined(sess)
             try:
-                fine.prolong_from(sess, scal, model_f.c, model_f.weight if weighted else None)
+                w_f = model_f.weight if weighted else None
+                if weighted and distributed:
+                    w_f = SL.split_state(rank, world, model_f.nt, model_f.nx, model_f.ny, None, None, None, None, None, None, w_f,
+                                         cuts=fine.cuts)[6]
+                fine.prolong_from(sess, scal, weight=w_f, c_first=model_f.c_first, c_last=model_f.c_last)
             except Exception:
                 fine.close()
                 raise
@@ -560,11 +606,22 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
             sess = fine
             var = SimpleNamespace(qInd=var_f.qInd, cScale=cS, dScale=dS, D=D, E=E, E2=E2)
             model = model_f
-        var.phi, var.q, var.z, var.alpha, var.beta = sess.download()
+        # ---- output (solver_dotsocp2d.m:268-287) on the device
+        fields, sumRho, sumNeg, w2 = sess.recover(var.cScale * var.D, var.dScale / var.D, model.rho0, model.rho1)
+        if return_state:
+            var.phi, var.q, var.z, var.alpha, var.beta = sess.download()
+            recoverOrgVar(var, inplace=True)
+        tc0, tc1, tn0, tn1 = SL.partition(model.nt, world, sess.cuts)[rank] if distributed else (0, model.nt - 1, 0, model.nt)
     finally:
         sess.close()
-    recoverOrgVar(var, inplace=True)
-    output = _finish_output(variant, var, model, level_iters, sigma, launches, timeML, levelN, clk)
+    output = SimpleNamespace(**fields)
+    output.sumRho, output.sumNegRho = sumRho, sumNeg
+    output.massOK = bool(max(np.abs(sumRho - 1).max(), np.abs(sumNeg).max()) <= 1e-2)     # check_massConservation.m:26-34
+    output.w2 = w2
+    output.slab = (tn0, tn1)
+    output.var = var if return_state else None
+    output.model, output.level_iters, output.sigma, output.gpu_launches = model, level_iters, sigma, launches
+    timeML[levelN] = {"ML_Time": time.perf_counter() - clk}
     return output, timeML, ML, runHist
 
 

@@ -17,35 +17,40 @@ import numpy as np
 from ._lib import check, lib
 
 
-def partition(nt, world):
-    """[(tc0, tc1, tn0, tn1)] for every slab -- same arithmetic as dotsocp_create."""
-    out = []
-    for r in range(world):
-        tc0 = r * (nt - 1) // world
-        tc1 = (r + 1) * (nt - 1) // world
-        out.append((tc0, tc1, tc0, nt if r == world - 1 else tc1))
-    return out
+def default_cuts(nt, world):
+    """first cell layer of every slab (world + 1 entries) -- same arithmetic as dotsocp_create"""
+    return [r * (nt - 1) // world for r in range(world)] + [nt - 1]
 
 
-def split_state(rank, world, nt, nx, ny, phi, q, z, alpha, beta, c, weight=None):
-    """slab-local copies of global arrays (MATLAB linear order)"""
-    tc0, tc1, tn0, tn1 = partition(nt, world)[rank]
+def partition(nt, world, cuts=None):
+    """[(tc0, tc1, tn0, tn1)] for every slab.  cuts: explicit partition (default_cuts; a refined session -- Session.refined,
+    dotsocp_create_refined -- uses the coarse cuts doubled so that slab r covers the same physical time on every level)."""
+    cuts = default_cuts(nt, world) if cuts is None else list(cuts)
+    assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == nt - 1
+    return [(cuts[r], cuts[r + 1], cuts[r], nt if r == world - 1 else cuts[r + 1]) for r in range(world)]
+
+
+def split_state(rank, world, nt, nx, ny, phi, q, z, alpha, beta, c, weight=None, cuts=None):
+    """slab-local copies of global arrays (MATLAB linear order); any of the arrays may be None"""
+    tc0, tc1, tn0, tn1 = partition(nt, world, cuts)[rank]
     P, PBX, PBY = nx * ny, (nx - 1) * ny, nx * (ny - 1)
     L = (nt - 1) * P
     NBX = nt * PBX
 
     def node(a):
-        return np.ascontiguousarray(a[tn0 * P: tn1 * P])
+        return None if a is None else np.ascontiguousarray(a[tn0 * P: tn1 * P])
 
     def stag(a):
+        if a is None:
+            return None
         return np.concatenate([a[tc0 * P: tc1 * P], a[L + tn0 * PBX: L + tn1 * PBX], a[L + NBX + tn0 * PBY: L + NBX + tn1 * PBY]])
 
     def cols(a):
-        return np.asfortranarray(a[tc0 * P: tc1 * P, :])
-    return (node(phi), stag(q), cols(z), stag(alpha), cols(beta), node(c), None if weight is None else stag(weight))
+        return None if a is None else np.asfortranarray(a[tc0 * P: tc1 * P, :])
+    return (node(phi), stag(q), cols(z), stag(alpha), cols(beta), node(c), stag(weight))
 
 
-def merge_state(world, nt, nx, ny, parts, ncol=10):
+def merge_state(world, nt, nx, ny, parts, ncol=10, cuts=None):
     """inverse of split_state for (phi, q, z, alpha, beta): `parts[r]` is the tuple downloaded by slab r"""
     P, PBX, PBY = nx * ny, (nx - 1) * ny, nx * (ny - 1)
     L = (nt - 1) * P
@@ -53,7 +58,7 @@ def merge_state(world, nt, nx, ny, parts, ncol=10):
     Q = L + NBX + nt * PBY
     phi, q, alpha = np.empty(nt * P), np.empty(Q), np.empty(Q)
     z, beta = np.empty((L, ncol), order="F"), np.empty((L, ncol), order="F")
-    for r, (tc0, tc1, tn0, tn1) in enumerate(partition(nt, world)):
+    for r, (tc0, tc1, tn0, tn1) in enumerate(partition(nt, world, cuts)):
         p_phi, p_q, p_z, p_alpha, p_beta = parts[r][:5]
         phi[tn0 * P: tn1 * P] = p_phi
         n0, n1 = (tc1 - tc0) * P, (tn1 - tn0) * PBX
@@ -66,8 +71,8 @@ def merge_state(world, nt, nx, ny, parts, ncol=10):
     return phi, q, z, alpha, beta
 
 
-def local_sizes(rank, world, nt, nx, ny):
-    tc0, tc1, tn0, tn1 = partition(nt, world)[rank]
+def local_sizes(rank, world, nt, nx, ny, cuts=None):
+    tc0, tc1, tn0, tn1 = partition(nt, world, cuts)[rank]
     P, PBX, PBY = nx * ny, (nx - 1) * ny, nx * (ny - 1)
     return {"N": (tn1 - tn0) * P, "L": (tc1 - tc0) * P, "Q": (tc1 - tc0) * P + (tn1 - tn0) * (PBX + PBY)}
 

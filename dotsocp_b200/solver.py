@@ -19,7 +19,7 @@ from types import SimpleNamespace
 
 import numpy as np
 
-from ._lib import METHOD, VARIANT, HistBuffers, LevelOpts, LevelResult, ProlongScal, check, lib, ptr
+from ._lib import METHOD, VARIANT, HistBuffers, LevelOpts, LevelResult, ProlongScal, RecoverScal, check, lib, ptr
 
 TIME_NAMES = {
     0: ["Step_1_1_FFT", "Step_1_2_ProjSOC", "Step_2_Q_Step", "Step_3_Multiplier", "KKT", "Total_Time"],
@@ -88,19 +88,38 @@ class Session:
         """world > 1 with nccl_id=None: all `world` time slabs live in this process on the current device (emulation of
         the multi-GPU path, global host arrays); with a 128-byte nccl_id: this process owns slab `rank` (one process per
         GPU, NCCL between them) and upload/download take the slab-local parts (see slab.py)."""
+        self._h = C.c_void_p()
+        check(lib().dotsocp_create(C.byref(self._h), VARIANT[variant], int(nt), int(nx), int(ny), rank, world, nccl_id))
+        self._describe(variant, nt, nx, ny, rank, world, nccl_id is not None, None)
+
+    def _describe(self, variant, nt, nx, ny, rank, world, distributed, cuts):
+        from .slab import default_cuts, local_sizes
         self.variant = variant
-        self.rank, self.world, self.distributed = int(rank), int(world), nccl_id is not None
+        self.rank, self.world, self.distributed = int(rank), int(world), bool(distributed)
         self.nt, self.nx, self.ny = int(nt), int(nx), int(ny)
         self.ncol = 6 if variant == "dot1d" else 10
-        self._h = C.c_void_p()
-        check(lib().dotsocp_create(C.byref(self._h), VARIANT[variant], self.nt, self.nx, self.ny, rank, world, nccl_id))
+        self.cuts = default_cuts(self.nt, self.world) if cuts is None else list(cuts)
         self.L = (self.nt - 1) * self.nx * self.ny
         self.Q = self.L + self.nt * (self.nx - 1) * self.ny + self.nt * self.nx * (self.ny - 1)
         self.N = self.nt * self.nx * self.ny
+        self.nt_local, self.nc_local = self.nt, self.nt - 1
         if self.distributed:   # host arrays hold this slab's owned part only (slab.py)
-            from .slab import local_sizes
-            sz = local_sizes(self.rank, self.world, self.nt, self.nx, self.ny)
+            sz = local_sizes(self.rank, self.world, self.nt, self.nx, self.ny, self.cuts)
             self.L, self.Q, self.N = sz["L"], sz["Q"], sz["N"]
+            P = self.nx * self.ny
+            self.nt_local, self.nc_local = self.N // P, self.L // P
+
+    @classmethod
+    def refined(cls, coarse):
+        """Fresh session of the next finer level (2n-1 nodes per refined axis) with the rank, world, communicator and --
+        every cut doubled -- the time partition of `coarse` (dotsocp_create_refined): the target of prolong_from."""
+        s = cls.__new__(cls)
+        s._h = C.c_void_p()
+        check(lib().dotsocp_create_refined(C.byref(s._h), coarse._h))
+        ny = 2 * coarse.ny - 1 if coarse.ny > 1 else 1
+        s._describe(coarse.variant, 2 * coarse.nt - 1, 2 * coarse.nx - 1, ny, coarse.rank, coarse.world, coarse.distributed,
+                    [2 * v for v in coarse.cuts])
+        return s
 
     def close(self):
         if self._h:
@@ -148,18 +167,47 @@ class Session:
         check(lib().dotsocp_download(self._h, ptr(phi), ptr(q), ptr(z), ptr(alpha), ptr(beta)))
         return phi, q, z, alpha, beta
 
-    def prolong_from(self, coarse, scal, c, weight=None):
-        """Level transfer on the device (dotsocp_prolong): fill this fresh session of the refined grid from the finished
-        `coarse` session.  scal: dict of the ProlongScal fields; c: the fine model.c (already divided by cScale)."""
-        c = np.ascontiguousarray(c, dtype=np.float64)
-        assert c.size == self.N
+    def prolong_from(self, coarse, scal, c=None, weight=None, c_first=None, c_last=None):
+        """Level transfer on the device (dotsocp_prolong): fill this fresh session of the refined grid (Session.refined for
+        time slabs) from the finished `coarse` session.  scal: dict of the ProlongScal fields; the fine model.c (already
+        divided by cScale) either whole (c) or as its two non-zero planes (c_first, c_last: nx*ny doubles each; a slab
+        that owns neither the first nor the last time level may pass None); weight follows the upload convention."""
         P = self.nx * self.ny
-        first, last = np.ascontiguousarray(c[:P]), np.ascontiguousarray(c[-P:])
-        assert not c[P:-P].any(), "model.c has a non-zero interior entry: unsupported"
+        if c is not None:
+            c = np.ascontiguousarray(c, dtype=np.float64)
+            assert c.size == self.N and not self.distributed
+            c_first, c_last = c[:P], c[-P:]
+            assert not c[P:-P].any(), "model.c has a non-zero interior entry: unsupported"
+        first = None if c_first is None else np.ascontiguousarray(c_first, dtype=np.float64).reshape(-1)
+        last = None if c_last is None else np.ascontiguousarray(c_last, dtype=np.float64).reshape(-1)
+        assert (first is None or first.size == P) and (last is None or last.size == P)
         w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64).reshape(-1)
         assert w is None or w.size == self.Q, f"weight has {0 if w is None else w.size} entries, expected {self.Q}"
         ps = ProlongScal(**{k: float(v) for k, v in scal.items()})
         check(lib().dotsocp_prolong(coarse._h, self._h, C.byref(ps), ptr(first), ptr(last), ptr(w)))
+
+    def recover(self, alpha_recover, q_recover, rho0, rho1, fields=("rho", "Ex", "Ey", "q0", "bx", "by"), stats=True):
+        """Output recovery on the device (dotsocp_recover) from the state of a finished run: recoverOrgVar + recover_RhoE +
+        recover_q + check_massConservation + transport cost.  rho0 / rho1: MATLAB-shaped (ny, nx) densities [1-D: (nx,)].
+        Returns (dict of C-order arrays (levels, nx, ny) -- this slab's levels in a distributed session --, sumRho,
+        sumNegRho, w2cost)."""
+        r0 = np.ascontiguousarray(np.asarray(rho0, dtype=np.float64).ravel(order="F"))
+        r1 = np.ascontiguousarray(np.asarray(rho1, dtype=np.float64).ravel(order="F"))
+        P = self.nx * self.ny
+        assert r0.size == P and r1.size == P
+        shp = (self.nx, self.ny) if self.variant != "dot1d" else (self.nx,)
+        out = {}
+        for name in ("rho", "Ex", "Ey", "q0", "bx", "by"):
+            if name in fields and not (self.variant == "dot1d" and name in ("Ey", "by")):
+                out[name] = np.empty(((self.nt_local if name in ("rho", "Ex", "Ey") else self.nc_local),) + shp)
+        sr = np.empty(self.nt) if stats else None
+        sn = np.empty(self.nt) if stats else None
+        w2 = C.c_double(float("nan"))
+        rs = RecoverScal(float(alpha_recover), float(q_recover))
+        check(lib().dotsocp_recover(self._h, C.byref(rs), ptr(r0), ptr(r1), *[ptr(out.get(k)) if out.get(k) is None else out[k].ctypes.data
+                                                                               for k in ("rho", "Ex", "Ey", "q0", "bx", "by")],
+                                    ptr(sr), ptr(sn), C.byref(w2) if stats else None))
+        return out, sr, sn, (w2.value if stats else None)
 
     def run(self, level_opts):
         hb = HistBuffers(level_opts.maxit)

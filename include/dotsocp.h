@@ -147,6 +147,21 @@ void dotsocp_destroy(dotsocp_ctx *ctx);
 int  dotsocp_upload(dotsocp_ctx *ctx, const double *phi, const double *q, const double *z,
                     const double *alpha, const double *beta, const double *c, const double *weight);
 int  dotsocp_download(dotsocp_ctx *ctx, double *phi, double *q, double *z, double *alpha, double *beta);
+/* Output recovery and checks on the device after the last level, instead of downloading the whole state: what
+ * solver_dotsocp2d.m:268-287 computes -- recoverOrgVar (:368-386), recover_RhoE (utils/recover_RhoE.m:13-25; wdot2d
+ * multiplies alpha by the weight), recover_q (utils/recover_q.m:12-22), check_massConservation (utils/
+ * check_massConservation.m:16-34) -- plus the transport cost mean(|m|^2/rho) over the space-time nodes with rho > 1e-12.
+ * rho0 / rho1: model.rho0(:), model.rho1(:) (nx*ny doubles).  Outputs (any may be NULL): rho, Ex, Ey on the nt node
+ * levels (N doubles, MATLAB order (ny,nx,nt)); q0, bx, by on the nt-1 cell layers (L doubles); sumRho / sumNegRho: nt
+ * doubles each; w2cost: one double.  One-process-per-GPU sessions pass / receive the slab's own levels for the fields and
+ * the full-length vectors for the per-level sums.  The fields are bit-identical to the host path.                     */
+typedef struct dotsocp_recover_scal {
+    double alpha_recover;           /* var.cScale * var.D   (var.alpha = (cScale*D) * var.alpha) */
+    double q_recover;               /* var.dScale / var.D   (var.q = (dScale/D) * var.q)         */
+} dotsocp_recover_scal;
+int  dotsocp_recover(dotsocp_ctx *ctx, const dotsocp_recover_scal *s, const double *rho0, const double *rho1,
+                     double *rho, double *Ex, double *Ey, double *q0, double *bx, double *by,
+                     double *sumRho, double *sumNegRho, double *w2cost);
 /* Level transfer of the multilevel drivers with the state resident in HBM: what solver_dotsocp2d.m:230-250 does between two
  * levels -- recoverOrgVar (:368-386), interpolate (utils/interpolate.m:46-84), jump_nextLevel (utils/jump_nextLevel.m:5-16:
  * z = 0, q = A phi, alpha = (BF)^*(-beta)), InitialScaling (:304-365) -- from the finished coarse session into a fresh
@@ -163,6 +178,7 @@ typedef struct dotsocp_prolong_scal {
     double alpha_scale;             /* fine 1/cScale/D                                                             */
     double beta_scale;              /* fine 1/cScale/E                                                             */
 } dotsocp_prolong_scal;
+int  dotsocp_create_refined(dotsocp_ctx **fine, const dotsocp_ctx *coarse);
 int  dotsocp_prolong(dotsocp_ctx *coarse, dotsocp_ctx *fine, const dotsocp_prolong_scal *s,
                      const double *c_first, const double *c_last, const double *weight);
 /* the reference loop on the resident state (sigma folding at entry, un-folding at exit, like :102-104, :335-336) */

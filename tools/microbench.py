@@ -15,10 +15,10 @@ o = bench.level_opts(var, model, steps)
 with dp.Session("dot2d", nt, nx, ny) as s:
     s.upload(var.phi, var.q, var.z, var.alpha, var.beta, model.c)
     s.iter_begin(o)
-    s.iterate(3)
+    s.iterate(3, kkt_every=kkt_every)      # warm-up (also loads the check-iteration kernels)
     ms, pk = s.iterate(steps, per_kernel=True, kkt_every=kkt_every)
     s.iter_end()
 peak = bench.measured_peaks()[0]
 mult = pk[2] / steps
-print(f"{wl} TU={os.environ.get('DOTSOCP_KM_TU','2')} kkt_every={kkt_every}: {ms/steps:.3f} ms/it  poisson {pk[0]/steps:.3f}  qstep {pk[1]/steps:.3f}  "
+print(f"{wl} PF={os.environ.get('DOTSOCP_KM_PF','default')} kkt_every={kkt_every}: {ms/steps:.3f} ms/it  poisson {pk[0]/steps:.3f}  qstep {pk[1]/steps:.3f}  "
       f"mult {mult:.3f} ({(N+4*Q+20*L)*8/mult/1e6/peak:.3f} of {peak:.0f} GB/s)  iter frac {(14*N+6*Q+30*L)*8/(ms/steps)/1e6/peak:.3f}", flush=True)
