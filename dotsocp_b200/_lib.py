@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DOTSOCP_LIB") or os.path.join(_HERE, "libdotsocp.so")   # override only for A/B experiments
 
 VARIANT = {"dot2d": 0, "wdot2d": 1, "dot1d": 2}
-METHOD = {"inPALM": 0, "ALG2": 0, "PALM": 1, "acc-ADMM": 2}
+METHOD = {"inPALM": 0, "ALG2": 0, "PALM": 1, "acc-ADMM": 2, "sGS-inPALM": 3}
 NTIMES = 8
 
 
@@ -65,7 +65,7 @@ class Hist(C.Structure):
 
 EXPORTS = [
     "dotsocp_last_error", "dotsocp_version", "dotsocp_device_count", "dotsocp_set_device",
-    "dotsocp_mexBFd", "dotsocp_mexBFdConj", "dotsocp_mexProjSoc", "dotsocp_mexBFd1d", "dotsocp_mexBFdConj1d",
+    "dotsocp_mexBFd", "dotsocp_mexBFdConj", "dotsocp_mexProjSoc", "dotsocp_mexsGS", "dotsocp_mexBFd1d", "dotsocp_mexBFdConj1d",
     "dotsocp_poisson", "dotsocp_dctn", "dotsocp_solve_level", "dotsocp_release_cached",
     "dotsocp_nccl_unique_id", "dotsocp_create", "dotsocp_destroy", "dotsocp_upload", "dotsocp_download",
     "dotsocp_create_refined", "dotsocp_prolong", "dotsocp_recover", "dotsocp_run", "dotsocp_iter_begin", "dotsocp_iterate", "dotsocp_iter_end", "dotsocp_launch_count",
@@ -91,6 +91,7 @@ def lib():
     L.dotsocp_mexBFd.argtypes = [P, P, I, I, I, D, D]
     L.dotsocp_mexBFdConj.argtypes = [P, P, I, I, I, D]
     L.dotsocp_mexProjSoc.argtypes = [P, P, I64, I]
+    L.dotsocp_mexsGS.argtypes = [P, P, D, D, I, I, I, I]
     L.dotsocp_mexBFd1d.argtypes = [P, P, I, I, D, D]
     L.dotsocp_mexBFdConj1d.argtypes = [P, P, I, I, D]
     L.dotsocp_poisson.argtypes = [P, P, I, I, I, D]

@@ -99,6 +99,27 @@ extern "C" int dotsocp_mexBFdConj1d(double* q, const double* z, int nt, int nx, 
     return DOTSOCP_OK;
 }
 
+extern "C" int dotsocp_mexsGS(double* phi, const double* rhs, double ep, double scale, int nt, int nx, int ny, int its)
+{
+    if (!phi || !rhs || nt < 3 || nx < 3 || ny < 3 || its < 0) return set_err(DOTSOCP_EINVAL, "bad arguments");
+    const Geo g = make_geo(nt, nx, ny);
+    if (!sgs_supported(g)) return set_err(DOTSOCP_EINVAL, "mexsGS handles only nx == ny with odd node counts (got %d x %d x %d)", nt, nx, ny);
+    int rc = require_device();
+    if (rc) return rc;
+    DevBuf a, b;
+    if ((rc = a.alloc(g.N)) || (rc = b.alloc(g.N))) return rc;
+    CU(cudaMemcpy(a.p, phi, (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(b.p, rhs, (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice));
+    launch_sgs_half(g, ep, scale, 1, b.p, a.p, 0, nt, 0);            // odd ; its x [even ; odd]   (mexFunction @0x2598-0x2629)
+    for (int i = 0; i < its; i++) {
+        launch_sgs_half(g, ep, scale, 0, b.p, a.p, 0, nt, 0);
+        launch_sgs_half(g, ep, scale, 1, b.p, a.p, 0, nt, 0);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(phi, a.p, (size_t)g.N * sizeof(double), cudaMemcpyDeviceToHost));
+    return DOTSOCP_OK;
+}
+
 static int dct_common(double* out, const double* in, int nt, int nx, int ny, int what, double D)
 {
     if (!out || !in || nt < 1 || nx < 1 || ny < 1) return set_err(DOTSOCP_EINVAL, "bad arguments");

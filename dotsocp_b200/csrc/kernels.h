@@ -66,6 +66,8 @@ enum { KN_Q2 = 0, KN_APHI2, KN_PRIM1, KN_ALPHA2, KN_FBB2, KN_DUAL2, KN_QDOTA, KN
        KN_DUAL1, KN_CPHI, KN_PHI2, KN_COUNT };
 constexpr int KSL = 24;                       // slots per level row: KC_* at 0.., KN_* at KC_COUNT.., then KS_*
 constexpr int KS_ELAPSED = KC_COUNT + KN_COUNT;   // host clock of slab 0 (row 0 only), so that all ranks decide alike
+constexpr int KS_SGS_BLOCKS = KS_ELAPSED + 1;     // sGS loops: sum (A'(A phi - q + alpha) - c)^2 over the even nodes (:212-216)
+constexpr int KS_SGS_KKT = KS_ELAPSED + 2;        //            sum (A'(A phi - q))^2 over all nodes (:322)
 // rescale norms (solver_socp_inPALM.m:140-143): one fused pass, slots 0..4 of a level row
 enum { NR_PHI2 = 0, NR_Q2, NR_Z2, NR_ALPHA2, NR_BETA2, NR_COUNT };
 struct KktArgs {
@@ -151,6 +153,16 @@ void launch_accel3(double* x, double* xold, double* xhatold, i64 n, double rho, 
 // 6 <-> 10 column conversion of the 1-D variant's z/beta (cols 0..4 -> 0..4, col 5 -> 9; 5..8 zero)
 void launch_cols6to10(const double* in6, double* out10, i64 L, cudaStream_t st);
 void launch_cols10to6(const double* in10, double* out6, i64 L, cudaStream_t st);
+
+// ---- red-black symmetric Gauss-Seidel (sgs.cu): mexsGS.mexa64 -----------------------------------------------------
+bool sgs_supported(const Geo& g);   // nx == ny, odd node counts (the only grids the reference binary handles)
+void launch_sgs_half(const Geo& g, double ep, double scale, int parity, const double* rhs, double* phi, int tn0, int tn1,
+                     cudaStream_t st);
+// sum over nodes of (A'(A phi - q + alpha) - c)^2 on the even nodes (with_alpha_c) or of (A'(A phi - q))^2 on all nodes
+void launch_sgs_resid(const Geo& g, const IterScal& sc, bool with_alpha_c, const double* phi, const double* q, const double* alpha,
+                      const double* c0, const double* c1, double* partial, double* lvl, int slot, int tn0, int tn1, cudaStream_t st);
+void launch_sum_nodes(const Geo& g, const double* phi, double* partial, double* lvl, int slot, int tn0, int tn1, cudaStream_t st);
+void launch_shift(double* x, i64 n, double shift, cudaStream_t st);
 
 // ---- Poisson / DCT (poisson.cu) -----------------------------------------------------------------------------
 struct DctPlan;   // per-length tables (chirps, twiddles, dense matrices), device resident

@@ -557,7 +557,7 @@ static int do_xfers(dotsocp_ctx* c, const std::vector<Xfer>& xs, cudaStream_t st
 }
 
 // ghost exchanges across every slab boundary (node level T between slab r and r+1)
-enum { GH_PHI_UP = 1, GH_Q_UP = 2, GH_Q_DOWN = 4, GH_ALPHA0_DOWN = 8, GH_BETA_DOWN = 16, GH_W = 32 };
+enum { GH_PHI_UP = 1, GH_Q_UP = 2, GH_Q_DOWN = 4, GH_ALPHA0_DOWN = 8, GH_BETA_DOWN = 16, GH_W = 32, GH_PHI_DOWN = 64 };
 static int ghosts(dotsocp_ctx* c, int what, int qk, int bk, cudaStream_t st = nullptr)
 {
     if (c->world == 1) return 0;
@@ -567,6 +567,7 @@ static int ghosts(dotsocp_ctx* c, int what, int qk, int bk, cudaStream_t st = nu
     for (int r = 0; r + 1 < c->world; r++) {
         const i64 T = c->part[r].tn1;   // == part[r+1].tn0
         if (what & GH_PHI_UP) xs.push_back({sel_phi, 0, T * g.P, g.P, r + 1, r});
+        if (what & GH_PHI_DOWN) xs.push_back({sel_phi, 0, (T - 1) * g.P, g.P, r, r + 1});
         if (what & GH_Q_UP) {
             xs.push_back({sel_q, qk, g.L + T * g.PBX, g.PBX, r + 1, r});
             xs.push_back({sel_q, qk, g.L + g.NBX + T * g.PBY, g.PBY, r + 1, r});
@@ -996,20 +997,24 @@ static const double UPDATE_RULE[11][2] = {   // solver_socp_inPALM.m:39-51
     {1.1, 1.10}, {1.2, 1.15}, {1.5, 1.20}, {2, 1.26}, {2.5, 1.28}, {3.33, 1.32},
     {5, 1.35}, {10, 1.40}, {20, 1.60}, {40, 1.80}, {50, 2.00}};
 
-static double get_factor(double xi)   // adjust_lagrangianParam.m:47-59
+static const double SGS_UPDATE_RULE[6][2] = {   // solver_socp_sGSinPALM.m:37-44
+    {1.5, 1.20}, {2, 1.26}, {2.5, 1.28}, {3.33, 1.32}, {5, 1.35}, {10, 1.40}};
+
+static double get_factor(double xi, const double (*rule)[2], int nrule)   // adjust_lagrangianParam.m:47-59
 {
     double factor = 1;
-    for (int i = 0; i < 11; i++) {
-        if (xi >= UPDATE_RULE[i][0]) factor = UPDATE_RULE[i][1];
+    for (int i = 0; i < nrule; i++) {
+        if (xi >= rule[i][0]) factor = rule[i][1];
         else break;
     }
     return factor;
 }
-static void adjust_lagrangianParam(double& sigma, double xi, double& factor)   // adjust_lagrangianParam.m:14-39
+static void adjust_lagrangianParam(double& sigma, double xi, double& factor, const double (*rule)[2] = UPDATE_RULE,
+                                   int nrule = 11)   // adjust_lagrangianParam.m:14-39
 {
     const double lower = 1e-3, upper = 1e3;
-    if (xi >= 1) factor = get_factor(xi);
-    else if (xi < 1) factor = 1 / get_factor(1 / xi);
+    if (xi >= 1) factor = get_factor(xi, rule, nrule);
+    else if (xi < 1) factor = 1 / get_factor(1 / xi, rule, nrule);
     else factor = 1;   // NaN ratio: MATLAB would raise; keep sigma
     if (factor != 1) {
         const double sigmaOld = sigma;
@@ -1026,6 +1031,18 @@ static bool IfAdjustSigma(double it, double last)   // solver_socp_inPALM.m:361-
     if (it < 200 && passed >= 15) return true;
     if (it < 500 && passed >= 25) return true;
     return passed >= 40;
+}
+static bool IfAdjustSigma_sGS(double it, double last, double scale)   // solver_socp_sGSinPALM.m:431-456
+{
+    double passed = it - last;
+    it = it / scale;
+    passed = passed / scale;
+    if (it < 20 && passed >= 5) return true;
+    if (it < 50 && passed >= 10) return true;
+    if (it < 100 && passed >= 20) return true;
+    if (it < 200 && passed >= 35) return true;
+    if (it < 500 && passed >= 50) return true;
+    return passed >= 100;
 }
 static double mmax(std::initializer_list<double> v)   // MATLAB max ignores NaN
 {
@@ -1089,6 +1106,21 @@ struct Loop {
         }
     }
     int step_phi() { return solve_poisson(c, sc_D2); }
+    // phi-step of the sGS loops: mexsGS(phi, rhs, 0, D^2, nt, nx, ny, 1) = odd, even, odd half sweeps (sgs.cu); time slabs
+    // refresh one ghost plane of phi per side after every half sweep -- the only communication of this phi-step
+    int step_sgs()
+    {
+        static const int order[3] = {1, 0, 1};
+        for (int hs = 0; hs < 3; hs++) {
+            for (Slab* s : c->slabs) {
+                launch_sgs_half(c->g, 0.0, sc_D2, order[hs], s->rhs, s->phi, s->tr.tn0, s->tr.tn1, c->st);
+                c->launches += 1;
+            }
+            int rc = ghosts(c, GH_PHI_UP | GH_PHI_DOWN, 0, 0);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     // fused KKT: per-slab partial buffers (allocated at the first fused check) + the scalars of the terms
     int kkt_fused(Slab* s, double sigma, double cScale, double dScale, double D, double E, KktFused* kf)
     {
@@ -1282,7 +1314,10 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
 {
     const Geo& g = c->g;
     const int method = o.method;
-    const bool inpalm = method == DOTSOCP_METHOD_INPALM, palm = method == DOTSOCP_METHOD_PALM, acc = method == DOTSOCP_METHOD_ACCADMM;
+    // sGS-inPALM (solver_socp_sGSinPALM.m) is the inPALM iteration with the phi-step replaced by one symmetric Gauss-Seidel
+    // sweep, its own check schedule and its own sigma voting: it shares the fused kernels and everything marked `inpalm`
+    const bool sgs = method == DOTSOCP_METHOD_SGSINPALM;
+    const bool inpalm = method == DOTSOCP_METHOD_INPALM || sgs, palm = method == DOTSOCP_METHOD_PALM, acc = method == DOTSOCP_METHOD_ACCADMM;
     const bool weighted = c->weighted;
     const bool checkPD = o.checkPrimDualFeas < 0 ? !weighted : (o.checkPrimDualFeas != 0);   // :20-24 / wsocp :25-29
     // NaN = opts.time_limit absent (default 3600 s, :26-30); a non-positive value is a budget that is already spent (the
@@ -1316,7 +1351,17 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     if (palm && (weighted || c->one_d)) return set_err(DOTSOCP_EINVAL, "PALM exists only for socp/dot2d");
     if (acc && c->one_d) return set_err(DOTSOCP_EINVAL, "acc-ADMM does not exist for socp/dot1d");
     if (!inpalm && c->world > 1) return set_err(DOTSOCP_EINVAL, "PALM / acc-ADMM run on a single slab only (world == 1)");
+    if (sgs && (c->variant != DOTSOCP_VARIANT_DOT2D || !sgs_supported(g)))
+        return set_err(DOTSOCP_EINVAL, "sGS-inPALM exists only for socp/dot2d, and mexsGS only handles nx == ny with odd node counts");
     int kacc = 0;
+    // sGS-inPALM state (:76-80, :109-112)
+    const int sgs_hist = 19, sgs_victory = 12;
+    const double initialSigmaScale = 1.10, sigma_adjust_val_gap = 0.95, tol_sgs_blocks = 5 * tol;
+    const double sigma_adjust_it_gap = fmax(1.0, pow((double)g.nt * g.nx * g.ny, 1.0 / 3.0) / 33.0);
+    bool stablePhase = false, sgs_superior_yes = false;
+    std::vector<double> FeasRatio;
+    if (sgs) FeasRatio.assign((size_t)maxit + 1, INFINITY);   // 1-based like the reference
+    double KRs[5] = {0, 0, 0, 0, 0}, norm_Aphi_s = 0, norm_q_s = 0;   // values of the last check (the :385-402 branch re-uses them)
 
     Loop L;
     L.c = c;
@@ -1349,6 +1394,16 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     L.scale(A_ALPHA, 1.0, sigma);
     L.scale(A_BETA, 1.0, sigma);
     L.scale(A_C, 1.0, sigma);
+    if (sgs) {   // phi = phi - integralL2(phi, h)   (solver_socp_sGSinPALM.m:142)
+        int r_;
+        if ((r_ = begin_sums(c))) return r_;
+        for (Slab* s : c->slabs) { launch_sum_nodes(g, s->phi, s->partial, c->d_lvl, 0, s->tr.tn0, s->tr.tn1, c->st); c->launches += 2; }
+        const double* v;
+        if ((r_ = finish_sums(c, &v))) return r_;
+        const double shift = (1.0 / (double)g.N) * v[0];
+        for (Slab* s : c->slabs)
+            for (auto& x : s->n_all) { launch_shift(s->phi + x.b, x.e - x.b, shift, c->st); c->launches += 1; }
+    }
     if (inpalm) L.prologue();   // z2 := d + BF q (:133) folded into the first z-step
     if (palm) {                 // tmp_q = A*phi ; mexBFd(z, tmp_q, ...)   (PALM :137-138)
         UpdateArgs a = L.ua(S0);
@@ -1425,7 +1480,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             if (!weighted) norm_d = norm_d / dScale2;
             L.scale(A_ALPHA, dScale2, cs2);
             L.scale(A_BETA, dScale2, cs2);
-            if (acc) L.scale(A_PHI, 1.0, dScale2);                 // accADMM :207
+            if (acc || sgs) L.scale(A_PHI, 1.0, dScale2);          // accADMM :207 ; sGSinPALM :184
             if (!palm) L.scale(A_Q, 1.0, dScale2);                 // :177 (absent in PALM)
             if (c->z_materialised) L.scale(A_ZMAT, 1.0, dScale2);
             if (palm) { launch_scale(tmpq, g.Q, 1.0, dScale2, c->st); c->launches += 1; }   // PALM :191
@@ -1444,14 +1499,25 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         // follows it and lets k_qstep / k_mult accumulate the KKT sums on the data they stream anyway (:218-267)
         bool fused_check = false;
         if (inpalm) {   // :192-216, fused order
-            fused_check = c->fuse_kkt && (checkSByS || IfAdjustSigma(it, lastSigmaIt) || it == maxit);
+            const bool sched = sgs ? IfAdjustSigma_sGS(it, lastSigmaIt, sigma_adjust_it_gap) : IfAdjustSigma(it, lastSigmaIt);
+            // sGS: while sgs_superior_yes holds the reference also evaluates two of the residuals on non-check iterations
+            // (:385-402); they come from the same fused sums
+            fused_check = (c->fuse_kkt || sgs) && (checkSByS || sched || it == maxit || (sgs && sgs_superior_yes));
             KktFused kf{sigma, cScale, dScale, D, E, nullptr, nullptr, c->d_lvl};
             if (fused_check) {
                 for (Slab* s : c->slabs) { KktFused tmp; if ((rc = L.kkt_fused(s, sigma, cScale, dScale, D, E, &tmp))) return rc; }
                 if ((rc = begin_sums(c))) return rc;
             }
             cudaEvent_t e0 = mark();
-            if ((rc = L.step_phi())) return rc;
+            if ((rc = sgs ? L.step_sgs() : L.step_phi())) return rc;
+            if (sgs && (checkSByS || sched || it == maxit)) {
+                // error of the sGS blocks (:212-216): ||A'(A phi - q + alpha) - c|| over the even nodes, q / alpha of the previous iterate
+                for (Slab* s : c->slabs) {
+                    launch_sgs_resid(g, L.sc, true, s->phi, s->q[c->qcur], s->alpha, s->c0, s->c1, s->partial, c->d_lvl, KS_SGS_BLOCKS,
+                                     s->tr.tn0, s->tr.tn1, c->st);
+                    c->launches += 2;
+                }
+            }
             cudaEvent_t e1 = mark();
             if ((rc = L.step_q(false, fused_check ? &kf : nullptr))) return rc;
             cudaEvent_t e2 = mark();
@@ -1511,7 +1577,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         }
 
         // ---------------------------------------------------------------- kkt :218-324
-        const bool adjustSigmaYes = IfAdjustSigma(it, lastSigmaIt);
+        const bool adjustSigmaYes = sgs ? IfAdjustSigma_sGS(it, lastSigmaIt, sigma_adjust_it_gap) : IfAdjustSigma(it, lastSigmaIt);
         bool over_time = false;
         if (!c->comm) {   // (between processes the clock is only consulted at collective points, see below)
             over_time = (now_s() - clock_total) > time_limit;
@@ -1529,6 +1595,11 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
                     KktFused kf{sigma, cScale, dScale, D, E, s->partial_q, s->partial_m, c->d_lvl};
                     launch_kkt_fused_reduce(g, s->tr, kf, c->st);
                     c->launches += 2;
+                    if (sgs) {   // ||A' resi_alpha|| = ||A'(A phi - q_new)|| of :322 (all nodes)
+                        launch_sgs_resid(g, L.sc, false, s->phi, s->q[c->qcur], nullptr, s->c0, s->c1, s->partial, c->d_lvl, KS_SGS_KKT,
+                                         s->tr.tn0, s->tr.tn1, c->st);
+                        c->launches += 2;
+                    }
                 } else {
                     launch_bfdconj(g, L.sc.S, s->beta[c->bcur], s->qtmp, c->st, &s->tr);   // q2 = s (BF)^* beta   (:225)
                     KktArgs ka;
@@ -1587,6 +1658,12 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             const double priVal = (sigma * cScale * dScale * h) * sn[KN_QDOTA];
             const double dualVal = (sigma * cScale * dScale * h) * sn[KN_CPHI];
             const double pdGap = fabs(priVal - dualVal) / (1 + fabs(priVal) + fabs(dualVal));
+            if (sgs) {   // :284 and the state the :385-402 branch re-uses
+                FeasRatio[it] = mmax({KR[0], KR[1]}) / mmax({KR[2], KR[4]});
+                for (int j = 0; j < 5; j++) KRs[j] = KR[j];
+                norm_Aphi_s = norm_Aphi;
+                norm_q_s = norm_q;
+            }
             if (hist && hist_len < hist->cap) {
                 if (hist->kkt) for (int j = 0; j < 7; j++) hist->kkt[(size_t)hist_len * 7 + j] = KO[j];
                 if (hist->time) hist->time[hist_len] = elapsed;
@@ -1601,33 +1678,91 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
                 stop = true;
             } else {
                 if (mmax({KR[0], KR[1], KR[2], KR[3], KR[4]}) < tol_feasOrg) use_feasOrg = 1;
-                if (adjustSigmaYes) {
+                auto apply_factor = [&](double factor) {
+                    L.scale(A_ALPHA, 1.0, factor);
+                    L.scale(A_BETA, 1.0, factor);
+                    L.scale(A_C, 1.0, factor);
+                    // inPALM: q2, rhs were computed with the old alpha/beta: refresh.  The prologue reads only the
+                    // current buffers, so the (q_old, beta_old) pair that defines z survives.
+                    if (inpalm) L.prologue();
+                    if (acc) {   // accADMM :346-358
+                        launch_scale(S0->old_[3], g.Q, 1.0, factor, c->st);
+                        launch_scale(S0->old_[4], nB, 1.0, factor, c->st);
+                        c->launches += 2;
+                        kacc = 0;
+                        copy_to(S0->anc_);
+                    }
+                };
+                if (sgs) {   // solver_socp_sGSinPALM.m:321-360
+                    const double kkt_sgs_blocks = sqrt(nrm(sums[KS_SGS_KKT]) * nrm(sums[KS_SGS_KKT]) + (dualFea1 / sigma) * (dualFea1 / sigma));
+                    const double resi_sGS_blocks = nrm(sums[KS_SGS_BLOCKS]);
+                    sgs_superior_yes = resi_sGS_blocks < sigma_adjust_val_gap * kkt_sgs_blocks;
+                    if (adjustSigmaYes) {
+                        lastSigmaIt = it;
+                        const int i0 = std::max(1, it - sgs_hist);
+                        double sum = 0;
+                        int primWin = 0, dualWin = 0;
+                        for (int i = i0; i <= it; i++) {
+                            sum += FeasRatio[i];
+                            primWin += FeasRatio[i] < 1;
+                            dualWin += FeasRatio[i] > 1;
+                        }
+                        const double meanFeasRatio = sum / (double)(it - i0 + 1);
+                        const bool adjust2 = sgs_superior_yes || stopv < tol_sgs_blocks || (dualWin >= sgs_victory && meanFeasRatio > 1);
+                        if (adjust2) {
+                            if (it > 2500) stablePhase = true;
+                            if ((primWin >= sgs_victory && meanFeasRatio < 1) || (dualWin >= sgs_victory && meanFeasRatio > 1)) {
+                                double factor = 1;
+                                if (stablePhase) {
+                                    adjust_lagrangianParam(sigma, meanFeasRatio, factor, SGS_UPDATE_RULE, 6);
+                                } else {
+                                    if (meanFeasRatio < 1) factor = 1 / initialSigmaScale;
+                                    else if (meanFeasRatio > 1) factor = initialSigmaScale;
+                                    sigma = sigma * factor;
+                                }
+                                if (factor != 1) apply_factor(factor);
+                            }
+                        }
+                    }
+                } else if (adjustSigmaYes) {
                     lastSigmaIt = it;
                     double resiPri, resiDual;
                     if (use_feasOrg) { resiPri = mmax({KO[0], KO[1]}); resiDual = mmax({KO[2], KO[4]}); }
                     else { resiPri = mmax({KR[0], KR[1]}); resiDual = mmax({KR[2], KR[4]}); }
                     double factor = 1;
                     adjust_lagrangianParam(sigma, resiPri / resiDual, factor);
-                    if (factor != 1) {
-                        L.scale(A_ALPHA, 1.0, factor);
-                        L.scale(A_BETA, 1.0, factor);
-                        L.scale(A_C, 1.0, factor);
-                        // inPALM: q2, rhs were computed with the old alpha/beta: refresh.  The prologue reads only the
-                        // current buffers, so the (q_old, beta_old) pair that defines z survives.
-                        if (inpalm) L.prologue();
-                        if (acc) {   // accADMM :346-358
-                            launch_scale(S0->old_[3], g.Q, 1.0, factor, c->st);
-                            launch_scale(S0->old_[4], nB, 1.0, factor, c->st);
-                            c->launches += 2;
-                            kacc = 0;
-                            copy_to(S0->anc_);
-                        }
-                    }
+                    if (factor != 1) apply_factor(factor);
                 }
                 if (rescale > 0) {
                     maxFeas = mmax({KR[0], KR[1], KR[2], KR[3], KR[4]});
                     relGap = pdGap;
                 }
+            }
+        }
+        if (sgs && !check) {
+            if (fused_check) {   // sgs_superior_yes: primal / dual feasibility of this iteration from the fused sums (:385-402)
+                for (Slab* s : c->slabs) {
+                    KktFused kf{sigma, cScale, dScale, D, E, s->partial_q, s->partial_m, c->d_lvl};
+                    launch_kkt_fused_reduce(g, s->tr, kf, c->st);
+                    c->launches += 2;
+                }
+                const double* sums;
+                if ((rc = finish_sums(c, &sums))) return rc;
+                flush_segs();
+                const double primFea1 = sqrt(h) * sqrt(sums[KC_COUNT + KN_PRIM1]);
+                const double dualFea1 = sigma * (sqrt(h) * sqrt(sums[KC_COUNT + KN_DUAL1]));
+                if (use_feasOrg) {
+                    const double dec = primFea1 / ((kktConst * D / dScale + norm_Aphi_s + norm_q_s) * KRs[0]);
+                    KRs[0] *= dec; KRs[1] *= dec;
+                    KRs[2] = dualFea1 / (kktConst / cScale + norm_c);
+                } else {
+                    const double dec = primFea1 / ((kktConst + norm_Aphi_s + norm_q_s) * KRs[0]);
+                    KRs[0] *= dec; KRs[1] *= dec;
+                    KRs[2] = dualFea1 / (kktConst + norm_c);
+                }
+                FeasRatio[it] = mmax({KRs[0], KRs[1]}) / mmax({KRs[2], KRs[4]});
+            } else {
+                FeasRatio[it] = FeasRatio[it - 1];
             }
         }
         if (stop) break;
@@ -1698,7 +1833,7 @@ extern "C" int dotsocp_run(dotsocp_ctx* c, const dotsocp_level_opts* o, dotsocp_
     if (o->variant != c->variant || o->nt != c->g.nt || o->nx != c->g.nx || o->ny != c->g.ny)
         return set_err(DOTSOCP_EINVAL, "opts do not match the context (variant/grid)");
     if (o->maxit < 1) return set_err(DOTSOCP_EINVAL, "maxit must be >= 1");
-    if (o->method < 0 || o->method > 2) return set_err(DOTSOCP_EINVAL, "unknown method %d", o->method);
+    if (o->method < 0 || o->method > 3) return set_err(DOTSOCP_EINVAL, "unknown method %d", o->method);
     return run_level(c, *o, hist, res);
 }
 
@@ -1742,7 +1877,7 @@ extern "C" int dotsocp_solve_level(const dotsocp_level_opts* o, double* phi, dou
     if (rc) return rc;
     const double launches0 = c->launches;
     // inPALM overwrites z (solver_socp_inPALM.m:199) before it is ever read, so its incoming value need not cross PCIe
-    const bool z_dead = o->method == DOTSOCP_METHOD_INPALM && o->maxit >= 1;
+    const bool z_dead = (o->method == DOTSOCP_METHOD_INPALM || o->method == DOTSOCP_METHOD_SGSINPALM) && o->maxit >= 1;
     rc = dotsocp_upload(c, phi, q, z_dead ? nullptr : z, alpha, beta, cvec, weight);
     if (!rc) rc = dotsocp_run(c, o, hist, res);
     if (!rc) rc = dotsocp_download(c, phi, q, z, alpha, beta);

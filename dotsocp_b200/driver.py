@@ -448,20 +448,22 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
         raise ValueError("Invalid input at position 4 (Number of levels in multilevel strategy)")
     if method not in _VALID[variant]:
         raise ValueError("Invalid input at position 6 (Solving method)")
-    if method in ("sGS-inPALM", "acc-sGS-ADMM"):
-        raise NotImplementedError("sGS variants are not part of this build (SURVEY.md §8f)")
+    if method == "acc-sGS-ADMM":
+        raise NotImplementedError("acc-sGS-ADMM is not part of this build (SURVEY.md §8f)")
+    sgsMethod = method == "sGS-inPALM"                                   # solver_dotsocp2d.m:93-97
+    admmMaxIt, sgsMaxIt = 3000, 6000
     opts.setdefault("ifCheckStepByStep", False)
     scalingYes = opts.setdefault("scaling", True)
     optsML = dict(opts)
     if "maxit" not in opts:
-        optsML["maxit"] = int(1e4) if variant == "wdot2d" else 3000
+        optsML["maxit"] = int(1e4) if variant == "wdot2d" else (sgsMaxIt if sgsMethod else admmMaxIt)
     optsML["tolFactor"] = -1 if optsML["tol"] > 0.99e-3 else -0.5
     tolLowerBound = 1e-5 if variant == "dot1d" else 1e-4
-    if method in ("PALM", "inPALM"):
+    if method in ("PALM", "inPALM", "sGS-inPALM"):
         optsML["tau"] = 1.9
     elif method == "ALG2":
         optsML["tau"] = 1.0
-    optsML.setdefault("sigma", 1)
+    optsML.setdefault("sigma", 0.1 if sgsMethod else 1)                  # :139-146
     optsML.setdefault("time_limit", 3600)
     weight = opts.get("weight") if variant == "wdot2d" else None
     if variant == "wdot2d" and weight is None:
@@ -513,6 +515,12 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
             runHist, sigma = S.solver_socp_PALM(var, o2, model)
         elif method in ("inPALM", "ALG2"):
             runHist, sigma = (S.solver_wsocp_inPALM if variant == "wdot2d" else S.solver_socp_inPALM)(var, o2, model)
+        elif method == "sGS-inPALM":                                     # :210-216: sGS on the last level only
+            if level == levelN - 1:
+                runHist, sigma = S.solver_socp_sGSinPALM(var, o2, model)
+            else:
+                o2["maxit"] = admmMaxIt
+                runHist, sigma = S.solver_socp_inPALM(var, o2, model)
         else:
             runHist, sigma = (S.solver_wsocp_accADMM if variant == "wdot2d" else S.solver_socp_accADMM)(var, o2, model)
         recoverOrgVar(var, inplace=True)          # the level solver returned freshly downloaded arrays
@@ -560,7 +568,8 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
         rank, world, ident, distributed = 0, int(slabs or 1), None, False
     InitialScaling(var, model, scalingYes, None, variant)          # coarsest level: host arrays, as the reference
     sess = S.Session(variant, model.nt, model.nx, model.ny, rank=rank, world=world, nccl_id=ident)
-    mname = "inPALM" if method in ("inPALM", "ALG2") else method
+    sgs_last = method == "sGS-inPALM"                               # coarse levels: inPALM with maxit 3000, last level: sGS (:210-216)
+    mname = "inPALM" if method in ("inPALM", "ALG2", "sGS-inPALM") else method
     z_dead = mname == "inPALM" and int(optsML["maxit"]) >= 1
     state0 = (var.phi, var.q, None if z_dead else var.z, var.alpha, var.beta, model.c, model.weight if weighted else None)
     if distributed:
@@ -573,7 +582,13 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
         for level in range(levelN):
             o2 = dict(optsML)
             o2["tol"] = tols[level]
-            lo = S.make_level_opts(variant, mname, var, o2, model)
+            lname = mname
+            if sgs_last:
+                if level == levelN - 1:
+                    lname = "sGS-inPALM"
+                else:
+                    o2["maxit"] = 3000
+            lo = S.make_level_opts(variant, lname, var, o2, model)
             hb, res = sess.run(lo)
             runHist, sigma = S._finish(var, lo.method, hb, res)      # var.cScale/dScale/D/E after in-loop rescaling, var.time
             timeML[level] = var.time

@@ -6,6 +6,7 @@ reference's pre-built MEX kernels:
     mexBFd(z2, q, nt, nx, ny, scaleBF, scaleD)      socp/dot2d/algorithms/solver_socp_inPALM.m:133
     mexBFdConj(q2, z, nt, nx, ny, scaleBF)          socp/dot2d/algorithms/solver_socp_inPALM.m:205
     mexProjSoc(out, in)                             socp/dot2d/algorithms/solver_socp_inPALM.m:199
+    mexsGS(phi, rhs, ep, scale, nt, nx, ny, its)    socp/dot2d/algorithms/solver_socp_sGSinPALM.m:205
     mexBFd1d(z, q, nt, nx, scale, dFactor)          socp/dot1d/algorithms/solver_socp_inPALM.m:132
     mexBFdConj1d(q, z, nt, nx, scale)               socp/dot1d/algorithms/solver_socp_inPALM.m:204
     oper_poisson3dim / oper_poisson                  socp/dot2d/utils/oper_poisson3dim.m:4, dot1d/utils/oper_poisson.m:4
@@ -54,6 +55,13 @@ def mexProjSoc(out, inp):
         raise ValueError("in: expected a 2-D array")
     _mat(inp, inp.shape, "in"); _mat(out, inp.shape, "out")
     check(lib().dotsocp_mexProjSoc(ptr(out), ptr(inp), inp.shape[0], inp.shape[1]))
+
+
+def mexsGS(phi, rhs, ep, scale, nt, nx, ny, its):
+    """`its` symmetric red-black Gauss-Seidel sweeps for scale*(A'A + ep*I) phi = rhs, in place into phi (nx == ny, odd sizes)"""
+    nt, nx, ny = int(nt), int(nx), int(ny)
+    _vec(phi, nt * nx * ny, "phi"); _vec(rhs, nt * nx * ny, "rhs")
+    check(lib().dotsocp_mexsGS(ptr(phi), ptr(rhs), float(ep), float(scale), nt, nx, ny, int(its)))
 
 
 def mexBFd1d(z, q, nt, nx, scale, dFactor):

@@ -25,8 +25,9 @@ TIME_NAMES = {
     0: ["Step_1_1_FFT", "Step_1_2_ProjSOC", "Step_2_Q_Step", "Step_3_Multiplier", "KKT", "Total_Time"],
     1: ["Step_1_Q_Step", "Step_2_1_FFT", "Step_2_2_ProjSOC", "Step_3_Q_Step", "Step_4_Multiplier", "KKT", "Total_Time"],
     2: ["Step_1_Q_Step", "Step_2_Multiplier", "Step_3_1_FFT", "Step_3_2_ProjSOC", "KKT", "Interp", "Total_Time"],
+    3: ["Step_1_1_sGS", "Step_1_2_ProjSOC", "Step_2_Q_Step", "Step_3_Multiplier", "KKT", "Total_Time"],
 }
-METHOD_NAMES = {0: "Inexact Proximal ALM", 1: "Proximal ALM", 2: "Accelerated ADMM"}
+METHOD_NAMES = {0: "Inexact Proximal ALM", 1: "Proximal ALM", 2: "Accelerated ADMM", 3: "Symmetric Gauss-seidel based inPALM"}
 
 
 def _get(opts, name, default=None):
@@ -254,7 +255,7 @@ def _solve(variant, method, var, opts, model):
         raise ValueError("solver_wsocp_*: model.weight is required")
     with Session(variant, o.nt, o.nx, o.ny) as s:
         # inPALM overwrites z (solver_socp_inPALM.m:199) before reading it: the incoming z stays on the host
-        z_dead = o.method == METHOD["inPALM"] and o.maxit >= 1
+        z_dead = o.method in (METHOD["inPALM"], METHOD["sGS-inPALM"]) and o.maxit >= 1
         s.upload(var.phi, var.q, None if z_dead else var.z, var.alpha, var.beta, model.c, weight)
         hb, res = s.run(o)
         var.phi, var.q, var.z, var.alpha, var.beta = s.download()
@@ -289,6 +290,11 @@ def solver_socp_PALM(var, opts, model):
 def solver_socp_accADMM(var, opts, model):
     """socp/dot2d/algorithms/solver_socp_accADMM.m:1"""
     return _solve("dot2d", "acc-ADMM", var, opts, model)
+
+
+def solver_socp_sGSinPALM(var, opts, model):
+    """socp/dot2d/algorithms/solver_socp_sGSinPALM.m:1 (the phi-step is one red-black symmetric Gauss-Seidel sweep, mexsGS)"""
+    return _solve("dot2d", "sGS-inPALM", var, opts, model)
 
 
 def solver_wsocp_accADMM(var, opts, model):

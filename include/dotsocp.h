@@ -15,13 +15,14 @@
  *     dotsocp_mexBFd        <- mexBFd(z2,q,nt,nx,ny,scaleBF,scaleD)     socp/dot2d/algorithms/solver_socp_inPALM.m:133,187,212,242
  *     dotsocp_mexBFdConj    <- mexBFdConj(q2,z,nt,nx,ny,scaleBF)        socp/dot2d/algorithms/solver_socp_inPALM.m:205,225 ; utils/jump_nextLevel.m:16
  *     dotsocp_mexProjSoc    <- mexProjSoc(out,in)                        socp/dot2d/algorithms/solver_socp_inPALM.m:199,240
+ *     dotsocp_mexsGS        <- mexsGS(phi,rhs,ep,scale,nt,nx,ny,its)      socp/dot2d/algorithms/solver_socp_sGSinPALM.m:205
  *     dotsocp_mexBFd1d      <- mexBFd1d(z,q,nt,nx,scale,dFactor)         socp/dot1d/algorithms/solver_socp_inPALM.m:132,186,211,241
  *     dotsocp_mexBFdConj1d  <- mexBFdConj1d(q,z,nt,nx,scale)             socp/dot1d/algorithms/solver_socp_inPALM.m:204,224
  *     dotsocp_poisson       <- oper_poisson3dim(D^2*initialize_FFTkernel(nt,nx,ny), rhs)   socp/dot2d/utils/oper_poisson3dim.m:4,
  *                              initialize_FFTkernel.m:6-15 ; 1-D: socp/dot1d/utils/oper_poisson.m:4  (ny = 1)
  *   solver level  (the boundary the north star names)
  *     dotsocp_solve_level   <- [runHist,sigma] = solver_socp_inPALM(var,opts,model)   socp/dot2d/algorithms/solver_socp_inPALM.m:1
- *                              solver_socp_PALM.m:1, solver_socp_accADMM.m:1,
+ *                              solver_socp_PALM.m:1, solver_socp_accADMM.m:1, solver_socp_sGSinPALM.m:1,
  *                              socp/wdot2d/algorithms/solver_wsocp_inPALM.m:1, solver_wsocp_accADMM.m:1,
  *                              socp/dot1d/algorithms/solver_socp_inPALM.m:1
  *   device-resident session (same loop, state stays in HBM; used by the multilevel driver and the benchmark)
@@ -53,6 +54,7 @@ extern "C" {
 #define DOTSOCP_METHOD_INPALM   0   /* solver_*socp_inPALM.m ; "ALG2" is the same loop with tau = 1 */
 #define DOTSOCP_METHOD_PALM     1   /* solver_socp_PALM.m (dot2d only) */
 #define DOTSOCP_METHOD_ACCADMM  2   /* solver_*socp_accADMM.m (dot2d, wdot2d) */
+#define DOTSOCP_METHOD_SGSINPALM 3  /* solver_socp_sGSinPALM.m (dot2d, nx == ny, odd node counts: the grids mexsGS handles) */
 
 #define DOTSOCP_NTIMES 8
 
@@ -90,6 +92,7 @@ typedef struct dotsocp_level_result {
                                        inPALM : FFT, ProjSOC, Q_Step, Multiplier, KKT, Total, 0, 0      (:339-340)
                                        PALM   : Q_Step(1), FFT, ProjSOC, Q_Step(3), Multiplier, KKT, Total, 0
                                        accADMM: Q_Step, Multiplier, FFT, ProjSOC, KKT, Interp, Total, 0
+                                       sGSinPALM: sGS, ProjSOC, Q_Step, Multiplier, KKT, Total, 0, 0  (:419-420)
                                        The fused kernels do not separate ProjSOC from the multiplier step; the fused
                                        time is booked under the step that dominates it.             */
     double  gpu_launches;       /* number of kernels launched by this call                              */
@@ -115,6 +118,9 @@ int  dotsocp_set_device(int device);
 int dotsocp_mexBFd(double *z2, const double *q, int nt, int nx, int ny, double scaleBF, double scaleD);
 int dotsocp_mexBFdConj(double *q2, const double *z, int nt, int nx, int ny, double scaleBF);
 int dotsocp_mexProjSoc(double *out, const double *in, int64_t M, int N);
+/* mexsGS(phi, rhs, ep, scale, nt, nx, ny, its): `its` symmetric red-black Gauss-Seidel sweeps, in place into phi
+ * (mexsGS.mexa64; solver_socp_sGSinPALM.m:205, solver_socp_accsGSADMM.m:256).  nx == ny, odd node counts only.        */
+int dotsocp_mexsGS(double *phi, const double *rhs, double ep, double scale, int nt, int nx, int ny, int its);
 int dotsocp_mexBFd1d(double *z, const double *q, int nt, int nx, double scale, double dFactor);
 int dotsocp_mexBFdConj1d(double *q, const double *z, int nt, int nx, double scale);
 /* phi = idctn( dctn(rhs) ./ (D^2 * kernel) ), Neumann eigenvalues, zero mode := 1 */

@@ -8,7 +8,7 @@
 //                          .m wrapper must own the only reference (the reference loop detaches them from the handle
 //                          for the same reason, solver_socp_inPALM.m:89-93).
 // c                      : model.c (N x 1, already scaled);   weight : model.weight (Q x 1) or [] (unweighted)
-// P                      : struct of scalars -- variant ('dot2d'|'wdot2d'|'dot1d'), method ('inPALM'|'PALM'|'acc-ADMM'),
+// P                      : struct of scalars -- variant ('dot2d'|'wdot2d'|'dot1d'), method ('inPALM'|'PALM'|'acc-ADMM'|'sGS-inPALM'),
 //                          nt,nx,ny, maxit, tol, tau, sigma, ifCheckStepByStep, scaling, checkPrimDualFeas (-1 = absent),
 //                          time_limit, restart, rho, theta, cScale, dScale, D, E, normc, normd, grad_t, grad_x, grad_y
 // out                    : struct with kkt (len x 7), time, iter, pdGap, priVal, dualVal (len x 1), len, iters, sigma,
@@ -77,6 +77,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
     if (method == "inPALM" || method == "ALG2") o.method = DOTSOCP_METHOD_INPALM;
     else if (method == "PALM") o.method = DOTSOCP_METHOD_PALM;
     else if (method == "acc-ADMM") o.method = DOTSOCP_METHOD_ACCADMM;
+    else if (method == "sGS-inPALM") o.method = DOTSOCP_METHOD_SGSINPALM;
     else mexErrMsgIdAndTxt("dotsocp:invalidInput", "unknown method '%s'", method.c_str());
     o.nt = (int)field(P, "nt", 0, true);
     o.nx = (int)field(P, "nx", 0, true);

@@ -563,6 +563,254 @@ def solver_socp_inPALM(var, opts, model, workers=1, palm=False, trace=None):
     return runHist, sigma / sigmaScale
 
 
+SGS_UPDATE_RULE = np.array([[1.5, 1.20], [2, 1.26], [2.5, 1.28], [3.33, 1.32], [5, 1.35], [10, 1.40]])   # sGSinPALM.m:37-44
+
+
+def IfAdjustSigma_sGS(it, last_it, scale=1):
+    """solver_socp_sGSinPALM.m:431-456"""
+    passed = it - last_it
+    it = it / scale
+    passed = passed / scale
+    if it < 20 and passed >= 5:
+        return True
+    if it < 50 and passed >= 10:
+        return True
+    if it < 100 and passed >= 20:
+        return True
+    if it < 200 and passed >= 35:
+        return True
+    if it < 500 and passed >= 50:
+        return True
+    return passed >= 100
+
+
+def solver_socp_sGSinPALM(var, opts, model, workers=1, trace=None):
+    """socp/dot2d/algorithms/solver_socp_sGSinPALM.m:1-429 : inPALM whose phi-step is ONE symmetric red-black Gauss-Seidel
+    sweep (mexsGS, :205) instead of the DCT Poisson solve, with the sGS-specific sigma voting (:322-360).  2-D, unweighted."""
+    ops = _Ops(model, var, workers)
+    checkPD = _opt(opts, "checkPrimDualFeas", True)                            # :20-24
+    time_limit = _opt(opts, "time_limit", 3600)
+    tau, sigma, maxit, tol = opts["tau"], opts["sigma"], int(opts["maxit"]), opts["tol"]
+    checkSByS = opts["ifCheckStepByStep"]
+    lastSigmaIt = -INF
+    sGSits = 1
+    cScale, dScale, D, E = var.cScale, var.dScale, var.D, var.E                # :47-55
+    scaleBF = E / D
+    scaleD = E / dScale
+    scaleLap = D ** 2
+    use_feasOrg = False
+    tol_feasOrg = 5 * tol
+    rescale = 1 if _opt(opts, "scaling", False) else 0
+    firstScaleIter, SecondScaleIter, checkRescaleIters, ratioThreshold = 10, 50, 100, 1.2
+    maxFeas, relGap = INF, INF
+    hist_n, victory, initialSigmaScale, stablePhase = 19, 12, 1.10, False     # :76-80
+    nx, ny, nt = model.nx, model.ny, model.nt
+    h = 1 / (nx * ny * nt)
+    A, AT = model.grad, model.gradT
+    c = model.c
+    phi, q, z, alpha, beta = var.phi, var.q, var.z, var.alpha, var.beta        # :92-96
+    var.phi = var.q = var.z = var.alpha = var.beta = None
+    z = np.asfortranarray(z)
+    diagQInv = 1 / ops.oper_q(D, E, None)                                      # :99
+    norm_c, norm_d = model.normc, model.normd
+    alpha = alpha / sigma
+    beta = np.asfortranarray(beta / sigma)
+    c = c / sigma
+    sigmaScale = 1
+    sigma_adjust_it_gap = max(1, (nt * nx * ny) ** (1 / 3) / 33)               # :109
+    sigma_adjust_val_gap = 0.95
+    sgs_superior_yes = False
+    tol_sgs_blocks = 5 * tol
+    kktConst = 1
+    hist = Handle(kkt=[], time=[], iter=[], pdGap=[], priVal=[], dualVal=[])
+    FeasRatio = np.full(maxit + 1, INF)                                        # 1-based like the reference
+    stopCondition = [0, 2, 5, 6] if checkPD else [0, 2, 5]
+    T = dict(lineq=0.0, proj=0.0, q=0.0, mult=0.0, kkt=0.0)
+    z2 = np.zeros(z.shape, order="F")
+    q2 = np.zeros(q.shape)
+    ops.BFd(z2, q, scaleBF, scaleD)
+    phi = phi - h * phi.sum()                                                  # :142  phi - integralL2(phi, h)
+    KKTResi = None
+    norm_Aphi = norm_q = None
+    clock_total = time.perf_counter()
+    it = 0
+    for it in range(1, maxit + 1):
+        # ---- rescaling :147-201 (phi is rescaled too, :184) ----
+        scaleYes = 0
+        if rescale >= 3 and it % checkRescaleIters == 0:
+            normPhi, normQ, normZ = normL2(phi, h), normL2(q, h), FnormL2(z, h)
+            normAlpha, normBeta = sigma * normL2(alpha, h), sigma * FnormL2(beta, h)
+            normPhis = max(normPhi, normQ, normZ)
+            normAlps = max(normAlpha, normBeta)
+            ratio = max(normAlps, normPhis) / min(normAlps, normPhis)
+            if ratio > ratioThreshold:
+                scaleYes = 1
+        if ((rescale == 1 and maxFeas < 2e-2 and it >= firstScaleIter and relGap < 5e-2)
+                or (rescale == 2 and maxFeas < 5e-3 and it >= SecondScaleIter and relGap < 1e-2)
+                or scaleYes):
+            if not scaleYes:
+                normPhi, normQ, normZ = normL2(phi, h), normL2(q, h), FnormL2(z, h)
+                normAlpha, normBeta = sigma * normL2(alpha, h), sigma * FnormL2(beta, h)
+                normPhis = max(normPhi, normQ, normZ)
+                normAlps = max(normAlpha, normBeta)
+            dScale2, cScale2 = normPhis, normAlps
+            sigma = sigma * (cScale2 / dScale2)
+            c = c * dScale2 / cScale2 ** 2
+            norm_c = norm_c / cScale2
+            norm_d = norm_d / dScale2
+            alpha = alpha * dScale2 / cScale2 ** 2
+            beta = beta * dScale2 / cScale2 ** 2
+            phi = phi / dScale2
+            q = q / dScale2
+            dScale = dScale2 * dScale
+            cScale = cScale2 * cScale
+            scaleD = E / dScale
+            sigmaScale = sigmaScale * (cScale2 / dScale2)
+            ops.BFd(z2, q, scaleBF, scaleD)
+            rescale += 1
+            if trace is not None:
+                trace.append(("rescale", it, dScale2, cScale2))
+        # ---- step phi :203-206 ----
+        t0 = time.perf_counter()
+        K.mexsGS(phi, AT @ (q - alpha) + c, 0, scaleLap, nt, nx, ny, sGSits)
+        T["lineq"] += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        adjustSigmaYes = IfAdjustSigma_sGS(it, lastSigmaIt, sigma_adjust_it_gap)
+        check = checkSByS or adjustSigmaYes or it == maxit or (time.perf_counter() - clock_total) > time_limit
+        if check:
+            tmp_resi_sGS = AT @ (A @ phi - q + alpha) - c                      # :212-216
+            resi_sGS_blocks = normL2(tmp_resi_sGS[0::2], h)
+        T["kkt"] += time.perf_counter() - t0
+        # ---- step z :219-222 ----
+        t0 = time.perf_counter()
+        K.mexProjSoc(z, np.asfortranarray(z2 - beta))
+        T["proj"] += time.perf_counter() - t0
+        # ---- step q :224-229 ----
+        t0 = time.perf_counter()
+        tmp_q = A @ phi
+        ops.BFdConj(q2, np.asfortranarray(z + beta), scaleBF)
+        q = (tmp_q + alpha + q2) * diagQInv
+        T["q"] += time.perf_counter() - t0
+        # ---- step alpha, beta :231-238 ----
+        t0 = time.perf_counter()
+        resi_alpha = tmp_q - q
+        ops.BFd(z2, q, scaleBF, scaleD)
+        resi_beta = z - z2
+        alpha = alpha + tau * resi_alpha
+        beta = beta + tau * resi_beta
+        T["mult"] += time.perf_counter() - t0
+        # ---- kkt :240-416 ----
+        t0 = time.perf_counter()
+        stop = False
+        if check:
+            ops.BFdConj(q2, np.asfortranarray(beta), scaleBF)
+            norm_q = normL2(q, h)
+            norm_z = FnormL2(z, h)
+            norm_Aphi = normL2(tmp_q, h)
+            norm_alpha = sigma * normL2(alpha, h)
+            norm_beta = sigma * FnormL2(beta, h)
+            norm_FBbeta = sigma * normL2(q2, h)
+            primFea1 = normL2(resi_alpha, h)
+            primFea2 = FnormL2(resi_beta, h)
+            dualFea1 = sigma * normL2(AT @ alpha - c, h)
+            dualFea2 = sigma * normL2(q2 + alpha, h)
+            K.mexProjSoc(z2, np.asfortranarray(z - sigma * beta))
+            complem = FnormL2(z - z2, h)
+            ops.BFd(z2, q, scaleBF, scaleD)
+            dotcomplem, normRho, norm_rhoFq, mRhoB, normM, normRhoB = ops.kkt_dot(q, alpha, z2, sigma, cScale, dScale, D, E, None)
+            KKTResiOrg = [
+                primFea1 / (kktConst * D / dScale + norm_Aphi + norm_q),
+                primFea2 / (kktConst * E / dScale + norm_d),
+                dualFea1 / (kktConst / cScale + norm_c),
+                complem / (kktConst * E / dScale + norm_z + norm_beta),
+                dualFea2 / (kktConst / cScale / D + norm_FBbeta + norm_alpha),
+                dotcomplem / (kktConst + normRho + norm_rhoFq),
+                mRhoB / (kktConst + normM + normRhoB)]
+            KKTResi = [
+                primFea1 / (kktConst + norm_Aphi + norm_q),
+                primFea2 / (kktConst + norm_d),
+                dualFea1 / (kktConst + norm_c),
+                complem / (kktConst + norm_z + norm_beta),
+                dualFea2 / (kktConst + norm_FBbeta + norm_alpha)]
+            FeasRatio[it] = mmax(KKTResi[0:2]) / mmax([KKTResi[2], KKTResi[4]])
+            priVal = (sigma * cScale * dScale * h) * float(np.dot(q, alpha))
+            dualVal = (sigma * cScale * dScale * h) * float(np.dot(c, phi))
+            pdGap = abs(priVal - dualVal) / (1 + abs(priVal) + abs(dualVal))
+            hist.kkt.append(KKTResiOrg)
+            hist.time.append(time.perf_counter() - clock_total)
+            hist.iter.append(it)
+            hist.pdGap.append(pdGap)
+            hist.priVal.append(priVal)
+            hist.dualVal.append(dualVal)
+            error = mmax([KKTResiOrg[i] for i in stopCondition])
+            if trace is not None:
+                trace.append(("check", it, sigma, list(KKTResiOrg), list(KKTResi), priVal, dualVal))
+            if error < tol or (time.perf_counter() - clock_total) > time_limit:
+                stop = True
+            else:
+                if (not use_feasOrg) and mmax(KKTResi) < tol_feasOrg:
+                    use_feasOrg = True
+                kkt_sgs_blocks = math.sqrt(normL2(AT @ resi_alpha, h) ** 2 + (dualFea1 / sigma) ** 2)      # :322-323
+                sgs_superior_yes = resi_sGS_blocks < sigma_adjust_val_gap * kkt_sgs_blocks
+                if adjustSigmaYes:
+                    lastSigmaIt = it
+                    feasRatioHist = FeasRatio[max(1, it - hist_n): it + 1]
+                    meanFeasRatio = float(np.mean(feasRatioHist))
+                    primWinTimes = int(np.sum(feasRatioHist < 1))
+                    dualWinTimes = int(np.sum(feasRatioHist > 1))
+                    adjust_sigma_yes_2 = (sgs_superior_yes or (error < tol_sgs_blocks)
+                                          or ((dualWinTimes >= victory) and (meanFeasRatio > 1)))
+                    if adjust_sigma_yes_2:
+                        if it > 2500:
+                            stablePhase = True
+                        if (((primWinTimes >= victory) and (meanFeasRatio < 1))
+                                or ((dualWinTimes >= victory) and (meanFeasRatio > 1))):
+                            factor = 1
+                            if stablePhase:
+                                sigma, factor = adjust_lagrangianParam(sigma, meanFeasRatio, SGS_UPDATE_RULE)
+                            else:
+                                if meanFeasRatio < 1:
+                                    factor = 1 / initialSigmaScale
+                                elif meanFeasRatio > 1:
+                                    factor = initialSigmaScale
+                                sigma = sigma * factor
+                            if factor != 1:
+                                alpha = alpha / factor
+                                beta = beta / factor
+                                c = c / factor
+                if rescale > 0:
+                    maxFeas = mmax(KKTResi)
+                    relGap = pdGap
+        elif sgs_superior_yes:                                                 # :385-402
+            primFea1 = normL2(resi_alpha, h)
+            dualFea1 = sigma * normL2(AT @ alpha - c, h)
+            if use_feasOrg:
+                relaPrimFeaDec = primFea1 / ((kktConst * D / dScale + norm_Aphi + norm_q) * KKTResi[0])
+                KKTResi[0] = KKTResi[0] * relaPrimFeaDec
+                KKTResi[1] = KKTResi[1] * relaPrimFeaDec
+                KKTResi[2] = dualFea1 / (kktConst / cScale + norm_c)
+            else:
+                relaPrimFeaDec = primFea1 / ((kktConst + norm_Aphi + norm_q) * KKTResi[0])
+                KKTResi[0] = KKTResi[0] * relaPrimFeaDec
+                KKTResi[1] = KKTResi[1] * relaPrimFeaDec
+                KKTResi[2] = dualFea1 / (kktConst + norm_c)
+            FeasRatio[it] = mmax(KKTResi[0:2]) / mmax([KKTResi[2], KKTResi[4]])
+        else:
+            FeasRatio[it] = FeasRatio[it - 1]
+        T["kkt"] += time.perf_counter() - t0
+        if stop:
+            break
+    time_total = time.perf_counter() - clock_total
+    var.name = "Symmetric Gauss-seidel based inPALM"
+    var.phi, var.q, var.z = phi, q, z
+    var.alpha = sigma * alpha
+    var.beta = sigma * beta
+    var.time = {"Step_1_1_sGS": T["lineq"], "Step_1_2_ProjSOC": T["proj"], "Step_2_Q_Step": T["q"], "Step_3_Multiplier": T["mult"],
+                "KKT": T["kkt"], "Total_Time": time_total, "Iters": it}
+    var.cScale, var.dScale, var.D, var.E = cScale, dScale, D, E
+    return _finish_hist(hist), sigma / sigmaScale
+
+
 def _finish_hist(hist):
     n = len(hist.iter)
     return Handle(kkt=np.array(hist.kkt, dtype=np.float64).reshape(n, 7), time=np.array(hist.time, dtype=np.float64),
@@ -1119,13 +1367,15 @@ def _solve_multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=Non
              "wdot2d": ["inPALM", "ALG2", "acc-ADMM"], "dot1d": ["inPALM", "ALG2"]}[variant]
     if method not in valid:
         raise ValueError("Invalid input at position 6 (Solving method)")
-    if method in ("sGS-inPALM", "acc-sGS-ADMM"):
-        raise NotImplementedError("sGS variants are SURVEY.md §8f 'next' rows")
+    if method == "acc-sGS-ADMM":
+        raise NotImplementedError("acc-sGS-ADMM is not restated (SURVEY.md §8f 'next' row)")
+    sgsMethod = method in ("sGS-inPALM", "acc-sGS-ADMM")                         # solver_dotsocp2d.m:93
+    admmMaxIt, sgsMaxIt = 3000, 6000                                             # :96-97
     opts.setdefault("ifCheckStepByStep", False)
     scalingYes = opts.setdefault("scaling", True)
     optsML = dict(opts)
     if "maxit" not in opts:
-        optsML["maxit"] = 1e4 if variant == "wdot2d" else 3000
+        optsML["maxit"] = 1e4 if variant == "wdot2d" else (sgsMaxIt if sgsMethod else admmMaxIt)     # :114-121
     optsML["tolFactor"] = -1 if optsML["tol"] > 0.99e-3 else -0.5
     tolLowerBound = 1e-5 if variant == "dot1d" else 1e-4
     if variant == "dot2d":
@@ -1139,7 +1389,7 @@ def _solve_multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=Non
         elif method == "ALG2":
             optsML["tau"] = 1.0
     if "sigma" not in optsML:
-        optsML["sigma"] = 1 if "scaling" in opts else 0.1
+        optsML["sigma"] = 1 if ("scaling" in opts and not sgsMethod) else 0.1   # :139-146
     optsML.setdefault("time_limit", 3600)
     weight = opts.get("weight") if variant == "wdot2d" else None
     # ---- preparation :159-178 ----
@@ -1188,6 +1438,12 @@ def _solve_multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=Non
             runHist, sigma = solver_socp_inPALM(var, o2, model, workers, palm=True, trace=trace)
         elif method in ("inPALM", "ALG2"):
             runHist, sigma = solver_socp_inPALM(var, o2, model, workers, trace=trace)
+        elif method == "sGS-inPALM":                                             # :210-216: sGS on the last level only
+            if level == levelN - 1:
+                runHist, sigma = solver_socp_sGSinPALM(var, o2, model, workers, trace=trace)
+            else:
+                o2["maxit"] = admmMaxIt
+                runHist, sigma = solver_socp_inPALM(var, o2, model, workers, trace=trace)
         else:
             runHist, sigma = solver_socp_accADMM(var, o2, model, workers, trace=trace)
         recoverOrgVar(var)

@@ -231,3 +231,64 @@ def mexBFdConj1d(q, z, nt, nx, scale, backend=None):
         _c().oracle_BFdConj1d(q.ctypes.data, z.ctypes.data, nt, nx, float(scale))
     else:
         _np_BFdConj(q, _embed1d(z, L), nt, nx, 1, float(scale))
+
+
+# ------------------------------------------------------------------------------------------------ mexsGS
+def _np_sGS(phi, rhs, ep, scale, nt, nx, ny, its):
+    """mexsGS.mexa64 (internal name mexRBsGSscaling) restated from the disassembly: `its` symmetric red-black Gauss-Seidel
+    sweeps for  scale*(A'A + ep*I) phi = rhs  on the (ny, nx, nt) node grid, in place.
+
+      mexFunction @0x23a0 : H = (1/(nx-1))^2 / scale ; C = ((nt-1)/(nx-1))^2 ; eH = H * (scale*ep) ;
+                            COE = 1 / ((n_t*C + n_s) + eH)  with n_t in {1,2} time neighbours (2C = C + C) and n_s in
+                            {2,3,4} space neighbours (Inside 2C+4, Face1 C+4, Face2 2C+3, Edge1 C+3, Edge2 2+2C, Corner C+2)
+                            order of the half sweeps: odd ; its x [ even (corners last) ; odd ]      (parity of t+x+y)
+      RBGS_inside @0x1380, RBGS_face @0x1c80 (+ transforms @0x1120/@0x11b0), RBGS_edge @0x17a0 (+ @0x1250/@0x12e0),
+      RBGS_corner @0x1530 : every node of the half sweep's parity becomes
+                            ((S + T) + H*rhs) * COE,   S = left-to-right sum of the existing neighbours in the order
+                            x-1, x+1, y-1, y+1 ;  T = C*(phi[t-1] + phi[t+1])  or  C*phi[the one time neighbour].
+    The binary walks rows with a start that toggles 1 <-> 2 and uses NY-based counts and 2*NX strides on faces and edges, so
+    it is only meaningful for nx == ny, both odd; nodes of one parity have all neighbours in the other, so
+    the order of the updates inside a half sweep does not matter."""
+    assert nx == ny and nx % 2 == 1 and nt % 2 == 1, "mexsGS needs nx == ny and odd node counts"
+    p = phi.reshape(nt, nx, ny)
+    r = rhs.reshape(nt, nx, ny)
+    hx = 1.0 / (nx - 1.0)
+    H = (hx * hx) / scale
+    c1 = (nt - 1.0) / (nx - 1.0)
+    C = c1 * c1
+    eH = H * (scale * ep)
+    t, x, y = np.meshgrid(np.arange(nt), np.arange(nx), np.arange(ny), indexing="ij")
+    par = (t + x + y) & 1
+    nts = (t > 0).astype(int) + (t < nt - 1)
+    nss = (x > 0).astype(int) + (x < nx - 1) + (y > 0) + (y < ny - 1)
+    twoC = C + C
+    coe = 1.0 / ((np.where(nts == 2, twoC, C) + nss.astype(float)) + eH)
+
+    def half(parity):
+        S = np.zeros_like(p)
+        started = np.zeros(p.shape, dtype=bool)
+        for ax, sh in ((1, -1), (1, 1), (2, -1), (2, 1)):
+            nb = np.roll(p, -sh, axis=ax)
+            idx = x if ax == 1 else y
+            n = nx if ax == 1 else ny
+            ok = (idx + sh >= 0) & (idx + sh <= n - 1)
+            S = np.where(ok, np.where(started, S + nb, nb), S)
+            started |= ok
+        tm, tp = np.roll(p, 1, axis=0), np.roll(p, -1, axis=0)
+        T = np.where(nts == 2, (tm + tp) * C, np.where(t == 0, tp, tm) * C)
+        new = ((S + T) + r * H) * coe
+        m = par == parity
+        p[m] = new[m]
+    half(1)
+    for _ in range(int(its)):
+        half(0)
+        half(1)
+
+
+def mexsGS(phi, rhs, ep, scale, nt, nx, ny, its, backend=None):
+    """mexsGS(phi, rhs, ep, scale, nt, nx, ny, its): in place into phi   (solver_socp_sGSinPALM.m:205)"""
+    b = backend or default_backend()
+    if b == "ref":
+        refmex.mexsGS(phi, rhs, float(ep), float(scale), float(nt), float(nx), float(ny), float(its))
+    else:
+        _np_sGS(phi, rhs, float(ep), float(scale), int(nt), int(nx), int(ny), int(its))

@@ -167,3 +167,22 @@ def test_poisson_t_direction_thomas_equals_transform(gpu, nt, nx, ny, monkeypatc
     for got in (thomas, viadct):
         assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max()
     assert np.abs(thomas - viadct).max() > 0.0 or nt < 3   # they really are two different code paths
+
+
+@pytest.mark.parametrize("nt,n,its,ep,scale", [(5, 5, 1, 0.0, 1.0), (9, 7, 1, 0.0, 0.37), (3, 9, 2, 0.5, 2.5), (17, 33, 1, 0.0, 1.3e-2),
+                                                (33, 17, 3, 1e-3, 0.7), (3, 3, 1, 0.0, 1.0), (65, 129, 1, 0.0, 2.1e-3)])
+def test_mexsGS_bit_exact(gpu, nt, n, its, ep, scale):
+    """red-black symmetric Gauss-Seidel sweeps (mexsGS.mexa64): one thread per node of the half sweep's parity, bit-identical to
+    the reference binary (through the oracle, whose numpy restatement is itself pinned to the binary)"""
+    from dotsocp_b200 import ops
+    from oracle import kernels as K
+    rng = np.random.default_rng(nt * 1000 + n)
+    phi = rng.standard_normal(nt * n * n)
+    rhs = rng.standard_normal(nt * n * n)
+    want, got = phi.copy(), phi.copy()
+    K.mexsGS(want, rhs.copy(), ep, scale, nt, n, n, its)
+    ops.mexsGS(got, rhs, ep, scale, nt, n, n, its)
+    assert np.array_equal(got, want)
+    from dotsocp_b200 import _lib
+    with pytest.raises(_lib.DotsocpError):
+        ops.mexsGS(np.zeros(5 * 5 * 7), np.zeros(5 * 5 * 7), 0.0, 1.0, 5, 5, 7, 1)      # nx != ny: the binary does not handle it

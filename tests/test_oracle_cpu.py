@@ -214,3 +214,41 @@ def test_oracle_reproduces_the_survey_probe_of_the_1d_demo():
     assert [int(v) for v in out.level_iters] == gold["level_iters"]
     assert np.abs(ML.kkt - np.array(gold["kkt"])).max() < 1e-12
     assert abs(rh.priVal[-1] - gold["priVal"]) <= 1e-12 * abs(gold["priVal"])
+
+
+def test_sgs_numpy_restatement_is_bit_identical_to_the_reference_binary():
+    """mexsGS.mexa64 has no source: its semantics come from the disassembly (oracle/kernels.py:_np_sGS) and are pinned here"""
+    from oracle import kernels as K, refmex
+    if not refmex.available():
+        pytest.skip("reference binaries not present (oracle/_ref)")
+    rng = np.random.default_rng(11)
+    for nt, n, its, ep, scale in [(5, 5, 1, 0.0, 1.0), (9, 7, 2, 0.25, 0.37), (17, 17, 1, 0.0, 1.3e-2), (3, 3, 1, 0.0, 1.0), (7, 13, 3, 1e-3, 4.0)]:
+        phi, rhs = rng.standard_normal(nt * n * n), rng.standard_normal(nt * n * n)
+        a, b = phi.copy(), phi.copy()
+        K.mexsGS(a, rhs.copy(), ep, scale, nt, n, n, its, backend="ref")
+        K.mexsGS(b, rhs.copy(), ep, scale, nt, n, n, its, backend="numpy")
+        assert np.array_equal(a, b), (nt, n, its)
+
+
+def test_sgs_sweeps_converge_to_the_poisson_solution():
+    """400 symmetric sweeps solve scale * A'A phi = rhs for zero-mean rhs (the fixed point of the smoother is the DCT solution)"""
+    from oracle import kernels as K
+    from oracle import dotsocp_oracle as O
+    nt, n = 5, 9
+    rng = np.random.default_rng(2)
+    rhs = rng.standard_normal(nt * n * n)
+    rhs -= rhs.mean()
+    A = O.gene_grad2d(nt, n, n)
+    phi = np.zeros(nt * n * n)
+    K.mexsGS(phi, rhs, 0.0, 1.0, nt, n, n, 400)
+    assert np.abs(A.T @ (A @ phi) - rhs).max() < 1e-9
+
+
+def test_sgs_inpalm_oracle_reaches_the_inpalm_solution():
+    from oracle import dotsocp_oracle as O
+    rho0, rho1 = O.get_example2d("example1", 17, 17)
+    out_s, _, ML_s, rh_s = O.solver_dotsocp2d(rho0, rho1, 9, 1, {"tol": 1e-4}, "sGS-inPALM")
+    out_i, _, ML_i, rh_i = O.solver_dotsocp2d(rho0, rho1, 9, 1, {"tol": 1e-4}, "inPALM")
+    assert np.max(ML_s.kkt[-1][[0, 2, 5, 6]]) < 1e-4
+    assert abs(rh_s.priVal[-1] - rh_i.priVal[-1]) < 1e-3 * abs(rh_i.priVal[-1])     # both stop at tol 1e-4
+    assert out_s.massOK

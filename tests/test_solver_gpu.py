@@ -490,3 +490,17 @@ def test_multilevel_solve_on_time_slabs_is_bit_identical_to_one_slab(gpu, case):
             assert np.array_equal(getattr(got[0], name), getattr(ref[0], name)), (name, k)
         assert np.array_equal(got[0].sumRho, ref[0].sumRho) and got[0].w2 == ref[0].w2
         assert got[0].sigma == ref[0].sigma
+
+
+@pytest.mark.parametrize("n,nt,levelN", [(17, 9, 1), (33, 17, 2)])
+def test_dot2d_sgs_inpalm_parity(gpu, n, nt, levelN):
+    """sGS-inPALM (solver_socp_sGSinPALM.m): the phi-step is one symmetric red-black Gauss-Seidel sweep instead of the DCT solve,
+    with its own check schedule and sigma voting; coarse levels run inPALM (solver_dotsocp2d.m:210-216).  Resident and host
+    transitions, and emulated time slabs (the sGS phi-step exchanges ghost planes only)."""
+    import dotsocp_b200 as dp
+    rho0, rho1 = O.get_example2d("example1", n, n)
+    opts = {"tol": 1e-4}
+    out_o, _, ML_o, rh_o = O.solver_dotsocp2d(rho0, rho1, nt, levelN, opts, "sGS-inPALM", workers=4)
+    for extra in ({}, {"resident": False}, {"slabs": 2}):
+        out_g, _, ML_g, rh_g = dp.solver_dotsocp2d(rho0, rho1, nt, levelN, dict(opts, **extra), "sGS-inPALM")
+        _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o)
