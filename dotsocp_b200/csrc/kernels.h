@@ -195,6 +195,14 @@ bool poisson_can_pack(const PoissonPlan* p);   // the x passes can read/write th
 // push_tab / tcut (device tables, see Slab::d_bwd): store the solution in the buffers of the owners of the time levels
 int  poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, cudaStream_t st, double* launches,
                      double* const* push_tab = nullptr, const int* tcut = nullptr, int world = 1);
+// pipelined slab Thomas: the t-solve with the time axis cut into slabs, one carry plane per slab boundary and direction
+// instead of the two transposes; bit-identical to the single-slab solve (poisson.cu)
+bool poisson_slab_thomas_ok(const PoissonPlan* p);
+int  poisson_thomas_slab(PoissonPlan* p, double* a, int t0, int t1, i64 m0, i64 m1, double D2, bool backward, const double* carry_in,
+                         double* carry_out, cudaStream_t st, double* launches);
+void poisson_line0_gather(PoissonPlan* p, const double* a, double* line, int t0, int t1, cudaStream_t st);
+void poisson_line0_solve(PoissonPlan* p, double* line, double D2, cudaStream_t st);
+void poisson_line0_scatter(PoissonPlan* p, double* a, const double* line, int t0, int t1, cudaStream_t st);
 // in-place orthonormal DCT-II (or inverse) along all axes
 int  poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches);
 

@@ -906,9 +906,9 @@ __global__ void __launch_bounds__(256) k_thomas(int nt, i64 lines, i64 stride, i
 #pragma unroll
         for (int u = 0; u < 4; u++) { r[u] = a[(i64)(t + u) * stride + l]; g[u] = gt(t + u); }
 #pragma unroll
-        for (int u = 0; u < 4; u++) { d = (r[u] * inv_scale + d) * g[u]; a[(i64)(t + u) * stride + l] = d; }
+        for (int u = 0; u < 4; u++) { d = __dmul_rn(__fma_rn(r[u], inv_scale, d), g[u]); a[(i64)(t + u) * stride + l] = d; }
     }
-    for (; t < nt; t++) { d = (a[(i64)t * stride + l] * inv_scale + d) * gt(t); a[(i64)t * stride + l] = d; }
+    for (; t < nt; t++) { d = __dmul_rn(__fma_rn(a[(i64)t * stride + l], inv_scale, d), gt(t)); a[(i64)t * stride + l] = d; }
     // back substitution
     double x = d;
     if (PUSH) put(nt - 1, x);
@@ -918,9 +918,120 @@ __global__ void __launch_bounds__(256) k_thomas(int nt, i64 lines, i64 stride, i
 #pragma unroll
         for (int u = 0; u < 4; u++) { dd[u] = a[(i64)(t - u) * stride + l]; g[u] = gt(t - u); }
 #pragma unroll
-        for (int u = 0; u < 4; u++) { x = dd[u] + g[u] * x; put(t - u, x); }
+        for (int u = 0; u < 4; u++) { x = __fma_rn(g[u], x, dd[u]); put(t - u, x); }
     }
-    for (; t >= 0; t--) { x = a[(i64)t * stride + l] + gt(t) * x; put(t, x); }
+    for (; t >= 0; t--) { x = __fma_rn(gt(t), x, a[(i64)t * stride + l]); put(t, x); }
+}
+
+// ---- the same solve with the time axis cut into slabs ("pipelined Thomas") -----------------------------------------------
+// A slab holds levels [t0, t1) of ALL modes in the natural layout a[t*P + mode] (the output of the (y,x) transforms, in place).
+// The forward elimination needs d of level t0-1 from the slab below, the back substitution x of level t1 from the slab above:
+// one plane of P doubles per slab boundary and direction instead of two all-to-all transposes of the whole array.  Every mode
+// runs through exactly the operations of k_thomas in the same order, so the result is bit-identical to the single-slab solve.
+// The sweeps are sequential across slabs; cutting the modes into chunks (solver.cu) lets slab r work on chunk c while slab
+// r+1 works on chunk c-1.  Pivot table: rows t0..t1-1 only (gtab[(t-t0)*P + mode]); t_fix as for k_thomas.
+__global__ void __launch_bounds__(256) k_thomas_table_slab(int nt, int ny, i64 P, int t0, int t1, const double* __restrict__ lam_x,
+                                                           const double* __restrict__ lam_y, double* __restrict__ gtab,
+                                                           int* __restrict__ t_fix)
+{
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int kx = (int)(p / ny), ky = (int)(p - (i64)kx * ny);
+    const double ct = (double)(nt - 1) * (double)(nt - 1);
+    const double nu = (lam_y[ky] + lam_x[kx]) / ct;
+    double g = 1.0 / (1.0 + nu);
+    if (t0 == 0) gtab[p] = g;
+    int fix = nt;
+    for (int t = 1; t < nt; t++) {
+        const double diag = (t == nt - 1 ? 1.0 : 2.0) + nu;
+        const double gn = 1.0 / (diag - g);
+        if (fix == nt && t < nt - 1 && gn == g) fix = t;
+        g = gn;
+        if (t >= t0 && t < t1) gtab[(i64)(t - t0) * P + p] = g;
+    }
+    t_fix[p] = fix;
+}
+
+// value of g_t for a mode: table below t_fix and on the last level, else the fixed point (gs = g at level tf, which a slab may
+// not hold: it is recomputed by iterating the recurrence to the fixed point -- the same expression, hence the same bits)
+struct SlabG {
+    const double* tab;
+    i64 P, p;
+    int t0, nt, tf;
+    double gs;
+    __device__ __forceinline__ double at(int t) const { return (t < tf || t == nt - 1) ? tab[(i64)(t - t0) * P + p] : gs; }
+};
+__device__ __forceinline__ double thomas_fixed_point(int nt, int tf, double nu)
+{
+    double g = 1.0 / (1.0 + nu);
+    for (int t = 1; t <= tf && t < nt; t++) g = 1.0 / (2.0 + nu - g);
+    return g;
+}
+
+__global__ void __launch_bounds__(256) k_thomas_fwd_slab(int nt, int ny, i64 P, i64 m0, i64 m1, int t0, int t1, double inv_scale,
+                                                         const double* __restrict__ lam_x, const double* __restrict__ lam_y,
+                                                         const double* __restrict__ gtab, const int* __restrict__ t_fix,
+                                                         double* __restrict__ a, const double* __restrict__ carry_in,
+                                                         double* __restrict__ carry_out)
+{
+    const i64 p = m0 + blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (p >= m1 || p == 0) return;        // mode (0,0) is solved separately (k_tline0)
+    const int kx = (int)(p / ny), ky = (int)(p - (i64)kx * ny);
+    const double ct = (double)(nt - 1) * (double)(nt - 1);
+    const double nu = (lam_y[ky] + lam_x[kx]) / ct;
+    SlabG G{gtab, P, p, t0, nt, t_fix[p], 0.0};
+    if (G.tf < nt) G.gs = thomas_fixed_point(nt, G.tf, nu);
+    double d = t0 > 0 ? carry_in[p] : 0.0;
+    int t = t0;
+    for (; t + 4 <= t1; t += 4) {
+        double r[4], g[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { r[u] = a[(i64)(t + u) * P + p]; g[u] = G.at(t + u); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { d = __dmul_rn(__fma_rn(r[u], inv_scale, d), g[u]); a[(i64)(t + u) * P + p] = d; }
+    }
+    for (; t < t1; t++) { d = __dmul_rn(__fma_rn(a[(i64)t * P + p], inv_scale, d), G.at(t)); a[(i64)t * P + p] = d; }
+    if (t1 < nt) carry_out[p] = d;
+}
+
+__global__ void __launch_bounds__(256) k_thomas_bwd_slab(int nt, int ny, i64 P, i64 m0, i64 m1, int t0, int t1,
+                                                         const double* __restrict__ lam_x, const double* __restrict__ lam_y,
+                                                         const double* __restrict__ gtab, const int* __restrict__ t_fix,
+                                                         double* __restrict__ a, const double* __restrict__ carry_in,
+                                                         double* __restrict__ carry_out)
+{
+    const i64 p = m0 + blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (p >= m1 || p == 0) return;
+    const int kx = (int)(p / ny), ky = (int)(p - (i64)kx * ny);
+    const double ct = (double)(nt - 1) * (double)(nt - 1);
+    const double nu = (lam_y[ky] + lam_x[kx]) / ct;
+    SlabG G{gtab, P, p, t0, nt, t_fix[p], 0.0};
+    if (G.tf < nt) G.gs = thomas_fixed_point(nt, G.tf, nu);
+    double x;
+    int t;
+    if (t1 == nt) { x = a[(i64)(nt - 1) * P + p]; t = nt - 2; }     // last level: x = d
+    else { x = carry_in[p]; t = t1 - 1; }
+    for (; t - 3 >= t0; t -= 4) {
+        double dd[4], g[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { dd[u] = a[(i64)(t - u) * P + p]; g[u] = G.at(t - u); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { x = __fma_rn(g[u], x, dd[u]); a[(i64)(t - u) * P + p] = x; }
+    }
+    for (; t >= t0; t--) { x = __fma_rn(G.at(t), x, a[(i64)t * P + p]); a[(i64)t * P + p] = x; }
+    if (t0 > 0) carry_out[p] = x;       // x of my first level, for the slab below
+}
+
+// the singular mode: its nt values live one per level on the owning slabs; line[t] <-> a[t*P]
+__global__ void k_line0_gather(int t0, int t1, i64 P, const double* __restrict__ a, double* __restrict__ line)
+{
+    const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < t1) line[t] = a[(i64)t * P];
+}
+__global__ void k_line0_scatter(int t0, int t1, i64 P, double* __restrict__ a, const double* __restrict__ line)
+{
+    const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < t1) a[(i64)t * P] = line[t];
 }
 
 // mode (0,0): phi = IDCT_t( DCT_t(r) ./ (D2 * lam_t) ), lam_t[0] := 1, dense nt x nt transform by one CTA
@@ -1095,6 +1206,59 @@ int poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, c
 {
     // push_tab != NULL needs the Thomas solve (the transform-based t pass works in place only)
     return t_solve(p, buf, chunk, p0, D2, st, launches, p->use_thomas && p->g.nt >= 3 ? push_tab : nullptr, tcut, world);
+}
+
+// ---- pipelined slab Thomas (see the kernels): pieces called by solver.cu ----------------------------------------------------
+bool poisson_slab_thomas_ok(const PoissonPlan* p) { return p->use_thomas && p->g.nt >= 3; }
+static PoissonPlan::GTab* slab_table(PoissonPlan* p, int t0, int t1, cudaStream_t st, double* launches)
+{
+    const Geo& g = p->g;
+    for (auto& e : p->gtabs)
+        if (e.p0 == -(i64)(t0 + 1) && e.lines == (i64)(t1 - t0)) return &e;     // slab tables are keyed by (-(t0+1), nlev)
+    double* gtab = nullptr;
+    int* t_fix = nullptr;
+    if (cudaMalloc(&gtab, (size_t)(t1 - t0) * g.P * sizeof(double)) != cudaSuccess || cudaMalloc(&t_fix, (size_t)g.P * sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(gtab);
+        return nullptr;
+    }
+    k_thomas_table_slab<<<(unsigned)((g.P + 255) / 256), 256, 0, st>>>(g.nt, g.ny, g.P, t0, t1, p->lam_x, p->lam_y, gtab, t_fix);
+    if (launches) *launches += 1;
+    if (!p->cmat_t) p->cmat_t = dense_dct_matrix(g.nt);
+    p->gtabs.push_back({-(i64)(t0 + 1), (i64)(t1 - t0), gtab, t_fix});
+    return &p->gtabs.back();
+}
+// forward elimination / back substitution of modes [m0, m1) on levels [t0, t1) of the natural-layout array `a`
+int poisson_thomas_slab(PoissonPlan* p, double* a, int t0, int t1, i64 m0, i64 m1, double D2, bool backward, const double* carry_in,
+                        double* carry_out, cudaStream_t st, double* launches)
+{
+    const Geo& g = p->g;
+    if (m1 <= m0) return 0;
+    PoissonPlan::GTab* tb = slab_table(p, t0, t1, st, launches);
+    if (!tb) return dsocp_set_err(-4, "pivot table of the slab Thomas solve: out of device memory");
+    const double ct = (double)(g.nt - 1) * (double)(g.nt - 1);
+    const unsigned nb = (unsigned)((m1 - m0 + 255) / 256);
+    if (!backward)
+        k_thomas_fwd_slab<<<nb, 256, 0, st>>>(g.nt, g.ny, g.P, m0, m1, t0, t1, 1.0 / (D2 * ct), p->lam_x, p->lam_y, tb->tab, tb->t_fix, a,
+                                              carry_in, carry_out);
+    else
+        k_thomas_bwd_slab<<<nb, 256, 0, st>>>(g.nt, g.ny, g.P, m0, m1, t0, t1, p->lam_x, p->lam_y, tb->tab, tb->t_fix, a, carry_in, carry_out);
+    if (launches) *launches += 1;
+    return 0;
+}
+// the singular mode (kx = ky = 0): gather its values of levels [t0, t1) into line[nt] / solve the complete line / scatter back
+void poisson_line0_gather(PoissonPlan* p, const double* a, double* line, int t0, int t1, cudaStream_t st)
+{
+    if (t1 > t0) k_line0_gather<<<(unsigned)((t1 - t0 + 127) / 128), 128, 0, st>>>(t0, t1, p->g.P, a, line);
+}
+void poisson_line0_solve(PoissonPlan* p, double* line, double D2, cudaStream_t st)
+{
+    if (!p->cmat_t) p->cmat_t = dense_dct_matrix(p->g.nt);
+    k_tline0<<<1, 1024, (size_t)2 * p->g.nt * sizeof(double), st>>>(p->g.nt, 1, D2, p->lam_t, p->cmat_t, line);
+}
+void poisson_line0_scatter(PoissonPlan* p, double* a, const double* line, int t0, int t1, cudaStream_t st)
+{
+    if (t1 > t0) k_line0_scatter<<<(unsigned)((t1 - t0 + 127) / 128), 128, 0, st>>>(t0, t1, p->g.P, a, line);
 }
 
 int poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches)

@@ -117,7 +117,8 @@ struct Slab {
            *weight = nullptr, *beta[2] = {nullptr, nullptr};
     double *c0 = nullptr, *c1 = nullptr, *partial = nullptr;
     double *partial_q = nullptr, *partial_m = nullptr;   // fused KKT partials (allocated at the first fused check)
-    double *tsend = nullptr, *trecv = nullptr;
+    double *tsend = nullptr, *trecv = nullptr;   // transposed t-solve (DOTSOCP_TSOLVE=transpose)
+    double* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // pipelined t-solve: forward in / out, backward in / out (P doubles each)
     std::vector<double*> peer_tsend, peer_trecv;   // CUDA-IPC mappings of the other ranks' transpose buffers (NCCL mode)
     // direct exchange (kernels store into the destination slab's buffer): device tables of `world` pointers
     //   d_fwd[b] = row tn0 of the t-solve buffer (trecv) of slab b   -- written by this slab's forward x pass
@@ -134,6 +135,7 @@ struct Slab {
         for (double* p : peer_trecv) if (p) cudaIpcCloseMemHandle(p);
         cudaFree(c0); cudaFree(c1); cudaFree(partial); cudaFree(partial_q); cudaFree(partial_m); cudaFree(tsend); cudaFree(trecv);
         cudaFree(tmpq); cudaFree(d_fwd); cudaFree(d_bwd);
+        for (double* p : carry) cudaFree(p);
         for (int i = 0; i < 5; i++) { cudaFree(old_[i]); cudaFree(anc_[i]); }
     }
 };
@@ -158,6 +160,9 @@ struct dotsocp_ctx {
     }
     // DOTSOCP_TRACE=1: device time of the phases of the distributed Poisson solve (printed by rank/slab 0 at destroy)
     bool trace = false;
+    bool tpipe = false;         // t-solve of the slabs by the pipelined Thomas sweeps (default) instead of transposes
+    int tchunks = 1;            // ... with the modes cut into this many chunks so that consecutive slabs overlap
+    double* d_line0 = nullptr;  // ... the singular mode's nt values
     bool ipc = false;           // transposes by peer-to-peer copies (copy engines over NVLink) instead of NCCL send/recv
     bool direct = false;        // ... or by the transform / t-solve kernels storing straight into the destination slab's buffer
     int* d_tcut = nullptr;      // first node level of every slab (world + 1 entries), device copy
@@ -228,6 +233,7 @@ extern "C" void dotsocp_destroy(dotsocp_ctx* c)
     cudaFree(c->barrier_buf);
     cudaFree(c->d_tcut);
     cudaFree(c->d_lvl);
+    cudaFree(c->d_line0);
     cudaFree(c->d_tot);
     if (c->h_tot) cudaFreeHost(c->h_tot);
     if (c->h_elapsed) cudaFreeHost(c->h_elapsed);
@@ -294,7 +300,9 @@ static int make_slab(dotsocp_ctx* c, int id)
     CU(cudaMemsetAsync(s->c0, 0, g.P * sizeof(double), c->st));
     CU(cudaMemsetAsync(s->c1, 0, g.P * sizeof(double), c->st));
     CU(cudaMalloc(&s->partial, partial_doubles(g, tr.tn1 - tr.tn0) * sizeof(double)));
-    if (c->world > 1) {
+    if (c->world > 1 && c->tpipe) {
+        for (double*& p : s->carry) CU(cudaMalloc(&p, (size_t)g.P * sizeof(double)));
+    } else if (c->world > 1) {
         CU(cudaMalloc(&s->tsend, (size_t)(tr.tn1 - tr.tn0) * g.P * sizeof(double)));
         CU(cudaMalloc(&s->trecv, (size_t)g.nt * (s->p1 - s->p0) * sizeof(double)));
     }
@@ -374,6 +382,14 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
         const i64 C = (g.P + world - 1) / world;
         for (int r = 0; r <= world; r++) c->pcut.push_back(std::min(g.P, (i64)r * C));
     }
+    {   // t-solve across slabs: pipelined Thomas sweeps (one carry plane per boundary and direction) unless DOTSOCP_TSOLVE asks
+        // for the transposes ("transpose") or for the transform-based t pass ("dct", which needs whole lines on one slab)
+        const char* ts = getenv("DOTSOCP_TSOLVE");
+        c->tpipe = world > 1 && nt >= 3 && !(ts && (strcmp(ts, "transpose") == 0 || strcmp(ts, "dct") == 0));
+        const char* tc = getenv("DOTSOCP_TCHUNKS");
+        const int want = tc ? atoi(tc) : 0;
+        c->tchunks = want > 0 ? want : (nccl_id ? 8 : 1);
+    }
     // the communication stream gets the highest priority so that the NCCL copy kernels are scheduled as soon as SM slots
     // free up instead of queueing behind the (much larger) compute grids they are meant to overlap with
     int prio_lo = 0, prio_hi = 0;
@@ -411,7 +427,7 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
         dotsocp_destroy(c);
         return rc;
     }
-    if (c->comm) {
+    if (c->comm && !c->tpipe) {
         // exchange CUDA-IPC handles of the transpose buffers; any failure just keeps the NCCL send/recv path
         const char* noipc = getenv("DOTSOCP_NO_IPC");
         Slab* s = c->slabs[0];
@@ -471,7 +487,7 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
         }
         cudaGetLastError();
     }
-    if (world > 1 && (c->ipc || !c->comm)) {
+    if (world > 1 && !c->tpipe && (c->ipc || !c->comm)) {
         // DOTSOCP_XCHG=direct: the kernels store straight into the destination slab's buffers instead of the copy-engine
         // pushes.  Off by default: on 8 B200s the t-solve of every GPU then writes to the SAME peer at the same time (the owner
         // of the current time level), and the 32-byte runs of the x pass cost more than the copies they replace
@@ -510,6 +526,7 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMalloc(&c->d_lvl, (size_t)nt * KSL * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tot, KSL * sizeof(double));
+    if (e == cudaSuccess && c->tpipe) e = cudaMalloc(&c->d_line0, (size_t)nt * sizeof(double));
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_tot, KSL * sizeof(double));
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_elapsed, sizeof(double));
     if (e != cudaSuccess) {
@@ -601,6 +618,50 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
         return poisson_solve(c->pp, s->rhs, s->phi, D2, c->st, &c->launches);
     }
     const NcclApi& n = nccl_api();
+    if (c->tpipe) {
+        // Pipelined Thomas: (y,x) transforms of the own levels in place, forward elimination slab 0 -> W-1 and back substitution
+        // W-1 -> 0 with one carry plane per boundary, (x,y) inverse transforms.  The sweeps are sequential over the slabs, so the
+        // modes are cut into chunks: slab r works on chunk k while slab r+1 works on chunk k-1.  No transposes, no packed
+        // buffers; bit-identical to the single-slab solve.
+        int rc = 0;
+        cudaStream_t st = c->st;
+        for (Slab* s : c->slabs)
+            if ((rc = poisson_xy(c->pp, s->rhs, s->phi, s->tr.tn0, s->tr.tn1 - s->tr.tn0, false, st, &c->launches))) return rc;
+        // the singular mode (zero eigenvalue := 1, initialize_FFTkernel.m:15) needs its whole line: nt doubles, every rank
+        // contributes its levels (all-reduce of disjoint rows) and solves the line redundantly
+        CU(cudaMemsetAsync(c->d_line0, 0, (size_t)g.nt * sizeof(double), st));
+        for (Slab* s : c->slabs) poisson_line0_gather(c->pp, s->phi, c->d_line0, s->tr.tn0, s->tr.tn1, st);
+        if (c->comm) NC(n.AllReduce(c->d_line0, c->d_line0, (size_t)g.nt, NCCL_FLOAT64, NCCL_SUM, c->comm, st));
+        poisson_line0_solve(c->pp, c->d_line0, D2, st);
+        for (Slab* s : c->slabs) poisson_line0_scatter(c->pp, s->phi, c->d_line0, s->tr.tn0, s->tr.tn1, st);
+        c->launches += 1 + 2.0 * c->slabs.size();
+        const int K = (int)std::max<i64>(1, std::min<i64>(c->tchunks, g.P / 1024 + 1));
+        for (int dir = 0; dir < 2; dir++) {            // 0: forward elimination (ascending slabs), 1: back substitution (descending)
+            const bool bwd = dir == 1;
+            for (int k = 0; k < K; k++) {
+                const i64 m0 = g.P * k / K, m1 = g.P * (k + 1) / K;
+                const int ns = (int)c->slabs.size();
+                for (int i = 0; i < ns; i++) {
+                    Slab* s = c->slabs[bwd ? ns - 1 - i : i];
+                    const int from = bwd ? s->id + 1 : s->id - 1, to = bwd ? s->id - 1 : s->id + 1;
+                    const bool has_in = from >= 0 && from < c->world, has_out = to >= 0 && to < c->world;
+                    double* cin = s->carry[bwd ? 2 : 0];
+                    double* cout = s->carry[bwd ? 3 : 1];
+                    const double* in_ptr = nullptr;
+                    if (has_in) {
+                        Slab* o = c->local(from);
+                        if (o) in_ptr = o->carry[bwd ? 3 : 1];          // same process: read the neighbour's carry-out directly
+                        else { NC(n.Recv(cin + m0, (size_t)(m1 - m0), NCCL_FLOAT64, from, c->comm, st)); in_ptr = cin; }
+                    }
+                    if ((rc = poisson_thomas_slab(c->pp, s->phi, s->tr.tn0, s->tr.tn1, m0, m1, D2, bwd, in_ptr, cout, st, &c->launches))) return rc;
+                    if (has_out && !c->local(to)) NC(n.Send(cout + m0, (size_t)(m1 - m0), NCCL_FLOAT64, to, c->comm, st));
+                }
+            }
+        }
+        for (Slab* s : c->slabs)
+            if ((rc = poisson_xy(c->pp, s->phi, s->phi, s->tr.tn0, s->tr.tn1 - s->tr.tn0, true, st, &c->launches))) return rc;
+        return ghosts(c, GH_PHI_UP, 0, 0);
+    }
     const bool fused_pack = poisson_can_pack(c->pp);
     // rows [r0, r1) (local level indices of the slab that owns the rows) of the transposed exchange, both directions
     auto exchange_rows = [&](bool forward, int grp, int ngrp, cudaStream_t st) -> int {

@@ -176,13 +176,21 @@ def test_golden_solver_histories(gpu):
         assert abs(driver.w2_cost(out, 1 if name.startswith("dot1d") else 2) - g["w2"]) <= 1e-6 * abs(g["w2"]), name
 
 
+@pytest.mark.parametrize("tsolve", ["pipelined", "transpose"])
 @pytest.mark.parametrize("world", [2, 3, 4])
 @pytest.mark.parametrize("variant", ["dot2d", "wdot2d"])
-def test_time_slab_partition_emulated_on_one_gpu(gpu, world, variant):
+def test_time_slab_partition_emulated_on_one_gpu(gpu, world, variant, tsolve, monkeypatch):
     """The multi-GPU code path (time slabs, ghost planes, transposed t-pass, reduced KKT sums) with all slabs on ONE
     device (device-to-device copies instead of NCCL): must reproduce the single-slab solve."""
     import dotsocp_b200 as dp
     from dotsocp_b200 import driver, solver
+    # t-direction of the Poisson solve across slabs: pipelined Thomas sweeps with one carry plane per boundary (default), with
+    # the modes cut into 3 chunks here, or the two all-to-all transposes (DOTSOCP_TSOLVE=transpose); both read when the session
+    # is created
+    if tsolve == "transpose":
+        monkeypatch.setenv("DOTSOCP_TSOLVE", "transpose")
+    else:
+        monkeypatch.setenv("DOTSOCP_TCHUNKS", "3")
     n, nt = 33, 17
     rho0, rho1 = O.get_example2d("example2", n, n)
     weight = O.gene_weight_circle(nt, n, n) if variant == "wdot2d" else None
@@ -219,6 +227,7 @@ def test_time_slabs_with_fused_transpose_pack(gpu, world, xchg, monkeypatch):
     the session is created)."""
     import dotsocp_b200 as dp
     monkeypatch.setenv("DOTSOCP_XCHG", xchg)
+    monkeypatch.setenv("DOTSOCP_TSOLVE", "transpose")      # the default t-solve of the slabs is the pipelined Thomas sweep
     from dotsocp_b200 import driver, solver
     nt, nx, ny = (33 if world == 2 else 9), 129, 12    # 16 levels per slab: all 8 pipeline groups of the transposes are used
     rng = np.random.default_rng(5)
