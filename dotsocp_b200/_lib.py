@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DOTSOCP_LIB") or os.path.join(_HERE, "libdotsocp.so")   # override only for A/B experiments
 
 VARIANT = {"dot2d": 0, "wdot2d": 1, "dot1d": 2}
-METHOD = {"inPALM": 0, "ALG2": 0, "PALM": 1, "acc-ADMM": 2, "sGS-inPALM": 3}
+METHOD = {"inPALM": 0, "ALG2": 0, "PALM": 1, "acc-ADMM": 2, "sGS-inPALM": 3, "acc-sGS-ADMM": 4}
 NTIMES = 8
 
 

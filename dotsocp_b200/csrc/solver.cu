@@ -1378,7 +1378,10 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     // sGS-inPALM (solver_socp_sGSinPALM.m) is the inPALM iteration with the phi-step replaced by one symmetric Gauss-Seidel
     // sweep, its own check schedule and its own sigma voting: it shares the fused kernels and everything marked `inpalm`
     const bool sgs = method == DOTSOCP_METHOD_SGSINPALM;
-    const bool inpalm = method == DOTSOCP_METHOD_INPALM || sgs, palm = method == DOTSOCP_METHOD_PALM, acc = method == DOTSOCP_METHOD_ACCADMM;
+    // acc-sGS-ADMM (solver_socp_accsGSADMM.m) is acc-ADMM with the same replacement of the phi-step and the same voting
+    const bool accsgs = method == DOTSOCP_METHOD_ACCSGSADMM, vote = sgs || accsgs;
+    const bool inpalm = method == DOTSOCP_METHOD_INPALM || sgs, palm = method == DOTSOCP_METHOD_PALM;
+    const bool acc = method == DOTSOCP_METHOD_ACCADMM || accsgs;
     const bool weighted = c->weighted;
     const bool checkPD = o.checkPrimDualFeas < 0 ? !weighted : (o.checkPrimDualFeas != 0);   // :20-24 / wsocp :25-29
     // NaN = opts.time_limit absent (default 3600 s, :26-30); a non-positive value is a budget that is already spent (the
@@ -1412,8 +1415,8 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     if (palm && (weighted || c->one_d)) return set_err(DOTSOCP_EINVAL, "PALM exists only for socp/dot2d");
     if (acc && c->one_d) return set_err(DOTSOCP_EINVAL, "acc-ADMM does not exist for socp/dot1d");
     if (!inpalm && c->world > 1) return set_err(DOTSOCP_EINVAL, "PALM / acc-ADMM run on a single slab only (world == 1)");
-    if (sgs && (c->variant != DOTSOCP_VARIANT_DOT2D || !sgs_supported(g)))
-        return set_err(DOTSOCP_EINVAL, "sGS-inPALM exists only for socp/dot2d, and mexsGS only handles nx == ny with odd node counts");
+    if (vote && (c->variant != DOTSOCP_VARIANT_DOT2D || !sgs_supported(g)))
+        return set_err(DOTSOCP_EINVAL, "the sGS loops exist only for socp/dot2d, and mexsGS only handles nx == ny with odd node counts");
     int kacc = 0;
     // sGS-inPALM state (:76-80, :109-112)
     const int sgs_hist = 19, sgs_victory = 12;
@@ -1421,7 +1424,8 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     const double sigma_adjust_it_gap = fmax(1.0, pow((double)g.nt * g.nx * g.ny, 1.0 / 3.0) / 33.0);
     bool stablePhase = false, sgs_superior_yes = false;
     std::vector<double> FeasRatio;
-    if (sgs) FeasRatio.assign((size_t)maxit + 1, INFINITY);   // 1-based like the reference
+    if (vote) FeasRatio.assign((size_t)maxit + 1, INFINITY);   // 1-based like the reference
+    const int stable_after = accsgs ? 1500 : 2500;            // accsGSADMM :379 / sGSinPALM :337
     double KRs[5] = {0, 0, 0, 0, 0}, norm_Aphi_s = 0, norm_q_s = 0;   // values of the last check (the :385-402 branch re-uses them)
 
     Loop L;
@@ -1455,7 +1459,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
     L.scale(A_ALPHA, 1.0, sigma);
     L.scale(A_BETA, 1.0, sigma);
     L.scale(A_C, 1.0, sigma);
-    if (sgs) {   // phi = phi - integralL2(phi, h)   (solver_socp_sGSinPALM.m:142)
+    if (vote) {   // phi = phi - integralL2(phi, h)   (solver_socp_sGSinPALM.m:142, solver_socp_accsGSADMM.m:165)
         int r_;
         if ((r_ = begin_sums(c))) return r_;
         for (Slab* s : c->slabs) { launch_sum_nodes(g, s->phi, s->partial, c->d_lvl, 0, s->tr.tn0, s->tr.tn1, c->st); c->launches += 2; }
@@ -1556,6 +1560,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
 
         // ---------------------------------------------------------------- iteration
         cudaEvent_t e_last;
+        bool sums_begun = false;   // the level table already holds a slot of this iteration (acc-sGS residual)
         // the check schedule depends only on (it, lastSigmaIt), so an inPALM iteration knows beforehand whether a check
         // follows it and lets k_qstep / k_mult accumulate the KKT sums on the data they stream anyway (:218-267)
         bool fused_check = false;
@@ -1626,7 +1631,14 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             launch_qstep(a, weighted, true, c->st);                                  // q ; alpha = (alpha + A phi) - w.*q
             cudaEvent_t e1 = mark();
             launch_rhs(g, L.sc, weighted, q, S0->alpha, S0->weight, S0->c0, S0->c1, S0->rhs, c->st);
-            if ((rc = L.step_phi())) return rc;
+            if ((rc = accsgs ? L.step_sgs() : L.step_phi())) return rc;
+            if (accsgs && (checkSByS || IfAdjustSigma_sGS(it, lastSigmaIt, sigma_adjust_it_gap) || it == maxit)) {
+                // error of the sGS blocks (accsGSADMM :262-268), on the new q and alpha
+                if ((rc = begin_sums(c))) return rc;
+                sums_begun = true;
+                launch_sgs_resid(g, L.sc, true, S0->phi, q, S0->alpha, S0->c0, S0->c1, S0->partial, c->d_lvl, KS_SGS_BLOCKS, 0, g.nt, c->st);
+                c->launches += 2;
+            }
             cudaEvent_t e2 = mark();
             launch_cells_update(g, L.sc, false, 1, q, zmat, beta, c->st);            // beta = (beta + z) - z2 ; z = Pi_Q(z2 - beta)
             cudaEvent_t e3 = mark();
@@ -1638,7 +1650,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         }
 
         // ---------------------------------------------------------------- kkt :218-324
-        const bool adjustSigmaYes = sgs ? IfAdjustSigma_sGS(it, lastSigmaIt, sigma_adjust_it_gap) : IfAdjustSigma(it, lastSigmaIt);
+        const bool adjustSigmaYes = vote ? IfAdjustSigma_sGS(it, lastSigmaIt, sigma_adjust_it_gap) : IfAdjustSigma(it, lastSigmaIt);
         bool over_time = false;
         if (!c->comm) {   // (between processes the clock is only consulted at collective points, see below)
             over_time = (now_s() - clock_total) > time_limit;
@@ -1650,7 +1662,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         const bool check = checkSByS || adjustSigmaYes || it == maxit || over_time;
         bool stop = false;
         if (check) {
-            if (!fused_check && (rc = begin_sums(c))) return rc;
+            if (!fused_check && !sums_begun && (rc = begin_sums(c))) return rc;
             for (Slab* s : c->slabs) {
                 if (fused_check) {
                     KktFused kf{sigma, cScale, dScale, D, E, s->partial_q, s->partial_m, c->d_lvl};
@@ -1671,6 +1683,11 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
                     launch_kkt_cells(ka, weighted, c->one_d, c->st);
                     launch_kkt_nodes(ka, weighted, c->st);
                     c->launches += 5;
+                    if (accsgs) {   // ||A'(A phi - q)|| of accsGSADMM :360
+                        launch_sgs_resid(g, L.sc, false, s->phi, s->q[c->qcur], nullptr, s->c0, s->c1, s->partial, c->d_lvl, KS_SGS_KKT,
+                                         s->tr.tn0, s->tr.tn1, c->st);
+                        c->launches += 2;
+                    }
                 }
                 // row 0 carries the elapsed time seen by slab 0 so that all processes decide alike
                 if (s->id == 0) {
@@ -1719,7 +1736,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             const double priVal = (sigma * cScale * dScale * h) * sn[KN_QDOTA];
             const double dualVal = (sigma * cScale * dScale * h) * sn[KN_CPHI];
             const double pdGap = fabs(priVal - dualVal) / (1 + fabs(priVal) + fabs(dualVal));
-            if (sgs) {   // :284 and the state the :385-402 branch re-uses
+            if (vote) {   // :284 and the state the :385-402 branch re-uses
                 FeasRatio[it] = mmax({KR[0], KR[1]}) / mmax({KR[2], KR[4]});
                 for (int j = 0; j < 5; j++) KRs[j] = KR[j];
                 norm_Aphi_s = norm_Aphi;
@@ -1754,7 +1771,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
                         copy_to(S0->anc_);
                     }
                 };
-                if (sgs) {   // solver_socp_sGSinPALM.m:321-360
+                if (vote) {   // solver_socp_sGSinPALM.m:321-360 ; solver_socp_accsGSADMM.m:359-412
                     const double kkt_sgs_blocks = sqrt(nrm(sums[KS_SGS_KKT]) * nrm(sums[KS_SGS_KKT]) + (dualFea1 / sigma) * (dualFea1 / sigma));
                     const double resi_sGS_blocks = nrm(sums[KS_SGS_BLOCKS]);
                     sgs_superior_yes = resi_sGS_blocks < sigma_adjust_val_gap * kkt_sgs_blocks;
@@ -1771,7 +1788,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
                         const double meanFeasRatio = sum / (double)(it - i0 + 1);
                         const bool adjust2 = sgs_superior_yes || stopv < tol_sgs_blocks || (dualWin >= sgs_victory && meanFeasRatio > 1);
                         if (adjust2) {
-                            if (it > 2500) stablePhase = true;
+                            if (it > stable_after) stablePhase = true;
                             if ((primWin >= sgs_victory && meanFeasRatio < 1) || (dualWin >= sgs_victory && meanFeasRatio > 1)) {
                                 double factor = 1;
                                 if (stablePhase) {
@@ -1800,9 +1817,21 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
                 }
             }
         }
-        if (sgs && !check) {
-            if (fused_check) {   // sgs_superior_yes: primal / dual feasibility of this iteration from the fused sums (:385-402)
+        if (vote && !check) {
+            if (fused_check || (accsgs && sgs_superior_yes)) {   // sgs_superior_yes: primal / dual feasibility of this iteration (:385-402)
+                if (accsgs) {   // acc keeps z as state and has no fused sums: the stand-alone node kernel (accsGSADMM :420-425)
+                    if ((rc = begin_sums(c))) return rc;
+                    launch_bfdconj(g, L.sc.S, S0->beta[c->bcur], S0->qtmp, c->st, &S0->tr);
+                    KktArgs ka;
+                    ka.g = g; ka.tr = S0->tr; ka.sc = L.sc; ka.sigma = sigma; ka.cScale = cScale; ka.dScale = dScale; ka.D = D; ka.E = E;
+                    ka.phi = S0->phi; ka.q = S0->q[c->qcur]; ka.alpha = S0->alpha; ka.weight = S0->weight;
+                    ka.beta = S0->beta[c->bcur]; ka.z = zmat; ka.q_old = S0->q[1 - c->qcur]; ka.beta_old = S0->beta[1 - c->bcur];
+                    ka.q2b = S0->qtmp; ka.c0 = S0->c0; ka.c1 = S0->c1; ka.partial = S0->partial; ka.lvl = c->d_lvl;
+                    launch_kkt_nodes(ka, weighted, c->st);
+                    c->launches += 3;
+                }
                 for (Slab* s : c->slabs) {
+                    if (accsgs) break;
                     KktFused kf{sigma, cScale, dScale, D, E, s->partial_q, s->partial_m, c->d_lvl};
                     launch_kkt_fused_reduce(g, s->tr, kf, c->st);
                     c->launches += 2;
@@ -1880,6 +1909,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         const double tot = total_ms * 1e-3;
         if (inpalm) { res->times[0] = T[0]; res->times[1] = T[1]; res->times[2] = T[2]; res->times[3] = T[3]; res->times[4] = T[4]; res->times[5] = tot; }
         else if (palm) { res->times[0] = T[5]; res->times[1] = T[0]; res->times[2] = T[1]; res->times[3] = T[2]; res->times[4] = T[3]; res->times[5] = T[4]; res->times[6] = tot; }
+        else if (accsgs) { res->times[0] = T[0]; res->times[1] = T[1]; res->times[2] = T[3]; res->times[3] = T[2]; res->times[4] = T[5]; res->times[5] = T[4]; res->times[6] = tot; }
         else { res->times[0] = T[2]; res->times[1] = T[3]; res->times[2] = T[0]; res->times[3] = T[1]; res->times[4] = T[4]; res->times[5] = T[5]; res->times[6] = tot; }
         res->gpu_launches = c->launches;
     }
@@ -1894,7 +1924,7 @@ extern "C" int dotsocp_run(dotsocp_ctx* c, const dotsocp_level_opts* o, dotsocp_
     if (o->variant != c->variant || o->nt != c->g.nt || o->nx != c->g.nx || o->ny != c->g.ny)
         return set_err(DOTSOCP_EINVAL, "opts do not match the context (variant/grid)");
     if (o->maxit < 1) return set_err(DOTSOCP_EINVAL, "maxit must be >= 1");
-    if (o->method < 0 || o->method > 3) return set_err(DOTSOCP_EINVAL, "unknown method %d", o->method);
+    if (o->method < 0 || o->method > 4) return set_err(DOTSOCP_EINVAL, "unknown method %d", o->method);
     return run_level(c, *o, hist, res);
 }
 

@@ -448,9 +448,7 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
         raise ValueError("Invalid input at position 4 (Number of levels in multilevel strategy)")
     if method not in _VALID[variant]:
         raise ValueError("Invalid input at position 6 (Solving method)")
-    if method == "acc-sGS-ADMM":
-        raise NotImplementedError("acc-sGS-ADMM is not part of this build (SURVEY.md §8f)")
-    sgsMethod = method == "sGS-inPALM"                                   # solver_dotsocp2d.m:93-97
+    sgsMethod = method in ("sGS-inPALM", "acc-sGS-ADMM")                 # solver_dotsocp2d.m:93-97
     admmMaxIt, sgsMaxIt = 3000, 6000
     opts.setdefault("ifCheckStepByStep", False)
     scalingYes = opts.setdefault("scaling", True)
@@ -515,11 +513,12 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
             runHist, sigma = S.solver_socp_PALM(var, o2, model)
         elif method in ("inPALM", "ALG2"):
             runHist, sigma = (S.solver_wsocp_inPALM if variant == "wdot2d" else S.solver_socp_inPALM)(var, o2, model)
-        elif method == "sGS-inPALM":                                     # :210-216: sGS on the last level only
+        elif sgsMethod:                                                  # :210-223: the sGS loop on the last level only
             if level == levelN - 1:
-                runHist, sigma = S.solver_socp_sGSinPALM(var, o2, model)
+                runHist, sigma = (S.solver_socp_sGSinPALM if method == "sGS-inPALM" else S.solver_socp_accsGSADMM)(var, o2, model)
             else:
                 o2["maxit"] = admmMaxIt
+                o2["tau"] = 1.9
                 runHist, sigma = S.solver_socp_inPALM(var, o2, model)
         else:
             runHist, sigma = (S.solver_wsocp_accADMM if variant == "wdot2d" else S.solver_socp_accADMM)(var, o2, model)
@@ -568,9 +567,10 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
         rank, world, ident, distributed = 0, int(slabs or 1), None, False
     InitialScaling(var, model, scalingYes, None, variant)          # coarsest level: host arrays, as the reference
     sess = S.Session(variant, model.nt, model.nx, model.ny, rank=rank, world=world, nccl_id=ident)
-    sgs_last = method == "sGS-inPALM"                               # coarse levels: inPALM with maxit 3000, last level: sGS (:210-216)
-    mname = "inPALM" if method in ("inPALM", "ALG2", "sGS-inPALM") else method
-    z_dead = mname == "inPALM" and int(optsML["maxit"]) >= 1
+    sgs_last = method if method in ("sGS-inPALM", "acc-sGS-ADMM") else None   # coarse levels: inPALM (tau 1.9, maxit 3000), :210-223
+    mname = "inPALM" if method in ("inPALM", "ALG2", "sGS-inPALM", "acc-sGS-ADMM") else method
+    first_is_inpalm = mname == "inPALM" and not (sgs_last == "acc-sGS-ADMM" and levelN == 1)   # acc loops read the incoming z
+    z_dead = first_is_inpalm and int(optsML["maxit"]) >= 1
     state0 = (var.phi, var.q, None if z_dead else var.z, var.alpha, var.beta, model.c, model.weight if weighted else None)
     if distributed:
         state0 = SL.split_state(rank, world, model.nt, model.nx, model.ny, *state0, cuts=sess.cuts)
@@ -585,9 +585,10 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
             lname = mname
             if sgs_last:
                 if level == levelN - 1:
-                    lname = "sGS-inPALM"
+                    lname = sgs_last
                 else:
                     o2["maxit"] = 3000
+                    o2["tau"] = 1.9
             lo = S.make_level_opts(variant, lname, var, o2, model)
             hb, res = sess.run(lo)
             runHist, sigma = S._finish(var, lo.method, hb, res)      # var.cScale/dScale/D/E after in-loop rescaling, var.time

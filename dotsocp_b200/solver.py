@@ -26,8 +26,10 @@ TIME_NAMES = {
     1: ["Step_1_Q_Step", "Step_2_1_FFT", "Step_2_2_ProjSOC", "Step_3_Q_Step", "Step_4_Multiplier", "KKT", "Total_Time"],
     2: ["Step_1_Q_Step", "Step_2_Multiplier", "Step_3_1_FFT", "Step_3_2_ProjSOC", "KKT", "Interp", "Total_Time"],
     3: ["Step_1_1_sGS", "Step_1_2_ProjSOC", "Step_2_Q_Step", "Step_3_Multiplier", "KKT", "Total_Time"],
+    4: ["Step_1_1_sGS", "Step_1_2_ProjSOC", "Step_2_Multiplier", "Step_3_Q_Step", "Step_4_Interp", "KKT", "Total_Time"],
 }
-METHOD_NAMES = {0: "Inexact Proximal ALM", 1: "Proximal ALM", 2: "Accelerated ADMM", 3: "Symmetric Gauss-seidel based inPALM"}
+METHOD_NAMES = {0: "Inexact Proximal ALM", 1: "Proximal ALM", 2: "Accelerated ADMM", 3: "Symmetric Gauss-seidel based inPALM",
+                4: "Accelerated symmetric Gauss-Seidel based ADMM"}
 
 
 def _get(opts, name, default=None):
@@ -290,6 +292,11 @@ def solver_socp_PALM(var, opts, model):
 def solver_socp_accADMM(var, opts, model):
     """socp/dot2d/algorithms/solver_socp_accADMM.m:1"""
     return _solve("dot2d", "acc-ADMM", var, opts, model)
+
+
+def solver_socp_accsGSADMM(var, opts, model):
+    """socp/dot2d/algorithms/solver_socp_accsGSADMM.m:1"""
+    return _solve("dot2d", "acc-sGS-ADMM", var, opts, model)
 
 
 def solver_socp_sGSinPALM(var, opts, model):

@@ -22,7 +22,7 @@
  *                              initialize_FFTkernel.m:6-15 ; 1-D: socp/dot1d/utils/oper_poisson.m:4  (ny = 1)
  *   solver level  (the boundary the north star names)
  *     dotsocp_solve_level   <- [runHist,sigma] = solver_socp_inPALM(var,opts,model)   socp/dot2d/algorithms/solver_socp_inPALM.m:1
- *                              solver_socp_PALM.m:1, solver_socp_accADMM.m:1, solver_socp_sGSinPALM.m:1,
+ *                              solver_socp_PALM.m:1, solver_socp_accADMM.m:1, solver_socp_sGSinPALM.m:1, solver_socp_accsGSADMM.m:1,
  *                              socp/wdot2d/algorithms/solver_wsocp_inPALM.m:1, solver_wsocp_accADMM.m:1,
  *                              socp/dot1d/algorithms/solver_socp_inPALM.m:1
  *   device-resident session (same loop, state stays in HBM; used by the multilevel driver and the benchmark)
@@ -55,6 +55,7 @@ extern "C" {
 #define DOTSOCP_METHOD_PALM     1   /* solver_socp_PALM.m (dot2d only) */
 #define DOTSOCP_METHOD_ACCADMM  2   /* solver_*socp_accADMM.m (dot2d, wdot2d) */
 #define DOTSOCP_METHOD_SGSINPALM 3  /* solver_socp_sGSinPALM.m (dot2d, nx == ny, odd node counts: the grids mexsGS handles) */
+#define DOTSOCP_METHOD_ACCSGSADMM 4 /* solver_socp_accsGSADMM.m (same grids, single GPU)                                       */
 
 #define DOTSOCP_NTIMES 8
 
@@ -93,6 +94,7 @@ typedef struct dotsocp_level_result {
                                        PALM   : Q_Step(1), FFT, ProjSOC, Q_Step(3), Multiplier, KKT, Total, 0
                                        accADMM: Q_Step, Multiplier, FFT, ProjSOC, KKT, Interp, Total, 0
                                        sGSinPALM: sGS, ProjSOC, Q_Step, Multiplier, KKT, Total, 0, 0  (:419-420)
+                                       accsGSADMM: sGS, ProjSOC, Multiplier, Q_Step, Interp, KKT, Total, 0  (:512-513)
                                        The fused kernels do not separate ProjSOC from the multiplier step; the fused
                                        time is booked under the step that dominates it.             */
     double  gpu_launches;       /* number of kernels launched by this call                              */

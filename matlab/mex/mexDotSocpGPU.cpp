@@ -8,7 +8,7 @@
 //                          .m wrapper must own the only reference (the reference loop detaches them from the handle
 //                          for the same reason, solver_socp_inPALM.m:89-93).
 // c                      : model.c (N x 1, already scaled);   weight : model.weight (Q x 1) or [] (unweighted)
-// P                      : struct of scalars -- variant ('dot2d'|'wdot2d'|'dot1d'), method ('inPALM'|'PALM'|'acc-ADMM'|'sGS-inPALM'),
+// P                      : struct of scalars -- variant ('dot2d'|'wdot2d'|'dot1d'), method ('inPALM'|'PALM'|'acc-ADMM'|'sGS-inPALM'|'acc-sGS-ADMM'),
 //                          nt,nx,ny, maxit, tol, tau, sigma, ifCheckStepByStep, scaling, checkPrimDualFeas (-1 = absent),
 //                          time_limit, restart, rho, theta, cScale, dScale, D, E, normc, normd, grad_t, grad_x, grad_y
 // out                    : struct with kkt (len x 7), time, iter, pdGap, priVal, dualVal (len x 1), len, iters, sigma,
@@ -78,6 +78,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])
     else if (method == "PALM") o.method = DOTSOCP_METHOD_PALM;
     else if (method == "acc-ADMM") o.method = DOTSOCP_METHOD_ACCADMM;
     else if (method == "sGS-inPALM") o.method = DOTSOCP_METHOD_SGSINPALM;
+    else if (method == "acc-sGS-ADMM") o.method = DOTSOCP_METHOD_ACCSGSADMM;
     else mexErrMsgIdAndTxt("dotsocp:invalidInput", "unknown method '%s'", method.c_str());
     o.nt = (int)field(P, "nt", 0, true);
     o.nx = (int)field(P, "nx", 0, true);

@@ -2,7 +2,7 @@ function [runHist, sigma] = dotsocp_gpu_level(var, opts, model, variant, method)
 %% Run one level of the DOT-SOCP loop on the GPU (libdotsocp.so through mexDotSocpGPU).
 % Drop-in body for socp/<variant>/algorithms/solver_*socp_*.m: same inputs, same side effects on the handle
 % objects var/model and the same outputs (reference: solver_socp_inPALM.m:1, :328-357).
-%   variant : 'dot2d' | 'wdot2d' | 'dot1d'          method : 'inPALM' | 'PALM' | 'acc-ADMM' | 'sGS-inPALM'
+%   variant : 'dot2d' | 'wdot2d' | 'dot1d'          method : 'inPALM' | 'PALM' | 'acc-ADMM' | 'sGS-inPALM' | 'acc-sGS-ADMM'
 % (ALG2 is inPALM with opts.tau = 1, exactly as in solver_dotsocp2d.m:133-137.)
 
 P = struct();
@@ -47,7 +47,7 @@ out = mexDotSocpGPU(phi, q, z, alpha, beta, model.c, weight, P);   % phi,q,z,alp
 
 %% output (solver_socp_inPALM.m:328-357)
 names3 = struct('inPALM', 'Inexact Proximal ALM', 'PALM', 'Proximal ALM', 'accADMM', 'Accelerated ADMM', ...
-                'sGSinPALM', 'Symmetric Gauss-seidel based inPALM');
+                'sGSinPALM', 'Symmetric Gauss-seidel based inPALM', 'accsGSADMM', 'Accelerated symmetric Gauss-Seidel based ADMM');
 var.name = names3.(strrep(strrep(method, '-', ''), 'ALG2', 'inPALM'));
 var.phi = phi;  var.q = q;  var.z = z;  var.alpha = alpha;  var.beta = beta;   % alpha, beta already times sigma
 switch method
@@ -56,6 +56,9 @@ switch method
         times = [out.times(1:7), out.iters];
     case 'acc-ADMM'
         tnames = {'Step_1_Q_Step', 'Step_2_Multiplier', 'Step_3_1_FFT', 'Step_3_2_ProjSOC', 'KKT', 'Interp', 'Total_Time', 'Iters'};
+        times = [out.times(1:7), out.iters];
+    case 'acc-sGS-ADMM'
+        tnames = {'Step_1_1_sGS', 'Step_1_2_ProjSOC', 'Step_2_Multiplier', 'Step_3_Q_Step', 'Step_4_Interp', 'KKT', 'Total_Time', 'Iters'};
         times = [out.times(1:7), out.iters];
     case 'sGS-inPALM'
         tnames = {'Step_1_1_sGS', 'Step_1_2_ProjSOC', 'Step_2_Q_Step', 'Step_3_Multiplier', 'KKT', 'Total_Time', 'Iters'};

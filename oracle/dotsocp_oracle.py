@@ -823,8 +823,15 @@ def _copyvar(phi, z, q, alpha, beta):
     return phi.copy(), z.copy(order="F"), q.copy(), alpha.copy(), beta.copy(order="F")
 
 
-def solver_socp_accADMM(var, opts, model, workers=1, trace=None):
-    """socp/dot2d/algorithms/solver_socp_accADMM.m:1-458 ; socp/wdot2d/algorithms/solver_wsocp_accADMM.m:1-463."""
+def solver_socp_accsGSADMM(var, opts, model, workers=1, trace=None):
+    """socp/dot2d/algorithms/solver_socp_accsGSADMM.m:1-568 : acc-ADMM whose phi-step is one symmetric red-black Gauss-Seidel
+    sweep (mexsGS, :256), with the sGS check schedule and sigma voting of solver_socp_sGSinPALM.m (stable phase after 1500)."""
+    return solver_socp_accADMM(var, opts, model, workers, trace, sgs=True)
+
+
+def solver_socp_accADMM(var, opts, model, workers=1, trace=None, sgs=False):
+    """socp/dot2d/algorithms/solver_socp_accADMM.m:1-458 ; socp/wdot2d/algorithms/solver_wsocp_accADMM.m:1-463 ;
+    sgs=True: socp/dot2d/algorithms/solver_socp_accsGSADMM.m (line numbers marked sGS:)."""
     weight = getattr(model, "weight", None)
     weighted = weight is not None
     ops = _Ops(model, var, workers)
@@ -847,7 +854,7 @@ def solver_socp_accADMM(var, opts, model, workers=1, trace=None):
     A, AT, c = model.grad, model.gradT, model.c
     phi, q, z, alpha, beta = var.phi, var.q, np.asfortranarray(var.z), var.alpha, var.beta
     var.phi = var.q = var.z = var.alpha = var.beta = None
-    kernel = D ** 2 * ops.fftkernel()
+    kernel = None if sgs else D ** 2 * ops.fftkernel()
     diagQInv = 1 / ops.oper_q(D, E, weight)
     norm_c = model.normc
     norm_d = None if weighted else model.normd
@@ -860,6 +867,16 @@ def solver_socp_accADMM(var, opts, model, workers=1, trace=None):
     T = dict(lineq=0.0, proj=0.0, q=0.0, mult=0.0, kkt=0.0, interp=0.0)
     z2 = np.zeros(z.shape, order="F")
     q2 = np.zeros(q.shape)
+    if sgs:                                                                                  # sGS:76-120,147,164-166
+        nx_, ny_, nt_ = model.nx, model.ny, model.nt
+        scaleLap = D ** 2
+        hist_n, victory, initialSigmaScale, stablePhase = 19, 12, 1.10, False
+        sigma_adjust_it_gap = max(1, (nt_ * nx_ * ny_) ** (1 / 3) / 33)
+        sigma_adjust_val_gap, sgs_superior_yes, tol_sgs_blocks = 0.95, False, 5 * tol
+        FeasRatio = np.full(maxit + 1, INF)
+        KKTResi = None
+        norm_Aphi = norm_q = None
+        phi = phi - h * phi.sum()
     phiOld, zOld, qOld, alphaOld, betaOld = _copyvar(phi, z, q, alpha, beta)                 # :157
     k = 0
     if HalpernYes:
@@ -919,8 +936,20 @@ def solver_socp_accADMM(var, opts, model, workers=1, trace=None):
         T["mult"] += time.perf_counter() - t0
         # step phi :241-244
         t0 = time.perf_counter()
-        phi = ops.poisson(kernel, AT @ (wq(q) - alpha) + c)
+        if sgs:
+            phi = phi.copy()                                                                 # in-place MEX write; Old/anchor copies are deep (sGS:563-566)
+            K.mexsGS(phi, AT @ (q - alpha) + c, 0, scaleLap, nt_, nx_, ny_, 1)                # sGS:256
+        else:
+            phi = ops.poisson(kernel, AT @ (wq(q) - alpha) + c)
         T["lineq"] += time.perf_counter() - t0
+        if sgs:                                                                              # sGS:259-269
+            t0 = time.perf_counter()
+            adjustSigmaYes = IfAdjustSigma_sGS(it, lastSigmaIt, sigma_adjust_it_gap)
+            check = checkSByS or adjustSigmaYes or it == maxit or (time.perf_counter() - clock_total) > time_limit
+            if check:
+                tmp_resi_sGS = AT @ (A @ phi - q + alpha) - c
+                resi_sGS_blocks = normL2(tmp_resi_sGS[0::2], h)
+            T["kkt"] += time.perf_counter() - t0
         # step z :246-249   (in place into z; the Old/anchor copies are deep, :480-484)
         t0 = time.perf_counter()
         znew = np.empty(z.shape, order="F")
@@ -929,8 +958,9 @@ def solver_socp_accADMM(var, opts, model, workers=1, trace=None):
         T["proj"] += time.perf_counter() - t0
         # kkt :251-367
         t0 = time.perf_counter()
-        adjustSigmaYes = IfAdjustSigma(it, lastSigmaIt)
-        check = checkSByS or adjustSigmaYes or it == maxit or (time.perf_counter() - clock_total) > time_limit
+        if not sgs:
+            adjustSigmaYes = IfAdjustSigma(it, lastSigmaIt)
+            check = checkSByS or adjustSigmaYes or it == maxit or (time.perf_counter() - clock_total) > time_limit
         stop = False
         if check:
             ops.BFdConj(q2, np.asfortranarray(beta), scaleBF)
@@ -964,18 +994,45 @@ def solver_socp_accADMM(var, opts, model, workers=1, trace=None):
             hist.iter.append(it); hist.pdGap.append(pdGap); hist.priVal.append(priVal); hist.dualVal.append(dualVal)
             if trace is not None:
                 trace.append(("check", it, sigma, list(KKTResiOrg), list(KKTResi), priVal, dualVal))
-            if mmax([KKTResiOrg[i] for i in stopCondition]) < tol or (time.perf_counter() - clock_total) > time_limit:
+            error = mmax([KKTResiOrg[i] for i in stopCondition])
+            if sgs:
+                FeasRatio[it] = mmax(KKTResi[0:2]) / mmax([KKTResi[2], KKTResi[4]])           # sGS:323
+            if error < tol or (time.perf_counter() - clock_total) > time_limit:
                 stop = True
             else:
                 if mmax(KKTResi) < tol_feasOrg:
                     use_feasOrg = 1
-                if adjustSigmaYes:
+                factor = 1
+                if sgs:                                                                      # sGS:360-412
+                    kkt_sgs_blocks = math.sqrt(normL2(AT @ (tmp_q - q), h) ** 2 + (dualFea1 / sigma) ** 2)
+                    sgs_superior_yes = resi_sGS_blocks < sigma_adjust_val_gap * kkt_sgs_blocks
+                    if adjustSigmaYes:
+                        lastSigmaIt = it
+                        feasRatioHist = FeasRatio[max(1, it - hist_n): it + 1]
+                        meanFeasRatio = float(np.mean(feasRatioHist))
+                        primWinTimes = int(np.sum(feasRatioHist < 1))
+                        dualWinTimes = int(np.sum(feasRatioHist > 1))
+                        if sgs_superior_yes or error < tol_sgs_blocks or (dualWinTimes >= victory and meanFeasRatio > 1):
+                            if it > 1500:
+                                stablePhase = True
+                            if ((primWinTimes >= victory and meanFeasRatio < 1)
+                                    or (dualWinTimes >= victory and meanFeasRatio > 1)):
+                                if stablePhase:
+                                    sigma, factor = adjust_lagrangianParam(sigma, meanFeasRatio, SGS_UPDATE_RULE)
+                                else:
+                                    if meanFeasRatio < 1:
+                                        factor = 1 / initialSigmaScale
+                                    elif meanFeasRatio > 1:
+                                        factor = initialSigmaScale
+                                    sigma = sigma * factor
+                elif adjustSigmaYes:
                     lastSigmaIt = it
                     if use_feasOrg:
                         resiPri, resiDual = mmax(KKTResiOrg[0:2]), mmax([KKTResiOrg[2], KKTResiOrg[4]])
                     else:
                         resiPri, resiDual = mmax(KKTResi[0:2]), mmax([KKTResi[2], KKTResi[4]])
                     sigma, factor = adjust_lagrangianParam(sigma, resiPri / resiDual, UPDATE_RULE)
+                if sgs or adjustSigmaYes:
                     if factor != 1:
                         alpha = alpha / factor
                         alphaOld = alphaOld / factor
@@ -988,6 +1045,20 @@ def solver_socp_accADMM(var, opts, model, workers=1, trace=None):
                 if rescale > 0:
                     maxFeas = mmax(KKTResi)
                     relGap = pdGap
+        elif sgs and sgs_superior_yes:                                                       # sGS:420-437
+            primFea1 = normL2(A @ phi - q, h)
+            dualFea1 = sigma * normL2(AT @ alpha - c, h)
+            if use_feasOrg:
+                dec = primFea1 / ((kktConst * D / dScale + norm_Aphi + norm_q) * KKTResi[0])
+                KKTResi[0], KKTResi[1] = KKTResi[0] * dec, KKTResi[1] * dec
+                KKTResi[2] = dualFea1 / (kktConst / cScale + norm_c)
+            else:
+                dec = primFea1 / ((kktConst + norm_Aphi + norm_q) * KKTResi[0])
+                KKTResi[0], KKTResi[1] = KKTResi[0] * dec, KKTResi[1] * dec
+                KKTResi[2] = dualFea1 / (kktConst + norm_c)
+            FeasRatio[it] = mmax(KKTResi[0:2]) / mmax([KKTResi[2], KKTResi[4]])
+        elif sgs:
+            FeasRatio[it] = FeasRatio[it - 1]
         T["kkt"] += time.perf_counter() - t0
         if stop:
             break
@@ -1036,13 +1107,17 @@ def solver_socp_accADMM(var, opts, model, workers=1, trace=None):
         beta = np.asfortranarray(beta)
         T["interp"] += time.perf_counter() - t0
     time_total = time.perf_counter() - clock_total
-    var.name = "Accelerated ADMM"
+    var.name = "Accelerated symmetric Gauss-Seidel based ADMM" if sgs else "Accelerated ADMM"
     var.phi, var.q, var.z = phi, q, z
     var.alpha = sigma * alpha
     var.beta = sigma * beta
-    var.time = {"Step_1_Q_Step": T["q"], "Step_2_Multiplier": T["mult"], "Step_3_1_FFT": T["lineq"],
-                "Step_3_2_ProjSOC": T["proj"], "KKT": T["kkt"], "Interp": T["interp"], "Total_Time": time_total,
-                "Iters": it}
+    if sgs:                                                                                  # sGS:512-513
+        var.time = {"Step_1_1_sGS": T["lineq"], "Step_1_2_ProjSOC": T["proj"], "Step_2_Multiplier": T["mult"],
+                    "Step_3_Q_Step": T["q"], "Step_4_Interp": T["interp"], "KKT": T["kkt"], "Total_Time": time_total, "Iters": it}
+    else:
+        var.time = {"Step_1_Q_Step": T["q"], "Step_2_Multiplier": T["mult"], "Step_3_1_FFT": T["lineq"],
+                    "Step_3_2_ProjSOC": T["proj"], "KKT": T["kkt"], "Interp": T["interp"], "Total_Time": time_total,
+                    "Iters": it}
     var.cScale, var.dScale, var.D, var.E = cScale, dScale, D, E
     return _finish_hist(hist), sigma / sigmaScale
 
@@ -1367,8 +1442,6 @@ def _solve_multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=Non
              "wdot2d": ["inPALM", "ALG2", "acc-ADMM"], "dot1d": ["inPALM", "ALG2"]}[variant]
     if method not in valid:
         raise ValueError("Invalid input at position 6 (Solving method)")
-    if method == "acc-sGS-ADMM":
-        raise NotImplementedError("acc-sGS-ADMM is not restated (SURVEY.md §8f 'next' row)")
     sgsMethod = method in ("sGS-inPALM", "acc-sGS-ADMM")                         # solver_dotsocp2d.m:93
     admmMaxIt, sgsMaxIt = 3000, 6000                                             # :96-97
     opts.setdefault("ifCheckStepByStep", False)
@@ -1443,6 +1516,13 @@ def _solve_multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=Non
                 runHist, sigma = solver_socp_sGSinPALM(var, o2, model, workers, trace=trace)
             else:
                 o2["maxit"] = admmMaxIt
+                runHist, sigma = solver_socp_inPALM(var, o2, model, workers, trace=trace)
+        elif method == "acc-sGS-ADMM":                                           # :217-223
+            if level == levelN - 1:
+                runHist, sigma = solver_socp_accsGSADMM(var, o2, model, workers, trace=trace)
+            else:
+                o2["maxit"] = admmMaxIt
+                o2["tau"] = 1.9
                 runHist, sigma = solver_socp_inPALM(var, o2, model, workers, trace=trace)
         else:
             runHist, sigma = solver_socp_accADMM(var, o2, model, workers, trace=trace)

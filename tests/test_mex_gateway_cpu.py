@@ -18,7 +18,7 @@ def test_mex_gateway_compiles_against_stub_mex_h():
 
 
 def test_matlab_wrappers_keep_reference_names():
-    want = {"dot2d": ["solver_socp_inPALM.m", "solver_socp_PALM.m", "solver_socp_accADMM.m", "solver_socp_sGSinPALM.m"],
+    want = {"dot2d": ["solver_socp_inPALM.m", "solver_socp_PALM.m", "solver_socp_accADMM.m", "solver_socp_sGSinPALM.m", "solver_socp_accsGSADMM.m"],
             "wdot2d": ["solver_wsocp_inPALM.m", "solver_wsocp_accADMM.m"], "dot1d": ["solver_socp_inPALM.m"]}
     for v, files in want.items():
         for f in files:

@@ -513,3 +513,15 @@ def test_dot2d_sgs_inpalm_parity(gpu, n, nt, levelN):
     for extra in ({}, {"resident": False}, {"slabs": 2}):
         out_g, _, ML_g, rh_g = dp.solver_dotsocp2d(rho0, rho1, nt, levelN, dict(opts, **extra), "sGS-inPALM")
         _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o)
+
+
+@pytest.mark.parametrize("n,nt,levelN", [(17, 9, 1), (17, 9, 2)])
+def test_dot2d_acc_sgs_admm_parity(gpu, n, nt, levelN):
+    """acc-sGS-ADMM (solver_socp_accsGSADMM.m): Halpern-accelerated ADMM with the Gauss-Seidel phi-step and the sGS sigma voting"""
+    import dotsocp_b200 as dp
+    rho0, rho1 = O.get_example2d("example1", n, n)
+    opts = {"tol": 1e-4}
+    out_o, _, ML_o, rh_o = O.solver_dotsocp2d(rho0, rho1, nt, levelN, opts, "acc-sGS-ADMM", workers=4)
+    for extra in ({}, {"resident": False}):
+        out_g, _, ML_g, rh_g = dp.solver_dotsocp2d(rho0, rho1, nt, levelN, dict(opts, **extra), "acc-sGS-ADMM")
+        _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o)
