@@ -947,7 +947,7 @@ extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q
     }
     c->z_materialised = true;
     c->z_absent = (z == nullptr);
-    int rc = ghosts(c, GH_PHI_UP | GH_Q_UP | GH_Q_DOWN | GH_ALPHA0_DOWN | GH_BETA_DOWN | GH_W, 0, 0);
+    int rc = ghosts(c, GH_PHI_UP | GH_PHI_DOWN | GH_Q_UP | GH_Q_DOWN | GH_ALPHA0_DOWN | GH_BETA_DOWN | GH_W, 0, 0);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->st));
     c->uploaded = true;
@@ -1024,7 +1024,7 @@ extern "C" int dotsocp_prolong(dotsocp_ctx* coarse, dotsocp_ctx* fine, const dot
         fine->launches += 5 + (double)sf->q_own.size() + 10;
     }
     CU(cudaGetLastError());
-    if ((rc = ghosts(fine, GH_Q_UP | GH_Q_DOWN | GH_ALPHA0_DOWN | GH_W, 0, 0))) return rc;
+    if ((rc = ghosts(fine, GH_PHI_DOWN | GH_Q_UP | GH_Q_DOWN | GH_ALPHA0_DOWN | GH_W, 0, 0))) return rc;   // (the sGS phi-step reads phi[t-1] too)
     CU(cudaStreamSynchronize(st));
     fine->z_materialised = true;
     fine->z_absent = false;
