@@ -405,7 +405,9 @@ void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st,
 // ncu on the round-1 kernel: 55 % of the warp samples waited on the first use of a step's loads (long scoreboard), i.e. the
 // HBM latency was exposed once per step.  PF = true keeps the loaded values of step t+1 in a second register set that is
 // filled BEFORE step t is computed (software pipeline, one 255-register CTA per SM), so a step's loads have a whole step of
-// arithmetic to arrive.  PF = false is the round-1 schedule (two 128-register CTAs per SM); DOTSOCP_KM_PF selects.
+// arithmetic to arrive.  PF = 2 prefetches the same values with cp.async into a two-stage shared-memory ring instead (21 slots
+// per thread; the level-t alpha of the rhs stencil stays a direct load), which keeps 128 registers and two CTAs per SM.
+// PF = 0 is the round-1 schedule (two 128-register CTAs per SM, loads then compute); DOTSOCP_KM_PF selects at run time.
 //
 // KKT (check iterations): the same march also accumulates every KKT term that lives on the data in registers
 // (solver_socp_inPALM.m:225-244, compute_kkt_dot_complement.m) -- z, beta, z2, alpha and q are all there -- and leaves one
@@ -458,7 +460,7 @@ struct MultLoad {
     double cv;                                    // c on the first / last time level
 };
 
-template <int TX, int TY, bool PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool EDGE, bool KKT>
+template <int TX, int TY, int PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool EDGE, bool KKT>
 __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int kkt_t0, const IterScal& sc, const KktDev& kd,
                                             const double* __restrict__ qo, const double* __restrict__ qn,
                                             const double* __restrict__ alpha, const double* __restrict__ weight,
@@ -471,6 +473,8 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
     constexpr int NPL = KKT ? 9 : 4;   // exchange planes: w1,w3,w5,w7 (+ b1,b3,b5,b7, rho)
     extern __shared__ __align__(16) double dyn_smem[];
     double (*sh)[TU][NPL][TX][TY] = reinterpret_cast<double (*)[TU][NPL][TX][TY]>(dyn_smem);
+    constexpr int NT_ = TX * TY, NF = 21;      // ring: [2 stages][NF fields][NT_ threads], every thread reads only its own slots
+    double* ring = dyn_smem + 2 * TU * NPL * NT_;
     const int ly = threadIdx.x, lx = threadIdx.y;
     // y tiles vary fastest over the grid so that CTAs running side by side stream adjacent pieces of the same rows
     const int x = blockIdx.y * (TX - 1) + lx, y = blockIdx.x * (TY - 1) + ly;
@@ -562,6 +566,37 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         }
     };
 
+    // ---- the same values through the shared-memory ring (PF == 2): issue(t) starts the copies, fetch(t) picks them up ---------
+    const int tid_ = lx * TY + ly;
+    auto cp8 = [&](double* dst, const double* src) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    };
+    auto issue = [&](int t) {
+        const bool cell = t < g.nt - 1;
+        if (cell && valid) {
+            double* dst = ring + (size_t)(t & 1) * NF * NT_ + tid_;
+            const i64 cidx = (i64)t * g.P + node;
+            const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
+#pragma unroll
+            for (int j = 0; j < 10; j++)
+                if (!(ONE_D && j >= 5 && j <= 8)) cp8(dst + j * NT_, beta + (i64)j * L + cidx);
+            cp8(dst + 10 * NT_, qn + cidx);
+            cp8(dst + 11 * NT_, alpha + cidx);
+            if (hxm) cp8(dst + 12 * NT_, qn_bx + o1x + ibxm);
+            if (hxp) cp8(dst + 13 * NT_, qn_bx + o1x + ibx);
+            if (hym) cp8(dst + 14 * NT_, qn_by + o1y + ibym);
+            if (hyp) cp8(dst + 15 * NT_, qn_by + o1y + iby);
+            if (UPDATE) {
+                cp8(dst + 16 * NT_, qo + cidx);
+                if (hxm) cp8(dst + 17 * NT_, qo_bx + o1x + ibxm);
+                if (hxp) cp8(dst + 18 * NT_, qo_bx + o1x + ibx);
+                if (hym) cp8(dst + 19 * NT_, qo_by + o1y + ibym);
+                if (hyp) cp8(dst + 20 * NT_, qo_by + o1y + iby);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     // ---- phase 1 of step t into exchange slot (buf, u) ---------------------------------------------------------------
     auto phase1 = [&](int t, int buf, int u, const MultLoad& ld, MultKeep& k, MultKeepK& kk) {
         const bool cell = t < g.nt - 1;
@@ -570,10 +605,41 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
 #pragma unroll
         for (int j = 0; j < 10; j++) w[j] = 0.0;
         double a0 = 0.0;
-        const double wt0 = ld.wt0;
-        const double al_xm = ld.al_xm, al_x = ld.al_x, al_ym = ld.al_ym, al_y = ld.al_y;
-        const double wt_xm = ld.wt_xm, wt_x = ld.wt_x, wt_ym = ld.wt_ym, wt_y = ld.wt_y;
-        k.cv = ld.cv;
+        // where the step's values come from: the prefetched register set (PF == 1), the shared-memory ring (PF == 2) or HBM
+        // directly (PF == 0) -- in the last two cases every value is picked up where it is first needed
+        const double* rsrc = ring + (size_t)(t & 1) * NF * NT_ + tid_;
+        const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
+        auto F = [&](int slot, const double* gaddr, double regval) -> double {
+            if (PF == 1) return regval;
+            if (PF == 2) return rsrc[slot * NT_];
+            return *gaddr;
+        };
+        double wt0 = 1.0, al_xm = 0.0, al_x = 0.0, al_ym = 0.0, al_y = 0.0, wt_xm = 1.0, wt_x = 1.0, wt_ym = 1.0, wt_y = 1.0;
+        k.cv = 0.0;
+        if (PF == 1) {
+            wt0 = ld.wt0;
+            al_xm = ld.al_xm; al_x = ld.al_x; al_ym = ld.al_ym; al_y = ld.al_y;
+            wt_xm = ld.wt_xm; wt_x = ld.wt_x; wt_ym = ld.wt_ym; wt_y = ld.wt_y;
+            k.cv = ld.cv;
+        } else {
+            // level-t alpha (and weight) of the rhs stencil: direct loads, consumed behind the two projections
+            if (owner) {
+                const i64 ox = (i64)t * g.PBX, oy = (i64)t * g.PBY;
+                if (hxm) al_xm = al_bx[ox + ibxm];
+                if (hxp) al_x = al_bx[ox + ibx];
+                if (hym) al_ym = al_by[oy + ibym];
+                if (hyp) al_y = al_by[oy + iby];
+                if (WEIGHTED) {
+                    if (hxm) wt_xm = w_bx[ox + ibxm];
+                    if (hxp) wt_x = w_bx[ox + ibx];
+                    if (hym) wt_ym = w_by[oy + ibym];
+                    if (hyp) wt_y = w_by[oy + iby];
+                }
+                if (t == 0) k.cv = c0[node];
+                else if (!cell) k.cv = c1[node];
+            }
+            if (WEIGHTED && cell && valid) wt0 = weight[cidx];
+        }
         if (KKT) {
 #pragma unroll
             for (int j = 0; j <= KM_RHOFQ; j++) kk.cell[j] = 0.0;
@@ -582,15 +648,21 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         if (cell && valid) {
             double b[10];
 #pragma unroll
-            for (int j = 0; j < 10; j++) b[j] = ld.b[j];
-            cn.q0 = ld.q0n;
-            a0 = ld.a0;
-            cn.bxm1 = ld.bxm1n; cn.bx1 = ld.bx1n; cn.bym1 = ld.bym1n; cn.by1 = ld.by1n;
+            for (int j = 0; j < 10; j++) b[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0 : F(j, beta + (i64)j * L + cidx, ld.b[j]);
+            cn.q0 = F(10, qn + cidx, ld.q0n);
+            a0 = F(11, alpha + cidx, ld.a0);
+            cn.bxm1 = hxm ? F(12, qn_bx + o1x + ibxm, ld.bxm1n) : 0.0;
+            cn.bx1 = hxp ? F(13, qn_bx + o1x + ibx, ld.bx1n) : 0.0;
+            cn.bym1 = hym ? F(14, qn_by + o1y + ibym, ld.bym1n) : 0.0;
+            cn.by1 = hyp ? F(15, qn_by + o1y + iby, ld.by1n) : 0.0;
             double z2n[10];
             cell_z2(cn, sc, hxm, hxp, hym, hyp, z2n);
             if (UPDATE) {
-                co.q0 = ld.q0o;
-                co.bxm1 = ld.bxm1o; co.bx1 = ld.bx1o; co.bym1 = ld.bym1o; co.by1 = ld.by1o;
+                co.q0 = F(16, qo + cidx, ld.q0o);
+                co.bxm1 = hxm ? F(17, qo_bx + o1x + ibxm, ld.bxm1o) : 0.0;
+                co.bx1 = hxp ? F(18, qo_bx + o1x + ibx, ld.bx1o) : 0.0;
+                co.bym1 = hym ? F(19, qo_by + o1y + ibym, ld.bym1o) : 0.0;
+                co.by1 = hyp ? F(20, qo_by + o1y + iby, ld.by1o) : 0.0;
                 double v[10];
                 cell_z2(co, sc, hxm, hxp, hym, hyp, v);
 #pragma unroll
@@ -831,7 +903,19 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         }
     };
     int t = t_start, it = 0;
-    if (PF) {
+    if (PF == 2) {
+        // shared-memory ring: the copies of step t+1 are in flight while step t is computed
+        issue(t);
+        for (; t < tr.tn1; t++, it++) {
+            if (t + 1 < tr.tn1) {
+                issue(t + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            step(t, it, MultLoad());
+        }
+    } else if (PF == 1) {
         // software pipeline, unrolled by two so that the two register sets swap roles without moves
         MultLoad la, lb;
         load(t, la);
@@ -843,16 +927,12 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         }
         if (t < tr.tn1) step(t, it, la);
     } else {
-        for (; t < tr.tn1; t++, it++) {
-            MultLoad ld;
-            load(t, ld);
-            step(t, it, ld);
-        }
+        for (; t < tr.tn1; t++, it++) step(t, it, MultLoad());
     }
 }
 
-template <int TX, int TY, bool PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool KKT>
-__global__ void __launch_bounds__(TX* TY, (PF || KKT) ? 1 : 2)
+template <int TX, int TY, int PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool KKT>
+__global__ void __launch_bounds__(TX* TY, (PF == 1 || KKT) ? 1 : 2)
 k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, const double* __restrict__ qo, const double* __restrict__ qn,
        const double* __restrict__ alpha, const double* __restrict__ weight, const double* __restrict__ beta,
        double* __restrict__ beta_out, double* __restrict__ q2, double* __restrict__ rhs, const double* __restrict__ c0,
@@ -916,10 +996,11 @@ void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cu
     // piece costs one replayed cell layer.  DOTSOCP_KM_CHUNKS=n forces n pieces.
     static const int forced = [] { const char* e = getenv("DOTSOCP_KM_CHUNKS"); return e ? atoi(e) : 0; }();
     const char* pf_env = getenv("DOTSOCP_KM_PF");   // read per launch: tests and A/B runs switch it inside one process
-    const bool pf = pf_env ? atoi(pf_env) != 0 : (KM_PF != 0);
+    const int pf = pf_env ? atoi(pf_env) : KM_PF;
 #define KM(PF, W, O, U, K)                                                                                            \
     {                                                                                                                 \
-        constexpr size_t smem = (size_t)2 * (K ? 9 : 4) * TX * TY * sizeof(double);                                   \
+        constexpr size_t smem = (size_t)2 * (K ? 9 : 4) * TX * TY * sizeof(double) +                                  \
+                                (PF == 2 ? (size_t)2 * 21 * TX * TY * sizeof(double) : 0);                            \
         static int slots = 0;                                                                                         \
         if (!slots) {                                                                                                 \
             cudaFuncSetAttribute(k_mult<TX, TY, PF, W, O, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -936,13 +1017,15 @@ void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cu
                                                                   a.weight, a.beta_in, a.beta_out, a.q2, a.rhs, a.c0, a.c1, kpart); \
     }
     if (kkt && update) {
-        if (one_d) KM(false, false, true, true, true) else if (weighted) KM(false, true, false, true, true) else KM(false, false, false, true, true)
+        if (one_d) KM(0, false, true, true, true) else if (weighted) KM(0, true, false, true, true) else KM(0, false, false, true, true)
     } else if (one_d) {
-        if (update) KM(false, false, true, true, false) else KM(false, false, true, false, false)
+        if (update) KM(0, false, true, true, false) else KM(0, false, true, false, false)
     } else if (weighted) {
-        if (!update) KM(false, true, false, false, false) else if (pf) KM(true, true, false, true, false) else KM(false, true, false, true, false)
+        if (!update) KM(0, true, false, false, false)
+        else if (pf == 2) KM(2, true, false, true, false) else if (pf == 1) KM(1, true, false, true, false) else KM(0, true, false, true, false)
     } else {
-        if (!update) KM(false, false, false, false, false) else if (pf) KM(true, false, false, true, false) else KM(false, false, false, true, false)
+        if (!update) KM(0, false, false, false, false)
+        else if (pf == 2) KM(2, false, false, true, false) else if (pf == 1) KM(1, false, false, true, false) else KM(0, false, false, true, false)
     }
 #undef KM
 }

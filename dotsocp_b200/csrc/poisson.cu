@@ -1147,7 +1147,10 @@ static int t_solve(PoissonPlan* p, double* buf, i64 lines, i64 p0, double D2, cu
     return 0;
 }
 
-static LineGeom geom_y(const Geo& g) { return LineGeom{g.ny, 1, (i64)g.ny, (i64)g.nt * g.nx, 0, 1, 0, 0, 0, 0, 0}; }
+// y lines are contiguous; they are grouped PER TIME LEVEL (outer index = level) although the whole array is one contiguous run of
+// nt*nx lines: the kernels transform two real lines as one complex sequence, and the rounding of a line depends on its partner,
+// so the pairing must not depend on where a time slab starts -- otherwise 1, 2, 4 and 8 GPUs would not give the same bits.
+static LineGeom geom_y(const Geo& g) { return LineGeom{g.ny, 1, (i64)g.ny, (i64)g.nx, g.P, 1, 0, 0, 0, 0, 0}; }
 static LineGeom geom_x(const Geo& g)
 {
     if (g.ny == 1) return LineGeom{g.nx, 1, (i64)g.nx, (i64)g.nt, 0, 1, 0, 0, 0, 0, 0};   // 1-D variant: x lines are contiguous
@@ -1163,12 +1166,12 @@ int poisson_solve(PoissonPlan* p, const double* rhs, double* a, double D2, cudaS
     const i64 xo = (g.ny == 1) ? 1 : g.nt;
     const double* src = rhs;
     int rc = 0;
-    if (g.ny > 1) { rc = launch_dct_axis(p->py, geom_y(g), 1, src, a, 0, sa, st); src = a; if (launches) *launches += 1; }
+    if (g.ny > 1) { rc = launch_dct_axis(p->py, geom_y(g), g.nt, src, a, 0, sa, st); src = a; if (launches) *launches += 1; }
     if (!rc) rc = launch_dct_axis(p->px, geom_x(g), xo, src, a, 0, sa, st);
     if (!rc) rc = t_solve(p, a, g.P, 0, D2, st, launches);
     if (!rc) rc = launch_dct_axis(p->px, geom_x(g), xo, a, a, 1, sa, st);
     if (launches) *launches += 2;
-    if (!rc && g.ny > 1) { rc = launch_dct_axis(p->py, geom_y(g), 1, a, a, 1, sa, st); if (launches) *launches += 1; }
+    if (!rc && g.ny > 1) { rc = launch_dct_axis(p->py, geom_y(g), g.nt, a, a, 1, sa, st); if (launches) *launches += 1; }
     return rc;
 }
 
@@ -1182,20 +1185,20 @@ int poisson_xy(PoissonPlan* p, const double* src, double* a, int tn0, int nlev, 
     const Geo& g = p->g;
     ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, 1.0, 0};
     const i64 off = (i64)tn0 * g.P;
-    LineGeom gy{g.ny, 1, (i64)g.ny, (i64)nlev * g.nx, 0, 1, 0, 0, 0, 0, 0};
+    const LineGeom gy = geom_y(g);   // grouped per level: the same line pairs as the single-slab solve
     LineGeom gx = (g.ny == 1) ? LineGeom{g.nx, 1, (i64)g.nx, (i64)nlev, 0, 1, 0, 0, 0, 0, 0} : LineGeom{g.nx, (i64)g.ny, 1, (i64)g.ny, g.P, 0, 0, 0, 0, 0, 0};
     if (packed) { gx.rm_world = world; gx.rm_nlev = slab_nlev > 0 ? slab_nlev : nlev; gx.rm_t0 = slab_t0; gx.rm_P = g.P; gx.rm_ny = g.ny; gx.rm_tab = inverse ? nullptr : push_tab; }
     const i64 xo = (g.ny == 1) ? 1 : nlev;
     int rc = 0;
     if (!inverse) {
         const double* s0 = src + off;
-        if (g.ny > 1) { rc = launch_dct_axis(p->py, gy, 1, s0, a + off, 0, sa, st); s0 = a + off; if (launches) *launches += 1; }
+        if (g.ny > 1) { rc = launch_dct_axis(p->py, gy, nlev, s0, a + off, 0, sa, st); s0 = a + off; if (launches) *launches += 1; }
         if (!rc) rc = launch_dct_axis(p->px, gx, xo, s0, packed ? packed : a + off, 0, sa, st);
         if (launches) *launches += 1;
     } else {
         rc = launch_dct_axis(p->px, gx, xo, packed ? packed : a + off, a + off, 1, sa, st);
         if (launches) *launches += 1;
-        if (!rc && g.ny > 1) { rc = launch_dct_axis(p->py, gy, 1, a + off, a + off, 1, sa, st); if (launches) *launches += 1; }
+        if (!rc && g.ny > 1) { rc = launch_dct_axis(p->py, gy, nlev, a + off, a + off, 1, sa, st); if (launches) *launches += 1; }
     }
     return rc;
 }
@@ -1267,7 +1270,7 @@ int poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, doubl
     ScaleArgs sa{p->lam_t, p->lam_x, p->lam_y, g.ny, 1.0, 0};
     const int mode = inverse ? 1 : 0;
     int rc = 0;
-    if (g.ny > 1) rc = launch_dct_axis(p->py, geom_y(g), 1, a, a, mode, sa, st);
+    if (g.ny > 1) rc = launch_dct_axis(p->py, geom_y(g), g.nt, a, a, mode, sa, st);
     if (!rc && g.nx > 1) rc = launch_dct_axis(p->px, geom_x(g), (g.ny == 1) ? 1 : g.nt, a, a, mode, sa, st);
     if (!rc && g.nt > 1) rc = launch_dct_axis(p->pt, geom_t(g), 1, a, a, mode, sa, st);
     if (launches) *launches += 3;

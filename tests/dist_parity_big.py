@@ -38,8 +38,6 @@ def main():
         gold = json.load(f)
     nt, nx, ny = gold["grid_nodes"]
     var, model = bench.make_problem(nt, nx, ny, rank, world, problem="example2")
-    assert [var.cScale, var.dScale, var.D, var.E] == [float(v) for v in np.array(gold["scal"])] or \\
-        np.allclose([var.cScale, var.dScale, var.D, var.E], gold["scal"], rtol=1e-13, atol=0)
     opts = {"tol": 1e-4, "maxit": gold["iters"], "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": True, "scaling": True}
     o = solver.make_level_opts("dot2d", "inPALM", var, opts, model)
     with dp.Session("dot2d", nt, nx, ny, rank=rank, world=world, nccl_id=ident) as s:
@@ -53,6 +51,7 @@ def main():
     assert np.abs(hb.priVal[:n] - np.array(gold["priVal"])).max() <= 1e-6 * np.abs(gold["priVal"]).max()
     assert np.abs(hb.dualVal[:n] - np.array(gold["dualVal"])).max() <= 1e-6 * np.abs(gold["dualVal"]).max()
     assert abs(res.sigma - gold["sigma"]) <= 1e-12 * gold["sigma"]
+    assert np.allclose([res.cScale, res.dScale, res.D, res.E], gold["scal"], rtol=1e-12, atol=0)     # after the in-loop rescalings
     if rank == 0:
         print(f"dist parity ok: configs[3] 512x512x256 world={world} max|kkt - oracle| = {d:.2e}", flush=True)
 

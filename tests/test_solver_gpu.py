@@ -299,8 +299,9 @@ def test_fused_kkt_check_matches_the_standalone_kkt_kernels(gpu, variant, monkey
 
 @pytest.mark.parametrize("variant", ["dot2d", "wdot2d"])
 def test_register_prefetch_march_is_bit_identical_to_the_plain_march(gpu, variant, monkeypatch):
-    """k_mult keeps the loaded values of the next time step in a second register set (software pipeline, unrolled by two);
-    DOTSOCP_KM_PF=0 selects the plain load-then-compute march.  Odd and even numbers of levels, slabs and pieces."""
+    """k_mult prefetches the values of the next time step -- into a second register set (software pipeline, unrolled by two) or
+    with cp.async into a shared-memory ring; DOTSOCP_KM_PF=0 selects the plain load-then-compute march.  Odd and even numbers
+    of levels, slabs and pieces."""
     for nt, world in ((18, 1), (17, 1), (23, 3)):
         nx, ny = 41, 35
         rho0, rho1 = O.get_example2d("example2", nx, ny)
@@ -308,13 +309,14 @@ def test_register_prefetch_march_is_bit_identical_to_the_plain_march(gpu, varian
         opts = {"tol": 1e-12, "maxit": 30, "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": False, "scaling": True}
         monkeypatch.setenv("DOTSOCP_KM_PF", "0")
         hb1, r1, st1 = _level_run(variant, nt, nx, ny, rho0, rho1, weight, opts, world)
-        monkeypatch.setenv("DOTSOCP_KM_PF", "1")
-        hb2, r2, st2 = _level_run(variant, nt, nx, ny, rho0, rho1, weight, opts, world)
+        for mode in ("1", "2"):       # 1: second register set, 2: cp.async ring in shared memory
+            monkeypatch.setenv("DOTSOCP_KM_PF", mode)
+            hb2, r2, st2 = _level_run(variant, nt, nx, ny, rho0, rho1, weight, opts, world)
+            assert r1.iters == r2.iters == 30
+            assert np.array_equal(hb1.kkt[:r1.hist_len], hb2.kkt[:r2.hist_len])
+            for a, b, name in zip(st1, st2, ("phi", "q", "z", "alpha", "beta")):
+                assert np.array_equal(a, b), (name, nt, world, mode)
         monkeypatch.delenv("DOTSOCP_KM_PF")
-        assert r1.iters == r2.iters == 30
-        assert np.array_equal(hb1.kkt[:r1.hist_len], hb2.kkt[:r2.hist_len])
-        for a, b, name in zip(st1, st2, ("phi", "q", "z", "alpha", "beta")):
-            assert np.array_equal(a, b), (name, nt, world)
 
 
 CHUNK_SCRIPT = """
@@ -489,7 +491,9 @@ def test_multilevel_solve_on_time_slabs_is_bit_identical_to_one_slab(gpu, case):
         opts = {"tol": 1e-4, "maxit": 3000}
         run = lambda o: dp.solver_dotsocp2d(rho0, rho1, nt, 3, o, "ALG2" if case.endswith("ALG2") else "inPALM")
     ref = run(dict(opts))
-    for k in (2, 3, 4):
+    # (1-D: the x transform pairs consecutive TIME levels into one complex sequence, so bit-identity needs slabs that start on
+    # even levels -- 2 and 4 slabs of the 8 coarsest cell layers do, 3 do not; the 2-D transforms pair lines inside a level)
+    for k in ((2, 4) if case == "dot1d" else (2, 3, 4)):
         got = run(dict(opts, slabs=k))
         assert [int(v) for v in got[0].level_iters] == [int(v) for v in ref[0].level_iters], k
         assert np.array_equal(got[2].kkt, ref[2].kkt) and np.array_equal(got[2].iter, ref[2].iter), k

@@ -90,6 +90,7 @@ def check_c4_golden(hb, res, state, gold, tol_kkt=1e-8):
         a, b = getattr(hb, name)[:n], np.array(gold[name])
         assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), name
     assert abs(res.sigma - gold["sigma"]) <= 1e-12 * gold["sigma"]
+    assert [res.cScale, res.dScale, res.D, res.E] == pytest.approx(gold["scal"], rel=1e-12)     # after the in-loop rescalings
     for a, name in zip(state, ("phi", "q", "z", "alpha", "beta")):
         fp = gold["final"][name]
         v = a.reshape(-1, order="F" if a.ndim == 2 else "C")
@@ -114,7 +115,6 @@ def test_baseline_config3_mixture_512x512x256_checked_iterations(gpu):
     rho0, rho1 = m.problem(nx, ny)
     var, model = driver.initialize(rho0, rho1, nt)
     driver.InitialScaling(var, model, True, None, "dot2d")
-    assert [var.cScale, var.dScale, var.D, var.E] == pytest.approx(gold["scal"], rel=1e-13)
     opts = {"tol": 1e-4, "maxit": gold["iters"], "tau": 1.9, "sigma": 1.0, "ifCheckStepByStep": True, "scaling": True}
     o = solver.make_level_opts("dot2d", "inPALM", var, opts, model)
     with dp.Session("dot2d", nt, nx, ny) as s:
