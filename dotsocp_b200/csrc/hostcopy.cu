@@ -162,30 +162,41 @@ void HostCopier::par_memcpy(char* dst, const char* src, size_t bytes)
     });
 }
 
-int HostCopier::h2d(void* dev, const void* host, size_t bytes, cudaStream_t st)
+// One implementation for flat and row-pitched transfers: the host side is always contiguous (rows * width bytes), cut into
+// chunks of whole rows; the device side is either the same bytes (dpitch == width: one 1-D copy per chunk) or rows dpitch
+// bytes apart (one 2-D copy per chunk).
+int HostCopier::h2d_impl(char* d, size_t dpitch, const char* h, size_t width, size_t rows, cudaStream_t st)
 {
     std::lock_guard<std::mutex> lk(mu_);
-    char* d = (char*)dev;
-    const char* h = (const char*)host;
-    for (size_t off = 0; off < bytes; off += chunk_) {
-        const size_t len = std::min(chunk_, bytes - off);
+    const bool flat = dpitch == width;
+    if (!flat && width > chunk_) return (int)cudaErrorInvalidValue;
+    const size_t rpc = flat ? rows : chunk_ / width;                 // rows per chunk (flat: bytes are cut freely below)
+    const size_t bytes = width * rows;
+    for (size_t off = 0, r0 = 0; off < bytes;) {
+        const size_t len = flat ? std::min(chunk_, bytes - off) : std::min(rpc, rows - r0) * width;
         const int b = cursor_;
         cursor_ = (cursor_ + 1) % NBUF;
         cudaError_t e;
         if (busy_[b] && (e = cudaEventSynchronize(ev_[b])) != cudaSuccess) return (int)e;
         par_memcpy(pinned_[b], h + off, len);
-        if ((e = cudaMemcpyAsync(d + off, pinned_[b], len, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
+        if (flat) e = cudaMemcpyAsync(d + off, pinned_[b], len, cudaMemcpyHostToDevice, st);
+        else e = cudaMemcpy2DAsync(d + r0 * dpitch, dpitch, pinned_[b], width, width, len / width, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return (int)e;
         if ((e = cudaEventRecord(ev_[b], st)) != cudaSuccess) return (int)e;
         busy_[b] = true;
+        off += len;
+        r0 += len / width;
     }
     return 0;
 }
 
-int HostCopier::d2h(void* host, const void* dev, size_t bytes, cudaStream_t st)
+int HostCopier::d2h_impl(char* h, const char* d, size_t dpitch, size_t width, size_t rows, cudaStream_t st)
 {
     std::lock_guard<std::mutex> lk(mu_);
-    char* h = (char*)host;
-    const char* d = (const char*)dev;
+    const bool flat = dpitch == width;
+    if (!flat && width > chunk_) return (int)cudaErrorInvalidValue;
+    const size_t rpc = flat ? rows : chunk_ / width;
+    const size_t bytes = width * rows;
     struct Item { int b; size_t off, len; };
     std::deque<Item> fifo;
     auto drain_one = [&]() -> int {
@@ -197,8 +208,8 @@ int HostCopier::d2h(void* host, const void* dev, size_t bytes, cudaStream_t st)
         busy_[it.b] = false;
         return 0;
     };
-    for (size_t off = 0; off < bytes; off += chunk_) {
-        const size_t len = std::min(chunk_, bytes - off);
+    for (size_t off = 0, r0 = 0; off < bytes;) {
+        const size_t len = flat ? std::min(chunk_, bytes - off) : std::min(rpc, rows - r0) * width;
         const int b = cursor_;
         cursor_ = (cursor_ + 1) % NBUF;
         cudaError_t e;
@@ -206,14 +217,35 @@ int HostCopier::d2h(void* host, const void* dev, size_t bytes, cudaStream_t st)
             if (!fifo.empty() && fifo.front().b == b) { int rc = drain_one(); if (rc) return rc; }
             else if ((e = cudaEventSynchronize(ev_[b])) != cudaSuccess) return (int)e;
         }
-        if ((e = cudaMemcpyAsync(pinned_[b], d + off, len, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+        if (flat) e = cudaMemcpyAsync(pinned_[b], d + off, len, cudaMemcpyDeviceToHost, st);
+        else e = cudaMemcpy2DAsync(pinned_[b], width, d + r0 * dpitch, dpitch, width, len / width, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return (int)e;
         if ((e = cudaEventRecord(ev_[b], st)) != cudaSuccess) return (int)e;
         busy_[b] = true;
         fifo.push_back({b, off, len});
+        off += len;
+        r0 += len / width;
         if ((int)fifo.size() >= NBUF - 1) { int rc = drain_one(); if (rc) return rc; }
     }
     while (!fifo.empty()) { int rc = drain_one(); if (rc) return rc; }
     return 0;
+}
+
+int HostCopier::h2d(void* dev, const void* host, size_t bytes, cudaStream_t st)
+{
+    return h2d_impl((char*)dev, bytes, (const char*)host, bytes, bytes ? 1 : 0, st);
+}
+int HostCopier::d2h(void* host, const void* dev, size_t bytes, cudaStream_t st)
+{
+    return d2h_impl((char*)host, (const char*)dev, bytes, bytes, bytes ? 1 : 0, st);
+}
+int HostCopier::h2d_rows(void* dev, size_t dpitch, const void* host, size_t width, size_t rows, cudaStream_t st)
+{
+    return h2d_impl((char*)dev, dpitch, (const char*)host, width, rows, st);
+}
+int HostCopier::d2h_rows(void* host, const void* dev, size_t dpitch, size_t width, size_t rows, cudaStream_t st)
+{
+    return d2h_impl((char*)host, (const char*)dev, dpitch, width, rows, st);
 }
 
 }  // namespace dsocp

@@ -49,6 +49,10 @@ public:
     // only after the copy, which later calls check by event).
     int h2d(void* dev, const void* host, size_t bytes, cudaStream_t st);
     int d2h(void* host, const void* dev, size_t bytes, cudaStream_t st);
+    // `rows` rows of `width` bytes: packed on the host, `dpitch` bytes apart on the device (the pitched device layout of the
+    // staggered arrays, common.cuh); same staging, the copy engine does the strided side (cudaMemcpy2DAsync)
+    int h2d_rows(void* dev, size_t dpitch, const void* host, size_t width, size_t rows, cudaStream_t st);
+    int d2h_rows(void* host, const void* dev, size_t dpitch, size_t width, size_t rows, cudaStream_t st);
     WorkerPool& pool() { return *pool_; }
     bool ok() const { return ok_; }
     ~HostCopier();
@@ -56,6 +60,8 @@ public:
 private:
     HostCopier();
     void par_memcpy(char* dst, const char* src, size_t bytes);
+    int h2d_impl(char* dev, size_t dpitch, const char* host, size_t width, size_t rows, cudaStream_t st);
+    int d2h_impl(char* host, const char* dev, size_t dpitch, size_t width, size_t rows, cudaStream_t st);
     static constexpr int NBUF = 4;
     size_t chunk_ = 0;
     char* pinned_[NBUF] = {nullptr, nullptr, nullptr, nullptr};

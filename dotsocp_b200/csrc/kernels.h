@@ -143,6 +143,7 @@ void launch_prolong_beta(const Geo& gc, const Geo& gf, double rec, const double*
 void launch_mul_inplace(double* x, i64 n, double s, cudaStream_t st);
 void launch_prolong_alpha(double* alpha, const double* weight, i64 n, double scale, cudaStream_t st);
 void launch_scale(double* x, i64 n, double mul, double div, cudaStream_t st);
+void launch_fill(double* x, i64 n, double v, cudaStream_t st);   // x[0..n) = v
 // Halpern / affine extrapolation of solver_socp_accADMM.m:371-388:
 //   x = c1*x0 + c2*((1-rho)*xold + rho*x) ; xold = x ; if (copy_anchor) x0 = x
 void launch_halpern(double* x, double* xold, double* x0, i64 n, double c1, double c2, double rho, bool copy_anchor,

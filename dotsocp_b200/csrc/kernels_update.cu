@@ -88,7 +88,7 @@ __device__ __forceinline__ void load_z(const Geo& g, const IterScal& sc, const d
                                        const double* __restrict__ q_old, const double* __restrict__ beta_old, int t, int x,
                                        int y, double (&z)[10])
 {
-    const i64 L = g.L, c = (i64)t * g.P + (i64)x * g.ny + y;
+    const i64 L = g.L, c = (i64)t * g.PC + (i64)x * g.py + y;
     if (zmat != nullptr) {
 #pragma unroll
         for (int j = 0; j < 10; j++) z[j] = (ONE_D && j >= 5 && j <= 8) ? 0.0 : zmat[(i64)j * L + c];
@@ -97,12 +97,12 @@ __device__ __forceinline__ void load_z(const Geo& g, const IterScal& sc, const d
     const bool hxm = x > 0, hxp = x < g.nx - 1, hym = y > 0, hyp = y < g.ny - 1;
     const double* bx = q_old + L;
     const double* by = bx + g.NBX;
-    const i64 ox = (i64)t * g.PBX + (i64)x * g.ny + y, oy = (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
+    const i64 ox = (i64)t * g.PBX + (i64)x * g.py + y, oy = (i64)t * g.PBY + (i64)x * g.pyb + y;
     CellQ cq;
     cq.q0 = q_old[c];
-    cq.bxm = hxm ? bx[ox - g.ny] : 0.0;
+    cq.bxm = hxm ? bx[ox - g.py] : 0.0;
     cq.bx = hxp ? bx[ox] : 0.0;
-    cq.bxm1 = hxm ? bx[ox + g.PBX - g.ny] : 0.0;
+    cq.bxm1 = hxm ? bx[ox + g.PBX - g.py] : 0.0;
     cq.bx1 = hxp ? bx[ox + g.PBX] : 0.0;
     cq.bym = hym ? by[oy - 1] : 0.0;
     cq.by = hyp ? by[oy] : 0.0;
@@ -122,29 +122,30 @@ __global__ void __launch_bounds__(256) k_bfd(Geo g, double S, double SF, double 
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
-    if (p >= g.P) return;
-    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
-    const i64 c = (i64)t * g.P + p;
+    const PlanePos pp = plane_pos(g, p);
+    if (!pp.ok) return;
+    const int x = pp.x, y = pp.y;
+    const i64 c = (i64)t * g.PC + p;
     const double* bx = q + g.L;
     const double* by = bx + g.NBX;
     const double pr = dmul(q[c], S);
     z[c] = dsub(DF, pr);
     z[9 * g.L + c] = dadd(pr, DF);
     if (x >= 1) {
-        z[1 * g.L + c] = dmul(bx[(i64)t * g.PBX + (i64)(x - 1) * g.ny + y], SF);
-        z[3 * g.L + c] = dmul(bx[(i64)(t + 1) * g.PBX + (i64)(x - 1) * g.ny + y], SF);
+        z[1 * g.L + c] = dmul(bx[(i64)t * g.PBX + (i64)(x - 1) * g.py + y], SF);
+        z[3 * g.L + c] = dmul(bx[(i64)(t + 1) * g.PBX + (i64)(x - 1) * g.py + y], SF);
     }
     if (x <= g.nx - 2) {
-        z[2 * g.L + c] = dmul(bx[(i64)t * g.PBX + (i64)x * g.ny + y], SF);
-        z[4 * g.L + c] = dmul(bx[(i64)(t + 1) * g.PBX + (i64)x * g.ny + y], SF);
+        z[2 * g.L + c] = dmul(bx[(i64)t * g.PBX + (i64)x * g.py + y], SF);
+        z[4 * g.L + c] = dmul(bx[(i64)(t + 1) * g.PBX + (i64)x * g.py + y], SF);
     }
     if (y >= 1) {
-        z[5 * g.L + c] = dmul(by[(i64)t * g.PBY + (i64)x * (g.ny - 1) + (y - 1)], SF);
-        z[7 * g.L + c] = dmul(by[(i64)(t + 1) * g.PBY + (i64)x * (g.ny - 1) + (y - 1)], SF);
+        z[5 * g.L + c] = dmul(by[(i64)t * g.PBY + (i64)x * g.pyb + (y - 1)], SF);
+        z[7 * g.L + c] = dmul(by[(i64)(t + 1) * g.PBY + (i64)x * g.pyb + (y - 1)], SF);
     }
     if (y <= g.ny - 2) {
-        z[6 * g.L + c] = dmul(by[(i64)t * g.PBY + (i64)x * (g.ny - 1) + y], SF);
-        z[8 * g.L + c] = dmul(by[(i64)(t + 1) * g.PBY + (i64)x * (g.ny - 1) + y], SF);
+        z[6 * g.L + c] = dmul(by[(i64)t * g.PBY + (i64)x * g.pyb + y], SF);
+        z[8 * g.L + c] = dmul(by[(i64)(t + 1) * g.PBY + (i64)x * g.pyb + y], SF);
     }
 }
 
@@ -158,7 +159,7 @@ static double host_sf(double S)
 
 void launch_bfd(const Geo& g, double S, double DF, const double* q, double* z, cudaStream_t st)
 {
-    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)(g.nt - 1));
+    dim3 grid((unsigned)((g.PC + 255) / 256), (unsigned)(g.nt - 1));
     k_bfd<<<grid, 256, 0, st>>>(g, S, host_sf(S), DF, q, z);
 }
 
@@ -174,25 +175,26 @@ __global__ void __launch_bounds__(256) k_bfdconj(Geo g, int tn0, double S, doubl
     auto Z = [&](i64 idx) -> double { return ADD2 ? dadd(za[idx], zb[idx]) : za[idx]; };
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int t = tn0 + blockIdx.y;
-    if (p >= g.P) return;
-    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    const PlanePos pp = plane_pos(g, p);
+    if (!pp.ok) return;
+    const int x = pp.x, y = pp.y;
     const i64 L = g.L;
-    const i64 cu = (i64)t * g.P + p;         // cell (t,x,y)
-    const i64 cd = cu - g.P;                 // cell (t-1,x,y)
+    const i64 cu = (i64)t * g.PC + p;        // cell (t,x,y)
+    const i64 cd = cu - g.PC;                // cell (t-1,x,y)
     const bool up = t < g.nt - 1, dn = t > 0;
     if (up) q2[cu] = dmul(dsub(Z(9 * L + cu), Z(cu)), S);
     if (x < g.nx - 1) {
         double s;
         if (!dn)
-            s = dadd(Z(1 * L + cu + g.ny), Z(2 * L + cu));
+            s = dadd(Z(1 * L + cu + g.py), Z(2 * L + cu));
         else if (!up)
-            s = dadd(Z(3 * L + cd + g.ny), Z(4 * L + cd));
+            s = dadd(Z(3 * L + cd + g.py), Z(4 * L + cd));
         else {
-            s = dadd(Z(1 * L + cu + g.ny), Z(2 * L + cu));
-            s = dadd(s, Z(3 * L + cd + g.ny));
+            s = dadd(Z(1 * L + cu + g.py), Z(2 * L + cu));
+            s = dadd(s, Z(3 * L + cd + g.py));
             s = dadd(s, Z(4 * L + cd));
         }
-        q2[L + (i64)t * g.PBX + (i64)x * g.ny + y] = dmul(s, SF);
+        q2[L + (i64)t * g.PBX + p] = dmul(s, SF);
     }
     if (y < g.ny - 1) {
         double s;
@@ -205,19 +207,19 @@ __global__ void __launch_bounds__(256) k_bfdconj(Geo g, int tn0, double S, doubl
             s = dadd(s, Z(7 * L + cd + 1));
             s = dadd(s, Z(8 * L + cd));
         }
-        q2[L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y] = dmul(s, SF);
+        q2[L + g.NBX + (i64)t * g.PBY + (i64)x * g.pyb + y] = dmul(s, SF);
     }
 }
 
 void launch_bfdconj(const Geo& g, double S, const double* z, double* q2, cudaStream_t st, const TRange* tr)
 {
     const int tn0 = tr ? tr->tn0 : 0, tn1 = tr ? tr->tn1 : g.nt;
-    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)(tn1 - tn0));
+    dim3 grid((unsigned)((g.PC + 255) / 256), (unsigned)(tn1 - tn0));
     k_bfdconj<false><<<grid, 256, 0, st>>>(g, tn0, S, host_sf(S), z, nullptr, q2);
 }
 void launch_bfdconj_sum(const Geo& g, double S, const double* za, const double* zb, double* q2, cudaStream_t st)
 {
-    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)g.nt);
+    dim3 grid((unsigned)((g.PC + 255) / 256), (unsigned)g.nt);
     k_bfdconj<true><<<grid, 256, 0, st>>>(g, 0, S, host_sf(S), za, zb, q2);
 }
 
@@ -337,30 +339,31 @@ __global__ void __launch_bounds__(256) k_qstep(Geo g, int tn0, IterScal sc, cons
     double ks[KQ_COUNT];
 #pragma unroll
     for (int k = 0; k < KQ_COUNT; k++) ks[k] = 0.0;
-    if (p < g.P) {
-        const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
-        const i64 n = (i64)t * g.P + p;
+    const PlanePos pp = plane_pos(g, p);
+    if (pp.ok) {
+        const int x = pp.x, y = pp.y;
+        const i64 n = (i64)t * g.P + pp.pn;
         const double ph = phi[n];
         const bool edge_t = (t == 0) || (t == g.nt - 1);
         if (t < g.nt - 1) {
             const double aphi = dadd(dmul(-sc.gt, ph), dmul(sc.gt, phi[n + g.P]));
-            q_update<WEIGHTED, ACC, KKT>(n, aphi, sc.dinv1, sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in, tmpq_out, upd_alpha, ks);
+            q_update<WEIGHTED, ACC, KKT>((i64)t * g.PC + p, aphi, sc.dinv1, sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in, tmpq_out, upd_alpha, ks);
         }
         if (x < g.nx - 1) {
             const double aphi = dadd(dmul(-sc.gx, ph), dmul(sc.gx, phi[n + g.ny]));
-            q_update<WEIGHTED, ACC, KKT>(g.L + (i64)t * g.PBX + (i64)x * g.ny + y, aphi, edge_t ? sc.dinv2 : sc.dinv1,
+            q_update<WEIGHTED, ACC, KKT>(g.L + (i64)t * g.PBX + p, aphi, edge_t ? sc.dinv2 : sc.dinv1,
                                          edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout, tmpq_in, tmpq_out, upd_alpha, ks);
         }
         if (y < g.ny - 1) {
             const double aphi = dadd(dmul(-sc.gy, ph), dmul(sc.gy, phi[n + 1]));
-            q_update<WEIGHTED, ACC, KKT>(g.L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y, aphi,
+            q_update<WEIGHTED, ACC, KKT>(g.L + g.NBX + (i64)t * g.PBY + (i64)x * g.pyb + y, aphi,
                                          edge_t ? sc.dinv2 : sc.dinv1, edge_t ? sc.s2x1 : sc.s2x2, sc, q2, weight, alpha, qout,
                                          tmpq_in, tmpq_out, upd_alpha, ks);
         }
         if (KKT) {
             double cv = 0.0;
-            if (t == 0) cv = c0[p];
-            else if (t == g.nt - 1) cv = c1[p];
+            if (t == 0) cv = c0[pp.pn];
+            else if (t == g.nt - 1) cv = c1[pp.pn];
             ks[KQ_CPHI] = cv * ph;
             ks[KQ_PHI2] = ph * ph;
         }
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(256) k_qstep(Geo g, int tn0, IterScal sc, cons
 void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st, const double* tmpq_in, double* tmpq_out,
                   bool upd_alpha, const KktFused* kkt)
 {
-    dim3 grid((unsigned)((a.g.P + 255) / 256), (unsigned)(a.tr.tn1 - a.tr.tn0));
+    dim3 grid((unsigned)((a.g.PC + 255) / 256), (unsigned)(a.tr.tn1 - a.tr.tn0));
     if (grid.y == 0) return;
 #define QS(W, A, K)                                                                                                          \
     k_qstep<W, A, K><<<grid, 256, 0, st>>>(a.g, a.tr.tn0, a.sc, a.phi, a.q2, a.weight, a.alpha, a.q_new, tmpq_in, tmpq_out, \
@@ -485,9 +488,10 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
     const bool hxm = EDGE ? (valid && x > 0) : true, hxp = EDGE ? (valid && x < g.nx - 1) : true;
     const bool hym = EDGE ? (valid && y > 0) : true, hyp = EDGE ? (valid && y < g.ny - 1) : true;
     const i64 L = g.L;
-    const i64 node = (i64)x * g.ny + y;
-    const i64 ibx = (i64)x * g.ny + y, ibxm = ibx - g.ny;
-    const i64 iby = (i64)x * (g.ny - 1) + y, ibym = iby - 1;
+    const i64 node = (i64)x * g.ny + y;            // inside a node plane (rhs, c)
+    const i64 cellp = (i64)x * g.py + y;           // inside a cell / q0 plane
+    const i64 ibx = cellp, ibxm = ibx - g.py;
+    const i64 iby = (i64)x * g.pyb + y, ibym = iby - 1;
     const double* __restrict__ qo_bx = qo + L;
     const double* __restrict__ qo_by = qo_bx + g.NBX;
     const double* __restrict__ qn_bx = qn + L;
@@ -526,7 +530,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
     // ---- LOAD: everything step t reads from HBM, and nothing else ------------------------------------------------------
     auto load = [&](int t, MultLoad& ld) {
         const bool cell = t < g.nt - 1;
-        const i64 cidx = (i64)t * g.P + node;
+        const i64 cidx = (i64)t * g.PC + cellp;
         ld.al_xm = ld.al_x = ld.al_ym = ld.al_y = 0.0;
         ld.wt0 = ld.wt_xm = ld.wt_x = ld.wt_ym = ld.wt_y = 1.0;
         ld.cv = 0.0;
@@ -576,7 +580,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         const bool cell = t < g.nt - 1;
         if (cell && valid) {
             double* dst = ring + (size_t)(t & 1) * NF * NT_ + tid_;
-            const i64 cidx = (i64)t * g.P + node;
+            const i64 cidx = (i64)t * g.PC + cellp;
             const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
 #pragma unroll
             for (int j = 0; j < 10; j++)
@@ -600,7 +604,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
     // ---- phase 1 of step t into exchange slot (buf, u) ---------------------------------------------------------------
     auto phase1 = [&](int t, int buf, int u, const MultLoad& ld, MultKeep& k, MultKeepK& kk) {
         const bool cell = t < g.nt - 1;
-        const i64 cidx = (i64)t * g.P + node;
+        const i64 cidx = (i64)t * g.PC + cellp;
         double w[10];
 #pragma unroll
         for (int j = 0; j < 10; j++) w[j] = 0.0;
@@ -751,7 +755,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         if (!owner) return;
         const bool cell = t < g.nt - 1;
         const bool emit = t >= tr.tn0;      // false only on the replayed ghost layer
-        const i64 cidx = (i64)t * g.P + node;
+        const i64 cidx = (i64)t * g.PC + cellp;
         const double w1n = cell ? sh[buf][u][0][lx + 1][ly] : 0.0, w3n = cell ? sh[buf][u][1][lx + 1][ly] : 0.0;
         const double w5n = cell ? sh[buf][u][2][lx][ly + 1] : 0.0, w7n = cell ? sh[buf][u][3][lx][ly + 1] : 0.0;
         // rhs = A' u + c : CSR-transpose row order (t-1 edge, t edge, x-1, x, y-1, y)
@@ -791,7 +795,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
             if (emit) q2_by[(i64)t * g.PBY + iby] = dmul(s, sc.SF);
             wp7n = w7n;
         }
-        if (emit) rhs[cidx] = dadd(first ? 0.0 : acc, k.cv);
+        if (emit) rhs[(i64)t * g.P + node] = dadd(first ? 0.0 : acc, k.cv);
         u0p = k.u0;
         wp4 = k.w4;
         wp8 = k.w8;
@@ -1041,9 +1045,10 @@ __global__ void __launch_bounds__(256) k_rhs(Geo g, IterScal sc, const double* _
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
-    if (p >= g.P) return;
-    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
-    const i64 L = g.L, n = (i64)t * g.P + p;
+    const PlanePos pp = plane_pos(g, p);
+    if (!pp.ok) return;
+    const int x = pp.x, y = pp.y;
+    const i64 L = g.L, n = (i64)t * g.PC + p;      // cell (t,x,y) == q0 edge above the node
     const bool up = t < g.nt - 1, dn = t > 0;
     auto u = [&](i64 e) -> double { return uval<WEIGHTED>(q[e], alpha[e], WEIGHTED ? weight[e] : 1.0); };
     double acc = 0.0;
@@ -1054,23 +1059,23 @@ __global__ void __launch_bounds__(256) k_rhs(Geo g, IterScal sc, const double* _
         acc = first ? tv_ : dadd(acc, tv_);  \
         first = false;                       \
     }
-    if (dn) ADDTERM(dmul(sc.gt, u(n - g.P)));
+    if (dn) ADDTERM(dmul(sc.gt, u(n - g.PC)));
     if (up) ADDTERM(dmul(-sc.gt, u(n)));
-    const i64 ox = L + (i64)t * g.PBX + (i64)x * g.ny + y, oy = L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
-    if (x > 0) ADDTERM(dmul(sc.gx, u(ox - g.ny)));
+    const i64 ox = L + (i64)t * g.PBX + p, oy = L + g.NBX + (i64)t * g.PBY + (i64)x * g.pyb + y;
+    if (x > 0) ADDTERM(dmul(sc.gx, u(ox - g.py)));
     if (x < g.nx - 1) ADDTERM(dmul(-sc.gx, u(ox)));
     if (y > 0) ADDTERM(dmul(sc.gy, u(oy - 1)));
     if (y < g.ny - 1) ADDTERM(dmul(-sc.gy, u(oy)));
 #undef ADDTERM
     double cv = 0.0;
-    if (t == 0) cv = c0[p];
-    else if (!up) cv = c1[p];
-    rhs[n] = dadd(first ? 0.0 : acc, cv);
+    if (t == 0) cv = c0[pp.pn];
+    else if (!up) cv = c1[pp.pn];
+    rhs[(i64)t * g.P + pp.pn] = dadd(first ? 0.0 : acc, cv);
 }
 void launch_rhs(const Geo& g, const IterScal& sc, bool weighted, const double* q, const double* alpha, const double* weight,
                 const double* c0, const double* c1, double* rhs, cudaStream_t st)
 {
-    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)g.nt);
+    dim3 grid((unsigned)((g.PC + 255) / 256), (unsigned)g.nt);
     if (weighted) k_rhs<true><<<grid, 256, 0, st>>>(g, sc, q, alpha, weight, c0, c1, rhs);
     else k_rhs<false><<<grid, 256, 0, st>>>(g, sc, q, alpha, weight, c0, c1, rhs);
 }
@@ -1084,18 +1089,19 @@ __global__ void __launch_bounds__(256) k_cells_update(Geo g, IterScal sc, const 
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
-    if (p >= g.P) return;
-    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    const PlanePos pp = plane_pos(g, p);
+    if (!pp.ok) return;
+    const int x = pp.x, y = pp.y;
     const bool hxm = x > 0, hxp = x < g.nx - 1, hym = y > 0, hyp = y < g.ny - 1;
-    const i64 L = g.L, c = (i64)t * g.P + p;
+    const i64 L = g.L, c = (i64)t * g.PC + p;
     const double* bx = q + L;
     const double* by = bx + g.NBX;
-    const i64 ox = (i64)t * g.PBX + (i64)x * g.ny + y, oy = (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
+    const i64 ox = (i64)t * g.PBX + p, oy = (i64)t * g.PBY + (i64)x * g.pyb + y;
     CellQ cq;
     cq.q0 = q[c];
-    cq.bxm = hxm ? bx[ox - g.ny] : 0.0;
+    cq.bxm = hxm ? bx[ox - g.py] : 0.0;
     cq.bx = hxp ? bx[ox] : 0.0;
-    cq.bxm1 = hxm ? bx[ox + g.PBX - g.ny] : 0.0;
+    cq.bxm1 = hxm ? bx[ox + g.PBX - g.py] : 0.0;
     cq.bx1 = hxp ? bx[ox + g.PBX] : 0.0;
     cq.bym = hym ? by[oy - 1] : 0.0;
     cq.by = hyp ? by[oy] : 0.0;
@@ -1132,7 +1138,7 @@ __global__ void __launch_bounds__(256) k_cells_update(Geo g, IterScal sc, const 
 void launch_cells_update(const Geo& g, const IterScal& sc, bool one_d, int mode, const double* q, double* z, double* beta,
                          cudaStream_t st)
 {
-    dim3 grid((unsigned)((g.P + 255) / 256), (unsigned)(g.nt - 1));
+    dim3 grid((unsigned)((g.PC + 255) / 256), (unsigned)(g.nt - 1));
 #define CUK(O, M) k_cells_update<O, M><<<grid, 256, 0, st>>>(g, sc, q, z, beta)
     if (one_d) { if (mode == 0) CUK(true, 0); else if (mode == 1) CUK(true, 1); else CUK(true, 2); }
     else { if (mode == 0) CUK(false, 0); else if (mode == 1) CUK(false, 1); else CUK(false, 2); }
@@ -1202,18 +1208,19 @@ __global__ void __launch_bounds__(256) k_kkt_cells(KktArgs a)
     double s[KC_COUNT];
 #pragma unroll
     for (int k = 0; k < KC_COUNT; k++) s[k] = 0.0;
-    if (p < g.P) {
-        const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    const PlanePos pp = plane_pos(g, p);
+    if (pp.ok) {
+        const int x = pp.x, y = pp.y;
         const bool hxm = x > 0, hxp = x < g.nx - 1, hym = y > 0, hyp = y < g.ny - 1;
-        const i64 L = g.L, c = (i64)t * g.P + p;
+        const i64 L = g.L, c = (i64)t * g.PC + p;
         const double* bx = a.q + L;
         const double* by = bx + g.NBX;
         CellQ cq;
         cq.q0 = a.q[c];
-        const i64 ox = (i64)t * g.PBX + (i64)x * g.ny + y, oy = (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
-        cq.bxm = hxm ? bx[ox - g.ny] : 0.0;
+        const i64 ox = (i64)t * g.PBX + p, oy = (i64)t * g.PBY + (i64)x * g.pyb + y;
+        cq.bxm = hxm ? bx[ox - g.py] : 0.0;
         cq.bx = hxp ? bx[ox] : 0.0;
-        cq.bxm1 = hxm ? bx[ox + g.PBX - g.ny] : 0.0;
+        cq.bxm1 = hxm ? bx[ox + g.PBX - g.py] : 0.0;
         cq.bx1 = hxp ? bx[ox + g.PBX] : 0.0;
         cq.bym = hym ? by[oy - 1] : 0.0;
         cq.by = hyp ? by[oy] : 0.0;
@@ -1258,9 +1265,9 @@ __global__ void __launch_bounds__(256) k_kkt_cells(KktArgs a)
     block_reduce_store<KC_COUNT, 256>(s, a.partial);
 }
 
-int kkt_cells_blocks(const Geo& g) { return (int)((g.P + 255) / 256) * (g.nt - 1); }
-int kkt_nodes_blocks(const Geo& g) { return (int)((g.P + 255) / 256) * g.nt; }
-static int blocks_x(const Geo& g) { return (int)((g.P + 255) / 256); }
+int kkt_cells_blocks(const Geo& g) { return (int)((g.PC + 255) / 256) * (g.nt - 1); }
+int kkt_nodes_blocks(const Geo& g) { return (int)((g.PC + 255) / 256) * g.nt; }
+static int blocks_x(const Geo& g) { return (int)((g.PC + 255) / 256); }
 int kkt_blocks_x(const Geo& g) { return blocks_x(g); }
 
 void launch_kkt_cells(const KktArgs& a, bool weighted, bool one_d, cudaStream_t st)
@@ -1288,11 +1295,12 @@ __global__ void __launch_bounds__(256) k_zstep(Geo g, int tc0, IterScal sc, cons
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int t = tc0 + blockIdx.y;
-    if (p >= g.P) return;
-    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    const PlanePos pp = plane_pos(g, p);
+    if (!pp.ok) return;
+    const int x = pp.x, y = pp.y;
     double z[10];
     load_z<ONE_D>(g, sc, nullptr, q_old, beta_old, t, x, y, z);
-    const i64 c = (i64)t * g.P + p;
+    const i64 c = (i64)t * g.PC + p;
 #pragma unroll
     for (int j = 0; j < 10; j++)
         if (!(ONE_D && j >= 5 && j <= 8)) zout[(i64)j * g.L + c] = z[j];
@@ -1323,10 +1331,11 @@ __global__ void __launch_bounds__(256) k_norms(KktArgs a)
     double s[NR_COUNT];
 #pragma unroll
     for (int k = 0; k < NR_COUNT; k++) s[k] = 0.0;
-    if (p < g.P) {
-        const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
-        const i64 L = g.L, n = (i64)t * g.P + p;
-        const double ph = a.phi[n];
+    const PlanePos pp = plane_pos(g, p);
+    if (pp.ok) {
+        const int x = pp.x, y = pp.y;
+        const i64 L = g.L, n = (i64)t * g.PC + p;      // cell / q0 index
+        const double ph = a.phi[(i64)t * g.P + pp.pn];
         s[NR_PHI2] = ph * ph;
         auto edge = [&](i64 e) {
             const double qv = a.q[e], av = a.alpha[e];
@@ -1344,8 +1353,8 @@ __global__ void __launch_bounds__(256) k_norms(KktArgs a)
                 s[NR_BETA2] += b * b;
             }
         }
-        if (x < g.nx - 1) edge(L + (i64)t * g.PBX + (i64)x * g.ny + y);
-        if (y < g.ny - 1) edge(L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y);
+        if (x < g.nx - 1) edge(L + (i64)t * g.PBX + p);
+        if (y < g.ny - 1) edge(L + g.NBX + (i64)t * g.PBY + (i64)x * g.pyb + y);
     }
     block_reduce_store<NR_COUNT, 256>(s, a.partial);
 }
@@ -1373,9 +1382,11 @@ __global__ void __launch_bounds__(256) k_kkt_nodes(KktArgs a)
     double s[KN_COUNT];
 #pragma unroll
     for (int k = 0; k < KN_COUNT; k++) s[k] = 0.0;
-    if (p < g.P) {
-        const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
-        const i64 L = g.L, n = (i64)t * g.P + p;
+    const PlanePos ppos = plane_pos(g, p);
+    if (ppos.ok) {
+        const int x = ppos.x, y = ppos.y;
+        const i64 L = g.L, n = (i64)t * g.P + ppos.pn;   // node index
+        const i64 ce = (i64)t * g.PC + p;                // cell / q0 index
         const bool up = t < g.nt - 1, dn = t > 0;
         const bool hxm = x > 0, hxp = x < g.nx - 1, hym = y > 0, hyp = y < g.ny - 1;
         const IterScal& sc = a.sc;
@@ -1385,8 +1396,8 @@ __global__ void __launch_bounds__(256) k_kkt_nodes(KktArgs a)
         // Dalpha on the t-edges around this node and its x+1 / y+1 neighbours (for rho = pair-average in t)
         auto dal0 = [&](i64 c) -> double { return WEIGHTED ? dmul(a.weight[c], a.alpha[c]) : a.alpha[c]; };
         auto rho_at = [&](i64 pp) -> double {   // rho(t, node pp) = (rhoT[t-1] + rhoT[t]) / 2 with zero padding
-            const double lo = dn ? dmul(scD, dal0((i64)(t - 1) * g.P + pp)) : 0.0;
-            const double hi = up ? dmul(scD, dal0((i64)t * g.P + pp)) : 0.0;
+            const double lo = dn ? dmul(scD, dal0((i64)(t - 1) * g.PC + pp)) : 0.0;
+            const double hi = up ? dmul(scD, dal0((i64)t * g.PC + pp)) : 0.0;
             return dadd(lo, hi) / 2.0;
         };
         auto edge = [&](i64 e, double aphi, bool momentum, double rho_avg) {
@@ -1413,12 +1424,12 @@ __global__ void __launch_bounds__(256) k_kkt_nodes(KktArgs a)
             }
         };
         const double rho_c = rho_at(p);
-        if (up) edge(n, dadd(dmul(-sc.gt, ph), dmul(sc.gt, a.phi[n + g.P])), false, 0.0);
+        if (up) edge(ce, dadd(dmul(-sc.gt, ph), dmul(sc.gt, a.phi[n + g.P])), false, 0.0);
         if (hxp)
-            edge(L + (i64)t * g.PBX + (i64)x * g.ny + y, dadd(dmul(-sc.gx, ph), dmul(sc.gx, a.phi[n + g.ny])), true,
-                 dadd(rho_c, rho_at(p + g.ny)) / 2.0);
+            edge(L + (i64)t * g.PBX + p, dadd(dmul(-sc.gx, ph), dmul(sc.gx, a.phi[n + g.ny])), true,
+                 dadd(rho_c, rho_at(p + g.py)) / 2.0);
         if (hyp)
-            edge(L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y, dadd(dmul(-sc.gy, ph), dmul(sc.gy, a.phi[n + 1])),
+            edge(L + g.NBX + (i64)t * g.PBY + (i64)x * g.pyb + y, dadd(dmul(-sc.gy, ph), dmul(sc.gy, a.phi[n + 1])),
                  true, dadd(rho_c, rho_at(p + 1)) / 2.0);
         // dual residual A' alpha - c at the node (CSR-transpose row order)
         const double* al_bx = a.alpha + L;
@@ -1431,17 +1442,17 @@ __global__ void __launch_bounds__(256) k_kkt_nodes(KktArgs a)
         acc = first ? tv_ : dadd(acc, tv_);  \
         first = false;                       \
     }
-        if (dn) ADDTERM(dmul(sc.gt, a.alpha[n - g.P]));
-        if (up) ADDTERM(dmul(-sc.gt, a.alpha[n]));
-        const i64 ox = (i64)t * g.PBX + (i64)x * g.ny + y, oy = (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
-        if (hxm) ADDTERM(dmul(sc.gx, al_bx[ox - g.ny]));
+        if (dn) ADDTERM(dmul(sc.gt, a.alpha[ce - g.PC]));
+        if (up) ADDTERM(dmul(-sc.gt, a.alpha[ce]));
+        const i64 ox = (i64)t * g.PBX + p, oy = (i64)t * g.PBY + (i64)x * g.pyb + y;
+        if (hxm) ADDTERM(dmul(sc.gx, al_bx[ox - g.py]));
         if (hxp) ADDTERM(dmul(-sc.gx, al_bx[ox]));
         if (hym) ADDTERM(dmul(sc.gy, al_by[oy - 1]));
         if (hyp) ADDTERM(dmul(-sc.gy, al_by[oy]));
 #undef ADDTERM
         double cv = 0.0;
-        if (t == 0) cv = a.c0[p];
-        else if (!up) cv = a.c1[p];
+        if (t == 0) cv = a.c0[ppos.pn];
+        else if (!up) cv = a.c1[ppos.pn];
         const double rd = dsub(first ? 0.0 : acc, cv);
         s[KN_DUAL1] = rd * rd;
         s[KN_CPHI] = cv * ph;
@@ -1491,6 +1502,18 @@ void launch_scale(double* x, i64 n, double mul, double div, cudaStream_t st)
     i64 b = (n + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
     k_scale<<<(unsigned)b, 256, 0, st>>>(x, n, mul, div);
+}
+
+__global__ void __launch_bounds__(256) k_fill(double* __restrict__ x, i64 n, double v)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) x[i] = v;
+}
+void launch_fill(double* x, i64 n, double v, cudaStream_t st)
+{
+    if (n <= 0) return;
+    i64 b = (n + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    k_fill<<<(unsigned)b, 256, 0, st>>>(x, n, v);
 }
 
 __global__ void __launch_bounds__(256) k_halpern(double* __restrict__ x, double* __restrict__ xold, double* __restrict__ x0,

@@ -39,17 +39,18 @@ __global__ void __launch_bounds__(256) k_prolong_beta(Geo gf, Geo gc, int t0, do
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int tf = t0 + blockIdx.y;
-    if (p >= gf.P) return;
-    const int xf = (int)(p / gf.ny), yf = (int)(p - (i64)xf * gf.ny);
+    const PlanePos pp = plane_pos(gf, p);
+    if (!pp.ok) return;
+    const int xf = pp.x, yf = pp.y;
     const bool ry = gc.ny > 1;
     const int tc = tf >> 1, xc = xf >> 1, yc = ry ? (yf >> 1) : 0;
     const bool ox = xf & 1, oy = ry && (yf & 1);
 #pragma unroll 1
     for (int j = 0; j < 10; j++) {
-        const double* src = bc + (i64)j * gc.L + (i64)tc * gc.P;
-        auto V = [&](int x, int y) { return dmul(rec, src[(i64)x * gc.ny + y]); };
+        const double* src = bc + (i64)j * gc.L + (i64)tc * gc.PC;
+        auto V = [&](int x, int y) { return dmul(rec, src[(i64)x * gc.py + y]); };
         auto Y = [&](int x) { return oy ? avg2(V(x, yc), V(x, yc + 1)) : V(x, yc); };
-        bf[(i64)j * gf.L + (i64)tf * gf.P + p] = ox ? avg2(Y(xc), Y(xc + 1)) : Y(xc);
+        bf[(i64)j * gf.L + (i64)tf * gf.PC + p] = ox ? avg2(Y(xc), Y(xc + 1)) : Y(xc);
     }
 }
 
@@ -60,23 +61,25 @@ __global__ void __launch_bounds__(256) k_prolong_q(Geo g, int t0, double gt, dou
 {
     const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     const int t = t0 + blockIdx.y;
-    if (p >= g.P) return;
-    const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
-    const i64 n = (i64)t * g.P + p;
+    const PlanePos pp = plane_pos(g, p);
+    if (!pp.ok) return;
+    const int x = pp.x, y = pp.y;
+    const i64 n = (i64)t * g.P + pp.pn;
     const double ph = phi[n];
     auto put = [&](i64 e, double gr, double next) {
         double v = dadd(dmul(-gr, ph), dmul(gr, next));
         if (weight) v = v / weight[e];
         q[e] = dmul(scale, v);
     };
-    if (t < g.nt - 1) put(n, gt, phi[n + g.P]);
-    if (x < g.nx - 1) put(g.L + (i64)t * g.PBX + (i64)x * g.ny + y, gx, phi[n + g.ny]);
-    if (y < g.ny - 1) put(g.L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y, gy, phi[n + 1]);
+    if (t < g.nt - 1) put((i64)t * g.PC + p, gt, phi[n + g.P]);
+    if (x < g.nx - 1) put(g.L + (i64)t * g.PBX + p, gx, phi[n + g.ny]);
+    if (y < g.ny - 1) put(g.L + g.NBX + (i64)t * g.PBY + (i64)x * g.pyb + y, gy, phi[n + 1]);
 }
 
 // alpha = scale * ((-a) [./ weight]) : a = (BF)^* beta was computed on +beta, (BF)^*(-beta) = -(BF)^* beta exactly
 __global__ void __launch_bounds__(256) k_prolong_alpha(i64 n, double scale, const double* __restrict__ weight, double* __restrict__ a)
 {
+    // (pad entries of a pitched layout: a = 0 and weight = 1, see dotsocp_upload -- they stay zero)
     for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         double v = -a[i];
         if (weight) v = v / weight[i];
@@ -94,7 +97,7 @@ static unsigned stream_blocks(i64 n)
     i64 b = (n + 255) / 256;
     return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
 }
-static dim3 level_grid(const Geo& g, int nlev) { return dim3((unsigned)((g.P + 255) / 256), (unsigned)nlev); }
+static dim3 level_grid(const Geo& g, int nlev) { return dim3((unsigned)((g.PC + 255) / 256), (unsigned)nlev); }   // PC >= P
 
 // unscaled fine phi on node levels [t0, t1)
 void launch_prolong_phi(const Geo& gc, const Geo& gf, double rec, const double* phi_c, double* phi_f, int t0, int t1, cudaStream_t st)

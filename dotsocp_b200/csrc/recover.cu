@@ -27,24 +27,25 @@ struct RecVal {
         const double v = dmul(a.arec, a.alpha[e]);
         return WEIGHTED ? dmul(a.weight[e], v) : v;
     }
-    __device__ __forceinline__ double rho(int t, i64 p) const
+    // p = x*ny + y (node plane), pc = x*py + y (cell plane of the pitched staggered arrays)
+    __device__ __forceinline__ double rho(int t, i64 p, i64 pc) const
     {
         const Geo& g = a.g;
         if (t == 0) return a.rho0[p];
         if (t == g.nt - 1) return a.rho1[p];
-        return dadd(al((i64)(t - 1) * g.P + p), al((i64)t * g.P + p)) / 2.0;
+        return dadd(al((i64)(t - 1) * g.PC + pc), al((i64)t * g.PC + pc)) / 2.0;
     }
     // alpha on the bx edge (t, x, y), doubled on the first and last time level (recover_RhoE.m:17-18)
     __device__ __forceinline__ double ex_edge(int t, int x, int y) const
     {
         const Geo& g = a.g;
-        const double v = al(g.L + (i64)t * g.PBX + (i64)x * g.ny + y);
+        const double v = al(g.L + (i64)t * g.PBX + (i64)x * g.py + y);
         return (t == 0 || t == g.nt - 1) ? dmul(2.0, v) : v;
     }
     __device__ __forceinline__ double ey_edge(int t, int x, int y) const
     {
         const Geo& g = a.g;
-        const double v = al(g.L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y);
+        const double v = al(g.L + g.NBX + (i64)t * g.PBY + (i64)x * g.pyb + y);
         return (t == 0 || t == g.nt - 1) ? dmul(2.0, v) : v;
     }
     __device__ __forceinline__ double Ex(int t, int x, int y) const
@@ -62,14 +63,14 @@ struct RecVal {
     {
         const Geo& g = a.g;
         if (x == 0 || x == g.nx - 1) return 0.0;
-        const i64 e = g.L + (i64)t * g.PBX + (i64)x * g.ny + y;
-        return dadd(dmul(a.qrec, a.q[e - g.ny]), dmul(a.qrec, a.q[e])) / 2.0;
+        const i64 e = g.L + (i64)t * g.PBX + (i64)x * g.py + y;
+        return dadd(dmul(a.qrec, a.q[e - g.py]), dmul(a.qrec, a.q[e])) / 2.0;
     }
     __device__ __forceinline__ double by_c(int t, int x, int y) const
     {
         const Geo& g = a.g;
         if (y == 0 || y == g.ny - 1) return 0.0;
-        const i64 e = g.L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
+        const i64 e = g.L + g.NBX + (i64)t * g.PBY + (i64)x * g.pyb + y;
         return dadd(dmul(a.qrec, a.q[e - 1]), dmul(a.qrec, a.q[e])) / 2.0;
     }
 };
@@ -82,14 +83,15 @@ __global__ void __launch_bounds__(256) k_recover(RecoverArgs a)
     const int t = a.tr.tn0 + blockIdx.y;
     if (p >= g.P) return;
     const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
+    const i64 pc = (i64)x * g.py + y;
     const RecVal<WEIGHTED> v{a};
     double r;
-    if (WHICH == RC_RHO) r = v.rho(t, p);
+    if (WHICH == RC_RHO) r = v.rho(t, p, pc);
     else if (WHICH == RC_EX) r = v.Ex(t, x, y);
     else if (WHICH == RC_EY) r = v.Ey(t, x, y);
     else {
         if (t >= g.nt - 1) return;                       // cell-indexed fields: nt-1 layers
-        if (WHICH == RC_Q0) r = dmul(a.qrec, a.q[(i64)t * g.P + p]);
+        if (WHICH == RC_Q0) r = dmul(a.qrec, a.q[(i64)t * g.PC + pc]);
         else if (WHICH == RC_BX) r = dadd(v.bx_c(t, x, y), v.bx_c(t + 1, x, y)) / 2.0;
         else r = dadd(v.by_c(t, x, y), v.by_c(t + 1, x, y)) / 2.0;
     }
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) k_recover_stats(RecoverArgs a)
     if (p < g.P) {
         const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
         const RecVal<WEIGHTED> v{a};
-        const double rho = v.rho(t, p);
+        const double rho = v.rho(t, p, (i64)x * g.py + y);
         const double ex = v.Ex(t, x, y);
         double m2 = dmul(ex, ex);
         if (!ONE_D) {

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256) k_sgs_resid(Geo g, int tn0, IterScal sc, 
         const int x = (int)(p / g.ny), y = (int)(p - (i64)x * g.ny);
         if (!WITH_ALPHA_C || (((t + x + y) & 1) == 0)) {
             const i64 L = g.L, n = (i64)t * g.P + p;
+            const i64 ce = (i64)t * g.PC + (i64)x * g.py + y;   // q0 edge above the node (pitched staggered arrays)
             const double ph = phi[n];
             // u on edge e between node a (lower) and node b: ((-g) phi_a + g phi_b) - q_e [+ alpha_e]
             auto u = [&](i64 e, double gr, double pa, double pb) -> double {
@@ -113,10 +114,10 @@ __global__ void __launch_bounds__(256) k_sgs_resid(Geo g, int tn0, IterScal sc, 
         acc = first ? tv_ : dadd(acc, tv_);  \
         first = false;                       \
     }
-            if (t > 0) ADDTERM(dmul(sc.gt, u(n - g.P, sc.gt, phi[n - g.P], ph)));
-            if (t < g.nt - 1) ADDTERM(dmul(-sc.gt, u(n, sc.gt, ph, phi[n + g.P])));
-            const i64 ox = L + (i64)t * g.PBX + (i64)x * g.ny + y, oy = L + g.NBX + (i64)t * g.PBY + (i64)x * (g.ny - 1) + y;
-            if (x > 0) ADDTERM(dmul(sc.gx, u(ox - g.ny, sc.gx, phi[n - g.ny], ph)));
+            if (t > 0) ADDTERM(dmul(sc.gt, u(ce - g.PC, sc.gt, phi[n - g.P], ph)));
+            if (t < g.nt - 1) ADDTERM(dmul(-sc.gt, u(ce, sc.gt, ph, phi[n + g.P])));
+            const i64 ox = L + (i64)t * g.PBX + (i64)x * g.py + y, oy = L + g.NBX + (i64)t * g.PBY + (i64)x * g.pyb + y;
+            if (x > 0) ADDTERM(dmul(sc.gx, u(ox - g.py, sc.gx, phi[n - g.ny], ph)));
             if (x < g.nx - 1) ADDTERM(dmul(-sc.gx, u(ox, sc.gx, ph, phi[n + g.ny])));
             if (y > 0) ADDTERM(dmul(sc.gy, u(oy - 1, sc.gy, phi[n - 1], ph)));
             if (y < g.ny - 1) ADDTERM(dmul(-sc.gy, u(oy, sc.gy, ph, phi[n + 1])));

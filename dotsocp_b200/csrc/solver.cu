@@ -148,7 +148,8 @@ struct dotsocp_ctx {
     int my = 0;                 // first (NCCL mode: only) local slab id
     void* comm = nullptr;       // ncclComm_t
     int device = 0;
-    Geo g;
+    Geo g;                      // device layout: rows of the staggered / 10-column arrays pitched to 256 bytes (common.cuh)
+    Geo gh;                     // the reference's packed layout: what the host arrays of the C ABI use
     cudaStream_t st = nullptr;
     cudaStream_t st2 = nullptr;  // communication stream (time slabs): transposes and ghost planes overlap with compute
     std::vector<cudaEvent_t> cev;   // reusable events for the st <-> st2 hand-offs
@@ -264,15 +265,15 @@ static int make_slab(dotsocp_ctx* c, int id)
     s->p1 = c->pcut[id + 1];
     add_range(s->n_own, tr.tn0 * g.P, tr.tn1 * g.P);
     add_range(s->n_all, s->lo_n * g.P, s->hi_n * g.P);
-    add_range(s->q_own, tr.tc0 * g.P, tr.tc1 * g.P);
+    add_range(s->q_own, tr.tc0 * g.PC, tr.tc1 * g.PC);
     add_range(s->q_own, g.L + tr.tn0 * g.PBX, g.L + tr.tn1 * g.PBX);
     add_range(s->q_own, g.L + g.NBX + tr.tn0 * g.PBY, g.L + g.NBX + tr.tn1 * g.PBY);
-    add_range(s->q_all, s->lo_c * g.P, s->hi_c * g.P);
+    add_range(s->q_all, s->lo_c * g.PC, s->hi_c * g.PC);
     add_range(s->q_all, g.L + s->lo_n * g.PBX, g.L + s->hi_n * g.PBX);
     add_range(s->q_all, g.L + g.NBX + s->lo_n * g.PBY, g.L + g.NBX + s->hi_n * g.PBY);
     for (int j = 0; j < 10; j++) {
-        add_range(s->b_own, j * g.L + tr.tc0 * g.P, j * g.L + tr.tc1 * g.P);
-        add_range(s->b_all, j * g.L + s->lo_c * g.P, j * g.L + s->hi_c * g.P);
+        add_range(s->b_own, j * g.L + tr.tc0 * g.PC, j * g.L + tr.tc1 * g.PC);
+        add_range(s->b_all, j * g.L + s->lo_c * g.PC, j * g.L + s->hi_c * g.PC);
     }
     auto win = [](const Ranges& r) {
         std::vector<std::pair<long long, long long>> w;
@@ -295,6 +296,15 @@ static int make_slab(dotsocp_ctx* c, int id)
     s->alpha = s->a_alpha.ptr(); s->q2 = s->a_q2.ptr(); s->qtmp = s->a_qtmp.ptr();
     s->weight = c->weighted ? s->a_weight.ptr() : nullptr;
     s->beta[0] = s->a_beta[0].ptr(); s->beta[1] = s->a_beta[1].ptr();
+    if (!g.packed()) {
+        // pad columns of the pitched rows are never written by the kernels: they must hold zeros (weight: ones, see
+        // dotsocp_upload) so that the flat streaming kernels (scalings, extrapolations) keep them finite
+        double* qa[] = {s->q[0], s->q[1], s->alpha, s->q2, s->qtmp, s->weight};
+        for (double* a : qa)
+            if (a) for (auto& x : s->q_all) CU(cudaMemsetAsync(a + x.b, 0, (size_t)(x.e - x.b) * sizeof(double), c->st));
+        for (int k = 0; k < 2; k++)
+            for (auto& x : s->b_all) CU(cudaMemsetAsync(s->beta[k] + x.b, 0, (size_t)(x.e - x.b) * sizeof(double), c->st));
+    }
     CU(cudaMalloc(&s->c0, g.P * sizeof(double)));
     CU(cudaMalloc(&s->c1, g.P * sizeof(double)));
     CU(cudaMemsetAsync(s->c0, 0, g.P * sizeof(double), c->st));
@@ -363,7 +373,11 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
     c->emulate = world > 1 && nccl_id == nullptr;
     { const char* tr_ = getenv("DOTSOCP_TRACE"); c->trace = tr_ && tr_[0] == '1'; }
     c->my = c->emulate ? 0 : rank;
-    c->g = make_geo(nt, nx, ny);
+    {   // DOTSOCP_LAYOUT=packed keeps the reference's packed rows on the device as well (A/B measurements, tests)
+        const char* lay = getenv("DOTSOCP_LAYOUT");
+        c->gh = make_geo(nt, nx, ny);
+        c->g = (lay && strcmp(lay, "packed") == 0) ? c->gh : make_geo_padded(nt, nx, ny);
+    }
     const Geo& g = c->g;
     cudaGetDevice(&c->device);
     for (int r = 0; r < world; r++) {
@@ -590,17 +604,17 @@ static int ghosts(dotsocp_ctx* c, int what, int qk, int bk, cudaStream_t st = nu
             xs.push_back({sel_q, qk, g.L + g.NBX + T * g.PBY, g.PBY, r + 1, r});
         }
         if (what & GH_Q_DOWN) {
-            xs.push_back({sel_q, qk, (T - 1) * g.P, g.P, r, r + 1});
+            xs.push_back({sel_q, qk, (T - 1) * g.PC, g.PC, r, r + 1});
             xs.push_back({sel_q, qk, g.L + (T - 1) * g.PBX, g.PBX, r, r + 1});
             xs.push_back({sel_q, qk, g.L + g.NBX + (T - 1) * g.PBY, g.PBY, r, r + 1});
         }
-        if (what & GH_ALPHA0_DOWN) xs.push_back({sel_alpha, 0, (T - 1) * g.P, g.P, r, r + 1});
+        if (what & GH_ALPHA0_DOWN) xs.push_back({sel_alpha, 0, (T - 1) * g.PC, g.PC, r, r + 1});
         if (what & GH_BETA_DOWN)
-            for (int j = 0; j < 10; j++) xs.push_back({sel_beta, bk, j * g.L + (T - 1) * g.P, g.P, r, r + 1});
+            for (int j = 0; j < 10; j++) xs.push_back({sel_beta, bk, j * g.L + (T - 1) * g.PC, g.PC, r, r + 1});
         if ((what & GH_W) && c->weighted) {
             xs.push_back({sel_weight, 0, g.L + T * g.PBX, g.PBX, r + 1, r});
             xs.push_back({sel_weight, 0, g.L + g.NBX + T * g.PBY, g.PBY, r + 1, r});
-            xs.push_back({sel_weight, 0, (T - 1) * g.P, g.P, r, r + 1});
+            xs.push_back({sel_weight, 0, (T - 1) * g.PC, g.PC, r, r + 1});
             xs.push_back({sel_weight, 0, g.L + (T - 1) * g.PBX, g.PBX, r, r + 1});
             xs.push_back({sel_weight, 0, g.L + g.NBX + (T - 1) * g.PBY, g.PBY, r, r + 1});
         }
@@ -846,7 +860,7 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
 //   z, beta: ncol columns of (owned cells) doubles, column-major.
 struct HostMap {
     bool local;
-    const Geo* g;
+    const Geo* g;     // the PACKED geometry (ctx->gh): host arrays always have the reference's layout
     TRange tr;
     i64 nodes(i64 t) const { return (local ? t - tr.tn0 : t) * g->P; }
     i64 q0(i64 t) const { return (local ? t - tr.tc0 : t) * g->P; }
@@ -876,17 +890,37 @@ static int xfer(dotsocp_ctx* c, double* dev, double* host, size_t n, bool up)
     else CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->st));
     return 0;
 }
+// `rows` rows of `w` doubles: packed on the host, `dpitch` doubles apart on the device
+static int xfer_rows(dotsocp_ctx* c, double* dev, i64 dpitch, double* host, i64 w, i64 rows, bool up)
+{
+    if (rows <= 0 || w <= 0) return 0;
+    if (dpitch == w) return xfer(c, dev, host, (size_t)(w * rows), up);
+    static const bool plain = [] { const char* e = getenv("DOTSOCP_HOSTCOPY"); return e && strcmp(e, "plain") == 0; }();
+    const size_t wb = (size_t)w * sizeof(double), db = (size_t)dpitch * sizeof(double);
+    if (!plain && wb * (size_t)rows >= ((size_t)1 << 20)) {
+        HostCopier* hc = HostCopier::get();
+        if (hc->ok()) {
+            const int e = up ? hc->h2d_rows(dev, db, host, wb, (size_t)rows, c->st) : hc->d2h_rows(host, dev, db, wb, (size_t)rows, c->st);
+            if (e) return set_err(DOTSOCP_ECUDA, "staged %s copy failed: %s", up ? "host-to-device" : "device-to-host", cudaGetErrorString((cudaError_t)e));
+            return 0;
+        }
+    }
+    if (up) CU(cudaMemcpy2DAsync(dev, db, host, wb, wb, (size_t)rows, cudaMemcpyHostToDevice, c->st));
+    else CU(cudaMemcpy2DAsync(host, wb, dev, db, wb, (size_t)rows, cudaMemcpyDeviceToHost, c->st));
+    return 0;
+}
 
 static int copy_stag(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev, double* host, bool up)
 {
     const Geo& g = c->g;
     const TRange& tr = s->tr;
-    struct P { i64 d, h, n; } parts[3] = {{tr.tc0 * g.P, hm.q0(tr.tc0), (i64)(tr.tc1 - tr.tc0) * g.P},
-                                          {g.L + tr.tn0 * g.PBX, hm.bx(tr.tn0), (i64)(tr.tn1 - tr.tn0) * g.PBX},
-                                          {g.L + g.NBX + tr.tn0 * g.PBY, hm.by(tr.tn0), (i64)(tr.tn1 - tr.tn0) * g.PBY}};
+    // q0 rows of the owned cell layers, bx / by rows of the owned node levels
+    struct P { i64 d, h, rows, w, dp; } parts[3] = {
+        {tr.tc0 * g.PC, hm.q0(tr.tc0), (i64)(tr.tc1 - tr.tc0) * g.nx, g.ny, g.py},
+        {g.L + tr.tn0 * g.PBX, hm.bx(tr.tn0), (i64)(tr.tn1 - tr.tn0) * (g.nx - 1), g.ny, g.py},
+        {g.L + g.NBX + tr.tn0 * g.PBY, hm.by(tr.tn0), (i64)(tr.tn1 - tr.tn0) * g.nx, g.ny - 1, g.pyb}};
     for (auto& p : parts) {
-        if (p.n <= 0) continue;
-        int rc = xfer(c, dev + p.d, host + p.h, (size_t)p.n, up);
+        int rc = xfer_rows(c, dev + p.d, p.dp, host + p.h, p.w, p.rows, up);
         if (rc) return rc;
     }
     return 0;
@@ -896,17 +930,25 @@ static int copy_cols(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev10, 
 {
     const Geo& g = c->g;
     const TRange& tr = s->tr;
-    const i64 n = (i64)(tr.tc1 - tr.tc0) * g.P;
     const int ncol = c->one_d ? 6 : 10;
     // 1-D variant: 6 columns at the boundary (c0..c4 -> 0..4, c5 -> 9; columns 5..8 are structural zeros on the device)
     for (int jh = 0; jh < ncol; jh++) {
         const int j = (c->one_d && jh == 5) ? 9 : jh;
-        int rc = xfer(c, dev10 + j * g.L + tr.tc0 * g.P, host + hm.col(jh, tr.tc0), (size_t)n, up);
+        int rc = xfer_rows(c, dev10 + j * g.L + tr.tc0 * g.PC, g.py, host + hm.col(jh, tr.tc0), g.ny, (i64)(tr.tc1 - tr.tc0) * g.nx, up);
         if (rc) return rc;
     }
     if (up && c->one_d)
         for (int j = 5; j < 9; j++)
-            CU(cudaMemsetAsync(dev10 + j * g.L + s->lo_c * g.P, 0, (size_t)(s->hi_c - s->lo_c) * g.P * sizeof(double), c->st));
+            CU(cudaMemsetAsync(dev10 + j * g.L + s->lo_c * g.PC, 0, (size_t)(s->hi_c - s->lo_c) * g.PC * sizeof(double), c->st));
+    return 0;
+}
+
+// pad entries of the weight are ones: the level transfer divides whole ranges by the weight (k_prolong_alpha)
+static int fill_weight_pads(dotsocp_ctx* c, Slab* s)
+{
+    if (c->g.packed() || !s->weight) return 0;
+    for (auto& x : s->q_all) launch_fill(s->weight + x.b, x.e - x.b, 1.0, c->st);
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -919,7 +961,7 @@ extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q
     c->qcur = 0;
     c->bcur = 0;
     for (Slab* s : c->slabs) {
-        HostMap hm{c->world > 1 && !c->emulate, &g, s->tr};
+        HostMap hm{c->world > 1 && !c->emulate, &c->gh, s->tr};
         const TRange& tr = s->tr;
         // c is -rho0/ht on the first time level, +rho1/ht on the last and zero in between (initialize.m:41-44); only the
         // two planes are kept on the device.
@@ -939,7 +981,10 @@ extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q
         if ((rc = xfer(c, s->phi + tr.tn0 * g.P, const_cast<double*>(phi) + hm.nodes(tr.tn0), (size_t)(tr.tn1 - tr.tn0) * g.P, true))) return rc;
         if ((rc = copy_stag(c, s, hm, s->q[0], const_cast<double*>(q), true))) return rc;
         if ((rc = copy_stag(c, s, hm, s->alpha, const_cast<double*>(alpha), true))) return rc;
-        if (c->weighted && (rc = copy_stag(c, s, hm, s->weight, const_cast<double*>(weight), true))) return rc;
+        if (c->weighted) {
+            if ((rc = fill_weight_pads(c, s))) return rc;
+            if ((rc = copy_stag(c, s, hm, s->weight, const_cast<double*>(weight), true))) return rc;
+        }
         if (tr.tn0 == 0) CU(cudaMemcpyAsync(s->c0, cvec + hm.nodes(0), g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
         if (tr.tn1 == g.nt) CU(cudaMemcpyAsync(s->c1, cvec + hm.nodes(g.nt - 1), g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
         if ((rc = copy_cols(c, s, hm, s->beta[0], const_cast<double*>(beta), true))) return rc;
@@ -990,7 +1035,8 @@ extern "C" int dotsocp_prolong(dotsocp_ctx* coarse, dotsocp_ctx* fine, const dot
         Slab* sc = coarse->local(sf->id);
         const TRange& tr = sf->tr;
         if (fine->weighted) {
-            HostMap hm{local_host, &gf, tr};
+            HostMap hm{local_host, &fine->gh, tr};
+            if ((rc = fill_weight_pads(fine, sf))) return rc;
             if ((rc = copy_stag(fine, sf, hm, sf->weight, const_cast<double*>(weight), true))) return rc;
         }
         if (tr.tn0 == 0) {
@@ -1019,7 +1065,7 @@ extern "C" int dotsocp_prolong(dotsocp_ctx* coarse, dotsocp_ctx* fine, const dot
         launch_bfdconj(gf, 1.0, sf->beta[0], sf->alpha, st, &tr);                                   // mexBFdConj(alpha, ., 1)
         for (auto& x : sf->q_own) launch_prolong_alpha(sf->alpha + x.b, w ? w + x.b : nullptr, x.e - x.b, k.alpha_scale, st);
         for (int j = 0; j < 10; j++)
-            launch_mul_inplace(sf->beta[0] + (i64)j * gf.L + (i64)sf->lo_c * gf.P, (i64)(tr.tc1 - sf->lo_c) * gf.P, k.beta_scale, st);
+            launch_mul_inplace(sf->beta[0] + (i64)j * gf.L + (i64)sf->lo_c * gf.PC, (i64)(tr.tc1 - sf->lo_c) * gf.PC, k.beta_scale, st);
         for (auto& x : sf->b_all) CU(cudaMemsetAsync(sf->beta[1] + x.b, 0, (size_t)(x.e - x.b) * sizeof(double), st));   // z = 0 (jump_nextLevel.m:9)
         fine->launches += 5 + (double)sf->q_own.size() + 10;
     }
@@ -1040,7 +1086,7 @@ extern "C" int dotsocp_download(dotsocp_ctx* c, double* phi, double* q, double* 
     if (c->z_absent && z) return set_err(DOTSOCP_ESTATE, "z was neither uploaded nor computed yet");
     const Geo& g = c->g;
     for (Slab* s : c->slabs) {
-        HostMap hm{c->world > 1 && !c->emulate, &g, s->tr};
+        HostMap hm{c->world > 1 && !c->emulate, &c->gh, s->tr};
         const TRange& tr = s->tr;
         int rc;
         if (phi && (rc = xfer(c, s->phi + tr.tn0 * g.P, phi + hm.nodes(tr.tn0), (size_t)(tr.tn1 - tr.tn0) * g.P, false))) return rc;
