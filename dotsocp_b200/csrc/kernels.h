@@ -35,6 +35,9 @@ struct UpdateArgs {
     const double* c0;       // c on the first time level (nx*ny)
     const double* c1;       // c on the last time level
     int kkt_t0;             // first node level of the slab (row 0 of the fused KKT partials)
+    // side buffer of the aligned march (mult_side_doubles), NULL: haloed tiling; covers cell layers [side_t0, side_t0 + side_layers)
+    double* side;
+    int side_t0, side_layers;
 };
 // q_new = ((A phi + alpha) + q2) .* diagQInv ; alpha += tau (A phi - q_new)      (solver_socp_inPALM.m:204-214)
 // acc: alpha = (alpha + A phi) - q_new                                            (solver_socp_accADMM.m:237)
@@ -50,8 +53,10 @@ void launch_cells_update(const Geo& g, const IterScal& sc, bool one_d, int mode,
 // update=false ("prologue"): no multiplier step, only q2/rhs from the current (q_new, alpha, beta).
 // kkt != NULL (update only): the launch also leaves the per-(time level, tile) partial sums of the KKT terms that live on
 // the data it streams anyway (see KktFused) -- a check then costs no extra pass over the 10-column arrays.
-void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st, const KktFused* kkt = nullptr);
+int  launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st, const KktFused* kkt = nullptr);   // returns the number of kernels launched
 int  mult_tiles(const Geo& g);   // CTAs per time level of launch_mult (rows of its KKT partials)
+bool mult_aligned_ok(const Geo& g, bool one_d);                 // the layout allows the aligned (halo-free) tiling of launch_mult
+i64  mult_side_doubles(const Geo& g, bool one_d, int nlayers);  // size of its side buffer for `nlayers` cell layers (0: not used)
 // z = Pi_Q(d + BF q_old - beta_old): optional store (zout may alias beta_old)
 void launch_zstep(const Geo& g, const IterScal& sc, bool one_d, const double* q_old, const double* beta_old, double* zout,
                   cudaStream_t st, const TRange* tr = nullptr);

@@ -408,9 +408,8 @@ void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st,
 // ncu on the round-1 kernel: 55 % of the warp samples waited on the first use of a step's loads (long scoreboard), i.e. the
 // HBM latency was exposed once per step.  PF = true keeps the loaded values of step t+1 in a second register set that is
 // filled BEFORE step t is computed (software pipeline, one 255-register CTA per SM), so a step's loads have a whole step of
-// arithmetic to arrive.  PF = 2 prefetches the same values with cp.async into a two-stage shared-memory ring instead (21 slots
-// per thread; the level-t alpha of the rhs stencil stays a direct load), which keeps 128 registers and two CTAs per SM.
-// PF = 0 is the round-1 schedule (two 128-register CTAs per SM, loads then compute); DOTSOCP_KM_PF selects at run time.
+// arithmetic to arrive.  PF = 0 is the round-1 schedule (two 128-register CTAs per SM, loads then compute); DOTSOCP_KM_PF
+// selects at run time.  (A cp.async shared-memory ring and a cp.async.bulk / mbarrier ring were measured slower, profiles/README.md.)
 //
 // KKT (check iterations): the same march also accumulates every KKT term that lives on the data in registers
 // (solver_socp_inPALM.m:225-244, compute_kkt_dot_complement.m) -- z, beta, z2, alpha and q are all there -- and leaves one
@@ -463,8 +462,32 @@ struct MultLoad {
     double cv;                                    // c on the first / last time level
 };
 
-template <int TX, int TY, int PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool EDGE, bool KKT>
+// AL ("aligned", pitched layouts only): the tile is TX x TY cells that are ALL owned, with its first column on a 32-column
+// (256-byte) boundary, so that every warp-wide load and store of a step is one aligned 256-byte run -- partially written
+// 32-byte sectors are what limits the packed / haloed tiling (common.cuh, tools/stream_pattern3.cu).  Without the halo the
+// last row / column of a tile cannot form its bx / by sums (they need w of the first row / column of the next tile):
+// both sides leave their two w columns in a small side buffer instead (rows: straight from the warps, columns: through
+// shared memory so that one warp writes full sectors) and k_q2_fix completes those edges after the march.
+struct SideGeo {
+    int t0;        // first cell layer backed by the buffer
+    int nbx, nby;  // tiles along x / y
+    int nxp;       // nx rounded up to TX
+    i64 sx_t;      // doubles per cell layer of the row part   [t][kx][4][py]   : w1, w3 of the tile's first row; w2, w4 of its last
+    i64 sy_off;    // offset of the column part                [t][ky][4][nxp]  : w5, w7 of the first column; w6, w8 of the last
+    i64 sy_t;
+};
+__host__ __device__ __forceinline__ i64 side_sx(const SideGeo& sg, const Geo& g, int t, int kx, int comp, int y)
+{
+    return (i64)(t - sg.t0) * sg.sx_t + ((i64)kx * 4 + comp) * g.py + y;
+}
+__host__ __device__ __forceinline__ i64 side_sy(const SideGeo& sg, int t, int ky, int comp, int x)
+{
+    return sg.sy_off + (i64)(t - sg.t0) * sg.sy_t + ((i64)ky * 4 + comp) * sg.nxp + x;
+}
+
+template <int TX, int TY, int PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool EDGE, bool KKT, bool AL>
 __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int kkt_t0, const IterScal& sc, const KktDev& kd,
+                                            const SideGeo& sg, double* __restrict__ side,
                                             const double* __restrict__ qo, const double* __restrict__ qn,
                                             const double* __restrict__ alpha, const double* __restrict__ weight,
                                             const double* __restrict__ beta, double* __restrict__ beta_out,
@@ -472,19 +495,21 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
                                             const double* __restrict__ c1, double* __restrict__ kpart)
 {
     static_assert(!KKT || UPDATE, "the KKT variant is an update kernel");
+    static_assert(!AL || (!KKT && !ONE_D && TY == 32 && 4 * TX <= 32), "aligned tiling: plain 2-D update / prologue kernels");
     constexpr int TU = 1;
     constexpr int NPL = KKT ? 9 : 4;   // exchange planes: w1,w3,w5,w7 (+ b1,b3,b5,b7, rho)
     extern __shared__ __align__(16) double dyn_smem[];
     double (*sh)[TU][NPL][TX][TY] = reinterpret_cast<double (*)[TU][NPL][TX][TY]>(dyn_smem);
-    constexpr int NT_ = TX * TY, NF = 21;      // ring: [2 stages][NF fields][NT_ threads], every thread reads only its own slots
-    double* ring = dyn_smem + 2 * TU * NPL * NT_;
+    double (*shy)[4][TX] = reinterpret_cast<double (*)[4][TX]>(dyn_smem + 2 * TU * NPL * TX * TY);   // AL: [2][4][TX]
     const int ly = threadIdx.x, lx = threadIdx.y;
     // y tiles vary fastest over the grid so that CTAs running side by side stream adjacent pieces of the same rows
-    const int x = blockIdx.y * (TX - 1) + lx, y = blockIdx.x * (TY - 1) + ly;
+    const int x = AL ? blockIdx.y * TX + lx : blockIdx.y * (TX - 1) + lx, y = AL ? blockIdx.x * TY + ly : blockIdx.x * (TY - 1) + ly;
     // EDGE = false: the whole tile (halo included) lies strictly inside the domain, every neighbour exists and all the
     // boundary predicates fold away at compile time (most CTAs of a large grid)
     const bool valid = EDGE ? ((x < g.nx) && (y < g.ny)) : true;
-    const bool owner = valid && (lx < TX - 1) && (ly < TY - 1);
+    const bool owner = AL ? valid : (valid && (lx < TX - 1) && (ly < TY - 1));
+    // AL: the x+1 / y+1 neighbour's w is inside the tile (else the edge is left to k_q2_fix)
+    const bool in_x = AL ? (lx < TX - 1) : true, in_y = AL ? (ly < TY - 1) : true;
     const bool hxm = EDGE ? (valid && x > 0) : true, hxp = EDGE ? (valid && x < g.nx - 1) : true;
     const bool hym = EDGE ? (valid && y > 0) : true, hyp = EDGE ? (valid && y < g.ny - 1) : true;
     const i64 L = g.L;
@@ -570,37 +595,6 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         }
     };
 
-    // ---- the same values through the shared-memory ring (PF == 2): issue(t) starts the copies, fetch(t) picks them up ---------
-    const int tid_ = lx * TY + ly;
-    auto cp8 = [&](double* dst, const double* src) {
-        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
-    };
-    auto issue = [&](int t) {
-        const bool cell = t < g.nt - 1;
-        if (cell && valid) {
-            double* dst = ring + (size_t)(t & 1) * NF * NT_ + tid_;
-            const i64 cidx = (i64)t * g.PC + cellp;
-            const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
-#pragma unroll
-            for (int j = 0; j < 10; j++)
-                if (!(ONE_D && j >= 5 && j <= 8)) cp8(dst + j * NT_, beta + (i64)j * L + cidx);
-            cp8(dst + 10 * NT_, qn + cidx);
-            cp8(dst + 11 * NT_, alpha + cidx);
-            if (hxm) cp8(dst + 12 * NT_, qn_bx + o1x + ibxm);
-            if (hxp) cp8(dst + 13 * NT_, qn_bx + o1x + ibx);
-            if (hym) cp8(dst + 14 * NT_, qn_by + o1y + ibym);
-            if (hyp) cp8(dst + 15 * NT_, qn_by + o1y + iby);
-            if (UPDATE) {
-                cp8(dst + 16 * NT_, qo + cidx);
-                if (hxm) cp8(dst + 17 * NT_, qo_bx + o1x + ibxm);
-                if (hxp) cp8(dst + 18 * NT_, qo_bx + o1x + ibx);
-                if (hym) cp8(dst + 19 * NT_, qo_by + o1y + ibym);
-                if (hyp) cp8(dst + 20 * NT_, qo_by + o1y + iby);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
     // ---- phase 1 of step t into exchange slot (buf, u) ---------------------------------------------------------------
     auto phase1 = [&](int t, int buf, int u, const MultLoad& ld, MultKeep& k, MultKeepK& kk) {
         const bool cell = t < g.nt - 1;
@@ -609,13 +603,11 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
 #pragma unroll
         for (int j = 0; j < 10; j++) w[j] = 0.0;
         double a0 = 0.0;
-        // where the step's values come from: the prefetched register set (PF == 1), the shared-memory ring (PF == 2) or HBM
-        // directly (PF == 0) -- in the last two cases every value is picked up where it is first needed
-        const double* rsrc = ring + (size_t)(t & 1) * NF * NT_ + tid_;
+        // where the step's values come from: the prefetched register set (PF == 1) or HBM directly (PF == 0), every value
+        // picked up where it is first needed
         const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
-        auto F = [&](int slot, const double* gaddr, double regval) -> double {
+        auto F = [&](int, const double* gaddr, double regval) -> double {
             if (PF == 1) return regval;
-            if (PF == 2) return rsrc[slot * NT_];
             return *gaddr;
         };
         double wt0 = 1.0, al_xm = 0.0, al_x = 0.0, al_ym = 0.0, al_y = 0.0, wt_xm = 1.0, wt_x = 1.0, wt_ym = 1.0, wt_y = 1.0;
@@ -725,6 +717,13 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
             sh[buf][u][1][lx][ly] = w[3];
             sh[buf][u][2][lx][ly] = w[5];
             sh[buf][u][3][lx][ly] = w[7];
+            if (AL) {
+                // the tile's first / last row and column: what the neighbouring tile (resp. k_q2_fix) needs of this layer
+                if (lx == 0) { side[side_sx(sg, g, t, blockIdx.y, 0, y)] = w[1]; side[side_sx(sg, g, t, blockIdx.y, 1, y)] = w[3]; }
+                if (lx == TX - 1) { side[side_sx(sg, g, t, blockIdx.y, 2, y)] = w[2]; side[side_sx(sg, g, t, blockIdx.y, 3, y)] = w[4]; }
+                if (ly == 0) { shy[buf][0][lx] = w[5]; shy[buf][1][lx] = w[7]; }
+                if (ly == TY - 1) { shy[buf][2][lx] = w[6]; shy[buf][3][lx] = w[8]; }
+            }
             if (owner && t >= tr.tn0) q2[cidx] = dmul(dsub(w[9], w[0]), sc.S);
         }
         k.w2 = w[2]; k.w4 = w[4]; k.w6 = w[6]; k.w8 = w[8];
@@ -756,8 +755,8 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         const bool cell = t < g.nt - 1;
         const bool emit = t >= tr.tn0;      // false only on the replayed ghost layer
         const i64 cidx = (i64)t * g.PC + cellp;
-        const double w1n = cell ? sh[buf][u][0][lx + 1][ly] : 0.0, w3n = cell ? sh[buf][u][1][lx + 1][ly] : 0.0;
-        const double w5n = cell ? sh[buf][u][2][lx][ly + 1] : 0.0, w7n = cell ? sh[buf][u][3][lx][ly + 1] : 0.0;
+        const double w1n = (cell && in_x) ? sh[buf][u][0][lx + 1][ly] : 0.0, w3n = (cell && in_x) ? sh[buf][u][1][lx + 1][ly] : 0.0;
+        const double w5n = (cell && in_y) ? sh[buf][u][2][lx][ly + 1] : 0.0, w7n = (cell && in_y) ? sh[buf][u][3][lx][ly + 1] : 0.0;
         // rhs = A' u + c : CSR-transpose row order (t-1 edge, t edge, x-1, x, y-1, y)
         double acc = 0.0;
         bool first = true;
@@ -779,7 +778,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
                 s = dadd(wp3n, wp4);
             else
                 s = dadd(dadd(dadd(w1n, k.w2), wp3n), wp4);
-            if (emit) q2_bx[(i64)t * g.PBX + ibx] = dmul(s, sc.SF);
+            if (emit && in_x) q2_bx[(i64)t * g.PBX + ibx] = dmul(s, sc.SF);
             wp3n = w3n;
         }
         if (hym) ADDTERM(dmul(sc.gy, k.uym));
@@ -792,7 +791,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
                 s = dadd(wp7n, wp8);
             else
                 s = dadd(dadd(dadd(w5n, k.w6), wp7n), wp8);
-            if (emit) q2_by[(i64)t * g.PBY + iby] = dmul(s, sc.SF);
+            if (emit && in_y) q2_by[(i64)t * g.PBY + iby] = dmul(s, sc.SF);
             wp7n = w7n;
         }
         if (emit) rhs[(i64)t * g.P + node] = dadd(first ? 0.0 : acc, k.cv);
@@ -879,6 +878,11 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         const int buf = it & 1;
         phase1(t, buf, 0, ld, keep, keepk);
         __syncthreads();
+        if (AL && lx == 0 && ly < 4 * TX && t < g.nt - 1) {
+            // column part of the side buffer: one warp stores the 4 x TX values of this layer as full 64-byte runs
+            const int comp = ly / TX, r = ly - comp * TX, xx = blockIdx.y * TX + r;
+            if (xx < g.nx) side[side_sy(sg, t, blockIdx.x, comp, xx)] = shy[buf][comp][r];
+        }
         double ks[KM_COUNT];
         if (KKT) {
 #pragma unroll
@@ -907,19 +911,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         }
     };
     int t = t_start, it = 0;
-    if (PF == 2) {
-        // shared-memory ring: the copies of step t+1 are in flight while step t is computed
-        issue(t);
-        for (; t < tr.tn1; t++, it++) {
-            if (t + 1 < tr.tn1) {
-                issue(t + 1);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            step(t, it, MultLoad());
-        }
-    } else if (PF == 1) {
+    if (PF == 1) {
         // software pipeline, unrolled by two so that the two register sets swap roles without moves
         MultLoad la, lb;
         load(t, la);
@@ -935,12 +927,12 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
     }
 }
 
-template <int TX, int TY, int PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool KKT>
+template <int TX, int TY, int PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool KKT, bool AL>
 __global__ void __launch_bounds__(TX* TY, (PF == 1 || KKT) ? 1 : 2)
-k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, const double* __restrict__ qo, const double* __restrict__ qn,
-       const double* __restrict__ alpha, const double* __restrict__ weight, const double* __restrict__ beta,
-       double* __restrict__ beta_out, double* __restrict__ q2, double* __restrict__ rhs, const double* __restrict__ c0,
-       const double* __restrict__ c1, double* __restrict__ kpart)
+k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, SideGeo sg, double* __restrict__ side, const double* __restrict__ qo,
+       const double* __restrict__ qn, const double* __restrict__ alpha, const double* __restrict__ weight,
+       const double* __restrict__ beta, double* __restrict__ beta_out, double* __restrict__ q2, double* __restrict__ rhs,
+       const double* __restrict__ c0, const double* __restrict__ c1, double* __restrict__ kpart)
 {
     const int kkt_t0 = tr.tn0;
     if (nchunk > 1) {
@@ -950,14 +942,52 @@ k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, const double* __res
         const int a = tr.tc0 + (int)((i64)i * nc / nchunk), b = tr.tc0 + (int)((i64)(i + 1) * nc / nchunk);
         tr = TRange{a, b, i == 0 ? tr.tn0 : a, i == nchunk - 1 ? tr.tn1 : b};
     }
-    const int x0 = blockIdx.y * (TX - 1), y0 = blockIdx.x * (TY - 1);
+    const int x0 = blockIdx.y * (AL ? TX : TX - 1), y0 = blockIdx.x * (AL ? TY : TY - 1);
     const bool interior = !ONE_D && x0 >= 1 && x0 + TX - 1 <= g.nx - 2 && y0 >= 1 && y0 + TY - 1 <= g.ny - 2;
     if (interior)
-        k_mult_body<TX, TY, PF, WEIGHTED, ONE_D, UPDATE, false, KKT>(g, tr, kkt_t0, sc, kd, qo, qn, alpha, weight, beta, beta_out, q2,
-                                                                     rhs, c0, c1, kpart);
+        k_mult_body<TX, TY, PF, WEIGHTED, ONE_D, UPDATE, false, KKT, AL>(g, tr, kkt_t0, sc, kd, sg, side, qo, qn, alpha, weight, beta,
+                                                                         beta_out, q2, rhs, c0, c1, kpart);
     else
-        k_mult_body<TX, TY, PF, WEIGHTED, ONE_D, UPDATE, true, KKT>(g, tr, kkt_t0, sc, kd, qo, qn, alpha, weight, beta, beta_out, q2,
-                                                                    rhs, c0, c1, kpart);
+        k_mult_body<TX, TY, PF, WEIGHTED, ONE_D, UPDATE, true, KKT, AL>(g, tr, kkt_t0, sc, kd, sg, side, qo, qn, alpha, weight, beta,
+                                                                        beta_out, q2, rhs, c0, c1, kpart);
+}
+
+// The bx / by sums on the tile boundaries of the aligned march, from the side buffer (same operations, same order as
+// phase 2 of k_mult: ((w1n + w2) + w3n') + w4' with ' = the cell layer below, times SF).  Node levels [tn0, tn1) of a slab.
+template <int TX, int TY>
+__global__ void __launch_bounds__(256) k_q2_fix(Geo g, int tn0, SideGeo sg, i64 nA, const double* __restrict__ side, double SF,
+                                                double* __restrict__ q2)
+{
+    const int t = tn0 + blockIdx.y;
+    const bool cell = t < g.nt - 1, below = t > 0;
+    i64 idx = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    double a_n, a_o, b_n, b_o;      // neighbour / own value of layer t, neighbour / own value of layer t-1
+    i64 dst;
+    if (idx < nA) {                 // bx edge between the last row of tile kx and the first row of tile kx+1
+        const int kx = (int)(idx / g.py), y = (int)(idx - (i64)kx * g.py);
+        const int xb = kx * TX + TX - 1;
+        if (xb >= g.nx - 1 || y >= g.ny) return;
+        a_n = cell ? side[side_sx(sg, g, t, kx + 1, 0, y)] : 0.0;
+        a_o = cell ? side[side_sx(sg, g, t, kx, 2, y)] : 0.0;
+        b_n = below ? side[side_sx(sg, g, t - 1, kx + 1, 1, y)] : 0.0;
+        b_o = below ? side[side_sx(sg, g, t - 1, kx, 3, y)] : 0.0;
+        dst = g.L + (i64)t * g.PBX + (i64)xb * g.py + y;
+    } else {                        // by edge between the last column of tile ky and the first column of tile ky+1
+        idx -= nA;
+        const int ky = (int)(idx / sg.nxp), x = (int)(idx - (i64)ky * sg.nxp);
+        const int yb = ky * TY + TY - 1;
+        if (ky >= sg.nby || yb >= g.ny - 1 || x >= g.nx) return;
+        a_n = cell ? side[side_sy(sg, t, ky + 1, 0, x)] : 0.0;
+        a_o = cell ? side[side_sy(sg, t, ky, 2, x)] : 0.0;
+        b_n = below ? side[side_sy(sg, t - 1, ky + 1, 1, x)] : 0.0;
+        b_o = below ? side[side_sy(sg, t - 1, ky, 3, x)] : 0.0;
+        dst = g.L + g.NBX + (i64)t * g.PBY + (i64)x * g.pyb + yb;
+    }
+    double s;
+    if (!below) s = dadd(a_n, a_o);
+    else if (!cell) s = dadd(b_n, b_o);
+    else s = dadd(dadd(dadd(a_n, a_o), b_n), b_o);
+    q2[dst] = dmul(s, SF);
 }
 
 // number of time pieces that maximises (fraction of the last round that is filled) x (useful layers / marched layers)
@@ -980,8 +1010,30 @@ static int km_pick_chunks(long long base_ctas, int ncells, int slots)
 
 int mult_tiles(const Geo& g) { return ((g.ny + KM_TY - 2) / (KM_TY - 1)) * ((g.nx + KM_TX - 2) / (KM_TX - 1)); }
 
-void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st, const KktFused* kkt)
+// side buffer of the aligned march for cell layers [t0, t1) (doubles); 0 when the layout / variant does not use it
+static SideGeo side_geo(const Geo& g, int t0)
 {
+    SideGeo sg;
+    sg.t0 = t0;
+    sg.nbx = (g.nx + KM_TX - 1) / KM_TX;
+    sg.nby = (g.ny + KM_TY - 1) / KM_TY;
+    sg.nxp = sg.nbx * KM_TX;
+    sg.sx_t = (i64)(sg.nbx + 1) * 4 * g.py;      // (+1: k_q2_fix addresses tile kx+1 before it tests the bounds)
+    sg.sy_t = (i64)(sg.nby + 1) * 4 * sg.nxp;
+    sg.sy_off = 0;
+    return sg;
+}
+bool mult_aligned_ok(const Geo& g, bool one_d) { return !one_d && g.ny > 1 && (g.py % KM_TY) == 0 && (g.pyb % KM_TY) == 0; }
+i64 mult_side_doubles(const Geo& g, bool one_d, int nlayers)
+{
+    if (!mult_aligned_ok(g, one_d)) return 0;
+    const SideGeo sg = side_geo(g, 0);
+    return (i64)nlayers * (sg.sx_t + sg.sy_t);
+}
+
+int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st, const KktFused* kkt)
+{
+    int nlaunch = 1;
     constexpr int TX = KM_TX, TY = KM_TY;
     dim3 block(TY, TX);
     dim3 grid((unsigned)((a.g.ny + TY - 2) / (TY - 1)), (unsigned)((a.g.nx + TX - 2) / (TX - 1)));
@@ -1001,15 +1053,20 @@ void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cu
     static const int forced = [] { const char* e = getenv("DOTSOCP_KM_CHUNKS"); return e ? atoi(e) : 0; }();
     const char* pf_env = getenv("DOTSOCP_KM_PF");   // read per launch: tests and A/B runs switch it inside one process
     const int pf = pf_env ? atoi(pf_env) : KM_PF;
-#define KM(PF, W, O, U, K)                                                                                            \
+    // aligned tiling (pitched layout, side buffer present, plain update kernel); DOTSOCP_KM_AL=0 keeps the haloed tiling
+    const char* al_env = getenv("DOTSOCP_KM_AL");
+    const bool al = update && !kkt && a.side != nullptr && mult_aligned_ok(a.g, one_d) && !(al_env && al_env[0] == '0');
+    SideGeo sg = side_geo(a.g, a.side_t0);
+    sg.sy_off = (i64)a.side_layers * sg.sx_t;
+    if (al) grid = dim3((unsigned)((a.g.ny + TY - 1) / TY), (unsigned)((a.g.nx + TX - 1) / TX));
+#define KM(PF, W, O, U, K, AL)                                                                                        \
     {                                                                                                                 \
-        constexpr size_t smem = (size_t)2 * (K ? 9 : 4) * TX * TY * sizeof(double) +                                  \
-                                (PF == 2 ? (size_t)2 * 21 * TX * TY * sizeof(double) : 0);                            \
+        constexpr size_t smem = (size_t)2 * (K ? 9 : 4) * TX * TY * sizeof(double) + (AL ? (size_t)2 * 4 * TX * sizeof(double) : 0); \
         static int slots = 0;                                                                                         \
         if (!slots) {                                                                                                 \
-            cudaFuncSetAttribute(k_mult<TX, TY, PF, W, O, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            cudaFuncSetAttribute(k_mult<TX, TY, PF, W, O, U, K, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             int per_sm = 0, dev = 0, sms = 0;                                                                         \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mult<TX, TY, PF, W, O, U, K>, TX * TY, smem);    \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mult<TX, TY, PF, W, O, U, K, AL>, TX * TY, smem); \
             cudaGetDevice(&dev);                                                                                      \
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);                                        \
             slots = per_sm > 0 && sms > 0 ? per_sm * sms : 1;                                                         \
@@ -1017,21 +1074,33 @@ void launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cu
         const int nchunk = forced > 0 ? std::min(forced, std::max(1, a.tr.tc1 - a.tr.tc0))                            \
                                       : km_pick_chunks((long long)grid.x * grid.y, a.tr.tc1 - a.tr.tc0, slots);       \
         grid.z = (unsigned)nchunk;                                                                                    \
-        k_mult<TX, TY, PF, W, O, U, K><<<grid, block, smem, st>>>(a.g, a.tr, nchunk, a.sc, kd, a.q_old, a.q_new, a.alpha, \
-                                                                  a.weight, a.beta_in, a.beta_out, a.q2, a.rhs, a.c0, a.c1, kpart); \
+        k_mult<TX, TY, PF, W, O, U, K, AL><<<grid, block, smem, st>>>(a.g, a.tr, nchunk, a.sc, kd, sg, a.side, a.q_old, a.q_new, \
+                                                                      a.alpha, a.weight, a.beta_in, a.beta_out, a.q2, a.rhs, a.c0, a.c1, kpart); \
     }
     if (kkt && update) {
-        if (one_d) KM(0, false, true, true, true) else if (weighted) KM(0, true, false, true, true) else KM(0, false, false, true, true)
+        if (one_d) KM(0, false, true, true, true, false) else if (weighted) KM(0, true, false, true, true, false) else KM(0, false, false, true, true, false)
     } else if (one_d) {
-        if (update) KM(0, false, true, true, false) else KM(0, false, true, false, false)
+        if (update) KM(0, false, true, true, false, false) else KM(0, false, true, false, false, false)
+    } else if (al) {
+        if (weighted) { if (pf == 1) KM(1, true, false, true, false, true) else KM(0, true, false, true, false, true) }
+        else { if (pf == 1) KM(1, false, false, true, false, true) else KM(0, false, false, true, false, true) }
+        // the edges on the tile boundaries, from the side buffer
+        const int nl = a.tr.tn1 - a.tr.tn0;
+        const i64 nA = (i64)sg.nbx * a.g.py, nB = (i64)sg.nby * sg.nxp;
+        if (nl > 0) {
+            dim3 fg((unsigned)((nA + nB + 255) / 256), (unsigned)nl);
+            k_q2_fix<TX, TY><<<fg, 256, 0, st>>>(a.g, a.tr.tn0, sg, nA, a.side, a.sc.SF, a.q2);
+            nlaunch = 2;
+        }
     } else if (weighted) {
-        if (!update) KM(0, true, false, false, false)
-        else if (pf == 2) KM(2, true, false, true, false) else if (pf == 1) KM(1, true, false, true, false) else KM(0, true, false, true, false)
+        if (!update) KM(0, true, false, false, false, false)
+        else if (pf == 1) KM(1, true, false, true, false, false) else KM(0, true, false, true, false, false)
     } else {
-        if (!update) KM(0, false, false, false, false)
-        else if (pf == 2) KM(2, false, false, true, false) else if (pf == 1) KM(1, false, false, true, false) else KM(0, false, false, true, false)
+        if (!update) KM(0, false, false, false, false, false)
+        else if (pf == 1) KM(1, false, false, true, false, false) else KM(0, false, false, true, false, false)
     }
 #undef KM
+    return nlaunch;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

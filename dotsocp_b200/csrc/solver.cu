@@ -116,6 +116,7 @@ struct Slab {
     double *phi = nullptr, *rhs = nullptr, *q[2] = {nullptr, nullptr}, *alpha = nullptr, *q2 = nullptr, *qtmp = nullptr,
            *weight = nullptr, *beta[2] = {nullptr, nullptr};
     double *c0 = nullptr, *c1 = nullptr, *partial = nullptr;
+    double* side = nullptr;                              // side buffer of the aligned k_mult (kernels.h: mult_side_doubles)
     double *partial_q = nullptr, *partial_m = nullptr;   // fused KKT partials (allocated at the first fused check)
     double *tsend = nullptr, *trecv = nullptr;   // transposed t-solve (DOTSOCP_TSOLVE=transpose)
     double* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // pipelined t-solve: forward in / out, backward in / out (P doubles each)
@@ -133,7 +134,7 @@ struct Slab {
     {
         for (double* p : peer_tsend) if (p) cudaIpcCloseMemHandle(p);
         for (double* p : peer_trecv) if (p) cudaIpcCloseMemHandle(p);
-        cudaFree(c0); cudaFree(c1); cudaFree(partial); cudaFree(partial_q); cudaFree(partial_m); cudaFree(tsend); cudaFree(trecv);
+        cudaFree(c0); cudaFree(c1); cudaFree(partial); cudaFree(side); cudaFree(partial_q); cudaFree(partial_m); cudaFree(tsend); cudaFree(trecv);
         cudaFree(tmpq); cudaFree(d_fwd); cudaFree(d_bwd);
         for (double* p : carry) cudaFree(p);
         for (int i = 0; i < 5; i++) { cudaFree(old_[i]); cudaFree(anc_[i]); }
@@ -310,6 +311,13 @@ static int make_slab(dotsocp_ctx* c, int id)
     CU(cudaMemsetAsync(s->c0, 0, g.P * sizeof(double), c->st));
     CU(cudaMemsetAsync(s->c1, 0, g.P * sizeof(double), c->st));
     CU(cudaMalloc(&s->partial, partial_doubles(g, tr.tn1 - tr.tn0) * sizeof(double)));
+    {
+        const i64 nside = mult_side_doubles(g, c->one_d, tr.tc1 - s->lo_c);
+        if (nside > 0) {
+            cudaError_t e_ = cudaMalloc(&s->side, (size_t)nside * sizeof(double));
+            if (e_ != cudaSuccess) { cudaGetLastError(); return set_err(DOTSOCP_ENOMEM, "side buffer of %lld doubles: %s", (long long)nside, cudaGetErrorString(e_)); }
+        }
+    }
     if (c->world > 1 && c->tpipe) {
         for (double*& p : s->carry) CU(cudaMalloc(&p, (size_t)g.P * sizeof(double)));
     } else if (c->world > 1) {
@@ -1198,6 +1206,7 @@ struct Loop {
         a.g = c->g; a.tr = s->tr; a.sc = sc; a.phi = s->phi; a.q_old = s->q[c->qcur]; a.q_new = s->q[1 - c->qcur];
         a.alpha = s->alpha; a.weight = s->weight; a.beta_in = s->beta[c->bcur]; a.beta_out = s->beta[1 - c->bcur];
         a.q2 = s->q2; a.rhs = s->rhs; a.c0 = s->c0; a.c1 = s->c1; a.kkt_t0 = s->tr.tn0;
+        a.side = s->side; a.side_t0 = s->lo_c; a.side_layers = s->tr.tc1 - s->lo_c;
         return a;
     }
     // q2, rhs from the current (q, alpha, beta): the z-step part of the first iteration / after any rescaling
@@ -1284,8 +1293,7 @@ struct Loop {
         for (Slab* s : c->slabs) {
             KktFused kf;
             if (kf_tmpl) { kf = *kf_tmpl; kf.partial_q = s->partial_q; kf.partial_m = s->partial_m; }
-            launch_mult(ua(s), c->weighted, c->one_d, true, c->st, kf_tmpl ? &kf : nullptr);
-            c->launches += 1;
+            c->launches += launch_mult(ua(s), c->weighted, c->one_d, true, c->st, kf_tmpl ? &kf : nullptr);
         }
         c->qcur ^= 1;
         c->bcur ^= 1;
