@@ -149,6 +149,8 @@ void launch_mul_inplace(double* x, i64 n, double s, cudaStream_t st);
 void launch_prolong_alpha(double* alpha, const double* weight, i64 n, double scale, cudaStream_t st);
 void launch_scale(double* x, i64 n, double mul, double div, cudaStream_t st);
 void launch_fill(double* x, i64 n, double v, cudaStream_t st);   // x[0..n) = v
+void debug_sum(const char* name, const double* x, i64 n, cudaStream_t st);   // debugging aid: sum |x| / non-finite count into a device log
+void debug_sum_flush(cudaStream_t st);                                        // ... printed here (the only synchronisation)
 // Halpern / affine extrapolation of solver_socp_accADMM.m:371-388:
 //   x = c1*x0 + c2*((1-rho)*xold + rho*x) ; xold = x ; if (copy_anchor) x0 = x
 void launch_halpern(double* x, double* xold, double* x0, i64 n, double c1, double c2, double rho, bool copy_anchor,
@@ -203,6 +205,9 @@ int  poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, 
                      double* const* push_tab = nullptr, const int* tcut = nullptr, int world = 1);
 // pipelined slab Thomas: the t-solve with the time axis cut into slabs, one carry plane per slab boundary and direction
 // instead of the two transposes; bit-identical to the single-slab solve (poisson.cu)
+// builds the tables of the session's t-solve now instead of inside its first solve (lines > 0: modes p0 .. p0+lines-1 of the
+// whole time axis; lines == 0: the slab of levels [t0, t1) for the pipelined sweeps)
+int  poisson_prepare(PoissonPlan* p, i64 p0, i64 lines, int t0, int t1, cudaStream_t st);
 bool poisson_slab_thomas_ok(const PoissonPlan* p);
 int  poisson_thomas_slab(PoissonPlan* p, double* a, int t0, int t1, i64 m0, i64 m1, double D2, bool backward, const double* carry_in,
                          double* carry_out, cudaStream_t st, double* launches);

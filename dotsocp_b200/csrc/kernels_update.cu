@@ -11,8 +11,10 @@
 #include "kernels.h"
 #include "reduce.cuh"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace dsocp {
 
@@ -462,6 +464,45 @@ struct MultLoad {
     double cv;                                    // c on the first / last time level
 };
 
+// ---- TMA-engine bulk copies (PF == 2 of the aligned march): global -> shared, completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 16-byte aligned source, destination and size
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared-memory image of one step's inputs (PF == 2): rows of the tile, bx rows x0-1 .. x0+TX-1, by rows with columns y0-2 .. y0+31
+template <int TX, bool WEIGHTED>
+struct KmStage {
+    static constexpr int NQ0 = 13 + (WEIGHTED ? 1 : 0);   // beta 0..9, q_new0, alpha0, q_old0 [, weight0]
+    static constexpr int NXB = 3 + (WEIGHTED ? 1 : 0);    // q_new, q_old (level t+1), alpha [, weight] (level t)
+    static constexpr int BYW = 34;                        // doubles per by row
+    static constexpr int Q0 = 0, BX = NQ0 * TX * 32, BY = BX + NXB * (TX + 1) * 32, SIZE = BY + NXB * TX * BYW;
+    enum { S_QN = 10, S_A0 = 11, S_QO = 12, S_W0 = 13 };
+    enum { X_QN = 0, X_QO = 1, X_AL = 2, X_W = 3 };
+};
+
 // AL ("aligned", pitched layouts only): the tile is TX x TY cells that are ALL owned, with its first column on a 32-column
 // (256-byte) boundary, so that every warp-wide load and store of a step is one aligned 256-byte run -- partially written
 // 32-byte sectors are what limits the packed / haloed tiling (common.cuh, tools/stream_pattern3.cu).  Without the halo the
@@ -501,6 +542,10 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
     extern __shared__ __align__(16) double dyn_smem[];
     double (*sh)[TU][NPL][TX][TY] = reinterpret_cast<double (*)[TU][NPL][TX][TY]>(dyn_smem);
     double (*shy)[4][TX] = reinterpret_cast<double (*)[4][TX]>(dyn_smem + 2 * TU * NPL * TX * TY);   // AL: [2][4][TX]
+    static_assert(PF != 2 || (AL && UPDATE && !KKT), "the bulk-copy ring exists for the aligned update kernel");
+    typedef KmStage<TX, WEIGHTED> ST;
+    double* ring = dyn_smem + 2 * TU * NPL * TX * TY + 2 * 4 * TX;             // PF == 2: [2][ST::SIZE]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + 2 * ST::SIZE);
     const int ly = threadIdx.x, lx = threadIdx.y;
     // y tiles vary fastest over the grid so that CTAs running side by side stream adjacent pieces of the same rows
     const int x = AL ? blockIdx.y * TX + lx : blockIdx.y * (TX - 1) + lx, y = AL ? blockIdx.x * TY + ly : blockIdx.x * (TY - 1) + ly;
@@ -595,6 +640,61 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         }
     };
 
+    // ---- PF == 2: every warp starts the bulk copies of its own row for step tt into ring stage `stg` (one copy per lane) -----
+    auto issue = [&](int tt, int stg) {
+        const bool cellt = tt < g.nt - 1;
+        const int xr = blockIdx.y * TX + lx, y0 = blockIdx.x * TY;
+        const bool row = xr < g.nx, rowx = xr < g.nx - 1;
+        double* stage = ring + (size_t)stg * ST::SIZE;
+        const double* src = nullptr;
+        double* dst = nullptr;
+        unsigned bytes = 0;
+        const i64 crow = (i64)tt * g.PC + (i64)xr * g.py + y0;                          // cell row
+        const i64 xrow1 = (i64)(tt + 1) * g.PBX + (i64)xr * g.py + y0, xrow0 = (i64)tt * g.PBX + (i64)xr * g.py + y0;
+        const i64 yrow1 = (i64)(tt + 1) * g.PBY + (i64)xr * g.pyb + y0, yrow0 = (i64)tt * g.PBY + (i64)xr * g.pyb + y0;
+        const int l = ly;
+        if (row) {
+            if (l < 10) { if (cellt) { src = beta + (i64)l * L + crow; dst = stage + ST::Q0 + (l * TX + lx) * 32; bytes = 256; } }
+            else if (l == 10) { if (cellt) { src = qn + crow; dst = stage + ST::Q0 + (ST::S_QN * TX + lx) * 32; bytes = 256; } }
+            else if (l == 11) { if (cellt) { src = alpha + crow; dst = stage + ST::Q0 + (ST::S_A0 * TX + lx) * 32; bytes = 256; } }
+            else if (l == 12) { if (cellt) { src = qo + crow; dst = stage + ST::Q0 + (ST::S_QO * TX + lx) * 32; bytes = 256; } }
+            else if (l == 13) { if (WEIGHTED && cellt) { src = weight + crow; dst = stage + ST::Q0 + (ST::S_W0 * TX + lx) * 32; bytes = 256; } }
+            else if (l <= 17) {          // bx rows: own row goes to slot lx + 1
+                const int k = l - 14;
+                const bool lvl1 = k <= ST::X_QO;      // q: node level tt+1 ; alpha / weight: node level tt
+                const double* base = k == ST::X_QN ? qn_bx : k == ST::X_QO ? qo_bx : k == ST::X_AL ? al_bx : w_bx;
+                if (rowx && (k < 3 || WEIGHTED) && (!lvl1 || cellt)) {
+                    src = base + (lvl1 ? xrow1 : xrow0);
+                    dst = stage + ST::BX + (k * (TX + 1) + lx + 1) * 32;
+                    bytes = 256;
+                }
+            } else if (l <= 21) {        // by rows: columns y0-2 .. y0+31 (the first tile has nothing to its left)
+                const int k = l - 18;
+                const bool lvl1 = k <= ST::X_QO;
+                const double* base = k == ST::X_QN ? qn_by : k == ST::X_QO ? qo_by : k == ST::X_AL ? al_by : w_by;
+                if ((k < 3 || WEIGHTED) && (!lvl1 || cellt)) {
+                    const int sh2 = y0 == 0 ? 0 : 2;
+                    src = base + (lvl1 ? yrow1 : yrow0) - sh2;
+                    dst = stage + ST::BY + (k * TX + lx) * ST::BYW + 2 - sh2;
+                    bytes = 256 + 8 * sh2;
+                }
+            } else if (l <= 25 && lx == 0 && xr > 0) {   // the bx row below the tile (x0 - 1), slot 0
+                const int k = l - 22;
+                const bool lvl1 = k <= ST::X_QO;
+                const double* base = k == ST::X_QN ? qn_bx : k == ST::X_QO ? qo_bx : k == ST::X_AL ? al_bx : w_bx;
+                if ((k < 3 || WEIGHTED) && (!lvl1 || cellt)) {
+                    src = base + (lvl1 ? xrow1 : xrow0) - g.py;
+                    dst = stage + ST::BX + (k * (TX + 1)) * 32;
+                    bytes = 256;
+                }
+            }
+        }
+        const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+        if (ly == 0) mbar_arrive_expect_tx(&mbar[stg], total);
+        __syncwarp();
+        if (bytes) bulk_g2s(dst, src, bytes, &mbar[stg]);
+    };
+
     // ---- phase 1 of step t into exchange slot (buf, u) ---------------------------------------------------------------
     auto phase1 = [&](int t, int buf, int u, const MultLoad& ld, MultKeep& k, MultKeepK& kk) {
         const bool cell = t < g.nt - 1;
@@ -606,8 +706,19 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         // where the step's values come from: the prefetched register set (PF == 1) or HBM directly (PF == 0), every value
         // picked up where it is first needed
         const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
-        auto F = [&](int, const double* gaddr, double regval) -> double {
+        const double* stq = ring + (size_t)buf * ST::SIZE;      // PF == 2: this step's stage (buf == it & 1)
+        auto F = [&](int slot, const double* gaddr, double regval) -> double {
             if (PF == 1) return regval;
+            if (PF == 2) {
+                // slots: 0..9 beta, 10 q_new0, 11 alpha0, 12..15 q_new bx[x-1], bx[x], by[y-1], by[y], 16 q_old0, 17..20 q_old likewise
+                if (slot <= 11) return stq[ST::Q0 + (slot * TX + lx) * 32 + ly];
+                if (slot == 16) return stq[ST::Q0 + (ST::S_QO * TX + lx) * 32 + ly];
+                const int k = slot >= 17 ? ST::X_QO : ST::X_QN, e = slot >= 17 ? slot - 17 : slot - 12;
+                if (e == 0) return stq[ST::BX + (k * (TX + 1) + lx) * 32 + ly];
+                if (e == 1) return stq[ST::BX + (k * (TX + 1) + lx + 1) * 32 + ly];
+                if (e == 2) return stq[ST::BY + (k * TX + lx) * ST::BYW + ly + 1];
+                return stq[ST::BY + (k * TX + lx) * ST::BYW + ly + 2];
+            }
             return *gaddr;
         };
         double wt0 = 1.0, al_xm = 0.0, al_x = 0.0, al_ym = 0.0, al_y = 0.0, wt_xm = 1.0, wt_x = 1.0, wt_ym = 1.0, wt_y = 1.0;
@@ -617,6 +728,22 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
             al_xm = ld.al_xm; al_x = ld.al_x; al_ym = ld.al_ym; al_y = ld.al_y;
             wt_xm = ld.wt_xm; wt_x = ld.wt_x; wt_ym = ld.wt_ym; wt_y = ld.wt_y;
             k.cv = ld.cv;
+        } else if (PF == 2) {
+            if (owner) {
+                if (hxm) al_xm = stq[ST::BX + (ST::X_AL * (TX + 1) + lx) * 32 + ly];
+                if (hxp) al_x = stq[ST::BX + (ST::X_AL * (TX + 1) + lx + 1) * 32 + ly];
+                if (hym) al_ym = stq[ST::BY + (ST::X_AL * TX + lx) * ST::BYW + ly + 1];
+                if (hyp) al_y = stq[ST::BY + (ST::X_AL * TX + lx) * ST::BYW + ly + 2];
+                if (WEIGHTED) {
+                    if (hxm) wt_xm = stq[ST::BX + (ST::X_W * (TX + 1) + lx) * 32 + ly];
+                    if (hxp) wt_x = stq[ST::BX + (ST::X_W * (TX + 1) + lx + 1) * 32 + ly];
+                    if (hym) wt_ym = stq[ST::BY + (ST::X_W * TX + lx) * ST::BYW + ly + 1];
+                    if (hyp) wt_y = stq[ST::BY + (ST::X_W * TX + lx) * ST::BYW + ly + 2];
+                }
+                if (t == 0) k.cv = c0[node];
+                else if (!cell) k.cv = c1[node];
+            }
+            if (WEIGHTED && cell && valid) wt0 = stq[ST::Q0 + (ST::S_W0 * TX + lx) * 32 + ly];
         } else {
             // level-t alpha (and weight) of the rhs stencil: direct loads, consumed behind the two projections
             if (owner) {
@@ -883,6 +1010,8 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
             const int comp = ly / TX, r = ly - comp * TX, xx = blockIdx.y * TX + r;
             if (xx < g.nx) side[side_sy(sg, t, blockIdx.x, comp, xx)] = shy[buf][comp][r];
         }
+        // PF == 2: every warp has read its inputs of step t (barrier above): refill the stage with step t+2
+        if (PF == 2 && t + 2 < tr.tn1) issue(t + 2, buf);
         double ks[KM_COUNT];
         if (KKT) {
 #pragma unroll
@@ -911,7 +1040,20 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         }
     };
     int t = t_start, it = 0;
-    if (PF == 1) {
+    if (PF == 2) {
+        if (lx == 0 && ly == 0) {
+            mbar_init(&mbar[0], TX);      // one arrival per warp and phase
+            mbar_init(&mbar[1], TX);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        issue(t, 0);
+        if (t + 1 < tr.tn1) issue(t + 1, 1);
+        for (; t < tr.tn1; t++, it++) {
+            mbar_wait(&mbar[it & 1], (unsigned)(it >> 1) & 1u);
+            step(t, it, MultLoad());
+        }
+    } else if (PF == 1) {
         // software pipeline, unrolled by two so that the two register sets swap roles without moves
         MultLoad la, lb;
         load(t, la);
@@ -1061,7 +1203,8 @@ int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cud
     if (al) grid = dim3((unsigned)((a.g.ny + TY - 1) / TY), (unsigned)((a.g.nx + TX - 1) / TX));
 #define KM(PF, W, O, U, K, AL)                                                                                        \
     {                                                                                                                 \
-        constexpr size_t smem = (size_t)2 * (K ? 9 : 4) * TX * TY * sizeof(double) + (AL ? (size_t)2 * 4 * TX * sizeof(double) : 0); \
+        constexpr size_t smem = (size_t)2 * (K ? 9 : 4) * TX * TY * sizeof(double) + (AL ? (size_t)2 * 4 * TX * sizeof(double) : 0) + \
+                                (PF == 2 ? (size_t)2 * KmStage<TX, W>::SIZE * sizeof(double) + 16 : 0);               \
         static int slots = 0;                                                                                         \
         if (!slots) {                                                                                                 \
             cudaFuncSetAttribute(k_mult<TX, TY, PF, W, O, U, K, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -1082,8 +1225,8 @@ int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cud
     } else if (one_d) {
         if (update) KM(0, false, true, true, false, false) else KM(0, false, true, false, false, false)
     } else if (al) {
-        if (weighted) { if (pf == 1) KM(1, true, false, true, false, true) else KM(0, true, false, true, false, true) }
-        else { if (pf == 1) KM(1, false, false, true, false, true) else KM(0, false, false, true, false, true) }
+        if (weighted) { if (pf == 2) KM(2, true, false, true, false, true) else if (pf == 1) KM(1, true, false, true, false, true) else KM(0, true, false, true, false, true) }
+        else { if (pf == 2) KM(2, false, false, true, false, true) else if (pf == 1) KM(1, false, false, true, false, true) else KM(0, false, false, true, false, true) }
         // the edges on the tile boundaries, from the side buffer
         const int nl = a.tr.tn1 - a.tr.tn0;
         const i64 nA = (i64)sg.nbx * a.g.py, nB = (i64)sg.nby * sg.nxp;
@@ -1583,6 +1726,41 @@ void launch_fill(double* x, i64 n, double v, cudaStream_t st)
     i64 b = (n + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
     k_fill<<<(unsigned)b, 256, 0, st>>>(x, n, v);
+}
+
+// debugging aid (DOTSOCP_DEBUG_SUMS): sum of |x| and number of non-finite entries of a whole array
+__global__ void __launch_bounds__(256) k_dbg_sum(const double* __restrict__ x, i64 n, double* __restrict__ out)
+{
+    double s = 0.0, bad = 0.0;
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        if (isfinite(v)) s += fabs(v); else bad += 1.0;
+    }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); bad += __shfl_down_sync(0xffffffffu, bad, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], s); atomicAdd(&out[1], bad); }
+}
+// no host synchronisation at the call (the sums land in a device log); debug_sum_flush prints what was collected
+static double* g_dbg_log = nullptr;
+static int g_dbg_n = 0;
+static char g_dbg_names[256][48];
+void debug_sum(const char* name, const double* x, i64 n, cudaStream_t st)
+{
+    if (!g_dbg_log) { cudaMalloc(&g_dbg_log, 256 * 16); cudaMemset(g_dbg_log, 0, 256 * 16); cudaDeviceSynchronize(); }
+    if (g_dbg_n >= 256) return;
+    snprintf(g_dbg_names[g_dbg_n], 48, "%s", name);
+    if (n > 0) k_dbg_sum<<<148 * 8, 256, 0, st>>>(x, n, g_dbg_log + 2 * g_dbg_n);
+    g_dbg_n++;
+}
+void debug_sum_flush(cudaStream_t st)
+{
+    if (!g_dbg_log || g_dbg_n == 0) return;
+    std::vector<double> h(2 * g_dbg_n);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), g_dbg_log, h.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < g_dbg_n; i++)
+        fprintf(stderr, "[dotsocp debug] %-40s sum|x|=%.15e nonfinite=%.0f\n", g_dbg_names[i], h[2 * i], h[2 * i + 1]);
+    cudaMemset(g_dbg_log, 0, 256 * 16);
+    g_dbg_n = 0;
 }
 
 __global__ void __launch_bounds__(256) k_halpern(double* __restrict__ x, double* __restrict__ xold, double* __restrict__ x0,

@@ -82,7 +82,10 @@ static T* to_device(const std::vector<T>& v)
 {
     T* d = nullptr;
     if (cudaMalloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
+    // a copy from pageable memory runs on the legacy stream, which is NOT ordered against the sessions' non-blocking streams (and
+    // may return before its last DMA has landed): wait for it here, the tables are read by kernels on other streams
     cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    cudaStreamSynchronize(0);
     return d;
 }
 
@@ -1231,6 +1234,34 @@ static PoissonPlan::GTab* slab_table(PoissonPlan* p, int t0, int t1, cudaStream_
     p->gtabs.push_back({-(i64)(t0 + 1), (i64)(t1 - t0), gtab, t_fix});
     return &p->gtabs.back();
 }
+// Build everything the first t-solve of a session would otherwise build lazily in the middle of the iteration stream: the
+// pivot table of the mode range (lines > 0: t_solve's [nt][lines] table for modes p0 ..; lines == 0: the slab table of levels
+// [t0, t1)) and the dense DCT matrix of the singular mode.  Called once per session right after the plan is created.
+int poisson_prepare(PoissonPlan* p, i64 p0, i64 lines, int t0, int t1, cudaStream_t st)
+{
+    const Geo& g = p->g;
+    if (!p->use_thomas || g.nt < 3) return 0;
+    if (lines > 0) {
+        bool have = false;
+        for (auto& e : p->gtabs) have = have || (e.p0 == p0 && e.lines == lines);
+        if (!have) {
+            double* gtab = nullptr;
+            int* t_fix = nullptr;
+            if (cudaMalloc(&gtab, (size_t)g.nt * lines * sizeof(double)) != cudaSuccess || cudaMalloc(&t_fix, (size_t)lines * sizeof(int)) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFree(gtab);
+                return dsocp_set_err(-4, "pivot table of the Thomas solve: out of device memory");
+            }
+            k_thomas_table<<<(unsigned)((lines + 255) / 256), 256, 0, st>>>(g.nt, g.ny, lines, lines, p0, p->lam_x, p->lam_y, gtab, t_fix);
+            p->gtabs.push_back({p0, lines, gtab, t_fix});
+        }
+    } else if (!slab_table(p, t0, t1, st, nullptr)) {
+        return dsocp_set_err(-4, "pivot table of the slab Thomas solve: out of device memory");
+    }
+    if (!p->cmat_t) p->cmat_t = dense_dct_matrix(g.nt);
+    return 0;
+}
+
 // forward elimination / back substitution of modes [m0, m1) on levels [t0, t1) of the natural-layout array `a`
 int poisson_thomas_slab(PoissonPlan* p, double* a, int t0, int t1, i64 m0, i64 m1, double D2, bool backward, const double* carry_in,
                         double* carry_out, cudaStream_t st, double* launches)

@@ -324,6 +324,22 @@ static int make_slab(dotsocp_ctx* c, int id)
         CU(cudaMalloc(&s->tsend, (size_t)(tr.tn1 - tr.tn0) * g.P * sizeof(double)));
         CU(cudaMalloc(&s->trecv, (size_t)g.nt * (s->p1 - s->p0) * sizeof(double)));
     }
+    if (const char* poison = getenv("DOTSOCP_POISON")) {
+        // debugging aid: everything a kernel must write before anybody reads it starts as NaN, so that a read of
+        // uninitialised memory shows up in the KKT rows of a small case instead of depending on what the allocator returned
+        if (poison[0] == '1') {
+            const double nan_ = std::numeric_limits<double>::quiet_NaN();
+            for (auto& x : s->n_all) { launch_fill(s->phi + x.b, x.e - x.b, nan_, c->st); launch_fill(s->rhs + x.b, x.e - x.b, nan_, c->st); }
+            if (s->side) launch_fill(s->side, mult_side_doubles(g, c->one_d, tr.tc1 - s->lo_c), nan_, c->st);
+            launch_fill(s->partial, (i64)partial_doubles(g, tr.tn1 - tr.tn0), nan_, c->st);
+            if (g.packed()) {
+                double* qa[] = {s->q[0], s->q[1], s->alpha, s->q2, s->qtmp};
+                for (double* a : qa) for (auto& x : s->q_all) launch_fill(a + x.b, x.e - x.b, nan_, c->st);
+                for (int k = 0; k < 2; k++) for (auto& x : s->b_all) launch_fill(s->beta[k] + x.b, x.e - x.b, nan_, c->st);
+            }
+            CU(cudaGetLastError());
+        }
+    }
     return 0;
 }
 
@@ -544,6 +560,22 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
         }
     }
     c->pp = poisson_plan_create(nt, nx, ny);
+    {
+        // Nothing is left to be built lazily inside the first Poisson solve, and the session starts with an idle device.  With the
+        // lazy construction (DOTSOCP_PREP=0) the first solve of a level occasionally returned a wrong singular-mode line when the
+        // host reached the table upload while the stream was still busy with the prologue -- about every second 3-level solve of
+        // 512x512x256 ended with hundreds of extra iterations on the last level (tools/diag_levels.py)
+        const char* pe = getenv("DOTSOCP_PREP");
+        if (!(pe && pe[0] == '0')) {
+            for (Slab* s : c->slabs) {
+                if (world == 1) rc = poisson_prepare(c->pp, 0, g.P, 0, 0, c->st);
+                else if (c->tpipe) rc = poisson_prepare(c->pp, 0, 0, s->tr.tn0, s->tr.tn1, c->st);
+                else rc = poisson_prepare(c->pp, s->p0, s->p1 - s->p0, 0, 0, c->st);
+                if (rc) { dotsocp_destroy(c); return rc; }
+            }
+            cudaDeviceSynchronize();
+        }
+    }
     { const char* kk = getenv("DOTSOCP_KKT"); c->fuse_kkt = !(kk && strcmp(kk, "separate") == 0); }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMalloc(&c->d_lvl, (size_t)nt * KSL * sizeof(double));
@@ -1191,7 +1223,22 @@ static int ensure_alloc(double*& p, i64 n)
     if (p) return 0;
     cudaError_t e = cudaMalloc(&p, (size_t)n * sizeof(double));
     if (e != cudaSuccess) { cudaGetLastError(); return set_err(DOTSOCP_ENOMEM, "cudaMalloc(%lld doubles): %s", (long long)n, cudaGetErrorString(e)); }
+    if (const char* poison = getenv("DOTSOCP_POISON"))
+        if (poison[0] == '1') { launch_fill(p, n, std::numeric_limits<double>::quiet_NaN(), 0); cudaDeviceSynchronize(); }
     return 0;
+}
+
+static bool dbg_sums() { static const bool on = [] { const char* e = getenv("DOTSOCP_DEBUG_SUMS"); return e && e[0] == '1'; }(); return on; }
+static void dbg_state(dotsocp_ctx* c, const char* tag, int point = 0)
+{
+    if (!dbg_sums() || c->world != 1) return;
+    Slab* s = c->slabs[0];
+    const Geo& g = c->g;
+    char nm[64];
+    auto one = [&](const char* a, const double* x, i64 n) { snprintf(nm, sizeof nm, "%d:%s %s", g.nx, tag, a); debug_sum(nm, x, n, c->st); };
+    one("phi", s->phi, g.N); one("rhs", s->rhs, g.N); one("q[0]", s->q[0], g.Q); one("q[1]", s->q[1], g.Q);
+    one("alpha", s->alpha, g.Q); one("q2", s->q2, g.Q); one("beta[0]", s->beta[0], 10 * g.L); one("beta[1]", s->beta[1], 10 * g.L);
+    if (point == 5) debug_sum_flush(c->st);
 }
 
 enum ArrKind { A_PHI, A_Q, A_ALPHA, A_BETA, A_ZMAT, A_C };
@@ -1523,7 +1570,9 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
         for (Slab* s : c->slabs)
             for (auto& x : s->n_all) { launch_shift(s->phi + x.b, x.e - x.b, shift, c->st); c->launches += 1; }
     }
+    dbg_state(c, "entry", 1);
     if (inpalm) L.prologue();   // z2 := d + BF q (:133) folded into the first z-step
+    dbg_state(c, "prologue", 2);
     if (palm) {                 // tmp_q = A*phi ; mexBFd(z, tmp_q, ...)   (PALM :137-138)
         UpdateArgs a = L.ua(S0);
         a.q_new = S0->q[1 - c->qcur];   // scratch: only tmpq_out matters here
@@ -1630,6 +1679,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             }
             cudaEvent_t e0 = mark();
             if ((rc = sgs ? L.step_sgs() : L.step_phi())) return rc;
+            if (it == 1) dbg_state(c, "it1 phi", 3);
             if (sgs && (checkSByS || sched || it == maxit)) {
                 // error of the sGS blocks (:212-216): ||A'(A phi - q + alpha) - c|| over the even nodes, q / alpha of the previous iterate
                 for (Slab* s : c->slabs) {
@@ -1641,7 +1691,9 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             cudaEvent_t e1 = mark();
             if ((rc = L.step_q(false, fused_check ? &kf : nullptr))) return rc;
             cudaEvent_t e2 = mark();
+            if (it == 1) dbg_state(c, "it1 q", 4);
             L.step_mult(fused_check ? &kf : nullptr);
+            if (it == 1) dbg_state(c, "it1 mult", 5);
             cudaEvent_t e3 = mark();
             segs.push_back({e0, e1, 0});
             segs.push_back({e1, e2, 2});
