@@ -209,8 +209,18 @@ int  poisson_t_chunk(PoissonPlan* p, double* buf, i64 chunk, i64 p0, double D2, 
 // whole time axis; lines == 0: the slab of levels [t0, t1) for the pipelined sweeps)
 int  poisson_prepare(PoissonPlan* p, i64 p0, i64 lines, int t0, int t1, cudaStream_t st);
 bool poisson_slab_thomas_ok(const PoissonPlan* p);
+// sync != NULL: the hand-off with the neighbouring GPUs happens inside the kernel (peer-memory stores + epoch flags) instead of
+// NCCL send / recv around it: wait until *wait_flag >= wait_value before reading carry_in (NULL: no wait); after the last CTA has
+// stored its part of carry_out (which then points into the neighbour's buffer) write signal_value to *signal_flag (NULL: no signal)
+struct SlabSync {
+    const int* wait_flag;
+    int wait_value;
+    int* done;            // CTA counter of this chunk (local, zero between launches)
+    int* signal_flag;     // the neighbour's flag (peer memory)
+    int signal_value;
+};
 int  poisson_thomas_slab(PoissonPlan* p, double* a, int t0, int t1, i64 m0, i64 m1, double D2, bool backward, const double* carry_in,
-                         double* carry_out, cudaStream_t st, double* launches);
+                         double* carry_out, cudaStream_t st, double* launches, const SlabSync* sync = nullptr);
 void poisson_line0_gather(PoissonPlan* p, const double* a, double* line, int t0, int t1, cudaStream_t st);
 void poisson_line0_solve(PoissonPlan* p, double* line, double D2, cudaStream_t st);
 void poisson_line0_scatter(PoissonPlan* p, double* a, const double* line, int t0, int t1, cudaStream_t st);

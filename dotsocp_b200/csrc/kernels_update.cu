@@ -542,10 +542,14 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
     extern __shared__ __align__(16) double dyn_smem[];
     double (*sh)[TU][NPL][TX][TY] = reinterpret_cast<double (*)[TU][NPL][TX][TY]>(dyn_smem);
     double (*shy)[4][TX] = reinterpret_cast<double (*)[4][TX]>(dyn_smem + 2 * TU * NPL * TX * TY);   // AL: [2][4][TX]
-    static_assert(PF != 2 || (AL && UPDATE && !KKT), "the bulk-copy ring exists for the aligned update kernel");
+    static_assert(PF < 2 || (AL && UPDATE && !KKT), "the bulk-copy ring exists for the aligned update kernel");
+    // PF == 2: two stages, 128 registers, two CTAs per SM ; PF == 3: three stages, one 255-register CTA per SM
+    constexpr bool RING = PF >= 2;
+    constexpr int NSTG = PF == 3 ? 3 : 2;
     typedef KmStage<TX, WEIGHTED> ST;
-    double* ring = dyn_smem + 2 * TU * NPL * TX * TY + 2 * 4 * TX;             // PF == 2: [2][ST::SIZE]
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + 2 * ST::SIZE);
+    double* ring = dyn_smem + 2 * TU * NPL * TX * TY + 2 * 4 * TX;             // RING: [NSTG][ST::SIZE]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + NSTG * ST::SIZE);
+    int rstage = 0;                                                            // ring stage of the step being computed
     const int ly = threadIdx.x, lx = threadIdx.y;
     // y tiles vary fastest over the grid so that CTAs running side by side stream adjacent pieces of the same rows
     const int x = AL ? blockIdx.y * TX + lx : blockIdx.y * (TX - 1) + lx, y = AL ? blockIdx.x * TY + ly : blockIdx.x * (TY - 1) + ly;
@@ -640,7 +644,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         }
     };
 
-    // ---- PF == 2: every warp starts the bulk copies of its own row for step tt into ring stage `stg` (one copy per lane) -----
+    // ---- RING: every warp starts the bulk copies of its own row for step tt into ring stage `stg` (one copy per lane) -----
     auto issue = [&](int tt, int stg) {
         const bool cellt = tt < g.nt - 1;
         const int xr = blockIdx.y * TX + lx, y0 = blockIdx.x * TY;
@@ -706,10 +710,10 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         // where the step's values come from: the prefetched register set (PF == 1) or HBM directly (PF == 0), every value
         // picked up where it is first needed
         const i64 o1x = (i64)(t + 1) * g.PBX, o1y = (i64)(t + 1) * g.PBY;
-        const double* stq = ring + (size_t)buf * ST::SIZE;      // PF == 2: this step's stage (buf == it & 1)
+        const double* stq = ring + (size_t)rstage * ST::SIZE;   // RING: this step's stage
         auto F = [&](int slot, const double* gaddr, double regval) -> double {
             if (PF == 1) return regval;
-            if (PF == 2) {
+            if (RING) {
                 // slots: 0..9 beta, 10 q_new0, 11 alpha0, 12..15 q_new bx[x-1], bx[x], by[y-1], by[y], 16 q_old0, 17..20 q_old likewise
                 if (slot <= 11) return stq[ST::Q0 + (slot * TX + lx) * 32 + ly];
                 if (slot == 16) return stq[ST::Q0 + (ST::S_QO * TX + lx) * 32 + ly];
@@ -728,7 +732,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
             al_xm = ld.al_xm; al_x = ld.al_x; al_ym = ld.al_ym; al_y = ld.al_y;
             wt_xm = ld.wt_xm; wt_x = ld.wt_x; wt_ym = ld.wt_ym; wt_y = ld.wt_y;
             k.cv = ld.cv;
-        } else if (PF == 2) {
+        } else if (RING) {
             if (owner) {
                 if (hxm) al_xm = stq[ST::BX + (ST::X_AL * (TX + 1) + lx) * 32 + ly];
                 if (hxp) al_x = stq[ST::BX + (ST::X_AL * (TX + 1) + lx + 1) * 32 + ly];
@@ -1010,8 +1014,8 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
             const int comp = ly / TX, r = ly - comp * TX, xx = blockIdx.y * TX + r;
             if (xx < g.nx) side[side_sy(sg, t, blockIdx.x, comp, xx)] = shy[buf][comp][r];
         }
-        // PF == 2: every warp has read its inputs of step t (barrier above): refill the stage with step t+2
-        if (PF == 2 && t + 2 < tr.tn1) issue(t + 2, buf);
+        // RING: every warp has read its inputs of step t (barrier above): refill the stage with step t + NSTG
+        if (RING && t + NSTG < tr.tn1) issue(t + NSTG, rstage);
         double ks[KM_COUNT];
         if (KKT) {
 #pragma unroll
@@ -1040,18 +1044,19 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
         }
     };
     int t = t_start, it = 0;
-    if (PF == 2) {
+    if (RING) {
         if (lx == 0 && ly == 0) {
-            mbar_init(&mbar[0], TX);      // one arrival per warp and phase
-            mbar_init(&mbar[1], TX);
+            for (int k = 0; k < NSTG; k++) mbar_init(&mbar[k], TX);      // one arrival per warp and phase
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        issue(t, 0);
-        if (t + 1 < tr.tn1) issue(t + 1, 1);
+        for (int k = 0; k < NSTG; k++)
+            if (t + k < tr.tn1) issue(t + k, k);
+        unsigned par = 0;
         for (; t < tr.tn1; t++, it++) {
-            mbar_wait(&mbar[it & 1], (unsigned)(it >> 1) & 1u);
+            mbar_wait(&mbar[rstage], par);
             step(t, it, MultLoad());
+            if (++rstage == NSTG) { rstage = 0; par ^= 1u; }
         }
     } else if (PF == 1) {
         // software pipeline, unrolled by two so that the two register sets swap roles without moves
@@ -1070,7 +1075,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
 }
 
 template <int TX, int TY, int PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool KKT, bool AL>
-__global__ void __launch_bounds__(TX* TY, (PF == 1 || KKT) ? 1 : 2)
+__global__ void __launch_bounds__(TX* TY, (PF == 1 || PF == 3 || KKT) ? 1 : 2)
 k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, SideGeo sg, double* __restrict__ side, const double* __restrict__ qo,
        const double* __restrict__ qn, const double* __restrict__ alpha, const double* __restrict__ weight,
        const double* __restrict__ beta, double* __restrict__ beta_out, double* __restrict__ q2, double* __restrict__ rhs,
@@ -1204,7 +1209,7 @@ int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cud
 #define KM(PF, W, O, U, K, AL)                                                                                        \
     {                                                                                                                 \
         constexpr size_t smem = (size_t)2 * (K ? 9 : 4) * TX * TY * sizeof(double) + (AL ? (size_t)2 * 4 * TX * sizeof(double) : 0) + \
-                                (PF == 2 ? (size_t)2 * KmStage<TX, W>::SIZE * sizeof(double) + 16 : 0);               \
+                                (PF >= 2 ? (size_t)(PF == 3 ? 3 : 2) * KmStage<TX, W>::SIZE * sizeof(double) + 32 : 0); \
         static int slots = 0;                                                                                         \
         if (!slots) {                                                                                                 \
             cudaFuncSetAttribute(k_mult<TX, TY, PF, W, O, U, K, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -1225,8 +1230,8 @@ int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cud
     } else if (one_d) {
         if (update) KM(0, false, true, true, false, false) else KM(0, false, true, false, false, false)
     } else if (al) {
-        if (weighted) { if (pf == 2) KM(2, true, false, true, false, true) else if (pf == 1) KM(1, true, false, true, false, true) else KM(0, true, false, true, false, true) }
-        else { if (pf == 2) KM(2, false, false, true, false, true) else if (pf == 1) KM(1, false, false, true, false, true) else KM(0, false, false, true, false, true) }
+        if (weighted) { if (pf == 3) KM(3, true, false, true, false, true) else if (pf == 2) KM(2, true, false, true, false, true) else if (pf == 1) KM(1, true, false, true, false, true) else KM(0, true, false, true, false, true) }
+        else { if (pf == 3) KM(3, false, false, true, false, true) else if (pf == 2) KM(2, false, false, true, false, true) else if (pf == 1) KM(1, false, false, true, false, true) else KM(0, false, false, true, false, true) }
         // the edges on the tile boundaries, from the side buffer
         const int nl = a.tr.tn1 - a.tr.tn0;
         const i64 nA = (i64)sg.nbx * a.g.py, nB = (i64)sg.nby * sg.nxp;

@@ -971,58 +971,100 @@ __device__ __forceinline__ double thomas_fixed_point(int nt, int tf, double nu)
     return g;
 }
 
+// Hand-off between the GPUs of neighbouring slabs without NCCL (SlabSync, kernels.h): the producer's kernel stores its carry
+// plane straight into the consumer's buffer (peer memory over NVLink) and, once all its CTAs have done so, publishes the solve's
+// epoch in the consumer's flag; the consumer's kernel -- already launched -- spins on that flag before it reads the plane.
+__device__ __forceinline__ void slab_wait(const SlabSync& sy)
+{
+    if (sy.wait_flag != nullptr) {
+        if (threadIdx.x == 0) {
+            int v;
+            const long long t_begin = clock64();
+            do {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(sy.wait_flag) : "memory");
+                if (v < sy.wait_value && clock64() - t_begin > 8000000000LL) {    // ~4 s: never hang the GPU on a lost signal
+                    if (blockIdx.x == 0) printf("[dotsocp] slab hand-off timed out: flag %p holds %d, waiting for %d\n", (const void*)sy.wait_flag, v, sy.wait_value);
+                    break;
+                }
+            } while (v < sy.wait_value);
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void slab_signal(const SlabSync& sy)
+{
+    if (sy.signal_flag != nullptr) {
+        __threadfence_system();              // this thread's carry stores are visible system-wide ...
+        __syncthreads();                     // ... for every thread of the CTA
+        if (threadIdx.x == 0) {
+            if (atomicAdd(sy.done, 1) == (int)gridDim.x - 1) {       // last CTA of the chunk
+                *sy.done = 0;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(sy.signal_flag), "r"(sy.signal_value) : "memory");
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_thomas_fwd_slab(int nt, int ny, i64 P, i64 m0, i64 m1, int t0, int t1, double inv_scale,
                                                          const double* __restrict__ lam_x, const double* __restrict__ lam_y,
                                                          const double* __restrict__ gtab, const int* __restrict__ t_fix,
-                                                         double* __restrict__ a, const double* __restrict__ carry_in,
-                                                         double* __restrict__ carry_out)
+                                                         double* __restrict__ a, const double* carry_in,
+                                                         double* __restrict__ carry_out, SlabSync sy)
 {
+    slab_wait(sy);
     const i64 p = m0 + blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    if (p >= m1 || p == 0) return;        // mode (0,0) is solved separately (k_tline0)
-    const int kx = (int)(p / ny), ky = (int)(p - (i64)kx * ny);
-    const double ct = (double)(nt - 1) * (double)(nt - 1);
-    const double nu = (lam_y[ky] + lam_x[kx]) / ct;
-    SlabG G{gtab, P, p, t0, nt, t_fix[p], 0.0};
-    if (G.tf < nt) G.gs = thomas_fixed_point(nt, G.tf, nu);
-    double d = t0 > 0 ? carry_in[p] : 0.0;
-    int t = t0;
-    for (; t + 4 <= t1; t += 4) {
-        double r[4], g[4];
+    // (no early return: slab_signal holds a CTA barrier, which every thread must reach from the same place)
+    if (p < m1 && p != 0) {        // mode (0,0) is solved separately (k_tline0)
+        const int kx = (int)(p / ny), ky = (int)(p - (i64)kx * ny);
+        const double ct = (double)(nt - 1) * (double)(nt - 1);
+        const double nu = (lam_y[ky] + lam_x[kx]) / ct;
+        SlabG G{gtab, P, p, t0, nt, t_fix[p], 0.0};
+        if (G.tf < nt) G.gs = thomas_fixed_point(nt, G.tf, nu);
+        double d = t0 > 0 ? __ldcg(carry_in + p) : 0.0;      // (written by the neighbour's GPU: not through the read-only path)
+        int t = t0;
+        for (; t + 4 <= t1; t += 4) {
+            double r[4], g[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { r[u] = a[(i64)(t + u) * P + p]; g[u] = G.at(t + u); }
+            for (int u = 0; u < 4; u++) { r[u] = a[(i64)(t + u) * P + p]; g[u] = G.at(t + u); }
 #pragma unroll
-        for (int u = 0; u < 4; u++) { d = __dmul_rn(__fma_rn(r[u], inv_scale, d), g[u]); a[(i64)(t + u) * P + p] = d; }
+            for (int u = 0; u < 4; u++) { d = __dmul_rn(__fma_rn(r[u], inv_scale, d), g[u]); a[(i64)(t + u) * P + p] = d; }
+        }
+        for (; t < t1; t++) { d = __dmul_rn(__fma_rn(a[(i64)t * P + p], inv_scale, d), G.at(t)); a[(i64)t * P + p] = d; }
+        if (t1 < nt) carry_out[p] = d;
     }
-    for (; t < t1; t++) { d = __dmul_rn(__fma_rn(a[(i64)t * P + p], inv_scale, d), G.at(t)); a[(i64)t * P + p] = d; }
-    if (t1 < nt) carry_out[p] = d;
+    slab_signal(sy);
 }
 
 __global__ void __launch_bounds__(256) k_thomas_bwd_slab(int nt, int ny, i64 P, i64 m0, i64 m1, int t0, int t1,
                                                          const double* __restrict__ lam_x, const double* __restrict__ lam_y,
                                                          const double* __restrict__ gtab, const int* __restrict__ t_fix,
-                                                         double* __restrict__ a, const double* __restrict__ carry_in,
-                                                         double* __restrict__ carry_out)
+                                                         double* __restrict__ a, const double* carry_in,
+                                                         double* __restrict__ carry_out, SlabSync sy)
 {
+    slab_wait(sy);
     const i64 p = m0 + blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    if (p >= m1 || p == 0) return;
-    const int kx = (int)(p / ny), ky = (int)(p - (i64)kx * ny);
-    const double ct = (double)(nt - 1) * (double)(nt - 1);
-    const double nu = (lam_y[ky] + lam_x[kx]) / ct;
-    SlabG G{gtab, P, p, t0, nt, t_fix[p], 0.0};
-    if (G.tf < nt) G.gs = thomas_fixed_point(nt, G.tf, nu);
-    double x;
-    int t;
-    if (t1 == nt) { x = a[(i64)(nt - 1) * P + p]; t = nt - 2; }     // last level: x = d
-    else { x = carry_in[p]; t = t1 - 1; }
-    for (; t - 3 >= t0; t -= 4) {
-        double dd[4], g[4];
+    if (p < m1 && p != 0) {
+        const int kx = (int)(p / ny), ky = (int)(p - (i64)kx * ny);
+        const double ct = (double)(nt - 1) * (double)(nt - 1);
+        const double nu = (lam_y[ky] + lam_x[kx]) / ct;
+        SlabG G{gtab, P, p, t0, nt, t_fix[p], 0.0};
+        if (G.tf < nt) G.gs = thomas_fixed_point(nt, G.tf, nu);
+        double x;
+        int t;
+        if (t1 == nt) { x = a[(i64)(nt - 1) * P + p]; t = nt - 2; }     // last level: x = d
+        else { x = __ldcg(carry_in + p); t = t1 - 1; }
+        for (; t - 3 >= t0; t -= 4) {
+            double dd[4], g[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { dd[u] = a[(i64)(t - u) * P + p]; g[u] = G.at(t - u); }
+            for (int u = 0; u < 4; u++) { dd[u] = a[(i64)(t - u) * P + p]; g[u] = G.at(t - u); }
 #pragma unroll
-        for (int u = 0; u < 4; u++) { x = __fma_rn(g[u], x, dd[u]); a[(i64)(t - u) * P + p] = x; }
+            for (int u = 0; u < 4; u++) { x = __fma_rn(g[u], x, dd[u]); a[(i64)(t - u) * P + p] = x; }
+        }
+        for (; t >= t0; t--) { x = __fma_rn(G.at(t), x, a[(i64)t * P + p]); a[(i64)t * P + p] = x; }
+        if (t0 > 0) carry_out[p] = x;       // x of my first level, for the slab below
     }
-    for (; t >= t0; t--) { x = __fma_rn(G.at(t), x, a[(i64)t * P + p]); a[(i64)t * P + p] = x; }
-    if (t0 > 0) carry_out[p] = x;       // x of my first level, for the slab below
+    slab_signal(sy);
 }
 
 // the singular mode: its nt values live one per level on the owning slabs; line[t] <-> a[t*P]
@@ -1264,8 +1306,9 @@ int poisson_prepare(PoissonPlan* p, i64 p0, i64 lines, int t0, int t1, cudaStrea
 
 // forward elimination / back substitution of modes [m0, m1) on levels [t0, t1) of the natural-layout array `a`
 int poisson_thomas_slab(PoissonPlan* p, double* a, int t0, int t1, i64 m0, i64 m1, double D2, bool backward, const double* carry_in,
-                        double* carry_out, cudaStream_t st, double* launches)
+                        double* carry_out, cudaStream_t st, double* launches, const SlabSync* sync)
 {
+    const SlabSync sy = sync ? *sync : SlabSync{nullptr, 0, nullptr, nullptr, 0};
     const Geo& g = p->g;
     if (m1 <= m0) return 0;
     PoissonPlan::GTab* tb = slab_table(p, t0, t1, st, launches);
@@ -1274,9 +1317,9 @@ int poisson_thomas_slab(PoissonPlan* p, double* a, int t0, int t1, i64 m0, i64 m
     const unsigned nb = (unsigned)((m1 - m0 + 255) / 256);
     if (!backward)
         k_thomas_fwd_slab<<<nb, 256, 0, st>>>(g.nt, g.ny, g.P, m0, m1, t0, t1, 1.0 / (D2 * ct), p->lam_x, p->lam_y, tb->tab, tb->t_fix, a,
-                                              carry_in, carry_out);
+                                              carry_in, carry_out, sy);
     else
-        k_thomas_bwd_slab<<<nb, 256, 0, st>>>(g.nt, g.ny, g.P, m0, m1, t0, t1, p->lam_x, p->lam_y, tb->tab, tb->t_fix, a, carry_in, carry_out);
+        k_thomas_bwd_slab<<<nb, 256, 0, st>>>(g.nt, g.ny, g.P, m0, m1, t0, t1, p->lam_x, p->lam_y, tb->tab, tb->t_fix, a, carry_in, carry_out, sy);
     if (launches) *launches += 1;
     return 0;
 }

@@ -120,6 +120,11 @@ struct Slab {
     double *partial_q = nullptr, *partial_m = nullptr;   // fused KKT partials (allocated at the first fused check)
     double *tsend = nullptr, *trecv = nullptr;   // transposed t-solve (DOTSOCP_TSOLVE=transpose)
     double* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // pipelined t-solve: forward in / out, backward in / out (P doubles each)
+    // ... with the hand-off inside the kernels (one process per GPU): xbuf = [forward in | backward in | flags] is ONE allocation
+    // (one CUDA-IPC handle) that the two neighbours map; carry[0] / carry[2] then point into it
+    double* xbuf = nullptr;
+    int *tflags = nullptr, *tdone = nullptr;        // epoch flags written by the neighbours (in xbuf) / local CTA counters
+    double *peer_up = nullptr, *peer_dn = nullptr;  // xbuf of slab id+1 / id-1 (peer memory)
     std::vector<double*> peer_tsend, peer_trecv;   // CUDA-IPC mappings of the other ranks' transpose buffers (NCCL mode)
     // direct exchange (kernels store into the destination slab's buffer): device tables of `world` pointers
     //   d_fwd[b] = row tn0 of the t-solve buffer (trecv) of slab b   -- written by this slab's forward x pass
@@ -136,6 +141,10 @@ struct Slab {
         for (double* p : peer_trecv) if (p) cudaIpcCloseMemHandle(p);
         cudaFree(c0); cudaFree(c1); cudaFree(partial); cudaFree(side); cudaFree(partial_q); cudaFree(partial_m); cudaFree(tsend); cudaFree(trecv);
         cudaFree(tmpq); cudaFree(d_fwd); cudaFree(d_bwd);
+        if (peer_up) cudaIpcCloseMemHandle(peer_up);
+        if (peer_dn) cudaIpcCloseMemHandle(peer_dn);
+        if (xbuf) { carry[0] = carry[2] = nullptr; cudaFree(xbuf); }
+        cudaFree(tdone);
         for (double* p : carry) cudaFree(p);
         for (int i = 0; i < 5; i++) { cudaFree(old_[i]); cudaFree(anc_[i]); }
     }
@@ -163,6 +172,8 @@ struct dotsocp_ctx {
     // DOTSOCP_TRACE=1: device time of the phases of the distributed Poisson solve (printed by rank/slab 0 at destroy)
     bool trace = false;
     bool tpipe = false;         // t-solve of the slabs by the pipelined Thomas sweeps (default) instead of transposes
+    bool tpush = false;         // ... whose carry planes go GPU to GPU inside the kernels (peer stores + epoch flags), not by NCCL
+    int tepoch = 0;             // ... number of the current solve (the value the flags are compared with)
     int tchunks = 1;            // ... with the modes cut into this many chunks so that consecutive slabs overlap
     double* d_line0 = nullptr;  // ... the singular mode's nt values
     bool ipc = false;           // transposes by peer-to-peer copies (copy engines over NVLink) instead of NCCL send/recv
@@ -228,7 +239,7 @@ extern "C" void dotsocp_destroy(dotsocp_ctx* c)
                 "t-solve %.3f | all-to-all back + (x,y) inverse %.3f | phi ghost %.3f\n", c->tcount, c->tacc[0] / c->tcount,
                 c->tacc[1] / c->tcount, c->tacc[2] / c->tcount, c->tacc[3] / c->tcount, c->tacc[4] / c->tcount);
     for (auto e : c->tev) cudaEventDestroy(e);
-    if (c->ipc && c->comm && c->barrier_buf) {   // nobody may unmap / free while a peer can still touch the buffers
+    if ((c->ipc || c->tpush) && c->comm && c->barrier_buf) {   // nobody may unmap / free while a peer can still touch the buffers
         nccl_api().AllReduce(c->barrier_buf, c->barrier_buf, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->st);
         cudaStreamSynchronize(c->st);
     }
@@ -465,6 +476,78 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
         dotsocp_destroy(c);
         return rc;
     }
+    if (c->comm && c->tpipe) {
+        // Pipelined sweeps, one process per GPU: map the neighbours' carry-in planes and flags (CUDA IPC) so that the Thomas kernels
+        // hand their boundary plane over themselves -- a peer store and a flag instead of an ncclSend / ncclRecv pair per chunk
+        // and direction (2 x 8 x ~25 us per solve on 8 GPUs).  DOTSOCP_TPUSH=0, or any failure here, keeps the NCCL hand-off.
+        const char* tp = getenv("DOTSOCP_TPUSH");
+        Slab* s = c->slabs[0];
+        const size_t xdoubles = (size_t)2 * g.P + 64;
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof mine);
+        bool ok = !(tp && tp[0] == '0') && cudaMalloc(&c->barrier_buf, 64) == cudaSuccess && cudaMalloc(&s->xbuf, xdoubles * sizeof(double)) == cudaSuccess &&
+                  cudaMalloc(&s->tdone, 128 * sizeof(int)) == cudaSuccess;
+        if (ok) {
+            cudaMemset(c->barrier_buf, 0, 64);
+            cudaMemset(s->xbuf, 0, xdoubles * sizeof(double));
+            cudaMemset(s->tdone, 0, 128 * sizeof(int));
+            cudaDeviceSynchronize();
+            ok = cudaIpcGetMemHandle(&mine, s->xbuf) == cudaSuccess;
+        }
+        cudaGetLastError();
+        // every rank takes part in the collectives even if its own export failed (flag byte), to stay in lock-step
+        const size_t hb = sizeof(cudaIpcMemHandle_t), slot = hb + 8;
+        std::vector<char> sendb(slot, 0), recvb(slot * world);
+        memcpy(sendb.data(), &mine, hb);
+        sendb[hb] = ok ? 1 : 0;
+        char* dall = nullptr;
+        bool all_ok = false;
+        if (cudaMalloc(&dall, slot * (world + 1)) == cudaSuccess) {
+            cudaMemcpyAsync(dall + slot * world, sendb.data(), slot, cudaMemcpyHostToDevice, c->st);
+            int r_ = nccl_api().AllGather(dall + slot * world, dall, slot, NCCL_INT8, c->comm, c->st);
+            cudaMemcpyAsync(recvb.data(), dall, slot * world, cudaMemcpyDeviceToHost, c->st);
+            cudaStreamSynchronize(c->st);
+            cudaFree(dall);
+            all_ok = r_ == 0;
+            for (int r = 0; r < world; r++) all_ok = all_ok && recvb[slot * r + hb] == 1;
+            if (all_ok) {
+                for (int nb = 0; nb < 2 && all_ok; nb++) {
+                    const int r = nb == 0 ? rank + 1 : rank - 1;
+                    if (r < 0 || r >= world) continue;
+                    cudaIpcMemHandle_t hh;
+                    memcpy(&hh, recvb.data() + slot * r, hb);
+                    void* pp_ = nullptr;
+                    if (cudaIpcOpenMemHandle(&pp_, hh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { all_ok = false; cudaGetLastError(); }
+                    (nb == 0 ? s->peer_up : s->peer_dn) = (double*)pp_;
+                }
+            }
+            // agree collectively (a rank that failed to open a handle disables the path for everybody)
+            if (c->barrier_buf) {
+                double flag = all_ok ? 0.0 : 1.0;
+                cudaMemcpyAsync(c->barrier_buf, &flag, sizeof(double), cudaMemcpyHostToDevice, c->st);
+                nccl_api().AllReduce(c->barrier_buf, c->barrier_buf, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->st);
+                cudaMemcpyAsync(&flag, c->barrier_buf, sizeof(double), cudaMemcpyDeviceToHost, c->st);
+                cudaStreamSynchronize(c->st);
+                all_ok = all_ok && flag == 0.0;
+            } else
+                all_ok = false;
+        }
+        cudaGetLastError();
+        c->tpush = all_ok;
+        if (c->trace) fprintf(stderr, "[dotsocp trace] rank %d: in-kernel carry hand-off %s (xbuf %p, up %p, down %p)\n", rank, c->tpush ? "on" : "off",
+                              (void*)s->xbuf, (void*)s->peer_up, (void*)s->peer_dn);
+        if (c->tpush) {
+            cudaFree(s->carry[0]); cudaFree(s->carry[2]);
+            s->carry[0] = s->xbuf;
+            s->carry[2] = s->xbuf + g.P;
+            s->tflags = reinterpret_cast<int*>(s->xbuf + 2 * g.P);
+        } else {
+            if (s->peer_up) { cudaIpcCloseMemHandle(s->peer_up); s->peer_up = nullptr; }
+            if (s->peer_dn) { cudaIpcCloseMemHandle(s->peer_dn); s->peer_dn = nullptr; }
+            cudaFree(s->xbuf); s->xbuf = nullptr;
+            cudaGetLastError();
+        }
+    }
     if (c->comm && !c->tpipe) {
         // exchange CUDA-IPC handles of the transpose buffers; any failure just keeps the NCCL send/recv path
         const char* noipc = getenv("DOTSOCP_NO_IPC");
@@ -689,7 +772,8 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
         poisson_line0_solve(c->pp, c->d_line0, D2, st);
         for (Slab* s : c->slabs) poisson_line0_scatter(c->pp, s->phi, c->d_line0, s->tr.tn0, s->tr.tn1, st);
         c->launches += 1 + 2.0 * c->slabs.size();
-        const int K = (int)std::max<i64>(1, std::min<i64>(c->tchunks, g.P / 1024 + 1));
+        const int K = (int)std::max<i64>(1, std::min<i64>(std::min(c->tchunks, 64), g.P / 1024 + 1));
+        if (c->tpush) c->tepoch++;
         for (int dir = 0; dir < 2; dir++) {            // 0: forward elimination (ascending slabs), 1: back substitution (descending)
             const bool bwd = dir == 1;
             for (int k = 0; k < K; k++) {
@@ -699,6 +783,21 @@ static int solve_poisson(dotsocp_ctx* c, double D2)
                     Slab* s = c->slabs[bwd ? ns - 1 - i : i];
                     const int from = bwd ? s->id + 1 : s->id - 1, to = bwd ? s->id - 1 : s->id + 1;
                     const bool has_in = from >= 0 && from < c->world, has_out = to >= 0 && to < c->world;
+                    if (c->tpush) {
+                        // hand-off inside the kernel: wait for the neighbour's flag of this chunk, store the carry plane into the
+                        // next slab's buffer, publish the epoch there (flags: [0, 64) forward chunks, [64, 128) backward chunks)
+                        SlabSync sy{nullptr, c->tepoch, s->tdone + dir * 64 + k, nullptr, c->tepoch};
+                        if (has_in) sy.wait_flag = s->tflags + dir * 64 + k;
+                        double* peer = bwd ? s->peer_dn : s->peer_up;      // xbuf of the slab the carry goes to
+                        double* out = s->carry[bwd ? 3 : 1];
+                        if (has_out) {
+                            out = bwd ? peer + g.P : peer;                 // its backward-in / forward-in plane
+                            sy.signal_flag = reinterpret_cast<int*>(peer + 2 * g.P) + dir * 64 + k;
+                        }
+                        if ((rc = poisson_thomas_slab(c->pp, s->phi, s->tr.tn0, s->tr.tn1, m0, m1, D2, bwd, has_in ? s->carry[bwd ? 2 : 0] : nullptr,
+                                                      out, st, &c->launches, &sy))) return rc;
+                        continue;
+                    }
                     double* cin = s->carry[bwd ? 2 : 0];
                     double* cout = s->carry[bwd ? 3 : 1];
                     const double* in_ptr = nullptr;

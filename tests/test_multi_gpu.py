@@ -10,10 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("env", [{}, {"DOTSOCP_TCHUNKS": "1"}, {"DOTSOCP_TSOLVE": "transpose"},
+@pytest.mark.parametrize("env", [{}, {"DOTSOCP_TCHUNKS": "1"}, {"DOTSOCP_TPUSH": "0"}, {"DOTSOCP_TSOLVE": "transpose"},
                                  {"DOTSOCP_TSOLVE": "transpose", "DOTSOCP_NO_IPC": "1"},
                                  {"DOTSOCP_TSOLVE": "transpose", "DOTSOCP_XCHG": "direct"}],
-                         ids=["pipelined-thomas", "pipelined-1-chunk", "transpose-ipc-push", "transpose-nccl-sendrecv", "transpose-direct-stores"])
+                         ids=["pipelined-thomas", "pipelined-1-chunk", "pipelined-nccl-handoff", "transpose-ipc-push", "transpose-nccl-sendrecv", "transpose-direct-stores"])
 def test_nccl_time_slab_parity(gpu, env):
     if gpu < 2:
         pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
