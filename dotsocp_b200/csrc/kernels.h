@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <cuda.h>
+
 #include <vector>
 
 namespace dsocp {
@@ -18,6 +20,16 @@ void launch_projsoc(i64 M, int N, const double* in, double* out, cudaStream_t st
 
 // ---- fused iteration kernels --------------------------------------------------------------------------------
 struct KktFused;
+// tensor maps (TMA descriptors) of the arrays one step of the aligned k_mult reads (DOTSOCP_KM_PF=4): the 10 planes of beta as
+// one 4-D view, and q0 / bx / by views of q_new, q_old, alpha and the weight
+struct KmMaps {
+    CUtensorMap beta;
+    CUtensorMap qn[3], qo[3], al[3], w[3];
+};
+// q0 / bx / by views of one staggered array (q0: box 32 x TX cells; bx: TX + 1 rows from x0 - 1; by: 34 columns from y0 - 2)
+// and the 4-D view of a 10-plane array; 0 on success
+int make_stag_maps(const Geo& g, const double* base, CUtensorMap out[3]);
+int make_beta_map(const Geo& g, const double* base, CUtensorMap* out);
 struct UpdateArgs {
     Geo g;
     TRange tr;
@@ -38,6 +50,7 @@ struct UpdateArgs {
     // side buffer of the aligned march (mult_side_doubles), NULL: haloed tiling; covers cell layers [side_t0, side_t0 + side_layers)
     double* side;
     int side_t0, side_layers;
+    const KmMaps* maps;     // NULL: no tensor maps (DOTSOCP_KM_PF=4 then falls back to the register prefetch)
 };
 // q_new = ((A phi + alpha) + q2) .* diagQInv ; alpha += tau (A phi - q_new)      (solver_socp_inPALM.m:204-214)
 // acc: alpha = (alpha + A phi) - q_new                                            (solver_socp_accADMM.m:237)

@@ -10,6 +10,7 @@
 // All kernels are HBM-bound streaming kernels: warps run along y (coalesced), k_mult marches along t.
 #include "kernels.h"
 #include "reduce.cuh"
+#include "vmm.h"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -410,8 +411,12 @@ void launch_qstep(const UpdateArgs& a, bool weighted, bool acc, cudaStream_t st,
 // ncu on the round-1 kernel: 55 % of the warp samples waited on the first use of a step's loads (long scoreboard), i.e. the
 // HBM latency was exposed once per step.  PF = true keeps the loaded values of step t+1 in a second register set that is
 // filled BEFORE step t is computed (software pipeline, one 255-register CTA per SM), so a step's loads have a whole step of
-// arithmetic to arrive.  PF = 0 is the round-1 schedule (two 128-register CTAs per SM, loads then compute); DOTSOCP_KM_PF
-// selects at run time.  (A cp.async shared-memory ring and a cp.async.bulk / mbarrier ring were measured slower, profiles/README.md.)
+// arithmetic to arrive.  PF = 0 is the round-1 schedule (two 128-register CTAs per SM, loads then compute).  PF = 4 (the
+// default on the aligned tiling): one thread per CTA issues the step's inputs as TMA tensor loads (cp.async.bulk.tensor, 10
+// boxes per step, the ten beta planes in one) into a two-stage shared-memory ring guarded by mbarriers, one step and a half
+// ahead; the arithmetic reads its operands from shared memory, which leaves 128 registers (two CTAs per SM) AND a deep
+// prefetch -- 4.13 -> 3.50 ms at 512x512x256.  PF = 2 / 3 fill the same ring with one 256-byte cp.async.bulk per row and
+// stream (155 per step): slower than PF = 1, the TMA unit cannot issue that many small copies.  DOTSOCP_KM_PF selects at run time.
 //
 // KKT (check iterations): the same march also accumulates every KKT term that lives on the data in registers
 // (solver_socp_inPALM.m:225-244, compute_kkt_dot_complement.m) -- z, beta, z2, alpha and q are all there -- and leaves one
@@ -431,7 +436,7 @@ __device__ __forceinline__ double uval(double q, double a, double w)
 #define KM_TY 32         // tile columns (y, contiguous) per CTA: one warp per tile row
 #endif
 #ifndef KM_PF
-#define KM_PF 1          // default of DOTSOCP_KM_PF: register prefetch of the next time step in the update kernel
+#define KM_PF 4          // default of DOTSOCP_KM_PF: TMA tensor loads into a two-stage shared-memory ring (aligned tiling; else 1)
 #endif
 
 struct KktDev {          // scalars of the fused KKT terms
@@ -492,7 +497,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// shared-memory image of one step's inputs (PF == 2): rows of the tile, bx rows x0-1 .. x0+TX-1, by rows with columns y0-2 .. y0+31
+// tensor (tiled) copies: one instruction moves a whole box of a tensor map; out-of-range parts arrive as zeros
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+// shared-memory image of one step's inputs (PF >= 2): rows of the tile, bx rows x0-1 .. x0+TX-1, by rows with columns y0-2 .. y0+31
 template <int TX, bool WEIGHTED>
 struct KmStage {
     static constexpr int NQ0 = 13 + (WEIGHTED ? 1 : 0);   // beta 0..9, q_new0, alpha0, q_old0 [, weight0]
@@ -528,7 +544,7 @@ __host__ __device__ __forceinline__ i64 side_sy(const SideGeo& sg, int t, int ky
 
 template <int TX, int TY, int PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool EDGE, bool KKT, bool AL>
 __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int kkt_t0, const IterScal& sc, const KktDev& kd,
-                                            const SideGeo& sg, double* __restrict__ side,
+                                            const SideGeo& sg, double* __restrict__ side, const KmMaps& maps,
                                             const double* __restrict__ qo, const double* __restrict__ qn,
                                             const double* __restrict__ alpha, const double* __restrict__ weight,
                                             const double* __restrict__ beta, double* __restrict__ beta_out,
@@ -539,12 +555,16 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
     static_assert(!AL || (!KKT && !ONE_D && TY == 32 && 4 * TX <= 32), "aligned tiling: plain 2-D update / prologue kernels");
     constexpr int TU = 1;
     constexpr int NPL = KKT ? 9 : 4;   // exchange planes: w1,w3,w5,w7 (+ b1,b3,b5,b7, rho)
-    extern __shared__ __align__(16) double dyn_smem[];
+    extern __shared__ __align__(128) double dyn_smem[];
     double (*sh)[TU][NPL][TX][TY] = reinterpret_cast<double (*)[TU][NPL][TX][TY]>(dyn_smem);
     double (*shy)[4][TX] = reinterpret_cast<double (*)[4][TX]>(dyn_smem + 2 * TU * NPL * TX * TY);   // AL: [2][4][TX]
     static_assert(PF < 2 || (AL && UPDATE && !KKT), "the bulk-copy ring exists for the aligned update kernel");
-    // PF == 2: two stages, 128 registers, two CTAs per SM ; PF == 3: three stages, one 255-register CTA per SM
+    // PF == 2: two stages, 128 registers, two CTAs per SM ; PF == 3: three stages, one 255-register CTA per SM ; both filled by
+    // one 256-byte bulk copy per row and stream.  PF == 4: two stages filled by TENSOR copies -- one thread issues 10 (13
+    // weighted) box loads per step (the 10 beta planes are one 20 KB box) instead of 155 row copies, which the TMA unit cannot
+    // issue fast enough (profiles/README.md)
     constexpr bool RING = PF >= 2;
+    constexpr bool TENSOR = PF == 4;
     constexpr int NSTG = PF == 3 ? 3 : 2;
     typedef KmStage<TX, WEIGHTED> ST;
     double* ring = dyn_smem + 2 * TU * NPL * TX * TY + 2 * 4 * TX;             // RING: [NSTG][ST::SIZE]
@@ -646,6 +666,34 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
 
     // ---- RING: every warp starts the bulk copies of its own row for step tt into ring stage `stg` (one copy per lane) -----
     auto issue = [&](int tt, int stg) {
+        if (TENSOR) {
+            if (lx == 0 && ly == 0) {
+                const bool cellt_ = tt < g.nt - 1;
+                double* stage_ = ring + (size_t)stg * ST::SIZE;
+                const int x0_ = blockIdx.y * TX, y0_ = blockIdx.x * TY;
+                constexpr unsigned BQ = TX * 32 * 8, BB = 10 * BQ, BXB = (TX + 1) * 32 * 8, BYB = TX * ST::BYW * 8;
+                const unsigned nlev = 1 + (WEIGHTED ? 1 : 0);                       // alpha (+ weight) on node level tt
+                const unsigned ncell = 3 + (WEIGHTED ? 1 : 0);                      // q_new0, alpha0, q_old0 (+ weight0)
+                const unsigned total = nlev * (BXB + BYB) + (cellt_ ? BB + ncell * BQ + 2 * (BXB + BYB) : 0);
+                mbar_arrive_expect_tx(&mbar[stg], total);
+                unsigned long long* bar = &mbar[stg];
+                auto q0 = [&](int slot, const CUtensorMap* m) { tma_load_3d(stage_ + ST::Q0 + slot * TX * 32, m, y0_, x0_, tt, bar); };
+                auto bxy = [&](int k, const CUtensorMap* m, int lvl) {
+                    tma_load_3d(stage_ + ST::BX + k * (TX + 1) * 32, m + 1, y0_, x0_ - 1, lvl, bar);
+                    tma_load_3d(stage_ + ST::BY + k * TX * ST::BYW, m + 2, y0_ - 2, x0_, lvl, bar);
+                };
+                if (cellt_) {
+                    tma_load_4d(stage_ + ST::Q0, &maps.beta, y0_, x0_, tt, 0, bar);
+                    q0(ST::S_QN, maps.qn); q0(ST::S_A0, maps.al); q0(ST::S_QO, maps.qo);
+                    if (WEIGHTED) q0(ST::S_W0, maps.w);
+                    bxy(ST::X_QN, maps.qn, tt + 1);
+                    bxy(ST::X_QO, maps.qo, tt + 1);
+                }
+                bxy(ST::X_AL, maps.al, tt);
+                if (WEIGHTED) bxy(ST::X_W, maps.w, tt);
+            }
+            return;
+        }
         const bool cellt = tt < g.nt - 1;
         const int xr = blockIdx.y * TX + lx, y0 = blockIdx.x * TY;
         const bool row = xr < g.nx, rowx = xr < g.nx - 1;
@@ -1046,7 +1094,7 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
     int t = t_start, it = 0;
     if (RING) {
         if (lx == 0 && ly == 0) {
-            for (int k = 0; k < NSTG; k++) mbar_init(&mbar[k], TX);      // one arrival per warp and phase
+            for (int k = 0; k < NSTG; k++) mbar_init(&mbar[k], TENSOR ? 1 : TX);      // one arrival per warp (issuing thread) and phase
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
@@ -1076,7 +1124,8 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
 
 template <int TX, int TY, int PF, bool WEIGHTED, bool ONE_D, bool UPDATE, bool KKT, bool AL>
 __global__ void __launch_bounds__(TX* TY, (PF == 1 || PF == 3 || KKT) ? 1 : 2)
-k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, SideGeo sg, double* __restrict__ side, const double* __restrict__ qo,
+k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, SideGeo sg, double* __restrict__ side, const __grid_constant__ KmMaps maps,
+       const double* __restrict__ qo,
        const double* __restrict__ qn, const double* __restrict__ alpha, const double* __restrict__ weight,
        const double* __restrict__ beta, double* __restrict__ beta_out, double* __restrict__ q2, double* __restrict__ rhs,
        const double* __restrict__ c0, const double* __restrict__ c1, double* __restrict__ kpart)
@@ -1092,10 +1141,10 @@ k_mult(Geo g, TRange tr, int nchunk, IterScal sc, KktDev kd, SideGeo sg, double*
     const int x0 = blockIdx.y * (AL ? TX : TX - 1), y0 = blockIdx.x * (AL ? TY : TY - 1);
     const bool interior = !ONE_D && x0 >= 1 && x0 + TX - 1 <= g.nx - 2 && y0 >= 1 && y0 + TY - 1 <= g.ny - 2;
     if (interior)
-        k_mult_body<TX, TY, PF, WEIGHTED, ONE_D, UPDATE, false, KKT, AL>(g, tr, kkt_t0, sc, kd, sg, side, qo, qn, alpha, weight, beta,
+        k_mult_body<TX, TY, PF, WEIGHTED, ONE_D, UPDATE, false, KKT, AL>(g, tr, kkt_t0, sc, kd, sg, side, maps, qo, qn, alpha, weight, beta,
                                                                          beta_out, q2, rhs, c0, c1, kpart);
     else
-        k_mult_body<TX, TY, PF, WEIGHTED, ONE_D, UPDATE, true, KKT, AL>(g, tr, kkt_t0, sc, kd, sg, side, qo, qn, alpha, weight, beta,
+        k_mult_body<TX, TY, PF, WEIGHTED, ONE_D, UPDATE, true, KKT, AL>(g, tr, kkt_t0, sc, kd, sg, side, maps, qo, qn, alpha, weight, beta,
                                                                         beta_out, q2, rhs, c0, c1, kpart);
 }
 
@@ -1178,6 +1227,28 @@ i64 mult_side_doubles(const Geo& g, bool one_d, int nlayers)
     return (i64)nlayers * (sg.sx_t + sg.sy_t);
 }
 
+int make_stag_maps(const Geo& g, const double* base, CUtensorMap out[3])
+{
+    if (!mult_aligned_ok(g, false) || g.nt < 2 || g.nx < 2) return -1;
+    const unsigned long long py = g.py, pyb = g.pyb;
+    const unsigned long long d0[3] = {py, (unsigned long long)g.nx, (unsigned long long)(g.nt - 1)}, s0[2] = {py * 8, (unsigned long long)g.PC * 8};
+    const unsigned long long d1[3] = {py, (unsigned long long)(g.nx - 1), (unsigned long long)g.nt}, s1[2] = {py * 8, (unsigned long long)g.PBX * 8};
+    const unsigned long long d2[3] = {pyb, (unsigned long long)g.nx, (unsigned long long)g.nt}, s2[2] = {pyb * 8, (unsigned long long)g.PBY * 8};
+    const unsigned b0[3] = {32, KM_TX, 1}, b1[3] = {32, KM_TX + 1, 1}, b2[3] = {KmStage<KM_TX, false>::BYW, KM_TX, 1};
+    if (make_tensor_map_f64(&out[0], base, 3, d0, s0, b0)) return -1;
+    if (make_tensor_map_f64(&out[1], base + g.L, 3, d1, s1, b1)) return -1;
+    if (make_tensor_map_f64(&out[2], base + g.L + g.NBX, 3, d2, s2, b2)) return -1;
+    return 0;
+}
+int make_beta_map(const Geo& g, const double* base, CUtensorMap* out)
+{
+    if (!mult_aligned_ok(g, false) || g.nt < 2) return -1;
+    const unsigned long long d[4] = {(unsigned long long)g.py, (unsigned long long)g.nx, (unsigned long long)(g.nt - 1), 10};
+    const unsigned long long s[3] = {(unsigned long long)g.py * 8, (unsigned long long)g.PC * 8, (unsigned long long)g.L * 8};
+    const unsigned b[4] = {32, KM_TX, 1, 10};
+    return make_tensor_map_f64(out, base, 4, d, s, b);
+}
+
 int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st, const KktFused* kkt)
 {
     int nlaunch = 1;
@@ -1199,7 +1270,10 @@ int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cud
     // piece costs one replayed cell layer.  DOTSOCP_KM_CHUNKS=n forces n pieces.
     static const int forced = [] { const char* e = getenv("DOTSOCP_KM_CHUNKS"); return e ? atoi(e) : 0; }();
     const char* pf_env = getenv("DOTSOCP_KM_PF");   // read per launch: tests and A/B runs switch it inside one process
-    const int pf = pf_env ? atoi(pf_env) : KM_PF;
+    int pf = pf_env ? atoi(pf_env) : KM_PF;
+    if (pf == 4 && a.maps == nullptr) pf = 1;
+    static const KmMaps no_maps = KmMaps();
+    const KmMaps& maps = a.maps ? *a.maps : no_maps;
     // aligned tiling (pitched layout, side buffer present, plain update kernel); DOTSOCP_KM_AL=0 keeps the haloed tiling
     const char* al_env = getenv("DOTSOCP_KM_AL");
     const bool al = update && !kkt && a.side != nullptr && mult_aligned_ok(a.g, one_d) && !(al_env && al_env[0] == '0');
@@ -1209,7 +1283,7 @@ int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cud
 #define KM(PF, W, O, U, K, AL)                                                                                        \
     {                                                                                                                 \
         constexpr size_t smem = (size_t)2 * (K ? 9 : 4) * TX * TY * sizeof(double) + (AL ? (size_t)2 * 4 * TX * sizeof(double) : 0) + \
-                                (PF >= 2 ? (size_t)(PF == 3 ? 3 : 2) * KmStage<TX, W>::SIZE * sizeof(double) + 32 : 0); \
+                                (PF >= 2 ? (size_t)(PF == 3 ? 3 : 2) * KmStage<TX, W>::SIZE * sizeof(double) + 32 + 128 : 0); \
         static int slots = 0;                                                                                         \
         if (!slots) {                                                                                                 \
             cudaFuncSetAttribute(k_mult<TX, TY, PF, W, O, U, K, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -1222,7 +1296,7 @@ int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cud
         const int nchunk = forced > 0 ? std::min(forced, std::max(1, a.tr.tc1 - a.tr.tc0))                            \
                                       : km_pick_chunks((long long)grid.x * grid.y, a.tr.tc1 - a.tr.tc0, slots);       \
         grid.z = (unsigned)nchunk;                                                                                    \
-        k_mult<TX, TY, PF, W, O, U, K, AL><<<grid, block, smem, st>>>(a.g, a.tr, nchunk, a.sc, kd, sg, a.side, a.q_old, a.q_new, \
+        k_mult<TX, TY, PF, W, O, U, K, AL><<<grid, block, smem, st>>>(a.g, a.tr, nchunk, a.sc, kd, sg, a.side, maps, a.q_old, a.q_new, \
                                                                       a.alpha, a.weight, a.beta_in, a.beta_out, a.q2, a.rhs, a.c0, a.c1, kpart); \
     }
     if (kkt && update) {
@@ -1230,8 +1304,8 @@ int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cud
     } else if (one_d) {
         if (update) KM(0, false, true, true, false, false) else KM(0, false, true, false, false, false)
     } else if (al) {
-        if (weighted) { if (pf == 3) KM(3, true, false, true, false, true) else if (pf == 2) KM(2, true, false, true, false, true) else if (pf == 1) KM(1, true, false, true, false, true) else KM(0, true, false, true, false, true) }
-        else { if (pf == 3) KM(3, false, false, true, false, true) else if (pf == 2) KM(2, false, false, true, false, true) else if (pf == 1) KM(1, false, false, true, false, true) else KM(0, false, false, true, false, true) }
+        if (weighted) { if (pf == 4) KM(4, true, false, true, false, true) else if (pf == 3) KM(3, true, false, true, false, true) else if (pf == 2) KM(2, true, false, true, false, true) else if (pf == 1) KM(1, true, false, true, false, true) else KM(0, true, false, true, false, true) }
+        else { if (pf == 4) KM(4, false, false, true, false, true) else if (pf == 3) KM(3, false, false, true, false, true) else if (pf == 2) KM(2, false, false, true, false, true) else if (pf == 1) KM(1, false, false, true, false, true) else KM(0, false, false, true, false, true) }
         // the edges on the tile boundaries, from the side buffer
         const int nl = a.tr.tn1 - a.tr.tn0;
         const i64 nA = (i64)sg.nbx * a.g.py, nB = (i64)sg.nby * sg.nxp;

@@ -117,6 +117,10 @@ struct Slab {
            *weight = nullptr, *beta[2] = {nullptr, nullptr};
     double *c0 = nullptr, *c1 = nullptr, *partial = nullptr;
     double* side = nullptr;                              // side buffer of the aligned k_mult (kernels.h: mult_side_doubles)
+    // tensor maps of the arrays k_mult streams (DOTSOCP_KM_PF=4); km = the set of the current launch
+    bool maps_ok = false;
+    CUtensorMap tm_beta[2], tm_q[2][3], tm_alpha[3], tm_w[3];
+    KmMaps km;
     double *partial_q = nullptr, *partial_m = nullptr;   // fused KKT partials (allocated at the first fused check)
     double *tsend = nullptr, *trecv = nullptr;   // transposed t-solve (DOTSOCP_TSOLVE=transpose)
     double* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // pipelined t-solve: forward in / out, backward in / out (P doubles each)
@@ -322,6 +326,12 @@ static int make_slab(dotsocp_ctx* c, int id)
     CU(cudaMemsetAsync(s->c0, 0, g.P * sizeof(double), c->st));
     CU(cudaMemsetAsync(s->c1, 0, g.P * sizeof(double), c->st));
     CU(cudaMalloc(&s->partial, partial_doubles(g, tr.tn1 - tr.tn0) * sizeof(double)));
+    if (mult_aligned_ok(g, c->one_d)) {
+        s->maps_ok = make_beta_map(g, s->beta[0], &s->tm_beta[0]) == 0 && make_beta_map(g, s->beta[1], &s->tm_beta[1]) == 0 &&
+                     make_stag_maps(g, s->q[0], s->tm_q[0]) == 0 && make_stag_maps(g, s->q[1], s->tm_q[1]) == 0 &&
+                     make_stag_maps(g, s->alpha, s->tm_alpha) == 0 && (!c->weighted || make_stag_maps(g, s->weight, s->tm_w) == 0);
+        cudaGetLastError();
+    }
     {
         const i64 nside = mult_side_doubles(g, c->one_d, tr.tc1 - s->lo_c);
         if (nside > 0) {
@@ -1353,6 +1363,17 @@ struct Loop {
         a.alpha = s->alpha; a.weight = s->weight; a.beta_in = s->beta[c->bcur]; a.beta_out = s->beta[1 - c->bcur];
         a.q2 = s->q2; a.rhs = s->rhs; a.c0 = s->c0; a.c1 = s->c1; a.kkt_t0 = s->tr.tn0;
         a.side = s->side; a.side_t0 = s->lo_c; a.side_layers = s->tr.tc1 - s->lo_c;
+        a.maps = nullptr;
+        if (s->maps_ok) {
+            s->km.beta = s->tm_beta[c->bcur];
+            for (int i = 0; i < 3; i++) {
+                s->km.qn[i] = s->tm_q[1 - c->qcur][i];
+                s->km.qo[i] = s->tm_q[c->qcur][i];
+                s->km.al[i] = s->tm_alpha[i];
+                s->km.w[i] = c->weighted ? s->tm_w[i] : s->tm_alpha[i];
+            }
+            a.maps = &s->km;
+        }
         return a;
     }
     // q2, rhs from the current (q, alpha, beta): the z-step part of the first iteration / after any rescaling

@@ -154,6 +154,24 @@ void SparseArray::release()
     dense_ = false;
 }
 
+int make_tensor_map_f64(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                        const unsigned long long* strides_bytes, const unsigned* box)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = [] { EncodeFn f = nullptr; return entry("cuTensorMapEncodeTiled", f) ? f : (EncodeFn) nullptr; }();
+    if (!fn || rank < 1 || rank > 5) return -1;
+    cuuint64_t d[5], st[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; i++) st[i] = strides_bytes[i];
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
 const NcclApi& nccl_api()
 {
     static NcclApi api = [] {

@@ -39,6 +39,12 @@ private:
     std::vector<Chunk> chunks_;
 };
 
+// FP64 tensor map (TMA descriptor) of a `rank`-dimensional view: dims[0] is the contiguous dimension, strides_bytes[i] the
+// distance between consecutive indices of dimension i+1 (rank-1 entries, multiples of 16), box[] the tile one copy moves.
+// Out-of-range parts of a box are filled with zeros.  Returns 0, or -1 when the driver lacks cuTensorMapEncodeTiled / rejects it.
+int make_tensor_map_f64(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                        const unsigned long long* strides_bytes, const unsigned* box);
+
 // ---- NCCL, loaded at run time --------------------------------------------------------------------------------------
 struct NcclId { char internal[128]; };
 struct NcclApi {
