@@ -304,12 +304,12 @@ static int make_slab(dotsocp_ctx* c, int id)
     } while (0)
     MK(s->a_phi, g.N, s->n_all); MK(s->a_rhs, g.N, s->n_all);
     MK(s->a_q[0], g.Q, s->q_all); MK(s->a_q[1], g.Q, s->q_all); MK(s->a_alpha, g.Q, s->q_all); MK(s->a_q2, g.Q, s->q_all);
-    MK(s->a_qtmp, g.Q, s->q_all);
+    // (a_qtmp, the scratch of the stand-alone KKT check, is created on first use: ensure_qtmp)
     if (c->weighted) MK(s->a_weight, g.Q, s->q_all);
     MK(s->a_beta[0], 10 * g.L, s->b_all); MK(s->a_beta[1], 10 * g.L, s->b_all);
 #undef MK
     s->phi = s->a_phi.ptr(); s->rhs = s->a_rhs.ptr(); s->q[0] = s->a_q[0].ptr(); s->q[1] = s->a_q[1].ptr();
-    s->alpha = s->a_alpha.ptr(); s->q2 = s->a_q2.ptr(); s->qtmp = s->a_qtmp.ptr();
+    s->alpha = s->a_alpha.ptr(); s->q2 = s->a_q2.ptr(); s->qtmp = nullptr;
     s->weight = c->weighted ? s->a_weight.ptr() : nullptr;
     s->beta[0] = s->a_beta[0].ptr(); s->beta[1] = s->a_beta[1].ptr();
     if (!g.packed()) {
@@ -355,12 +355,29 @@ static int make_slab(dotsocp_ctx* c, int id)
             launch_fill(s->partial, (i64)partial_doubles(g, tr.tn1 - tr.tn0), nan_, c->st);
             if (g.packed()) {
                 double* qa[] = {s->q[0], s->q[1], s->alpha, s->q2, s->qtmp};
-                for (double* a : qa) for (auto& x : s->q_all) launch_fill(a + x.b, x.e - x.b, nan_, c->st);
+                for (double* a : qa) if (a) for (auto& x : s->q_all) launch_fill(a + x.b, x.e - x.b, nan_, c->st);
                 for (int k = 0; k < 2; k++) for (auto& x : s->b_all) launch_fill(s->beta[k] + x.b, x.e - x.b, nan_, c->st);
             }
             CU(cudaGetLastError());
         }
     }
+    return 0;
+}
+
+// Q doubles of scratch for s (BF)^* beta of the stand-alone KKT check (PALM / acc-ADMM, DOTSOCP_KKT=separate, or a check the
+// schedule did not announce): 13 GB at 1024x1024x512 that the fused inPALM loop never touches, so it is not part of a session
+// until somebody asks -- which is what lets the last level transfer of that grid fit one 180 GB GPU
+static int ensure_qtmp(dotsocp_ctx* c, Slab* s)
+{
+    if (s->qtmp) return 0;
+    std::vector<std::pair<long long, long long>> w;
+    for (auto& x : s->q_all) w.emplace_back(x.b, x.e);
+    const char* why = "";
+    const int e_ = s->a_qtmp.create(c->g.Q, w, c->world == 1, c->device, &why);
+    if (e_) return set_err(e_ == 2 ? DOTSOCP_ENOMEM : DOTSOCP_ECUDA, "KKT scratch of %lld doubles: %s", (long long)c->g.Q, why);
+    s->qtmp = s->a_qtmp.ptr();
+    if (!c->g.packed())
+        for (auto& x : s->q_all) CU(cudaMemsetAsync(s->qtmp + x.b, 0, (size_t)(x.e - x.b) * sizeof(double), c->st));
     return 0;
 }
 
@@ -479,6 +496,8 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
         }
         c->comm = g_comm;
     }
+    const auto t_c0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     if (c->emulate) {
         for (int r = 0; r < world; r++)
             if ((rc = make_slab(c, r))) { dotsocp_destroy(c); return rc; }
@@ -652,7 +671,11 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
             }
         }
     }
+    const double ms_slabs = since(t_c0);
+    const auto t_c1 = std::chrono::steady_clock::now();
     c->pp = poisson_plan_create(nt, nx, ny);
+    const double ms_plan = since(t_c1);
+    const auto t_c2 = std::chrono::steady_clock::now();
     {
         // Nothing is left to be built lazily inside the first Poisson solve, and the session starts with an idle device.  With the
         // lazy construction (DOTSOCP_PREP=0) the first solve of a level occasionally returned a wrong singular-mode line when the
@@ -670,6 +693,8 @@ static int create_impl(dotsocp_ctx** out, int variant, int nt, int nx, int ny, i
         }
     }
     { const char* kk = getenv("DOTSOCP_KKT"); c->fuse_kkt = !(kk && strcmp(kk, "separate") == 0); }
+    if (c->trace) fprintf(stderr, "[dotsocp trace] create %d x %d x %d: arrays %.1f ms, Poisson plan %.1f ms, tables + sync %.1f ms\n", nt, nx, ny,
+                          ms_slabs, ms_plan, since(t_c2));
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMalloc(&c->d_lvl, (size_t)nt * KSL * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tot, KSL * sizeof(double));
@@ -1040,12 +1065,26 @@ static int xfer(dotsocp_ctx* c, double* dev, double* host, size_t n, bool up)
     return 0;
 }
 // `rows` rows of `w` doubles: packed on the host, `dpitch` doubles apart on the device
-static int xfer_rows(dotsocp_ctx* c, double* dev, i64 dpitch, double* host, i64 w, i64 rows, bool up)
+static int xfer_rows(dotsocp_ctx* c, double* dev, i64 dpitch, double* host, i64 w, i64 rows, bool up, double pad_value = 0.0)
 {
     if (rows <= 0 || w <= 0) return 0;
     if (dpitch == w) return xfer(c, dev, host, (size_t)(w * rows), up);
     static const bool plain = [] { const char* e = getenv("DOTSOCP_HOSTCOPY"); return e && strcmp(e, "plain") == 0; }();
     const size_t wb = (size_t)w * sizeof(double), db = (size_t)dpitch * sizeof(double);
+    if (wb * (size_t)rows < ((size_t)1 << 20)) {
+        // small pieces (coarse multilevel grids): a 2-D copy from pageable memory is driven row by row (milliseconds per array);
+        // re-pitch on the host instead and move ONE contiguous block (the pads travel with it and keep their value)
+        std::vector<double> tmp((size_t)rows * dpitch, pad_value);
+        if (up) {
+            for (i64 r = 0; r < rows; r++) memcpy(tmp.data() + r * dpitch, host + r * w, wb);
+            CU(cudaMemcpyAsync(dev, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));   // returns once tmp is staged
+        } else {
+            CU(cudaMemcpyAsync(tmp.data(), dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaStreamSynchronize(c->st));
+            for (i64 r = 0; r < rows; r++) memcpy(host + r * w, tmp.data() + r * dpitch, wb);
+        }
+        return 0;
+    }
     if (!plain && wb * (size_t)rows >= ((size_t)1 << 20)) {
         HostCopier* hc = HostCopier::get();
         if (hc->ok()) {
@@ -1059,7 +1098,7 @@ static int xfer_rows(dotsocp_ctx* c, double* dev, i64 dpitch, double* host, i64 
     return 0;
 }
 
-static int copy_stag(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev, double* host, bool up)
+static int copy_stag(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev, double* host, bool up, double pad_value = 0.0)
 {
     const Geo& g = c->g;
     const TRange& tr = s->tr;
@@ -1069,7 +1108,7 @@ static int copy_stag(dotsocp_ctx* c, Slab* s, const HostMap& hm, double* dev, do
         {g.L + tr.tn0 * g.PBX, hm.bx(tr.tn0), (i64)(tr.tn1 - tr.tn0) * (g.nx - 1), g.ny, g.py},
         {g.L + g.NBX + tr.tn0 * g.PBY, hm.by(tr.tn0), (i64)(tr.tn1 - tr.tn0) * g.nx, g.ny - 1, g.pyb}};
     for (auto& p : parts) {
-        int rc = xfer_rows(c, dev + p.d, p.dp, host + p.h, p.w, p.rows, up);
+        int rc = xfer_rows(c, dev + p.d, p.dp, host + p.h, p.w, p.rows, up, pad_value);
         if (rc) return rc;
     }
     return 0;
@@ -1132,7 +1171,7 @@ extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q
         if ((rc = copy_stag(c, s, hm, s->alpha, const_cast<double*>(alpha), true))) return rc;
         if (c->weighted) {
             if ((rc = fill_weight_pads(c, s))) return rc;
-            if ((rc = copy_stag(c, s, hm, s->weight, const_cast<double*>(weight), true))) return rc;
+            if ((rc = copy_stag(c, s, hm, s->weight, const_cast<double*>(weight), true, 1.0))) return rc;
         }
         if (tr.tn0 == 0) CU(cudaMemcpyAsync(s->c0, cvec + hm.nodes(0), g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
         if (tr.tn1 == g.nt) CU(cudaMemcpyAsync(s->c1, cvec + hm.nodes(g.nt - 1), g.P * sizeof(double), cudaMemcpyHostToDevice, c->st));
@@ -1186,7 +1225,7 @@ extern "C" int dotsocp_prolong(dotsocp_ctx* coarse, dotsocp_ctx* fine, const dot
         if (fine->weighted) {
             HostMap hm{local_host, &fine->gh, tr};
             if ((rc = fill_weight_pads(fine, sf))) return rc;
-            if ((rc = copy_stag(fine, sf, hm, sf->weight, const_cast<double*>(weight), true))) return rc;
+            if ((rc = copy_stag(fine, sf, hm, sf->weight, const_cast<double*>(weight), true, 1.0))) return rc;
         }
         if (tr.tn0 == 0) {
             if (!c_first) return set_err(DOTSOCP_EINVAL, "prolong: c_first is required on the slab that owns the first time level");
@@ -1900,6 +1939,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
                         c->launches += 2;
                     }
                 } else {
+                    if ((rc = ensure_qtmp(c, s))) return rc;
                     launch_bfdconj(g, L.sc.S, s->beta[c->bcur], s->qtmp, c->st, &s->tr);   // q2 = s (BF)^* beta   (:225)
                     KktArgs ka;
                     ka.g = g; ka.tr = s->tr; ka.sc = L.sc; ka.sigma = sigma; ka.cScale = cScale; ka.dScale = dScale; ka.D = D; ka.E = E;
@@ -2047,6 +2087,7 @@ static int run_level(dotsocp_ctx* c, const dotsocp_level_opts& o, dotsocp_hist* 
             if (fused_check || (accsgs && sgs_superior_yes)) {   // sgs_superior_yes: primal / dual feasibility of this iteration (:385-402)
                 if (accsgs) {   // acc keeps z as state and has no fused sums: the stand-alone node kernel (accsGSADMM :420-425)
                     if ((rc = begin_sums(c))) return rc;
+                    if ((rc = ensure_qtmp(c, S0))) return rc;
                     launch_bfdconj(g, L.sc.S, S0->beta[c->bcur], S0->qtmp, c->st, &S0->tr);
                     KktArgs ka;
                     ka.g = g; ka.tr = S0->tr; ka.sc = L.sc; ka.sigma = sigma; ka.cScale = cScale; ka.dScale = dScale; ka.D = D; ka.E = E;

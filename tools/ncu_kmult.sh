@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu --set full capture of k_mult (update launches) at 512x512x256; run only after the plain run has exited 0
+# ncu --set full capture of one k_mult update launch at 1024x1024x512 (source of roofline.traffic); the plain run comes first
 set -e
-python tools/microbench.py c4 4 > gpurun_out/plain_kmult.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_mult -s 6 -c 2 -o gpurun_out/prof_r02_kmult_al -f python tools/microbench.py c4 4 > gpurun_out/ncu_kmult.log 2>&1
+timeout -s KILL 200 python tools/microbench.py c5 3 > gpurun_out/plain_kmult_c5.log 2>&1
+timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:k_mult -s 4 -c 1 -o gpurun_out/prof_r02_kmult_c5 -f python tools/microbench.py c5 3 > gpurun_out/ncu_kmult_c5.log 2>&1
