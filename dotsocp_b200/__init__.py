@@ -10,8 +10,8 @@ Layout
 from . import _lib, driver, ops, slab, solver  # noqa: F401
 from ._lib import DotsocpError  # noqa: F401
 from .driver import solver_dotsocp1d, solver_dotsocp2d, solver_wdotsocp2d  # noqa: F401
-from .solver import (Session, solver_socp_accADMM, solver_socp_inPALM, solver_socp_PALM,  # noqa: F401
+from .solver import (Session, Weights, solver_socp_accADMM, solver_socp_inPALM, solver_socp_PALM,  # noqa: F401
                      solver_socp_accsGSADMM, solver_socp_sGSinPALM, solver_wsocp_accADMM, solver_wsocp_inPALM)
 
-__all__ = ["DotsocpError", "ops", "solver", "driver", "Session", "solver_socp_inPALM", "solver_socp_PALM", "solver_socp_accADMM", "solver_socp_sGSinPALM", "solver_socp_accsGSADMM",
+__all__ = ["DotsocpError", "ops", "solver", "driver", "Session", "Weights", "solver_socp_inPALM", "solver_socp_PALM", "solver_socp_accADMM", "solver_socp_sGSinPALM", "solver_socp_accsGSADMM",
            "solver_wsocp_inPALM", "solver_wsocp_accADMM", "solver_dotsocp2d", "solver_wdotsocp2d", "solver_dotsocp1d"]

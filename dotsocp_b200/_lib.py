@@ -69,6 +69,8 @@ EXPORTS = [
     "dotsocp_poisson", "dotsocp_dctn", "dotsocp_solve_level", "dotsocp_release_cached",
     "dotsocp_nccl_unique_id", "dotsocp_create", "dotsocp_destroy", "dotsocp_upload", "dotsocp_download",
     "dotsocp_create_refined", "dotsocp_prolong", "dotsocp_recover", "dotsocp_run", "dotsocp_iter_begin", "dotsocp_iterate", "dotsocp_iter_end", "dotsocp_launch_count",
+    "dotsocp_weights_create", "dotsocp_weights_destroy", "dotsocp_weights_set", "dotsocp_weights_set_planes", "dotsocp_weights_restrict",
+    "dotsocp_weights_get", "dotsocp_weights_dims", "dotsocp_weights_log10_mean", "dotsocp_weights_launch_count", "dotsocp_set_weight",
 ]
 
 _lib = None
@@ -112,6 +114,18 @@ def lib():
     L.dotsocp_iter_begin.argtypes = [P, C.POINTER(LevelOpts)]
     L.dotsocp_iterate.argtypes = [P, I, I, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.dotsocp_iter_end.argtypes = [P]
+    L.dotsocp_weights_create.argtypes = [C.POINTER(P), I, I, I, I]
+    L.dotsocp_weights_destroy.argtypes = [P]
+    L.dotsocp_weights_destroy.restype = None
+    L.dotsocp_weights_set.argtypes = [P, P]
+    L.dotsocp_weights_set_planes.argtypes = [P, P, P]
+    L.dotsocp_weights_restrict.argtypes = [P, I]
+    L.dotsocp_weights_get.argtypes = [P, I, P]
+    L.dotsocp_weights_dims.argtypes = [P, I, C.POINTER(I), C.POINTER(I), C.POINTER(I)]
+    L.dotsocp_weights_log10_mean.argtypes = [P, I, C.POINTER(D)]
+    L.dotsocp_weights_launch_count.argtypes = [P]
+    L.dotsocp_weights_launch_count.restype = D
+    L.dotsocp_set_weight.argtypes = [P, P, I]
     _lib = L
     return L
 

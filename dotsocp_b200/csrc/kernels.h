@@ -240,4 +240,22 @@ void poisson_line0_scatter(PoissonPlan* p, double* a, const double* line, int t0
 // in-place orthonormal DCT-II (or inverse) along all axes
 int  poisson_dctn(PoissonPlan* p, double* a, bool inverse, cudaStream_t st, double* launches);
 
+// ---- level weights resident on the device (weights.cu): one packed array [q0 | bx | by] per level, finest first
+struct WeightLevel {
+    int nt, nx, ny;        // nodes
+    i64 L, NBX, NBY, Q;    // packed (reference) sizes
+    double* w;             // device
+};
+// window [b, e) of a session's staggered array (device layout g) <- the packed level array; pad entries become 1
+void launch_weight_scatter(const Geo& g, i64 b, i64 e, const double* packed, double* dst, cudaStream_t st);
+
 }  // namespace dsocp
+
+struct dotsocp_weights {
+    std::vector<dsocp::WeightLevel> lv;
+    int device = 0;
+    int filled = 0;            // levels 0 .. filled-1 hold values
+    double* scratch = nullptr;
+    double launches = 0.0;
+    ~dotsocp_weights();
+};

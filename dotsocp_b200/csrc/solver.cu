@@ -157,6 +157,7 @@ struct Slab {
 struct dotsocp_ctx {
     int variant = 0;
     bool one_d = false, weighted = false;
+    bool weight_set = false;    // the weight came from a device pyramid (dotsocp_set_weight): upload / prolong may pass NULL
     int world = 1;
     bool emulate = false;       // all slabs in this process
     int my = 0;                 // first (NCCL mode: only) local slab id
@@ -1140,11 +1141,36 @@ static int fill_weight_pads(dotsocp_ctx* c, Slab* s)
     return 0;
 }
 
+// The session's weight from level `level` of a device pyramid (weights.cu) instead of a host array: every window the slab
+// backs (owned levels and ghost layers alike, so no exchange follows) is filled by a device-to-device scatter from the packed
+// level array into the pitched layout.  Call it before dotsocp_upload / dotsocp_prolong, which then take weight == NULL.
+extern "C" int dotsocp_set_weight(dotsocp_ctx* c, const dotsocp_weights* w, int level)
+{
+    if (!c || !w) return set_err(DOTSOCP_EINVAL, "NULL argument");
+    if (!c->weighted) return set_err(DOTSOCP_EINVAL, "set_weight: not a weighted (WDOT2D) session");
+    if (level < 0 || level >= (int)w->lv.size()) return set_err(DOTSOCP_EINVAL, "set_weight: level %d of %d", level, (int)w->lv.size());
+    if (level >= w->filled) return set_err(DOTSOCP_ESTATE, "set_weight: level %d of the pyramid has not been computed", level);
+    const WeightLevel& l = w->lv[level];
+    const Geo& g = c->g;
+    if (l.nt != g.nt || l.nx != g.nx || l.ny != g.ny)
+        return set_err(DOTSOCP_EINVAL, "set_weight: level %d is %d x %d x %d, the session %d x %d x %d", level, l.nt, l.nx, l.ny, g.nt, g.nx, g.ny);
+    if (w->device != c->device) return set_err(DOTSOCP_EINVAL, "set_weight: the pyramid lives on device %d, the session on %d", w->device, c->device);
+    for (Slab* s : c->slabs) {
+        for (auto& x : s->q_all) launch_weight_scatter(g, x.b, x.e, l.w, s->weight, c->st);
+        CU(cudaGetLastError());
+        c->launches += (double)s->q_all.size();
+    }
+    CU(cudaStreamSynchronize(c->st));
+    c->weight_set = true;
+    return DOTSOCP_OK;
+}
+
 extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q, const double* z, const double* alpha,
                               const double* beta, const double* cvec, const double* weight)
 {
     if (!c || !phi || !q || !alpha || !beta || !cvec) return set_err(DOTSOCP_EINVAL, "NULL array");
-    if (c->weighted && !weight) return set_err(DOTSOCP_EINVAL, "weighted variant needs weight");
+    if (c->weighted && !weight && !c->weight_set)
+        return set_err(DOTSOCP_EINVAL, "weighted variant needs weight (a host array here, or dotsocp_set_weight before)");
     const Geo& g = c->g;
     c->qcur = 0;
     c->bcur = 0;
@@ -1169,7 +1195,7 @@ extern "C" int dotsocp_upload(dotsocp_ctx* c, const double* phi, const double* q
         if ((rc = xfer(c, s->phi + tr.tn0 * g.P, const_cast<double*>(phi) + hm.nodes(tr.tn0), (size_t)(tr.tn1 - tr.tn0) * g.P, true))) return rc;
         if ((rc = copy_stag(c, s, hm, s->q[0], const_cast<double*>(q), true))) return rc;
         if ((rc = copy_stag(c, s, hm, s->alpha, const_cast<double*>(alpha), true))) return rc;
-        if (c->weighted) {
+        if (c->weighted && weight) {
             if ((rc = fill_weight_pads(c, s))) return rc;
             if ((rc = copy_stag(c, s, hm, s->weight, const_cast<double*>(weight), true, 1.0))) return rc;
         }
@@ -1204,7 +1230,8 @@ extern "C" int dotsocp_prolong(dotsocp_ctx* coarse, dotsocp_ctx* fine, const dot
     if (gf.nt != 2 * gc.nt - 1 || gf.nx != 2 * gc.nx - 1 || gf.ny != (gc.ny > 1 ? 2 * gc.ny - 1 : 1))
         return set_err(DOTSOCP_EINVAL, "prolong: the fine grid must have 2n-1 nodes per axis (%d,%d,%d) -> (%d,%d,%d)", gc.nt, gc.nx,
                        gc.ny, gf.nt, gf.nx, gf.ny);
-    if (fine->weighted && !weight) return set_err(DOTSOCP_EINVAL, "weighted variant needs weight");
+    if (fine->weighted && !weight && !fine->weight_set)
+        return set_err(DOTSOCP_EINVAL, "weighted variant needs weight (a host array here, or dotsocp_set_weight on the fine session before)");
     if (coarse->world != fine->world || coarse->emulate != fine->emulate || coarse->comm != fine->comm || coarse->my != fine->my)
         return set_err(DOTSOCP_EINVAL, "prolong: the two sessions must share rank, world and communicator (dotsocp_create_refined)");
     for (int r = 0; r < fine->world; r++)
@@ -1222,7 +1249,7 @@ extern "C" int dotsocp_prolong(dotsocp_ctx* coarse, dotsocp_ctx* fine, const dot
     for (Slab* sf : fine->slabs) {
         Slab* sc = coarse->local(sf->id);
         const TRange& tr = sf->tr;
-        if (fine->weighted) {
+        if (fine->weighted && weight) {
             HostMap hm{local_host, &fine->gh, tr};
             if ((rc = fill_weight_pads(fine, sf))) return rc;
             if ((rc = copy_stag(fine, sf, hm, sf->weight, const_cast<double*>(weight), true, 1.0))) return rc;

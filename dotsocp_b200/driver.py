@@ -125,7 +125,10 @@ def scaling_scalars(N, model, scalingYes, lastLevelKKT, E2_prev, variant):
         norm_c = (math.sqrt(h) * norm_c_planes(model)) * math.sqrt(model.nt)
         norm_d = math.sqrt(2)
         if variant == "wdot2d":
-            adjust = 10 ** float(np.mean(np.log10(model.weight + 1e-10)))
+            if isinstance(model.weight, S.DeviceWeight):     # level of a device pyramid: fixed-order reduction in HBM
+                adjust = 10 ** model.weight.log10_mean()
+            else:
+                adjust = 10 ** float(np.mean(np.log10(model.weight + 1e-10)))
             D = math.sqrt(2) * math.sqrt(hMean) * adjust
             E = D / Escale2
             cScale = max(1, norm_c * math.sqrt(hMean) / adjust)
@@ -325,6 +328,41 @@ def downSample_barrier(nt, nx, ny, weight):
     return np.exp(downSample_q(nt, nx, ny, np.log(weight)))
 
 
+def _stag_grids(nx, ny):
+    hx, hy = 1 / (nx - 1), 1 / (ny - 1)
+    return (np.linspace(.5 * hx, 1 - .5 * hx, nx - 1), np.linspace(0, 1, nx),
+            np.linspace(.5 * hy, 1 - .5 * hy, ny - 1), np.linspace(0, 1, ny))
+
+
+def weight_planes_circle(nx, ny):
+    """The two (x,y) planes of examples/wdot2d/gene_weight_circle.m:6-22: distance to (.5,.5) on the bx / by edge grids, each
+    normalised to the sum ny*(nx-1) (the reference uses that count for BOTH planes, :18,:22).  MATLAB-shaped (ny, nx-1), (ny-1, nx)."""
+    xS, xC, yS, yC = _stag_grids(nx, ny)
+    dist = lambda xx, yy: np.sqrt((xx - .5) ** 2 + (yy - .5) ** 2)
+    wX = dist(*np.meshgrid(xS, yC))
+    wX = wX * (ny * (nx - 1) / wX.sum())
+    wY = dist(*np.meshgrid(xC, yS))
+    wY = wY * (ny * (nx - 1) / wY.sum())
+    return wX, wY
+
+
+def weight_planes_barrier(nx, ny, barrier, barrierWeight=1e6):
+    """The two planes of examples/wdot2d/get_weight_by_barrier.m:12-28: barrierWeight where barrier(x, y) > 0 on the bx / by
+    edge grids, 1 elsewhere.  barrier takes (nx', ny')-shaped coordinate arrays like the reference's function handles."""
+    xS, xC, yS, yC = _stag_grids(nx, ny)
+    xx, yy = np.meshgrid(xS, yC)
+    wX = np.where((barrier(xx.T, yy.T) > 0).T, float(barrierWeight), 1.0)
+    xx, yy = np.meshgrid(xC, yS)
+    wY = np.where((barrier(xx.T, yy.T) > 0).T, float(barrierWeight), 1.0)
+    return wX, wY
+
+
+def weight_from_planes(nt, wX, wY):
+    """[ones ; repmat(weightX, nt) ; repmat(weightY, nt)] (gene_weight_circle.m:24-27, get_weight_by_barrier.m:30-33) on the host"""
+    ny, nxm1 = wX.shape
+    return np.concatenate([np.ones((nt - 1) * (nxm1 + 1) * ny), np.tile(wX.ravel(order="F"), nt), np.tile(wY.ravel(order="F"), nt)])
+
+
 def ensure_barrier_validity(rho0, rho1, barrier):
     """examples/wdot2d/ensure_barrier_validity.m:4-16"""
     ny, nx = rho0.shape
@@ -464,14 +502,32 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
     optsML.setdefault("sigma", 0.1 if sgsMethod else 1)                  # :139-146
     optsML.setdefault("time_limit", 3600)
     weight = opts.get("weight") if variant == "wdot2d" else None
-    if variant == "wdot2d" and weight is None:
+    planes = opts.get("weight_planes") if variant == "wdot2d" else None     # (weightX, weightY) of the generators
+    if variant == "wdot2d" and weight is None and planes is None:
         raise ValueError("opts.weight is required")
+    # opts["weights_on_device"] (implied by weight_planes): the finest weight, its restriction chain and the log-means live in a
+    # device pyramid (solver.Weights): no Q-sized host array per level.  Resident path only.
+    on_device = variant == "wdot2d" and (planes is not None or bool(opts.get("weights_on_device", False)))
+    for k in ("weight", "weight_planes", "weights_on_device"):
+        optsML.pop(k, None)
     rho0s, rho1s, nts, tols, weights = ([None] * levelN for _ in range(5))
     rho0s[-1], rho1s[-1] = np.asarray(rho0, float), np.asarray(rho1, float)
     nts[-1], tols[-1], weights[-1] = int(nt), optsML["tol"], weight
     nxs, nys = [None] * levelN, [None] * levelN
     if variant != "dot1d":
         nys[-1], nxs[-1] = rho0s[-1].shape
+    pyramid = None
+    if on_device:
+        if not optsML.get("resident", True):
+            raise ValueError("weights_on_device needs the resident multilevel path")
+        pyramid = S.Weights(nts[-1], nxs[-1], nys[-1], levelN)
+        if planes is not None:
+            pyramid.set_planes(*planes)
+        else:
+            pyramid.set(weight)
+        pyramid.restrict(geometric=barrier is not None)        # downSample_barrier / downSample_q chain (:179-187)
+        weights = [pyramid.level(levelN - 1 - lv) for lv in range(levelN)]
+        weight = None
     for lv in range(levelN - 2, -1, -1):
         nts[lv] = (nts[lv + 1] - 1) // 2 + 1
         tols[lv] = max(tols[lv + 1] * 2 ** optsML["tolFactor"], tolLowerBound)
@@ -481,9 +537,10 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
             nxs[lv], nys[lv] = (nxs[lv + 1] + 1) // 2, (nys[lv + 1] + 1) // 2
         if variant == "wdot2d" and barrier is not None:
             rho0s[lv], rho1s[lv], _ = ensure_barrier_validity(rho0s[lv], rho1s[lv], barrier)
-            weights[lv] = downSample_barrier(nts[lv + 1], nxs[lv + 1], nys[lv + 1], weights[lv + 1])
+            if pyramid is None:
+                weights[lv] = downSample_barrier(nts[lv + 1], nxs[lv + 1], nys[lv + 1], weights[lv + 1])
         else:
-            if variant == "wdot2d":
+            if variant == "wdot2d" and pyramid is None:
                 weights[lv] = downSample_q(nts[lv + 1], nxs[lv + 1], nys[lv + 1], weights[lv + 1])
             N = rho0s[lv].size
             rho0s[lv] = rho0s[lv] / (rho0s[lv].sum() / N)
@@ -503,8 +560,12 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
     resident = bool(optsML.pop("resident", True))
     opts.pop("resident", None)
     if resident:
-        return _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model, rho0s, rho1s, nts, tols, weights,
-                                    timeML, ML, clk)
+        try:
+            return _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model, rho0s, rho1s, nts, tols, weights,
+                                        timeML, ML, clk)
+        finally:
+            if pyramid is not None:
+                pyramid.close()
     for level in range(levelN):
         InitialScaling(var, model, scalingYes, lastLevelKKT, variant)
         o2 = dict(optsML)
@@ -573,7 +634,11 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
     z_dead = first_is_inpalm and int(optsML["maxit"]) >= 1
     state0 = (var.phi, var.q, None if z_dead else var.z, var.alpha, var.beta, model.c, model.weight if weighted else None)
     if distributed:
-        state0 = SL.split_state(rank, world, model.nt, model.nx, model.ny, *state0, cuts=sess.cuts)
+        w0 = state0[6]
+        state0 = SL.split_state(rank, world, model.nt, model.nx, model.ny, *state0[:6],
+                                None if isinstance(w0, S.DeviceWeight) else w0, cuts=sess.cuts)
+        if isinstance(w0, S.DeviceWeight):       # the session takes its slab's part of the device level itself
+            state0 = state0[:6] + (w0,)
     sess.upload(*state0)
     del state0
     var.phi = var.q = var.z = var.alpha = var.beta = None
@@ -611,7 +676,7 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
             fine = S.Session.refined(sess)
             try:
                 w_f = model_f.weight if weighted else None
-                if weighted and distributed:
+                if weighted and distributed and not isinstance(w_f, S.DeviceWeight):
                     w_f = SL.split_state(rank, world, model_f.nt, model_f.nx, model_f.ny, None, None, None, None, None, None, w_f,
                                          cuts=fine.cuts)[6]
                 fine.prolong_from(sess, scal, weight=w_f, c_first=model_f.c_first, c_last=model_f.c_last)

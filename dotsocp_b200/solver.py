@@ -84,6 +84,92 @@ def make_level_opts(variant, method, var, opts, model):
     return o
 
 
+class Weights:
+    """Pyramid of level weights resident on the device (dotsocp_weights_*): what the weighted drivers do with the weight
+    before the first level starts -- the generators' time replication (gene_weight_circle.m:24-27, get_weight_by_barrier.m:
+    30-33), the restriction chain downSample_q.m / downSample_barrier.m and mean(log10(weight + 1e-10)) of
+    solver_wdotsocp2d.m:312-316 -- without a Q-sized host array per level.  Level 0 is the finest grid."""
+
+    def __init__(self, nt, nx, ny, levels):
+        self._h = C.c_void_p()
+        check(lib().dotsocp_weights_create(C.byref(self._h), int(nt), int(nx), int(ny), int(levels)))
+        self.levels = int(levels)
+
+    def dims(self, level):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        check(lib().dotsocp_weights_dims(self._h, int(level), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def size(self, level):
+        nt, nx, ny = self.dims(level)
+        return (nt - 1) * nx * ny + nt * (nx - 1) * ny + nt * nx * (ny - 1)
+
+    def set(self, weight):
+        """finest level from a host array (Q doubles, [q0 | bx | by])"""
+        w = np.ascontiguousarray(weight, dtype=np.float64).reshape(-1)
+        assert w.size == self.size(0), f"weight has {w.size} entries, expected {self.size(0)}"
+        check(lib().dotsocp_weights_set(self._h, ptr(w)))
+        return self
+
+    def set_planes(self, weightX, weightY):
+        """finest level from the generators' two planes, MATLAB-shaped weightX (ny, nx-1) and weightY (ny-1, nx)"""
+        nt, nx, ny = self.dims(0)
+        wx = np.ascontiguousarray(np.asarray(weightX, dtype=np.float64).T).reshape(-1)     # C order (x, y)
+        wy = np.ascontiguousarray(np.asarray(weightY, dtype=np.float64).T).reshape(-1)
+        assert wx.size == (nx - 1) * ny and wy.size == nx * (ny - 1)
+        check(lib().dotsocp_weights_set_planes(self._h, ptr(wx), ptr(wy)))
+        return self
+
+    def restrict(self, geometric=False):
+        """levels 1 .. from level 0: downSample_q, or downSample_barrier (exp of the restricted log) when geometric"""
+        check(lib().dotsocp_weights_restrict(self._h, 1 if geometric else 0))
+        return self
+
+    def get(self, level):
+        out = np.empty(self.size(level))
+        check(lib().dotsocp_weights_get(self._h, int(level), ptr(out)))
+        return out
+
+    def log10_mean(self, level):
+        m = C.c_double()
+        check(lib().dotsocp_weights_log10_mean(self._h, int(level), C.byref(m)))
+        return m.value
+
+    @property
+    def gpu_launches(self):
+        return float(lib().dotsocp_weights_launch_count(self._h))
+
+    def level(self, level):
+        return DeviceWeight(self, int(level))
+
+    def close(self):
+        if self._h:
+            lib().dotsocp_weights_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceWeight:
+    """One level of a Weights pyramid, accepted wherever the drivers take model.weight (Session.upload / prolong_from)."""
+
+    def __init__(self, pyramid, level):
+        self.pyramid, self.level = pyramid, level
+
+    def log10_mean(self):
+        return self.pyramid.log10_mean(self.level)
+
+
 class Session:
     """Device-resident state of one level (dotsocp_create / _upload / _run / _download / _destroy)."""
 
@@ -147,10 +233,17 @@ class Session:
         assert arrs[0].size == self.N and arrs[1].size == self.Q and arrs[3].size == self.Q and arrs[5].size == self.N
         assert arrs[4].shape == (self.L, self.ncol)
         assert arrs[2] is None or arrs[2].shape == (self.L, self.ncol)   # z=None: inPALM never reads the incoming z
+        assert (weight is None) == (self.variant != "wdot2d"), "weight is required for (and only for) the weighted variant"
+        if isinstance(weight, DeviceWeight):      # resident pyramid: device-to-device, nothing crosses PCIe
+            self.set_weight(weight)
+            weight = None
         w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64).reshape(-1)
-        assert (w is None) == (self.variant != "wdot2d"), "weight is required for (and only for) the weighted variant"
         assert w is None or w.size == self.Q, f"weight has {0 if w is None else w.size} entries, expected {self.Q}"
         check(lib().dotsocp_upload(self._h, *[ptr(a) for a in arrs], ptr(w)))
+
+    def set_weight(self, dw):
+        """weight of this (wdot2d) session from a level of a device pyramid (dotsocp_set_weight); the slab takes its own part"""
+        check(lib().dotsocp_set_weight(self._h, dw.pyramid._h, dw.level))
 
     def download(self, out=None):
         """out = (phi, q, z, alpha, beta): fill these float64 arrays IN PLACE (the convention of the reference's MEX
@@ -184,6 +277,9 @@ class Session:
         first = None if c_first is None else np.ascontiguousarray(c_first, dtype=np.float64).reshape(-1)
         last = None if c_last is None else np.ascontiguousarray(c_last, dtype=np.float64).reshape(-1)
         assert (first is None or first.size == P) and (last is None or last.size == P)
+        if isinstance(weight, DeviceWeight):
+            self.set_weight(weight)
+            weight = None
         w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64).reshape(-1)
         assert w is None or w.size == self.Q, f"weight has {0 if w is None else w.size} entries, expected {self.Q}"
         ps = ProlongScal(**{k: float(v) for k, v in scal.items()})

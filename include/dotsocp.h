@@ -176,7 +176,8 @@ int  dotsocp_recover(dotsocp_ctx *ctx, const dotsocp_recover_scal *s, const doub
  * session of the refined grid (2n-1 nodes per refined axis).  The scalars are the ones the driver computes on the host;
  * every value is rounded exactly where the host path rounds it.  c_first / c_last: the two non-zero planes of the fine
  * model.c (nx*ny doubles each, already divided by cScale); weight: fine weight (Q doubles) for WDOT2D, else NULL.
- * Single-GPU sessions only.                                                                                            */
+ * Time slabs: `fine` comes from dotsocp_create_refined (slab r of the fine grid refines slab r of the coarse one), the
+ * host arrays follow the upload convention (global arrays, or the slab's own part in a one-process-per-GPU run).       */
 typedef struct dotsocp_prolong_scal {
     double phi_recover;             /* coarse var.dScale                 (var.phi  = dScale * var.phi)             */
     double beta_recover;            /* coarse var.cScale * var.E         (var.beta = (cScale*E) * var.beta)        */
@@ -189,6 +190,33 @@ typedef struct dotsocp_prolong_scal {
 int  dotsocp_create_refined(dotsocp_ctx **fine, const dotsocp_ctx *coarse);
 int  dotsocp_prolong(dotsocp_ctx *coarse, dotsocp_ctx *fine, const dotsocp_prolong_scal *s,
                      const double *c_first, const double *c_last, const double *weight);
+/* ------------------------------------------------------------------ level weights resident on the device (WDOT2D)
+ * What the weighted drivers do with the weight before the first level starts -- examples/wdot2d/gene_weight_circle.m:6-27 and
+ * get_weight_by_barrier.m:12-33 (finest weight = [ones ; repmat(weightX, nt) ; repmat(weightY, nt)]), the restriction chain
+ * socp/wdot2d/utils/downSample_q.m:4-19 / downSample_barrier.m:4-24 (solver_wdotsocp2d.m:179-187) and mean(log10(weight +
+ * 1e-10)) of solver_wdotsocp2d.m:312-316 -- without a Q-sized host array per level: a pyramid of `levels` packed arrays
+ * [q0 | bx | by] in HBM, level 0 = the finest (nt, nx, ny) grid, level l = (n+1)/2 nodes per axis of level l-1.
+ *   _set        : finest level from a host array (Q doubles, the reference layout)
+ *   _set_planes : finest level from the two (x,y) planes of the generators: weightX (nx-1)*ny doubles, weightY nx*(ny-1)
+ *                 doubles, both in C order (x, y) = MATLAB (ny, nx-1)(:) / (ny-1, nx)(:); replicated over the time levels,
+ *                 ones on the q0 part
+ *   _restrict   : levels 1 .. levels-1 from level 0; geometric != 0: exp(restrict(log w)) (downSample_barrier), else downSample_q
+ *   _get / _log10_mean / _dims : read a level back (tests), the mean for `adjust`, the node counts of a level
+ *   dotsocp_set_weight : level `level` becomes the weight of a WDOT2D session (any slab layout; device to device);
+ *                 dotsocp_upload / dotsocp_prolong then take weight == NULL.  In a one-process-per-GPU run every rank builds
+ *                 the pyramid on its own GPU (no communication) and its session takes only the slab's part.               */
+typedef struct dotsocp_weights dotsocp_weights;
+int  dotsocp_weights_create(dotsocp_weights **w, int nt, int nx, int ny, int levels);
+void dotsocp_weights_destroy(dotsocp_weights *w);
+int  dotsocp_weights_set(dotsocp_weights *w, const double *weight);
+int  dotsocp_weights_set_planes(dotsocp_weights *w, const double *weightX, const double *weightY);
+int  dotsocp_weights_restrict(dotsocp_weights *w, int geometric);
+int  dotsocp_weights_get(const dotsocp_weights *w, int level, double *weight);
+int  dotsocp_weights_dims(const dotsocp_weights *w, int level, int *nt, int *nx, int *ny);
+int  dotsocp_weights_log10_mean(dotsocp_weights *w, int level, double *mean);
+double dotsocp_weights_launch_count(const dotsocp_weights *w);
+int  dotsocp_set_weight(dotsocp_ctx *ctx, const dotsocp_weights *w, int level);
+
 /* the reference loop on the resident state (sigma folding at entry, un-folding at exit, like :102-104, :335-336) */
 int  dotsocp_run(dotsocp_ctx *ctx, const dotsocp_level_opts *opts, dotsocp_hist *hist, dotsocp_level_result *res);
 /* benchmark primitive: begin (sigma folding + prologue), n iterations, elapsed device ms.  with_kkt_every = k > 0 makes every

@@ -107,3 +107,16 @@ def test_driver_output_recovery_matches_oracle():
     v1.alpha = rng.standard_normal(v1.alpha.size); o1.alpha = v1.alpha.copy()
     for a, b in zip(driver.recover_RhoE(v1, m1), O.recover_RhoE(o1, n1)):
         assert np.array_equal(a, b)
+
+
+def test_weight_plane_generators_match_oracle():
+    """the product's own plane generators (gene_weight_circle.m / get_weight_by_barrier.m) against the oracle's full weights"""
+    from dotsocp_b200 import driver
+    for nt, nx, ny in ((5, 9, 9), (9, 17, 33)):
+        wX, wY = driver.weight_planes_circle(nx, ny)
+        assert wX.shape == (ny, nx - 1) and wY.shape == (ny - 1, nx)
+        assert np.array_equal(driver.weight_from_planes(nt, wX, wY), O.gene_weight_circle(nt, nx, ny))
+    barrier = O.gene_barrier_of_love_heart()
+    wX, wY = driver.weight_planes_barrier(17, 17, barrier)
+    assert np.array_equal(driver.weight_from_planes(9, wX, wY), O.get_weight_by_barrier(17, 17, 9, barrier))
+    assert (wX == 1e6).any() and (wX == 1.0).any()

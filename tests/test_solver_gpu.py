@@ -529,3 +529,80 @@ def test_dot2d_acc_sgs_admm_parity(gpu, n, nt, levelN):
     for extra in ({}, {"resident": False}):
         out_g, _, ML_g, rh_g = dp.solver_dotsocp2d(rho0, rho1, nt, levelN, dict(opts, **extra), "acc-sGS-ADMM")
         _compare(out_g, rh_g, ML_g, out_o, rh_o, ML_o)
+
+
+@pytest.mark.parametrize("nt,nx,ny,levels", [(9, 17, 17, 3), (17, 9, 33, 2), (5, 5, 9, 2), (3, 3, 3, 2)])
+def test_device_weight_pyramid_matches_host_restriction(gpu, nt, nx, ny, levels):
+    """the restriction chain downSample_q.m / downSample_barrier.m, the generators' time replication and
+    mean(log10(w + 1e-10)) on the device.  Arithmetic chain: bit-identical to the host mirror (same separable order), which
+    agrees with the oracle's sparse kron products to 1e-14; geometric chain: to the rounding of log / exp."""
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import driver, solver
+    rng = np.random.default_rng(7)
+    Q = (nt - 1) * nx * ny + nt * (nx - 1) * ny + nt * nx * (ny - 1)
+    w = np.abs(rng.standard_normal(Q)) + 0.1
+    with solver.Weights(nt, nx, ny, levels) as pyr:
+        pyr.set(w).restrict(False)
+        assert np.array_equal(pyr.get(0), w)
+        host, dims = w, (nt, nx, ny)
+        for l in range(1, levels):
+            host = driver.downSample_q(*dims, host)
+            dims = tuple((d + 1) // 2 for d in dims)
+            assert pyr.dims(l) == dims
+            got = pyr.get(l)
+            assert np.array_equal(got, host), (l, np.abs(got - host).max())
+        assert np.allclose(host, O.downSample_q(*[2 * d - 1 for d in dims], pyr.get(levels - 2)), rtol=1e-13, atol=0)
+        for l in range(levels):
+            ref = float(np.mean(np.log10(pyr.get(l) + 1e-10)))
+            assert abs(pyr.log10_mean(l) - ref) <= 1e-13 * max(1.0, abs(ref))
+        pyr.restrict(True)
+        host, dims = w, (nt, nx, ny)
+        for l in range(1, levels):
+            host = driver.downSample_barrier(*dims, host)
+            dims = tuple((d + 1) // 2 for d in dims)
+            assert np.allclose(pyr.get(l), host, rtol=1e-13, atol=0)
+        wX, wY = driver.weight_planes_circle(nx, ny)
+        pyr.set_planes(wX, wY)
+        assert np.array_equal(pyr.get(0), O.gene_weight_circle(nt, nx, ny))
+        assert pyr.gpu_launches > 0
+    with pytest.raises(dp.DotsocpError):
+        solver.Weights(8, 17, 17, 2)       # an even node count cannot be halved
+    with solver.Weights(5, 5, 5, 2) as pyr:
+        with pytest.raises(dp.DotsocpError):
+            pyr.get(1)                      # nothing computed yet
+
+
+@pytest.mark.parametrize("case", ["circle", "barrier", "circle-slabs"])
+def test_wdot2d_with_device_resident_weights(gpu, case):
+    """the weighted multilevel solve with the weights taken from the device pyramid (planes in, nothing Q-sized on the host)
+    against the same solve with host weights: same iterations; KKT history and outputs agree to rounding (the log-mean of
+    `adjust` is reduced in a different order, the barrier chain uses the device's log / exp)"""
+    import dotsocp_b200 as dp
+    from dotsocp_b200 import driver
+    n, nt = 33, 17
+    barrier = None
+    if case == "barrier":
+        barrier = O.gene_barrier_of_love_heart()
+        rho0, rho1 = O.gene_exampleLoveHeart(n, n)
+        rho0, rho1 = O._normalize2d(rho0, rho1, n, n)
+        rho0, rho1, _ = O.ensure_barrier_validity(rho0, rho1, barrier)
+        planes = driver.weight_planes_barrier(n, n, barrier)
+        opts = {"tol": 1e-3, "maxit": 3000}
+    else:
+        rho0, rho1 = O.get_example2d("example1", n, n)
+        planes = driver.weight_planes_circle(n, n)
+        opts = {"tol": 1e-3, "maxit": 10000}
+    if case.endswith("slabs"):
+        opts["slabs"] = 3
+    host = dp.solver_wdotsocp2d(rho0, rho1, nt, 2, dict(opts, weight=driver.weight_from_planes(nt, *planes)), "inPALM", barrier)
+    dev = dp.solver_wdotsocp2d(rho0, rho1, nt, 2, dict(opts, weight_planes=planes), "inPALM", barrier)
+    dev2 = dp.solver_wdotsocp2d(rho0, rho1, nt, 2, dict(opts, weight=driver.weight_from_planes(nt, *planes), weights_on_device=True),
+                                "inPALM", barrier)
+    for got in (dev, dev2):
+        assert [int(v) for v in got[0].level_iters] == [int(v) for v in host[0].level_iters]
+        assert np.abs(got[2].kkt - host[2].kkt).max() < 1e-9
+        for name in ("rho", "Ex", "Ey", "q0", "bx", "by"):
+            # (barrier: weights of 1e6 multiply alpha in recover_RhoE and amplify the rounding differences; 1e-6 is _compare's bound)
+            assert np.abs(getattr(got[0], name) - getattr(host[0], name)).max() < (1e-6 if case == "barrier" else 1e-8), name
+        assert abs(got[0].w2 - host[0].w2) <= 1e-9 * abs(host[0].w2)
+    assert np.array_equal(dev[2].kkt, dev2[2].kkt)     # planes or an uploaded finest level: the same pyramid
