@@ -25,11 +25,15 @@ struct KktFused;
 struct KmMaps {
     CUtensorMap beta;
     CUtensorMap qn[3], qo[3], al[3], w[3];
+    int toc, ton;   // first cell layer / node level the views start at (time coordinate of a box = level - offset)
 };
 // q0 / bx / by views of one staggered array (q0: box 32 x TX cells; bx: TX + 1 rows from x0 - 1; by: 34 columns from y0 - 2)
 // and the 4-D view of a 10-plane array; 0 on success
-int make_stag_maps(const Geo& g, const double* base, CUtensorMap out[3]);
-int make_beta_map(const Geo& g, const double* base, CUtensorMap* out);
+// The views cover cell layers [c_lo, c_hi) and node levels [n_lo, n_hi) only -- the window a time slab backs -- so that no part
+// of a tensor lies in unmapped address space (a view of the whole array faults in slab sessions of large grids, where the
+// windows of a slab are whole 2 MB pages away from the start of the array)
+int make_stag_maps(const Geo& g, const double* base, CUtensorMap out[3], int c_lo, int c_hi, int n_lo, int n_hi);
+int make_beta_map(const Geo& g, const double* base, CUtensorMap* out, int c_lo, int c_hi);
 struct UpdateArgs {
     Geo g;
     TRange tr;

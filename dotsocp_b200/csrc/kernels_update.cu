@@ -677,13 +677,14 @@ __device__ __forceinline__ void k_mult_body(const Geo& g, const TRange& tr, int 
                 const unsigned total = nlev * (BXB + BYB) + (cellt_ ? BB + ncell * BQ + 2 * (BXB + BYB) : 0);
                 mbar_arrive_expect_tx(&mbar[stg], total);
                 unsigned long long* bar = &mbar[stg];
-                auto q0 = [&](int slot, const CUtensorMap* m) { tma_load_3d(stage_ + ST::Q0 + slot * TX * 32, m, y0_, x0_, tt, bar); };
+                // (time coordinates are relative to the first layer / level of the views: maps.toc, maps.ton)
+                auto q0 = [&](int slot, const CUtensorMap* m) { tma_load_3d(stage_ + ST::Q0 + slot * TX * 32, m, y0_, x0_, tt - maps.toc, bar); };
                 auto bxy = [&](int k, const CUtensorMap* m, int lvl) {
-                    tma_load_3d(stage_ + ST::BX + k * (TX + 1) * 32, m + 1, y0_, x0_ - 1, lvl, bar);
-                    tma_load_3d(stage_ + ST::BY + k * TX * ST::BYW, m + 2, y0_ - 2, x0_, lvl, bar);
+                    tma_load_3d(stage_ + ST::BX + k * (TX + 1) * 32, m + 1, y0_, x0_ - 1, lvl - maps.ton, bar);
+                    tma_load_3d(stage_ + ST::BY + k * TX * ST::BYW, m + 2, y0_ - 2, x0_, lvl - maps.ton, bar);
                 };
                 if (cellt_) {
-                    tma_load_4d(stage_ + ST::Q0, &maps.beta, y0_, x0_, tt, 0, bar);
+                    tma_load_4d(stage_ + ST::Q0, &maps.beta, y0_, x0_, tt - maps.toc, 0, bar);
                     q0(ST::S_QN, maps.qn); q0(ST::S_A0, maps.al); q0(ST::S_QO, maps.qo);
                     if (WEIGHTED) q0(ST::S_W0, maps.w);
                     bxy(ST::X_QN, maps.qn, tt + 1);
@@ -1227,26 +1228,26 @@ i64 mult_side_doubles(const Geo& g, bool one_d, int nlayers)
     return (i64)nlayers * (sg.sx_t + sg.sy_t);
 }
 
-int make_stag_maps(const Geo& g, const double* base, CUtensorMap out[3])
+int make_stag_maps(const Geo& g, const double* base, CUtensorMap out[3], int c_lo, int c_hi, int n_lo, int n_hi)
 {
-    if (!mult_aligned_ok(g, false) || g.nt < 2 || g.nx < 2) return -1;
-    const unsigned long long py = g.py, pyb = g.pyb;
-    const unsigned long long d0[3] = {py, (unsigned long long)g.nx, (unsigned long long)(g.nt - 1)}, s0[2] = {py * 8, (unsigned long long)g.PC * 8};
-    const unsigned long long d1[3] = {py, (unsigned long long)(g.nx - 1), (unsigned long long)g.nt}, s1[2] = {py * 8, (unsigned long long)g.PBX * 8};
-    const unsigned long long d2[3] = {pyb, (unsigned long long)g.nx, (unsigned long long)g.nt}, s2[2] = {pyb * 8, (unsigned long long)g.PBY * 8};
+    if (!mult_aligned_ok(g, false) || g.nt < 2 || g.nx < 2 || c_hi <= c_lo || n_hi <= n_lo) return -1;
+    const unsigned long long py = g.py, pyb = g.pyb, nc = (unsigned long long)(c_hi - c_lo), nn = (unsigned long long)(n_hi - n_lo);
+    const unsigned long long d0[3] = {py, (unsigned long long)g.nx, nc}, s0[2] = {py * 8, (unsigned long long)g.PC * 8};
+    const unsigned long long d1[3] = {py, (unsigned long long)(g.nx - 1), nn}, s1[2] = {py * 8, (unsigned long long)g.PBX * 8};
+    const unsigned long long d2[3] = {pyb, (unsigned long long)g.nx, nn}, s2[2] = {pyb * 8, (unsigned long long)g.PBY * 8};
     const unsigned b0[3] = {32, KM_TX, 1}, b1[3] = {32, KM_TX + 1, 1}, b2[3] = {KmStage<KM_TX, false>::BYW, KM_TX, 1};
-    if (make_tensor_map_f64(&out[0], base, 3, d0, s0, b0)) return -1;
-    if (make_tensor_map_f64(&out[1], base + g.L, 3, d1, s1, b1)) return -1;
-    if (make_tensor_map_f64(&out[2], base + g.L + g.NBX, 3, d2, s2, b2)) return -1;
+    if (make_tensor_map_f64(&out[0], base + (i64)c_lo * g.PC, 3, d0, s0, b0)) return -1;
+    if (make_tensor_map_f64(&out[1], base + g.L + (i64)n_lo * g.PBX, 3, d1, s1, b1)) return -1;
+    if (make_tensor_map_f64(&out[2], base + g.L + g.NBX + (i64)n_lo * g.PBY, 3, d2, s2, b2)) return -1;
     return 0;
 }
-int make_beta_map(const Geo& g, const double* base, CUtensorMap* out)
+int make_beta_map(const Geo& g, const double* base, CUtensorMap* out, int c_lo, int c_hi)
 {
-    if (!mult_aligned_ok(g, false) || g.nt < 2) return -1;
-    const unsigned long long d[4] = {(unsigned long long)g.py, (unsigned long long)g.nx, (unsigned long long)(g.nt - 1), 10};
+    if (!mult_aligned_ok(g, false) || g.nt < 2 || c_hi <= c_lo) return -1;
+    const unsigned long long d[4] = {(unsigned long long)g.py, (unsigned long long)g.nx, (unsigned long long)(c_hi - c_lo), 10};
     const unsigned long long s[3] = {(unsigned long long)g.py * 8, (unsigned long long)g.PC * 8, (unsigned long long)g.L * 8};
     const unsigned b[4] = {32, KM_TX, 1, 10};
-    return make_tensor_map_f64(out, base, 4, d, s, b);
+    return make_tensor_map_f64(out, base + (i64)c_lo * g.PC, 4, d, s, b);
 }
 
 int launch_mult(const UpdateArgs& a, bool weighted, bool one_d, bool update, cudaStream_t st, const KktFused* kkt)

@@ -328,9 +328,12 @@ static int make_slab(dotsocp_ctx* c, int id)
     CU(cudaMemsetAsync(s->c1, 0, g.P * sizeof(double), c->st));
     CU(cudaMalloc(&s->partial, partial_doubles(g, tr.tn1 - tr.tn0) * sizeof(double)));
     if (mult_aligned_ok(g, c->one_d)) {
-        s->maps_ok = make_beta_map(g, s->beta[0], &s->tm_beta[0]) == 0 && make_beta_map(g, s->beta[1], &s->tm_beta[1]) == 0 &&
-                     make_stag_maps(g, s->q[0], s->tm_q[0]) == 0 && make_stag_maps(g, s->q[1], s->tm_q[1]) == 0 &&
-                     make_stag_maps(g, s->alpha, s->tm_alpha) == 0 && (!c->weighted || make_stag_maps(g, s->weight, s->tm_w) == 0);
+        // views of the slab's own window (backed cell layers / node levels), not of the whole index space
+        const int cl = s->lo_c, ch = s->hi_c, nl = s->lo_n, nh = s->hi_n;
+        s->maps_ok = make_beta_map(g, s->beta[0], &s->tm_beta[0], cl, ch) == 0 && make_beta_map(g, s->beta[1], &s->tm_beta[1], cl, ch) == 0 &&
+                     make_stag_maps(g, s->q[0], s->tm_q[0], cl, ch, nl, nh) == 0 && make_stag_maps(g, s->q[1], s->tm_q[1], cl, ch, nl, nh) == 0 &&
+                     make_stag_maps(g, s->alpha, s->tm_alpha, cl, ch, nl, nh) == 0 &&
+                     (!c->weighted || make_stag_maps(g, s->weight, s->tm_w, cl, ch, nl, nh) == 0);
         cudaGetLastError();
     }
     {
@@ -1438,6 +1441,8 @@ struct Loop {
                 s->km.al[i] = s->tm_alpha[i];
                 s->km.w[i] = c->weighted ? s->tm_w[i] : s->tm_alpha[i];
             }
+            s->km.toc = s->lo_c;
+            s->km.ton = s->lo_n;
             a.maps = &s->km;
         }
         return a;

@@ -600,9 +600,10 @@ def test_wdot2d_with_device_resident_weights(gpu, case):
                                 "inPALM", barrier)
     for got in (dev, dev2):
         assert [int(v) for v in got[0].level_iters] == [int(v) for v in host[0].level_iters]
-        assert np.abs(got[2].kkt - host[2].kkt).max() < 1e-9
+        loose = case == "barrier"
+        assert np.abs(got[2].kkt - host[2].kkt).max() < (1e-8 if loose else 1e-9)
         for name in ("rho", "Ex", "Ey", "q0", "bx", "by"):
             # (barrier: weights of 1e6 multiply alpha in recover_RhoE and amplify the rounding differences; 1e-6 is _compare's bound)
             assert np.abs(getattr(got[0], name) - getattr(host[0], name)).max() < (1e-6 if case == "barrier" else 1e-8), name
-        assert abs(got[0].w2 - host[0].w2) <= 1e-9 * abs(host[0].w2)
+        assert abs(got[0].w2 - host[0].w2) <= (1e-6 if loose else 1e-9) * abs(host[0].w2)
     assert np.array_equal(dev[2].kkt, dev2[2].kkt)     # planes or an uploaded finest level: the same pyramid
