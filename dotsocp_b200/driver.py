@@ -47,21 +47,47 @@ def initialize(rho0, rho1, nt):
     c[n - nx * ny:] = r1 / ht
     model.c = c
     model.c_first, model.c_last = c[: nx * ny], c[n - nx * ny:]     # views: model.c is zero in between (initialize.m:41-44)
-    xs = np.arange(nx) * hx
-    if dim == 2:
-        ys = np.arange(ny) * hy
-        phi2 = 0.5 * (xs[:, None] ** 2 + ys[None, :] ** 2)       # C-order (nx, ny)
-        phi = np.tile(phi2.ravel(), nt)
-        ncol = 10
-    else:
-        phi = np.tile(0.5 * xs ** 2, nt)
-        ncol = 6
+    phi = np.tile(initial_phi_plane(nx, ny), nt)
+    ncol = 10 if dim == 2 else 6
     L = (nt - 1) * nx * ny
     Q = L + nt * (nx - 1) * ny + nt * nx * (ny - 1)
     qInd = SimpleNamespace(bx=L + 1, by=L + nt * (nx - 1) * ny + 1)
     var = SimpleNamespace(qInd=qInd, phi=phi, z=np.zeros((L, ncol), order="F"), beta=np.zeros((L, ncol), order="F"),
                           q=np.zeros(Q), alpha=np.zeros(Q))
     return var, model
+
+
+def initial_phi_plane(nx, ny):
+    """one time level of the initial phi = (x^2 + y^2) / 2 (initialize.m:46-52), C order (nx, ny); 1-D: x^2 / 2"""
+    xs = np.arange(nx) * (1 / (nx - 1))
+    if ny > 1:
+        ys = np.arange(ny) * (1 / (ny - 1))
+        return (0.5 * (xs[:, None] ** 2 + ys[None, :] ** 2)).ravel()
+    return 0.5 * xs ** 2
+
+
+def initial_state_local(model, dScale, tc0, tc1, tn0, tn1, with_z=True):
+    """The reference's initial state (initialize.m:46-64: phi = |x|^2/2 on every level, everything else zero) after
+    InitialScaling (solver_dotsocp2d.m:338-342; dScale = None: unscaled), for node levels [tn0, tn1) / cell layers [tc0, tc1)
+    only -- a time slab's part of split_state(initialize(...)) without the full-grid arrays (the zeros stay zeros under the
+    scaling).  model.c_first / c_last are the already scaled planes (level_model + scaling_scalars).
+    Returns (phi, q, z or None, alpha, beta, c)."""
+    nt, nx, ny = model.nt, model.nx, model.ny
+    P = nx * ny
+    plane = initial_phi_plane(nx, ny)
+    if dScale is not None:
+        plane = (1 / dScale) * plane
+    phi = np.tile(plane, tn1 - tn0)
+    Lloc = (tc1 - tc0) * P
+    Qloc = Lloc + (tn1 - tn0) * ((nx - 1) * ny + nx * (ny - 1))
+    ncol = 10 if model.dim == 2 else 6
+    c = np.zeros((tn1 - tn0) * P)
+    if tn0 == 0:
+        c[:P] = np.ravel(model.c_first)
+    if tn1 == nt:
+        c[c.size - P:] = np.ravel(model.c_last)
+    z = np.zeros((Lloc, ncol), order="F") if with_z else None
+    return phi, np.zeros(Qloc), z, np.zeros(Qloc), np.zeros((Lloc, ncol), order="F"), c
 
 
 def normL2(x, h):
@@ -548,17 +574,20 @@ def _multilevel(variant, rho0, rho1, nt, levelN, opts, method, barrier=None):
     timeML = [None] * (levelN + 1)
     lastLevelKKT = None
     clk = time.perf_counter()
-    var, model = initialize(rho0s[0], rho1s[0], nts[0])
+    # state resident in HBM between levels (device-side transitions) unless opts["resident"] = False asks for the
+    # reference-shaped download -> host transfer -> upload loop; both give the same bits
+    resident = bool(optsML.pop("resident", True))
+    opts.pop("resident", None)
+    if resident:      # the coarsest state is built slab by slab (initial_state_local): no full-grid host array
+        var, model = level_model(rho0s[0], rho1s[0], nts[0])
+    else:
+        var, model = initialize(rho0s[0], rho1s[0], nts[0])
     if variant == "wdot2d":
         model.weight = weights[0]
     ML = SimpleNamespace(kkt=None, time=None, iter=None, pdGap=None, len=0)
     runHist = None
     level_iters, launches = [], 0.0
     sigma = optsML["sigma"]
-    # state resident in HBM between levels (device-side transitions) unless opts["resident"] = False asks for the
-    # reference-shaped download -> host transfer -> upload loop; both give the same bits
-    resident = bool(optsML.pop("resident", True))
-    opts.pop("resident", None)
     if resident:
         try:
             return _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model, rho0s, rho1s, nts, tols, weights,
@@ -626,23 +655,23 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
         rank, world, ident, distributed = int(slabs["rank"]), int(slabs["world"]), slabs["nccl_id"], True
     else:
         rank, world, ident, distributed = 0, int(slabs or 1), None, False
-    InitialScaling(var, model, scalingYes, None, variant)          # coarsest level: host arrays, as the reference
+    # coarsest level: the scalar half of InitialScaling on the host, the arrays (phi = |x|^2/2, zeros) slab by slab
+    cS0, dS0, D0, E0, E20 = scaling_scalars(model.nt * model.nx * model.ny, model, scalingYes, None, None, variant)
+    var.cScale, var.dScale, var.D, var.E, var.E2 = cS0, dS0, D0, E0, E20
     sess = S.Session(variant, model.nt, model.nx, model.ny, rank=rank, world=world, nccl_id=ident)
     sgs_last = method if method in ("sGS-inPALM", "acc-sGS-ADMM") else None   # coarse levels: inPALM (tau 1.9, maxit 3000), :210-223
     mname = "inPALM" if method in ("inPALM", "ALG2", "sGS-inPALM", "acc-sGS-ADMM") else method
     first_is_inpalm = mname == "inPALM" and not (sgs_last == "acc-sGS-ADMM" and levelN == 1)   # acc loops read the incoming z
     z_dead = first_is_inpalm and int(optsML["maxit"]) >= 1
-    state0 = (var.phi, var.q, None if z_dead else var.z, var.alpha, var.beta, model.c, model.weight if weighted else None)
-    if distributed:
-        w0 = state0[6]
-        state0 = SL.split_state(rank, world, model.nt, model.nx, model.ny, *state0[:6],
-                                None if isinstance(w0, S.DeviceWeight) else w0, cuts=sess.cuts)
-        if isinstance(w0, S.DeviceWeight):       # the session takes its slab's part of the device level itself
-            state0 = state0[:6] + (w0,)
+    tr0 = SL.partition(model.nt, world, sess.cuts)[rank] if distributed else (0, model.nt - 1, 0, model.nt)
+    w0 = model.weight if weighted else None
+    if distributed and w0 is not None and not isinstance(w0, S.DeviceWeight):   # (a device level is taken slab by slab by the session)
+        w0 = SL.split_state(rank, world, model.nt, model.nx, model.ny, None, None, None, None, None, None, w0, cuts=sess.cuts)[6]
+    state0 = initial_state_local(model, dS0 if scalingYes else None, *tr0, with_z=not z_dead) + (w0,)
     sess.upload(*state0)
     del state0
-    var.phi = var.q = var.z = var.alpha = var.beta = None
     level_iters, launches, runHist, sigma = [], 0.0, None, optsML["sigma"]
+    outbuf = None
     try:
         for level in range(levelN):
             o2 = dict(optsML)
@@ -655,6 +684,8 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
                     o2["maxit"] = 3000
                     o2["tau"] = 1.9
             lo = S.make_level_opts(variant, lname, var, o2, model)
+            if level == levelN - 1:     # the output arrays are allocated and their pages faulted in while the last level runs
+                outbuf = S.OutputBuffers(sess)
             hb, res = sess.run(lo)
             runHist, sigma = S._finish(var, lo.method, hb, res)      # var.cScale/dScale/D/E after in-loop rescaling, var.time
             timeML[level] = var.time
@@ -688,7 +719,7 @@ def _multilevel_resident(variant, method, levelN, optsML, scalingYes, var, model
             var = SimpleNamespace(qInd=var_f.qInd, cScale=cS, dScale=dS, D=D, E=E, E2=E2)
             model = model_f
         # ---- output (solver_dotsocp2d.m:268-287) on the device
-        fields, sumRho, sumNeg, w2 = sess.recover(var.cScale * var.D, var.dScale / var.D, model.rho0, model.rho1)
+        fields, sumRho, sumNeg, w2 = sess.recover(var.cScale * var.D, var.dScale / var.D, model.rho0, model.rho1, out=outbuf.get())
         if return_state:
             var.phi, var.q, var.z, var.alpha, var.beta = sess.download()
             recoverOrgVar(var, inplace=True)

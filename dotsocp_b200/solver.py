@@ -170,6 +170,40 @@ class DeviceWeight:
         return self.pyramid.log10_mean(self.level)
 
 
+class OutputBuffers:
+    """Host arrays for Session.recover, allocated and touched page by page on background threads while the device is busy
+    with the last level: a fresh 26 GB of output at 1024x1024x512 otherwise takes its first-touch page faults inside the
+    device-to-host copies (1.6 s instead of 0.7 s).  get() joins the threads and returns the dict of arrays."""
+
+    def __init__(self, session, fields=("rho", "Ex", "Ey", "q0", "bx", "by"), threads=4):
+        import threading
+        self._shapes = session.output_shapes(fields)
+        self._out = {}
+        self._thread = threading.Thread(target=self._fill, args=(threads,), daemon=True)
+        self._thread.start()
+
+    def _fill(self, threads):
+        from concurrent.futures import ThreadPoolExecutor
+        jobs = []
+        for name, shp in self._shapes.items():
+            a = np.empty(shp)
+            self._out[name] = a
+            v = a.reshape(-1)
+            step = max(1 << 20, -(-v.size // 16))
+            jobs += [(v, i, min(i + step, v.size)) for i in range(0, v.size, step)]
+        touch = lambda job: job[0][job[1]:job[2]].fill(0.0)        # numpy releases the GIL inside fill
+        if sum(j - i for _, i, j in jobs) < (1 << 22):              # small outputs: not worth a pool
+            for job in jobs:
+                touch(job)
+        else:
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(touch, jobs))
+
+    def get(self):
+        self._thread.join()
+        return self._out
+
+
 class Session:
     """Device-resident state of one level (dotsocp_create / _upload / _run / _download / _destroy)."""
 
@@ -285,7 +319,14 @@ class Session:
         ps = ProlongScal(**{k: float(v) for k, v in scal.items()})
         check(lib().dotsocp_prolong(coarse._h, self._h, C.byref(ps), ptr(first), ptr(last), ptr(w)))
 
-    def recover(self, alpha_recover, q_recover, rho0, rho1, fields=("rho", "Ex", "Ey", "q0", "bx", "by"), stats=True):
+    def output_shapes(self, fields=("rho", "Ex", "Ey", "q0", "bx", "by")):
+        """shapes of the recovered fields (this slab's levels in a distributed session)"""
+        shp = (self.nx, self.ny) if self.variant != "dot1d" else (self.nx,)
+        return {name: ((self.nt_local if name in ("rho", "Ex", "Ey") else self.nc_local),) + shp
+                for name in ("rho", "Ex", "Ey", "q0", "bx", "by")
+                if name in fields and not (self.variant == "dot1d" and name in ("Ey", "by"))}
+
+    def recover(self, alpha_recover, q_recover, rho0, rho1, fields=("rho", "Ex", "Ey", "q0", "bx", "by"), stats=True, out=None):
         """Output recovery on the device (dotsocp_recover) from the state of a finished run: recoverOrgVar + recover_RhoE +
         recover_q + check_massConservation + transport cost.  rho0 / rho1: MATLAB-shaped (ny, nx) densities [1-D: (nx,)].
         Returns (dict of C-order arrays (levels, nx, ny) -- this slab's levels in a distributed session --, sumRho,
@@ -294,11 +335,13 @@ class Session:
         r1 = np.ascontiguousarray(np.asarray(rho1, dtype=np.float64).ravel(order="F"))
         P = self.nx * self.ny
         assert r0.size == P and r1.size == P
-        shp = (self.nx, self.ny) if self.variant != "dot1d" else (self.nx,)
-        out = {}
-        for name in ("rho", "Ex", "Ey", "q0", "bx", "by"):
-            if name in fields and not (self.variant == "dot1d" and name in ("Ey", "by")):
-                out[name] = np.empty(((self.nt_local if name in ("rho", "Ex", "Ey") else self.nc_local),) + shp)
+        shapes = self.output_shapes(fields)
+        if out is None:
+            out = {name: np.empty(shp) for name, shp in shapes.items()}
+        else:       # caller-provided arrays (OutputBuffers): filled in place
+            assert set(out) == set(shapes)
+            for name, shp in shapes.items():
+                assert out[name].shape == shp and out[name].dtype == np.float64 and out[name].flags.c_contiguous, name
         sr = np.empty(self.nt) if stats else None
         sn = np.empty(self.nt) if stats else None
         w2 = C.c_double(float("nan"))

@@ -95,6 +95,19 @@ def main():
         for a, b, name in zip(state, state1, ("phi", "q", "z", "alpha", "beta")):
             assert np.abs(a - b).max() <= 1e-11 * max(1.0, np.abs(a).max()), name
         print(f"dist parity ok: fused transposes world={world}", flush=True)
+    # weighted multilevel solve on slabs with the level weights taken from the device pyramid: every rank builds
+    # the pyramid on its own GPU from the two generator planes, its sessions take their slab's part device to device
+    n, nt = 33, 17
+    rho0, rho1 = O.get_example2d("example1", n, n)
+    planes = driver.weight_planes_circle(n, n)
+    o3 = {"tol": 1e-3, "maxit": 10000, "slabs": {"rank": rank, "world": world, "nccl_id": slab.REUSE_COMM}}
+    dev = dp.solver_wdotsocp2d(rho0, rho1, nt, 2, dict(o3, weight_planes=planes), "inPALM")
+    host = dp.solver_wdotsocp2d(rho0, rho1, nt, 2, dict(o3, weight=driver.weight_from_planes(nt, *planes)), "inPALM")
+    assert [int(v) for v in dev[0].level_iters] == [int(v) for v in host[0].level_iters]
+    assert np.abs(dev[2].kkt - host[2].kkt).max() < 1e-9
+    assert dev[0].slab == host[0].slab and np.abs(dev[0].rho - host[0].rho).max() < 1e-8
+    if rank == 0:
+        print(f"dist parity ok: device weights world={world} iters={[int(v) for v in dev[0].level_iters]}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -120,3 +120,37 @@ def test_weight_plane_generators_match_oracle():
     wX, wY = driver.weight_planes_barrier(17, 17, barrier)
     assert np.array_equal(driver.weight_from_planes(9, wX, wY), O.get_weight_by_barrier(17, 17, 9, barrier))
     assert (wX == 1e6).any() and (wX == 1.0).any()
+
+
+def test_slab_local_initial_state_equals_split_of_the_full_initial_state():
+    """the resident multilevel driver builds the coarsest state slab by slab (driver.initial_state_local): bit-identical to
+    split_state(initialize + InitialScaling), for 2-D and 1-D, scaled and unscaled, 1 and 3 slabs"""
+    from dotsocp_b200 import driver
+    from dotsocp_b200 import slab as SL
+    for dim in (2, 1):
+        r0, r1 = O.get_example2d("example1", 9, 17) if dim == 2 else O.get_example1d("gaussian", 33)
+        nt, variant = 9, ("dot2d" if dim == 2 else "dot1d")
+        for scalingYes in (True, False):
+            var, model = driver.initialize(r0, r1, nt)
+            driver.InitialScaling(var, model, scalingYes, None, variant)
+            _, m2 = driver.level_model(r0, r1, nt)
+            cS, dS, D, E, _ = driver.scaling_scalars(m2.nt * m2.nx * m2.ny, m2, scalingYes, None, None, variant)
+            assert (cS, dS, D, E) == (var.cScale, var.dScale, var.D, var.E)
+            assert m2.normc == model.normc and m2.normd == model.normd and m2.grad == model.grad
+            for world in (1, 3):
+                for rank in range(world):
+                    tr = SL.partition(nt, world)[rank]
+                    ref = SL.split_state(rank, world, model.nt, model.nx, model.ny, var.phi, var.q, var.z, var.alpha, var.beta, model.c)
+                    got = driver.initial_state_local(m2, dS if scalingYes else None, *tr)
+                    for a, b in zip(ref[:6], got):
+                        assert a.shape == b.shape and np.array_equal(a, b)
+            assert driver.initial_state_local(m2, None, 0, nt - 1, 0, nt, with_z=False)[2] is None
+
+
+def test_output_buffers_prefault_in_the_background():
+    from types import SimpleNamespace
+    from dotsocp_b200 import solver
+    fake = SimpleNamespace(output_shapes=lambda fields: {"rho": (5, 9, 9), "q0": (4, 9, 9), "big": (3, 1200, 1200)})
+    out = solver.OutputBuffers(fake).get()
+    assert set(out) == {"rho", "q0", "big"} and out["big"].shape == (3, 1200, 1200) and out["rho"].flags.c_contiguous
+    assert not out["big"].any()

@@ -25,7 +25,7 @@ def test_nccl_time_slab_parity(gpu, env):
                           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_parity.py")],
                          capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
     assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-4000:]
-    assert out.stdout.count("dist parity ok") == 3
+    assert out.stdout.count("dist parity ok") == 4
 
 
 def test_nccl_parity_at_baseline_grids(gpu):
