@@ -26,6 +26,7 @@ def refined(cls, coarse):
     log.append(("refined", time.perf_counter() - t0))
     return r
 S.Session.refined = classmethod(refined)
+wrap(S.OutputBuffers, "get")
 r0, r1 = bench.densities_matlab(n, n)
 for rep in range(2):
     log.clear()
