@@ -469,12 +469,7 @@ def main():
         ph["destroy"] = time.perf_counter() - t1
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        # the e2e leg made 116 GB of host arrays resident (and left the state after K iterations in them): hand them back to the
-        # OS and start the later legs from fresh, lazily backed arrays of the reference's initial state -- the multilevel solves
-        # below need the host memory for their outputs (7.8 s instead of 5.8-6.9 s for the 1024x1024x512 solve under pressure)
-        del out_state, e2e_out
-        var.phi = var.q = var.z = var.alpha = var.beta = model.c = None
-        var, model = make_problem(nt, nx, ny, rank, world)
+        del out_state
         h2d = (2 * N + 2 * Q + 10 * L) * 8.0
         d2h = (N + 2 * Q + 20 * L) * 8.0
         e2e = {"value": K_ / dt, "unit": "iterations/s", "h2d_bytes_per_step": h2d / K_, "d2h_bytes_per_step": d2h / K_,
