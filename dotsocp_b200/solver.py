@@ -183,6 +183,12 @@ class OutputBuffers:
         self._thread.start()
 
     def _fill(self, threads):
+        try:
+            self._fill_impl(threads)
+        except Exception:          # (e.g. MemoryError) recover() then allocates its own arrays and reports the real problem
+            self._out = None
+
+    def _fill_impl(self, threads):
         from concurrent.futures import ThreadPoolExecutor
         jobs = []
         for name, shp in self._shapes.items():
