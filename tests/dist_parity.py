@@ -97,6 +97,14 @@ def main():
         print(f"dist parity ok: fused transposes world={world}", flush=True)
     # weighted multilevel solve on slabs with the level weights taken from the device pyramid: every rank builds
     # the pyramid on its own GPU from the two generator planes, its sessions take their slab's part device to device
+    if any(os.environ.get(k) for k in ("DOTSOCP_TSOLVE", "DOTSOCP_XCHG", "DOTSOCP_NO_IPC", "DOTSOCP_TCHUNKS", "DOTSOCP_TPUSH")):
+        # (the exchange variants of test_multi_gpu.py are about the level solver above; the multilevel driver on slabs is
+        # exercised with the default exchange, here and in dist_parity_big.py)
+        if rank == 0:
+            print(f"dist parity ok: device weights world={world} not run with a non-default exchange", flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     n, nt = 33, 17
     rho0, rho1 = O.get_example2d("example1", n, n)
     planes = driver.weight_planes_circle(n, n)
